@@ -1,0 +1,319 @@
+// c_api.cpp -- the extern "C" boundary declared in include/spear_particles.h.
+// Thin: argument checks, exception -> status translation, read-back copies.
+
+#include "particle_system.h"
+
+#include <string.h>
+
+#include <new>
+
+using namespace spr;
+
+struct SprContext { Context ctx; explicit SprContext(const SprContextDesc &d) : ctx(d) { } };
+struct SprSystem { ParticleSystem sys; SprSystem(Context *c, const SprSystemsDesc &d) : sys(c, d) { } };
+
+static thread_local std::string g_lastError;
+
+template <typename F>
+static int guarded(F &&f)
+{
+	try { f(); return SPR_OK; }
+	catch (const CudaError &e) { g_lastError = e.what(); return SPR_ERR_CUDA; }
+	catch (const std::bad_alloc &) { g_lastError = "out of host memory"; return SPR_ERR_OUT_OF_MEMORY; }
+	catch (const std::exception &e) { g_lastError = e.what(); return SPR_ERR_INVALID_ARGUMENT; }
+}
+
+#define REQUIRE(cond) do { if (!(cond)) { g_lastError = "invalid argument: " #cond; return SPR_ERR_INVALID_ARGUMENT; } } while (0)
+
+static bool validEffect(SprSystem *s, uint32_t id) { return s && id < s->sys.effects.size() && s->sys.effects[id].inUse; }
+
+extern "C" {
+
+SPR_API void sprComponentDefaults(SprParticleSystemComponent *c)
+{
+	memset(c, 0, sizeof(*c));
+	c->frameCount[0] = c->frameCount[1] = 1;
+	c->timeStep = 0.1f;
+	c->updateRadius = 10.0f;
+	c->cullPadding = 1.5f;
+	c->spawnTime = 0.2f;
+	c->emitterOnTime = -1.0f;
+	SprRandomVec3 *rv[2] = { &c->emitPosition, &c->emitVelocity };
+	for (int i = 0; i < 2; i++) {
+		rv[i]->sphere.maxTheta = 360.0f;
+		rv[i]->sphere.maxPhi = 180.0f;
+		rv[i]->sphere.scale.x = rv[i]->sphere.scale.y = rv[i]->sphere.scale.z = 1.0f;
+	}
+	c->size = 0.5f;
+	c->lifeTime = 1.0f;
+	c->gradient.defaultColor.x = c->gradient.defaultColor.y = c->gradient.defaultColor.z = 1.0f;
+}
+
+SPR_API const char *sprGetLastError(void) { return g_lastError.c_str(); }
+
+SPR_API int sprContextCreate(const SprContextDesc *desc, SprContext **out)
+{
+	REQUIRE(desc && out);
+	*out = nullptr;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { g_lastError = "no CUDA device available (this library has no CPU fallback)"; return SPR_ERR_NO_DEVICE; }
+	REQUIRE(desc->device >= 0 && desc->device < count);
+	return guarded([&] { *out = new SprContext(*desc); });
+}
+
+SPR_API int sprContextDestroy(SprContext *ctx) { REQUIRE(ctx); return guarded([&] { delete ctx; }); }
+SPR_API int sprContextSynchronize(SprContext *ctx) { REQUIRE(ctx); return guarded([&] { ctx->ctx.sync(); }); }
+SPR_API void *sprContextStream(SprContext *ctx) { return ctx ? (void*)ctx->ctx.stream : nullptr; }
+SPR_API uint64_t sprContextLaunchCount(SprContext *ctx) { return ctx ? ctx->ctx.launchCount : 0; }
+
+SPR_API int sprSystemCreate(SprContext *ctx, const SprSystemsDesc *desc, SprSystem **out)
+{
+	REQUIRE(ctx && desc && out);
+	return guarded([&] { *out = new SprSystem(&ctx->ctx, *desc); });
+}
+
+SPR_API int sprSystemDestroy(SprSystem *sys) { REQUIRE(sys); return guarded([&] { delete sys; }); }
+
+SPR_API int sprReserveEffectType(SprSystem *sys, const SprParticleSystemComponent *c, uint32_t *outTypeId)
+{
+	REQUIRE(sys && c);
+	return guarded([&] { uint32_t t = sys->sys.reserveEffectType(c); if (outTypeId) *outTypeId = t; });
+}
+
+SPR_API int sprReleaseEffectType(SprSystem *sys, const SprParticleSystemComponent *c)
+{
+	REQUIRE(sys && c);
+	return guarded([&] { sys->sys.releaseEffectType(c); });
+}
+
+SPR_API int sprAddEffect(SprSystem *sys, uint32_t entityId, uint8_t componentIndex,
+	const SprParticleSystemComponent *c, const SprTransform *transform, uint32_t *outEffectId)
+{
+	REQUIRE(sys && c && transform);
+	return guarded([&] { uint32_t e = sys->sys.addEffect(entityId, componentIndex, c, *transform); if (outEffectId) *outEffectId = e; });
+}
+
+SPR_API int sprUpdateTransform(SprSystem *sys, uint32_t effectId, const SprTransformUpdate *update)
+{
+	REQUIRE(validEffect(sys, effectId) && update);
+	return guarded([&] { sys->sys.updateTransform(effectId, *update); });
+}
+
+SPR_API int sprPrepareForRemove(SprSystem *sys, uint32_t effectId, const SprFrameArgs *args, int *outCanRemove)
+{
+	REQUIRE(validEffect(sys, effectId) && args);
+	return guarded([&] { bool r = sys->sys.prepareForRemove(effectId, *args); if (outCanRemove) *outCanRemove = r ? 1 : 0; });
+}
+
+SPR_API int sprRemoveEffect(SprSystem *sys, uint32_t effectId)
+{
+	REQUIRE(validEffect(sys, effectId));
+	return guarded([&] { sys->sys.remove(effectId); });
+}
+
+SPR_API int sprUpdateParticles(SprSystem *sys, const uint32_t *activeIds, uint32_t numActive, const SprFrameArgs *args)
+{
+	REQUIRE(sys && args && (activeIds || numActive == 0));
+	for (uint32_t i = 0; i < numActive; i++) REQUIRE(validEffect(sys, activeIds[i]));
+	return guarded([&] { sys->sys.updateParticles(activeIds, numActive, *args); });
+}
+
+SPR_API int sprUpdateParticlesBatch(SprContext *ctx, SprSystem *const *systems, uint32_t numSystems,
+	const uint32_t *const *activeIds, const uint32_t *numActive, const SprFrameArgs *args, size_t argsStride)
+{
+	REQUIRE(ctx && systems && activeIds && numActive && args);
+	return guarded([&] {
+		std::vector<UpdateRequest> reqs(numSystems);
+		for (uint32_t i = 0; i < numSystems; i++) {
+			if (!systems[i] || systems[i]->sys.ctx != &ctx->ctx) throw std::runtime_error("system does not belong to this context");
+			reqs[i].system = &systems[i]->sys;
+			reqs[i].activeIds = activeIds[i];
+			reqs[i].numActive = numActive[i];
+			reqs[i].args = (const SprFrameArgs*)((const char*)args + argsStride * i);
+		}
+		ctx->ctx.update(reqs.data(), numSystems);
+	});
+}
+
+SPR_API int sprRenderMain(SprSystem *sys, const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs *args, SprRenderOutput *out)
+{
+	REQUIRE(sys && args && out && (visibleIds || numVisible == 0));
+	for (uint32_t i = 0; i < numVisible; i++) REQUIRE(validEffect(sys, visibleIds[i]));
+	return guarded([&] { sys->sys.renderMain(visibleIds, numVisible, *args, *out); });
+}
+
+// ---- parity read-backs
+
+SPR_API int sprGetEffectInfo(SprSystem *sys, uint32_t effectId, SprEffectInfo *out)
+{
+	REQUIRE(validEffect(sys, effectId) && out);
+	return guarded([&] {
+		const HostEffect &E = sys->sys.effects[effectId];
+		RenderGather g;
+		sys->sys.ctx->gatherEffects(&E.global, 1, &g);
+		memset(out, 0, sizeof(*out));
+		out->typeId = E.typeId;
+		out->slotCount = g.slotCount;
+		out->aliveCount = g.aliveCount;
+		out->freeCount = g.freeCount;
+		out->timeStep = E.timeStep;
+		out->timeDelta = E.timeDelta;
+		out->spawnTimer = g.spawnTimer;
+		out->emitOnTimer = g.emitOnTimer;
+		out->stopEmit = (g.stopEmit || E.hostStopEmit) ? 1 : 0;
+		out->firstEmit = (uint8_t)g.firstEmit;
+		out->instantDelete = E.instantDelete ? 1 : 0;
+		out->gpuBounds = boundsFromGather(g, sys->sys.types[E.typeId], E);
+		out->lastUpdateTime = E.lastUpdateTime;
+		out->simSteps = E.simSteps;
+	});
+}
+
+static int readRange(SprSystem *sys, uint32_t effectId, int what, void *out, uint32_t capacity, uint32_t *outCount)
+{
+	return guarded([&] {
+		Context *ctx = sys->sys.ctx;
+		const HostEffect &E = sys->sys.effects[effectId];
+		RenderGather g;
+		ctx->gatherEffects(&E.global, 1, &g);
+		const EffectParams &P = ctx->hParams[E.global];
+		uint32_t n = 0; size_t elem = 0; const void *src = nullptr;
+		switch (what) {
+		case 0: n = g.freeCount; elem = 4; src = ctx->dFreeStack + P.slotBase; break;
+		case 1: n = g.aliveCount * 4; elem = 32; src = ctx->dVertices + 8ull * P.slotBase; break;
+		case 2: n = g.slotCount; elem = 32; src = ctx->dSlotState + 2ull * P.slotBase; break;
+		}
+		if (outCount) *outCount = n;
+		uint32_t m = n < capacity ? n : capacity;
+		if (m && out) {
+			SPR_CUDA(cudaMemcpyAsync(out, src, (size_t)m * elem, cudaMemcpyDeviceToHost, ctx->stream));
+			SPR_CUDA(cudaStreamSynchronize(ctx->stream));
+		}
+	});
+}
+
+SPR_API int sprReadFreeIndices(SprSystem *sys, uint32_t effectId, uint32_t *out, uint32_t capacity, uint32_t *outCount)
+{
+	REQUIRE(validEffect(sys, effectId));
+	return readRange(sys, effectId, 0, out, capacity, outCount);
+}
+
+SPR_API int sprReadVertexStream(SprSystem *sys, uint32_t effectId, SprGpuParticle *out, uint32_t capacityVertices, uint32_t *outCount)
+{
+	REQUIRE(validEffect(sys, effectId));
+	return readRange(sys, effectId, 1, out, capacityVertices, outCount);
+}
+
+SPR_API int sprReadSlots(SprSystem *sys, uint32_t effectId, SprGpuParticle *out, uint32_t capacitySlots, uint32_t *outCount)
+{
+	REQUIRE(validEffect(sys, effectId));
+	return readRange(sys, effectId, 2, out, capacitySlots, outCount);
+}
+
+SPR_API int sprReadStreamSlots(SprSystem *sys, uint32_t effectId, uint32_t *out, uint32_t capacity, uint32_t *outCount)
+{
+	REQUIRE(validEffect(sys, effectId));
+	return guarded([&] {
+		Context *ctx = sys->sys.ctx;
+		const HostEffect &E = sys->sys.effects[effectId];
+		RenderGather g;
+		ctx->gatherEffects(&E.global, 1, &g);
+		const EffectParams &P = ctx->hParams[E.global];
+		if (outCount) *outCount = g.aliveCount;
+		uint32_t m = g.aliveCount < capacity ? g.aliveCount : capacity;
+		if (!m || !out) return;
+		if (ctx->flags & SPR_CTX_SORT_PARTICLES) {
+			SPR_CUDA(cudaMemcpyAsync(out, ctx->dVals[0] + P.slotBase, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			SPR_CUDA(cudaStreamSynchronize(ctx->stream));
+		} else {
+			// stream order is ascending slot order over the live slots (ParticleSystem.cpp:611-665)
+			std::vector<SprGpuParticle> slots(g.slotCount);
+			if (g.slotCount) {
+				SPR_CUDA(cudaMemcpyAsync(slots.data(), ctx->dSlotState + 2ull * P.slotBase, (size_t)g.slotCount * 32, cudaMemcpyDeviceToHost, ctx->stream));
+				SPR_CUDA(cudaStreamSynchronize(ctx->stream));
+			}
+			uint32_t k = 0;
+			for (uint32_t i = 0; i < g.slotCount && k < m; i++) if (slots[i].life < kHugeLifeCmp) out[k++] = i;
+		}
+	});
+}
+
+SPR_API int sprGetRngState(SprSystem *sys, uint64_t outStateInc[2])
+{
+	REQUIRE(sys && outStateInc);
+	return guarded([&] {
+		Context *ctx = sys->sys.ctx;
+		ctx->flushUploads();
+		SystemDev sd;
+		SPR_CUDA(cudaMemcpyAsync(&sd, ctx->dSystems.ptr + sys->sys.systemIdx, sizeof(sd), cudaMemcpyDeviceToHost, ctx->stream));
+		SPR_CUDA(cudaStreamSynchronize(ctx->stream));
+		outStateInc[0] = sd.rngState; outStateInc[1] = sd.rngInc;
+	});
+}
+
+SPR_API int sprGetEffectTypeLut(SprSystem *sys, uint32_t typeId, uint8_t out[SPR_SPLINE_LUT_BYTES])
+{
+	REQUIRE(sys && out && typeId < sys->sys.types.size() && sys->sys.types[typeId].comp);
+	memcpy(out, sys->sys.types[typeId].lut, SPR_SPLINE_LUT_BYTES);
+	return SPR_OK;
+}
+
+SPR_API int sprGetEffectTypeUbo(SprSystem *sys, uint32_t typeId, SprVertexTypeUbo *out)
+{
+	REQUIRE(sys && out && typeId < sys->sys.types.size() && sys->sys.types[typeId].comp);
+	*out = sys->sys.types[typeId].typeUbo;
+	return SPR_OK;
+}
+
+SPR_API int sprGetEffectDeviceView(SprSystem *sys, uint32_t effectId, SprEffectDeviceView *out)
+{
+	REQUIRE(validEffect(sys, effectId) && out);
+	Context *ctx = sys->sys.ctx;
+	const HostEffect &E = sys->sys.effects[effectId];
+	const EffectParams &P = ctx->hParams[E.global];
+	out->vertices = (const SprGpuParticle*)(ctx->dVertices + 8ull * P.slotBase);
+	out->slots = (const SprGpuParticle*)(ctx->dSlotState + 2ull * P.slotBase);
+	out->aliveCount = &ctx->dState.ptr[E.global].aliveCount;
+	out->vertexByteOffset = (uint64_t)P.slotBase * 128ull;
+	out->slotCapacity = P.slotCapacity;
+	return SPR_OK;
+}
+
+SPR_API int sprPackRuns(SprContext *c, SprSystem *const *systems, const uint32_t *effectIds, uint32_t numEffects,
+	SprGpuParticle *deviceOut, uint64_t capacityRecords, uint32_t *deviceCounts, uint64_t *outTotalRecords)
+{
+	REQUIRE(c && systems && effectIds && deviceOut);
+	return guarded([&] {
+		Context *ctx = &c->ctx;
+		std::vector<uint32_t> globals(numEffects);
+		for (uint32_t i = 0; i < numEffects; i++) {
+			if (!validEffect(systems[i], effectIds[i])) throw std::runtime_error("invalid effect in sprPackRuns");
+			globals[i] = systems[i]->sys.effects[effectIds[i]].global;
+		}
+		ctx->flushUploads();
+		ctx->gatherIdxD.reserve(numEffects, 0, ctx->stream);
+		ctx->dRunOffsets.reserve(numEffects + 1, 0, ctx->stream);
+		SPR_CUDA(cudaMemcpyAsync(ctx->gatherIdxD.ptr, globals.data(), numEffects * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		launch_run_offsets(ctx->stream, ctx->tablePtrs(), ctx->gatherIdxD.ptr, numEffects, ctx->dRunOffsets.ptr, deviceCounts);
+		launch_pack_runs(ctx->stream, ctx->poolPtrs(), ctx->tablePtrs(), ctx->gatherIdxD.ptr, numEffects, ctx->dRunOffsets.ptr,
+			(float4*)deviceOut, capacityRecords, ctx->numSms);
+		ctx->launchCount += 2;
+		SPR_CUDA(cudaGetLastError());
+		if (outTotalRecords) {
+			SPR_CUDA(cudaMemcpyAsync(outTotalRecords, ctx->dRunOffsets.ptr + numEffects, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+			SPR_CUDA(cudaStreamSynchronize(ctx->stream));
+		}
+	});
+}
+
+SPR_API int sprExpandRuns(SprContext *c, const SprGpuParticle *deviceRecords, uint64_t numRecords, SprGpuParticle *deviceVerticesOut)
+{
+	REQUIRE(c && deviceRecords && deviceVerticesOut);
+	return guarded([&] {
+		launch_expand_runs(c->ctx.stream, (const float4*)deviceRecords, numRecords, (float4*)deviceVerticesOut, c->ctx.numSms);
+		c->ctx.launchCount++;
+		SPR_CUDA(cudaGetLastError());
+	});
+}
+
+}

@@ -1,0 +1,161 @@
+// device_types.h -- structures shared by the host layer and the sm_100a kernels.
+//
+// Layout decisions (DESIGN.md "Data layout in HBM"):
+//  * slot state is an AoS of 32-byte records {pos.xyz, life, vel.xyz, seed} (two float4),
+//    i.e. one lane of the reference's Particle4 (ParticleSystem.cpp:170-176) per record;
+//    slot index i is the only thing parity observes.
+//  * all effects of all systems of a context live in ONE slot pool; an effect owns a
+//    power-of-two range [slotBase, slotBase + slotCapacity) aligned to min(capacity, 1024).
+//  * a 128-slot granule (one warp x 4 slots per lane) belongs to exactly one effect
+//    (granuleOwner), a 1024-slot tile (one CTA) either belongs to one large effect or
+//    holds whole small effects.
+#pragma once
+
+#include <stdint.h>
+
+namespace spr {
+
+static const uint32_t kGranuleSlots = 128;     // slots per warp
+static const uint32_t kTileSlots = 1024;       // slots per CTA (8 warps)
+static const uint32_t kMaxTimerSpawns = 20;    // ParticleSystem.cpp:478
+static const uint32_t kNoOwner = 0xffffffffu;
+static const uint32_t kSortTileKeys = 4096;    // keys per CTA in the radix sort passes
+
+static const float kHugeLife = 1e20f;          // ParticleSystem.cpp:27
+static const float kHugeLifeCmp = 1e19f;       // ParticleSystem.cpp:28
+
+enum RandomVec3Flags { kRvBox = 1, kRvSphere = 2, kRvRotation = 4 }; // ParticleSystem.cpp:68-72
+
+// RandomVec3Imp (ParticleSystem.cpp:66-116), baked on the host.
+struct RandomVec3Dev {
+	uint32_t flags;
+	float offset[3];
+	float boxExtent[3];
+	float thetaBias, thetaScale;
+	float cosPhiBias, cosPhiScale;
+	float radiusCubeScale, radiusScale;
+	float sphereScale[3];
+	float rotation[4];
+};
+
+struct GravityPointDev {
+	float position[3]; // emitter-local (ServerState.h:182)
+	float radius;      // max(radius, 0.05), ParticleSystem.cpp:548
+	float strength;    // negated, :549
+};
+
+// Per effect type constants the kernels read.
+struct TypeDev {
+	RandomVec3Dev emitPosition, emitVelocity;
+	float attractorOffset[3];
+	float attractorStrength;
+	float spawnTime, spawnTimeVariance;
+	uint32_t burstAmount;
+	uint32_t drawsPerSpawn;           // K: RNG draws of one timer spawn; a burst spawn uses K-1
+	uint64_t mulKm1, sumKm1;          // LCG jump by K-1 draws: s' = s*mulKm1 + inc*sumKm1
+	float drag, lifeTime, lifeTimeVariance /* pre-scaled by 2^-24, :535 */, cullPadding;
+	uint32_t numGravityPoints;
+	uint32_t localSpace;
+	GravityPointDev gravityPoints[16];
+};
+
+// Host-owned per-effect parameters (uploaded when they change).
+struct EffectParams {
+	uint32_t typeIdx;       // context-wide type index
+	uint32_t systemIdx;     // context-wide system index
+	uint32_t slotBase;      // first pool slot
+	uint32_t slotCapacity;  // power of two >= 128
+	float timeStep;         // per-effect jittered step, ParticleSystem.cpp:744
+	float gravity[3];
+	float emitterToWorld[16]; // column-major 4x4, :200
+	uint32_t hostStopEmit;  // prepareForRemove, :791
+	uint32_t _pad[3];
+};
+
+// Device-owned per-effect state.
+struct EffectState {
+	float prevEmitterToWorld[16]; // :201
+	float spawnTimer;             // :210
+	float emitOnTimer;            // :211
+	uint32_t stopEmit;            // :207 (device part: emitOnTimer expiry)
+	uint32_t firstEmit;           // :208
+	uint32_t parity;              // which entry of slotCount/freeCount is current
+	uint32_t slotCount[2];        // particles.size * 4
+	uint32_t freeCount[2];        // freeIndices.size
+	uint32_t aliveCount;          // gpuParticles.size / 4
+	uint32_t boundsMin[4];        // order-preserving uint encoding of min(px,py,pz,life), :532
+	uint32_t boundsMax[4];
+	uint32_t _pad[1];
+};
+
+struct SystemDev {
+	uint64_t rngState, rngInc;    // updateCtx.rng, :251,:267
+};
+
+// One system's share of a frame.
+struct SystemWork {
+	uint32_t systemIdx;
+	uint32_t firstActive;   // index into the frame's active arrays
+	uint32_t numActive;
+	uint32_t _pad;
+};
+
+// One active effect of the frame (host computed: sub-step count from timeDelta, :816-820).
+struct ActiveEntry {
+	uint32_t effect;        // context-wide effect index
+	uint32_t numSubsteps;
+	uint32_t planBase;      // first PlanRec of this effect in the frame
+	uint32_t flags;         // bit0: burst handled by the wide burst kernel
+};
+
+// Spawn plan of one simulateParticlesImp call (one effect, one sub-step), written by
+// the planner kernel (control flow of ParticleSystem.cpp:457-485,:524).
+struct PlanRec {
+	uint64_t rngState;      // RNG state before the first draw of this sub-step
+	uint32_t effect;
+	uint32_t burst;         // burst spawns (all precede timer spawns, :480)
+	uint32_t timer;         // timer spawns (<= 20)
+	uint32_t flags;         // bit0 usePrev (prevEmitterToWorld is the stored one), bit1 count parity in
+	float dt;
+	float spawnTimer0;      // spawnTimer after `-= dt` (:477): emitT of burst spawns
+	float timerVals[kMaxTimerSpawns]; // spawnTimer after each timer increment (:484)
+};
+
+// A job of the wide burst-emission kernel: `count` burst spawns of active entry `entry`
+// starting at CTA `firstBlock`.
+struct BurstJob {
+	uint32_t entry;
+	uint32_t firstBlock;
+	uint32_t numBlocks;
+	uint32_t _pad;
+};
+
+struct FillJob { uint32_t start, count, value, _pad; };
+
+// Sort tile: `tile`-th 4096-key tile of effect `effect`'s pair segment.
+struct SortTile { uint32_t effect; uint32_t tile; };
+
+// Launch-constant pointers for the per-round kernels.
+struct PoolPtrs {
+	float4 *state;            // 2 float4 per slot
+	uint32_t *freeStack;      // per slot capacity; effect e uses [slotBase, slotBase+freeCount)
+	float4 *vertices;         // 8 float4 per slot capacity (4 x 32 B per live particle)
+	uint32_t *keys;           // sort mode: compacted depth keys (descending-order transform applied)
+	uint32_t *vals;           // sort mode: compacted local slot indices
+	const uint32_t *granuleOwner;
+	unsigned long long *tileStatusAlive;
+	unsigned long long *tileStatusDead;
+};
+
+struct TablePtrs {
+	const EffectParams *params;
+	EffectState *state;
+	const TypeDev *types;
+	SystemDev *systems;
+	PlanRec *plans;
+	uint32_t *effectStamp;    // frame stamp of the last plan that covers the effect
+	uint32_t *effectPlanBase;
+	uint32_t *effectNumSubsteps;
+};
+
+} // namespace spr

@@ -1,0 +1,841 @@
+// kernels.cu -- hand-written sm_100a kernels for the particle hot path.
+//
+// Reference semantics: src/client/ParticleSystem.cpp:452-680 (simulateParticlesImp).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (bit-exact float
+// parity needs every multiply-add to round twice).
+//
+// Per frame (one set of launches covers every system of the context):
+//   k_plan            one thread per system: spawn control flow + RNG stream offsets
+//   per sub-step round:
+//     k_emit_warp     one warp per active effect: timer spawns (+ small bursts)
+//     k_emit_burst    one thread per burst spawn of large bursts
+//     k_integrate     one warp per 128-slot granule, one CTA per 1024-slot pool tile:
+//                     integrate + alive/dead ballot ranks + chained look-back across the
+//                     tiles of a large effect + free-list append + 4x vertex expansion
+//                     (or depth key/slot pair emission in sort mode) + bounds
+//   k_finalize        prevEmitterToWorld = emitterToWorld (:668)
+// Sort mode adds the segmented radix sort (sort.cuh) and k_expand_sorted.
+//
+// Everything order-sensitive (compaction order, free-list order, spawn->slot
+// assignment, RNG offsets) is a scan, never an atomic.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace spr {
+
+#define FULL_MASK 0xffffffffu
+
+// ---------------------------------------------------------------------------
+// PCG-XSH-RR 64/32 (src/sf/Random.cpp:8-20) with LCG jump-ahead
+// ---------------------------------------------------------------------------
+
+static const uint64_t kPcgMul = 6364136223846793005ULL;
+
+__host__ __device__ inline uint32_t pcg_output(uint64_t old)
+{
+	uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+	uint32_t rot = (uint32_t)(old >> 59u);
+	return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
+}
+
+struct Pcg {
+	uint64_t state, inc;
+	__device__ inline uint32_t nextU32() { uint64_t old = state; state = old * kPcgMul + inc; return pcg_output(old); }
+	// (float)((double)u * 2^-32) == RN(u) * 2^-32 exactly
+	__device__ inline float nextFloat() { return __uint2float_rn(nextU32()) * 2.3283064365386963e-10f; }
+	// advance by `delta` draws in O(log delta)
+	__device__ inline void advance(uint64_t delta)
+	{
+		uint64_t curMul = kPcgMul, curPlus = inc, accMul = 1, accPlus = 0;
+		while (delta > 0) {
+			if (delta & 1) { accMul *= curMul; accPlus = accPlus * curMul + curPlus; }
+			curPlus = (curMul + 1) * curPlus;
+			curMul *= curMul;
+			delta >>= 1;
+		}
+		state = accMul * state + accPlus;
+	}
+};
+
+// ---------------------------------------------------------------------------
+// Approximations and samplers (ParticleSystem.cpp:43-64, :118-145)
+// ---------------------------------------------------------------------------
+
+__device__ inline float sf_min(float a, float b) { return a < b ? a : b; } // minss
+__device__ inline float sf_max(float a, float b) { return a > b ? a : b; } // maxss
+
+__device__ inline float approx_acos(float a)
+{
+	float x = fabsf(a);
+	float v = -1.280827681872808f + 1.280827681872808f * __fsqrt_rn(1.0f - x) - 0.28996864492208857f * x;
+	return 3.14159265358979323846f * 0.5f - copysignf(v, a);
+}
+
+__device__ inline float cossin_lane(float v, float bias)
+{
+	const float rcp2pi = 1.0f / 6.28318530717958647692f;
+	float t = v;
+	t *= rcp2pi;
+	t += bias;
+	t -= rintf(t - 0.25f) + 0.25f;
+	t *= (fabsf(t) - 0.5f) * 16.0f;
+	t += t * (fabsf(t) - 1.0f) * 0.225f;
+	return t;
+}
+
+__device__ inline float approx_cbrt(float a)
+{
+	return 1.5142669123810535f * __fsqrt_rn(a) - 0.5142669123810535f * a;
+}
+
+__device__ inline float3 sample_random_vec3(const RandomVec3Dev &r, Pcg &rng)
+{
+	float3 p = make_float3(r.offset[0], r.offset[1], r.offset[2]);
+	if (r.flags & kRvBox) {
+		float x = rng.nextFloat(), y = rng.nextFloat(), z = rng.nextFloat();
+		p.x += (x - 0.5f) * r.boxExtent[0];
+		p.y += (y - 0.5f) * r.boxExtent[1];
+		p.z += (z - 0.5f) * r.boxExtent[2];
+	}
+	if (r.flags & kRvSphere) {
+		float u = rng.nextFloat();
+		float v = rng.nextFloat();
+		float w = rng.nextFloat();
+		float theta = r.thetaBias + u * r.thetaScale;
+		float phi = approx_acos(r.cosPhiBias + v * r.cosPhiScale);
+		float cosTheta = cossin_lane(theta, 0.0f), sinTheta = cossin_lane(theta, -0.25f);
+		float cosPhi = cossin_lane(phi, 0.0f), sinPhi = cossin_lane(phi, -0.25f);
+		float radius = approx_cbrt(1.0f - w * r.radiusCubeScale) * r.radiusScale;
+		p.x += (sinPhi * cosTheta) * radius * r.sphereScale[0];
+		p.y += (cosPhi) * radius * r.sphereScale[1];
+		p.z += (sinPhi * sinTheta) * radius * r.sphereScale[2];
+	}
+	if (r.flags & kRvRotation) { // sf::rotate, src/sf/Quaternion.h:66-75
+		float qx = r.rotation[0], qy = r.rotation[1], qz = r.rotation[2], qw = r.rotation[3];
+		float xy = qx*p.y - qy*p.x;
+		float xz = qx*p.z - qz*p.x;
+		float yz = qy*p.z - qz*p.y;
+		float3 o;
+		o.x = 2.0f * (+ qw*yz + qy*xy + qz*xz) + p.x;
+		o.y = 2.0f * (- qx*xy - qw*xz + qz*yz) + p.y;
+		o.z = 2.0f * (- qx*xz - qy*yz + qw*xy) + p.z;
+		p = o;
+	}
+	return p;
+}
+
+// order-preserving float <-> uint (min/max through integer atomics and redux)
+__device__ inline uint32_t enc_float(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+
+// ---------------------------------------------------------------------------
+// Small utility kernels
+// ---------------------------------------------------------------------------
+
+__global__ void k_fill_jobs(uint32_t *dst, const FillJob *jobs, uint32_t numJobs)
+{
+	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t j = warp; j < numJobs; j += numWarps) {
+		FillJob job = jobs[j];
+		for (uint32_t i = lane; i < job.count; i += 32) dst[job.start + i] = job.value;
+	}
+}
+
+// dst[idx[i]] = src[i] for structs of `words` 32-bit words
+__global__ void k_scatter_words(uint32_t *dst, const uint32_t *idx, const uint32_t *src, uint32_t n, uint32_t words)
+{
+	uint64_t total = (uint64_t)n * words;
+	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t i = (uint32_t)(t / words), w = (uint32_t)(t % words);
+		dst[(uint64_t)idx[i] * words + w] = src[t];
+	}
+}
+
+// ---------------------------------------------------------------------------
+// k_plan: spawn control flow of simulateParticlesImp (:457-485, :524) for every
+// (effect, sub-step) of every system, in the reference's RNG consumption order
+// (all sub-steps of effect A before effect B, :812-821).
+// ---------------------------------------------------------------------------
+
+__global__ void k_plan(TablePtrs tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp)
+{
+	uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= numWork) return;
+	SystemWork sw = work[w];
+	Pcg rng;
+	rng.state = tab.systems[sw.systemIdx].rngState;
+	rng.inc = tab.systems[sw.systemIdx].rngInc;
+
+	for (uint32_t a = 0; a < sw.numActive; a++) {
+		ActiveEntry ae = active[sw.firstActive + a];
+		uint32_t g = ae.effect;
+		const EffectParams &P = tab.params[g];
+		EffectState &S = tab.state[g];
+		const TypeDev &T = tab.types[P.typeIdx];
+		tab.effectStamp[g] = stamp;
+		tab.effectPlanBase[g] = ae.planBase;
+		tab.effectNumSubsteps[g] = ae.numSubsteps;
+		if (ae.numSubsteps == 0) continue;
+
+		float spawnTimer = S.spawnTimer, emitOnTimer = S.emitOnTimer;
+		uint32_t stopEmit = S.stopEmit, firstEmit = S.firstEmit, parity = S.parity;
+		const float dt = P.timeStep;
+		const uint32_t K = T.drawsPerSpawn;
+
+		for (uint32_t s = 0; s < ae.numSubsteps; s++) {
+			PlanRec &rec = tab.plans[ae.planBase + s];
+			uint32_t burst = 0, usePrev = (s == 0) ? 1u : 0u;
+			if (firstEmit) { burst = T.burstAmount; firstEmit = 0; usePrev = 0; }   // :457-464
+			if (emitOnTimer >= 0.0f) {                                              // :466-471
+				emitOnTimer -= dt;
+				if (emitOnTimer < 0.0f) stopEmit = 1;
+			}
+			bool stop = stopEmit || P.hostStopEmit;
+			spawnTimer -= dt;                                                        // :477
+			rec.rngState = rng.state;
+			rec.effect = g;
+			rec.burst = burst;
+			rec.dt = dt;
+			rec.spawnTimer0 = spawnTimer;
+			rec.flags = usePrev | ((parity & 1u) << 1);
+			if (burst) rng.advance((uint64_t)burst * (K - 1));                       // burst spawns draw first (:480-481)
+			uint32_t timer = 0;
+			int spawnsLeft = (int)kMaxTimerSpawns;
+			while (spawnTimer <= 0.0f && !stop) {                                    // :479-485
+				if (spawnsLeft-- <= 0) break;
+				spawnTimer += T.spawnTime + T.spawnTimeVariance * rng.nextFloat();
+				rec.timerVals[timer++] = spawnTimer;
+				rng.state = rng.state * T.mulKm1 + rng.inc * T.sumKm1;               // the spawn's own K-1 draws
+			}
+			rec.timer = timer;
+			spawnTimer = sf_max(spawnTimer, 0.0f);                                   // :524
+			parity ^= 1u;
+		}
+		S.spawnTimer = spawnTimer;
+		S.emitOnTimer = emitOnTimer;
+		S.stopEmit = stopEmit;
+		S.firstEmit = firstEmit;
+		S.parity = parity;
+	}
+	tab.systems[sw.systemIdx].rngState = rng.state;
+}
+
+// ---------------------------------------------------------------------------
+// Emission (:487-522)
+// ---------------------------------------------------------------------------
+
+struct EmitCtx {
+	const EffectParams *P;
+	const EffectState *S;
+	const TypeDev *T;
+	const PlanRec *rec;
+	uint64_t inc;
+	uint32_t top, blocks; // free-list size and Particle4 block count before this sub-step
+	float e[16], pe[16];  // emitterToWorld / prevEmitterToWorld
+};
+
+__device__ inline void emit_ctx_init(EmitCtx &c, const TablePtrs &tab, const PlanRec *rec)
+{
+	c.rec = rec;
+	uint32_t g = rec->effect;
+	c.P = &tab.params[g];
+	c.S = &tab.state[g];
+	c.T = &tab.types[c.P->typeIdx];
+	c.inc = tab.systems[c.P->systemIdx].rngInc;
+	uint32_t par = (rec->flags >> 1) & 1u;
+	c.top = c.S->freeCount[par];
+	c.blocks = c.S->slotCount[par] >> 2;
+#pragma unroll
+	for (int i = 0; i < 16; i++) {
+		c.e[i] = c.P->emitterToWorld[i];
+		c.pe[i] = (rec->flags & 1u) ? c.S->prevEmitterToWorld[i] : c.e[i];
+	}
+}
+
+// Spawn number j of the sub-step (burst spawns first, then timer spawns).
+__device__ inline void emit_spawn(const EmitCtx &c, const PoolPtrs &pool, uint32_t j)
+{
+	const PlanRec &rec = *c.rec;
+	const TypeDev &T = *c.T;
+	const uint32_t K = T.drawsPerSpawn;
+	Pcg rng;
+	rng.state = rec.rngState;
+	rng.inc = c.inc;
+	float timerVal;
+	if (j < rec.burst) {
+		rng.advance((uint64_t)j * (K - 1));
+		timerVal = rec.spawnTimer0;
+	} else {
+		uint32_t k = j - rec.burst;
+		rng.advance((uint64_t)rec.burst * (K - 1) + (uint64_t)k * K + 1); // +1: the timer draw (:484)
+		timerVal = rec.timerVals[k];
+	}
+
+	// slot: pop of the LIFO free list, growing by one Particle4 at a time (:487-496)
+	uint32_t slot;
+	if (j < c.top) {
+		slot = pool.freeStack[c.P->slotBase + (c.top - 1 - j)];
+	} else {
+		uint32_t r = j - c.top;
+		slot = 4u * (c.blocks + (r >> 2)) + 3u - (r & 3u);
+	}
+
+	float3 pos = sample_random_vec3(T.emitPosition, rng);   // :498
+	float3 vel = sample_random_vec3(T.emitVelocity, rng);   // :499
+
+	if (T.attractorStrength != 0.0f) {                      // :501-503
+		float dx = pos.x - T.attractorOffset[0], dy = pos.y - T.attractorOffset[1], dz = pos.z - T.attractorOffset[2];
+		float len = __fsqrt_rn(dx*dx + dy*dy + dz*dz);
+		if ((double)len > 1e-9) {
+			float rcp = __fdiv_rn(1.0f, len);
+			dx *= rcp; dy *= rcp; dz *= rcp;
+		} else {
+			dx = dy = dz = 0.0f;
+		}
+		vel.x += dx * T.attractorStrength;
+		vel.y += dy * T.attractorStrength;
+		vel.z += dz * T.attractorStrength;
+	}
+
+	float emitT = sf_min(sf_max(__fdiv_rn(-timerVal, rec.dt), 0.0f), 1.0f); // :505
+	float world[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) {                           // :506-509
+		float p = c.e[12 + k] + (c.pe[12 + k] - c.e[12 + k]) * emitT;
+		p += (c.e[0 + k] + (c.pe[0 + k] - c.e[0 + k]) * emitT) * pos.x;
+		p += (c.e[4 + k] + (c.pe[4 + k] - c.e[4 + k]) * emitT) * pos.y;
+		p += (c.e[8 + k] + (c.pe[8 + k] - c.e[8 + k]) * emitT) * pos.z;
+		world[k] = p;
+	}
+	float seed = rng.nextFloat() * 16777216.0f;             // :522
+
+	float4 *dst = pool.state + 2ull * (c.P->slotBase + slot);
+	dst[0] = make_float4(world[0], world[1], world[2], 1.0f);
+	dst[1] = make_float4(vel.x, vel.y, vel.z, seed);
+}
+
+// The last spawn of a sub-step that grew the effect initialises the unused lanes of the
+// final new Particle4 (life = 1e20, :490); their free-list entries are written by k_integrate.
+__device__ inline void emit_init_leftover(const EmitCtx &c, const PoolPtrs &pool, uint32_t n)
+{
+	if (n <= c.top) return;
+	uint32_t nNew = n - c.top;
+	uint32_t newBlocks = (nNew + 3) >> 2;
+	uint32_t leftover = newBlocks * 4 - nNew;
+	uint32_t lastBlock = c.blocks + newBlocks - 1;
+	for (uint32_t i = 0; i < leftover; i++) {
+		float4 *dst = pool.state + 2ull * (c.P->slotBase + 4 * lastBlock + i);
+		dst[0] = make_float4(0.0f, 0.0f, 0.0f, kHugeLife);
+		dst[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	}
+}
+
+// One warp per active effect: all timer spawns, and the burst unless it is flagged for
+// the wide kernel. Also resets the per-step bounds and handles the empty-effect corner.
+__global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab, const ActiveEntry *active, uint32_t numActive, uint32_t round)
+{
+	uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (a >= numActive) return;
+	ActiveEntry ae = active[a];
+	if (round >= ae.numSubsteps) return;
+	const PlanRec *rec = &tab.plans[ae.planBase + round];
+	EmitCtx c;
+	emit_ctx_init(c, tab, rec);
+	uint32_t n = rec->burst + rec->timer;
+	uint32_t first = (ae.flags & 1u) ? rec->burst : 0u;
+	for (uint32_t j = first + lane; j < n; j += 32) emit_spawn(c, pool, j);
+	if (lane == 0) {
+		EffectState &S = tab.state[rec->effect];
+		emit_init_leftover(c, pool, n);
+		// pMin = +HUGE_VALF, pMax = -HUGE_VALF (:532)
+		uint32_t pinf = 0xff800000u /* enc(+inf) */, ninf = 0x007fffffu /* enc(-inf) */;
+#pragma unroll
+		for (int k = 0; k < 4; k++) { S.boundsMin[k] = pinf; S.boundsMax[k] = ninf; }
+		uint32_t slots = c.blocks * 4;
+		if (n > c.top) slots += 4 * ((n - c.top + 3) >> 2);
+		if (slots == 0) { // nothing for k_integrate to do: carry the counts over
+			uint32_t par = (rec->flags >> 1) & 1u;
+			S.slotCount[par ^ 1u] = 0;
+			S.freeCount[par ^ 1u] = 0;
+			S.aliveCount = 0;
+		}
+	}
+}
+
+// One thread per burst spawn, for bursts too large for one warp.
+__global__ void __launch_bounds__(256) k_emit_burst(PoolPtrs pool, TablePtrs tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs)
+{
+	// find the job of this CTA (jobs are sorted by firstBlock; numJobs is small)
+	uint32_t lo = 0, hi = numJobs;
+	while (hi - lo > 1) {
+		uint32_t mid = (lo + hi) >> 1;
+		if (jobs[mid].firstBlock <= blockIdx.x) lo = mid; else hi = mid;
+	}
+	BurstJob job = jobs[lo];
+	ActiveEntry ae = active[job.entry];
+	const PlanRec *rec = &tab.plans[ae.planBase];
+	uint32_t j = (blockIdx.x - job.firstBlock) * blockDim.x + threadIdx.x;
+	if (j >= rec->burst) return;
+	EmitCtx c;
+	emit_ctx_init(c, tab, rec);
+	emit_spawn(c, pool, j);
+}
+
+// ---------------------------------------------------------------------------
+// k_integrate (:526-666)
+// ---------------------------------------------------------------------------
+
+__device__ inline unsigned long long ld_status(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ inline void st_status(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Chained (decoupled look-back) exclusive prefix over the tiles of one large effect, for the
+// alive and the dead counts at once. Status word: [63:34] launch epoch, [33:32] flag
+// (1 aggregate, 2 inclusive prefix), [31:0] value. Called by one full warp.
+__device__ inline void tile_lookback(unsigned long long *stA, unsigned long long *stD, uint32_t poolTile, uint32_t tileIdx,
+	uint32_t aggA, uint32_t aggD, uint32_t epoch, uint32_t lane, uint32_t &exclA, uint32_t &exclD)
+{
+	const unsigned long long tag = (unsigned long long)epoch << 34;
+	const unsigned long long fAgg = 1ull << 32, fIncl = 2ull << 32;
+	exclA = 0; exclD = 0;
+	if (tileIdx == 0) {
+		if (lane == 0) { st_status(stA + poolTile, tag | fIncl | aggA); st_status(stD + poolTile, tag | fIncl | aggD); }
+		return;
+	}
+	if (lane == 0) { st_status(stA + poolTile, tag | fAgg | aggA); st_status(stD + poolTile, tag | fAgg | aggD); }
+	int32_t rel = (int32_t)tileIdx - 1 - (int32_t)lane; // tile (within the effect) this lane inspects
+	for (;;) {
+		unsigned long long va = tag | fIncl, vd = tag | fIncl; // virtual zero prefix in front of tile 0
+		if (rel >= 0) {
+			uint32_t t = poolTile - (tileIdx - (uint32_t)rel);
+			do { va = ld_status(stA + t); } while ((va >> 34) != epoch);
+			do { vd = ld_status(stD + t); } while ((vd >> 34) != epoch);
+		}
+		uint32_t incl = __ballot_sync(FULL_MASK, ((va >> 32) & 3u) == 2u);
+		// a tile publishes both words with the same flag progression; use the weaker of the two
+		uint32_t inclD = __ballot_sync(FULL_MASK, ((vd >> 32) & 3u) == 2u);
+		incl &= inclD;
+		if (incl) {
+			uint32_t firstLane = __ffs(incl) - 1;
+			exclA += __reduce_add_sync(FULL_MASK, lane <= firstLane ? (uint32_t)va : 0u);
+			exclD += __reduce_add_sync(FULL_MASK, lane <= firstLane ? (uint32_t)vd : 0u);
+			break;
+		}
+		exclA += __reduce_add_sync(FULL_MASK, (uint32_t)va);
+		exclD += __reduce_add_sync(FULL_MASK, (uint32_t)vd);
+		rel -= 32;
+	}
+	if (lane == 0) { st_status(stA + poolTile, tag | fIncl | (exclA + aggA)); st_status(stD + poolTile, tag | fIncl | (exclD + aggD)); }
+}
+
+template <bool SORT>
+__global__ void __launch_bounds__(256) k_integrate(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch,
+	float camX, float camY, float camZ)
+{
+	__shared__ float4 sStage[SORT ? 1 : 8 * 256]; // per warp: 128 records x 2 float4
+	__shared__ uint32_t sOwner[8], sAlive[8], sDead[8];
+	__shared__ uint32_t sTileExcl[2];
+
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t poolTile = blockIdx.x;
+	const uint32_t granule = poolTile * 8 + warp;
+
+	uint32_t g = pool.granuleOwner[granule];
+	bool active = false;
+	if (g != kNoOwner) active = tab.effectStamp[g] == stamp && round < tab.effectNumSubsteps[g];
+	if (!__syncthreads_or(active)) return;
+
+	uint32_t slotBase = 0, slotsPost = 0, topPost = 0, localBase = 0, parIn = 0, nSpawn = 0, topIn = 0, blocksIn = 0;
+	bool large = false;
+	float dt = 0.0f, drag = 0.0f, lifeTime = 1.0f, lifeVar = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
+	uint32_t numGp = 0;
+	const PlanRec *rec = nullptr;
+	const EffectParams *P = nullptr;
+	const TypeDev *T = nullptr;
+	EffectState *S = nullptr;
+	if (active) {
+		rec = &tab.plans[tab.effectPlanBase[g] + round];
+		P = &tab.params[g];
+		S = &tab.state[g];
+		T = &tab.types[P->typeIdx];
+		slotBase = P->slotBase;
+		large = P->slotCapacity > kTileSlots;
+		parIn = (rec->flags >> 1) & 1u;
+		nSpawn = rec->burst + rec->timer;
+		topIn = S->freeCount[parIn];
+		blocksIn = S->slotCount[parIn] >> 2;
+		if (nSpawn > topIn) {
+			uint32_t nNew = nSpawn - topIn, newBlocks = (nNew + 3) >> 2;
+			slotsPost = (blocksIn + newBlocks) * 4;
+			topPost = newBlocks * 4 - nNew;
+		} else {
+			slotsPost = blocksIn * 4;
+			topPost = topIn - nSpawn;
+		}
+		localBase = granule * kGranuleSlots - slotBase;
+		dt = rec->dt;
+		drag = T->drag; lifeTime = T->lifeTime; lifeVar = T->lifeTimeVariance;
+		gx = P->gravity[0]; gy = P->gravity[1]; gz = P->gravity[2];
+		numGp = T->numGravityPoints;
+		if (localBase >= slotsPost) active = false;
+	}
+	// A tile of a large effect that lies wholly beyond slotsPost has no work and nobody waits for it.
+	if (!__syncthreads_or(active)) return;
+
+	// ---- load (all 8 loads in flight before any use)
+	float4 a[4], b[4];
+	bool valid[4];
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+		uint32_t li = localBase + r * 32 + lane;
+		valid[r] = active && li < slotsPost;
+		if (valid[r]) {
+			const float4 *src = pool.state + 2ull * (slotBase + li);
+			a[r] = src[0];
+			b[r] = src[1];
+		}
+	}
+
+	// ---- integrate
+	uint32_t aliveMask[4], deadMask[4];
+	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
+	uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+		bool alive = false, dead = false;
+		if (valid[r]) {
+			float life = a[r].w;
+			bool wasFree = !(life < kHugeLifeCmp) && life == life; // parked at 1e20: unobservable, skip the arithmetic
+			if (life <= 0.0f) { dead = true; life = kHugeLife; }   // :556-567
+			if (!wasFree) {
+				float px = a[r].x, py = a[r].y, pz = a[r].z;
+				float vx = b[r].x, vy = b[r].y, vz = b[r].z, seed = b[r].w;
+				float ax = gx, ay = gy, az = gz;                    // :574-579
+				ax -= vx * drag;
+				ay -= vy * drag;
+				az -= vz * drag;
+				for (uint32_t k = 0; k < numGp; k++) {              // :539-550, :581-590
+					const GravityPointDev &gp = T->gravityPoints[k];
+					float wp[3];
+#pragma unroll
+					for (int c = 0; c < 3; c++) {
+						float e3 = P->emitterToWorld[12 + c];
+						float pe3 = (rec->flags & 1u) ? S->prevEmitterToWorld[12 + c] : e3;
+						float v = e3 + (pe3 - e3);
+						v += P->emitterToWorld[0 + c] * gp.position[0];
+						v += P->emitterToWorld[4 + c] * gp.position[1];
+						v += P->emitterToWorld[8 + c] * gp.position[2];
+						wp[c] = v;
+					}
+					float dx = px - wp[0], dy = py - wp[1], dz = pz - wp[2];
+					float lenSq = (dx*dx + dy*dy + dz*dz) + gp.radius;
+					float weight = __fdiv_rn(__fdiv_rn(1.0f, __fsqrt_rn(lenSq)), lenSq) * gp.strength;
+					ax += dx * weight;
+					ay += dy * weight;
+					az += dz * weight;
+				}
+				vx += ax * dt; vy += ay * dt; vz += az * dt;        // :592-594
+				px += vx * dt; py += vy * dt; pz += vz * dt;        // :598-600
+				life -= __fdiv_rn(dt, seed * lifeVar + lifeTime);   // :604
+				a[r] = make_float4(px, py, pz, life);
+				b[r] = make_float4(vx, vy, vz, seed);
+				alive = life < kHugeLifeCmp;                        // :611
+				float4 *dst = pool.state + 2ull * (slotBase + localBase + r * 32 + lane);
+				dst[0] = a[r];
+				dst[1] = b[r];
+			}
+		}
+		aliveMask[r] = __ballot_sync(FULL_MASK, alive);
+		deadMask[r] = __ballot_sync(FULL_MASK, dead);
+		if (alive) {                                                // :620-621
+			uint32_t ex = enc_float(a[r].x), ey = enc_float(a[r].y), ez = enc_float(a[r].z), el = enc_float(a[r].w);
+			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez); mnl = min(mnl, el);
+			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez); mxl = max(mxl, el);
+		}
+	}
+	uint32_t nA = __popc(aliveMask[0]) + __popc(aliveMask[1]) + __popc(aliveMask[2]) + __popc(aliveMask[3]);
+	uint32_t nD = __popc(deadMask[0]) + __popc(deadMask[1]) + __popc(deadMask[2]) + __popc(deadMask[3]);
+
+	// ---- ranks: warps of the same effect inside the CTA, then tiles of a large effect
+	if (lane == 0) { sOwner[warp] = active ? g : kNoOwner; sAlive[warp] = nA; sDead[warp] = nD; }
+	__syncthreads();
+	uint32_t baseA = 0, baseD = 0, tileA = 0, tileD = 0;
+#pragma unroll
+	for (uint32_t w = 0; w < 8; w++) {
+		bool same = active && sOwner[w] == g;
+		if (same && w < warp) { baseA += sAlive[w]; baseD += sDead[w]; }
+		if (same) { tileA += sAlive[w]; tileD += sDead[w]; }
+	}
+	if (large) { // CTA-uniform: a large effect owns whole tiles
+		uint32_t tileIdx = (poolTile * kTileSlots - slotBase) / kTileSlots;
+		if (warp == 0) {
+			uint32_t eA, eD;
+			tile_lookback(pool.tileStatusAlive, pool.tileStatusDead, poolTile, tileIdx, tileA, tileD, epoch, lane, eA, eD);
+			if (lane == 0) { sTileExcl[0] = eA; sTileExcl[1] = eD; }
+		}
+		__syncthreads();
+		baseA += sTileExcl[0];
+		baseD += sTileExcl[1];
+	}
+	if (!active) return;
+
+	// ---- free-list append, ascending slot order (:556-567), behind the post-emission stack
+	{
+		uint32_t run = baseD;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			if (deadMask[r] >> lane & 1u) {
+				uint32_t rank = run + __popc(deadMask[r] & ((1u << lane) - 1u));
+				pool.freeStack[slotBase + topPost + rank] = localBase + r * 32 + lane;
+			}
+			run += __popc(deadMask[r]);
+		}
+	}
+	// entries of a partially used new Particle4 stay at the bottom of the stack (:491-493)
+	if (localBase == 0 && nSpawn > topIn && lane < topPost) {
+		pool.freeStack[slotBase + lane] = slotsPost - 4 + lane;
+	}
+
+	// ---- output
+	if (SORT) {
+		uint32_t run = baseA;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			if (aliveMask[r] >> lane & 1u) {
+				uint32_t rank = run + __popc(aliveMask[r] & ((1u << lane) - 1u));
+				float dx = camX - a[r].x, dy = camY - a[r].y, dz = camZ - a[r].z;
+				float d2 = dx*dx + dy*dy + dz*dz;          // sf::lengthSq, src/sf/Vector.h:99
+				pool.keys[slotBase + rank] = ~enc_float(d2); // descending depth = back to front
+				pool.vals[slotBase + rank] = localBase + r * 32 + lane;
+			}
+			run += __popc(aliveMask[r]);
+		}
+	} else {
+		// stage the warp's live records contiguously, then 4x expand with fully coalesced
+		// 512-byte warp stores (:611-665; the run of a warp is contiguous in the stream)
+		float4 *stage = sStage + warp * 256;
+		uint32_t run = 0;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			if (aliveMask[r] >> lane & 1u) {
+				uint32_t k = run + __popc(aliveMask[r] & ((1u << lane) - 1u));
+				stage[2 * k] = a[r];
+				stage[2 * k + 1] = b[r];
+			}
+			run += __popc(aliveMask[r]);
+		}
+		__syncwarp();
+		float4 *dst = pool.vertices + 8ull * (slotBase + baseA);
+		uint32_t total = nA * 8;
+		for (uint32_t q = lane; q < total; q += 32) {
+			dst[q] = stage[((q >> 3) << 1) | (q & 1u)];
+		}
+	}
+
+	// ---- bounds (:532, :620-663): warp redux, then an atomic only when it extends the box
+	if (nA) {
+		mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny);
+		mnz = __reduce_min_sync(FULL_MASK, mnz); mnl = __reduce_min_sync(FULL_MASK, mnl);
+		mxx = __reduce_max_sync(FULL_MASK, mxx); mxy = __reduce_max_sync(FULL_MASK, mxy);
+		mxz = __reduce_max_sync(FULL_MASK, mxz); mxl = __reduce_max_sync(FULL_MASK, mxl);
+		if (lane < 8) {
+			uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz : lane == 3 ? mnl
+				: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : mxl;
+			uint32_t *addr = lane < 4 ? &S->boundsMin[lane] : &S->boundsMax[lane - 4];
+			uint32_t cur = *(volatile uint32_t*)addr;
+			if (lane < 4) { if (v < cur) atomicMin(addr, v); }
+			else { if (v > cur) atomicMax(addr, v); }
+		}
+	}
+
+	// ---- the warp that holds the last slot publishes the effect's new counts (:670)
+	if (lane == 0 && slotsPost - 1 - localBase < kGranuleSlots) {
+		S->aliveCount = baseA + nA;
+		S->freeCount[parIn ^ 1u] = topPost + baseD + nD;
+		S->slotCount[parIn ^ 1u] = slotsPost;
+	}
+}
+
+// prevEmitterToWorld = emitterToWorld after the frame's sub-steps (:668)
+__global__ void k_finalize(TablePtrs tab, const ActiveEntry *active, uint32_t numActive)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t a = t >> 4, i = t & 15;
+	if (a >= numActive) return;
+	ActiveEntry ae = active[a];
+	if (ae.numSubsteps == 0) return;
+	tab.state[ae.effect].prevEmitterToWorld[i] = tab.params[ae.effect].emitterToWorld[i];
+}
+
+// ---------------------------------------------------------------------------
+// Render-side gather: what renderMain reads per visible effect (:838-846)
+// ---------------------------------------------------------------------------
+
+__device__ inline float dec_float(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void k_gather_render(TablePtrs tab, const uint32_t *effects, uint32_t n, RenderGather *out)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const EffectState &S = tab.state[effects[i]];
+	RenderGather r;
+	r.aliveCount = S.aliveCount;
+	r.slotCount = S.slotCount[S.parity];
+	r.freeCount = S.freeCount[S.parity];
+	r.stopEmit = S.stopEmit;
+	r.firstEmit = S.firstEmit;
+	r.spawnTimer = S.spawnTimer;
+	r.emitOnTimer = S.emitOnTimer;
+#pragma unroll
+	for (int k = 0; k < 4; k++) { r.boundsMin[k] = dec_float(S.boundsMin[k]); r.boundsMax[k] = dec_float(S.boundsMax[k]); }
+	out[i] = r;
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU run packing / expansion
+// ---------------------------------------------------------------------------
+
+// offsets[i] = sum of aliveCount of effects[0..i), offsets[n] = total (single CTA; n is small)
+__global__ void k_run_offsets(TablePtrs tab, const uint32_t *effects, uint32_t n, uint64_t *offsets, uint32_t *counts)
+{
+	__shared__ uint64_t sWarp[32];
+	__shared__ uint64_t sCarry;
+	if (threadIdx.x == 0) sCarry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < n; base += blockDim.x) {
+		uint32_t i = base + threadIdx.x;
+		uint64_t v = i < n ? tab.state[effects[i]].aliveCount : 0;
+		if (i < n && counts) counts[i] = (uint32_t)v;
+		uint64_t incl = v;
+		for (int d = 1; d < 32; d <<= 1) { uint64_t o = __shfl_up_sync(FULL_MASK, incl, d); if ((threadIdx.x & 31) >= d) incl += o; }
+		if ((threadIdx.x & 31) == 31) sWarp[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		uint64_t warpOff = 0;
+		for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) warpOff += sWarp[w];
+		uint64_t carry = sCarry;
+		if (i < n) offsets[i] = carry + warpOff + incl - v;
+		__syncthreads();
+		if (threadIdx.x == blockDim.x - 1) sCarry = carry + warpOff + incl;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) offsets[n] = sCarry;
+}
+
+// out float4 q -> record q>>1 of the concatenated runs; source is every 4th vertex of the effect's stream
+__global__ void __launch_bounds__(256) k_pack_runs(PoolPtrs pool, TablePtrs tab, const uint32_t *effects, uint32_t n,
+	const uint64_t *offsets, float4 *out, uint64_t capacityRecords)
+{
+	uint64_t total = offsets[n];
+	if (total > capacityRecords) total = capacityRecords;
+	uint64_t totalQ = total * 2;
+	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < totalQ; q += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t rcd = q >> 1;
+		uint32_t lo = 0, hi = n;
+		while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= rcd) lo = mid; else hi = mid; }
+		uint64_t k = rcd - offsets[lo];
+		uint32_t slotBase = tab.params[effects[lo]].slotBase;
+		out[q] = pool.vertices[8ull * (slotBase + k) + (q & 1u)];
+	}
+}
+
+// 4x expansion of gathered 32-byte records into the vertex layout (:611-665)
+__global__ void __launch_bounds__(256) k_expand_runs(const float4 *records, uint64_t numRecords, float4 *out)
+{
+	uint64_t totalQ = numRecords * 8;
+	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < totalQ; q += (uint64_t)gridDim.x * blockDim.x) {
+		out[q] = records[((q >> 3) << 1) | (q & 1u)];
+	}
+}
+
+// ---------------------------------------------------------------------------
+// Launch wrappers
+// ---------------------------------------------------------------------------
+
+static inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+void launch_fill_jobs(cudaStream_t st, uint32_t *dst, const FillJob *jobs, uint32_t numJobs)
+{
+	if (!numJobs) return;
+	uint32_t blocks = div_up((uint64_t)numJobs * 32, 256);
+	if (blocks > 4096) blocks = 4096;
+	k_fill_jobs<<<blocks, 256, 0, st>>>(dst, jobs, numJobs);
+}
+
+void launch_scatter_words(cudaStream_t st, void *dst, const uint32_t *idx, const void *src, uint32_t n, uint32_t words)
+{
+	if (!n) return;
+	uint32_t blocks = div_up((uint64_t)n * words, 256);
+	if (blocks > 8192) blocks = 8192;
+	k_scatter_words<<<blocks, 256, 0, st>>>((uint32_t*)dst, idx, (const uint32_t*)src, n, words);
+}
+
+void launch_plan(cudaStream_t st, const TablePtrs &tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp)
+{
+	if (!numWork) return;
+	k_plan<<<div_up(numWork, 64), 64, 0, st>>>(tab, work, numWork, active, stamp);
+}
+
+void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t round)
+{
+	if (!numActive) return;
+	k_emit_warp<<<div_up((uint64_t)numActive * 32, 256), 256, 0, st>>>(pool, tab, active, numActive, round);
+}
+
+void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs, uint32_t totalBlocks)
+{
+	if (!numJobs || !totalBlocks) return;
+	k_emit_burst<<<totalBlocks, 256, 0, st>>>(pool, tab, active, jobs, numJobs);
+}
+
+void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
+	uint32_t epoch, bool sortMode, const float camera[3])
+{
+	if (!numPoolTiles) return;
+	if (sortMode) k_integrate<true><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
+	else k_integrate<false><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
+}
+
+void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive)
+{
+	if (!numActive) return;
+	k_finalize<<<div_up((uint64_t)numActive * 16, 256), 256, 0, st>>>(tab, active, numActive);
+}
+
+void launch_gather_render(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, RenderGather *out)
+{
+	if (!n) return;
+	k_gather_render<<<div_up(n, 128), 128, 0, st>>>(tab, effects, n, out);
+}
+
+void launch_run_offsets(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, uint64_t *offsets, uint32_t *counts)
+{
+	k_run_offsets<<<1, 1024, 0, st>>>(tab, effects, n, offsets, counts);
+}
+
+void launch_pack_runs(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,
+	const uint64_t *offsets, float4 *out, uint64_t capacityRecords, uint32_t numSms)
+{
+	if (!n) return;
+	k_pack_runs<<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, out, capacityRecords);
+}
+
+void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numRecords, float4 *out, uint32_t numSms)
+{
+	if (!numRecords) return;
+	uint32_t blocks = div_up(numRecords * 8, 256);
+	if (blocks > numSms * 16) blocks = numSms * 16;
+	k_expand_runs<<<blocks, 256, 0, st>>>(records, numRecords, out);
+}
+
+} // namespace spr

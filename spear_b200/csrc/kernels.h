@@ -1,0 +1,43 @@
+// kernels.h -- launch wrappers of kernels.cu / sort.cu (host-callable, stream-ordered).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+
+namespace spr {
+
+// What renderMain / the parity read-backs need from the device per effect.
+struct RenderGather {
+	uint32_t aliveCount, slotCount, freeCount;
+	uint32_t stopEmit, firstEmit;
+	float spawnTimer, emitOnTimer;
+	float boundsMin[4], boundsMax[4];
+};
+
+void launch_fill_jobs(cudaStream_t st, uint32_t *dst, const FillJob *jobs, uint32_t numJobs);
+void launch_scatter_words(cudaStream_t st, void *dst, const uint32_t *idx, const void *src, uint32_t n, uint32_t words);
+void launch_plan(cudaStream_t st, const TablePtrs &tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp);
+void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t round);
+void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs, uint32_t totalBlocks);
+void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
+	uint32_t epoch, bool sortMode, const float camera[3]);
+void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive);
+void launch_gather_render(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, RenderGather *out);
+void launch_run_offsets(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, uint64_t *offsets, uint32_t *counts);
+void launch_pack_runs(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,
+	const uint64_t *offsets, float4 *out, uint64_t capacityRecords, uint32_t numSms);
+void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numRecords, float4 *out, uint32_t numSms);
+
+// sort.cu: segmented stable LSD radix sort of the (key, slot) pairs of the listed effects
+// followed by the 4x expansion in sorted order.
+struct SortScratch {
+	uint32_t *keysAlt, *valsAlt;     // ping-pong buffers, same indexing as PoolPtrs::keys/vals
+	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases
+	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
+};
+uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &scratch,
+	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles);
+
+} // namespace spr

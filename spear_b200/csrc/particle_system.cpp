@@ -1,0 +1,697 @@
+// particle_system.cpp -- host layer (see particle_system.h).
+//
+// The host keeps only what the reference's callers can observe without running the
+// simulation (ids, type tables, timeDelta / sub-step counts, transforms); everything
+// a sub-step reads or writes (timers, RNG, slots, free lists, streams, bounds) lives
+// on the device. There is no CPU simulation path in this file.
+
+#include "particle_system.h"
+
+#include <algorithm>
+#include <string.h>
+
+namespace spr {
+
+static uint32_t pow2ceil(uint64_t v)
+{
+	uint64_t p = kGranuleSlots;
+	while (p < v) p <<= 1;
+	if (p > 0x80000000ull) throw std::runtime_error("effect larger than 2^31 slots");
+	return (uint32_t)p;
+}
+
+static uint32_t log2u(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; }
+
+// ---------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------
+
+Context::Context(const SprContextDesc &desc)
+{
+	int count = 0;
+	cudaError_t err = cudaGetDeviceCount(&count);
+	if (err != cudaSuccess || count == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(err));
+	device = desc.device;
+	SPR_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	SPR_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) throw CudaError("spear_particles kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+	numSms = (uint32_t)prop.multiProcessorCount;
+	flags = desc.flags;
+	maxParticlesPerFrame = desc.maxParticlesPerFrame ? desc.maxParticlesPerFrame : 4096;
+	maxParticleCacheFrames = desc.maxParticleCacheFrames ? desc.maxParticleCacheFrames : 16;
+	if (desc.stream) { stream = (cudaStream_t)desc.stream; ownStream = false; }
+	else { SPR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); ownStream = true; }
+	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[0], cudaEventDisableTiming));
+	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[1], cudaEventDisableTiming));
+	freeRanges.resize(33);
+	ensurePool(desc.initialSlotCapacity ? desc.initialSlotCapacity : (1u << 20));
+}
+
+Context::~Context()
+{
+	cudaSetDevice(device);
+	cudaStreamSynchronize(stream);
+	cudaFree(dSlotState); cudaFree(dFreeStack); cudaFree(dVertices);
+	cudaFree(dKeys[0]); cudaFree(dKeys[1]); cudaFree(dVals[0]); cudaFree(dVals[1]);
+	cudaFree(dGranuleOwner); cudaFree(dTileStatus[0]); cudaFree(dTileStatus[1]);
+	cudaEventDestroy(stagingEvent[0]); cudaEventDestroy(stagingEvent[1]);
+	if (ownStream) cudaStreamDestroy(stream);
+}
+
+PoolPtrs Context::poolPtrs() const
+{
+	PoolPtrs p;
+	p.state = dSlotState; p.freeStack = dFreeStack; p.vertices = dVertices;
+	p.keys = dKeys[0]; p.vals = dVals[0];
+	p.granuleOwner = dGranuleOwner;
+	p.tileStatusAlive = dTileStatus[0]; p.tileStatusDead = dTileStatus[1];
+	return p;
+}
+
+TablePtrs Context::tablePtrs()
+{
+	TablePtrs t;
+	t.params = dParams.ptr; t.state = dState.ptr; t.types = dTypes.ptr; t.systems = dSystems.ptr;
+	t.plans = dPlans.ptr;
+	t.effectStamp = dEffectStamp.ptr; t.effectPlanBase = dEffectPlanBase.ptr; t.effectNumSubsteps = dEffectNumSubsteps.ptr;
+	return t;
+}
+
+template <typename T>
+static void regrow(T *&ptr, uint64_t oldCount, uint64_t newCount, uint64_t keepCount, int fillByte, cudaStream_t st)
+{
+	T *p = nullptr;
+	SPR_CUDA(cudaMalloc(&p, newCount * sizeof(T)));
+	if (keepCount) SPR_CUDA(cudaMemcpyAsync(p, ptr, keepCount * sizeof(T), cudaMemcpyDeviceToDevice, st));
+	if (fillByte >= 0) SPR_CUDA(cudaMemsetAsync(p + keepCount, fillByte, (newCount - keepCount) * sizeof(T), st));
+	(void)oldCount;
+	if (ptr) { SPR_CUDA(cudaStreamSynchronize(st)); SPR_CUDA(cudaFree(ptr)); }
+	ptr = p;
+}
+
+void Context::ensurePool(uint64_t slots)
+{
+	if (slots <= poolCapacity) return;
+	uint64_t cap = poolCapacity ? poolCapacity * 2 : kTileSlots;
+	while (cap < slots) cap *= 2;
+	if (cap > 0xffffffffull) throw std::runtime_error("slot pool larger than 2^32 slots");
+	uint64_t used = poolCapacity; // copy everything that was addressable
+	regrow(dSlotState, poolCapacity * 2, cap * 2, used * 2, -1, stream);
+	regrow(dFreeStack, poolCapacity, cap, used, -1, stream);
+	regrow(dVertices, poolCapacity * 8, cap * 8, used * 8, -1, stream);
+	regrow(dGranuleOwner, poolCapacity / kGranuleSlots, cap / kGranuleSlots, used / kGranuleSlots, 0xff, stream);
+	regrow(dTileStatus[0], poolCapacity / kTileSlots, cap / kTileSlots, 0, 0, stream);
+	regrow(dTileStatus[1], poolCapacity / kTileSlots, cap / kTileSlots, 0, 0, stream);
+	if (flags & SPR_CTX_SORT_PARTICLES) {
+		for (int i = 0; i < 2; i++) {
+			regrow(dKeys[i], poolCapacity, cap, 0, -1, stream);
+			regrow(dVals[i], poolCapacity, cap, 0, -1, stream);
+		}
+	}
+	poolCapacity = cap;
+}
+
+uint32_t Context::allocRange(uint32_t capacity)
+{
+	uint32_t cls = log2u(capacity);
+	if (!freeRanges[cls].empty()) {
+		uint32_t base = freeRanges[cls].back();
+		freeRanges[cls].pop_back();
+		return base;
+	}
+	uint64_t align = capacity < kTileSlots ? capacity : kTileSlots;
+	uint64_t base = (poolUsed + align - 1) / align * align;
+	poolUsed = base + capacity;
+	ensurePool(poolUsed);
+	return (uint32_t)base;
+}
+
+void Context::freeRange(uint32_t slotBase, uint32_t capacity)
+{
+	freeRanges[log2u(capacity)].push_back(slotBase);
+	ownerJobs.push_back({ slotBase / kGranuleSlots, capacity / kGranuleSlots, kNoOwner, 0 });
+}
+
+uint32_t Context::allocEffectGlobal()
+{
+	uint32_t g;
+	if (!freeEffectGlobals.empty()) { g = freeEffectGlobals.back(); freeEffectGlobals.pop_back(); }
+	else {
+		g = numEffectGlobals++;
+		hParams.resize(numEffectGlobals);
+		dirtyParamsFlag.resize(numEffectGlobals, 0);
+		size_t keep = numEffectGlobals - 1;
+		dParams.reserve(numEffectGlobals, keep, stream);
+		dState.reserve(numEffectGlobals, keep, stream);
+		dEffectStamp.reserve(numEffectGlobals, keep, stream);
+		dEffectPlanBase.reserve(numEffectGlobals, keep, stream);
+		dEffectNumSubsteps.reserve(numEffectGlobals, keep, stream);
+	}
+	return g;
+}
+
+void Context::markParamsDirty(uint32_t g)
+{
+	if (!dirtyParamsFlag[g]) { dirtyParamsFlag[g] = 1; dirtyParams.push_back(g); }
+}
+
+void Context::growEffect(uint32_t g, uint32_t minCapacity, bool copyContents)
+{
+	EffectParams &P = hParams[g];
+	uint32_t newCap = pow2ceil(minCapacity);
+	if (newCap <= P.slotCapacity) return;
+	uint32_t oldBase = P.slotBase, oldCap = P.slotCapacity;
+	uint32_t newBase = allocRange(newCap);
+	if (copyContents && oldCap) {
+		SPR_CUDA(cudaMemcpyAsync(dSlotState + 2ull * newBase, dSlotState + 2ull * oldBase, (size_t)oldCap * 32, cudaMemcpyDeviceToDevice, stream));
+		SPR_CUDA(cudaMemcpyAsync(dFreeStack + newBase, dFreeStack + oldBase, (size_t)oldCap * 4, cudaMemcpyDeviceToDevice, stream));
+	}
+	if (oldCap) freeRange(oldBase, oldCap);
+	ownerJobs.push_back({ newBase / kGranuleSlots, newCap / kGranuleSlots, g, 0 });
+	P.slotBase = newBase;
+	P.slotCapacity = newCap;
+	markParamsDirty(g);
+}
+
+// One staging blob per submit: pending table uploads + the frame's work lists.
+namespace {
+struct BlobWriter {
+	uint8_t *host; size_t size = 0;
+	explicit BlobWriter(uint8_t *h) : host(h) { }
+	template <typename T> size_t put(const T *src, size_t n) {
+		size = (size + 15) & ~(size_t)15;
+		size_t off = size;
+		if (n) memcpy(host + off, src, n * sizeof(T));
+		size += n * sizeof(T);
+		return off;
+	}
+};
+}
+
+void Context::flushUploads()
+{
+	UpdateRequest none = { nullptr, nullptr, 0, nullptr };
+	(void)none;
+	update(nullptr, 0);
+}
+
+void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
+{
+	SPR_CUDA(cudaSetDevice(device));
+	const bool sortMode = (flags & SPR_CTX_SORT_PARTICLES) != 0;
+
+	// ---- host pass: sub-step counts (ParticleSystem.cpp:810-820) and capacity bounds
+	std::vector<ActiveEntry> entries;
+	std::vector<SystemWork> work;
+	std::vector<BurstJob> burstJobs;
+	struct Resolve { HostEffect *E; uint32_t add; };
+	std::vector<Resolve> resolve;
+	std::vector<uint32_t> resolveGlobals;
+	uint32_t numPlans = 0, maxSub = 0, burstBlocks = 0;
+	float camera[3] = { 0, 0, 0 };
+	for (uint32_t r = 0; r < numReqs; r++) {
+		ParticleSystem *sys = reqs[r].system;
+		const SprFrameArgs &args = *reqs[r].args;
+		camera[0] = args.cameraPosition.x; camera[1] = args.cameraPosition.y; camera[2] = args.cameraPosition.z;
+		float clampedDt = args.dt < 0.1f ? args.dt : 0.1f; // sf::min(args.dt, 0.1f), :810
+		SystemWork sw = { sys->systemIdx, (uint32_t)entries.size(), reqs[r].numActive, 0 };
+		for (uint32_t i = 0; i < reqs[r].numActive; i++) {
+			HostEffect &E = sys->effects[reqs[r].activeIds[i]];
+			E.lastUpdateTime = args.gameTime;                // :814
+			E.timeDelta += clampedDt;                        // :816
+			uint32_t nsub = 0;
+			while (E.timeDelta >= E.timeStep) { nsub++; E.timeDelta -= E.timeStep; } // :817-820
+			ActiveEntry ae = { E.global, nsub, numPlans, 0 };
+			numPlans += nsub;
+			if (nsub > maxSub) maxSub = nsub;
+			if (nsub) {
+				const HostType &type = sys->types[E.typeId];
+				uint32_t burst = E.firstEmit ? type.comp->burstAmount : 0;
+				// <= 20 timer spawns per sub-step (:478), each sub-step rounds up to one Particle4
+				uint64_t add = (uint64_t)nsub * (kMaxTimerSpawns + 3) + burst + 3;
+				uint64_t need = (uint64_t)E.slotUpperBound + add;
+				if (need > hParams[E.global].slotCapacity) {
+					if (E.simSteps == 0) { growEffect(E.global, pow2ceil(need), false); E.slotUpperBound = (uint32_t)need; }
+					else { resolve.push_back({ &E, (uint32_t)add }); resolveGlobals.push_back(E.global); }
+				} else {
+					E.slotUpperBound = (uint32_t)need;
+				}
+				if (burst > 1024) {
+					ae.flags |= 1u;
+					uint32_t blocks = (burst + 255) / 256;
+					burstJobs.push_back({ (uint32_t)entries.size(), burstBlocks, blocks, 0 });
+					burstBlocks += blocks;
+				}
+				E.firstEmit = false;
+				E.simSteps += nsub;
+				E.uploadFrameIndex = 0;                      // :679
+				E.boundsToWorld = E.particlesToWorld;        // gpuBounds uses the matrix of the simulated step (:675-677)
+			}
+			entries.push_back(ae);
+		}
+		work.push_back(sw);
+	}
+	if (!resolve.empty()) {
+		// the conservative bound ran out: read the exact slot counts back (rare) and grow if needed
+		std::vector<RenderGather> got(resolve.size());
+		gatherEffects(resolveGlobals.data(), (uint32_t)resolve.size(), got.data());
+		for (size_t i = 0; i < resolve.size(); i++) {
+			HostEffect &E = *resolve[i].E;
+			uint64_t need = (uint64_t)got[i].slotCount + resolve[i].add;
+			if (need > hParams[E.global].slotCapacity) growEffect(E.global, pow2ceil(need * 2), true);
+			E.slotUpperBound = (uint32_t)need;
+		}
+	}
+
+	// ---- sort-mode work lists
+	std::vector<uint32_t> segEffects;
+	std::vector<SortTile> sortTiles;
+	if (sortMode) {
+		for (const ActiveEntry &ae : entries) {
+			if (!ae.numSubsteps) continue;
+			uint32_t seg = (uint32_t)segEffects.size();
+			(void)seg;
+			segEffects.push_back(ae.effect);
+		}
+	}
+
+	// ---- staging blob
+	size_t bound = 256
+		+ dirtyParams.size() * (sizeof(uint32_t) + sizeof(EffectParams))
+		+ initStateIdx.size() * (sizeof(uint32_t) + sizeof(EffectState))
+		+ typeIdx.size() * (sizeof(uint32_t) + sizeof(TypeDev))
+		+ systemIdx.size() * (sizeof(uint32_t) + sizeof(SystemDev))
+		+ ownerJobs.size() * sizeof(FillJob)
+		+ entries.size() * sizeof(ActiveEntry) + work.size() * sizeof(SystemWork) + burstJobs.size() * sizeof(BurstJob)
+		+ segEffects.size() * sizeof(uint32_t);
+	if (sortMode) {
+		for (uint32_t g : segEffects) bound += ((size_t)hParams[g].slotCapacity / kSortTileKeys + 1) * sizeof(SortTile);
+	}
+	bound += 16 * 16;
+	int par = stagingParity; stagingParity ^= 1;
+	SPR_CUDA(cudaEventSynchronize(stagingEvent[par]));
+	stagingH[par].reserve(bound);
+	stagingD.reserve(bound, 0, stream);
+	BlobWriter bw(stagingH[par].ptr);
+
+	std::vector<EffectParams> paramVals(dirtyParams.size());
+	for (size_t i = 0; i < dirtyParams.size(); i++) { paramVals[i] = hParams[dirtyParams[i]]; dirtyParamsFlag[dirtyParams[i]] = 0; }
+	size_t oParamIdx = bw.put(dirtyParams.data(), dirtyParams.size());
+	size_t oParamVal = bw.put(paramVals.data(), paramVals.size());
+	size_t oStateIdx = bw.put(initStateIdx.data(), initStateIdx.size());
+	size_t oStateVal = bw.put(initStateVal.data(), initStateVal.size());
+	size_t oTypeIdx = bw.put(typeIdx.data(), typeIdx.size());
+	size_t oTypeVal = bw.put(typeVal.data(), typeVal.size());
+	size_t oSysIdx = bw.put(systemIdx.data(), systemIdx.size());
+	size_t oSysVal = bw.put(systemVal.data(), systemVal.size());
+	{ // jobs run in parallel on the device: for a range touched twice (freed, then reused) keep the last write
+		std::unordered_map<uint32_t, size_t> last;
+		for (size_t i = 0; i < ownerJobs.size(); i++) last[ownerJobs[i].start] = i;
+		if (last.size() != ownerJobs.size()) {
+			std::vector<FillJob> kept;
+			for (size_t i = 0; i < ownerJobs.size(); i++) if (last[ownerJobs[i].start] == i) kept.push_back(ownerJobs[i]);
+			ownerJobs.swap(kept);
+		}
+	}
+	size_t oOwner = bw.put(ownerJobs.data(), ownerJobs.size());
+	size_t oEntries = bw.put(entries.data(), entries.size());
+	size_t oWork = bw.put(work.data(), work.size());
+	size_t oBurst = bw.put(burstJobs.data(), burstJobs.size());
+	if (sortMode) {
+		for (size_t s = 0; s < segEffects.size(); s++) {
+			const EffectParams &P = hParams[segEffects[s]];
+			uint32_t tiles = (P.slotCapacity + kSortTileKeys - 1) / kSortTileKeys;
+			for (uint32_t t = 0; t < tiles; t++) sortTiles.push_back({ (uint32_t)s, t });
+		}
+	}
+	size_t oSeg = bw.put(segEffects.data(), segEffects.size());
+	size_t oTiles = bw.put(sortTiles.data(), sortTiles.size());
+	if (bw.size > bound) throw std::runtime_error("staging blob overflow");
+
+	const uint32_t nParams = (uint32_t)dirtyParams.size(), nState = (uint32_t)initStateIdx.size();
+	const uint32_t nTypes = (uint32_t)typeIdx.size(), nSys = (uint32_t)systemIdx.size(), nOwner = (uint32_t)ownerJobs.size();
+	dirtyParams.clear(); initStateIdx.clear(); initStateVal.clear(); typeIdx.clear(); typeVal.clear();
+	systemIdx.clear(); systemVal.clear(); ownerJobs.clear();
+
+	if (bw.size) {
+		SPR_CUDA(cudaMemcpyAsync(stagingD.ptr, stagingH[par].ptr, bw.size, cudaMemcpyHostToDevice, stream));
+		SPR_CUDA(cudaEventRecord(stagingEvent[par], stream));
+	}
+	uint8_t *D = stagingD.ptr;
+#define DPTR(T, off) ((const T*)(D + (off)))
+	if (nParams) { launch_scatter_words(stream, dParams.ptr, DPTR(uint32_t, oParamIdx), D + oParamVal, nParams, sizeof(EffectParams) / 4); launchCount++; }
+	if (nState) { launch_scatter_words(stream, dState.ptr, DPTR(uint32_t, oStateIdx), D + oStateVal, nState, sizeof(EffectState) / 4); launchCount++; }
+	if (nTypes) { launch_scatter_words(stream, dTypes.ptr, DPTR(uint32_t, oTypeIdx), D + oTypeVal, nTypes, sizeof(TypeDev) / 4); launchCount++; }
+	if (nSys) { launch_scatter_words(stream, dSystems.ptr, DPTR(uint32_t, oSysIdx), D + oSysVal, nSys, sizeof(SystemDev) / 4); launchCount++; }
+	if (nOwner) { launch_fill_jobs(stream, dGranuleOwner, DPTR(FillJob, oOwner), nOwner); launchCount++; }
+
+	if (numPlans == 0) { SPR_CUDA(cudaGetLastError()); return; }
+
+	// ---- the frame
+	frameStamp++;
+	dPlans.reserve(numPlans, 0, stream);
+	PoolPtrs pool = poolPtrs();
+	TablePtrs tab = tablePtrs();
+	const ActiveEntry *dEntries = DPTR(ActiveEntry, oEntries);
+	const uint32_t nEntries = (uint32_t)entries.size();
+	launch_plan(stream, tab, DPTR(SystemWork, oWork), (uint32_t)work.size(), dEntries, frameStamp); launchCount++;
+	const uint32_t poolTiles = (uint32_t)((poolUsed + kTileSlots - 1) / kTileSlots);
+	for (uint32_t round = 0; round < maxSub; round++) {
+		launch_emit_warp(stream, pool, tab, dEntries, nEntries, round); launchCount++;
+		if (round == 0 && !burstJobs.empty()) {
+			launch_emit_burst(stream, pool, tab, dEntries, DPTR(BurstJob, oBurst), (uint32_t)burstJobs.size(), burstBlocks); launchCount++;
+		}
+		epoch = (epoch + 1) & 0x3fffffffu;
+		if (epoch == 0) { // status words carry a 30-bit epoch: wipe them when it wraps
+			SPR_CUDA(cudaMemsetAsync(dTileStatus[0], 0, poolCapacity / kTileSlots * 8, stream));
+			SPR_CUDA(cudaMemsetAsync(dTileStatus[1], 0, poolCapacity / kTileSlots * 8, stream));
+			epoch = 1;
+		}
+		launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, camera); launchCount++;
+	}
+	launch_finalize(stream, tab, dEntries, nEntries); launchCount++;
+
+	if (sortMode && !segEffects.empty()) {
+		SortScratch sc;
+		sc.keysAlt = dKeys[1]; sc.valsAlt = dVals[1];
+		dSortHist.reserve(segEffects.size() * 4 * 256, 0, stream);
+		dSortLookback.reserve(sortTiles.size() * 4 * 256 + 1, 0, stream);
+		sc.hist = dSortHist.ptr; sc.lookback = dSortLookback.ptr;
+		launchCount += launch_sort_and_expand(stream, pool, tab, sc, DPTR(uint32_t, oSeg), (uint32_t)segEffects.size(),
+			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size());
+	}
+#undef DPTR
+	SPR_CUDA(cudaGetLastError());
+}
+
+void Context::gatherEffects(const uint32_t *globals, uint32_t n, RenderGather *out)
+{
+	if (!n) return;
+	SPR_CUDA(cudaSetDevice(device));
+	if (!dirtyParams.empty() || !initStateIdx.empty() || !typeIdx.empty() || !systemIdx.empty() || !ownerJobs.empty()) flushUploads();
+	gatherIdxD.reserve(n, 0, stream);
+	gatherD.reserve(n, 0, stream);
+	gatherH.reserve(n);
+	SPR_CUDA(cudaMemcpyAsync(gatherIdxD.ptr, globals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+	launch_gather_render(stream, tablePtrs(), gatherIdxD.ptr, n, gatherD.ptr); launchCount++;
+	SPR_CUDA(cudaMemcpyAsync(gatherH.ptr, gatherD.ptr, n * sizeof(RenderGather), cudaMemcpyDeviceToHost, stream));
+	SPR_CUDA(cudaStreamSynchronize(stream));
+	memcpy(out, gatherH.ptr, n * sizeof(RenderGather));
+}
+
+// ---------------------------------------------------------------------------
+// ParticleSystem
+// ---------------------------------------------------------------------------
+
+ParticleSystem::ParticleSystem(Context *c, const SprSystemsDesc &desc)
+	: ctx(c), initRng(1, 1), bufferFrameIndex(c->maxParticleCacheFrames)
+{
+	if (!ctx->freeSystemGlobals.empty()) { systemIdx = ctx->freeSystemGlobals.back(); ctx->freeSystemGlobals.pop_back(); }
+	else {
+		systemIdx = ctx->numSystemGlobals++;
+		ctx->dSystems.reserve(ctx->numSystemGlobals, ctx->numSystemGlobals - 1, ctx->stream);
+	}
+	SystemDev sd;
+	sd.rngState = desc.seed[1];            // sf::Random(desc.seed[1], 581271), :267; ctor src/sf/Random.h:11
+	sd.rngInc = 581271ull | 1ull;
+	ctx->systemIdx.push_back(systemIdx);
+	ctx->systemVal.push_back(sd);
+}
+
+ParticleSystem::~ParticleSystem()
+{
+	for (uint32_t id = 0; id < effects.size(); id++) if (effects[id].inUse) remove(id);
+	for (HostType &t : types) if (t.comp) { ctx->freeTypeGlobals.push_back(t.global); t.comp = nullptr; }
+	ctx->freeSystemGlobals.push_back(systemIdx);
+}
+
+uint32_t ParticleSystem::reserveEffectType(const SprParticleSystemComponent *c)
+{
+	uint32_t typeId;
+	auto it = componentToType.find((const void*)c);
+	if (it == componentToType.end()) {
+		if (!freeTypeIds.empty()) { typeId = freeTypeIds.back(); freeTypeIds.pop_back(); }
+		else { typeId = (uint32_t)types.size(); types.emplace_back(); }
+		componentToType[(const void*)c] = typeId;
+		HostType &type = types[typeId];
+		type.comp = c;
+		type.refCount = 0;
+		type.renderOrder = c->renderOrder;
+		type.tiebreaker = typeId;
+		type.timeStep = c->timeStep;
+
+		// initEffectType (:298-450): LUT + type UBO on the host, sampler constants for the device
+		bakeTypeUbo(type.typeUbo, typeId, *c);
+		memset(type.lut, 0, sizeof(type.lut));
+		bakeSplineRow(type.lut, 0, c->scaleSpline, false);
+		bakeSplineRow(type.lut, 1, c->alphaSpline, false);
+		bakeSplineRow(type.lut, 2, c->additiveSpline, true);
+		bakeSplineRow(type.lut, 3, c->erosionSpline, false);
+		bakeGradientRow(type.lut + SPR_SPLINE_SAMPLE_RATE * 4, c->gradient);
+
+		if (!ctx->freeTypeGlobals.empty()) { type.global = ctx->freeTypeGlobals.back(); ctx->freeTypeGlobals.pop_back(); }
+		else {
+			type.global = ctx->numTypeGlobals++;
+			ctx->dTypes.reserve(ctx->numTypeGlobals, ctx->numTypeGlobals - 1, ctx->stream);
+		}
+		TypeDev td;
+		memset(&td, 0, sizeof(td));
+		bakeRandomVec3(td.emitPosition, c->emitPosition);
+		bakeRandomVec3(td.emitVelocity, c->emitVelocity);
+		td.attractorOffset[0] = c->emitVelocityAttractorOffset.x;
+		td.attractorOffset[1] = c->emitVelocityAttractorOffset.y;
+		td.attractorOffset[2] = c->emitVelocityAttractorOffset.z;
+		td.attractorStrength = c->emitVelocityAttractorStrength;
+		td.spawnTime = c->spawnTime;
+		td.spawnTimeVariance = c->spawnTimeVariance;
+		td.burstAmount = c->burstAmount;
+		// draws of one timer spawn: timer + position + velocity + seed (:484, :498-499, :522)
+		td.drawsPerSpawn = 1 + drawsOfSampler(td.emitPosition) + drawsOfSampler(td.emitVelocity) + 1;
+		lcgJump(td.drawsPerSpawn - 1, td.mulKm1, td.sumKm1);
+		td.drag = c->drag;
+		td.lifeTime = c->lifeTime;
+		td.lifeTimeVariance = c->lifeTimeVariance * (1.0f / 16777216.0f);   // :535
+		td.cullPadding = c->cullPadding;
+		td.localSpace = c->localSpace ? 1u : 0u;
+		td.numGravityPoints = c->numGravityPoints < SPR_MAX_GRAVITY_POINTS ? c->numGravityPoints : SPR_MAX_GRAVITY_POINTS;
+		for (uint32_t i = 0; i < td.numGravityPoints; i++) {               // :540-550
+			const SprGravityPoint &p = c->gravityPoints[i];
+			td.gravityPoints[i].position[0] = p.position.x;
+			td.gravityPoints[i].position[1] = p.position.y;
+			td.gravityPoints[i].position[2] = p.position.z;
+			td.gravityPoints[i].radius = p.radius > 0.05f ? p.radius : 0.05f; // sf::max(p.radius, 0.05f)
+			td.gravityPoints[i].strength = -p.strength;
+		}
+		ctx->typeIdx.push_back(type.global);
+		ctx->typeVal.push_back(td);
+	} else {
+		typeId = it->second;
+	}
+	types[typeId].refCount++;
+	return typeId;
+}
+
+void ParticleSystem::releaseEffectTypeImp(uint32_t typeId)
+{
+	HostType &type = types[typeId];
+	if (--type.refCount == 0) {
+		componentToType.erase((const void*)type.comp);
+		ctx->freeTypeGlobals.push_back(type.global);
+		type = HostType();
+		freeTypeIds.push_back(typeId);
+	}
+}
+
+void ParticleSystem::releaseEffectType(const SprParticleSystemComponent *c)
+{
+	auto it = componentToType.find((const void*)c);
+	if (it != componentToType.end()) releaseEffectTypeImp(it->second);
+}
+
+uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, const SprParticleSystemComponent *c, const SprTransform &transform)
+{
+	(void)entityId; (void)componentIndex;
+	uint32_t effectId;
+	if (!freeEffectIds.empty()) { effectId = freeEffectIds.back(); freeEffectIds.pop_back(); }
+	else { effectId = (uint32_t)effects.size(); effects.emplace_back(); }
+
+	uint32_t typeId = reserveEffectType(c);
+	const HostType &type = types[typeId];
+
+	HostEffect &E = effects[effectId];
+	E = HostEffect();
+	E.inUse = true;
+	E.typeId = typeId;
+	E.timeStep = type.timeStep * (1.0f + initRng.nextFloat() * 0.1f);   // :744
+	E.origin = transform.position;
+	E.instantDelete = c->instantDelete != 0;
+	E.particlesToWorld = identity34();
+	E.boundsToWorld = identity34();
+	E.uploadFrameIndex = ctx->maxParticleCacheFrames;
+	E.global = ctx->allocEffectGlobal();
+
+	EffectParams &P = ctx->hParams[E.global];
+	memset(&P, 0, sizeof(P));
+	P.typeIdx = type.global;
+	P.systemIdx = systemIdx;
+	P.timeStep = E.timeStep;
+	P.gravity[0] = c->gravity.x; P.gravity[1] = c->gravity.y; P.gravity[2] = c->gravity.z;
+	SprMat34 entityToWorld = transformToMatrix(transform);
+	if (c->localSpace) {                                                  // :755-760
+		writeColMajor44(identity34(), P.emitterToWorld);
+		E.particlesToWorld = entityToWorld;
+	} else {
+		writeColMajor44(entityToWorld, P.emitterToWorld);
+	}
+	P.slotBase = 0; P.slotCapacity = 0;
+	ctx->growEffect(E.global, pow2ceil((uint64_t)c->burstAmount + 64), false);
+
+	EffectState S;
+	memset(&S, 0, sizeof(S));
+	S.firstEmit = 1;
+	S.emitOnTimer = c->emitterOnTime;                                      // :750
+	ctx->initStateIdx.push_back(E.global);
+	ctx->initStateVal.push_back(S);
+	ctx->markParamsDirty(E.global);
+	return effectId;
+}
+
+void ParticleSystem::updateTransform(uint32_t effectId, const SprTransformUpdate &update)
+{
+	HostEffect &E = effects[effectId];
+	const HostType &type = types[E.typeId];
+	if (type.comp->localSpace) {
+		E.particlesToWorld = update.entityToWorld;
+	} else {
+		writeColMajor44(update.entityToWorld, ctx->hParams[E.global].emitterToWorld);
+		ctx->markParamsDirty(E.global);
+	}
+	E.origin = update.transform.position;
+}
+
+bool ParticleSystem::prepareForRemove(uint32_t effectId, const SprFrameArgs &args)
+{
+	HostEffect &E = effects[effectId];
+	if (!E.hostStopEmit) {
+		E.hostStopEmit = true;                                             // :791
+		ctx->hParams[E.global].hostStopEmit = 1;
+		ctx->markParamsDirty(E.global);
+	}
+	if (E.instantDelete || args.gameTime - E.lastUpdateTime > 2.0) return true; // :793 (order-free ||)
+	RenderGather g;
+	ctx->gatherEffects(&E.global, 1, &g);
+	return g.aliveCount == 0;
+}
+
+void ParticleSystem::remove(uint32_t effectId)
+{
+	HostEffect &E = effects[effectId];
+	if (!E.inUse) return;
+	releaseEffectTypeImp(E.typeId);
+	EffectParams &P = ctx->hParams[E.global];
+	if (P.slotCapacity) ctx->freeRange(P.slotBase, P.slotCapacity);
+	P.slotCapacity = 0;
+	ctx->freeEffectGlobals.push_back(E.global);
+	E = HostEffect();
+	freeEffectIds.push_back(effectId);
+}
+
+void ParticleSystem::updateParticles(const uint32_t *activeIds, uint32_t numActive, const SprFrameArgs &args)
+{
+	UpdateRequest req = { this, activeIds, numActive, &args };
+	ctx->update(&req, 1);
+}
+
+namespace {
+struct SortedEffect { // :225-239
+	double renderOrder; uint32_t tiebreaker; float depth; uint32_t effectId;
+	bool operator<(const SortedEffect &rhs) const {
+		if (renderOrder != rhs.renderOrder) return renderOrder < rhs.renderOrder;
+		if (tiebreaker != rhs.tiebreaker) return tiebreaker < rhs.tiebreaker;
+		if (depth != rhs.depth) return depth < rhs.depth;
+		if (effectId != rhs.effectId) return effectId < rhs.effectId;
+		return false;
+	}
+};
+}
+
+SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const HostEffect &E)
+{
+	// :672-677
+	SprBounds3 b;
+	b.origin.x = (g.boundsMin[0] + g.boundsMax[0]) * 0.5f;
+	b.origin.y = (g.boundsMin[1] + g.boundsMax[1]) * 0.5f;
+	b.origin.z = (g.boundsMin[2] + g.boundsMax[2]) * 0.5f;
+	b.extent.x = (g.boundsMax[0] - g.boundsMin[0]) * 0.5f + type.comp->cullPadding;
+	b.extent.y = (g.boundsMax[1] - g.boundsMin[1]) * 0.5f + type.comp->cullPadding;
+	b.extent.z = (g.boundsMax[2] - g.boundsMin[2]) * 0.5f + type.comp->cullPadding;
+	if (type.comp->localSpace) b = transformBounds(E.boundsToWorld, b);
+	return b;
+}
+
+void ParticleSystem::renderMain(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, SprRenderOutput &out)
+{
+	uint32_t frameParticlesLeft = ctx->maxParticlesPerFrame;              // :827
+	bufferFrameIndex++;                                                   // :831
+	const uint64_t frame = bufferFrameIndex;
+
+	std::vector<uint32_t> globals(numVisible);
+	for (uint32_t i = 0; i < numVisible; i++) globals[i] = effects[visibleIds[i]].global;
+	std::vector<RenderGather> got(numVisible);
+	ctx->gatherEffects(globals.data(), numVisible, got.data());
+
+	std::vector<SortedEffect> sorted;
+	std::vector<uint32_t> sortedCount;
+	std::unordered_map<uint32_t, uint32_t> countOf;
+	for (uint32_t i = 0; i < numVisible; i++) {                           // :835-846
+		uint32_t effectId = visibleIds[i];
+		const HostEffect &E = effects[effectId];
+		const HostType &type = types[E.typeId];
+		uint32_t numParticles = got[i].aliveCount;
+		if (numParticles == 0) continue;
+		if (!frustumIntersects(args.frustum, boundsFromGather(got[i], type, E))) continue;
+		SortedEffect s;
+		s.renderOrder = type.renderOrder;
+		s.tiebreaker = type.tiebreaker;
+		float dx = args.cameraPosition.x - E.origin.x, dy = args.cameraPosition.y - E.origin.y, dz = args.cameraPosition.z - E.origin.z;
+		s.depth = dx*dx + dy*dy + dz*dz;                                  // sf::lengthSq, :844
+		s.effectId = effectId;
+		sorted.push_back(s);
+		countOf[effectId] = numParticles;
+	}
+	std::sort(sorted.begin(), sorted.end());                              // :848 (strict total order)
+
+	drawRecords.clear();
+	uint32_t prevTypeId = ~0u;
+	for (const SortedEffect &s : sorted) {                                // :851-902
+		HostEffect &E = effects[s.effectId];
+		const HostType &type = types[E.typeId];
+		uint32_t numParticles = countOf[s.effectId];
+		if (frame - E.uploadFrameIndex >= ctx->maxParticleCacheFrames) {  // :861-867
+			if (numParticles >= frameParticlesLeft) break;               // `return`, :862
+			frameParticlesLeft -= numParticles;
+			E.uploadFrameIndex = frame;
+		}
+		SprDrawRecord r;
+		memset(&r, 0, sizeof(r));
+		r.effectId = s.effectId;
+		r.typeId = E.typeId;
+		r.numParticles = numParticles;
+		r.vertexByteOffset = (uint64_t)ctx->hParams[E.global].slotBase * 128ull;
+		writeColMajor44(E.particlesToWorld, r.instanceUbo.u_ParticleToWorld); // :871-876
+		memcpy(r.instanceUbo.u_WorldToClip, args.worldToClip.v, sizeof(float) * 16);
+		r.instanceUbo.u_Aspect = args.viewToClip.v[0] / args.viewToClip.v[5];
+		r.instanceUbo.u_InvDelta = E.timeStep - E.timeDelta;
+		r.instanceUbo.u_VisFogMad = args.visFogWorldMad;
+		if (E.typeId != prevTypeId) { r.typeUboChanged = 1; prevTypeId = E.typeId; } // :880-883
+		(void)type;
+		drawRecords.push_back(r);
+	}
+	out.deviceVertices = (const SprGpuParticle*)ctx->dVertices;
+	out.records = drawRecords.data();
+	out.numRecords = (uint32_t)drawRecords.size();
+	out.numSortedEffects = (uint32_t)sorted.size();
+}
+
+} // namespace spr

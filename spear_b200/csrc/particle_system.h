@@ -1,0 +1,208 @@
+// particle_system.h -- C++ host layer of the B200 particle path.
+//
+// spr::ParticleSystem mirrors the reference's operator interface
+// (cl::ParticleSystem, src/client/ParticleSystem.h:9-22; implementation
+// ParticleSystemImp, src/client/ParticleSystem.cpp:148-905): same entry points,
+// same argument meaning, same id recycling, same (absent) error behaviour.
+// spr::Context owns everything that lives on one GPU: the slot pool, the effect /
+// type / system tables and the stream; any number of systems share one context so
+// that a frame over thousands of independent systems is ONE set of kernel launches.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/spear_particles.h"
+#include "device_types.h"
+#include "host_math.h"
+#include "kernels.h"
+
+namespace spr {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define SPR_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) throw spr::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <typename T>
+struct DeviceArray {
+	T *ptr = nullptr;
+	size_t capacity = 0;
+	~DeviceArray() { if (ptr) cudaFree(ptr); }
+	// grow to at least n elements keeping the first `keep` elements; new tail zero-filled
+	void reserve(size_t n, size_t keep, cudaStream_t st, int fillByte = 0) {
+		if (n <= capacity) return;
+		size_t cap = capacity ? capacity : 64;
+		while (cap < n) cap *= 2;
+		T *p = nullptr;
+		SPR_CUDA(cudaMalloc(&p, cap * sizeof(T)));
+		if (keep) SPR_CUDA(cudaMemcpyAsync(p, ptr, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+		SPR_CUDA(cudaMemsetAsync(p + keep, fillByte, (cap - keep) * sizeof(T), st));
+		if (ptr) { SPR_CUDA(cudaStreamSynchronize(st)); cudaFree(ptr); }
+		ptr = p; capacity = cap;
+	}
+};
+
+template <typename T>
+struct PinnedArray {
+	T *ptr = nullptr;
+	size_t capacity = 0;
+	~PinnedArray() { if (ptr) cudaFreeHost(ptr); }
+	void reserve(size_t n) {
+		if (n <= capacity) return;
+		size_t cap = capacity ? capacity : 64;
+		while (cap < n) cap *= 2;
+		if (ptr) cudaFreeHost(ptr);
+		SPR_CUDA(cudaMallocHost(&ptr, cap * sizeof(T)));
+		capacity = cap;
+	}
+};
+
+// Host mirror of one effect (ParticleSystemImp::Effect, ParticleSystem.cpp:186-218).
+struct HostEffect {
+	bool inUse = false;
+	uint32_t typeId = 0;          // system-local
+	uint32_t global = 0;          // context-wide effect index
+	SprVec3 origin = { 0, 0, 0 };
+	float timeDelta = 0.0f;
+	float timeStep = 0.0f;
+	double lastUpdateTime = 0.0;
+	SprMat34 particlesToWorld;
+	bool hostStopEmit = false;
+	bool firstEmit = true;        // host view: no sub-step simulated yet
+	bool instantDelete = false;
+	uint64_t simSteps = 0;
+	uint32_t slotUpperBound = 0;  // conservative bound of particles.size*4
+	uint64_t uploadFrameIndex = 16;
+	SprMat34 boundsToWorld;       // particlesToWorld at the last simulated step (gpuBounds, :675-677)
+};
+
+struct HostType {
+	const SprParticleSystemComponent *comp = nullptr; // pointer identity is the key (:30-41)
+	uint32_t refCount = 0;
+	uint32_t global = 0;          // context-wide type index
+	double renderOrder = 0.0;
+	uint32_t tiebreaker = 0;
+	float timeStep = 0.0f;
+	SprVertexTypeUbo typeUbo;
+	uint8_t lut[SPR_SPLINE_LUT_BYTES];
+};
+
+struct Context;
+
+struct ParticleSystem {
+	Context *ctx;
+	uint32_t systemIdx;           // context-wide
+	HostRng initRng;              // :250
+	std::vector<HostEffect> effects;          // :241
+	std::vector<uint32_t> freeEffectIds;      // :242
+	std::vector<HostType> types;              // :244
+	std::vector<uint32_t> freeTypeIds;        // :245
+	std::unordered_map<const void*, uint32_t> componentToType; // :246
+	uint64_t bufferFrameIndex;                // :263
+	std::vector<SprDrawRecord> drawRecords;
+
+	ParticleSystem(Context *ctx, const SprSystemsDesc &desc); // :265-267
+	~ParticleSystem();
+
+	uint32_t reserveEffectType(const SprParticleSystemComponent *c);   // :696-720
+	void releaseEffectType(const SprParticleSystemComponent *c);       // :722-728
+	uint32_t addEffect(uint32_t entityId, uint8_t componentIndex, const SprParticleSystemComponent *c, const SprTransform &transform); // :730-766
+	void updateTransform(uint32_t effectId, const SprTransformUpdate &update); // :768-784
+	bool prepareForRemove(uint32_t effectId, const SprFrameArgs &args);        // :786-794
+	void remove(uint32_t effectId);                                            // :796-806
+	void updateParticles(const uint32_t *activeIds, uint32_t numActive, const SprFrameArgs &args); // :808-822
+	void renderMain(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, SprRenderOutput &out); // :824-903
+
+	void releaseEffectTypeImp(uint32_t typeId);                        // :682-692
+};
+
+SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const HostEffect &E); // gpuBounds, :672-677
+
+struct UpdateRequest {
+	ParticleSystem *system;
+	const uint32_t *activeIds;
+	uint32_t numActive;
+	const SprFrameArgs *args;
+};
+
+struct Context {
+	int device = 0;
+	uint32_t flags = 0;
+	uint32_t maxParticlesPerFrame = 4096;
+	uint32_t maxParticleCacheFrames = 16;
+	cudaStream_t stream = nullptr;
+	bool ownStream = false;
+	uint32_t numSms = 148;
+	uint64_t launchCount = 0;
+
+	// ---- slot pool
+	uint64_t poolCapacity = 0;     // slots
+	uint64_t poolUsed = 0;         // bump pointer
+	float4 *dSlotState = nullptr;
+	uint32_t *dFreeStack = nullptr;
+	float4 *dVertices = nullptr;
+	uint32_t *dKeys[2] = { nullptr, nullptr };
+	uint32_t *dVals[2] = { nullptr, nullptr };
+	uint32_t *dGranuleOwner = nullptr;
+	unsigned long long *dTileStatus[2] = { nullptr, nullptr };
+	std::vector<std::vector<uint32_t>> freeRanges; // per log2(capacity): free slotBase values
+
+	// ---- tables
+	DeviceArray<EffectParams> dParams;
+	DeviceArray<EffectState> dState;
+	DeviceArray<uint32_t> dEffectStamp, dEffectPlanBase, dEffectNumSubsteps;
+	DeviceArray<TypeDev> dTypes;
+	DeviceArray<SystemDev> dSystems;
+	DeviceArray<PlanRec> dPlans;
+	std::vector<EffectParams> hParams;    // host copy, indexed by global effect index
+	std::vector<uint8_t> effectInUse;
+	std::vector<uint32_t> freeEffectGlobals, freeTypeGlobals, freeSystemGlobals;
+	uint32_t numEffectGlobals = 0, numTypeGlobals = 0, numSystemGlobals = 0;
+
+	// ---- pending uploads (applied at the next submit / read-back)
+	std::vector<uint32_t> dirtyParams;        // global effect indices
+	std::vector<uint8_t> dirtyParamsFlag;
+	std::vector<uint32_t> initStateIdx; std::vector<EffectState> initStateVal;
+	std::vector<uint32_t> typeIdx; std::vector<TypeDev> typeVal;
+	std::vector<uint32_t> systemIdx; std::vector<SystemDev> systemVal;
+	std::vector<FillJob> ownerJobs;
+
+	// ---- per-frame staging
+	PinnedArray<uint8_t> stagingH[2];
+	DeviceArray<uint8_t> stagingD;
+	cudaEvent_t stagingEvent[2] = { nullptr, nullptr };
+	int stagingParity = 0;
+	PinnedArray<RenderGather> gatherH;
+	DeviceArray<RenderGather> gatherD;
+	DeviceArray<uint32_t> gatherIdxD;
+	uint32_t frameStamp = 0;
+	uint32_t epoch = 0;
+
+	// ---- sort scratch
+	DeviceArray<uint32_t> dSortHist, dSortLookback;
+	DeviceArray<uint64_t> dRunOffsets;
+
+	explicit Context(const SprContextDesc &desc);
+	~Context();
+
+	PoolPtrs poolPtrs() const;
+	TablePtrs tablePtrs();
+
+	uint32_t allocEffectGlobal();
+	uint32_t allocRange(uint32_t capacity);
+	void freeRange(uint32_t slotBase, uint32_t capacity);
+	void ensurePool(uint64_t slots);
+	void markParamsDirty(uint32_t g);
+	void flushUploads();
+	void update(const UpdateRequest *reqs, uint32_t numReqs);
+	void gatherEffects(const uint32_t *globals, uint32_t n, RenderGather *out); // synchronous read-back
+	void growEffect(uint32_t g, uint32_t minCapacity, bool copyContents);
+	void sync() { SPR_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+} // namespace spr

@@ -1,0 +1,235 @@
+// sort.cu -- segmented, stable LSD radix sort of the per-effect (depth key, slot) pairs
+// (one segment per effect, 8-bit digits, onesweep-style chained scan per digit) and the
+// 4x vertex expansion in sorted order.
+//
+// Extension row A11/K4 of SURVEY.md: the reference sorts effects, not particles; the
+// per-particle order follows the BillboardOrder idiom (src/client/BillboardSystem.cpp:41-51):
+// depth descending (back to front), ties by ascending slot. The keys were written by
+// k_integrate in ascending slot order as ~enc(depth), so a STABLE ascending sort gives
+// exactly that order.
+//
+//   k_sort_hist    per tile: digit histograms of all four passes (keys read once)
+//   k_sort_scan    per (segment, pass): exclusive scan of the 256 bins -> digit bases
+//   k_sort_pass    x4: rank keys inside a 4096-key tile (warp match ranking, stable),
+//                  chained look-back per digit across the tiles of the segment,
+//                  stage the tile in shared memory in sorted order, coalesced scatter
+//   k_expand_sorted  rank r -> slot -> 32-byte record -> 4 x 32 B at rank r (:607-665)
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace spr {
+
+#define FULL_MASK 0xffffffffu
+
+static const uint32_t kSortThreads = 256;
+static const uint32_t kItemsPerThread = kSortTileKeys / kSortThreads; // 16
+static const uint32_t kWarpKeys = kSortTileKeys / 8;                  // 512 keys per warp
+
+__global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t *hist)
+{
+	__shared__ uint32_t sHist[4 * 256];
+	SortTile st = tiles[blockIdx.x];
+	uint32_t g = segEffects[st.effect];
+	uint32_t alive = tab.state[g].aliveCount;
+	uint32_t begin = st.tile * kSortTileKeys;
+	if (begin >= alive) return;
+	uint32_t count = min(kSortTileKeys, alive - begin);
+	for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) sHist[i] = 0;
+	__syncthreads();
+	const uint32_t *keys = pool.keys + tab.params[g].slotBase + begin;
+	for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+		uint32_t k = keys[i];
+		atomicAdd(&sHist[0 * 256 + (k & 255u)], 1u);
+		atomicAdd(&sHist[1 * 256 + ((k >> 8) & 255u)], 1u);
+		atomicAdd(&sHist[2 * 256 + ((k >> 16) & 255u)], 1u);
+		atomicAdd(&sHist[3 * 256 + (k >> 24)], 1u);
+	}
+	__syncthreads();
+	uint32_t *dst = hist + (size_t)st.effect * 1024;
+	for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) {
+		uint32_t v = sHist[i];
+		if (v) atomicAdd(&dst[i], v);
+	}
+}
+
+// one warp per (segment, pass)
+__global__ void k_sort_scan(uint32_t *hist, uint32_t numRows)
+{
+	uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (row >= numRows) return;
+	uint32_t *h = hist + (size_t)row * 256;
+	uint32_t v[8], sum = 0;
+#pragma unroll
+	for (int i = 0; i < 8; i++) { v[i] = h[lane * 8 + i]; sum += v[i]; }
+	uint32_t incl = sum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += o; }
+	uint32_t run = incl - sum;
+#pragma unroll
+	for (int i = 0; i < 8; i++) { h[lane * 8 + i] = run; run += v[i]; }
+}
+
+__device__ inline uint32_t ld_relaxed_u32(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ inline void st_relaxed_u32(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// One radix pass over digit `shift/8`. lookback: [numTiles][256] status words of THIS pass,
+// zero-initialised; word = [31:30] flag (1 aggregate, 2 inclusive prefix), [29:0] count.
+__global__ void __launch_bounds__(256) k_sort_pass(TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
+	const uint32_t *keysIn, const uint32_t *valsIn, uint32_t *keysOut, uint32_t *valsOut,
+	const uint32_t *hist, uint32_t *lookback, uint32_t pass)
+{
+	__shared__ uint32_t sKeys[kSortTileKeys];
+	__shared__ uint32_t sVals[kSortTileKeys];
+	__shared__ uint32_t sCnt[8 * 256];      // per-warp digit counts -> per-warp exclusive offsets
+	__shared__ uint32_t sTileExcl[256];     // exclusive scan of the tile's digit counts
+	__shared__ int32_t sGlobal[256];        // global position of local index j with digit d: sGlobal[d] + j
+	__shared__ uint32_t sWarpSum[8];
+
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const SortTile st = tiles[blockIdx.x];
+	const uint32_t g = segEffects[st.effect];
+	const uint32_t alive = tab.state[g].aliveCount;
+	const uint32_t begin = st.tile * kSortTileKeys;
+	if (begin >= alive) return;
+	const uint32_t count = min(kSortTileKeys, alive - begin);
+	const uint32_t segBase = tab.params[g].slotBase;
+	const uint32_t shift = pass * 8;
+
+	for (uint32_t i = tid; i < 8 * 256; i += kSortThreads) sCnt[i] = 0;
+	__syncthreads();
+
+	// ---- load (warp-striped: warp w owns keys [w*512, w*512+512) of the tile) and rank
+	uint32_t key[kItemsPerThread], val[kItemsPerThread], rank[kItemsPerThread];
+	const uint32_t *kin = keysIn + segBase + begin;
+	const uint32_t *vin = valsIn + segBase + begin;
+#pragma unroll
+	for (uint32_t i = 0; i < kItemsPerThread; i++) {
+		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
+		bool ok = idx < count;
+		key[i] = ok ? kin[idx] : 0xffffffffu;
+		val[i] = ok ? vin[idx] : 0u;
+	}
+	uint32_t *cnt = sCnt + warp * 256;
+#pragma unroll
+	for (uint32_t i = 0; i < kItemsPerThread; i++) {
+		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
+		bool ok = idx < count;
+		uint32_t d = ok ? ((key[i] >> shift) & 255u) : 256u; // padding lanes form their own group
+		uint32_t peers = __match_any_sync(FULL_MASK, d);
+		uint32_t before = ok ? cnt[d] : 0u;
+		__syncwarp();
+		rank[i] = before + __popc(peers & ((1u << lane) - 1u));
+		if (ok && (peers & ((1u << lane) - 1u)) == 0) cnt[d] = before + __popc(peers);
+		__syncwarp();
+	}
+	__syncthreads();
+
+	// ---- thread d: per-warp exclusive offsets of digit d, tile count, chained look-back
+	uint32_t total = 0;
+#pragma unroll
+	for (uint32_t w = 0; w < 8; w++) { uint32_t c = sCnt[w * 256 + tid]; sCnt[w * 256 + tid] = total; total += c; }
+	uint32_t *lb = lookback + (size_t)blockIdx.x * 256 + tid;
+	uint32_t excl = 0;
+	if (st.tile == 0) {
+		st_relaxed_u32(lb, (2u << 30) | total);
+	} else {
+		st_relaxed_u32(lb, (1u << 30) | total);
+		const uint32_t *p = lb - 256; // tiles of one segment are consecutive in the tile table
+		for (uint32_t t = st.tile; t > 0; t--, p -= 256) {
+			uint32_t v;
+			do { v = ld_relaxed_u32(p); } while ((v >> 30) == 0);
+			excl += v & 0x3fffffffu;
+			if ((v >> 30) == 2u) break;
+		}
+		st_relaxed_u32(lb, (2u << 30) | (excl + total));
+	}
+	// exclusive scan of the 256 digit counts of the tile
+	uint32_t incl = total;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += o; }
+	if (lane == 31) sWarpSum[warp] = incl;
+	__syncthreads();
+	uint32_t warpBase = 0;
+#pragma unroll
+	for (uint32_t w = 0; w < 8; w++) if (w < warp) warpBase += sWarpSum[w];
+	uint32_t tileExcl = warpBase + incl - total;
+	sTileExcl[tid] = tileExcl;
+	sGlobal[tid] = (int32_t)(hist[((size_t)st.effect * 4 + pass) * 256 + tid] + excl) - (int32_t)tileExcl;
+	__syncthreads();
+
+	// ---- stage the tile in sorted order
+#pragma unroll
+	for (uint32_t i = 0; i < kItemsPerThread; i++) {
+		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
+		if (idx < count) {
+			uint32_t d = (key[i] >> shift) & 255u;
+			uint32_t pos = sTileExcl[d] + sCnt[warp * 256 + d] + rank[i];
+			sKeys[pos] = key[i];
+			sVals[pos] = val[i];
+		}
+	}
+	__syncthreads();
+
+	// ---- scatter: consecutive threads write consecutive addresses inside each digit run
+	uint32_t *kout = keysOut + segBase;
+	uint32_t *vout = valsOut + segBase;
+	for (uint32_t j = tid; j < count; j += kSortThreads) {
+		uint32_t k = sKeys[j];
+		uint32_t d = (k >> shift) & 255u;
+		uint32_t dst = (uint32_t)(sGlobal[d] + (int32_t)j);
+		kout[dst] = k;
+		vout[dst] = sVals[j];
+	}
+}
+
+// 8 lanes per particle: each lane moves one float4, a warp store covers 512 contiguous bytes.
+__global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles)
+{
+	SortTile st = tiles[blockIdx.x];
+	uint32_t g = segEffects[st.effect];
+	uint32_t alive = tab.state[g].aliveCount;
+	uint32_t begin = st.tile * kSortTileKeys;
+	if (begin >= alive) return;
+	uint32_t count = min(kSortTileKeys, alive - begin);
+	uint32_t segBase = tab.params[g].slotBase;
+	const uint32_t *vals = pool.vals + segBase + begin;
+	float4 *dst = pool.vertices + 8ull * (segBase + begin);
+	uint32_t totalQ = count * 8;
+	for (uint32_t q = threadIdx.x; q < totalQ; q += blockDim.x) {
+		uint32_t slot = vals[q >> 3];
+		dst[q] = pool.state[2ull * (segBase + slot) + (q & 1u)];
+	}
+}
+
+uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &sc,
+	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles)
+{
+	if (!numSegments || !numTiles) return 0;
+	cudaMemsetAsync(sc.hist, 0, (size_t)numSegments * 1024 * sizeof(uint32_t), st);
+	cudaMemsetAsync(sc.lookback, 0, (size_t)numTiles * 4 * 256 * sizeof(uint32_t), st);
+	k_sort_hist<<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, sc.hist);
+	uint32_t rows = numSegments * 4;
+	k_sort_scan<<<(rows * 32 + 255) / 256, 256, 0, st>>>(sc.hist, rows);
+	uint32_t *kbuf[2] = { pool.keys, sc.keysAlt };
+	uint32_t *vbuf[2] = { pool.vals, sc.valsAlt };
+	for (uint32_t p = 0; p < 4; p++) {
+		k_sort_pass<<<numTiles, 256, 0, st>>>(tab, segEffects, tiles, kbuf[p & 1], vbuf[p & 1], kbuf[(p & 1) ^ 1], vbuf[(p & 1) ^ 1],
+			sc.hist, sc.lookback + (size_t)p * numTiles * 256, p);
+	}
+	k_expand_sorted<<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles);
+	return 7;
+}
+
+} // namespace spr

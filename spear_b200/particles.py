@@ -1,0 +1,269 @@
+"""ctypes binding of include/spear_particles.h (the reference-facing plugin API).
+
+ParticleSystem mirrors cl::ParticleSystem (src/client/ParticleSystem.h:9-22) method for
+method; ParticleContext is the per-GPU owner (device, stream, slot pool). Everything
+here calls straight into libspear_particles.so -- if the library is missing this
+module raises ImportError rather than falling back to anything.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspear_particles.so")
+
+GPU_PARTICLE_DTYPE = np.dtype([("pos", "<f4", 3), ("life", "<f4"), ("vel", "<f4", 3), ("seed", "<f4")])
+
+EXPORTS = [
+    "sprComponentDefaults", "sprGetLastError", "sprContextCreate", "sprContextDestroy", "sprContextSynchronize",
+    "sprContextStream", "sprContextLaunchCount", "sprSystemCreate", "sprSystemDestroy", "sprReserveEffectType",
+    "sprReleaseEffectType", "sprAddEffect", "sprUpdateTransform", "sprPrepareForRemove", "sprRemoveEffect",
+    "sprUpdateParticles", "sprUpdateParticlesBatch", "sprRenderMain", "sprGetEffectInfo", "sprReadFreeIndices",
+    "sprReadVertexStream", "sprReadSlots", "sprReadStreamSlots", "sprGetRngState", "sprGetEffectTypeLut",
+    "sprGetEffectTypeUbo", "sprGetEffectDeviceView", "sprPackRuns", "sprExpandRuns",
+]
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "spear_b200: %s is not built (run `python spear_b200/build.py`); there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    P = C.POINTER
+    lib.sprGetLastError.restype = C.c_char_p
+    lib.sprComponentDefaults.argtypes = [P(abi.ParticleSystemComponent)]
+    lib.sprContextCreate.argtypes = [P(abi.ContextDesc), P(vp)]
+    lib.sprContextDestroy.argtypes = [vp]
+    lib.sprContextSynchronize.argtypes = [vp]
+    lib.sprContextStream.restype = vp
+    lib.sprContextStream.argtypes = [vp]
+    lib.sprContextLaunchCount.restype = u64
+    lib.sprContextLaunchCount.argtypes = [vp]
+    lib.sprSystemCreate.argtypes = [vp, P(abi.SystemsDesc), P(vp)]
+    lib.sprSystemDestroy.argtypes = [vp]
+    lib.sprReserveEffectType.argtypes = [vp, P(abi.ParticleSystemComponent), P(u32)]
+    lib.sprReleaseEffectType.argtypes = [vp, P(abi.ParticleSystemComponent)]
+    lib.sprAddEffect.argtypes = [vp, u32, C.c_uint8, P(abi.ParticleSystemComponent), P(abi.Transform), P(u32)]
+    lib.sprUpdateTransform.argtypes = [vp, u32, P(abi.TransformUpdate)]
+    lib.sprPrepareForRemove.argtypes = [vp, u32, P(abi.FrameArgs), P(C.c_int)]
+    lib.sprRemoveEffect.argtypes = [vp, u32]
+    lib.sprUpdateParticles.argtypes = [vp, P(u32), u32, P(abi.FrameArgs)]
+    lib.sprUpdateParticlesBatch.argtypes = [vp, P(vp), u32, P(P(u32)), P(u32), P(abi.FrameArgs), C.c_size_t]
+    lib.sprRenderMain.argtypes = [vp, P(u32), u32, P(abi.RenderArgs), P(abi.RenderOutput)]
+    lib.sprGetEffectInfo.argtypes = [vp, u32, P(abi.EffectInfo)]
+    lib.sprReadFreeIndices.argtypes = [vp, u32, vp, u32, P(u32)]
+    lib.sprReadVertexStream.argtypes = [vp, u32, vp, u32, P(u32)]
+    lib.sprReadSlots.argtypes = [vp, u32, vp, u32, P(u32)]
+    lib.sprReadStreamSlots.argtypes = [vp, u32, vp, u32, P(u32)]
+    lib.sprGetRngState.argtypes = [vp, P(u64)]
+    lib.sprGetEffectTypeLut.argtypes = [vp, u32, vp]
+    lib.sprGetEffectTypeUbo.argtypes = [vp, u32, P(abi.VertexTypeUbo)]
+    lib.sprGetEffectDeviceView.argtypes = [vp, u32, P(abi.EffectDeviceView)]
+    lib.sprPackRuns.argtypes = [vp, P(vp), P(u32), u32, vp, u64, vp, P(u64)]
+    lib.sprExpandRuns.argtypes = [vp, vp, u64, vp]
+    return lib
+
+
+lib = _load()
+
+
+class SpearError(RuntimeError):
+    pass
+
+
+def _check(status):
+    if status != 0:
+        raise SpearError("spear_particles status %d: %s" % (status, lib.sprGetLastError().decode()))
+
+
+def _ids(ids):
+    arr = np.ascontiguousarray(ids, dtype=np.uint32)
+    return arr, arr.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+class ParticleContext:
+    """One GPU: device, stream, slot pool, tables (SprContext)."""
+
+    def __init__(self, device=0, sort_particles=False, max_particles_per_frame=0, max_cache_frames=0,
+                 initial_slot_capacity=0, stream=None):
+        desc = abi.ContextDesc()
+        desc.device = device
+        desc.flags = abi.CTX_SORT_PARTICLES if sort_particles else 0
+        desc.maxParticlesPerFrame = max_particles_per_frame
+        desc.maxParticleCacheFrames = max_cache_frames
+        desc.initialSlotCapacity = initial_slot_capacity
+        desc.stream = stream
+        self.h = C.c_void_p()
+        _check(lib.sprContextCreate(C.byref(desc), C.byref(self.h)))
+        self.systems = []
+
+    def close(self):
+        if self.h:
+            for s in list(self.systems):
+                s.close()
+            lib.sprContextDestroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(lib.sprContextSynchronize(self.h))
+
+    @property
+    def stream(self):
+        return lib.sprContextStream(self.h)
+
+    @property
+    def launch_count(self):
+        return int(lib.sprContextLaunchCount(self.h))
+
+    def create_system(self, seed=(1, 2, 3, 4)):
+        return ParticleSystem(self, seed)
+
+    def update_batch(self, systems, id_lists, frame_args):
+        """sprUpdateParticlesBatch: one set of launches for many systems (shared FrameArgs)."""
+        n = len(systems)
+        handles = (C.c_void_p * n)(*[s.h for s in systems])
+        arrs = [np.ascontiguousarray(ids, dtype=np.uint32) for ids in id_lists]
+        ptrs = (C.POINTER(C.c_uint32) * n)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
+        counts = (C.c_uint32 * n)(*[len(a) for a in arrs])
+        _check(lib.sprUpdateParticlesBatch(self.h, handles, n, ptrs, counts, C.byref(frame_args), 0))
+
+    def make_batch(self, systems, id_lists):
+        """Pre-marshalled batch for benchmark loops (no per-step Python marshalling)."""
+        n = len(systems)
+        handles = (C.c_void_p * n)(*[s.h for s in systems])
+        arrs = [np.ascontiguousarray(ids, dtype=np.uint32) for ids in id_lists]
+        ptrs = (C.POINTER(C.c_uint32) * n)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
+        counts = (C.c_uint32 * n)(*[len(a) for a in arrs])
+        return (handles, ptrs, counts, n, arrs)
+
+    def update_prepared(self, batch, frame_args):
+        handles, ptrs, counts, n, _ = batch
+        _check(lib.sprUpdateParticlesBatch(self.h, handles, n, ptrs, counts, C.byref(frame_args), 0))
+
+    def pack_runs(self, systems, effect_ids, device_out, capacity_records, device_counts=None, want_total=True):
+        n = len(systems)
+        handles = (C.c_void_p * n)(*[s.h for s in systems])
+        arr, p = _ids(effect_ids)
+        total = C.c_uint64(0)
+        _check(lib.sprPackRuns(self.h, handles, p, n, device_out, capacity_records, device_counts,
+                               C.byref(total) if want_total else None))
+        return total.value
+
+    def expand_runs(self, device_records, num_records, device_vertices_out):
+        _check(lib.sprExpandRuns(self.h, device_records, num_records, device_vertices_out))
+
+
+class ParticleSystem:
+    """cl::ParticleSystem over the C ABI (same calls as oracle.orc.OracleSystem)."""
+
+    def __init__(self, ctx, seed=(1, 2, 3, 4)):
+        self.ctx = ctx
+        desc = abi.make_systems_desc(seed)
+        self.h = C.c_void_p()
+        _check(lib.sprSystemCreate(ctx.h, C.byref(desc), C.byref(self.h)))
+        ctx.systems.append(self)
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            lib.sprSystemDestroy(self.h)
+            self.h = None
+            if self in self.ctx.systems:
+                self.ctx.systems.remove(self)
+
+    def reserve_type(self, comp):
+        self._keep.append(comp)
+        t = C.c_uint32()
+        _check(lib.sprReserveEffectType(self.h, C.byref(comp), C.byref(t)))
+        return t.value
+
+    def release_type(self, comp):
+        _check(lib.sprReleaseEffectType(self.h, C.byref(comp)))
+
+    def add_effect(self, comp, transform=None, entity_id=0, component_index=0):
+        self._keep.append(comp)
+        t = transform if transform is not None else abi.make_transform()
+        e = C.c_uint32()
+        _check(lib.sprAddEffect(self.h, entity_id, component_index, C.byref(comp), C.byref(t), C.byref(e)))
+        return e.value
+
+    def update_transform(self, effect_id, update):
+        _check(lib.sprUpdateTransform(self.h, effect_id, C.byref(update)))
+
+    def prepare_for_remove(self, effect_id, frame_args):
+        r = C.c_int()
+        _check(lib.sprPrepareForRemove(self.h, effect_id, C.byref(frame_args), C.byref(r)))
+        return bool(r.value)
+
+    def remove(self, effect_id):
+        _check(lib.sprRemoveEffect(self.h, effect_id))
+
+    def update(self, ids, frame_args):
+        arr, p = _ids(ids)
+        _check(lib.sprUpdateParticles(self.h, p, len(arr), C.byref(frame_args)))
+
+    def render(self, ids, render_args, capacity=None):
+        arr, p = _ids(ids)
+        out = abi.RenderOutput()
+        _check(lib.sprRenderMain(self.h, p, len(arr), C.byref(render_args), C.byref(out)))
+        recs = []
+        for i in range(out.numRecords):
+            r = abi.DrawRecord()
+            C.memmove(C.byref(r), C.byref(out.records[i]), C.sizeof(abi.DrawRecord))
+            recs.append(r)
+        self.last_device_vertices = out.deviceVertices
+        return recs, out.numSortedEffects
+
+    def effect_info(self, effect_id):
+        info = abi.EffectInfo()
+        _check(lib.sprGetEffectInfo(self.h, effect_id, C.byref(info)))
+        return info
+
+    def _read(self, fn, effect_id, dtype):
+        n = C.c_uint32()
+        _check(fn(self.h, effect_id, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=dtype)
+        _check(fn(self.h, effect_id, out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value]
+
+    def read_free(self, effect_id):
+        return self._read(lib.sprReadFreeIndices, effect_id, np.uint32)
+
+    def read_stream(self, effect_id):
+        return self._read(lib.sprReadVertexStream, effect_id, GPU_PARTICLE_DTYPE)
+
+    def read_slots(self, effect_id):
+        return self._read(lib.sprReadSlots, effect_id, GPU_PARTICLE_DTYPE)
+
+    def read_stream_slots(self, effect_id):
+        return self._read(lib.sprReadStreamSlots, effect_id, np.uint32)
+
+    def rng_state(self):
+        out = (C.c_uint64 * 2)()
+        _check(lib.sprGetRngState(self.h, out))
+        return int(out[0]), int(out[1])
+
+    def type_lut(self, type_id):
+        out = np.zeros(abi.SPLINE_LUT_BYTES, dtype=np.uint8)
+        _check(lib.sprGetEffectTypeLut(self.h, type_id, out.ctypes.data))
+        return out
+
+    def type_ubo(self, type_id):
+        out = abi.VertexTypeUbo()
+        _check(lib.sprGetEffectTypeUbo(self.h, type_id, C.byref(out)))
+        return out
+
+    def device_view(self, effect_id):
+        v = abi.EffectDeviceView()
+        _check(lib.sprGetEffectDeviceView(self.h, effect_id, C.byref(v)))
+        return v
