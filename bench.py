@@ -1,0 +1,472 @@
+#!/usr/bin/env python3
+"""bench.py -- particle-steps/s of the update + sort + billboard step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4]
+
+One "step" = one pass of the hot path over every particle of the workload:
+sprUpdateParticles[Batch] = plan + emit + integrate/compact/depth-key + segmented radix
+sort + 4x vertex expansion (sort mode on), through the C ABI of include/spear_particles.h.
+
+Workloads:
+  c3  (default at N=1)  BASELINE configs[2]: one effect, 10M live particles -- the configuration
+                        north_star quotes the 70 %-of-HBM-roofline target on.
+  c2                    BASELINE configs[1]: 64 emitters x 16k particles, 4 effect types.
+  c4  (default at N>1)  BASELINE configs[3]: 1024 independent instances (64M particles) at 8 GPUs =
+                        128 instances x 65536 particles per GPU (weak scaling: per-GPU work fixed).
+                        `value` = shard compute only (no data-path collective); the NCCL all-gather of
+                        the sorted 32-byte runs + 4x expansion after the gather is timed separately
+                        and reported under "gather".
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, built from the
+reference sources; falls back to the plain-C port oracle/libspear_oracle.so) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CAMERA = (16.0, 20.0, -30.0)
+METRIC = "particle-steps/sec (update+sort+billboard)"
+UNIT = "particle-steps/s"
+ALG_BYTES_SORTED = 220.0   # 60 update + 32 re-read in sorted order + 128 vertices
+ALG_BYTES_UNSORTED = 188.0
+# per-kernel algorithmic bytes per particle (DESIGN.md "Kernels"): pairs (key,slot) are excluded by section 8(d)
+KERNEL_ALG_BYTES = {"k_integrate": 60.0, "k_expand_sorted": 160.0, "k_integrate_unsorted": 188.0}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------
+# workload descriptors (shared by both arms)
+# ---------------------------------------------------------------------------
+
+def workload_components(name):
+    from spear_b200 import abi
+    import scenarios as S
+    if name == "c3":
+        comp = abi.make_component(
+            timeStep=1 / 60, burstAmount=10_000_000, spawnTime=1e9, lifeTime=1e9, drag=0.3, gravity=(0, -9.81, 0),
+            emitPosition=dict(boxExtent=(8, 4, 8)), emitVelocity=dict(sphere=dict(minRadius=1, maxRadius=3)),
+            scaleSpline=[(0, 0), (0.3, 1), (1, 0.2)], gradient=dict(points=[(0, (1, 0.5, 0.1)), (1, (0.1, 0.1, 0.1))]))
+        return dict(systems=1, effects=[(comp, abi.make_transform((1, 2, 3)))], particles_per_effect=10_000_000,
+                    desc="C3: 1 effect x 10M particles (BASELINE configs[2]), burst-populated, steady population")
+    if name == "c2":
+        effects = []
+        comps = [S.comp_c2(k, burst=16384) for k in range(4)]
+        for i in range(64):
+            effects.append((comps[i % 4], abi.make_transform((4.0 * (i % 8), 0.0, 4.0 * (i // 8)))))
+        return dict(systems=1, effects=effects, particles_per_effect=16384,
+                    desc="C2: 64 emitters x 16k particles, 4 effect types (BASELINE configs[1])")
+    if name == "c4":
+        comps = [S.comp_c2(k % 4, burst=65536) for k in range(8)]
+        for k in range(4, 8):
+            comps[k].drag = 0.35
+            comps[k].gravity.y = -4.0
+        return dict(systems=128, comps=comps, particles_per_effect=65536,
+                    desc="C4 slice: 128 independent systems x 1 effect x 65536 particles per GPU (BASELINE configs[3] = 1024 instances / 64M at 8 GPUs)")
+    raise SystemExit("unknown workload %s" % name)
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+
+def build_ours(ctx, wl):
+    """Create systems/effects; returns (systems, id lists, dt)."""
+    from spear_b200 import abi
+    systems, ids = [], []
+    if "effects" in wl:
+        s = ctx.create_system((1, 2, 3, 4))
+        my = [s.add_effect(c, t) for c, t in wl["effects"]]
+        systems.append(s); ids.append(my)
+    else:
+        for i in range(wl["systems"]):
+            s = ctx.create_system((1, 2 + i + wl.get("seed_offset", 0), 3, 4))
+            comp = wl["comps"][i % len(wl["comps"])]
+            my = [s.add_effect(comp, abi.make_transform((4.0 * (i % 16), 0.0, 4.0 * (i // 16))))]
+            systems.append(s); ids.append(my)
+    # dt = the largest per-effect timeStep (effects are jittered +0..10 %, ParticleSystem.cpp:744):
+    # every effect does >= 1 sub-step per frame, a few do 2 now and then; particle-steps are counted exactly.
+    dt = max(s.effect_info(e).timeStep for s, my in zip(systems, ids) for e in my)
+    return systems, ids, dt
+
+
+def run_ours(args, rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from spear_b200 import abi, particles
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name = args.workload or ("c3" if world == 1 else "c4")
+    wl = workload_components(name)
+    if name == "c4":
+        wl["seed_offset"] = rank * wl["systems"]
+    total_particles = wl["particles_per_effect"] * (len(wl["effects"]) if "effects" in wl else wl["systems"])
+    ctx = particles.ParticleContext(device=local, sort_particles=not args.no_sort, max_particles_per_frame=1 << 30,
+                                    initial_slot_capacity=int(total_particles * 1.1) + (1 << 16))
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local)
+    systems, ids, dt = build_ours(ctx, wl)
+    batch = ctx.make_batch(systems, ids)
+    all_effects = [(s, e) for s, my in zip(systems, ids) for e in my]
+
+    frame = [0]
+
+    def step():
+        fa = abi.make_frame_args(dt, game_time=frame[0] * dt, frame_index=frame[0], camera=CAMERA)
+        ctx.update_prepared(batch, fa)
+        frame[0] += 1
+
+    def sim_steps():
+        return sum(s.effect_info(e).simSteps for s, e in all_effects)
+
+    def alive():
+        return sum(s.effect_info(e).aliveCount for s, e in all_effects)
+
+    # population: burst step(s), untimed
+    step(); step()
+    ctx.synchronize()
+    for _ in range(args.warmup):
+        step()
+    ctx.synchronize()
+    n_alive = alive()
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    steps0, launches0 = sim_steps(), ctx.launch_count
+    ctx.enable_kernel_timing(True)
+    ctx.kernel_times(reset=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    for _ in range(args.steps):
+        step()
+    ev1.record(ext)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    ktimes = ctx.kernel_times(reset=True)
+    ctx.enable_kernel_timing(False)
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    effect_steps = sim_steps() - steps0
+    # every effect holds a constant population in the timed window; sub-steps are counted exactly
+    particle_steps = 0
+    for s, e in all_effects:
+        pass
+    per_effect_alive = n_alive / len(all_effects)
+    particle_steps = effect_steps * per_effect_alive
+
+    # ---- e2e: the plugin call a user makes, host buffers in, host-visible result out, every step:
+    # sprUpdateParticlesBatch (H2D of the frame's work lists from pinned memory) + sprRenderMain
+    # (D2H of the per-effect counts/bounds, host effect sort, draw records) + synchronise.
+    from tests_render_args import make_render_args  # noqa: E402
+    ra = make_render_args()
+    vis = [np.ascontiguousarray(my, dtype=np.uint32) for my in ids]
+    barrier()
+    e_steps0 = sim_steps()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        for s, v in zip(systems, vis):
+            recs, _ = s.render(v, ra)
+    ctx.synchronize()
+    t1 = time.perf_counter()
+    e2e_ms = (t1 - t0) * 1e3
+    e2e_particle_steps = (sim_steps() - e_steps0) * per_effect_alive
+    n_eff = len(all_effects)
+    h2d = n_eff * 16 + len(systems) * 16 + n_eff * 4  # ActiveEntry + SystemWork per frame, ids for the gather
+    d2h = n_eff * 60                                   # RenderGather per visible effect
+
+    # ---- optional: multi-GPU draw-stream assembly (all-gather of sorted 32-byte runs, expand after)
+    gather = None
+    if world > 1:
+        cap = int(n_alive * 1.02) + 1024
+        mine = torch.empty((cap, 8), dtype=torch.float32, device="cuda")
+        allrec = torch.empty((world * cap, 8), dtype=torch.float32, device="cuda")
+        verts = torch.empty((world * cap * 4, 8), dtype=torch.float32, device="cuda")
+        sys_list = [s for s, e in all_effects]
+        eff_list = [e for s, e in all_effects]
+        with torch.cuda.stream(ext):
+            def gstep():
+                step()
+                ctx.pack_runs(sys_list, eff_list, mine.data_ptr(), cap, None, want_total=False)
+                dist.all_gather_into_tensor(allrec, mine)
+                ctx.expand_runs(allrec.data_ptr(), world * cap, verts.data_ptr())
+            for _ in range(2):
+                gstep()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gs0 = sim_steps()
+            g0.record(ext)
+            for _ in range(args.steps):
+                gstep()
+            g1.record(ext)
+            barrier()
+        gms = g0.elapsed_time(g1)
+        gps = (sim_steps() - gs0) * per_effect_alive
+        gather = {"ms_per_step": gms / args.steps, "particle_steps_this_rank": gps,
+                  "nvlink_bytes_in_per_step": (world - 1) * cap * 32}
+
+    # ---- max over ranks / aggregate
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms, gather["ms_per_step"] * args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, gms_tot = [float(x) for x in t.tolist()]
+        c = torch.tensor([particle_steps, e2e_particle_steps, gather["particle_steps_this_rank"], float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        particle_steps, e2e_particle_steps, g_total_ps, launches_all = [float(x) for x in c.tolist()]
+    else:
+        launches_all = float(launches)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        value = particle_steps / (ms * 1e-3)
+        sorted_mode = not args.no_sort
+        alg = ALG_BYTES_SORTED if sorted_mode else ALG_BYTES_UNSORTED
+        # dominant kernel by measured time
+        kern = {k: {"ms_total": v[0], "launches": v[1]} for k, v in ktimes.items()}
+        tot_k = sum(v["ms_total"] for v in kern.values()) or 1.0
+        alg_key = {"k_integrate": KERNEL_ALG_BYTES["k_integrate"] if sorted_mode else KERNEL_ALG_BYTES["k_integrate_unsorted"],
+                   "k_expand_sorted": KERNEL_ALG_BYTES["k_expand_sorted"]}
+        for k, v in kern.items():
+            v["share"] = v["ms_total"] / tot_k
+            v["ms_per_launch"] = v["ms_total"] / max(v["launches"], 1)
+            if k in alg_key:
+                # particles processed by one launch of this kernel (this rank)
+                per_launch = (particle_steps / world) / max(v["launches"], 1)
+                v["alg_bytes_per_launch"] = alg_key[k] * per_launch
+                v["achieved_gbs"] = v["alg_bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9
+        cand = [k for k in kern if "achieved_gbs" in kern[k]]
+        dom = max(cand, key=lambda k: kern[k]["ms_total"]) if cand else None
+        roof = None
+        if dom:
+            roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_particle": alg_key[dom],
+                    "step": {"alg_bytes_per_particle_step": alg, "achieved": value / world * alg / 1e9,
+                             "frac": value / world * alg / 1e9 / peak,
+                             "note": "whole step per GPU: particle-steps/s x %g B (SURVEY.md 8(d)) / peak" % alg}}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": name, "particles_per_gpu": int(n_alive), "sort": sorted_mode,
+                       "l2": "inputs larger than L2 (state %d MB + vertex stream %d MB per GPU)" % (n_alive * 32 >> 20, n_alive * 128 >> 20)
+                       if n_alive * 160 > 200e6 else "working set %d MB: state is L2-resident, the 128 B/particle vertex stream is not re-read" % (n_alive * 160 >> 20),
+                       "dt": dt, "parallelism": "independent systems sharded per GPU" if world > 1 else "1 GPU"},
+            "e2e": {"value": e2e_particle_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "note": "sprUpdateParticlesBatch + sprRenderMain per step through the C ABI with host id lists in and host draw records out; "
+                            "the vertex stream stays in HBM where the renderer reads it (the reference uploads it with sg_append_buffer)"},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": kern,
+        }
+        if gather is not None:
+            g_val = g_total_ps / (gms_tot * 1e-3)
+            out["gather"] = {"value_with_gather": g_val, "unit": UNIT, "ms_per_step": gms_tot / args.steps,
+                             "nvlink_bytes_in_per_gpu_per_step": gather["nvlink_bytes_in_per_step"],
+                             "nvlink_gbs_in_per_gpu": gather["nvlink_bytes_in_per_step"] / (gms_tot / args.steps * 1e-3) / 1e9,
+                             "note": "step + sprPackRuns (32 B sorted records) + NCCL all_gather + sprExpandRuns (4x) of the whole %d-GPU draw stream on every GPU" % world}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(name, seconds=15.0)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# CPU arms (oracle/_ref = the reference's own code; never the product path)
+# ---------------------------------------------------------------------------
+
+def _cpu_worker(kind, name, idx, steps, warmup, scale, q):
+    from oracle import orc
+    from spear_b200 import abi
+    wl = workload_components(name)
+    if "effects" in wl:
+        o = orc.OracleSystem(kind, (1, 2, 3, 4))
+        effs = wl["effects"]
+        if scale < 1.0 and len(effs) == 1:
+            effs[0][0].burstAmount = int(effs[0][0].burstAmount * scale)
+        ids = [o.add_effect(c, t) for c, t in effs]
+    else:
+        o = orc.OracleSystem(kind, (1, 2 + idx, 3, 4))
+        ids = [o.add_effect(wl["comps"][idx % len(wl["comps"])], abi.make_transform((idx, 0, 0)))]
+    dt = max(o.effect_info(e).timeStep for e in ids)
+    fa = abi.make_frame_args(dt, camera=CAMERA)
+    o.bench_steps(ids, fa, 2 + warmup)          # burst + warm-up, untimed
+    s0 = sum(o.effect_info(e).simSteps for e in ids)
+    secs, _ = o.bench_steps(ids, fa, steps)
+    s1 = sum(o.effect_info(e).simSteps for e in ids)
+    alive = sum(o.effect_info(e).aliveCount for e in ids)
+    q.put((secs, (s1 - s0) * alive / len(ids)))
+
+
+def cpu_run(name, steps, warmup, procs, scale=1.0):
+    import multiprocessing as mp
+    from oracle import orc
+    kind = "reference" if orc.have("reference") else "port"
+    if kind == "port":
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    ctxm = mp.get_context("fork")
+    q = ctxm.Queue()
+    ps = [ctxm.Process(target=_cpu_worker, args=(kind, name, i, steps, warmup, scale, q)) for i in range(procs)]
+    t0 = time.perf_counter()
+    for p in ps:
+        p.start()
+    res = [q.get() for _ in ps]
+    for p in ps:
+        p.join()
+    wall = time.perf_counter() - t0
+    secs = max(r[0] for r in res)
+    total = sum(r[1] for r in res)
+    return kind, total / secs, secs, wall
+
+
+def cpu_baseline(name, seconds=15.0):
+    """Bounded sample of the same workload on the host cores (rank 0, N=1)."""
+    if name == "c3":
+        kind, v, secs, wall = cpu_run("c3", steps=20, warmup=1, procs=1)
+        sample = "the full C3 effect (10M particles) on 1 core: burst + 1 warm-up step untimed, 20 timed steps; the reference has no per-particle sort, so this is update+compact+4x expand"
+        cores = 1
+    elif name == "c2":
+        kind, v, secs, wall = cpu_run("c2", steps=100, warmup=3, procs=1)
+        sample = "the full C2 system (64 x 16k) on 1 core (one system shares one RNG, so it cannot be threaded), 100 timed steps"
+        cores = 1
+    else:
+        cores = os.cpu_count() or 1
+        kind, v, secs, wall = cpu_run("c4", steps=60, warmup=3, procs=cores)
+        sample = "%d of the 128 instances (65536 particles each), one reference system per host core, 60 timed steps" % cores
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "seconds": secs}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    name = args.workload or ("c3" if world == 1 else "c4")
+    wl = workload_components(name)
+    cores_avail = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    if name in ("c3", "c2"):
+        # a single system is single-threaded in the reference (one shared RNG, ParticleSystem.cpp:251)
+        kind, v, secs, wall = cpu_run(name, steps=args.steps, warmup=args.warmup, procs=1)
+        cores = 1
+        sample = "%s on 1 host core (the path is single-threaded per system): %d timed steps after burst + %d warm-up" % (wl["desc"], args.steps, args.warmup)
+    else:
+        cores = cores_avail
+        kind, v, secs, wall = cpu_run(name, steps=args.steps, warmup=args.warmup, procs=cores)
+        sample = "%d instances of %s, one per host core, %d timed steps" % (cores, wl["desc"], args.steps)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": name, "note": "reference CPU ParticleSystem (no per-particle sort exists in the reference: update+compact+4x expand)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4"])
+    ap.add_argument("--no-sort", action="store_true", help="strict drop-in stream (slot order), no per-particle depth sort")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

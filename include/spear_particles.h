@@ -335,6 +335,12 @@ SPR_API const char *sprGetLastError(void);
 /* Number of kernel launches this context has enqueued so far (bench `gpu_launches`). */
 SPR_API uint64_t sprContextLaunchCount(SprContext *ctx);
 
+/* Measurement hooks (no reference counterpart): CUDA events around every kernel launch
+ * of the context, accumulated per kernel name. Used by bench.py for the roofline. */
+SPR_API int sprContextEnableKernelTiming(SprContext *ctx, int enable);
+SPR_API int sprContextGetKernelTimes(SprContext *ctx, int reset, const char **names, double *ms, uint64_t *launches,
+	uint32_t capacity, uint32_t *outCount);
+
 /* ------------------------------------------------------------------------ */
 /* System API == cl::ParticleSystem (src/client/ParticleSystem.h:9-22)         */
 /* ------------------------------------------------------------------------ */
@@ -397,6 +403,11 @@ SPR_API int sprGetRngState(SprSystem *sys, uint64_t outStateInc[2]);
  * gradient texel is never written by the reference (:398-399); this library writes 0. */
 SPR_API int sprGetEffectTypeLut(SprSystem *sys, uint32_t typeId, uint8_t out[SPR_SPLINE_LUT_BYTES]);
 SPR_API int sprGetEffectTypeUbo(SprSystem *sys, uint32_t typeId, SprVertexTypeUbo *out);
+
+/* Host-only type bake (initEffectType, ParticleSystem.cpp:298-450) without a context:
+ * the 512-byte spline/gradient LUT and the 96-byte type UBO for `typeId`. Needs no GPU. */
+SPR_API int sprBakeEffectType(const SprParticleSystemComponent *c, uint32_t typeId,
+	uint8_t outLut[SPR_SPLINE_LUT_BYTES], SprVertexTypeUbo *outUbo);
 
 /* Device pointers for zero-copy consumers (benchmarks, the multi-GPU gather). */
 typedef struct SprEffectDeviceView {

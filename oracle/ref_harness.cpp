@@ -525,6 +525,7 @@ double orc_bench_steps(void *sys, const uint32_t *activeIds, uint32_t numActive,
 	for (uint32_t s = 0; s < steps; s++) {
 		fa.frameIndex++;
 		fa.gameTime += (double)fa.dt;
+		countSteps(rs, activeIds, numActive, fa.dt);
 		rs->ps->updateParticles(rs->areas, fa);
 		for (uint32_t i = 0; i < numActive; i++) total += rs->imp->effects[activeIds[i]].gpuParticles.size / 4;
 	}

@@ -963,16 +963,8 @@ double orc_bench_steps(void *sys, const uint32_t *activeIds, uint32_t numActive,
 	for (uint32_t k = 0; k < steps; k++) {
 		fa.frameIndex++;
 		fa.gameTime += (double)fa.dt;
-		uint64_t before = 0, after = 0;
-		for (uint32_t i = 0; i < numActive; i++) before += s->effects[activeIds[i]].simSteps;
 		orc_update(sys, activeIds, numActive, &fa);
-		for (uint32_t i = 0; i < numActive; i++) {
-			const Effect *e = &s->effects[activeIds[i]];
-			after += e->simSteps;
-			(void)after;
-		}
 		for (uint32_t i = 0; i < numActive; i++) total += s->effects[activeIds[i]].numGpu / 4;
-		(void)before;
 	}
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	if (particleSteps) *particleSteps += total;

@@ -66,6 +66,32 @@ SPR_API int sprContextSynchronize(SprContext *ctx) { REQUIRE(ctx); return guarde
 SPR_API void *sprContextStream(SprContext *ctx) { return ctx ? (void*)ctx->ctx.stream : nullptr; }
 SPR_API uint64_t sprContextLaunchCount(SprContext *ctx) { return ctx ? ctx->ctx.launchCount : 0; }
 
+static const char *const kKernelNames[16] = {
+	"k_scatter_words", "k_plan", "k_emit_warp", "k_emit_burst", "k_integrate", "k_finalize", "sort", "k_gather_render",
+	"k_pack_runs", "k_expand_runs", "k_sort_hist", "k_sort_scan", "k_sort_pass", "k_expand_sorted", "", "" };
+
+SPR_API int sprContextEnableKernelTiming(SprContext *ctx, int enable)
+{
+	REQUIRE(ctx);
+	return guarded([&] { ctx->ctx.resolveTimings(); ctx->ctx.timingEnabled = enable != 0; });
+}
+
+SPR_API int sprContextGetKernelTimes(SprContext *ctx, int reset, const char **names, double *ms, uint64_t *launches, uint32_t capacity, uint32_t *outCount)
+{
+	REQUIRE(ctx && outCount);
+	return guarded([&] {
+		ctx->ctx.resolveTimings();
+		uint32_t n = 0;
+		for (int k = 0; k < 16; k++) {
+			if (!ctx->ctx.kernelLaunches[k]) continue;
+			if (n < capacity) { if (names) names[n] = kKernelNames[k]; if (ms) ms[n] = ctx->ctx.kernelMs[k]; if (launches) launches[n] = ctx->ctx.kernelLaunches[k]; }
+			n++;
+		}
+		*outCount = n;
+		if (reset) for (int k = 0; k < 16; k++) { ctx->ctx.kernelMs[k] = 0; ctx->ctx.kernelLaunches[k] = 0; }
+	});
+}
+
 SPR_API int sprSystemCreate(SprContext *ctx, const SprSystemsDesc *desc, SprSystem **out)
 {
 	REQUIRE(ctx && desc && out);
@@ -262,6 +288,19 @@ SPR_API int sprGetEffectTypeUbo(SprSystem *sys, uint32_t typeId, SprVertexTypeUb
 {
 	REQUIRE(sys && out && typeId < sys->sys.types.size() && sys->sys.types[typeId].comp);
 	*out = sys->sys.types[typeId].typeUbo;
+	return SPR_OK;
+}
+
+SPR_API int sprBakeEffectType(const SprParticleSystemComponent *c, uint32_t typeId, uint8_t outLut[SPR_SPLINE_LUT_BYTES], SprVertexTypeUbo *outUbo)
+{
+	REQUIRE(c && outLut && outUbo);
+	bakeTypeUbo(*outUbo, typeId, *c);
+	memset(outLut, 0, SPR_SPLINE_LUT_BYTES);
+	bakeSplineRow(outLut, 0, c->scaleSpline, false);
+	bakeSplineRow(outLut, 1, c->alphaSpline, false);
+	bakeSplineRow(outLut, 2, c->additiveSpline, true);
+	bakeSplineRow(outLut, 3, c->erosionSpline, false);
+	bakeGradientRow(outLut + SPR_SPLINE_SAMPLE_RATE * 4, c->gradient);
 	return SPR_OK;
 }
 

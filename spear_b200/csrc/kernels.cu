@@ -415,25 +415,29 @@ __device__ inline void tile_lookback(unsigned long long *stA, unsigned long long
 	}
 	if (lane == 0) { st_status(stA + poolTile, tag | fAgg | aggA); st_status(stD + poolTile, tag | fAgg | aggD); }
 	int32_t rel = (int32_t)tileIdx - 1 - (int32_t)lane; // tile (within the effect) this lane inspects
-	for (;;) {
+	// The two words of a tile are published by separate stores, so each chain is resolved on its
+	// own flags: a reader may see a predecessor's alive word already inclusive and its dead word
+	// still an aggregate.
+	bool doneA = false, doneD = false;
+	while (!doneA || !doneD) {
 		unsigned long long va = tag | fIncl, vd = tag | fIncl; // virtual zero prefix in front of tile 0
 		if (rel >= 0) {
 			uint32_t t = poolTile - (tileIdx - (uint32_t)rel);
-			do { va = ld_status(stA + t); } while ((va >> 34) != epoch);
-			do { vd = ld_status(stD + t); } while ((vd >> 34) != epoch);
+			if (!doneA) do { va = ld_status(stA + t); } while ((va >> 34) != epoch);
+			if (!doneD) do { vd = ld_status(stD + t); } while ((vd >> 34) != epoch);
 		}
-		uint32_t incl = __ballot_sync(FULL_MASK, ((va >> 32) & 3u) == 2u);
-		// a tile publishes both words with the same flag progression; use the weaker of the two
-		uint32_t inclD = __ballot_sync(FULL_MASK, ((vd >> 32) & 3u) == 2u);
-		incl &= inclD;
-		if (incl) {
-			uint32_t firstLane = __ffs(incl) - 1;
-			exclA += __reduce_add_sync(FULL_MASK, lane <= firstLane ? (uint32_t)va : 0u);
-			exclD += __reduce_add_sync(FULL_MASK, lane <= firstLane ? (uint32_t)vd : 0u);
-			break;
+		if (!doneA) {
+			uint32_t incl = __ballot_sync(FULL_MASK, ((va >> 32) & 3u) == 2u);
+			uint32_t upTo = incl ? (uint32_t)(__ffs(incl) - 1) : 31u;
+			exclA += __reduce_add_sync(FULL_MASK, lane <= upTo ? (uint32_t)va : 0u);
+			doneA = incl != 0;
 		}
-		exclA += __reduce_add_sync(FULL_MASK, (uint32_t)va);
-		exclD += __reduce_add_sync(FULL_MASK, (uint32_t)vd);
+		if (!doneD) {
+			uint32_t incl = __ballot_sync(FULL_MASK, ((vd >> 32) & 3u) == 2u);
+			uint32_t upTo = incl ? (uint32_t)(__ffs(incl) - 1) : 31u;
+			exclD += __reduce_add_sync(FULL_MASK, lane <= upTo ? (uint32_t)vd : 0u);
+			doneD = incl != 0;
+		}
 		rel -= 32;
 	}
 	if (lane == 0) { st_status(stA + poolTile, tag | fIncl | (exclA + aggA)); st_status(stD + poolTile, tag | fIncl | (exclD + aggD)); }

@@ -37,7 +37,13 @@ struct SortScratch {
 	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases
 	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
 };
+// Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted).
+struct SortTimingHooks {
+	void *ctx;
+	void *(*begin)(void *ctx, int kernel);
+	void (*end)(void *ctx, int kernel, void *token);
+};
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &scratch,
-	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles);
+	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles, const SortTimingHooks *hooks);
 
 } // namespace spr

@@ -8,6 +8,7 @@
 #include "particle_system.h"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 namespace spr {
@@ -173,6 +174,50 @@ void Context::growEffect(uint32_t g, uint32_t minCapacity, bool copyContents)
 	P.slotCapacity = newCap;
 	markParamsDirty(g);
 }
+
+// Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
+enum { kKScatter = 0, kKPlan, kKEmit, kKEmitBurst, kKIntegrate, kKFinalize, kKSort, kKGather, kKPack, kKExpandRuns,
+	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */ };
+
+cudaEvent_t Context::timingBegin(int kernel)
+{
+	(void)kernel;
+	if (!timingEnabled) return nullptr;
+	cudaEvent_t e;
+	if (!eventPool.empty()) { e = eventPool.back(); eventPool.pop_back(); }
+	else SPR_CUDA(cudaEventCreate(&e));
+	SPR_CUDA(cudaEventRecord(e, stream));
+	return e;
+}
+
+void Context::timingEnd(int kernel, cudaEvent_t begin)
+{
+	if (!timingEnabled || !begin) return;
+	cudaEvent_t e;
+	if (!eventPool.empty()) { e = eventPool.back(); eventPool.pop_back(); }
+	else SPR_CUDA(cudaEventCreate(&e));
+	SPR_CUDA(cudaEventRecord(e, stream));
+	timedLaunches.push_back({ kernel, begin, e });
+}
+
+void Context::resolveTimings()
+{
+	SPR_CUDA(cudaStreamSynchronize(stream));
+	for (const TimedLaunch &t : timedLaunches) {
+		float ms = 0.0f;
+		SPR_CUDA(cudaEventElapsedTime(&ms, t.begin, t.end));
+		kernelMs[t.kernel] += ms;
+		kernelLaunches[t.kernel]++;
+		eventPool.push_back(t.begin);
+		eventPool.push_back(t.end);
+	}
+	timedLaunches.clear();
+}
+
+// SPR_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted (debug aid only).
+static const bool kDebugSync = getenv("SPR_DEBUG_SYNC") != nullptr;
+#define TIMED(kernel, call) do { cudaEvent_t tb_ = timingBegin(kernel); call; launchCount++; timingEnd(kernel, tb_); \
+	if (kDebugSync) { cudaError_t de_ = cudaStreamSynchronize(stream); if (de_ != cudaSuccess) throw CudaError(std::string(#call) + " -> " + cudaGetErrorString(de_)); } } while (0)
 
 // One staging blob per submit: pending table uploads + the frame's work lists.
 namespace {
@@ -355,12 +400,12 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	TablePtrs tab = tablePtrs();
 	const ActiveEntry *dEntries = DPTR(ActiveEntry, oEntries);
 	const uint32_t nEntries = (uint32_t)entries.size();
-	launch_plan(stream, tab, DPTR(SystemWork, oWork), (uint32_t)work.size(), dEntries, frameStamp); launchCount++;
+	TIMED(kKPlan, launch_plan(stream, tab, DPTR(SystemWork, oWork), (uint32_t)work.size(), dEntries, frameStamp));
 	const uint32_t poolTiles = (uint32_t)((poolUsed + kTileSlots - 1) / kTileSlots);
 	for (uint32_t round = 0; round < maxSub; round++) {
-		launch_emit_warp(stream, pool, tab, dEntries, nEntries, round); launchCount++;
+		TIMED(kKEmit, launch_emit_warp(stream, pool, tab, dEntries, nEntries, round));
 		if (round == 0 && !burstJobs.empty()) {
-			launch_emit_burst(stream, pool, tab, dEntries, DPTR(BurstJob, oBurst), (uint32_t)burstJobs.size(), burstBlocks); launchCount++;
+			TIMED(kKEmitBurst, launch_emit_burst(stream, pool, tab, dEntries, DPTR(BurstJob, oBurst), (uint32_t)burstJobs.size(), burstBlocks));
 		}
 		epoch = (epoch + 1) & 0x3fffffffu;
 		if (epoch == 0) { // status words carry a 30-bit epoch: wipe them when it wraps
@@ -368,9 +413,9 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			SPR_CUDA(cudaMemsetAsync(dTileStatus[1], 0, poolCapacity / kTileSlots * 8, stream));
 			epoch = 1;
 		}
-		launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, camera); launchCount++;
+		TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, camera));
 	}
-	launch_finalize(stream, tab, dEntries, nEntries); launchCount++;
+	TIMED(kKFinalize, launch_finalize(stream, tab, dEntries, nEntries));
 
 	if (sortMode && !segEffects.empty()) {
 		SortScratch sc;
@@ -378,8 +423,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		dSortHist.reserve(segEffects.size() * 4 * 256, 0, stream);
 		dSortLookback.reserve(sortTiles.size() * 4 * 256 + 1, 0, stream);
 		sc.hist = dSortHist.ptr; sc.lookback = dSortLookback.ptr;
+		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(kKSortBase + k); },
+			[](void *c, int k, void *b) { ((Context*)c)->timingEnd(kKSortBase + k, (cudaEvent_t)b); } };
 		launchCount += launch_sort_and_expand(stream, pool, tab, sc, DPTR(uint32_t, oSeg), (uint32_t)segEffects.size(),
-			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size());
+			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size(), timingEnabled ? &hooks : nullptr);
 	}
 #undef DPTR
 	SPR_CUDA(cudaGetLastError());

@@ -183,6 +183,17 @@ struct Context {
 	uint32_t frameStamp = 0;
 	uint32_t epoch = 0;
 
+	// ---- optional per-kernel timing (bench.py roofline): CUDA events around every launch class
+	struct TimedLaunch { int kernel; cudaEvent_t begin, end; };
+	bool timingEnabled = false;
+	std::vector<TimedLaunch> timedLaunches;
+	std::vector<cudaEvent_t> eventPool;
+	double kernelMs[16] = { 0 };
+	uint64_t kernelLaunches[16] = { 0 };
+	cudaEvent_t timingBegin(int kernel);
+	void timingEnd(int kernel, cudaEvent_t begin);
+	void resolveTimings();
+
 	// ---- sort scratch
 	DeviceArray<uint32_t> dSortHist, dSortLookback;
 	DeviceArray<uint64_t> dRunOffsets;

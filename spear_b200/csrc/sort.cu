@@ -214,21 +214,32 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 }
 
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &sc,
-	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles)
+	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles, const SortTimingHooks *hooks)
 {
 	if (!numSegments || !numTiles) return 0;
+	void *tok = nullptr;
+#define T_BEGIN(k) do { if (hooks) tok = hooks->begin(hooks->ctx, k); } while (0)
+#define T_END(k) do { if (hooks) hooks->end(hooks->ctx, k, tok); } while (0)
 	cudaMemsetAsync(sc.hist, 0, (size_t)numSegments * 1024 * sizeof(uint32_t), st);
 	cudaMemsetAsync(sc.lookback, 0, (size_t)numTiles * 4 * 256 * sizeof(uint32_t), st);
+	T_BEGIN(0);
 	k_sort_hist<<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, sc.hist);
+	T_END(0);
 	uint32_t rows = numSegments * 4;
+	T_BEGIN(1);
 	k_sort_scan<<<(rows * 32 + 255) / 256, 256, 0, st>>>(sc.hist, rows);
+	T_END(1);
 	uint32_t *kbuf[2] = { pool.keys, sc.keysAlt };
 	uint32_t *vbuf[2] = { pool.vals, sc.valsAlt };
 	for (uint32_t p = 0; p < 4; p++) {
+		T_BEGIN(2);
 		k_sort_pass<<<numTiles, 256, 0, st>>>(tab, segEffects, tiles, kbuf[p & 1], vbuf[p & 1], kbuf[(p & 1) ^ 1], vbuf[(p & 1) ^ 1],
 			sc.hist, sc.lookback + (size_t)p * numTiles * 256, p);
+		T_END(2);
 	}
+	T_BEGIN(3);
 	k_expand_sorted<<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles);
+	T_END(3);
 	return 7;
 }
 

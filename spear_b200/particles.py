@@ -24,6 +24,7 @@ EXPORTS = [
     "sprUpdateParticles", "sprUpdateParticlesBatch", "sprRenderMain", "sprGetEffectInfo", "sprReadFreeIndices",
     "sprReadVertexStream", "sprReadSlots", "sprReadStreamSlots", "sprGetRngState", "sprGetEffectTypeLut",
     "sprGetEffectTypeUbo", "sprGetEffectDeviceView", "sprPackRuns", "sprExpandRuns",
+    "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType",
 ]
 
 
@@ -65,6 +66,9 @@ def _load():
     lib.sprGetEffectDeviceView.argtypes = [vp, u32, P(abi.EffectDeviceView)]
     lib.sprPackRuns.argtypes = [vp, P(vp), P(u32), u32, vp, u64, vp, P(u64)]
     lib.sprExpandRuns.argtypes = [vp, vp, u64, vp]
+    lib.sprBakeEffectType.argtypes = [P(abi.ParticleSystemComponent), u32, vp, P(abi.VertexTypeUbo)]
+    lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
+    lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
     return lib
 
 
@@ -83,6 +87,14 @@ def _check(status):
 def _ids(ids):
     arr = np.ascontiguousarray(ids, dtype=np.uint32)
     return arr, arr.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def bake_effect_type(comp, type_id=0):
+    """Host-only LUT + type UBO bake (no GPU needed): (lut uint8[512], VertexTypeUbo)."""
+    lut = np.zeros(abi.SPLINE_LUT_BYTES, dtype=np.uint8)
+    ubo = abi.VertexTypeUbo()
+    _check(lib.sprBakeEffectType(C.byref(comp), type_id, lut.ctypes.data, C.byref(ubo)))
+    return lut, ubo
 
 
 class ParticleContext:
@@ -124,6 +136,18 @@ class ParticleContext:
     @property
     def launch_count(self):
         return int(lib.sprContextLaunchCount(self.h))
+
+    def enable_kernel_timing(self, enable=True):
+        _check(lib.sprContextEnableKernelTiming(self.h, 1 if enable else 0))
+
+    def kernel_times(self, reset=True):
+        """{kernel name: (total ms, launches)} measured with CUDA events on the context stream."""
+        names = (C.c_char_p * 16)()
+        ms = (C.c_double * 16)()
+        launches = (C.c_uint64 * 16)()
+        n = C.c_uint32()
+        _check(lib.sprContextGetKernelTimes(self.h, 1 if reset else 0, names, ms, launches, 16, C.byref(n)))
+        return {names[i].decode(): (ms[i], int(launches[i])) for i in range(n.value)}
 
     def create_system(self, seed=(1, 2, 3, 4)):
         return ParticleSystem(self, seed)

@@ -1,0 +1,275 @@
+"""More GPU parity: large multi-tile effects, per-particle depth sort, many systems in one
+launch set, renderMain draw records, type LUT/UBO, and full-size property checks."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import scenarios as S
+from oracle import orc
+from spear_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+CAMERA = (16.0, 20.0, -30.0)
+
+
+def _particles():
+    from spear_b200 import particles
+    return particles
+
+
+def sort_key(stream_records, camera=CAMERA):
+    """~enc(|camera - pos|^2) with float32 arithmetic in the reference's order (src/sf/Vector.h:99)."""
+    pos = stream_records["pos"].astype(np.float32)
+    cam = np.asarray(camera, dtype=np.float32)
+    d = cam[None, :] - pos
+    d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+    bits = d2.view(np.uint32)
+    enc = np.where(bits & 0x80000000, ~bits, bits | np.uint32(0x80000000)).astype(np.uint32)
+    return ~enc
+
+
+def expected_sorted(oracle_stream, camera=CAMERA):
+    recs = oracle_stream[::4]
+    order = np.argsort(sort_key(recs, camera), kind="stable")
+    return np.repeat(recs[order], 4), order
+
+
+def comp_big(burst):
+    return abi.make_component(
+        timeStep=1 / 60, burstAmount=burst, spawnTime=0.0001, lifeTime=0.05, lifeTimeVariance=0.1, drag=0.2,
+        gravity=(0, -9.81, 0), emitPosition=dict(sphere=dict(minRadius=0.5, maxRadius=4.0)),
+        emitVelocity=dict(boxExtent=(2, 2, 2), sphere=dict(minRadius=0.1, maxRadius=1.0)))
+
+
+def test_large_effect_multi_tile(oracle_port):
+    """200k-particle burst: wide burst kernel, chained look-back across ~200 tiles, deaths and
+    re-use of freed slots across tiles."""
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 16)
+    try:
+        sc = S.Scenario("big", (3, 1234, 5, 6), [(comp_big(200_000), abi.make_transform((1, 2, 3)))], frames=12)
+        ref = S.run_scenario(orc.OracleSystem(oracle_port, sc.seed), sc)
+        got = S.run_scenario(ctx.create_system(sc.seed), sc)
+        for f, (a, b) in enumerate(zip(ref, got)):
+            S.assert_snapshots_equal(a, b, "big frame %d" % f)
+        assert ref[0][0]["info"]["aliveCount"] == 200_020
+        assert ref[-1][0]["info"]["freeCount"] > 1000
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("name", ["c1_small", "fountain", "multi", "churn_c5", "remove_reuse"])
+def test_sorted_stream_is_stable_depth_sort_of_reference_stream(oracle_port, name):
+    P = _particles()
+    sc = [s for s in S.scenarios() if s.name == name][0]
+    ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 16)
+    try:
+        ref = S.run_scenario(orc.OracleSystem(oracle_port, sc.seed), sc)
+        sys_ = ctx.create_system(sc.seed)
+        frames = []
+
+        def on_frame(frame, snap):
+            ids = [e for e in snap if e != "rng"]
+            frames.append({e: sys_.read_stream_slots(e).copy() for e in ids})
+
+        got = S.run_scenario(sys_, sc, on_frame=on_frame)
+        for f, (a, b) in enumerate(zip(ref, got)):
+            assert a["rng"] == b["rng"]
+            for e in a:
+                if e == "rng":
+                    continue
+                assert a[e]["info"] == b[e]["info"], "%s frame %d effect %d" % (name, f, e)
+                assert np.array_equal(a[e]["free"], b[e]["free"])
+                exp, order = expected_sorted(a[e]["stream"])
+                assert exp.tobytes() == b[e]["stream"].tobytes(), "%s frame %d effect %d sorted stream" % (name, f, e)
+    finally:
+        ctx.close()
+
+
+def test_sorted_large_effect(oracle_port):
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 16)
+    try:
+        sc = S.Scenario("bigsort", (3, 77, 5, 6), [(comp_big(70_000), abi.make_transform((1, 2, 3)))], frames=6)
+        ref = S.run_scenario(orc.OracleSystem(oracle_port, sc.seed), sc)
+        got = S.run_scenario(ctx.create_system(sc.seed), sc)
+        for f, (a, b) in enumerate(zip(ref, got)):
+            assert a[0]["info"] == b[0]["info"]
+            exp, _ = expected_sorted(a[0]["stream"])
+            assert exp.tobytes() == b[0]["stream"].tobytes(), "frame %d" % f
+    finally:
+        ctx.close()
+
+
+def test_many_systems_one_launch_set(oracle_port):
+    """sprUpdateParticlesBatch: 24 independent systems (own RNG each, seed[1] = 2 + i) advance in one
+    set of launches and each matches its own oracle instance."""
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 16)
+    try:
+        comps = [S.comp_c2(k, burst=200 + 31 * k, churn=True) for k in range(4)] + [S.comp_c5(), S.comp_fountain()]
+        n = 24
+        systems, oracles, ids = [], [], []
+        for i in range(n):
+            seed = (1, 2 + i, 3, 4)
+            s, o = ctx.create_system(seed), orc.OracleSystem(oracle_port, seed)
+            my = []
+            for k in range(3):
+                comp = comps[(i + k) % len(comps)]
+                tr = abi.make_transform((i, k, 0))
+                e1, e2 = s.add_effect(comp, tr), o.add_effect(comp, tr)
+                assert e1 == e2
+                my.append(e1)
+            systems.append(s); oracles.append(o); ids.append(my)
+        for frame in range(25):
+            fa = abi.make_frame_args(0.0172, game_time=frame * 0.0172, frame_index=frame)
+            ctx.update_batch(systems, ids, fa)
+            for o, my in zip(oracles, ids):
+                o.update(my, fa)
+            if frame % 6 == 0 or frame == 24:
+                for s, o, my in zip(systems, oracles, ids):
+                    S.assert_snapshots_equal(S.snapshot(o, my), S.snapshot(s, my), "batch frame %d" % frame)
+    finally:
+        ctx.close()
+
+
+def look_at_perspective(eye, target, fovy=1.0, aspect=16 / 9, near=0.1, far=200.0):
+    eye, target = np.asarray(eye, np.float64), np.asarray(target, np.float64)
+    f = target - eye; f /= np.linalg.norm(f)
+    r = np.cross(f, [0, 1, 0]); r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    view = np.eye(4); view[0, :3] = r; view[1, :3] = u; view[2, :3] = -f
+    view[:3, 3] = -view[:3, :3] @ eye
+    t = 1.0 / np.tan(fovy / 2)
+    proj = np.zeros((4, 4)); proj[0, 0] = t / aspect; proj[1, 1] = t
+    proj[2, 2] = (far + near) / (near - far); proj[2, 3] = 2 * far * near / (near - far); proj[3, 2] = -1
+    return proj, proj @ view
+
+
+def make_render_args(oracle_kind):
+    proj, w2c = look_at_perspective(CAMERA, (6.0, 0.0, 6.0))
+    ra = abi.RenderArgs()
+    ra.cameraPosition = abi.Vec3(*CAMERA)
+    for c in range(4):
+        for r in range(4):
+            ra.viewToClip.v[c * 4 + r] = float(np.float32(proj[r, c]))
+            ra.worldToClip.v[c * 4 + r] = float(np.float32(w2c[r, c]))
+    ra.frustum = orc.make_frustum(list(ra.worldToClip.v), 0.0, kind=oracle_kind)
+    ra.visFogWorldMad = abi.Vec4(0.1, 0.2, 0.3, 0.4)
+    return ra
+
+
+@pytest.mark.parametrize("budget", [0, 1 << 20])
+def test_render_main_draw_records(oracle_port, budget):
+    """renderMain (ParticleSystem.cpp:824-903): culling, effect sort, the 4096-particle frame budget,
+    type-UBO change flags and the 160-byte instance UBO."""
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 16, max_particles_per_frame=budget)
+    try:
+        seed = (1, 5, 3, 4)
+        s, o = ctx.create_system(seed), orc.OracleSystem(oracle_port, seed)
+        comps = [S.comp_c2(k, burst=250, churn=True) for k in range(4)] + [S.comp_local_space()]
+        ids = []
+        for i in range(20):
+            comp = comps[i % len(comps)]
+            tr = abi.make_transform((4.0 * (i % 5), 0.0, 4.0 * (i // 5) - (40.0 if i == 19 else 0.0)), (0, 0.38268343, 0, 0.92387953), 1.0)
+            e1, e2 = s.add_effect(comp, tr), o.add_effect(comp, tr)
+            assert e1 == e2
+            ids.append(e1)
+        ra = make_render_args(oracle_port)
+        cut = culled = False
+        for frame in range(6):
+            fa = abi.make_frame_args(0.0171, game_time=frame * 0.0171, frame_index=frame, camera=CAMERA)
+            s.update(ids, fa); o.update(ids, fa)
+            vis = ids if frame % 2 == 0 else ids[::-1]
+            got, got_sorted = s.render(vis, ra)
+            exp, exp_sorted = o.render(vis, ra, capacity=64)
+            assert got_sorted == exp_sorted
+            if budget == 0:
+                assert len(got) == len(exp)
+                cut = cut or len(got) < got_sorted
+                culled = culled or got_sorted < sum(1 for e in ids if s.effect_info(e).aliveCount > 0)
+                pairs = zip(got, exp)
+            else:
+                assert len(got) == got_sorted
+                pairs = zip(got[:len(exp)], exp)
+            for a, b in pairs:
+                assert (a.effectId, a.typeId, a.numParticles, a.typeUboChanged) == (b.effectId, b.typeId, b.numParticles, b.typeUboChanged)
+                assert bytes(a.instanceUbo)[:152] == bytes(b.instanceUbo)[:152]
+        if budget == 0:
+            assert cut and culled  # the 4096-particle budget cut-off and the frustum cull were both exercised
+    finally:
+        ctx.close()
+
+
+def test_prepare_for_remove_and_drain(oracle_port):
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 16)
+    try:
+        seed = (1, 6, 3, 4)
+        s, o = ctx.create_system(seed), orc.OracleSystem(oracle_port, seed)
+        comp = S.comp_timed_emitter()
+        e = s.add_effect(comp); assert e == o.add_effect(comp)
+        dt = s.effect_info(e).timeStep
+        for frame in range(60):
+            fa = abi.make_frame_args(dt, game_time=frame * dt, frame_index=frame)
+            if frame >= 5:
+                assert s.prepare_for_remove(e, fa) == o.prepare_for_remove(e, fa), "frame %d" % frame
+            s.update([e], fa); o.update([e], fa)
+        assert s.effect_info(e).aliveCount == 0
+    finally:
+        ctx.close()
+
+
+def test_full_size_properties():
+    """BASELINE configs[2] at full size (10M-particle single effect), size-independent properties:
+    alive = burst + 1, every particle replicated 4x, slot order ascending /
+    depth order descending, checksum of the sorted stream equals the checksum of the unsorted one."""
+    P = _particles()
+    burst = 10_000_000
+    comp = abi.make_component(timeStep=1 / 60, burstAmount=burst, spawnTime=1e9, lifeTime=1e9, drag=0.3,
+                              gravity=(0, -9.81, 0), emitPosition=dict(boxExtent=(8, 4, 8)),
+                              emitVelocity=dict(sphere=dict(minRadius=1, maxRadius=3)))
+    sums = []
+    for sort in (False, True):
+        ctx = P.ParticleContext(sort_particles=sort, initial_slot_capacity=1 << 24)
+        try:
+            s = ctx.create_system((1, 2, 3, 4))
+            e = s.add_effect(comp, abi.make_transform((1, 2, 3)))
+            dt = s.effect_info(e).timeStep
+            for frame in range(3):
+                s.update([e], abi.make_frame_args(dt, game_time=frame * dt, frame_index=frame, camera=CAMERA))
+            info = s.effect_info(e)
+            assert info.aliveCount == burst + 1 and info.slotCount == burst + 4 and info.freeCount == 3
+            st = s.read_stream(e)
+            assert len(st) == 4 * (burst + 1)
+            raw = st.view(np.uint32).reshape(-1, 4, 8)
+            assert (raw[:, 0] == raw[:, 1]).all() and (raw[:, 0] == raw[:, 2]).all() and (raw[:, 0] == raw[:, 3]).all()
+            recs = st[::4]
+            slots = s.read_stream_slots(e)
+            if sort:
+                k = sort_key(recs)
+                assert (k[1:] >= k[:-1]).all()
+                ties = k[1:] == k[:-1]
+                assert (slots[1:][ties] > slots[:-1][ties]).all()
+                assert len(np.unique(slots)) == len(slots)
+            else:
+                assert (slots[1:] > slots[:-1]).all()
+            sums.append(int(raw[:, 0].astype(np.uint64).sum()))
+        finally:
+            ctx.close()
+    assert sums[0] == sums[1]
+
+
+def test_type_lut_and_ubo(oracle_port):
+    P = _particles()
+    comps = [S.comp_c1(), S.comp_fountain()] + [S.comp_c2(k) for k in range(4)]
+    o = orc.OracleSystem(oracle_port)
+    for i, comp in enumerate(comps):
+        t = o.reserve_type(comp)
+        lut, ubo = P.bake_effect_type(comp, t)
+        ref = o.type_lut(t)
+        assert np.array_equal(lut, ref)
+        assert bytes(ubo) == bytes(o.type_ubo(t))
