@@ -140,8 +140,11 @@ struct PoolPtrs {
 	float4 *state;            // 2 float4 per slot
 	uint32_t *freeStack;      // per slot capacity; effect e uses [slotBase, slotBase+freeCount)
 	float4 *vertices;         // 8 float4 per slot capacity (4 x 32 B per live particle)
-	uint32_t *keys;           // sort mode: compacted depth keys (descending-order transform applied)
-	uint32_t *vals;           // sort mode: compacted local slot indices
+	uint32_t *keys;           // sort mode: depth keys (descending-order transform applied); written per SLOT by
+	                          // k_integrate_sort, compacted by the first radix pass
+	uint32_t *vals;           // sort mode: local slot indices, compacted/sorted alongside the keys
+	uint32_t *aliveMask;      // sort mode: one word per 32 slots, bit = slot emits a particle this step (:611)
+	uint32_t *deadMask;       // sort mode: one word per 32 slots, bit = slot was freed this step (:556-567)
 	const uint32_t *granuleOwner;
 	unsigned long long *tileStatusAlive;
 	unsigned long long *tileStatusDead;

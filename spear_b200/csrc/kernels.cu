@@ -400,6 +400,20 @@ __device__ inline void st_status(unsigned long long *p, unsigned long long v)
 	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+// One slot record {pos.xyz, life, vel.xyz, seed} = 32 bytes = one DRAM sector: moved with a single
+// 256-bit access per lane (LDG.E.256 / STG.E.256 on sm_100a), so a warp request covers 1 KB
+// contiguous and every sector is touched exactly once.
+__device__ inline void ld_record(const float4 *p, float4 &a, float4 &b)
+{
+	asm("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ inline void st_record(float4 *p, const float4 &a, const float4 &b)
+{
+	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+		:: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
 // Chained (decoupled look-back) exclusive prefix over the tiles of one large effect, for the
 // alive and the dead counts at once. Status word: [63:34] launch epoch, [33:32] flag
 // (1 aggregate, 2 inclusive prefix), [31:0] value. Called by one full warp.
@@ -443,8 +457,234 @@ __device__ inline void tile_lookback(unsigned long long *stA, unsigned long long
 	if (lane == 0) { st_status(stA + poolTile, tag | fIncl | (exclA + aggA)); st_status(stD + poolTile, tag | fIncl | (exclD + aggD)); }
 }
 
+// Per-effect constants of one sub-step, as every slot of the effect needs them.
+struct StepConsts {
+	const PlanRec *rec; const EffectParams *P; const TypeDev *T; EffectState *S;
+	float dt, drag, lifeTime, lifeVar, gx, gy, gz;
+	uint32_t numGp;
+};
+
+// One slot of the integration loop (:552-605). Returns alive (:611) / dead (:556-567); `ra`,`rb`
+// hold the post-step record when the slot is not a parked free slot.
+__device__ __forceinline__ void integrate_slot(const StepConsts &c, float4 &ra, float4 &rb, bool &alive, bool &dead, bool &touched)
+{
+	float life = ra.w;
+	bool wasFree = !(life < kHugeLifeCmp) && life == life; // parked at 1e20: unobservable, skip the arithmetic
+	alive = false; dead = false; touched = !wasFree;
+	if (life <= 0.0f) { dead = true; life = kHugeLife; }   // :556-567
+	if (wasFree) return;
+	float px = ra.x, py = ra.y, pz = ra.z;
+	float vx = rb.x, vy = rb.y, vz = rb.z, seed = rb.w;
+	float ax = c.gx, ay = c.gy, az = c.gz;                  // :574-579
+	ax -= vx * c.drag;
+	ay -= vy * c.drag;
+	az -= vz * c.drag;
+	for (uint32_t k = 0; k < c.numGp; k++) {                // :539-550, :581-590
+		const GravityPointDev &gp = c.T->gravityPoints[k];
+		float wp[3];
+#pragma unroll
+		for (int i = 0; i < 3; i++) {
+			float e3 = c.P->emitterToWorld[12 + i];
+			float pe3 = (c.rec->flags & 1u) ? c.S->prevEmitterToWorld[12 + i] : e3;
+			float v = e3 + (pe3 - e3);
+			v += c.P->emitterToWorld[0 + i] * gp.position[0];
+			v += c.P->emitterToWorld[4 + i] * gp.position[1];
+			v += c.P->emitterToWorld[8 + i] * gp.position[2];
+			wp[i] = v;
+		}
+		float dx = px - wp[0], dy = py - wp[1], dz = pz - wp[2];
+		float lenSq = (dx*dx + dy*dy + dz*dz) + gp.radius;
+		float weight = __fdiv_rn(__fdiv_rn(1.0f, __fsqrt_rn(lenSq)), lenSq) * gp.strength;
+		ax += dx * weight;
+		ay += dy * weight;
+		az += dz * weight;
+	}
+	vx += ax * c.dt; vy += ay * c.dt; vz += az * c.dt;      // :592-594
+	px += vx * c.dt; py += vy * c.dt; pz += vz * c.dt;      // :598-600
+	life -= __fdiv_rn(c.dt, seed * c.lifeVar + c.lifeTime); // :604
+	ra = make_float4(px, py, pz, life);
+	rb = make_float4(vx, vy, vz, seed);
+	alive = life < kHugeLifeCmp;                            // :611
+}
+
+// Slot / free-list sizes after the emission of a sub-step.
+struct PostEmit { uint32_t slotsPost, topPost, topIn, nSpawn, parIn; };
+__device__ __forceinline__ PostEmit post_emit_counts(const PlanRec *rec, const EffectState *S)
+{
+	PostEmit r;
+	r.parIn = (rec->flags >> 1) & 1u;
+	r.nSpawn = rec->burst + rec->timer;
+	r.topIn = S->freeCount[r.parIn];
+	uint32_t blocksIn = S->slotCount[r.parIn] >> 2;
+	if (r.nSpawn > r.topIn) {
+		uint32_t nNew = r.nSpawn - r.topIn, newBlocks = (nNew + 3) >> 2;
+		r.slotsPost = (blocksIn + newBlocks) * 4;
+		r.topPost = newBlocks * 4 - nNew;
+	} else {
+		r.slotsPost = blocksIn * 4;
+		r.topPost = r.topIn - r.nSpawn;
+	}
+	return r;
+}
+
+// Sort mode: a pure streaming pass, no barrier and no cross-tile dependency. One warp per
+// 128-slot granule: integrate, store the state, write the depth key of every slot and the
+// alive / dead ballots. Compaction is left to the first radix pass (its scatter is dense by
+// construction), the free-list append to k_dead_append.
+__global__ void __launch_bounds__(256, 3) k_integrate_sort(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round,
+	float camX, float camY, float camZ)
+{
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t granule = blockIdx.x * 8 + warp;
+	uint32_t g = pool.granuleOwner[granule];
+	if (g == kNoOwner) return;
+	if (tab.effectStamp[g] != stamp || round >= tab.effectNumSubsteps[g]) return;
+
+	StepConsts c;
+	c.rec = &tab.plans[tab.effectPlanBase[g] + round];
+	c.P = &tab.params[g];
+	c.S = &tab.state[g];
+	c.T = &tab.types[c.P->typeIdx];
+	PostEmit pe = post_emit_counts(c.rec, c.S);
+	const uint32_t slotBase = c.P->slotBase;
+	const uint32_t localBase = granule * kGranuleSlots - slotBase;
+	if (localBase >= pe.slotsPost) return;
+	c.dt = c.rec->dt;
+	c.drag = c.T->drag; c.lifeTime = c.T->lifeTime; c.lifeVar = c.T->lifeTimeVariance;
+	c.gx = c.P->gravity[0]; c.gy = c.P->gravity[1]; c.gz = c.P->gravity[2];
+	c.numGp = c.T->numGravityPoints;
+
+	float4 a[4], b[4];
+	float4 *slotPtr = pool.state + 2ull * (slotBase + localBase + lane);
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+		if (localBase + r * 32 + lane < pe.slotsPost) ld_record(slotPtr + r * 64, a[r], b[r]);
+	}
+	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
+	uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
+	uint32_t anyAlive = 0;
+	uint32_t *keyPtr = pool.keys + slotBase + localBase + lane;
+	const uint32_t maskWord = (slotBase + localBase) >> 5;
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+		bool alive = false, dead = false, touched = false;
+		float4 ra = a[r], rb = b[r];
+		if (localBase + r * 32 + lane < pe.slotsPost) {
+			integrate_slot(c, ra, rb, alive, dead, touched);
+			if (touched) st_record(slotPtr + r * 64, ra, rb);
+		}
+		if (alive) {
+			uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z), el = enc_float(ra.w);
+			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez); mnl = min(mnl, el);
+			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez); mxl = max(mxl, el);
+			float dx = camX - ra.x, dy = camY - ra.y, dz = camZ - ra.z;
+			keyPtr[r * 32] = ~enc_float(dx*dx + dy*dy + dz*dz);  // sf::lengthSq (src/sf/Vector.h:99), descending
+		}
+		uint32_t am = __ballot_sync(FULL_MASK, alive), dm = __ballot_sync(FULL_MASK, dead);
+		if (lane == 0) { pool.aliveMask[maskWord + r] = am; pool.deadMask[maskWord + r] = dm; }
+		anyAlive |= am;
+	}
+	if (anyAlive) {
+		mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny);
+		mnz = __reduce_min_sync(FULL_MASK, mnz); mnl = __reduce_min_sync(FULL_MASK, mnl);
+		mxx = __reduce_max_sync(FULL_MASK, mxx); mxy = __reduce_max_sync(FULL_MASK, mxy);
+		mxz = __reduce_max_sync(FULL_MASK, mxz); mxl = __reduce_max_sync(FULL_MASK, mxl);
+		if (lane < 8) {
+			uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz : lane == 3 ? mnl
+				: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : mxl;
+			uint32_t *addr = lane < 4 ? &c.S->boundsMin[lane] : &c.S->boundsMax[lane - 4];
+			uint32_t cur = *(volatile uint32_t*)addr;
+			if (lane < 4) { if (v < cur) atomicMin(addr, v); }
+			else { if (v > cur) atomicMax(addr, v); }
+		}
+	}
+}
+
+// Single-chain variant of tile_lookback (dead counts only).
+__device__ inline uint32_t tile_lookback1(unsigned long long *st, uint32_t poolTile, uint32_t tileIdx, uint32_t agg, uint32_t epoch, uint32_t lane)
+{
+	const unsigned long long tag = (unsigned long long)epoch << 34;
+	const unsigned long long fAgg = 1ull << 32, fIncl = 2ull << 32;
+	if (tileIdx == 0) { if (lane == 0) st_status(st + poolTile, tag | fIncl | agg); return 0; }
+	if (lane == 0) st_status(st + poolTile, tag | fAgg | agg);
+	uint32_t excl = 0;
+	int32_t rel = (int32_t)tileIdx - 1 - (int32_t)lane;
+	for (;;) {
+		unsigned long long v = tag | fIncl;
+		if (rel >= 0) { uint32_t t = poolTile - (tileIdx - (uint32_t)rel); do { v = ld_status(st + t); } while ((v >> 34) != epoch); }
+		uint32_t incl = __ballot_sync(FULL_MASK, ((v >> 32) & 3u) == 2u);
+		uint32_t upTo = incl ? (uint32_t)(__ffs(incl) - 1) : 31u;
+		excl += __reduce_add_sync(FULL_MASK, lane <= upTo ? (uint32_t)v : 0u);
+		if (incl) break;
+		rel -= 32;
+	}
+	if (lane == 0) st_status(st + poolTile, tag | fIncl | (excl + agg));
+	return excl;
+}
+
+// Sort mode: free-list append in ascending slot order (:556-567) from the dead ballots, and the
+// effect's new slot / free counts. One warp per 1024-slot pool tile, lane = one 32-slot mask word.
+// Touches 4 bytes per 32 slots, so it is cheap even though it keeps the chained scan.
+__global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t poolTile = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (poolTile >= numPoolTiles) return;
+	const uint32_t granule = poolTile * 8 + (lane >> 2);
+	uint32_t g = pool.granuleOwner[granule];
+	bool active = false;
+	if (g != kNoOwner) active = tab.effectStamp[g] == stamp && round < tab.effectNumSubsteps[g];
+	if (!__any_sync(FULL_MASK, active)) return;
+
+	uint32_t slotBase = 0, wordBase = 0, word = 0;
+	PostEmit pe = { 0, 0, 0, 0, 0 };
+	bool large = false;
+	EffectState *S = nullptr;
+	if (active) {
+		const PlanRec *rec = &tab.plans[tab.effectPlanBase[g] + round];
+		const EffectParams *P = &tab.params[g];
+		S = &tab.state[g];
+		pe = post_emit_counts(rec, S);
+		slotBase = P->slotBase;
+		large = P->slotCapacity > kTileSlots;
+		wordBase = poolTile * kTileSlots + lane * 32 - slotBase; // first local slot of this lane's word
+		if (wordBase < pe.slotsPost) word = pool.deadMask[(poolTile * kTileSlots >> 5) + lane];
+		else active = false;
+	}
+	if (!__any_sync(FULL_MASK, active)) return;
+	uint32_t d = __popc(word);
+	// exclusive prefix among the lower lanes of the same effect, and the effect's total inside the tile
+	uint32_t base = 0, tileTotal = 0;
+	for (int j = 0; j < 32; j++) {
+		uint32_t oj = __shfl_sync(FULL_MASK, active ? g : kNoOwner, j);
+		uint32_t dj = __shfl_sync(FULL_MASK, d, j);
+		if (active && oj == g) { tileTotal += dj; if (j < (int)lane) base += dj; }
+	}
+	if (__any_sync(FULL_MASK, large)) { // a large effect owns the whole tile: all lanes agree
+		uint32_t tileIdx = (poolTile * kTileSlots - slotBase) / kTileSlots;
+		base += tile_lookback1(pool.tileStatusDead, poolTile, __shfl_sync(FULL_MASK, tileIdx, 0), __shfl_sync(FULL_MASK, tileTotal, 0), epoch, lane);
+	}
+	if (!active) return;
+	uint32_t w = word, rank = base;
+	while (w) {
+		uint32_t bit = __ffs(w) - 1;
+		pool.freeStack[slotBase + pe.topPost + rank] = wordBase + bit;
+		rank++;
+		w &= w - 1;
+	}
+	// entries of a partially used new Particle4 stay at the bottom of the stack (:491-493)
+	if (wordBase == 0 && pe.nSpawn > pe.topIn) {
+		for (uint32_t i = 0; i < pe.topPost; i++) pool.freeStack[slotBase + i] = pe.slotsPost - 4 + i;
+	}
+	// the lane that holds the last slot publishes the new counts
+	if (pe.slotsPost - 1 - wordBase < 32) {
+		S->freeCount[pe.parIn ^ 1u] = pe.topPost + base + d;
+		S->slotCount[pe.parIn ^ 1u] = pe.slotsPost;
+	}
+}
+
 template <bool SORT>
-__global__ void __launch_bounds__(256) k_integrate(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch,
+__global__ void __launch_bounds__(256, 3) k_integrate(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch,
 	float camX, float camY, float camZ)
 {
 	__shared__ float4 sStage[SORT ? 1 : 8 * 256]; // per warp: 128 records x 2 float4
@@ -454,13 +694,14 @@ __global__ void __launch_bounds__(256) k_integrate(PoolPtrs pool, TablePtrs tab,
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t poolTile = blockIdx.x;
 	const uint32_t granule = poolTile * 8 + warp;
+	const uint32_t ltMask = (1u << lane) - 1u;
 
 	uint32_t g = pool.granuleOwner[granule];
 	bool active = false;
 	if (g != kNoOwner) active = tab.effectStamp[g] == stamp && round < tab.effectNumSubsteps[g];
 	if (!__syncthreads_or(active)) return;
 
-	uint32_t slotBase = 0, slotsPost = 0, topPost = 0, localBase = 0, parIn = 0, nSpawn = 0, topIn = 0, blocksIn = 0;
+	uint32_t slotBase = 0, slotsPost = 0, topPost = 0, localBase = 0, parIn = 0, nSpawn = 0, topIn = 0;
 	bool large = false;
 	float dt = 0.0f, drag = 0.0f, lifeTime = 1.0f, lifeVar = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
 	uint32_t numGp = 0;
@@ -478,7 +719,7 @@ __global__ void __launch_bounds__(256) k_integrate(PoolPtrs pool, TablePtrs tab,
 		parIn = (rec->flags >> 1) & 1u;
 		nSpawn = rec->burst + rec->timer;
 		topIn = S->freeCount[parIn];
-		blocksIn = S->slotCount[parIn] >> 2;
+		uint32_t blocksIn = S->slotCount[parIn] >> 2;
 		if (nSpawn > topIn) {
 			uint32_t nNew = nSpawn - topIn, newBlocks = (nNew + 3) >> 2;
 			slotsPost = (blocksIn + newBlocks) * 4;
@@ -497,34 +738,35 @@ __global__ void __launch_bounds__(256) k_integrate(PoolPtrs pool, TablePtrs tab,
 	// A tile of a large effect that lies wholly beyond slotsPost has no work and nobody waits for it.
 	if (!__syncthreads_or(active)) return;
 
-	// ---- load (all 8 loads in flight before any use)
+	// ---- load: four 256-bit loads per lane in flight before any use
 	float4 a[4], b[4];
 	bool valid[4];
+	float4 *slotPtr = pool.state + 2ull * (slotBase + localBase + lane);
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
 		uint32_t li = localBase + r * 32 + lane;
 		valid[r] = active && li < slotsPost;
-		if (valid[r]) {
-			const float4 *src = pool.state + 2ull * (slotBase + li);
-			a[r] = src[0];
-			b[r] = src[1];
-		}
+		if (valid[r]) ld_record(slotPtr + r * 64, a[r], b[r]);
 	}
 
-	// ---- integrate
-	uint32_t aliveMask[4], deadMask[4];
+	// ---- integrate; state goes straight back, what the output needs is kept small:
+	// sort mode keeps one key per slot, stream mode stages the record at its warp-local rank
+	uint32_t aliveMask[4], deadMask[4], key[4];
 	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
 	uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
+	uint32_t nA = 0, nD = 0;
+	float4 *stage = sStage + (SORT ? 0 : warp * 256);
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
 		bool alive = false, dead = false;
+		float4 ra = a[r], rb = b[r];
 		if (valid[r]) {
-			float life = a[r].w;
+			float life = ra.w;
 			bool wasFree = !(life < kHugeLifeCmp) && life == life; // parked at 1e20: unobservable, skip the arithmetic
 			if (life <= 0.0f) { dead = true; life = kHugeLife; }   // :556-567
 			if (!wasFree) {
-				float px = a[r].x, py = a[r].y, pz = a[r].z;
-				float vx = b[r].x, vy = b[r].y, vz = b[r].z, seed = b[r].w;
+				float px = ra.x, py = ra.y, pz = ra.z;
+				float vx = rb.x, vy = rb.y, vz = rb.z, seed = rb.w;
 				float ax = gx, ay = gy, az = gz;                    // :574-579
 				ax -= vx * drag;
 				ay -= vy * drag;
@@ -552,24 +794,30 @@ __global__ void __launch_bounds__(256) k_integrate(PoolPtrs pool, TablePtrs tab,
 				vx += ax * dt; vy += ay * dt; vz += az * dt;        // :592-594
 				px += vx * dt; py += vy * dt; pz += vz * dt;        // :598-600
 				life -= __fdiv_rn(dt, seed * lifeVar + lifeTime);   // :604
-				a[r] = make_float4(px, py, pz, life);
-				b[r] = make_float4(vx, vy, vz, seed);
+				ra = make_float4(px, py, pz, life);
+				rb = make_float4(vx, vy, vz, seed);
 				alive = life < kHugeLifeCmp;                        // :611
-				float4 *dst = pool.state + 2ull * (slotBase + localBase + r * 32 + lane);
-				dst[0] = a[r];
-				dst[1] = b[r];
+				st_record(slotPtr + r * 64, ra, rb);
 			}
 		}
 		aliveMask[r] = __ballot_sync(FULL_MASK, alive);
 		deadMask[r] = __ballot_sync(FULL_MASK, dead);
 		if (alive) {                                                // :620-621
-			uint32_t ex = enc_float(a[r].x), ey = enc_float(a[r].y), ez = enc_float(a[r].z), el = enc_float(a[r].w);
+			uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z), el = enc_float(ra.w);
 			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez); mnl = min(mnl, el);
 			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez); mxl = max(mxl, el);
+			if (SORT) {
+				float dx = camX - ra.x, dy = camY - ra.y, dz = camZ - ra.z;
+				key[r] = ~enc_float(dx*dx + dy*dy + dz*dz);      // sf::lengthSq (src/sf/Vector.h:99), descending
+			} else {
+				uint32_t k = nA + __popc(aliveMask[r] & ltMask);
+				stage[2 * k] = ra;
+				stage[2 * k + 1] = rb;
+			}
 		}
+		nA += __popc(aliveMask[r]);
+		nD += __popc(deadMask[r]);
 	}
-	uint32_t nA = __popc(aliveMask[0]) + __popc(aliveMask[1]) + __popc(aliveMask[2]) + __popc(aliveMask[3]);
-	uint32_t nD = __popc(deadMask[0]) + __popc(deadMask[1]) + __popc(deadMask[2]) + __popc(deadMask[3]);
 
 	// ---- ranks: warps of the same effect inside the CTA, then tiles of a large effect
 	if (lane == 0) { sOwner[warp] = active ? g : kNoOwner; sAlive[warp] = nA; sDead[warp] = nD; }
@@ -595,12 +843,12 @@ __global__ void __launch_bounds__(256) k_integrate(PoolPtrs pool, TablePtrs tab,
 	if (!active) return;
 
 	// ---- free-list append, ascending slot order (:556-567), behind the post-emission stack
-	{
+	if (nD) {
 		uint32_t run = baseD;
 #pragma unroll
 		for (int r = 0; r < 4; r++) {
 			if (deadMask[r] >> lane & 1u) {
-				uint32_t rank = run + __popc(deadMask[r] & ((1u << lane) - 1u));
+				uint32_t rank = run + __popc(deadMask[r] & ltMask);
 				pool.freeStack[slotBase + topPost + rank] = localBase + r * 32 + lane;
 			}
 			run += __popc(deadMask[r]);
@@ -617,28 +865,15 @@ __global__ void __launch_bounds__(256) k_integrate(PoolPtrs pool, TablePtrs tab,
 #pragma unroll
 		for (int r = 0; r < 4; r++) {
 			if (aliveMask[r] >> lane & 1u) {
-				uint32_t rank = run + __popc(aliveMask[r] & ((1u << lane) - 1u));
-				float dx = camX - a[r].x, dy = camY - a[r].y, dz = camZ - a[r].z;
-				float d2 = dx*dx + dy*dy + dz*dz;          // sf::lengthSq, src/sf/Vector.h:99
-				pool.keys[slotBase + rank] = ~enc_float(d2); // descending depth = back to front
+				uint32_t rank = run + __popc(aliveMask[r] & ltMask);
+				pool.keys[slotBase + rank] = key[r];
 				pool.vals[slotBase + rank] = localBase + r * 32 + lane;
 			}
 			run += __popc(aliveMask[r]);
 		}
 	} else {
-		// stage the warp's live records contiguously, then 4x expand with fully coalesced
-		// 512-byte warp stores (:611-665; the run of a warp is contiguous in the stream)
-		float4 *stage = sStage + warp * 256;
-		uint32_t run = 0;
-#pragma unroll
-		for (int r = 0; r < 4; r++) {
-			if (aliveMask[r] >> lane & 1u) {
-				uint32_t k = run + __popc(aliveMask[r] & ((1u << lane) - 1u));
-				stage[2 * k] = a[r];
-				stage[2 * k + 1] = b[r];
-			}
-			run += __popc(aliveMask[r]);
-		}
+		// 4x expansion of the staged run with fully coalesced 512-byte warp stores
+		// (:611-665; the run of a warp is contiguous in the stream)
 		__syncwarp();
 		float4 *dst = pool.vertices + 8ull * (slotBase + baseA);
 		uint32_t total = nA * 8;
@@ -806,8 +1041,17 @@ void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &ta
 	uint32_t epoch, bool sortMode, const float camera[3])
 {
 	if (!numPoolTiles) return;
-	if (sortMode) k_integrate<true><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
-	else k_integrate<false><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
+	if (sortMode) {
+		k_integrate_sort<<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, camera[0], camera[1], camera[2]);
+	} else {
+		k_integrate<false><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
+	}
+}
+
+void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch)
+{
+	if (!numPoolTiles) return;
+	k_dead_append<<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
 }
 
 void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive)

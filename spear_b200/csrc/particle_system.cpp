@@ -38,6 +38,9 @@ Context::Context(const SprContextDesc &desc)
 	SPR_CUDA(cudaGetDeviceProperties(&prop, device));
 	if (prop.major < 10) throw CudaError("spear_particles kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
 	numSms = (uint32_t)prop.multiProcessorCount;
+	// The sorted expansion gathers one 32-byte record (= one sector) per particle in depth order;
+	// ask L2 to fetch exactly the sector it needs instead of a wider line (a hint, per device).
+	cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
 	flags = desc.flags;
 	maxParticlesPerFrame = desc.maxParticlesPerFrame ? desc.maxParticlesPerFrame : 4096;
 	maxParticleCacheFrames = desc.maxParticleCacheFrames ? desc.maxParticleCacheFrames : 16;
@@ -55,6 +58,7 @@ Context::~Context()
 	cudaStreamSynchronize(stream);
 	cudaFree(dSlotState); cudaFree(dFreeStack); cudaFree(dVertices);
 	cudaFree(dKeys[0]); cudaFree(dKeys[1]); cudaFree(dVals[0]); cudaFree(dVals[1]);
+	cudaFree(dAliveMask); cudaFree(dDeadMask);
 	cudaFree(dGranuleOwner); cudaFree(dTileStatus[0]); cudaFree(dTileStatus[1]);
 	cudaEventDestroy(stagingEvent[0]); cudaEventDestroy(stagingEvent[1]);
 	if (ownStream) cudaStreamDestroy(stream);
@@ -65,6 +69,7 @@ PoolPtrs Context::poolPtrs() const
 	PoolPtrs p;
 	p.state = dSlotState; p.freeStack = dFreeStack; p.vertices = dVertices;
 	p.keys = dKeys[0]; p.vals = dVals[0];
+	p.aliveMask = dAliveMask; p.deadMask = dDeadMask;
 	p.granuleOwner = dGranuleOwner;
 	p.tileStatusAlive = dTileStatus[0]; p.tileStatusDead = dTileStatus[1];
 	return p;
@@ -109,6 +114,8 @@ void Context::ensurePool(uint64_t slots)
 			regrow(dKeys[i], poolCapacity, cap, 0, -1, stream);
 			regrow(dVals[i], poolCapacity, cap, 0, -1, stream);
 		}
+		regrow(dAliveMask, poolCapacity / 32, cap / 32, 0, 0, stream);
+		regrow(dDeadMask, poolCapacity / 32, cap / 32, 0, 0, stream);
 	}
 	poolCapacity = cap;
 }
@@ -177,7 +184,7 @@ void Context::growEffect(uint32_t g, uint32_t minCapacity, bool copyContents)
 
 // Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
 enum { kKScatter = 0, kKPlan, kKEmit, kKEmitBurst, kKIntegrate, kKFinalize, kKSort, kKGather, kKPack, kKExpandRuns,
-	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */ };
+	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14 };
 
 cudaEvent_t Context::timingBegin(int kernel)
 {
@@ -414,6 +421,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			epoch = 1;
 		}
 		TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, camera));
+		if (sortMode) TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch));
 	}
 	TIMED(kKFinalize, launch_finalize(stream, tab, dEntries, nEntries));
 

@@ -148,6 +148,7 @@ struct Context {
 	float4 *dVertices = nullptr;
 	uint32_t *dKeys[2] = { nullptr, nullptr };
 	uint32_t *dVals[2] = { nullptr, nullptr };
+	uint32_t *dAliveMask = nullptr, *dDeadMask = nullptr;
 	uint32_t *dGranuleOwner = nullptr;
 	unsigned long long *dTileStatus[2] = { nullptr, nullptr };
 	std::vector<std::vector<uint32_t>> freeRanges; // per log2(capacity): free slotBase values

@@ -34,14 +34,18 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 	__shared__ uint32_t sHist[4 * 256];
 	SortTile st = tiles[blockIdx.x];
 	uint32_t g = segEffects[st.effect];
-	uint32_t alive = tab.state[g].aliveCount;
+	const EffectState &S = tab.state[g];
+	uint32_t slots = S.slotCount[S.parity];
 	uint32_t begin = st.tile * kSortTileKeys;
-	if (begin >= alive) return;
-	uint32_t count = min(kSortTileKeys, alive - begin);
+	if (begin >= slots) return;
+	uint32_t count = min(kSortTileKeys, slots - begin);
 	for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) sHist[i] = 0;
 	__syncthreads();
-	const uint32_t *keys = pool.keys + tab.params[g].slotBase + begin;
+	const uint32_t segBase = tab.params[g].slotBase;
+	const uint32_t *keys = pool.keys + segBase + begin;
+	const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5);
 	for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
+		if (!((mask[i >> 5] >> (i & 31)) & 1u)) continue;
 		uint32_t k = keys[i];
 		atomicAdd(&sHist[0 * 256 + (k & 255u)], 1u);
 		atomicAdd(&sHist[1 * 256 + ((k >> 8) & 255u)], 1u);
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 }
 
 // one warp per (segment, pass)
-__global__ void k_sort_scan(uint32_t *hist, uint32_t numRows)
+__global__ void k_sort_scan(TablePtrs tab, const uint32_t *segEffects, uint32_t *hist, uint32_t numRows)
 {
 	uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (row >= numRows) return;
@@ -71,6 +75,8 @@ __global__ void k_sort_scan(uint32_t *hist, uint32_t numRows)
 	uint32_t run = incl - sum;
 #pragma unroll
 	for (int i = 0; i < 8; i++) { h[lane * 8 + i] = run; run += v[i]; }
+	// the bins of any pass add up to the number of live particles (gpuParticles.size / 4, :670)
+	if ((row & 3u) == 0 && lane == 31) tab.state[segEffects[row >> 2]].aliveCount = run;
 }
 
 __device__ inline uint32_t ld_relaxed_u32(const uint32_t *p)
@@ -86,7 +92,8 @@ __device__ inline void st_relaxed_u32(uint32_t *p, uint32_t v)
 
 // One radix pass over digit `shift/8`. lookback: [numTiles][256] status words of THIS pass,
 // zero-initialised; word = [31:30] flag (1 aggregate, 2 inclusive prefix), [29:0] count.
-__global__ void __launch_bounds__(256) k_sort_pass(TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	const uint32_t *keysIn, const uint32_t *valsIn, uint32_t *keysOut, uint32_t *valsOut,
 	const uint32_t *hist, uint32_t *lookback, uint32_t pass)
 {
@@ -96,36 +103,46 @@ __global__ void __launch_bounds__(256) k_sort_pass(TablePtrs tab, const uint32_t
 	__shared__ uint32_t sTileExcl[256];     // exclusive scan of the tile's digit counts
 	__shared__ int32_t sGlobal[256];        // global position of local index j with digit d: sGlobal[d] + j
 	__shared__ uint32_t sWarpSum[8];
+	__shared__ uint32_t sTileCount;
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const SortTile st = tiles[blockIdx.x];
 	const uint32_t g = segEffects[st.effect];
-	const uint32_t alive = tab.state[g].aliveCount;
+	// the first pass reads the keys in SLOT space (holes masked out by the alive ballots) and its
+	// scatter compacts them; later passes run on the dense (key, slot) pairs
+	const uint32_t alive = FIRST ? tab.state[g].slotCount[tab.state[g].parity] : tab.state[g].aliveCount;
 	const uint32_t begin = st.tile * kSortTileKeys;
 	if (begin >= alive) return;
 	const uint32_t count = min(kSortTileKeys, alive - begin);
 	const uint32_t segBase = tab.params[g].slotBase;
 	const uint32_t shift = pass * 8;
+	const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5) + warp * (kWarpKeys / 32);
 
 	for (uint32_t i = tid; i < 8 * 256; i += kSortThreads) sCnt[i] = 0;
 	__syncthreads();
 
 	// ---- load (warp-striped: warp w owns keys [w*512, w*512+512) of the tile) and rank
 	uint32_t key[kItemsPerThread], val[kItemsPerThread], rank[kItemsPerThread];
+	uint32_t okBits = 0;
 	const uint32_t *kin = keysIn + segBase + begin;
 	const uint32_t *vin = valsIn + segBase + begin;
 #pragma unroll
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
 		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
 		bool ok = idx < count;
+		if (FIRST) {
+			ok = ok && ((mask[i] >> lane) & 1u);
+			val[i] = begin + idx;
+		} else {
+			val[i] = ok ? vin[idx] : 0u;
+		}
 		key[i] = ok ? kin[idx] : 0xffffffffu;
-		val[i] = ok ? vin[idx] : 0u;
+		okBits |= (ok ? 1u : 0u) << i;
 	}
 	uint32_t *cnt = sCnt + warp * 256;
 #pragma unroll
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
-		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
-		bool ok = idx < count;
+		bool ok = (okBits >> i) & 1u;
 		uint32_t d = ok ? ((key[i] >> shift) & 255u) : 256u; // padding lanes form their own group
 		uint32_t peers = __match_any_sync(FULL_MASK, d);
 		uint32_t before = ok ? cnt[d] : 0u;
@@ -166,14 +183,14 @@ __global__ void __launch_bounds__(256) k_sort_pass(TablePtrs tab, const uint32_t
 	for (uint32_t w = 0; w < 8; w++) if (w < warp) warpBase += sWarpSum[w];
 	uint32_t tileExcl = warpBase + incl - total;
 	sTileExcl[tid] = tileExcl;
+	if (tid == 255) sTileCount = tileExcl + total;
 	sGlobal[tid] = (int32_t)(hist[((size_t)st.effect * 4 + pass) * 256 + tid] + excl) - (int32_t)tileExcl;
 	__syncthreads();
 
 	// ---- stage the tile in sorted order
 #pragma unroll
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
-		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
-		if (idx < count) {
+		if ((okBits >> i) & 1u) {
 			uint32_t d = (key[i] >> shift) & 255u;
 			uint32_t pos = sTileExcl[d] + sCnt[warp * 256 + d] + rank[i];
 			sKeys[pos] = key[i];
@@ -185,7 +202,8 @@ __global__ void __launch_bounds__(256) k_sort_pass(TablePtrs tab, const uint32_t
 	// ---- scatter: consecutive threads write consecutive addresses inside each digit run
 	uint32_t *kout = keysOut + segBase;
 	uint32_t *vout = valsOut + segBase;
-	for (uint32_t j = tid; j < count; j += kSortThreads) {
+	const uint32_t tileCount = sTileCount;
+	for (uint32_t j = tid; j < tileCount; j += kSortThreads) {
 		uint32_t k = sKeys[j];
 		uint32_t d = (k >> shift) & 255u;
 		uint32_t dst = (uint32_t)(sGlobal[d] + (int32_t)j);
@@ -194,7 +212,21 @@ __global__ void __launch_bounds__(256) k_sort_pass(TablePtrs tab, const uint32_t
 	}
 }
 
-// 8 lanes per particle: each lane moves one float4, a warp store covers 512 contiguous bytes.
+// One lane per particle: a coalesced read of 32 slot indices, one 256-bit gather of the 32-byte
+// record per lane (L1 bypassed: a record is exactly one sector and is used once, a full-line L1
+// fill would quadruple the traffic), then the record is stored four times (:607-665). The four
+// 256-bit stores of a warp together fill 32 complete 128-byte lines.
+__device__ inline void ld_record_cg(const float4 *p, float4 &a, float4 &b)
+{
+	asm("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ inline void st_record_cs(float4 *p, const float4 &a, const float4 &b)
+{
+	asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+		:: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
 __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles)
 {
 	SortTile st = tiles[blockIdx.x];
@@ -205,11 +237,27 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	uint32_t count = min(kSortTileKeys, alive - begin);
 	uint32_t segBase = tab.params[g].slotBase;
 	const uint32_t *vals = pool.vals + segBase + begin;
+	const float4 *state = pool.state + 2ull * segBase;
 	float4 *dst = pool.vertices + 8ull * (segBase + begin);
-	uint32_t totalQ = count * 8;
-	for (uint32_t q = threadIdx.x; q < totalQ; q += blockDim.x) {
-		uint32_t slot = vals[q >> 3];
-		dst[q] = pool.state[2ull * (segBase + slot) + (q & 1u)];
+	for (uint32_t base = 0; base < count; base += 4 * 256) {
+		uint32_t slot[4];
+		float4 a[4], b[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			uint32_t i = base + u * 256 + threadIdx.x;
+			slot[u] = i < count ? vals[i] : 0xffffffffu;
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_cg(state + 2ull * slot[u], a[u], b[u]);
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			if (slot[u] == 0xffffffffu) continue;
+			float4 *d = dst + 8ull * (base + u * 256 + threadIdx.x);
+			st_record_cs(d, a[u], b[u]);
+			st_record_cs(d + 2, a[u], b[u]);
+			st_record_cs(d + 4, a[u], b[u]);
+			st_record_cs(d + 6, a[u], b[u]);
+		}
 	}
 }
 
@@ -227,13 +275,14 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 	T_END(0);
 	uint32_t rows = numSegments * 4;
 	T_BEGIN(1);
-	k_sort_scan<<<(rows * 32 + 255) / 256, 256, 0, st>>>(sc.hist, rows);
+	k_sort_scan<<<(rows * 32 + 255) / 256, 256, 0, st>>>(tab, segEffects, sc.hist, rows);
 	T_END(1);
 	uint32_t *kbuf[2] = { pool.keys, sc.keysAlt };
 	uint32_t *vbuf[2] = { pool.vals, sc.valsAlt };
 	for (uint32_t p = 0; p < 4; p++) {
 		T_BEGIN(2);
-		k_sort_pass<<<numTiles, 256, 0, st>>>(tab, segEffects, tiles, kbuf[p & 1], vbuf[p & 1], kbuf[(p & 1) ^ 1], vbuf[(p & 1) ^ 1],
+		if (p == 0) k_sort_pass<true><<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, sc.lookback, p);
+		else k_sort_pass<false><<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, kbuf[p & 1], vbuf[p & 1], kbuf[(p & 1) ^ 1], vbuf[(p & 1) ^ 1],
 			sc.hist, sc.lookback + (size_t)p * numTiles * 256, p);
 		T_END(2);
 	}
