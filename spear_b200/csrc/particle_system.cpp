@@ -38,9 +38,6 @@ Context::Context(const SprContextDesc &desc)
 	SPR_CUDA(cudaGetDeviceProperties(&prop, device));
 	if (prop.major < 10) throw CudaError("spear_particles kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
 	numSms = (uint32_t)prop.multiProcessorCount;
-	// The sorted expansion gathers one 32-byte record (= one sector) per particle in depth order;
-	// ask L2 to fetch exactly the sector it needs instead of a wider line (a hint, per device).
-	cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
 	flags = desc.flags;
 	maxParticlesPerFrame = desc.maxParticlesPerFrame ? desc.maxParticlesPerFrame : 4096;
 	maxParticleCacheFrames = desc.maxParticleCacheFrames ? desc.maxParticleCacheFrames : 16;

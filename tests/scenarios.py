@@ -258,3 +258,45 @@ def scenarios():
                         frames=40, prepare={8: [0]}, removes={20: [1]},
                         readds={25: [(comp_c1(burst=50), _tr((3, 0, 0)))], 30: [(comp_c5(), _tr((4, 0, 0)))]}))
     return out
+
+
+# ---------------------------------------------------------------------------
+# Per-particle depth order (extension): oracle = stable sort of the
+# reference's own compacted stream.
+# ---------------------------------------------------------------------------
+
+CAMERA = (16.0, 20.0, -30.0)
+
+
+def sort_key(stream_records, camera=CAMERA):
+    """~enc(|camera - pos|^2) with float32 arithmetic in the reference's order (src/sf/Vector.h:99)."""
+    pos = stream_records["pos"].astype(np.float32)
+    cam = np.asarray(camera, dtype=np.float32)
+    d = cam[None, :] - pos
+    d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+    bits = d2.view(np.uint32)
+    enc = np.where(bits & 0x80000000, ~bits, bits | np.uint32(0x80000000)).astype(np.uint32)
+    return ~enc
+
+
+def expected_sorted(oracle_stream, camera=CAMERA):
+    """Back-to-front, ties by ascending slot (BillboardOrder idiom, src/client/BillboardSystem.cpp:41-51)."""
+    recs = oracle_stream[::4]
+    order = np.argsort(sort_key(recs, camera), kind="stable")
+    return np.repeat(recs[order], 4), order
+
+
+# ---------------------------------------------------------------------------
+# Digests for the golden vectors (tests/golden/)
+# ---------------------------------------------------------------------------
+
+def snapshot_digest(snap):
+    import hashlib
+    out = {"rng": "%016x" % snap["rng"][0]}
+    for e in sorted(k for k in snap if k != "rng"):
+        info = dict(snap[e]["info"])
+        info["bounds"] = list(info["bounds"]) if info["bounds"] is not None else None
+        out[str(e)] = dict(info=info,
+                           free=hashlib.sha256(snap[e]["free"].tobytes()).hexdigest()[:16],
+                           stream=hashlib.sha256(snap[e]["stream"].tobytes()).hexdigest()[:16])
+    return out

@@ -19,21 +19,7 @@ def _particles():
     return particles
 
 
-def sort_key(stream_records, camera=CAMERA):
-    """~enc(|camera - pos|^2) with float32 arithmetic in the reference's order (src/sf/Vector.h:99)."""
-    pos = stream_records["pos"].astype(np.float32)
-    cam = np.asarray(camera, dtype=np.float32)
-    d = cam[None, :] - pos
-    d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
-    bits = d2.view(np.uint32)
-    enc = np.where(bits & 0x80000000, ~bits, bits | np.uint32(0x80000000)).astype(np.uint32)
-    return ~enc
-
-
-def expected_sorted(oracle_stream, camera=CAMERA):
-    recs = oracle_stream[::4]
-    order = np.argsort(sort_key(recs, camera), kind="stable")
-    return np.repeat(recs[order], 4), order
+sort_key, expected_sorted = S.sort_key, S.expected_sorted
 
 
 def comp_big(burst):

@@ -1,0 +1,77 @@
+// Micro-benchmark: random 32-byte record gather (the sorted expansion's access pattern) under
+// different L2 fetch-granularity limits and load flavours. Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include <random>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+template <int MODE>
+__device__ inline void ld32(const float4 *p, float4 &a, float4 &b)
+{
+	if (MODE == 0) asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w),"=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p));
+	if (MODE == 1) asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w),"=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p));
+	if (MODE == 2) asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w),"=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p));
+	if (MODE == 3) { a = __ldg(p); b = __ldg(p + 1); }
+	if (MODE == 4) { asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w) : "l"(p));
+	                 asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p + 1)); }
+	if (MODE == 5) asm volatile("ld.global.lu.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w),"=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p));
+}
+
+template <int MODE, bool WRITE4>
+__global__ void __launch_bounds__(256) k_gather(const float4 *state, const uint32_t *idx, float4 *out, uint32_t n)
+{
+	uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+#pragma unroll
+	for (int u = 0; u < 4; u++, i += 256) {
+		if (i >= n) return;
+		float4 a, b;
+		ld32<MODE>(state + 2ull * idx[i], a, b);
+		float4 *d = out + (WRITE4 ? 8ull : 2ull) * i;
+		asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(d), "f"(a.x),"f"(a.y),"f"(a.z),"f"(a.w),"f"(b.x),"f"(b.y),"f"(b.z),"f"(b.w) : "memory");
+		if (WRITE4) {
+			asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(d + 2), "f"(a.x),"f"(a.y),"f"(a.z),"f"(a.w),"f"(b.x),"f"(b.y),"f"(b.z),"f"(b.w) : "memory");
+			asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(d + 4), "f"(a.x),"f"(a.y),"f"(a.z),"f"(a.w),"f"(b.x),"f"(b.y),"f"(b.z),"f"(b.w) : "memory");
+			asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(d + 6), "f"(a.x),"f"(a.y),"f"(a.z),"f"(a.w),"f"(b.x),"f"(b.y),"f"(b.z),"f"(b.w) : "memory");
+		}
+	}
+}
+
+template <int MODE, bool W4>
+float run(const float4 *state, const uint32_t *idx, float4 *out, uint32_t n)
+{
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	for (int i = 0; i < 2; i++) k_gather<MODE, W4><<<(n + 1023) / 1024, 256>>>(state, idx, out, n);
+	cudaEventRecord(e0);
+	for (int i = 0; i < 5; i++) k_gather<MODE, W4><<<(n + 1023) / 1024, 256>>>(state, idx, out, n);
+	cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+	float ms; cudaEventElapsedTime(&ms, e0, e1); return ms / 5;
+}
+
+int main()
+{
+	const uint32_t n = 10000000;
+	std::vector<uint32_t> h(n);
+	for (uint32_t i = 0; i < n; i++) h[i] = i;
+	std::mt19937 rng(1); std::shuffle(h.begin(), h.end(), rng);
+	float4 *state, *out; uint32_t *idx;
+	CK(cudaMalloc(&state, (size_t)n * 32)); CK(cudaMalloc(&out, (size_t)n * 128)); CK(cudaMalloc(&idx, (size_t)n * 4));
+	CK(cudaMemset(state, 0, (size_t)n * 32));
+	CK(cudaMemcpy(idx, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+	size_t lim = 0; cudaDeviceGetLimit(&lim, cudaLimitMaxL2FetchGranularity); printf("default L2 fetch granularity limit: %zu\n", lim);
+	for (size_t gran : { (size_t)0, (size_t)32, (size_t)64, (size_t)128 }) {
+		if (gran) { cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaDeviceGetLimit(&lim, cudaLimitMaxL2FetchGranularity); printf("set %zu -> %s, now %zu\n", gran, cudaGetErrorString(e), lim); }
+		printf("  gather+1x store : v8 %.3f  cg %.3f  cs %.3f  ldg2x %.3f  nc.noalloc %.3f  lu %.3f ms\n",
+			run<0, false>(state, idx, out, n), run<1, false>(state, idx, out, n), run<2, false>(state, idx, out, n), run<3, false>(state, idx, out, n), run<4, false>(state, idx, out, n), run<5, false>(state, idx, out, n));
+		printf("  gather+4x store : v8 %.3f  cg %.3f  cs %.3f  ldg2x %.3f  nc.noalloc %.3f  lu %.3f ms\n",
+			run<0, true>(state, idx, out, n), run<1, true>(state, idx, out, n), run<2, true>(state, idx, out, n), run<3, true>(state, idx, out, n), run<4, true>(state, idx, out, n), run<5, true>(state, idx, out, n));
+	}
+	// sorted (identity) order for reference
+	for (uint32_t i = 0; i < n; i++) h[i] = i;
+	CK(cudaMemcpy(idx, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+	printf("  identity order  : 1x %.3f  4x %.3f ms\n", run<1, false>(state, idx, out, n), run<1, true>(state, idx, out, n));
+	return 0;
+}
