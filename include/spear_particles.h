@@ -384,6 +384,13 @@ SPR_API int sprUpdateParticlesBatch(SprContext *ctx, SprSystem *const *systems, 
 SPR_API int sprRenderMain(SprSystem *sys, const uint32_t *visibleIds, uint32_t numVisible,
 	const SprRenderArgs *args, SprRenderOutput *out);
 
+/* renderMain for many systems of one context with a single device read-back. Equivalent to
+ * sprRenderMain(systems[i], visibleIds[i], numVisible[i], &args[i], &outs[i]) for every i;
+ * pass argsStride = 0 when the RenderArgs are shared. */
+SPR_API int sprRenderMainBatch(SprContext *ctx, SprSystem *const *systems, uint32_t numSystems,
+	const uint32_t *const *visibleIds, const uint32_t *numVisible,
+	const SprRenderArgs *args, size_t argsStride, SprRenderOutput *outs);
+
 /* ------------------------------------------------------------------------ */
 /* Parity read-backs (host copies; each synchronises the context stream)      */
 /* ------------------------------------------------------------------------ */

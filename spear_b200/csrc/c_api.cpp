@@ -168,6 +168,21 @@ SPR_API int sprRenderMain(SprSystem *sys, const uint32_t *visibleIds, uint32_t n
 	return guarded([&] { sys->sys.renderMain(visibleIds, numVisible, *args, *out); });
 }
 
+SPR_API int sprRenderMainBatch(SprContext *ctx, SprSystem *const *systems, uint32_t numSystems,
+	const uint32_t *const *visibleIds, const uint32_t *numVisible, const SprRenderArgs *args, size_t argsStride, SprRenderOutput *outs)
+{
+	REQUIRE(ctx && systems && visibleIds && numVisible && args && outs);
+	return guarded([&] {
+		std::vector<ParticleSystem*> sys(numSystems);
+		for (uint32_t i = 0; i < numSystems; i++) {
+			if (!systems[i] || systems[i]->sys.ctx != &ctx->ctx) throw std::runtime_error("system does not belong to this context");
+			for (uint32_t k = 0; k < numVisible[i]; k++) if (!validEffect(systems[i], visibleIds[i][k])) throw std::runtime_error("invalid effect id");
+			sys[i] = &systems[i]->sys;
+		}
+		ctx->ctx.renderBatch(sys.data(), numSystems, visibleIds, numVisible, args, argsStride, outs);
+	});
+}
+
 // ---- parity read-backs
 
 SPR_API int sprGetEffectInfo(SprSystem *sys, uint32_t effectId, SprEffectInfo *out)

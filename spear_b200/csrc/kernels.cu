@@ -161,67 +161,87 @@ __global__ void k_scatter_words(uint32_t *dst, const uint32_t *idx, const uint32
 // (all sub-steps of effect A before effect B, :812-821).
 // ---------------------------------------------------------------------------
 
-__global__ void k_plan(TablePtrs tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp)
+// One WARP per system. The RNG chain makes the effects of a system sequential, but only the few
+// arithmetic steps of the spawn loop are: each lane first loads everything one effect needs (32
+// effects' dependent global loads in flight at once), then the lanes take turns running the control
+// loop on registers, handing the RNG state to the next lane by shuffle, and finally every lane writes
+// its own plan records and state back in parallel.
+__global__ void __launch_bounds__(128) k_plan(TablePtrs tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp)
 {
-	uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (w >= numWork) return;
-	SystemWork sw = work[w];
+	const SystemWork sw = work[w];
 	Pcg rng;
 	rng.state = tab.systems[sw.systemIdx].rngState;
 	rng.inc = tab.systems[sw.systemIdx].rngInc;
 
-	for (uint32_t a = 0; a < sw.numActive; a++) {
-		ActiveEntry ae = active[sw.firstActive + a];
-		uint32_t g = ae.effect;
-		const EffectParams &P = tab.params[g];
-		EffectState &S = tab.state[g];
-		const TypeDev &T = tab.types[P.typeIdx];
-		tab.effectStamp[g] = stamp;
-		tab.effectPlanBase[g] = ae.planBase;
-		tab.effectNumSubsteps[g] = ae.numSubsteps;
-		if (ae.numSubsteps == 0) continue;
-
-		float spawnTimer = S.spawnTimer, emitOnTimer = S.emitOnTimer;
-		uint32_t stopEmit = S.stopEmit, firstEmit = S.firstEmit, parity = S.parity;
-		const float dt = P.timeStep;
-		const uint32_t K = T.drawsPerSpawn;
-
-		for (uint32_t s = 0; s < ae.numSubsteps; s++) {
-			PlanRec &rec = tab.plans[ae.planBase + s];
-			uint32_t burst = 0, usePrev = (s == 0) ? 1u : 0u;
-			if (firstEmit) { burst = T.burstAmount; firstEmit = 0; usePrev = 0; }   // :457-464
-			if (emitOnTimer >= 0.0f) {                                              // :466-471
-				emitOnTimer -= dt;
-				if (emitOnTimer < 0.0f) stopEmit = 1;
-			}
-			bool stop = stopEmit || P.hostStopEmit;
-			spawnTimer -= dt;                                                        // :477
-			rec.rngState = rng.state;
-			rec.effect = g;
-			rec.burst = burst;
-			rec.dt = dt;
-			rec.spawnTimer0 = spawnTimer;
-			rec.flags = usePrev | ((parity & 1u) << 1);
-			if (burst) rng.advance((uint64_t)burst * (K - 1));                       // burst spawns draw first (:480-481)
-			uint32_t timer = 0;
-			int spawnsLeft = (int)kMaxTimerSpawns;
-			while (spawnTimer <= 0.0f && !stop) {                                    // :479-485
-				if (spawnsLeft-- <= 0) break;
-				spawnTimer += T.spawnTime + T.spawnTimeVariance * rng.nextFloat();
-				rec.timerVals[timer++] = spawnTimer;
-				rng.state = rng.state * T.mulKm1 + rng.inc * T.sumKm1;               // the spawn's own K-1 draws
-			}
-			rec.timer = timer;
-			spawnTimer = sf_max(spawnTimer, 0.0f);                                   // :524
-			parity ^= 1u;
+	for (uint32_t base = 0; base < sw.numActive; base += 32) {
+		const uint32_t a = base + lane;
+		const bool have = a < sw.numActive;
+		ActiveEntry ae = { 0, 0, 0, 0 };
+		float spawnTimer = 0.0f, emitOnTimer = 0.0f, dt = 0.0f, spawnTime = 0.0f, spawnVar = 0.0f;
+		uint32_t stopEmit = 0, firstEmit = 0, parity = 0, hostStop = 0, K = 2, burstAmount = 0;
+		uint64_t mulKm1 = 1, sumKm1 = 0;
+		if (have) {
+			ae = active[sw.firstActive + a];
+			const EffectParams &P = tab.params[ae.effect];
+			const EffectState &S = tab.state[ae.effect];
+			const TypeDev &T = tab.types[P.typeIdx];
+			tab.effectStamp[ae.effect] = stamp;
+			tab.effectPlanBase[ae.effect] = ae.planBase;
+			tab.effectNumSubsteps[ae.effect] = ae.numSubsteps;
+			spawnTimer = S.spawnTimer; emitOnTimer = S.emitOnTimer;
+			stopEmit = S.stopEmit; firstEmit = S.firstEmit; parity = S.parity;
+			dt = P.timeStep; hostStop = P.hostStopEmit;
+			K = T.drawsPerSpawn; burstAmount = T.burstAmount;
+			spawnTime = T.spawnTime; spawnVar = T.spawnTimeVariance;
+			mulKm1 = T.mulKm1; sumKm1 = T.sumKm1;
 		}
-		S.spawnTimer = spawnTimer;
-		S.emitOnTimer = emitOnTimer;
-		S.stopEmit = stopEmit;
-		S.firstEmit = firstEmit;
-		S.parity = parity;
+		const uint32_t n = min(32u, sw.numActive - base);
+		for (uint32_t k = 0; k < n; k++) {
+			if (lane == k) {
+				for (uint32_t s = 0; s < ae.numSubsteps; s++) {
+					PlanRec &rec = tab.plans[ae.planBase + s];
+					uint32_t burst = 0, usePrev = (s == 0) ? 1u : 0u;
+					if (firstEmit) { burst = burstAmount; firstEmit = 0; usePrev = 0; }     // :457-464
+					if (emitOnTimer >= 0.0f) {                                              // :466-471
+						emitOnTimer -= dt;
+						if (emitOnTimer < 0.0f) stopEmit = 1;
+					}
+					const bool stop = stopEmit || hostStop;
+					spawnTimer -= dt;                                                        // :477
+					rec.rngState = rng.state;
+					rec.effect = ae.effect;
+					rec.burst = burst;
+					rec.dt = dt;
+					rec.spawnTimer0 = spawnTimer;
+					rec.flags = usePrev | ((parity & 1u) << 1);
+					if (burst) rng.advance((uint64_t)burst * (K - 1));                       // burst spawns draw first (:480-481)
+					uint32_t timer = 0;
+					int spawnsLeft = (int)kMaxTimerSpawns;
+					while (spawnTimer <= 0.0f && !stop) {                                    // :479-485
+						if (spawnsLeft-- <= 0) break;
+						spawnTimer += spawnTime + spawnVar * rng.nextFloat();
+						rec.timerVals[timer++] = spawnTimer;
+						rng.state = rng.state * mulKm1 + rng.inc * sumKm1;                   // the spawn's own K-1 draws
+					}
+					rec.timer = timer;
+					spawnTimer = sf_max(spawnTimer, 0.0f);                                   // :524
+					parity ^= 1u;
+				}
+			}
+			rng.state = __shfl_sync(FULL_MASK, rng.state, k);
+		}
+		if (have && ae.numSubsteps) {
+			EffectState &S = tab.state[ae.effect];
+			S.spawnTimer = spawnTimer;
+			S.emitOnTimer = emitOnTimer;
+			S.stopEmit = stopEmit;
+			S.firstEmit = firstEmit;
+			S.parity = parity;
+		}
 	}
-	tab.systems[sw.systemIdx].rngState = rng.state;
+	if (lane == 0) tab.systems[sw.systemIdx].rngState = rng.state;
 }
 
 // ---------------------------------------------------------------------------
@@ -1022,7 +1042,7 @@ void launch_scatter_words(cudaStream_t st, void *dst, const uint32_t *idx, const
 void launch_plan(cudaStream_t st, const TablePtrs &tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp)
 {
 	if (!numWork) return;
-	k_plan<<<div_up(numWork, 64), 64, 0, st>>>(tab, work, numWork, active, stamp);
+	k_plan<<<div_up((uint64_t)numWork * 32, 128), 128, 0, st>>>(tab, work, numWork, active, stamp);
 }
 
 void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t round)

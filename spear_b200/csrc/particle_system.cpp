@@ -684,14 +684,35 @@ SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const H
 
 void ParticleSystem::renderMain(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, SprRenderOutput &out)
 {
-	uint32_t frameParticlesLeft = ctx->maxParticlesPerFrame;              // :827
-	bufferFrameIndex++;                                                   // :831
-	const uint64_t frame = bufferFrameIndex;
-
 	std::vector<uint32_t> globals(numVisible);
 	for (uint32_t i = 0; i < numVisible; i++) globals[i] = effects[visibleIds[i]].global;
 	std::vector<RenderGather> got(numVisible);
 	ctx->gatherEffects(globals.data(), numVisible, got.data());
+	renderMainWith(visibleIds, numVisible, args, got.data(), out);
+}
+
+// renderMain for many systems with ONE device read-back (counts + bounds of every visible effect).
+void Context::renderBatch(ParticleSystem *const *systems, uint32_t numSystems, const uint32_t *const *visibleIds,
+	const uint32_t *numVisible, const SprRenderArgs *args, size_t argsStride, SprRenderOutput *outs)
+{
+	std::vector<uint32_t> globals;
+	for (uint32_t s = 0; s < numSystems; s++)
+		for (uint32_t i = 0; i < numVisible[s]; i++) globals.push_back(systems[s]->effects[visibleIds[s][i]].global);
+	std::vector<RenderGather> got(globals.size());
+	gatherEffects(globals.data(), (uint32_t)globals.size(), got.data());
+	size_t off = 0;
+	for (uint32_t s = 0; s < numSystems; s++) {
+		const SprRenderArgs &a = *(const SprRenderArgs*)((const char*)args + argsStride * s);
+		systems[s]->renderMainWith(visibleIds[s], numVisible[s], a, got.data() + off, outs[s]);
+		off += numVisible[s];
+	}
+}
+
+void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, const RenderGather *got, SprRenderOutput &out)
+{
+	uint32_t frameParticlesLeft = ctx->maxParticlesPerFrame;              // :827
+	bufferFrameIndex++;                                                   // :831
+	const uint64_t frame = bufferFrameIndex;
 
 	std::vector<SortedEffect> sorted;
 	std::vector<uint32_t> sortedCount;

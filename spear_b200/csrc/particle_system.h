@@ -118,6 +118,7 @@ struct ParticleSystem {
 	void updateParticles(const uint32_t *activeIds, uint32_t numActive, const SprFrameArgs &args); // :808-822
 	void renderMain(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, SprRenderOutput &out); // :824-903
 
+	void renderMainWith(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, const RenderGather *got, SprRenderOutput &out);
 	void releaseEffectTypeImp(uint32_t typeId);                        // :682-692
 };
 
@@ -213,6 +214,8 @@ struct Context {
 	void flushUploads();
 	void update(const UpdateRequest *reqs, uint32_t numReqs);
 	void gatherEffects(const uint32_t *globals, uint32_t n, RenderGather *out); // synchronous read-back
+	void renderBatch(ParticleSystem *const *systems, uint32_t numSystems, const uint32_t *const *visibleIds,
+		const uint32_t *numVisible, const SprRenderArgs *args, size_t argsStride, SprRenderOutput *outs);
 	void growEffect(uint32_t g, uint32_t minCapacity, bool copyContents);
 	void sync() { SPR_CUDA(cudaStreamSynchronize(stream)); }
 };

@@ -24,7 +24,7 @@ EXPORTS = [
     "sprUpdateParticles", "sprUpdateParticlesBatch", "sprRenderMain", "sprGetEffectInfo", "sprReadFreeIndices",
     "sprReadVertexStream", "sprReadSlots", "sprReadStreamSlots", "sprGetRngState", "sprGetEffectTypeLut",
     "sprGetEffectTypeUbo", "sprGetEffectDeviceView", "sprPackRuns", "sprExpandRuns",
-    "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType",
+    "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType", "sprRenderMainBatch",
 ]
 
 
@@ -55,6 +55,7 @@ def _load():
     lib.sprUpdateParticles.argtypes = [vp, P(u32), u32, P(abi.FrameArgs)]
     lib.sprUpdateParticlesBatch.argtypes = [vp, P(vp), u32, P(P(u32)), P(u32), P(abi.FrameArgs), C.c_size_t]
     lib.sprRenderMain.argtypes = [vp, P(u32), u32, P(abi.RenderArgs), P(abi.RenderOutput)]
+    lib.sprRenderMainBatch.argtypes = [vp, P(vp), u32, P(P(u32)), P(u32), P(abi.RenderArgs), C.c_size_t, P(abi.RenderOutput)]
     lib.sprGetEffectInfo.argtypes = [vp, u32, P(abi.EffectInfo)]
     lib.sprReadFreeIndices.argtypes = [vp, u32, vp, u32, P(u32)]
     lib.sprReadVertexStream.argtypes = [vp, u32, vp, u32, P(u32)]
@@ -173,6 +174,13 @@ class ParticleContext:
     def update_prepared(self, batch, frame_args):
         handles, ptrs, counts, n, _ = batch
         _check(lib.sprUpdateParticlesBatch(self.h, handles, n, ptrs, counts, C.byref(frame_args), 0))
+
+    def render_prepared(self, batch, render_args):
+        """sprRenderMainBatch over a pre-marshalled batch; returns the list of RenderOutput structs."""
+        handles, ptrs, counts, n, _ = batch
+        outs = (abi.RenderOutput * n)()
+        _check(lib.sprRenderMainBatch(self.h, handles, n, ptrs, counts, C.byref(render_args), 0, outs))
+        return outs
 
     def pack_runs(self, systems, effect_ids, device_out, capacity_records, device_counts=None, want_total=True):
         n = len(systems)
