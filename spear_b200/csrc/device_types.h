@@ -121,6 +121,21 @@ struct PlanRec {
 	float timerVals[kMaxTimerSpawns]; // spawnTimer after each timer increment (:484)
 };
 
+// Everything a slot needs to know about its effect in one sub-step, digested by k_emit_warp into
+// one 64-byte record so that the streaming kernels reach their data loads after two dependent
+// loads (granule owner -> this record) instead of seven.
+struct __align__(16) RoundConsts {
+	uint32_t stamp, round;   // valid for this (frame stamp, sub-step round) only
+	uint32_t slotBase;
+	uint32_t slotsPost;      // particles.size*4 after the emission of this sub-step
+	uint32_t topPost;        // freeIndices.size after the emission of this sub-step
+	uint32_t flags;          // bit0 parity in, bit1 large (capacity > 1024), bit2 usePrev, bit3 grew (nSpawn > topIn), [15:8] numGravityPoints
+	uint32_t typeIdx, planIdx;
+	float dt, drag, lifeTime, lifeVar;
+	float gx, gy, gz;
+	uint32_t _pad;
+};
+
 // A job of the wide burst-emission kernel: `count` burst spawns of active entry `entry`
 // starting at CTA `firstBlock`.
 struct BurstJob {
@@ -159,6 +174,7 @@ struct TablePtrs {
 	uint32_t *effectStamp;    // frame stamp of the last plan that covers the effect
 	uint32_t *effectPlanBase;
 	uint32_t *effectNumSubsteps;
+	RoundConsts *roundConsts; // per effect, rewritten every sub-step round by k_emit_warp
 };
 
 } // namespace spr

@@ -356,7 +356,7 @@ __device__ inline void emit_init_leftover(const EmitCtx &c, const PoolPtrs &pool
 
 // One warp per active effect: all timer spawns, and the burst unless it is flagged for
 // the wide kernel. Also resets the per-step bounds and handles the empty-effect corner.
-__global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab, const ActiveEntry *active, uint32_t numActive, uint32_t round)
+__global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
 {
 	uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (a >= numActive) return;
@@ -375,14 +375,25 @@ __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab,
 		uint32_t pinf = 0xff800000u /* enc(+inf) */, ninf = 0x007fffffu /* enc(-inf) */;
 #pragma unroll
 		for (int k = 0; k < 4; k++) { S.boundsMin[k] = pinf; S.boundsMax[k] = ninf; }
-		uint32_t slots = c.blocks * 4;
-		if (n > c.top) slots += 4 * ((n - c.top + 3) >> 2);
+		uint32_t slots = c.blocks * 4, topPost = c.top - (n <= c.top ? n : c.top);
+		if (n > c.top) { uint32_t nb = (n - c.top + 3) >> 2; slots += 4 * nb; topPost = nb * 4 - (n - c.top); }
+		uint32_t par = (rec->flags >> 1) & 1u;
 		if (slots == 0) { // nothing for k_integrate to do: carry the counts over
-			uint32_t par = (rec->flags >> 1) & 1u;
 			S.slotCount[par ^ 1u] = 0;
 			S.freeCount[par ^ 1u] = 0;
 			S.aliveCount = 0;
 		}
+		RoundConsts rc;
+		rc.stamp = stamp; rc.round = round;
+		rc.slotBase = c.P->slotBase;
+		rc.slotsPost = slots;
+		rc.topPost = topPost;
+		rc.flags = par | (c.P->slotCapacity > kTileSlots ? 2u : 0u) | ((rec->flags & 1u) << 2) | (n > c.top ? 8u : 0u) | (c.T->numGravityPoints << 8);
+		rc.typeIdx = c.P->typeIdx; rc.planIdx = ae.planBase + round;
+		rc.dt = rec->dt; rc.drag = c.T->drag; rc.lifeTime = c.T->lifeTime; rc.lifeVar = c.T->lifeTimeVariance;
+		rc.gx = c.P->gravity[0]; rc.gy = c.P->gravity[1]; rc.gz = c.P->gravity[2];
+		rc._pad = 0;
+		tab.roundConsts[rec->effect] = rc;
 	}
 }
 
@@ -484,8 +495,37 @@ struct StepConsts {
 	uint32_t numGp;
 };
 
+// Gravity points (:539-550 world transform, :581-590 force). Rare in practice: the kernels are
+// instantiated with and without this path (GP) and the host picks the lean one when no live
+// effect type has gravity points, which saves the streaming kernels ~20 registers.
+__device__ __forceinline__ void gravity_points_accel(const PlanRec *rec, const EffectParams *P, const EffectState *S, const TypeDev *T,
+	uint32_t numGp, float px, float py, float pz, float &ax, float &ay, float &az)
+{
+	for (uint32_t k = 0; k < numGp; k++) {
+		const GravityPointDev &gp = T->gravityPoints[k];
+		float wp[3];
+#pragma unroll
+		for (int i = 0; i < 3; i++) {
+			float e3 = P->emitterToWorld[12 + i];
+			float pe3 = (rec->flags & 1u) ? S->prevEmitterToWorld[12 + i] : e3;
+			float v = e3 + (pe3 - e3);
+			v += P->emitterToWorld[0 + i] * gp.position[0];
+			v += P->emitterToWorld[4 + i] * gp.position[1];
+			v += P->emitterToWorld[8 + i] * gp.position[2];
+			wp[i] = v;
+		}
+		float dx = px - wp[0], dy = py - wp[1], dz = pz - wp[2];
+		float lenSq = (dx*dx + dy*dy + dz*dz) + gp.radius;
+		float weight = __fdiv_rn(__fdiv_rn(1.0f, __fsqrt_rn(lenSq)), lenSq) * gp.strength;
+		ax += dx * weight;
+		ay += dy * weight;
+		az += dz * weight;
+	}
+}
+
 // One slot of the integration loop (:552-605). Returns alive (:611) / dead (:556-567); `ra`,`rb`
 // hold the post-step record when the slot is not a parked free slot.
+template <bool GP>
 __device__ __forceinline__ void integrate_slot(const StepConsts &c, float4 &ra, float4 &rb, bool &alive, bool &dead, bool &touched)
 {
 	float life = ra.w;
@@ -499,32 +539,24 @@ __device__ __forceinline__ void integrate_slot(const StepConsts &c, float4 &ra, 
 	ax -= vx * c.drag;
 	ay -= vy * c.drag;
 	az -= vz * c.drag;
-	for (uint32_t k = 0; k < c.numGp; k++) {                // :539-550, :581-590
-		const GravityPointDev &gp = c.T->gravityPoints[k];
-		float wp[3];
-#pragma unroll
-		for (int i = 0; i < 3; i++) {
-			float e3 = c.P->emitterToWorld[12 + i];
-			float pe3 = (c.rec->flags & 1u) ? c.S->prevEmitterToWorld[12 + i] : e3;
-			float v = e3 + (pe3 - e3);
-			v += c.P->emitterToWorld[0 + i] * gp.position[0];
-			v += c.P->emitterToWorld[4 + i] * gp.position[1];
-			v += c.P->emitterToWorld[8 + i] * gp.position[2];
-			wp[i] = v;
-		}
-		float dx = px - wp[0], dy = py - wp[1], dz = pz - wp[2];
-		float lenSq = (dx*dx + dy*dy + dz*dz) + gp.radius;
-		float weight = __fdiv_rn(__fdiv_rn(1.0f, __fsqrt_rn(lenSq)), lenSq) * gp.strength;
-		ax += dx * weight;
-		ay += dy * weight;
-		az += dz * weight;
-	}
+	if (GP && c.numGp) gravity_points_accel(c.rec, c.P, c.S, c.T, c.numGp, px, py, pz, ax, ay, az); // :539-550, :581-590 (rare: kept out of line)
 	vx += ax * c.dt; vy += ay * c.dt; vz += az * c.dt;      // :592-594
 	px += vx * c.dt; py += vy * c.dt; pz += vz * c.dt;      // :598-600
 	life -= __fdiv_rn(c.dt, seed * c.lifeVar + c.lifeTime); // :604
 	ra = make_float4(px, py, pz, life);
 	rb = make_float4(vx, vy, vz, seed);
 	alive = life < kHugeLifeCmp;                            // :611
+}
+
+__device__ __forceinline__ void step_consts_from(StepConsts &c, const RoundConsts &rc, const TablePtrs &tab, uint32_t g)
+{
+	c.rec = &tab.plans[rc.planIdx];
+	c.P = &tab.params[g];
+	c.S = &tab.state[g];
+	c.T = &tab.types[rc.typeIdx];
+	c.dt = rc.dt; c.drag = rc.drag; c.lifeTime = rc.lifeTime; c.lifeVar = rc.lifeVar;
+	c.gx = rc.gx; c.gy = rc.gy; c.gz = rc.gz;
+	c.numGp = rc.flags >> 8;
 }
 
 // Slot / free-list sizes after the emission of a sub-step.
@@ -547,39 +579,37 @@ __device__ __forceinline__ PostEmit post_emit_counts(const PlanRec *rec, const E
 	return r;
 }
 
+template <bool GP>
 // Sort mode: a pure streaming pass, no barrier and no cross-tile dependency. One warp per
 // 128-slot granule: integrate, store the state, write the depth key of every slot and the
 // alive / dead ballots. Compaction is left to the first radix pass (its scatter is dense by
 // construction), the free-list append to k_dead_append.
-__global__ void __launch_bounds__(256, 3) k_integrate_sort(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round,
+__global__ void __launch_bounds__(256, GP ? 3 : 4) k_integrate_sort(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round,
 	float camX, float camY, float camZ)
 {
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t granule = blockIdx.x * 8 + warp;
 	uint32_t g = pool.granuleOwner[granule];
 	if (g == kNoOwner) return;
-	if (tab.effectStamp[g] != stamp || round >= tab.effectNumSubsteps[g]) return;
-
-	StepConsts c;
-	c.rec = &tab.plans[tab.effectPlanBase[g] + round];
-	c.P = &tab.params[g];
-	c.S = &tab.state[g];
-	c.T = &tab.types[c.P->typeIdx];
-	PostEmit pe = post_emit_counts(c.rec, c.S);
-	const uint32_t slotBase = c.P->slotBase;
-	const uint32_t localBase = granule * kGranuleSlots - slotBase;
-	if (localBase >= pe.slotsPost) return;
-	c.dt = c.rec->dt;
-	c.drag = c.T->drag; c.lifeTime = c.T->lifeTime; c.lifeVar = c.T->lifeTimeVariance;
-	c.gx = c.P->gravity[0]; c.gy = c.P->gravity[1]; c.gz = c.P->gravity[2];
-	c.numGp = c.T->numGravityPoints;
-
+	// Everything that depends only on the owner is requested at once: the effect's round record,
+	// its current bounds (a stale value is a valid filter for the min/max atomics, they only ever
+	// tighten) and the 128 slot records, whose address is a function of the granule alone.
+	// Ownership covers only the slots the effect can have reached, so these loads are rarely wasted.
 	float4 a[4], b[4];
-	float4 *slotPtr = pool.state + 2ull * (slotBase + localBase + lane);
+	float4 *slotPtr = pool.state + 2ull * ((uint64_t)granule * kGranuleSlots + lane);
 #pragma unroll
-	for (int r = 0; r < 4; r++) {
-		if (localBase + r * 32 + lane < pe.slotsPost) ld_record(slotPtr + r * 64, a[r], b[r]);
-	}
+	for (int r = 0; r < 4; r++) ld_record(slotPtr + r * 64, a[r], b[r]);
+	const RoundConsts rc = tab.roundConsts[g];
+	uint32_t curBound = 0;
+	if (lane < 8) curBound = lane < 4 ? tab.state[g].boundsMin[lane] : tab.state[g].boundsMax[lane - 4];
+	if (rc.stamp != stamp || rc.round != round) return;
+	const uint32_t slotBase = rc.slotBase;
+	const uint32_t localBase = granule * kGranuleSlots - slotBase;
+	if (localBase >= rc.slotsPost) return;
+	StepConsts c;
+	step_consts_from(c, rc, tab, g);
+	struct { uint32_t slotsPost; } pe = { rc.slotsPost };
+
 	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
 	uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
 	uint32_t anyAlive = 0;
@@ -590,7 +620,7 @@ __global__ void __launch_bounds__(256, 3) k_integrate_sort(PoolPtrs pool, TableP
 		bool alive = false, dead = false, touched = false;
 		float4 ra = a[r], rb = b[r];
 		if (localBase + r * 32 + lane < pe.slotsPost) {
-			integrate_slot(c, ra, rb, alive, dead, touched);
+			integrate_slot<GP>(c, ra, rb, alive, dead, touched);
 			if (touched) st_record(slotPtr + r * 64, ra, rb);
 		}
 		if (alive) {
@@ -613,9 +643,8 @@ __global__ void __launch_bounds__(256, 3) k_integrate_sort(PoolPtrs pool, TableP
 			uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz : lane == 3 ? mnl
 				: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : mxl;
 			uint32_t *addr = lane < 4 ? &c.S->boundsMin[lane] : &c.S->boundsMax[lane - 4];
-			uint32_t cur = *(volatile uint32_t*)addr;
-			if (lane < 4) { if (v < cur) atomicMin(addr, v); }
-			else { if (v > cur) atomicMax(addr, v); }
+			if (lane < 4) { if (v < curBound) atomicMin(addr, v); }
+			else { if (v > curBound) atomicMax(addr, v); }
 		}
 	}
 }
@@ -653,23 +682,22 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 	const uint32_t granule = poolTile * 8 + (lane >> 2);
 	uint32_t g = pool.granuleOwner[granule];
 	bool active = false;
-	if (g != kNoOwner) active = tab.effectStamp[g] == stamp && round < tab.effectNumSubsteps[g];
-	if (!__any_sync(FULL_MASK, active)) return;
-
 	uint32_t slotBase = 0, wordBase = 0, word = 0;
-	PostEmit pe = { 0, 0, 0, 0, 0 };
+	struct { uint32_t slotsPost, topPost, parIn; bool grew; } pe = { 0, 0, 0, false };
 	bool large = false;
 	EffectState *S = nullptr;
-	if (active) {
-		const PlanRec *rec = &tab.plans[tab.effectPlanBase[g] + round];
-		const EffectParams *P = &tab.params[g];
-		S = &tab.state[g];
-		pe = post_emit_counts(rec, S);
-		slotBase = P->slotBase;
-		large = P->slotCapacity > kTileSlots;
-		wordBase = poolTile * kTileSlots + lane * 32 - slotBase; // first local slot of this lane's word
-		if (wordBase < pe.slotsPost) word = pool.deadMask[(poolTile * kTileSlots >> 5) + lane];
-		else active = false;
+	if (g != kNoOwner) {
+		const RoundConsts rc = tab.roundConsts[g];
+		active = rc.stamp == stamp && rc.round == round;
+		if (active) {
+			S = &tab.state[g];
+			pe.slotsPost = rc.slotsPost; pe.topPost = rc.topPost; pe.parIn = rc.flags & 1u; pe.grew = (rc.flags & 8u) != 0;
+			slotBase = rc.slotBase;
+			large = (rc.flags & 2u) != 0;
+			wordBase = poolTile * kTileSlots + lane * 32 - slotBase; // first local slot of this lane's word
+			if (wordBase < pe.slotsPost) word = pool.deadMask[(poolTile * kTileSlots >> 5) + lane];
+			else active = false;
+		}
 	}
 	if (!__any_sync(FULL_MASK, active)) return;
 	uint32_t d = __popc(word);
@@ -693,7 +721,7 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 		w &= w - 1;
 	}
 	// entries of a partially used new Particle4 stay at the bottom of the stack (:491-493)
-	if (wordBase == 0 && pe.nSpawn > pe.topIn) {
+	if (wordBase == 0 && pe.grew) {
 		for (uint32_t i = 0; i < pe.topPost; i++) pool.freeStack[slotBase + i] = pe.slotsPost - 4 + i;
 	}
 	// the lane that holds the last slot publishes the new counts
@@ -703,7 +731,7 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 	}
 }
 
-template <bool SORT>
+template <bool SORT, bool GP>
 __global__ void __launch_bounds__(256, 3) k_integrate(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch,
 	float camX, float camY, float camZ)
 {
@@ -718,42 +746,22 @@ __global__ void __launch_bounds__(256, 3) k_integrate(PoolPtrs pool, TablePtrs t
 
 	uint32_t g = pool.granuleOwner[granule];
 	bool active = false;
-	if (g != kNoOwner) active = tab.effectStamp[g] == stamp && round < tab.effectNumSubsteps[g];
-	if (!__syncthreads_or(active)) return;
-
-	uint32_t slotBase = 0, slotsPost = 0, topPost = 0, localBase = 0, parIn = 0, nSpawn = 0, topIn = 0;
-	bool large = false;
-	float dt = 0.0f, drag = 0.0f, lifeTime = 1.0f, lifeVar = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
-	uint32_t numGp = 0;
-	const PlanRec *rec = nullptr;
-	const EffectParams *P = nullptr;
-	const TypeDev *T = nullptr;
+	uint32_t slotBase = 0, slotsPost = 0, topPost = 0, localBase = 0, parIn = 0;
+	bool large = false, grew = false;
+	StepConsts c;
+	c.numGp = 0; c.dt = 0.0f; c.drag = 0.0f; c.lifeTime = 1.0f; c.lifeVar = 0.0f; c.gx = c.gy = c.gz = 0.0f;
 	EffectState *S = nullptr;
-	if (active) {
-		rec = &tab.plans[tab.effectPlanBase[g] + round];
-		P = &tab.params[g];
-		S = &tab.state[g];
-		T = &tab.types[P->typeIdx];
-		slotBase = P->slotBase;
-		large = P->slotCapacity > kTileSlots;
-		parIn = (rec->flags >> 1) & 1u;
-		nSpawn = rec->burst + rec->timer;
-		topIn = S->freeCount[parIn];
-		uint32_t blocksIn = S->slotCount[parIn] >> 2;
-		if (nSpawn > topIn) {
-			uint32_t nNew = nSpawn - topIn, newBlocks = (nNew + 3) >> 2;
-			slotsPost = (blocksIn + newBlocks) * 4;
-			topPost = newBlocks * 4 - nNew;
-		} else {
-			slotsPost = blocksIn * 4;
-			topPost = topIn - nSpawn;
+	if (g != kNoOwner) {
+		const RoundConsts rc = tab.roundConsts[g];
+		active = rc.stamp == stamp && rc.round == round;
+		if (active) {
+			step_consts_from(c, rc, tab, g);
+			S = c.S;
+			slotBase = rc.slotBase; slotsPost = rc.slotsPost; topPost = rc.topPost;
+			parIn = rc.flags & 1u; large = (rc.flags & 2u) != 0; grew = (rc.flags & 8u) != 0;
+			localBase = granule * kGranuleSlots - slotBase;
+			if (localBase >= slotsPost) active = false;
 		}
-		localBase = granule * kGranuleSlots - slotBase;
-		dt = rec->dt;
-		drag = T->drag; lifeTime = T->lifeTime; lifeVar = T->lifeTimeVariance;
-		gx = P->gravity[0]; gy = P->gravity[1]; gz = P->gravity[2];
-		numGp = T->numGravityPoints;
-		if (localBase >= slotsPost) active = false;
 	}
 	// A tile of a large effect that lies wholly beyond slotsPost has no work and nobody waits for it.
 	if (!__syncthreads_or(active)) return;
@@ -778,47 +786,11 @@ __global__ void __launch_bounds__(256, 3) k_integrate(PoolPtrs pool, TablePtrs t
 	float4 *stage = sStage + (SORT ? 0 : warp * 256);
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
-		bool alive = false, dead = false;
+		bool alive = false, dead = false, touched = false;
 		float4 ra = a[r], rb = b[r];
 		if (valid[r]) {
-			float life = ra.w;
-			bool wasFree = !(life < kHugeLifeCmp) && life == life; // parked at 1e20: unobservable, skip the arithmetic
-			if (life <= 0.0f) { dead = true; life = kHugeLife; }   // :556-567
-			if (!wasFree) {
-				float px = ra.x, py = ra.y, pz = ra.z;
-				float vx = rb.x, vy = rb.y, vz = rb.z, seed = rb.w;
-				float ax = gx, ay = gy, az = gz;                    // :574-579
-				ax -= vx * drag;
-				ay -= vy * drag;
-				az -= vz * drag;
-				for (uint32_t k = 0; k < numGp; k++) {              // :539-550, :581-590
-					const GravityPointDev &gp = T->gravityPoints[k];
-					float wp[3];
-#pragma unroll
-					for (int c = 0; c < 3; c++) {
-						float e3 = P->emitterToWorld[12 + c];
-						float pe3 = (rec->flags & 1u) ? S->prevEmitterToWorld[12 + c] : e3;
-						float v = e3 + (pe3 - e3);
-						v += P->emitterToWorld[0 + c] * gp.position[0];
-						v += P->emitterToWorld[4 + c] * gp.position[1];
-						v += P->emitterToWorld[8 + c] * gp.position[2];
-						wp[c] = v;
-					}
-					float dx = px - wp[0], dy = py - wp[1], dz = pz - wp[2];
-					float lenSq = (dx*dx + dy*dy + dz*dz) + gp.radius;
-					float weight = __fdiv_rn(__fdiv_rn(1.0f, __fsqrt_rn(lenSq)), lenSq) * gp.strength;
-					ax += dx * weight;
-					ay += dy * weight;
-					az += dz * weight;
-				}
-				vx += ax * dt; vy += ay * dt; vz += az * dt;        // :592-594
-				px += vx * dt; py += vy * dt; pz += vz * dt;        // :598-600
-				life -= __fdiv_rn(dt, seed * lifeVar + lifeTime);   // :604
-				ra = make_float4(px, py, pz, life);
-				rb = make_float4(vx, vy, vz, seed);
-				alive = life < kHugeLifeCmp;                        // :611
-				st_record(slotPtr + r * 64, ra, rb);
-			}
+			integrate_slot<GP>(c, ra, rb, alive, dead, touched);
+			if (touched) st_record(slotPtr + r * 64, ra, rb);
 		}
 		aliveMask[r] = __ballot_sync(FULL_MASK, alive);
 		deadMask[r] = __ballot_sync(FULL_MASK, dead);
@@ -875,7 +847,7 @@ __global__ void __launch_bounds__(256, 3) k_integrate(PoolPtrs pool, TablePtrs t
 		}
 	}
 	// entries of a partially used new Particle4 stay at the bottom of the stack (:491-493)
-	if (localBase == 0 && nSpawn > topIn && lane < topPost) {
+	if (localBase == 0 && grew && lane < topPost) {
 		pool.freeStack[slotBase + lane] = slotsPost - 4 + lane;
 	}
 
@@ -1045,10 +1017,10 @@ void launch_plan(cudaStream_t st, const TablePtrs &tab, const SystemWork *work, 
 	k_plan<<<div_up((uint64_t)numWork * 32, 128), 128, 0, st>>>(tab, work, numWork, active, stamp);
 }
 
-void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t round)
+void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
 {
 	if (!numActive) return;
-	k_emit_warp<<<div_up((uint64_t)numActive * 32, 256), 256, 0, st>>>(pool, tab, active, numActive, round);
+	k_emit_warp<<<div_up((uint64_t)numActive * 32, 256), 256, 0, st>>>(pool, tab, active, numActive, round, stamp);
 }
 
 void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs, uint32_t totalBlocks)
@@ -1058,13 +1030,15 @@ void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &t
 }
 
 void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool sortMode, const float camera[3])
+	uint32_t epoch, bool sortMode, bool gravityPoints, const float camera[3])
 {
 	if (!numPoolTiles) return;
 	if (sortMode) {
-		k_integrate_sort<<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, camera[0], camera[1], camera[2]);
+		if (gravityPoints) k_integrate_sort<true><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, camera[0], camera[1], camera[2]);
+		else k_integrate_sort<false><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, camera[0], camera[1], camera[2]);
 	} else {
-		k_integrate<false><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
+		if (gravityPoints) k_integrate<false, true><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
+		else k_integrate<false, false><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
 	}
 }
 

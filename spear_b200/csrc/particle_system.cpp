@@ -8,6 +8,7 @@
 #include "particle_system.h"
 
 #include <algorithm>
+#include <map>
 #include <stdlib.h>
 #include <string.h>
 
@@ -78,6 +79,7 @@ TablePtrs Context::tablePtrs()
 	t.params = dParams.ptr; t.state = dState.ptr; t.types = dTypes.ptr; t.systems = dSystems.ptr;
 	t.plans = dPlans.ptr;
 	t.effectStamp = dEffectStamp.ptr; t.effectPlanBase = dEffectPlanBase.ptr; t.effectNumSubsteps = dEffectNumSubsteps.ptr;
+	t.roundConsts = dRoundConsts.ptr;
 	return t;
 }
 
@@ -145,6 +147,7 @@ uint32_t Context::allocEffectGlobal()
 	else {
 		g = numEffectGlobals++;
 		hParams.resize(numEffectGlobals);
+		ownedSlots.resize(numEffectGlobals, 0);
 		dirtyParamsFlag.resize(numEffectGlobals, 0);
 		size_t keep = numEffectGlobals - 1;
 		dParams.reserve(numEffectGlobals, keep, stream);
@@ -152,6 +155,7 @@ uint32_t Context::allocEffectGlobal()
 		dEffectStamp.reserve(numEffectGlobals, keep, stream);
 		dEffectPlanBase.reserve(numEffectGlobals, keep, stream);
 		dEffectNumSubsteps.reserve(numEffectGlobals, keep, stream);
+		dRoundConsts.reserve(numEffectGlobals, keep, stream);
 	}
 	return g;
 }
@@ -173,10 +177,25 @@ void Context::growEffect(uint32_t g, uint32_t minCapacity, bool copyContents)
 		SPR_CUDA(cudaMemcpyAsync(dFreeStack + newBase, dFreeStack + oldBase, (size_t)oldCap * 4, cudaMemcpyDeviceToDevice, stream));
 	}
 	if (oldCap) freeRange(oldBase, oldCap);
-	ownerJobs.push_back({ newBase / kGranuleSlots, newCap / kGranuleSlots, g, 0 });
+	uint32_t owned = ownedSlots[g];
+	ownedSlots[g] = 0;
 	P.slotBase = newBase;
 	P.slotCapacity = newCap;
+	ensureOwned(g, owned);
 	markParamsDirty(g);
+}
+
+// Granule ownership is only set for the part of the range the effect can have reached
+// (its conservative slot bound, rounded up to a tile): the streaming kernels issue their record
+// loads as soon as they know a granule is owned, so owned-but-unused granules would be wasted reads.
+void Context::ensureOwned(uint32_t g, uint32_t slotUpperBound)
+{
+	const EffectParams &P = hParams[g];
+	uint64_t target = ((uint64_t)slotUpperBound + kTileSlots - 1) / kTileSlots * kTileSlots;
+	if (target > P.slotCapacity) target = P.slotCapacity;
+	if (target <= ownedSlots[g]) return;
+	ownerJobs.push_back({ (P.slotBase + ownedSlots[g]) / kGranuleSlots, (uint32_t)(target - ownedSlots[g]) / kGranuleSlots, g, 0 });
+	ownedSlots[g] = (uint32_t)target;
 }
 
 // Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
@@ -281,10 +300,11 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				uint64_t add = (uint64_t)nsub * (kMaxTimerSpawns + 3) + burst + 3;
 				uint64_t need = (uint64_t)E.slotUpperBound + add;
 				if (need > hParams[E.global].slotCapacity) {
-					if (E.simSteps == 0) { growEffect(E.global, pow2ceil(need), false); E.slotUpperBound = (uint32_t)need; }
+					if (E.simSteps == 0) { growEffect(E.global, pow2ceil(need), false); E.slotUpperBound = (uint32_t)need; ensureOwned(E.global, E.slotUpperBound); }
 					else { resolve.push_back({ &E, (uint32_t)add }); resolveGlobals.push_back(E.global); }
 				} else {
 					E.slotUpperBound = (uint32_t)need;
+					ensureOwned(E.global, E.slotUpperBound);
 				}
 				if (burst > 1024) {
 					ae.flags |= 1u;
@@ -310,6 +330,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			uint64_t need = (uint64_t)got[i].slotCount + resolve[i].add;
 			if (need > hParams[E.global].slotCapacity) growEffect(E.global, pow2ceil(need * 2), true);
 			E.slotUpperBound = (uint32_t)need;
+			ensureOwned(E.global, E.slotUpperBound);
 		}
 	}
 
@@ -354,14 +375,20 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	size_t oTypeVal = bw.put(typeVal.data(), typeVal.size());
 	size_t oSysIdx = bw.put(systemIdx.data(), systemIdx.size());
 	size_t oSysVal = bw.put(systemVal.data(), systemVal.size());
-	{ // jobs run in parallel on the device: for a range touched twice (freed, then reused) keep the last write
-		std::unordered_map<uint32_t, size_t> last;
-		for (size_t i = 0; i < ownerJobs.size(); i++) last[ownerJobs[i].start] = i;
-		if (last.size() != ownerJobs.size()) {
-			std::vector<FillJob> kept;
-			for (size_t i = 0; i < ownerJobs.size(); i++) if (last[ownerJobs[i].start] == i) kept.push_back(ownerJobs[i]);
-			ownerJobs.swap(kept);
+	// Fill jobs of one launch run in parallel; a range touched twice (freed, then re-owned) must see
+	// its jobs in order, so the list is cut into batches without overlaps, launched one after another.
+	std::vector<uint32_t> ownerBatchEnd;
+	{
+		std::map<uint32_t, uint32_t> inBatch; // start -> end of the ranges in the current batch
+		for (size_t i = 0; i < ownerJobs.size(); i++) {
+			uint32_t st = ownerJobs[i].start, en = st + ownerJobs[i].count;
+			auto it = inBatch.upper_bound(st);
+			bool overlap = (it != inBatch.end() && it->first < en);
+			if (!overlap && it != inBatch.begin()) { --it; overlap = it->second > st; }
+			if (overlap) { ownerBatchEnd.push_back((uint32_t)i); inBatch.clear(); }
+			inBatch[st] = en;
 		}
+		ownerBatchEnd.push_back((uint32_t)ownerJobs.size());
 	}
 	size_t oOwner = bw.put(ownerJobs.data(), ownerJobs.size());
 	size_t oEntries = bw.put(entries.data(), entries.size());
@@ -393,7 +420,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	if (nState) { launch_scatter_words(stream, dState.ptr, DPTR(uint32_t, oStateIdx), D + oStateVal, nState, sizeof(EffectState) / 4); launchCount++; }
 	if (nTypes) { launch_scatter_words(stream, dTypes.ptr, DPTR(uint32_t, oTypeIdx), D + oTypeVal, nTypes, sizeof(TypeDev) / 4); launchCount++; }
 	if (nSys) { launch_scatter_words(stream, dSystems.ptr, DPTR(uint32_t, oSysIdx), D + oSysVal, nSys, sizeof(SystemDev) / 4); launchCount++; }
-	if (nOwner) { launch_fill_jobs(stream, dGranuleOwner, DPTR(FillJob, oOwner), nOwner); launchCount++; }
+	for (uint32_t b0 = 0, bi = 0; nOwner && bi < ownerBatchEnd.size(); b0 = ownerBatchEnd[bi++]) {
+		uint32_t cnt = ownerBatchEnd[bi] - b0;
+		if (cnt) { launch_fill_jobs(stream, dGranuleOwner, DPTR(FillJob, oOwner) + b0, cnt); launchCount++; }
+	}
 
 	if (numPlans == 0) { SPR_CUDA(cudaGetLastError()); return; }
 
@@ -407,7 +437,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	TIMED(kKPlan, launch_plan(stream, tab, DPTR(SystemWork, oWork), (uint32_t)work.size(), dEntries, frameStamp));
 	const uint32_t poolTiles = (uint32_t)((poolUsed + kTileSlots - 1) / kTileSlots);
 	for (uint32_t round = 0; round < maxSub; round++) {
-		TIMED(kKEmit, launch_emit_warp(stream, pool, tab, dEntries, nEntries, round));
+		TIMED(kKEmit, launch_emit_warp(stream, pool, tab, dEntries, nEntries, round, frameStamp));
 		if (round == 0 && !burstJobs.empty()) {
 			TIMED(kKEmitBurst, launch_emit_burst(stream, pool, tab, dEntries, DPTR(BurstJob, oBurst), (uint32_t)burstJobs.size(), burstBlocks));
 		}
@@ -417,7 +447,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			SPR_CUDA(cudaMemsetAsync(dTileStatus[1], 0, poolCapacity / kTileSlots * 8, stream));
 			epoch = 1;
 		}
-		TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, camera));
+		TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, camera));
 		if (sortMode) TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch));
 	}
 	TIMED(kKFinalize, launch_finalize(stream, tab, dEntries, nEntries));
@@ -474,7 +504,7 @@ ParticleSystem::ParticleSystem(Context *c, const SprSystemsDesc &desc)
 ParticleSystem::~ParticleSystem()
 {
 	for (uint32_t id = 0; id < effects.size(); id++) if (effects[id].inUse) remove(id);
-	for (HostType &t : types) if (t.comp) { ctx->freeTypeGlobals.push_back(t.global); t.comp = nullptr; }
+	for (HostType &t : types) if (t.comp) { if (t.hasGravityPoints) ctx->typesWithGravityPoints--; ctx->freeTypeGlobals.push_back(t.global); t.comp = nullptr; }
 	ctx->freeSystemGlobals.push_back(systemIdx);
 }
 
@@ -535,6 +565,8 @@ uint32_t ParticleSystem::reserveEffectType(const SprParticleSystemComponent *c)
 			td.gravityPoints[i].radius = p.radius > 0.05f ? p.radius : 0.05f; // sf::max(p.radius, 0.05f)
 			td.gravityPoints[i].strength = -p.strength;
 		}
+		type.hasGravityPoints = td.numGravityPoints != 0;
+		if (type.hasGravityPoints) ctx->typesWithGravityPoints++;
 		ctx->typeIdx.push_back(type.global);
 		ctx->typeVal.push_back(td);
 	} else {
@@ -549,6 +581,7 @@ void ParticleSystem::releaseEffectTypeImp(uint32_t typeId)
 	HostType &type = types[typeId];
 	if (--type.refCount == 0) {
 		componentToType.erase((const void*)type.comp);
+		if (type.hasGravityPoints) ctx->typesWithGravityPoints--;
 		ctx->freeTypeGlobals.push_back(type.global);
 		type = HostType();
 		freeTypeIds.push_back(typeId);
@@ -644,6 +677,7 @@ void ParticleSystem::remove(uint32_t effectId)
 	EffectParams &P = ctx->hParams[E.global];
 	if (P.slotCapacity) ctx->freeRange(P.slotBase, P.slotCapacity);
 	P.slotCapacity = 0;
+	ctx->ownedSlots[E.global] = 0;
 	ctx->freeEffectGlobals.push_back(E.global);
 	E = HostEffect();
 	freeEffectIds.push_back(effectId);

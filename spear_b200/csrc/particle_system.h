@@ -88,6 +88,7 @@ struct HostType {
 	double renderOrder = 0.0;
 	uint32_t tiebreaker = 0;
 	float timeStep = 0.0f;
+	bool hasGravityPoints = false;
 	SprVertexTypeUbo typeUbo;
 	uint8_t lut[SPR_SPLINE_LUT_BYTES];
 };
@@ -158,11 +159,12 @@ struct Context {
 	DeviceArray<EffectParams> dParams;
 	DeviceArray<EffectState> dState;
 	DeviceArray<uint32_t> dEffectStamp, dEffectPlanBase, dEffectNumSubsteps;
+	DeviceArray<RoundConsts> dRoundConsts;
 	DeviceArray<TypeDev> dTypes;
 	DeviceArray<SystemDev> dSystems;
 	DeviceArray<PlanRec> dPlans;
 	std::vector<EffectParams> hParams;    // host copy, indexed by global effect index
-	std::vector<uint8_t> effectInUse;
+	std::vector<uint32_t> ownedSlots;     // per effect: slots [0, ownedSlots) have their granuleOwner entries set
 	std::vector<uint32_t> freeEffectGlobals, freeTypeGlobals, freeSystemGlobals;
 	uint32_t numEffectGlobals = 0, numTypeGlobals = 0, numSystemGlobals = 0;
 
@@ -182,6 +184,7 @@ struct Context {
 	PinnedArray<RenderGather> gatherH;
 	DeviceArray<RenderGather> gatherD;
 	DeviceArray<uint32_t> gatherIdxD;
+	uint32_t typesWithGravityPoints = 0; // live effect types with gravityPoints (selects the kernel variant)
 	uint32_t frameStamp = 0;
 	uint32_t epoch = 0;
 
@@ -211,6 +214,7 @@ struct Context {
 	void freeRange(uint32_t slotBase, uint32_t capacity);
 	void ensurePool(uint64_t slots);
 	void markParamsDirty(uint32_t g);
+	void ensureOwned(uint32_t g, uint32_t slotUpperBound);
 	void flushUploads();
 	void update(const UpdateRequest *reqs, uint32_t numReqs);
 	void gatherEffects(const uint32_t *globals, uint32_t n, RenderGather *out); // synchronous read-back

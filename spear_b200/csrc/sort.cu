@@ -229,35 +229,34 @@ __device__ inline void st_record_cs(float4 *p, const float4 &a, const float4 &b)
 
 __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles)
 {
-	SortTile st = tiles[blockIdx.x];
+	// four CTAs per 4096-key sort tile: 1024 particles per CTA, 4 per thread, all gathers in flight at once
+	SortTile st = tiles[blockIdx.x >> 2];
 	uint32_t g = segEffects[st.effect];
 	uint32_t alive = tab.state[g].aliveCount;
-	uint32_t begin = st.tile * kSortTileKeys;
+	uint32_t begin = st.tile * kSortTileKeys + (blockIdx.x & 3u) * 1024u;
 	if (begin >= alive) return;
-	uint32_t count = min(kSortTileKeys, alive - begin);
+	uint32_t count = min(1024u, alive - begin);
 	uint32_t segBase = tab.params[g].slotBase;
 	const uint32_t *vals = pool.vals + segBase + begin;
 	const float4 *state = pool.state + 2ull * segBase;
 	float4 *dst = pool.vertices + 8ull * (segBase + begin);
-	for (uint32_t base = 0; base < count; base += 4 * 256) {
-		uint32_t slot[4];
-		float4 a[4], b[4];
+	uint32_t slot[4];
+	float4 a[4], b[4];
 #pragma unroll
-		for (int u = 0; u < 4; u++) {
-			uint32_t i = base + u * 256 + threadIdx.x;
-			slot[u] = i < count ? vals[i] : 0xffffffffu;
-		}
+	for (int u = 0; u < 4; u++) {
+		uint32_t i = u * 256 + threadIdx.x;
+		slot[u] = i < count ? vals[i] : 0xffffffffu;
+	}
 #pragma unroll
-		for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_cg(state + 2ull * slot[u], a[u], b[u]);
+	for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_cg(state + 2ull * slot[u], a[u], b[u]);
 #pragma unroll
-		for (int u = 0; u < 4; u++) {
-			if (slot[u] == 0xffffffffu) continue;
-			float4 *d = dst + 8ull * (base + u * 256 + threadIdx.x);
-			st_record_cs(d, a[u], b[u]);
-			st_record_cs(d + 2, a[u], b[u]);
-			st_record_cs(d + 4, a[u], b[u]);
-			st_record_cs(d + 6, a[u], b[u]);
-		}
+	for (int u = 0; u < 4; u++) {
+		if (slot[u] == 0xffffffffu) continue;
+		float4 *d = dst + 8ull * (u * 256 + threadIdx.x);
+		st_record_cs(d, a[u], b[u]);
+		st_record_cs(d + 2, a[u], b[u]);
+		st_record_cs(d + 4, a[u], b[u]);
+		st_record_cs(d + 6, a[u], b[u]);
 	}
 }
 
@@ -287,7 +286,7 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 		T_END(2);
 	}
 	T_BEGIN(3);
-	k_expand_sorted<<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles);
+	k_expand_sorted<<<numTiles * 4, 256, 0, st>>>(pool, tab, segEffects, tiles);
 	T_END(3);
 	return 7;
 }
