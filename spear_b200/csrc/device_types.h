@@ -175,6 +175,7 @@ struct TablePtrs {
 	uint32_t *effectPlanBase;
 	uint32_t *effectNumSubsteps;
 	RoundConsts *roundConsts; // per effect, rewritten every sub-step round by k_emit_warp
+	uint32_t *effectAnyDead;  // per effect: some slot was freed in this round (lets k_dead_append skip its scan)
 };
 
 } // namespace spr

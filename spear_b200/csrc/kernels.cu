@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab,
 		rc.gx = c.P->gravity[0]; rc.gy = c.P->gravity[1]; rc.gz = c.P->gravity[2];
 		rc._pad = 0;
 		tab.roundConsts[rec->effect] = rc;
+		tab.effectAnyDead[rec->effect] = 0;
 	}
 }
 
@@ -612,7 +613,7 @@ __global__ void __launch_bounds__(256, GP ? 3 : 4) k_integrate_sort(PoolPtrs poo
 
 	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
 	uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
-	uint32_t anyAlive = 0;
+	uint32_t anyAlive = 0, anyDead = 0;
 	uint32_t *keyPtr = pool.keys + slotBase + localBase + lane;
 	const uint32_t maskWord = (slotBase + localBase) >> 5;
 #pragma unroll
@@ -633,7 +634,9 @@ __global__ void __launch_bounds__(256, GP ? 3 : 4) k_integrate_sort(PoolPtrs poo
 		uint32_t am = __ballot_sync(FULL_MASK, alive), dm = __ballot_sync(FULL_MASK, dead);
 		if (lane == 0) { pool.aliveMask[maskWord + r] = am; pool.deadMask[maskWord + r] = dm; }
 		anyAlive |= am;
+		anyDead |= dm;
 	}
+	if (anyDead && lane == 0) tab.effectAnyDead[g] = 1; // idempotent flag, a plain store is enough
 	if (anyAlive) {
 		mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny);
 		mnz = __reduce_min_sync(FULL_MASK, mnz); mnl = __reduce_min_sync(FULL_MASK, mnl);
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 	bool active = false;
 	uint32_t slotBase = 0, wordBase = 0, word = 0;
 	struct { uint32_t slotsPost, topPost, parIn; bool grew; } pe = { 0, 0, 0, false };
-	bool large = false;
+	bool large = false, anyDead = false;
 	EffectState *S = nullptr;
 	if (g != kNoOwner) {
 		const RoundConsts rc = tab.roundConsts[g];
@@ -695,20 +698,21 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 			slotBase = rc.slotBase;
 			large = (rc.flags & 2u) != 0;
 			wordBase = poolTile * kTileSlots + lane * 32 - slotBase; // first local slot of this lane's word
-			if (wordBase < pe.slotsPost) word = pool.deadMask[(poolTile * kTileSlots >> 5) + lane];
-			else active = false;
+			if (wordBase >= pe.slotsPost) active = false;
+			else if (tab.effectAnyDead[g]) { anyDead = true; word = pool.deadMask[(poolTile * kTileSlots >> 5) + lane]; }
 		}
 	}
 	if (!__any_sync(FULL_MASK, active)) return;
 	uint32_t d = __popc(word);
 	// exclusive prefix among the lower lanes of the same effect, and the effect's total inside the tile
 	uint32_t base = 0, tileTotal = 0;
-	for (int j = 0; j < 32; j++) {
+	const bool scan = __any_sync(FULL_MASK, anyDead); // nothing died in any effect of this tile: no ranks needed
+	for (int j = 0; scan && j < 32; j++) {
 		uint32_t oj = __shfl_sync(FULL_MASK, active ? g : kNoOwner, j);
 		uint32_t dj = __shfl_sync(FULL_MASK, d, j);
 		if (active && oj == g) { tileTotal += dj; if (j < (int)lane) base += dj; }
 	}
-	if (__any_sync(FULL_MASK, large)) { // a large effect owns the whole tile: all lanes agree
+	if (scan && __any_sync(FULL_MASK, large)) { // a large effect owns the whole tile: all lanes agree
 		uint32_t tileIdx = (poolTile * kTileSlots - slotBase) / kTileSlots;
 		base += tile_lookback1(pool.tileStatusDead, poolTile, __shfl_sync(FULL_MASK, tileIdx, 0), __shfl_sync(FULL_MASK, tileTotal, 0), epoch, lane);
 	}

@@ -80,6 +80,7 @@ TablePtrs Context::tablePtrs()
 	t.plans = dPlans.ptr;
 	t.effectStamp = dEffectStamp.ptr; t.effectPlanBase = dEffectPlanBase.ptr; t.effectNumSubsteps = dEffectNumSubsteps.ptr;
 	t.roundConsts = dRoundConsts.ptr;
+	t.effectAnyDead = dEffectAnyDead.ptr;
 	return t;
 }
 
@@ -156,6 +157,7 @@ uint32_t Context::allocEffectGlobal()
 		dEffectPlanBase.reserve(numEffectGlobals, keep, stream);
 		dEffectNumSubsteps.reserve(numEffectGlobals, keep, stream);
 		dRoundConsts.reserve(numEffectGlobals, keep, stream);
+		dEffectAnyDead.reserve(numEffectGlobals, keep, stream);
 	}
 	return g;
 }

@@ -160,6 +160,7 @@ struct Context {
 	DeviceArray<EffectState> dState;
 	DeviceArray<uint32_t> dEffectStamp, dEffectPlanBase, dEffectNumSubsteps;
 	DeviceArray<RoundConsts> dRoundConsts;
+	DeviceArray<uint32_t> dEffectAnyDead;
 	DeviceArray<TypeDev> dTypes;
 	DeviceArray<SystemDev> dSystems;
 	DeviceArray<PlanRec> dPlans;

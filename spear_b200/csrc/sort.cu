@@ -93,7 +93,7 @@ __device__ inline void st_relaxed_u32(uint32_t *p, uint32_t v)
 // One radix pass over digit `shift/8`. lookback: [numTiles][256] status words of THIS pass,
 // zero-initialised; word = [31:30] flag (1 aggregate, 2 inclusive prefix), [29:0] count.
 template <bool FIRST>
-__global__ void __launch_bounds__(256) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
+__global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	const uint32_t *keysIn, const uint32_t *valsIn, uint32_t *keysOut, uint32_t *valsOut,
 	const uint32_t *hist, uint32_t *lookback, uint32_t pass)
 {
@@ -121,8 +121,10 @@ __global__ void __launch_bounds__(256) k_sort_pass(PoolPtrs pool, TablePtrs tab,
 	for (uint32_t i = tid; i < 8 * 256; i += kSortThreads) sCnt[i] = 0;
 	__syncthreads();
 
-	// ---- load (warp-striped: warp w owns keys [w*512, w*512+512) of the tile) and rank
-	uint32_t key[kItemsPerThread], val[kItemsPerThread], rank[kItemsPerThread];
+	// ---- load keys (warp-striped: warp w owns keys [w*512, w*512+512) of the tile) and rank them.
+	// Register diet for 4 CTAs/SM: ranks and staging positions are 16-bit and packed in pairs, the
+	// slot values are only fetched once the keys have been staged.
+	uint32_t key[kItemsPerThread], rank2[kItemsPerThread / 2];
 	uint32_t okBits = 0;
 	const uint32_t *kin = keysIn + segBase + begin;
 	const uint32_t *vin = valsIn + segBase + begin;
@@ -130,16 +132,12 @@ __global__ void __launch_bounds__(256) k_sort_pass(PoolPtrs pool, TablePtrs tab,
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
 		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
 		bool ok = idx < count;
-		if (FIRST) {
-			ok = ok && ((mask[i] >> lane) & 1u);
-			val[i] = begin + idx;
-		} else {
-			val[i] = ok ? vin[idx] : 0u;
-		}
+		if (FIRST) ok = ok && ((mask[i] >> lane) & 1u);
 		key[i] = ok ? kin[idx] : 0xffffffffu;
 		okBits |= (ok ? 1u : 0u) << i;
 	}
 	uint32_t *cnt = sCnt + warp * 256;
+	const uint32_t ltMask = (1u << lane) - 1u;
 #pragma unroll
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
 		bool ok = (okBits >> i) & 1u;
@@ -147,9 +145,10 @@ __global__ void __launch_bounds__(256) k_sort_pass(PoolPtrs pool, TablePtrs tab,
 		uint32_t peers = __match_any_sync(FULL_MASK, d);
 		uint32_t before = ok ? cnt[d] : 0u;
 		__syncwarp();
-		rank[i] = before + __popc(peers & ((1u << lane) - 1u));
-		if (ok && (peers & ((1u << lane) - 1u)) == 0) cnt[d] = before + __popc(peers);
+		uint32_t rk = before + __popc(peers & ltMask);
+		if (ok && (peers & ltMask) == 0) cnt[d] = before + __popc(peers);
 		__syncwarp();
+		if (i & 1u) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
 	}
 	__syncthreads();
 
@@ -187,14 +186,28 @@ __global__ void __launch_bounds__(256) k_sort_pass(PoolPtrs pool, TablePtrs tab,
 	sGlobal[tid] = (int32_t)(hist[((size_t)st.effect * 4 + pass) * 256 + tid] + excl) - (int32_t)tileExcl;
 	__syncthreads();
 
-	// ---- stage the tile in sorted order
+	// ---- stage the tile in sorted order: keys first, then the values behind them
 #pragma unroll
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
 		if ((okBits >> i) & 1u) {
 			uint32_t d = (key[i] >> shift) & 255u;
-			uint32_t pos = sTileExcl[d] + sCnt[warp * 256 + d] + rank[i];
+			uint32_t rk = (i & 1u) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
+			uint32_t pos = sTileExcl[d] + sCnt[warp * 256 + d] + rk;
 			sKeys[pos] = key[i];
-			sVals[pos] = val[i];
+			if (i & 1u) rank2[i >> 1] = (rank2[i >> 1] & 0xffffu) | (pos << 16); else rank2[i >> 1] = (rank2[i >> 1] & 0xffff0000u) | pos;
+		}
+	}
+	{
+		uint32_t val[kItemsPerThread];
+#pragma unroll
+		for (uint32_t i = 0; i < kItemsPerThread; i++) {
+			uint32_t idx = warp * kWarpKeys + i * 32 + lane;
+			if (FIRST) val[i] = begin + idx;
+			else val[i] = ((okBits >> i) & 1u) ? vin[idx] : 0u;
+		}
+#pragma unroll
+		for (uint32_t i = 0; i < kItemsPerThread; i++) {
+			if ((okBits >> i) & 1u) sVals[(i & 1u) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu)] = val[i];
 		}
 	}
 	__syncthreads();
@@ -264,6 +277,12 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles, const SortTimingHooks *hooks)
 {
 	if (!numSegments || !numTiles) return 0;
+	static bool carveoutSet = false;
+	if (!carveoutSet) { // 4 CTAs x 43 KB of shared memory per SM
+		cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		carveoutSet = true;
+	}
 	void *tok = nullptr;
 #define T_BEGIN(k) do { if (hooks) tok = hooks->begin(hooks->ctx, k); } while (0)
 #define T_END(k) do { if (hooks) hooks->end(hooks->ctx, k, tok); } while (0)
