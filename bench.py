@@ -39,7 +39,7 @@ UNIT = "particle-steps/s"
 ALG_BYTES_SORTED = 220.0   # 60 update + 32 re-read in sorted order + 128 vertices
 ALG_BYTES_UNSORTED = 188.0
 # per-kernel algorithmic bytes per particle (DESIGN.md "Kernels"): pairs (key,slot) are excluded by section 8(d)
-KERNEL_ALG_BYTES = {"k_integrate": 60.0, "k_expand_sorted": 160.0, "k_integrate_unsorted": 188.0}
+KERNEL_ALG_BYTES = {"k_integrate": 60.0, "k_expand_sorted": 160.0, "k_expand_stream": 160.0}
 
 
 def measured_peak():
@@ -73,6 +73,9 @@ def workload_components(name):
             effects.append((comps[i % 4], abi.make_transform((4.0 * (i % 8), 0.0, 4.0 * (i // 8)))))
         return dict(systems=1, effects=effects, particles_per_effect=16384,
                     desc="C2: 64 emitters x 16k particles, 4 effect types (BASELINE configs[1])")
+    if name == "c5":
+        return dict(systems=1000, effects_per_system=100, comps=[S.comp_c5()], particles_per_effect=40,
+                    desc="C5 slice: 1000 systems x 100 effects, 20 die + 20 spawn per effect-step, ~40 live per effect (BASELINE configs[4] = 32M particles at 8 GPUs)")
     if name == "c4":
         comps = [S.comp_c2(k % 4, burst=65536) for k in range(8)]
         for k in range(4, 8):
@@ -151,11 +154,14 @@ def build_ours(ctx, wl):
         for i in range(wl["systems"]):
             s = ctx.create_system((1, 2 + i + wl.get("seed_offset", 0), 3, 4))
             comp = wl["comps"][i % len(wl["comps"])]
-            my = [s.add_effect(comp, abi.make_transform((4.0 * (i % 16), 0.0, 4.0 * (i // 16))))]
+            my = [s.add_effect(comp, abi.make_transform((4.0 * (i % 16) + 0.25 * k, 0.0, 4.0 * (i // 16))))
+                  for k in range(wl.get("effects_per_system", 1))]
             systems.append(s); ids.append(my)
     # dt = the largest per-effect timeStep (effects are jittered +0..10 %, ParticleSystem.cpp:744):
     # every effect does >= 1 sub-step per frame, a few do 2 now and then; particle-steps are counted exactly.
-    dt = max(s.effect_info(e).timeStep for s, my in zip(systems, ids) for e in my)
+    dt = max(s.effect_info(my[0]).timeStep for s, my in zip(systems, ids)) * (1.1 if wl.get("effects_per_system", 1) > 1 else 1.0)
+    if "effects" in wl:
+        dt = max(s.effect_info(e).timeStep for s, my in zip(systems, ids) for e in my)
     return systems, ids, dt
 
 
@@ -171,9 +177,11 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.workload or ("c3" if world == 1 else "c4")
     wl = workload_components(name)
-    if name == "c4":
+    if name in ("c4", "c5"):
         wl["seed_offset"] = rank * wl["systems"]
-    total_particles = wl["particles_per_effect"] * (len(wl["effects"]) if "effects" in wl else wl["systems"])
+    total_particles = wl["particles_per_effect"] * (len(wl["effects"]) if "effects" in wl else wl["systems"] * wl.get("effects_per_system", 1))
+    if name == "c5":
+        total_particles = wl["systems"] * wl["effects_per_system"] * 128
     ctx = particles.ParticleContext(device=local, sort_particles=not args.no_sort, max_particles_per_frame=1 << 30,
                                     initial_slot_capacity=int(total_particles * 1.1) + (1 << 16))
     ext = torch.cuda.ExternalStream(ctx.stream, device=local)
@@ -189,13 +197,14 @@ def run_ours(args, rank, world):
         frame[0] += 1
 
     def sim_steps():
-        return sum(s.effect_info(e).simSteps for s, e in all_effects)
+        return ctx.totals(alive=False)[0]
 
     def alive():
-        return sum(s.effect_info(e).aliveCount for s, e in all_effects)
+        return ctx.totals()[1]
 
     # population: burst step(s), untimed
-    step(); step()
+    for _ in range(6 if name == "c5" else 2):
+        step()
     ctx.synchronize()
     for _ in range(args.warmup):
         step()
@@ -308,8 +317,7 @@ def run_ours(args, rank, world):
         # dominant kernel by measured time
         kern = {k: {"ms_total": v[0], "launches": v[1]} for k, v in ktimes.items()}
         tot_k = sum(v["ms_total"] for v in kern.values()) or 1.0
-        alg_key = {"k_integrate": KERNEL_ALG_BYTES["k_integrate"] if sorted_mode else KERNEL_ALG_BYTES["k_integrate_unsorted"],
-                   "k_expand_sorted": KERNEL_ALG_BYTES["k_expand_sorted"]}
+        alg_key = dict(KERNEL_ALG_BYTES)
         for k, v in kern.items():
             v["share"] = v["ms_total"] / tot_k
             v["ms_per_launch"] = v["ms_total"] / max(v["launches"], 1)
@@ -375,7 +383,8 @@ def _cpu_worker(kind, name, idx, steps, warmup, scale, q):
         ids = [o.add_effect(c, t) for c, t in effs]
     else:
         o = orc.OracleSystem(kind, (1, 2 + idx, 3, 4))
-        ids = [o.add_effect(wl["comps"][idx % len(wl["comps"])], abi.make_transform((idx, 0, 0)))]
+        ids = [o.add_effect(wl["comps"][idx % len(wl["comps"])], abi.make_transform((idx + 0.25 * k, 0, 0)))
+               for k in range(wl.get("effects_per_system", 1))]
     dt = max(o.effect_info(e).timeStep for e in ids)
     fa = abi.make_frame_args(dt, camera=CAMERA)
     o.bench_steps(ids, fa, 2 + warmup)          # burst + warm-up, untimed
@@ -419,8 +428,8 @@ def cpu_baseline(name, seconds=15.0):
         cores = 1
     else:
         cores = os.cpu_count() or 1
-        kind, v, secs, wall = cpu_run("c4", steps=60, warmup=3, procs=cores)
-        sample = "%d of the 128 instances (65536 particles each), one reference system per host core, 60 timed steps" % cores
+        kind, v, secs, wall = cpu_run(name, steps=60, warmup=6, procs=cores)
+        sample = "%d of the per-GPU system instances of %s, one reference system per host core, 60 timed steps" % (cores, name)
     return {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "seconds": secs}
 
 
@@ -458,7 +467,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4"])
+    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-sort", action="store_true", help="strict drop-in stream (slot order), no per-particle depth sort")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -335,6 +335,10 @@ SPR_API const char *sprGetLastError(void);
 /* Number of kernel launches this context has enqueued so far (bench `gpu_launches`). */
 SPR_API uint64_t sprContextLaunchCount(SprContext *ctx);
 
+/* Totals over every live effect of the context: simulateParticlesImp calls issued so far and
+ * the current number of live particles (one device read-back). Either pointer may be NULL. */
+SPR_API int sprContextGetTotals(SprContext *ctx, uint64_t *outSimSteps, uint64_t *outAliveParticles);
+
 /* Measurement hooks (no reference counterpart): CUDA events around every kernel launch
  * of the context, accumulated per kernel name. Used by bench.py for the roofline. */
 SPR_API int sprContextEnableKernelTiming(SprContext *ctx, int enable);

@@ -68,7 +68,7 @@ SPR_API uint64_t sprContextLaunchCount(SprContext *ctx) { return ctx ? ctx->ctx.
 
 static const char *const kKernelNames[16] = {
 	"k_scatter_words", "k_plan", "k_emit_warp", "k_emit_burst", "k_integrate", "k_finalize", "sort", "k_gather_render",
-	"k_pack_runs", "k_expand_runs", "k_sort_hist", "k_sort_scan", "k_sort_pass", "k_expand_sorted", "k_dead_append", "" };
+	"k_pack_runs", "k_expand_runs", "k_sort_hist", "k_sort_scan", "k_sort_pass", "k_expand_sorted", "k_dead_append", "k_expand_stream" };
 
 SPR_API int sprContextEnableKernelTiming(SprContext *ctx, int enable)
 {
@@ -96,6 +96,23 @@ SPR_API int sprSystemCreate(SprContext *ctx, const SprSystemsDesc *desc, SprSyst
 {
 	REQUIRE(ctx && desc && out);
 	return guarded([&] { *out = new SprSystem(&ctx->ctx, *desc); });
+}
+
+SPR_API int sprContextGetTotals(SprContext *ctx, uint64_t *outSimSteps, uint64_t *outAliveParticles)
+{
+	REQUIRE(ctx);
+	return guarded([&] {
+		if (outSimSteps) *outSimSteps = ctx->ctx.totalSimSteps;
+		if (outAliveParticles) {
+			std::vector<uint32_t> globals;
+			for (uint32_t g = 0; g < ctx->ctx.numEffectGlobals; g++) if (ctx->ctx.effectLive[g]) globals.push_back(g);
+			std::vector<RenderGather> got(globals.size());
+			ctx->ctx.gatherEffects(globals.data(), (uint32_t)globals.size(), got.data());
+			uint64_t total = 0;
+			for (const RenderGather &r : got) total += r.aliveCount;
+			*outAliveParticles = total;
+		}
+	});
 }
 
 SPR_API int sprSystemDestroy(SprSystem *sys) { REQUIRE(sys); return guarded([&] { delete sys; }); }

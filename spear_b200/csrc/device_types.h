@@ -158,8 +158,9 @@ struct PoolPtrs {
 	uint32_t *keys;           // sort mode: depth keys (descending-order transform applied); written per SLOT by
 	                          // k_integrate_sort, compacted by the first radix pass
 	uint32_t *vals;           // sort mode: local slot indices, compacted/sorted alongside the keys
-	uint32_t *aliveMask;      // sort mode: one word per 32 slots, bit = slot emits a particle this step (:611)
-	uint32_t *deadMask;       // sort mode: one word per 32 slots, bit = slot was freed this step (:556-567)
+	uint32_t *aliveMask;      // one word per 32 slots, bit = slot emits a particle this step (:611)
+	uint32_t *deadMask;       // one word per 32 slots, bit = slot was freed this step (:556-567)
+	uint32_t *wordAliveBase;  // stream mode: rank in the effect's stream of the first live slot of each 32-slot word
 	const uint32_t *granuleOwner;
 	unsigned long long *tileStatusAlive;
 	unsigned long long *tileStatusDead;

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab,
 		rc.slotBase = c.P->slotBase;
 		rc.slotsPost = slots;
 		rc.topPost = topPost;
-		rc.flags = par | (c.P->slotCapacity > kTileSlots ? 2u : 0u) | ((rec->flags & 1u) << 2) | (n > c.top ? 8u : 0u) | (c.T->numGravityPoints << 8);
+		rc.flags = par | (c.P->slotCapacity > kTileSlots ? 2u : 0u) | ((rec->flags & 1u) << 2) | (n > c.top ? 8u : 0u) | (c.P->slotCapacity == kGranuleSlots ? 16u : 0u) | (c.T->numGravityPoints << 8);
 		rc.typeIdx = c.P->typeIdx; rc.planIdx = ae.planBase + round;
 		rc.dt = rec->dt; rc.drag = c.T->drag; rc.lifeTime = c.T->lifeTime; rc.lifeVar = c.T->lifeTimeVariance;
 		rc.gx = c.P->gravity[0]; rc.gy = c.P->gravity[1]; rc.gz = c.P->gravity[2];
@@ -444,49 +444,6 @@ __device__ inline void st_record(float4 *p, const float4 &a, const float4 &b)
 {
 	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
 		:: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
-}
-
-// Chained (decoupled look-back) exclusive prefix over the tiles of one large effect, for the
-// alive and the dead counts at once. Status word: [63:34] launch epoch, [33:32] flag
-// (1 aggregate, 2 inclusive prefix), [31:0] value. Called by one full warp.
-__device__ inline void tile_lookback(unsigned long long *stA, unsigned long long *stD, uint32_t poolTile, uint32_t tileIdx,
-	uint32_t aggA, uint32_t aggD, uint32_t epoch, uint32_t lane, uint32_t &exclA, uint32_t &exclD)
-{
-	const unsigned long long tag = (unsigned long long)epoch << 34;
-	const unsigned long long fAgg = 1ull << 32, fIncl = 2ull << 32;
-	exclA = 0; exclD = 0;
-	if (tileIdx == 0) {
-		if (lane == 0) { st_status(stA + poolTile, tag | fIncl | aggA); st_status(stD + poolTile, tag | fIncl | aggD); }
-		return;
-	}
-	if (lane == 0) { st_status(stA + poolTile, tag | fAgg | aggA); st_status(stD + poolTile, tag | fAgg | aggD); }
-	int32_t rel = (int32_t)tileIdx - 1 - (int32_t)lane; // tile (within the effect) this lane inspects
-	// The two words of a tile are published by separate stores, so each chain is resolved on its
-	// own flags: a reader may see a predecessor's alive word already inclusive and its dead word
-	// still an aggregate.
-	bool doneA = false, doneD = false;
-	while (!doneA || !doneD) {
-		unsigned long long va = tag | fIncl, vd = tag | fIncl; // virtual zero prefix in front of tile 0
-		if (rel >= 0) {
-			uint32_t t = poolTile - (tileIdx - (uint32_t)rel);
-			if (!doneA) do { va = ld_status(stA + t); } while ((va >> 34) != epoch);
-			if (!doneD) do { vd = ld_status(stD + t); } while ((vd >> 34) != epoch);
-		}
-		if (!doneA) {
-			uint32_t incl = __ballot_sync(FULL_MASK, ((va >> 32) & 3u) == 2u);
-			uint32_t upTo = incl ? (uint32_t)(__ffs(incl) - 1) : 31u;
-			exclA += __reduce_add_sync(FULL_MASK, lane <= upTo ? (uint32_t)va : 0u);
-			doneA = incl != 0;
-		}
-		if (!doneD) {
-			uint32_t incl = __ballot_sync(FULL_MASK, ((vd >> 32) & 3u) == 2u);
-			uint32_t upTo = incl ? (uint32_t)(__ffs(incl) - 1) : 31u;
-			exclD += __reduce_add_sync(FULL_MASK, lane <= upTo ? (uint32_t)vd : 0u);
-			doneD = incl != 0;
-		}
-		rel -= 32;
-	}
-	if (lane == 0) { st_status(stA + poolTile, tag | fIncl | (exclA + aggA)); st_status(stD + poolTile, tag | fIncl | (exclD + aggD)); }
 }
 
 // Per-effect constants of one sub-step, as every slot of the effect needs them.
@@ -560,32 +517,15 @@ __device__ __forceinline__ void step_consts_from(StepConsts &c, const RoundConst
 	c.numGp = rc.flags >> 8;
 }
 
-// Slot / free-list sizes after the emission of a sub-step.
-struct PostEmit { uint32_t slotsPost, topPost, topIn, nSpawn, parIn; };
-__device__ __forceinline__ PostEmit post_emit_counts(const PlanRec *rec, const EffectState *S)
-{
-	PostEmit r;
-	r.parIn = (rec->flags >> 1) & 1u;
-	r.nSpawn = rec->burst + rec->timer;
-	r.topIn = S->freeCount[r.parIn];
-	uint32_t blocksIn = S->slotCount[r.parIn] >> 2;
-	if (r.nSpawn > r.topIn) {
-		uint32_t nNew = r.nSpawn - r.topIn, newBlocks = (nNew + 3) >> 2;
-		r.slotsPost = (blocksIn + newBlocks) * 4;
-		r.topPost = newBlocks * 4 - nNew;
-	} else {
-		r.slotsPost = blocksIn * 4;
-		r.topPost = r.topIn - r.nSpawn;
-	}
-	return r;
-}
-
-template <bool GP>
-// Sort mode: a pure streaming pass, no barrier and no cross-tile dependency. One warp per
-// 128-slot granule: integrate, store the state, write the depth key of every slot and the
-// alive / dead ballots. Compaction is left to the first radix pass (its scatter is dense by
-// construction), the free-list append to k_dead_append.
-__global__ void __launch_bounds__(256, GP ? 3 : 4) k_integrate_sort(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round,
+// The integration pass of both modes: pure streaming, no barrier and no cross-tile dependency.
+// One warp per 128-slot granule: integrate (:552-605), store the state, write the alive / dead
+// ballots and -- in sort mode (KEYS) -- the depth key of every live slot. Everything order
+// dependent is left to the cheap follow-up kernels that only read the ballots: k_dead_append
+// (free-list append, alive ranks, counts) and then either the radix sort (whose first scatter is
+// dense by construction, i.e. it IS the compaction) or k_expand_stream (slot-order stream).
+// Effects that fit one granule (TINY) are finished right here, inside the warp.
+template <bool GP, bool TINY, bool KEYS>
+__global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round,
 	float camX, float camY, float camZ)
 {
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -616,6 +556,8 @@ __global__ void __launch_bounds__(256, GP ? 3 : 4) k_integrate_sort(PoolPtrs poo
 	uint32_t anyAlive = 0, anyDead = 0;
 	uint32_t *keyPtr = pool.keys + slotBase + localBase + lane;
 	const uint32_t maskWord = (slotBase + localBase) >> 5;
+	const bool tiny = TINY && (rc.flags & 16u); // the whole effect is this one granule: sort and expand in the warp
+	uint32_t am[4], dm[4], key[4];
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
 		bool alive = false, dead = false, touched = false;
@@ -624,19 +566,70 @@ __global__ void __launch_bounds__(256, GP ? 3 : 4) k_integrate_sort(PoolPtrs poo
 			integrate_slot<GP>(c, ra, rb, alive, dead, touched);
 			if (touched) st_record(slotPtr + r * 64, ra, rb);
 		}
+		key[r] = 0;
 		if (alive) {
 			uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z), el = enc_float(ra.w);
 			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez); mnl = min(mnl, el);
 			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez); mxl = max(mxl, el);
-			float dx = camX - ra.x, dy = camY - ra.y, dz = camZ - ra.z;
-			keyPtr[r * 32] = ~enc_float(dx*dx + dy*dy + dz*dz);  // sf::lengthSq (src/sf/Vector.h:99), descending
+			if (KEYS) {
+				float dx = camX - ra.x, dy = camY - ra.y, dz = camZ - ra.z;
+				key[r] = ~enc_float(dx*dx + dy*dy + dz*dz);       // sf::lengthSq (src/sf/Vector.h:99), descending
+				if (!tiny) keyPtr[r * 32] = key[r];
+			}
 		}
-		uint32_t am = __ballot_sync(FULL_MASK, alive), dm = __ballot_sync(FULL_MASK, dead);
-		if (lane == 0) { pool.aliveMask[maskWord + r] = am; pool.deadMask[maskWord + r] = dm; }
-		anyAlive |= am;
-		anyDead |= dm;
+		if (TINY) { a[r] = ra; b[r] = rb; }
+		am[r] = __ballot_sync(FULL_MASK, alive); dm[r] = __ballot_sync(FULL_MASK, dead);
+		if (lane == 0 && !tiny) { pool.aliveMask[maskWord + r] = am[r]; pool.deadMask[maskWord + r] = dm[r]; }
+		anyAlive |= am[r];
+		anyDead |= dm[r];
 	}
-	if (anyDead && lane == 0) tab.effectAnyDead[g] = 1; // idempotent flag, a plain store is enough
+	if (tiny) {
+		const uint32_t ltMask = (1u << lane) - 1u;
+		// free-list append in ascending slot order (:556-567) and the leftover entries (:491-493)
+		uint32_t run = rc.topPost;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			if (dm[r] >> lane & 1u) pool.freeStack[slotBase + run + __popc(dm[r] & ltMask)] = r * 32 + lane;
+			run += __popc(dm[r]);
+		}
+		if ((rc.flags & 8u) && lane < rc.topPost) pool.freeStack[slotBase + lane] = rc.slotsPost - 4 + lane;
+		// sort mode: stable depth rank by counting, #{j : key_j < key_i, or equal and slot_j < slot_i};
+		// stream mode: ascending slot order (:611-665)
+		uint32_t rank[4] = { 0, 0, 0, 0 };
+		if (!KEYS) {
+			uint32_t runA = 0;
+#pragma unroll
+			for (int r = 0; r < 4; r++) { rank[r] = runA + __popc(am[r] & ltMask); runA += __popc(am[r]); }
+		}
+#pragma unroll
+		for (int rj = 0; KEYS && rj < 4; rj++) {
+			uint32_t m = am[rj];
+			while (m) {
+				uint32_t lj = __ffs(m) - 1;
+				m &= m - 1;
+				uint32_t kj = __shfl_sync(FULL_MASK, key[rj], lj);
+				uint32_t sj = rj * 32 + lj;
+#pragma unroll
+				for (int r = 0; r < 4; r++) rank[r] += (kj < key[r] || (kj == key[r] && sj < (uint32_t)(r * 32) + lane)) ? 1u : 0u;
+			}
+		}
+		uint32_t total = __popc(am[0]) + __popc(am[1]) + __popc(am[2]) + __popc(am[3]);
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			if (am[r] >> lane & 1u) {
+				float4 *d = pool.vertices + 8ull * (slotBase + rank[r]);
+				st_record(d, a[r], b[r]); st_record(d + 2, a[r], b[r]); st_record(d + 4, a[r], b[r]); st_record(d + 6, a[r], b[r]);
+				if (KEYS) pool.vals[slotBase + rank[r]] = r * 32 + lane;
+			}
+		}
+		if (lane == 0) {
+			const uint32_t parIn = rc.flags & 1u;
+			c.S->aliveCount = total;                              // :670
+			c.S->freeCount[parIn ^ 1u] = run;
+			c.S->slotCount[parIn ^ 1u] = rc.slotsPost;
+		}
+	}
+	if (anyDead && lane == 0 && !tiny) tab.effectAnyDead[g] = 1; // idempotent flag, a plain store is enough
 	if (anyAlive) {
 		mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny);
 		mnz = __reduce_min_sync(FULL_MASK, mnz); mnl = __reduce_min_sync(FULL_MASK, mnl);
@@ -674,9 +667,12 @@ __device__ inline uint32_t tile_lookback1(unsigned long long *st, uint32_t poolT
 	return excl;
 }
 
-// Sort mode: free-list append in ascending slot order (:556-567) from the dead ballots, and the
-// effect's new slot / free counts. One warp per 1024-slot pool tile, lane = one 32-slot mask word.
-// Touches 4 bytes per 32 slots, so it is cheap even though it keeps the chained scan.
+// Everything order dependent, from the ballots alone: the free-list append in ascending slot order
+// (:556-567), the effect's new slot / free counts and -- in stream mode (ALIVE) -- the rank of every
+// 32-slot word's first live particle in the effect's stream (:611-665) plus gpuParticles.size (:670).
+// One warp per 1024-slot pool tile, lane = one mask word; chained look-back across the tiles of a
+// large effect. Touches 8 bytes per 32 slots, so the chain is cheap.
+template <bool ALIVE>
 __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles)
 {
 	const uint32_t lane = threadIdx.x & 31;
@@ -685,13 +681,13 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 	const uint32_t granule = poolTile * 8 + (lane >> 2);
 	uint32_t g = pool.granuleOwner[granule];
 	bool active = false;
-	uint32_t slotBase = 0, wordBase = 0, word = 0;
+	uint32_t slotBase = 0, wordBase = 0, word = 0, aword = 0;
 	struct { uint32_t slotsPost, topPost, parIn; bool grew; } pe = { 0, 0, 0, false };
 	bool large = false, anyDead = false;
 	EffectState *S = nullptr;
 	if (g != kNoOwner) {
 		const RoundConsts rc = tab.roundConsts[g];
-		active = rc.stamp == stamp && rc.round == round;
+		active = rc.stamp == stamp && rc.round == round && !(rc.flags & 16u); // single-granule effects are finished by k_integrate_sort
 		if (active) {
 			S = &tab.state[g];
 			pe.slotsPost = rc.slotsPost; pe.topPost = rc.topPost; pe.parIn = rc.flags & 1u; pe.grew = (rc.flags & 8u) != 0;
@@ -699,15 +695,51 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 			large = (rc.flags & 2u) != 0;
 			wordBase = poolTile * kTileSlots + lane * 32 - slotBase; // first local slot of this lane's word
 			if (wordBase >= pe.slotsPost) active = false;
-			else if (tab.effectAnyDead[g]) { anyDead = true; word = pool.deadMask[(poolTile * kTileSlots >> 5) + lane]; }
+			else {
+				if (tab.effectAnyDead[g]) { anyDead = true; word = pool.deadMask[(poolTile * kTileSlots >> 5) + lane]; }
+				if (ALIVE) aword = pool.aliveMask[(poolTile * kTileSlots >> 5) + lane];
+			}
 		}
 	}
 	if (!__any_sync(FULL_MASK, active)) return;
 	uint32_t d = __popc(word);
+	// a tile wholly inside one large effect (the common case for big effects) scans with log-step shuffles
+	const bool uniform = __all_sync(FULL_MASK, large);
+	if (ALIVE) { // same two-level scan for the alive ballots; always needed in stream mode
+		uint32_t na = __popc(aword), baseA = 0, tileA = 0;
+		if (uniform) {
+			uint32_t incl = active ? na : 0u;
+#pragma unroll
+			for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t o = __shfl_up_sync(FULL_MASK, incl, dlt); if ((int)lane >= dlt) incl += o; }
+			baseA = incl - (active ? na : 0u);
+			tileA = __shfl_sync(FULL_MASK, incl, 31);
+		} else {
+			for (int j = 0; j < 32; j++) {
+				uint32_t oj = __shfl_sync(FULL_MASK, active ? g : kNoOwner, j);
+				uint32_t aj = __shfl_sync(FULL_MASK, na, j);
+				if (active && oj == g) { tileA += aj; if (j < (int)lane) baseA += aj; }
+			}
+		}
+		if (__any_sync(FULL_MASK, large)) {
+			uint32_t tileIdx = (poolTile * kTileSlots - slotBase) / kTileSlots;
+			baseA += tile_lookback1(pool.tileStatusAlive, poolTile, __shfl_sync(FULL_MASK, tileIdx, 0), __shfl_sync(FULL_MASK, tileA, 0), epoch, lane);
+		}
+		if (active) {
+			pool.wordAliveBase[(poolTile * kTileSlots >> 5) + lane] = baseA;
+			if (pe.slotsPost - 1 - wordBase < 32) S->aliveCount = baseA + na;
+		}
+	}
 	// exclusive prefix among the lower lanes of the same effect, and the effect's total inside the tile
 	uint32_t base = 0, tileTotal = 0;
 	const bool scan = __any_sync(FULL_MASK, anyDead); // nothing died in any effect of this tile: no ranks needed
-	for (int j = 0; scan && j < 32; j++) {
+	if (scan && uniform) {
+		uint32_t incl = active ? d : 0u;
+#pragma unroll
+		for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t o = __shfl_up_sync(FULL_MASK, incl, dlt); if ((int)lane >= dlt) incl += o; }
+		base = incl - (active ? d : 0u);
+		tileTotal = __shfl_sync(FULL_MASK, incl, 31);
+	}
+	for (int j = 0; scan && !uniform && j < 32; j++) {
 		uint32_t oj = __shfl_sync(FULL_MASK, active ? g : kNoOwner, j);
 		uint32_t dj = __shfl_sync(FULL_MASK, d, j);
 		if (active && oj == g) { tileTotal += dj; if (j < (int)lane) base += dj; }
@@ -735,170 +767,36 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 	}
 }
 
-template <bool SORT, bool GP>
-__global__ void __launch_bounds__(256, 3) k_integrate(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch,
-	float camX, float camY, float camZ)
+// Stream mode: the 4x vertex expansion in ascending slot order (:607-665). One warp per granule,
+// no dependency on any other warp: the rank of a word's first live particle comes from
+// k_dead_append, the rest is a popcount. A lane re-reads its 32-byte record (256-bit, streaming) and
+// stores it four times; for a dense population the 32 lanes fill 4 KB of contiguous vertex stream.
+__global__ void __launch_bounds__(256) k_expand_stream(PoolPtrs pool, TablePtrs tab, uint32_t stamp)
 {
-	__shared__ float4 sStage[SORT ? 1 : 8 * 256]; // per warp: 128 records x 2 float4
-	__shared__ uint32_t sOwner[8], sAlive[8], sDead[8];
-	__shared__ uint32_t sTileExcl[2];
-
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t poolTile = blockIdx.x;
-	const uint32_t granule = poolTile * 8 + warp;
-	const uint32_t ltMask = (1u << lane) - 1u;
-
+	const uint32_t granule = blockIdx.x * 8 + warp;
 	uint32_t g = pool.granuleOwner[granule];
-	bool active = false;
-	uint32_t slotBase = 0, slotsPost = 0, topPost = 0, localBase = 0, parIn = 0;
-	bool large = false, grew = false;
-	StepConsts c;
-	c.numGp = 0; c.dt = 0.0f; c.drag = 0.0f; c.lifeTime = 1.0f; c.lifeVar = 0.0f; c.gx = c.gy = c.gz = 0.0f;
-	EffectState *S = nullptr;
-	if (g != kNoOwner) {
-		const RoundConsts rc = tab.roundConsts[g];
-		active = rc.stamp == stamp && rc.round == round;
-		if (active) {
-			step_consts_from(c, rc, tab, g);
-			S = c.S;
-			slotBase = rc.slotBase; slotsPost = rc.slotsPost; topPost = rc.topPost;
-			parIn = rc.flags & 1u; large = (rc.flags & 2u) != 0; grew = (rc.flags & 8u) != 0;
-			localBase = granule * kGranuleSlots - slotBase;
-			if (localBase >= slotsPost) active = false;
-		}
-	}
-	// A tile of a large effect that lies wholly beyond slotsPost has no work and nobody waits for it.
-	if (!__syncthreads_or(active)) return;
-
-	// ---- load: four 256-bit loads per lane in flight before any use
+	if (g == kNoOwner) return;
+	const uint32_t word0 = granule * (kGranuleSlots / 32);
 	float4 a[4], b[4];
-	bool valid[4];
-	float4 *slotPtr = pool.state + 2ull * (slotBase + localBase + lane);
+	const float4 *slotPtr = pool.state + 2ull * ((uint64_t)granule * kGranuleSlots + lane);
+#pragma unroll
+	for (int r = 0; r < 4; r++) ld_record(slotPtr + r * 64, a[r], b[r]);
+	uint32_t am = lane < 4 ? pool.aliveMask[word0 + lane] : 0u;
+	uint32_t base = lane < 4 ? pool.wordAliveBase[word0 + lane] : 0u;
+	const RoundConsts rc = tab.roundConsts[g];
+	if (rc.stamp != stamp || (rc.flags & 16u)) return; // not simulated this frame, or finished inside k_integrate_pass
+	const uint32_t localBase = granule * kGranuleSlots - rc.slotBase;
+	if (localBase >= rc.slotsPost) return;
+	float4 *dst = pool.vertices + 8ull * rc.slotBase;
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
-		uint32_t li = localBase + r * 32 + lane;
-		valid[r] = active && li < slotsPost;
-		if (valid[r]) ld_record(slotPtr + r * 64, a[r], b[r]);
-	}
-
-	// ---- integrate; state goes straight back, what the output needs is kept small:
-	// sort mode keeps one key per slot, stream mode stages the record at its warp-local rank
-	uint32_t aliveMask[4], deadMask[4], key[4];
-	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
-	uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
-	uint32_t nA = 0, nD = 0;
-	float4 *stage = sStage + (SORT ? 0 : warp * 256);
-#pragma unroll
-	for (int r = 0; r < 4; r++) {
-		bool alive = false, dead = false, touched = false;
-		float4 ra = a[r], rb = b[r];
-		if (valid[r]) {
-			integrate_slot<GP>(c, ra, rb, alive, dead, touched);
-			if (touched) st_record(slotPtr + r * 64, ra, rb);
+		uint32_t m = __shfl_sync(FULL_MASK, am, r), bs = __shfl_sync(FULL_MASK, base, r);
+		if (localBase + r * 32 >= rc.slotsPost) m = 0; // words past the end were not rewritten this step
+		if (m >> lane & 1u) {
+			float4 *d = dst + 8ull * (bs + __popc(m & ((1u << lane) - 1u)));
+			st_record(d, a[r], b[r]); st_record(d + 2, a[r], b[r]); st_record(d + 4, a[r], b[r]); st_record(d + 6, a[r], b[r]);
 		}
-		aliveMask[r] = __ballot_sync(FULL_MASK, alive);
-		deadMask[r] = __ballot_sync(FULL_MASK, dead);
-		if (alive) {                                                // :620-621
-			uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z), el = enc_float(ra.w);
-			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez); mnl = min(mnl, el);
-			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez); mxl = max(mxl, el);
-			if (SORT) {
-				float dx = camX - ra.x, dy = camY - ra.y, dz = camZ - ra.z;
-				key[r] = ~enc_float(dx*dx + dy*dy + dz*dz);      // sf::lengthSq (src/sf/Vector.h:99), descending
-			} else {
-				uint32_t k = nA + __popc(aliveMask[r] & ltMask);
-				stage[2 * k] = ra;
-				stage[2 * k + 1] = rb;
-			}
-		}
-		nA += __popc(aliveMask[r]);
-		nD += __popc(deadMask[r]);
-	}
-
-	// ---- ranks: warps of the same effect inside the CTA, then tiles of a large effect
-	if (lane == 0) { sOwner[warp] = active ? g : kNoOwner; sAlive[warp] = nA; sDead[warp] = nD; }
-	__syncthreads();
-	uint32_t baseA = 0, baseD = 0, tileA = 0, tileD = 0;
-#pragma unroll
-	for (uint32_t w = 0; w < 8; w++) {
-		bool same = active && sOwner[w] == g;
-		if (same && w < warp) { baseA += sAlive[w]; baseD += sDead[w]; }
-		if (same) { tileA += sAlive[w]; tileD += sDead[w]; }
-	}
-	if (large) { // CTA-uniform: a large effect owns whole tiles
-		uint32_t tileIdx = (poolTile * kTileSlots - slotBase) / kTileSlots;
-		if (warp == 0) {
-			uint32_t eA, eD;
-			tile_lookback(pool.tileStatusAlive, pool.tileStatusDead, poolTile, tileIdx, tileA, tileD, epoch, lane, eA, eD);
-			if (lane == 0) { sTileExcl[0] = eA; sTileExcl[1] = eD; }
-		}
-		__syncthreads();
-		baseA += sTileExcl[0];
-		baseD += sTileExcl[1];
-	}
-	if (!active) return;
-
-	// ---- free-list append, ascending slot order (:556-567), behind the post-emission stack
-	if (nD) {
-		uint32_t run = baseD;
-#pragma unroll
-		for (int r = 0; r < 4; r++) {
-			if (deadMask[r] >> lane & 1u) {
-				uint32_t rank = run + __popc(deadMask[r] & ltMask);
-				pool.freeStack[slotBase + topPost + rank] = localBase + r * 32 + lane;
-			}
-			run += __popc(deadMask[r]);
-		}
-	}
-	// entries of a partially used new Particle4 stay at the bottom of the stack (:491-493)
-	if (localBase == 0 && grew && lane < topPost) {
-		pool.freeStack[slotBase + lane] = slotsPost - 4 + lane;
-	}
-
-	// ---- output
-	if (SORT) {
-		uint32_t run = baseA;
-#pragma unroll
-		for (int r = 0; r < 4; r++) {
-			if (aliveMask[r] >> lane & 1u) {
-				uint32_t rank = run + __popc(aliveMask[r] & ltMask);
-				pool.keys[slotBase + rank] = key[r];
-				pool.vals[slotBase + rank] = localBase + r * 32 + lane;
-			}
-			run += __popc(aliveMask[r]);
-		}
-	} else {
-		// 4x expansion of the staged run with fully coalesced 512-byte warp stores
-		// (:611-665; the run of a warp is contiguous in the stream)
-		__syncwarp();
-		float4 *dst = pool.vertices + 8ull * (slotBase + baseA);
-		uint32_t total = nA * 8;
-		for (uint32_t q = lane; q < total; q += 32) {
-			dst[q] = stage[((q >> 3) << 1) | (q & 1u)];
-		}
-	}
-
-	// ---- bounds (:532, :620-663): warp redux, then an atomic only when it extends the box
-	if (nA) {
-		mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny);
-		mnz = __reduce_min_sync(FULL_MASK, mnz); mnl = __reduce_min_sync(FULL_MASK, mnl);
-		mxx = __reduce_max_sync(FULL_MASK, mxx); mxy = __reduce_max_sync(FULL_MASK, mxy);
-		mxz = __reduce_max_sync(FULL_MASK, mxz); mxl = __reduce_max_sync(FULL_MASK, mxl);
-		if (lane < 8) {
-			uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz : lane == 3 ? mnl
-				: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : mxl;
-			uint32_t *addr = lane < 4 ? &S->boundsMin[lane] : &S->boundsMax[lane - 4];
-			uint32_t cur = *(volatile uint32_t*)addr;
-			if (lane < 4) { if (v < cur) atomicMin(addr, v); }
-			else { if (v > cur) atomicMax(addr, v); }
-		}
-	}
-
-	// ---- the warp that holds the last slot publishes the effect's new counts (:670)
-	if (lane == 0 && slotsPost - 1 - localBase < kGranuleSlots) {
-		S->aliveCount = baseA + nA;
-		S->freeCount[parIn ^ 1u] = topPost + baseD + nD;
-		S->slotCount[parIn ^ 1u] = slotsPost;
 	}
 }
 
@@ -1034,22 +932,37 @@ void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &t
 }
 
 void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool sortMode, bool gravityPoints, const float camera[3])
+	uint32_t epoch, bool sortMode, bool gravityPoints, bool tinyEffects, const float camera[3])
 {
 	if (!numPoolTiles) return;
-	if (sortMode) {
-		if (gravityPoints) k_integrate_sort<true><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, camera[0], camera[1], camera[2]);
-		else k_integrate_sort<false><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, camera[0], camera[1], camera[2]);
-	} else {
-		if (gravityPoints) k_integrate<false, true><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
-		else k_integrate<false, false><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, epoch, camera[0], camera[1], camera[2]);
+	(void)epoch;
+	const float cx = camera[0], cy = camera[1], cz = camera[2];
+#define SPR_LAUNCH_PASS(GP, TINY, KEYS) k_integrate_pass<GP, TINY, KEYS><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, cx, cy, cz)
+	int variant = (gravityPoints ? 4 : 0) | (tinyEffects ? 2 : 0) | (sortMode ? 1 : 0);
+	switch (variant) {
+	case 0: SPR_LAUNCH_PASS(false, false, false); break;
+	case 1: SPR_LAUNCH_PASS(false, false, true); break;
+	case 2: SPR_LAUNCH_PASS(false, true, false); break;
+	case 3: SPR_LAUNCH_PASS(false, true, true); break;
+	case 4: SPR_LAUNCH_PASS(true, false, false); break;
+	case 5: SPR_LAUNCH_PASS(true, false, true); break;
+	case 6: SPR_LAUNCH_PASS(true, true, false); break;
+	default: SPR_LAUNCH_PASS(true, true, true); break;
 	}
+#undef SPR_LAUNCH_PASS
 }
 
-void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch)
+void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch, bool aliveScan)
 {
 	if (!numPoolTiles) return;
-	k_dead_append<<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
+	if (aliveScan) k_dead_append<true><<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
+	else k_dead_append<false><<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
+}
+
+void launch_expand_stream(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp)
+{
+	if (!numPoolTiles) return;
+	k_expand_stream<<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp);
 }
 
 void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive)

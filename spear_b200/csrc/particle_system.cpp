@@ -56,7 +56,7 @@ Context::~Context()
 	cudaStreamSynchronize(stream);
 	cudaFree(dSlotState); cudaFree(dFreeStack); cudaFree(dVertices);
 	cudaFree(dKeys[0]); cudaFree(dKeys[1]); cudaFree(dVals[0]); cudaFree(dVals[1]);
-	cudaFree(dAliveMask); cudaFree(dDeadMask);
+	cudaFree(dAliveMask); cudaFree(dDeadMask); cudaFree(dWordAliveBase);
 	cudaFree(dGranuleOwner); cudaFree(dTileStatus[0]); cudaFree(dTileStatus[1]);
 	cudaEventDestroy(stagingEvent[0]); cudaEventDestroy(stagingEvent[1]);
 	if (ownStream) cudaStreamDestroy(stream);
@@ -67,7 +67,7 @@ PoolPtrs Context::poolPtrs() const
 	PoolPtrs p;
 	p.state = dSlotState; p.freeStack = dFreeStack; p.vertices = dVertices;
 	p.keys = dKeys[0]; p.vals = dVals[0];
-	p.aliveMask = dAliveMask; p.deadMask = dDeadMask;
+	p.aliveMask = dAliveMask; p.deadMask = dDeadMask; p.wordAliveBase = dWordAliveBase;
 	p.granuleOwner = dGranuleOwner;
 	p.tileStatusAlive = dTileStatus[0]; p.tileStatusDead = dTileStatus[1];
 	return p;
@@ -112,10 +112,15 @@ void Context::ensurePool(uint64_t slots)
 	if (flags & SPR_CTX_SORT_PARTICLES) {
 		for (int i = 0; i < 2; i++) {
 			regrow(dKeys[i], poolCapacity, cap, 0, -1, stream);
-			regrow(dVals[i], poolCapacity, cap, 0, -1, stream);
+			regrow(dVals[i], poolCapacity, cap, i == 0 ? used : 0, -1, stream); // vals[0] holds the sorted slot order of every effect
 		}
-		regrow(dAliveMask, poolCapacity / 32, cap / 32, 0, 0, stream);
-		regrow(dDeadMask, poolCapacity / 32, cap / 32, 0, 0, stream);
+	}
+	{
+		// the ballots (and, in stream mode, the word ranks) are rewritten by every simulated step, but an
+		// effect that is not simulated in the frame after a pool growth still needs its old ones
+		regrow(dAliveMask, poolCapacity / 32, cap / 32, poolCapacity / 32, 0, stream);
+		regrow(dDeadMask, poolCapacity / 32, cap / 32, poolCapacity / 32, 0, stream);
+		if (!(flags & SPR_CTX_SORT_PARTICLES)) regrow(dWordAliveBase, poolCapacity / 32, cap / 32, poolCapacity / 32, 0, stream);
 	}
 	poolCapacity = cap;
 }
@@ -149,6 +154,7 @@ uint32_t Context::allocEffectGlobal()
 		g = numEffectGlobals++;
 		hParams.resize(numEffectGlobals);
 		ownedSlots.resize(numEffectGlobals, 0);
+		effectLive.resize(numEffectGlobals, 0);
 		dirtyParamsFlag.resize(numEffectGlobals, 0);
 		size_t keep = numEffectGlobals - 1;
 		dParams.reserve(numEffectGlobals, keep, stream);
@@ -159,6 +165,7 @@ uint32_t Context::allocEffectGlobal()
 		dRoundConsts.reserve(numEffectGlobals, keep, stream);
 		dEffectAnyDead.reserve(numEffectGlobals, keep, stream);
 	}
+	effectLive[g] = 1;
 	return g;
 }
 
@@ -179,6 +186,8 @@ void Context::growEffect(uint32_t g, uint32_t minCapacity, bool copyContents)
 		SPR_CUDA(cudaMemcpyAsync(dFreeStack + newBase, dFreeStack + oldBase, (size_t)oldCap * 4, cudaMemcpyDeviceToDevice, stream));
 	}
 	if (oldCap) freeRange(oldBase, oldCap);
+	if (oldCap == kGranuleSlots) numTinyEffects--;
+	if (newCap == kGranuleSlots) numTinyEffects++;
 	uint32_t owned = ownedSlots[g];
 	ownedSlots[g] = 0;
 	P.slotBase = newBase;
@@ -202,7 +211,7 @@ void Context::ensureOwned(uint32_t g, uint32_t slotUpperBound)
 
 // Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
 enum { kKScatter = 0, kKPlan, kKEmit, kKEmitBurst, kKIntegrate, kKFinalize, kKSort, kKGather, kKPack, kKExpandRuns,
-	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14 };
+	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15 };
 
 cudaEvent_t Context::timingBegin(int kernel)
 {
@@ -316,6 +325,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				}
 				E.firstEmit = false;
 				E.simSteps += nsub;
+				totalSimSteps += nsub;
 				E.uploadFrameIndex = 0;                      // :679
 				E.boundsToWorld = E.particlesToWorld;        // gpuBounds uses the matrix of the simulated step (:675-677)
 			}
@@ -342,8 +352,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	if (sortMode) {
 		for (const ActiveEntry &ae : entries) {
 			if (!ae.numSubsteps) continue;
-			uint32_t seg = (uint32_t)segEffects.size();
-			(void)seg;
+			if (hParams[ae.effect].slotCapacity == kGranuleSlots) continue; // sorted and expanded inside k_integrate_sort
 			segEffects.push_back(ae.effect);
 		}
 	}
@@ -449,9 +458,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			SPR_CUDA(cudaMemsetAsync(dTileStatus[1], 0, poolCapacity / kTileSlots * 8, stream));
 			epoch = 1;
 		}
-		TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, camera));
-		if (sortMode) TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch));
+		TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, numTinyEffects != 0, camera));
+		TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch, !sortMode));
 	}
+	if (!sortMode) TIMED(kKExpandStream, launch_expand_stream(stream, pool, tab, poolTiles, frameStamp));
 	TIMED(kKFinalize, launch_finalize(stream, tab, dEntries, nEntries));
 
 	if (sortMode && !segEffects.empty()) {
@@ -678,9 +688,11 @@ void ParticleSystem::remove(uint32_t effectId)
 	releaseEffectTypeImp(E.typeId);
 	EffectParams &P = ctx->hParams[E.global];
 	if (P.slotCapacity) ctx->freeRange(P.slotBase, P.slotCapacity);
+	if (P.slotCapacity == kGranuleSlots) ctx->numTinyEffects--;
 	P.slotCapacity = 0;
 	ctx->ownedSlots[E.global] = 0;
 	ctx->freeEffectGlobals.push_back(E.global);
+	ctx->effectLive[E.global] = 0;
 	E = HostEffect();
 	freeEffectIds.push_back(effectId);
 }

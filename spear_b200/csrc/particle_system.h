@@ -141,6 +141,8 @@ struct Context {
 	bool ownStream = false;
 	uint32_t numSms = 148;
 	uint64_t launchCount = 0;
+	uint64_t totalSimSteps = 0;            // simulateParticlesImp calls issued so far (all effects)
+	std::vector<uint8_t> effectLive;       // per effect global: currently in use
 
 	// ---- slot pool
 	uint64_t poolCapacity = 0;     // slots
@@ -150,7 +152,7 @@ struct Context {
 	float4 *dVertices = nullptr;
 	uint32_t *dKeys[2] = { nullptr, nullptr };
 	uint32_t *dVals[2] = { nullptr, nullptr };
-	uint32_t *dAliveMask = nullptr, *dDeadMask = nullptr;
+	uint32_t *dAliveMask = nullptr, *dDeadMask = nullptr, *dWordAliveBase = nullptr;
 	uint32_t *dGranuleOwner = nullptr;
 	unsigned long long *dTileStatus[2] = { nullptr, nullptr };
 	std::vector<std::vector<uint32_t>> freeRanges; // per log2(capacity): free slotBase values
@@ -185,6 +187,7 @@ struct Context {
 	PinnedArray<RenderGather> gatherH;
 	DeviceArray<RenderGather> gatherD;
 	DeviceArray<uint32_t> gatherIdxD;
+	uint32_t numTinyEffects = 0;          // live effects whose whole range is one 128-slot granule
 	uint32_t typesWithGravityPoints = 0; // live effect types with gravityPoints (selects the kernel variant)
 	uint32_t frameStamp = 0;
 	uint32_t epoch = 0;

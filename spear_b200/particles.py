@@ -24,7 +24,7 @@ EXPORTS = [
     "sprUpdateParticles", "sprUpdateParticlesBatch", "sprRenderMain", "sprGetEffectInfo", "sprReadFreeIndices",
     "sprReadVertexStream", "sprReadSlots", "sprReadStreamSlots", "sprGetRngState", "sprGetEffectTypeLut",
     "sprGetEffectTypeUbo", "sprGetEffectDeviceView", "sprPackRuns", "sprExpandRuns",
-    "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType", "sprRenderMainBatch",
+    "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType", "sprRenderMainBatch", "sprContextGetTotals",
 ]
 
 
@@ -68,6 +68,7 @@ def _load():
     lib.sprPackRuns.argtypes = [vp, P(vp), P(u32), u32, vp, u64, vp, P(u64)]
     lib.sprExpandRuns.argtypes = [vp, vp, u64, vp]
     lib.sprBakeEffectType.argtypes = [P(abi.ParticleSystemComponent), u32, vp, P(abi.VertexTypeUbo)]
+    lib.sprContextGetTotals.argtypes = [vp, P(u64), P(u64)]
     lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
     lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
     return lib
@@ -137,6 +138,12 @@ class ParticleContext:
     @property
     def launch_count(self):
         return int(lib.sprContextLaunchCount(self.h))
+
+    def totals(self, alive=True):
+        """(sim steps issued so far, live particles now) over every live effect of the context."""
+        steps, n = C.c_uint64(), C.c_uint64()
+        _check(lib.sprContextGetTotals(self.h, C.byref(steps), C.byref(n) if alive else None))
+        return int(steps.value), int(n.value)
 
     def enable_kernel_timing(self, enable=True):
         _check(lib.sprContextEnableKernelTiming(self.h, 1 if enable else 0))
