@@ -42,6 +42,15 @@ ALG_BYTES_UNSORTED = 188.0
 KERNEL_ALG_BYTES = {"k_integrate": 60.0, "k_expand_sorted": 160.0, "k_expand_stream": 160.0}
 
 
+def profiled_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (C3 only)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -109,9 +118,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken in [t0, t1] (perf_counter), all samples if no window is given."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -122,7 +132,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.05):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -202,6 +214,8 @@ def run_ours(args, rank, world):
     def alive():
         return ctx.totals()[1]
 
+    sampler = ClockSampler(local)
+    sampler.start()
     # population: burst step(s), untimed
     for _ in range(6 if name == "c5" else 2):
         step()
@@ -219,24 +233,36 @@ def run_ours(args, rank, world):
             torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream
-    sampler = ClockSampler(local)
-    sampler.start()
     steps0, launches0 = sim_steps(), ctx.launch_count
     ctx.enable_kernel_timing(True)
     ctx.kernel_times(reset=True)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     ev0.record(ext)
     for _ in range(args.steps):
         step()
     ev1.record(ext)
     barrier()
+    tw1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     ktimes = ctx.kernel_times(reset=True)
     ctx.enable_kernel_timing(False)
-    clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     effect_steps = sim_steps() - steps0
+    # nvidia-smi samples every 100 ms; a timed region shorter than that gets its clocks from the same
+    # steps repeated back to back right after it (identical load, not part of any reported time)
+    clock_window = (tw0, tw1)
+    if tw1 - tw0 < 0.7:
+        tx0 = time.perf_counter()
+        while time.perf_counter() - tx0 < 0.8:
+            for _ in range(args.steps):
+                step()
+            ctx.synchronize()
+        clock_window = (tw0, time.perf_counter())
+        steps_after_clock_loop = True
+    else:
+        steps_after_clock_loop = False
     # every effect holds a constant population in the timed window; sub-steps are counted exactly
     particle_steps = 0
     for s, e in all_effects:
@@ -262,6 +288,8 @@ def run_ours(args, rank, world):
     ctx.synchronize()
     assert n_records > 0
     t1 = time.perf_counter()
+    clocks = sampler.stop(*clock_window)
+    clocks["window"] = "timed region" + (" + the same steps repeated for 0.8 s right after it (region shorter than the 100 ms sampling period)" if steps_after_clock_loop else "")
     e2e_ms = (t1 - t0) * 1e3
     e2e_particle_steps = (sim_steps() - e_steps0) * per_effect_alive
     n_eff = len(all_effects)
@@ -331,7 +359,9 @@ def run_ours(args, rank, world):
         roof = None
         if dom:
             roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": profiled_traffic(dom) if name == "c3" and sorted_mode else None,
+                    "traffic_source": "profiles/r01_ncu_c3_sorted_step.md (ncu --set full, bytes per launch)" if name == "c3" and sorted_mode else None,
+                    "peak_source": peak_src,
                     "alg_bytes_per_particle": alg_key[dom],
                     "step": {"alg_bytes_per_particle_step": alg, "achieved": value / world * alg / 1e9,
                              "frac": value / world * alg / 1e9 / peak,
