@@ -276,6 +276,10 @@ def run_ours(args, rank, world):
     # Multi-system workloads use the batched forms (one read-back for all systems).
     from tests_render_args import make_render_args  # noqa: E402
     ra = make_render_args()
+    for k in range(4):  # an all-inclusive frustum: the bench population falls for as long as the bench runs
+        for pl in range(4):
+            ra.frustum.side[k][pl] = 1.0 if k == 3 else 0.0
+            ra.frustum.caps[k][pl] = 1.0 if k == 3 else 0.0
     vis = [np.ascontiguousarray(my, dtype=np.uint32) for my in ids]
     barrier()
     e_steps0 = sim_steps()
@@ -286,7 +290,7 @@ def run_ours(args, rank, world):
         outs = ctx.render_prepared(batch, ra)
         n_records += sum(o.numRecords for o in outs)
     ctx.synchronize()
-    assert n_records > 0
+    assert n_records > 0, "renderMain produced no draw records"
     t1 = time.perf_counter()
     clocks = sampler.stop(*clock_window)
     clocks["window"] = "timed region" + (" + the same steps repeated for 0.8 s right after it (region shorter than the 100 ms sampling period)" if steps_after_clock_loop else "")
