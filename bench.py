@@ -309,7 +309,11 @@ def run_ours(args, rank, world):
     h2d = n_eff * 16 + len(systems) * 16 + n_eff * 4  # ActiveEntry + SystemWork per frame, ids for the gather
     d2h = n_eff * 60                                   # RenderGather per visible effect
 
-    # ---- optional: multi-GPU draw-stream assembly (all-gather of sorted 32-byte runs, expand after)
+    # ---- multi-GPU draw-stream assembly: every rank ends up with the whole draw stream (4 vertices per
+    # particle, rank-major). Two implementations, both timed:
+    #   nccl : sprPackRuns -> NCCL all_gather of the 32-byte records -> sprExpandRuns
+    #   fused: sprRunBufferPack -> 4-byte all_reduce as the cross-rank barrier -> sprExpandFromPeers, ONE kernel
+    #          that reads every rank's run out of peer memory over NVLink and expands it while it arrives
     gather = None
     if world > 1:
         cap = int(n_alive * 1.02) + 1024
@@ -318,35 +322,77 @@ def run_ours(args, rank, world):
         verts = torch.empty((world * cap * 4, 8), dtype=torch.float32, device="cuda")
         sys_list = [s for s, e in all_effects]
         eff_list = [e for s, e in all_effects]
+        pack_list = ctx.make_pack_list(sys_list, eff_list)
+        bufs = [ctx.run_buffer_create(cap) for _ in range(2)]
+        my_handles = [ctx.run_buffer_ipc_handle(b) for b in bufs]
+        all_handles = [None] * world
+        dist.all_gather_object(all_handles, my_handles)
+        peer_ptrs = [[ctx.run_buffer_ptr(bufs[k]) if r == rank else ctx.run_buffer_open_peer(all_handles[r][k]) for r in range(world)]
+                     for k in range(2)]
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        verts_f = torch.empty((world * cap * 4, 8), dtype=torch.float32, device="cuda")
+        total_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+        kstep = [0]
         with torch.cuda.stream(ext):
             def gstep():
                 step()
                 ctx.pack_runs(sys_list, eff_list, mine.data_ptr(), cap, None, want_total=False)
                 dist.all_gather_into_tensor(allrec, mine)
                 ctx.expand_runs(allrec.data_ptr(), world * cap, verts.data_ptr())
-            for _ in range(2):
-                gstep()
+
+            def fstep(do_step=True):
+                k = kstep[0] & 1
+                kstep[0] += 1
+                if do_step:
+                    step()
+                ctx.run_buffer_pack(pack_list, bufs[k])
+                dist.all_reduce(flag)           # stream-ordered cross-rank barrier: every rank's pack is complete
+                ctx.expand_from_peers(peer_ptrs[k], verts_f.data_ptr(), world * cap, total_dev.data_ptr())
+
+            def timed(fn):
+                for _ in range(2):
+                    fn()
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                gs0 = sim_steps()
+                g0.record(ext)
+                for _ in range(args.steps):
+                    fn()
+                g1.record(ext)
+                barrier()
+                return g0.elapsed_time(g1), (sim_steps() - gs0) * per_effect_alive
+
+            gms, gps = timed(gstep)
+            fms, fps = timed(fstep)
+            # same state through both paths: the fused stream must equal the NCCL one (padding removed)
+            ctx.pack_runs(sys_list, eff_list, mine.data_ptr(), cap, None, want_total=False)
+            dist.all_gather_into_tensor(allrec, mine)
+            ctx.expand_runs(allrec.data_ptr(), world * cap, verts.data_ptr())
+            fstep(do_step=False)
             barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            gs0 = sim_steps()
-            g0.record(ext)
-            for _ in range(args.steps):
-                gstep()
-            g1.record(ext)
-            barrier()
-        gms = g0.elapsed_time(g1)
-        gps = (sim_steps() - gs0) * per_effect_alive
-        gather = {"ms_per_step": gms / args.steps, "particle_steps_this_rank": gps,
-                  "nvlink_bytes_in_per_step": (world - 1) * cap * 32}
+            counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(counts, torch.tensor([int(n_alive)], dtype=torch.int64, device="cuda"))
+            counts = [int(c.item()) for c in counts]
+            ok, off = True, 0
+            for r, c in enumerate(counts):
+                a = verts_f[off * 4:(off + c) * 4].view(torch.int32)
+                b = verts[r * cap * 4:(r * cap + c) * 4].view(torch.int32)
+                ok = ok and bool(torch.equal(a, b))
+                off += c
+            ok = ok and int(total_dev.item()) == sum(counts)
+        gather = {"ms_per_step": gms / args.steps, "particle_steps_this_rank": gps, "fused_ms_per_step": fms / args.steps,
+                  "fused_particle_steps_this_rank": fps, "fused_matches_nccl": ok,
+                  "nvlink_bytes_in_per_step": int(sum(c for r, c in enumerate(counts) if r != rank) * 32)}
 
     # ---- max over ranks / aggregate
     if world > 1:
-        t = torch.tensor([ms, e2e_ms, gather["ms_per_step"] * args.steps], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_ms, gather["ms_per_step"] * args.steps, gather["fused_ms_per_step"] * args.steps], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, gms_tot = [float(x) for x in t.tolist()]
-        c = torch.tensor([particle_steps, e2e_particle_steps, gather["particle_steps_this_rank"], float(launches)], dtype=torch.float64, device="cuda")
+        ms, e2e_ms, gms_tot, fms_tot = [float(x) for x in t.tolist()]
+        c = torch.tensor([particle_steps, e2e_particle_steps, gather["particle_steps_this_rank"], float(launches),
+                          gather["fused_particle_steps_this_rank"], 1.0 if gather["fused_matches_nccl"] else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        particle_steps, e2e_particle_steps, g_total_ps, launches_all = [float(x) for x in c.tolist()]
+        particle_steps, e2e_particle_steps, g_total_ps, launches_all, f_total_ps, f_ok = [float(x) for x in c.tolist()]
     else:
         launches_all = float(launches)
 
@@ -398,11 +444,19 @@ def run_ours(args, rank, world):
             "kernel_timing": "CUDA event pair around every launch, over the same K steps repeated immediately after the timed region",
         }
         if gather is not None:
-            g_val = g_total_ps / (gms_tot * 1e-3)
-            out["gather"] = {"value_with_gather": g_val, "unit": UNIT, "ms_per_step": gms_tot / args.steps,
-                             "nvlink_bytes_in_per_gpu_per_step": gather["nvlink_bytes_in_per_step"],
-                             "nvlink_gbs_in_per_gpu": gather["nvlink_bytes_in_per_step"] / (gms_tot / args.steps * 1e-3) / 1e9,
-                             "note": "step + sprPackRuns (32 B sorted records) + NCCL all_gather + sprExpandRuns (4x) of the whole %d-GPU draw stream on every GPU" % world}
+            nv = gather["nvlink_bytes_in_per_step"]
+            out["gather"] = {
+                "unit": UNIT,
+                "nccl": {"value_with_gather": g_total_ps / (gms_tot * 1e-3), "ms_per_step": gms_tot / args.steps,
+                         "note": "step + sprPackRuns (32 B sorted records) + NCCL all_gather + sprExpandRuns (4x) of the whole %d-GPU draw stream on every GPU" % world},
+                "fused": {"value_with_gather": f_total_ps / (fms_tot * 1e-3), "ms_per_step": fms_tot / args.steps,
+                          "assembly_ms": (fms_tot - ms) / args.steps,
+                          "nvlink_gbs_in_per_gpu_during_assembly": nv / max((fms_tot - ms) / args.steps * 1e-3, 1e-9) / 1e9,
+                          "nvlink_roofline": {"peak_gbs": 770.0, "peak_source": "B200_PROFILING.md measured peer copy per direction",
+                                              "frac": nv / max((fms_tot - ms) / args.steps * 1e-3, 1e-9) / 1e9 / 770.0},
+                          "matches_nccl_path_bit_for_bit": f_ok == world,
+                          "note": "step + sprRunBufferPack + 4-byte all_reduce barrier + sprExpandFromPeers: ONE kernel per rank reads every rank's run from IPC-mapped peer memory over NVLink and writes the 4x expanded draw stream locally"},
+                "nvlink_bytes_in_per_gpu_per_step": nv}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(name, seconds=15.0)
         print(json.dumps(out))

@@ -442,6 +442,32 @@ SPR_API int sprPackRuns(SprContext *ctx, SprSystem *const *systems, const uint32
 SPR_API int sprExpandRuns(SprContext *ctx, const SprGpuParticle *deviceRecords, uint64_t numRecords,
 	SprGpuParticle *deviceVerticesOut);
 
+/* Fused gather + expansion over NVLink peer memory (one process per GPU).
+ *
+ * Each rank packs its sorted 32-byte runs into a run buffer that the other ranks map through
+ * CUDA IPC; ONE kernel per rank then reads every rank's run straight out of peer memory
+ * (plain loads on the mapped pointers, the transfer overlapping the 4x expansion tile by tile)
+ * and writes the whole draw stream locally. No intermediate gathered-records buffer, no NCCL copy.
+ * The caller provides the cross-rank ordering: a stream-ordered barrier between sprRunBufferPack on
+ * every rank and sprExpandFromPeers (bench.py uses a 4-byte NCCL all_reduce), and double-buffers
+ * the run buffers so that the next step's pack never overwrites a buffer a peer may still read. */
+typedef struct SprRunBuffer SprRunBuffer;
+#define SPR_IPC_HANDLE_BYTES 64
+SPR_API int sprRunBufferCreate(SprContext *ctx, uint64_t capacityRecords, SprRunBuffer **out);
+SPR_API int sprRunBufferDestroy(SprRunBuffer *buf);
+SPR_API int sprRunBufferGetIpcHandle(SprRunBuffer *buf, uint8_t outHandle[SPR_IPC_HANDLE_BYTES]);
+/* Map a peer's run buffer (same node). Returns a device pointer valid in this process. */
+SPR_API int sprRunBufferOpenPeer(SprContext *ctx, const uint8_t handle[SPR_IPC_HANDLE_BYTES], void **outDevicePtr);
+SPR_API int sprRunBufferClosePeer(SprContext *ctx, void *devicePtr);
+SPR_API void *sprRunBufferDevicePtr(SprRunBuffer *buf);
+/* sprPackRuns into `buf` (record count stored in the buffer header, no host sync). */
+SPR_API int sprRunBufferPack(SprContext *ctx, SprSystem *const *systems, const uint32_t *effectIds, uint32_t numEffects, SprRunBuffer *buf);
+/* bufferPtrs[r] = run buffer of rank r (own pointer for the own rank, mapped pointers for peers), rank-major
+ * output: deviceVerticesOut receives 4 vertices per record of rank 0's run, then rank 1's, ...
+ * deviceTotalRecords (may be NULL) receives the total record count (device uint64). */
+SPR_API int sprExpandFromPeers(SprContext *ctx, void *const *bufferPtrs, uint32_t numRanks,
+	SprGpuParticle *deviceVerticesOut, uint64_t capacityRecords, uint64_t *deviceTotalRecords);
+
 #ifdef __cplusplus
 }
 #endif

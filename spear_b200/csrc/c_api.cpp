@@ -377,6 +377,89 @@ SPR_API int sprPackRuns(SprContext *c, SprSystem *const *systems, const uint32_t
 	});
 }
 
+struct SprRunBuffer { Context *ctx; void *dev; uint64_t capacityRecords; };
+
+SPR_API int sprRunBufferCreate(SprContext *c, uint64_t capacityRecords, SprRunBuffer **out)
+{
+	REQUIRE(c && out && capacityRecords);
+	return guarded([&] {
+		SPR_CUDA(cudaSetDevice(c->ctx.device));
+		SprRunBuffer *b = new SprRunBuffer{ &c->ctx, nullptr, capacityRecords };
+		SPR_CUDA(cudaMalloc(&b->dev, 16 + capacityRecords * 32)); // plain cudaMalloc: exportable through CUDA IPC
+		SPR_CUDA(cudaMemsetAsync(b->dev, 0, 16, c->ctx.stream));
+		*out = b;
+	});
+}
+
+SPR_API int sprRunBufferDestroy(SprRunBuffer *buf)
+{
+	REQUIRE(buf);
+	return guarded([&] { cudaStreamSynchronize(buf->ctx->stream); cudaFree(buf->dev); delete buf; });
+}
+
+SPR_API void *sprRunBufferDevicePtr(SprRunBuffer *buf) { return buf ? buf->dev : nullptr; }
+
+SPR_API int sprRunBufferGetIpcHandle(SprRunBuffer *buf, uint8_t outHandle[SPR_IPC_HANDLE_BYTES])
+{
+	REQUIRE(buf && outHandle);
+	static_assert(sizeof(cudaIpcMemHandle_t) == SPR_IPC_HANDLE_BYTES, "ipc handle size");
+	return guarded([&] { cudaIpcMemHandle_t h; SPR_CUDA(cudaIpcGetMemHandle(&h, buf->dev)); memcpy(outHandle, &h, sizeof(h)); });
+}
+
+SPR_API int sprRunBufferOpenPeer(SprContext *c, const uint8_t handle[SPR_IPC_HANDLE_BYTES], void **outDevicePtr)
+{
+	REQUIRE(c && handle && outDevicePtr);
+	return guarded([&] {
+		SPR_CUDA(cudaSetDevice(c->ctx.device));
+		cudaIpcMemHandle_t h; memcpy(&h, handle, sizeof(h));
+		SPR_CUDA(cudaIpcOpenMemHandle(outDevicePtr, h, cudaIpcMemLazyEnablePeerAccess));
+	});
+}
+
+SPR_API int sprRunBufferClosePeer(SprContext *c, void *devicePtr)
+{
+	REQUIRE(c && devicePtr);
+	return guarded([&] { SPR_CUDA(cudaSetDevice(c->ctx.device)); cudaStreamSynchronize(c->ctx.stream); SPR_CUDA(cudaIpcCloseMemHandle(devicePtr)); });
+}
+
+SPR_API int sprRunBufferPack(SprContext *c, SprSystem *const *systems, const uint32_t *effectIds, uint32_t numEffects, SprRunBuffer *buf)
+{
+	REQUIRE(c && systems && effectIds && buf);
+	return guarded([&] {
+		Context *ctx = &c->ctx;
+		// the effect list of a steady-state frame does not change: keep the uploaded list of the last call
+		std::vector<uint32_t> globals(numEffects);
+		for (uint32_t i = 0; i < numEffects; i++) {
+			if (!validEffect(systems[i], effectIds[i])) throw std::runtime_error("invalid effect in sprRunBufferPack");
+			globals[i] = systems[i]->sys.effects[effectIds[i]].global;
+		}
+		ctx->flushUploads();
+		if (globals != ctx->packList) {
+			ctx->packListD.reserve(numEffects, 0, ctx->stream);
+			ctx->dRunOffsets.reserve(numEffects + 1, 0, ctx->stream);
+			SPR_CUDA(cudaMemcpyAsync(ctx->packListD.ptr, globals.data(), numEffects * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+			SPR_CUDA(cudaStreamSynchronize(ctx->stream));
+			ctx->packList.swap(globals);
+		}
+		launch_run_offsets(ctx->stream, ctx->tablePtrs(), ctx->packListD.ptr, numEffects, ctx->dRunOffsets.ptr, nullptr);
+		launch_pack_runs_buf(ctx->stream, ctx->poolPtrs(), ctx->tablePtrs(), ctx->packListD.ptr, numEffects, ctx->dRunOffsets.ptr,
+			buf->dev, buf->capacityRecords, ctx->numSms);
+		ctx->launchCount += 2;
+		SPR_CUDA(cudaGetLastError());
+	});
+}
+
+SPR_API int sprExpandFromPeers(SprContext *c, void *const *bufferPtrs, uint32_t numRanks, SprGpuParticle *deviceVerticesOut,
+	uint64_t capacityRecords, uint64_t *deviceTotalRecords)
+{
+	REQUIRE(c && bufferPtrs && deviceVerticesOut && numRanks >= 1 && numRanks <= 16);
+	return guarded([&] {
+		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms);
+		c->ctx.launchCount++;
+		SPR_CUDA(cudaGetLastError());
+	});
+}
+
 SPR_API int sprExpandRuns(SprContext *c, const SprGpuParticle *deviceRecords, uint64_t numRecords, SprGpuParticle *deviceVerticesOut)
 {
 	REQUIRE(c && deviceRecords && deviceVerticesOut);

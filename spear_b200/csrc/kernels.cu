@@ -891,6 +891,72 @@ __global__ void __launch_bounds__(256) k_expand_runs(const float4 *records, uint
 	}
 }
 
+// Run buffer layout: 16-byte header {uint64 count, uint64 pad} followed by `count` 32-byte records.
+// Same as k_pack_runs, but the record count goes into the header of the destination buffer.
+__global__ void __launch_bounds__(256) k_pack_runs_buf(PoolPtrs pool, TablePtrs tab, const uint32_t *effects, uint32_t n,
+	const uint64_t *offsets, float4 *buf, uint64_t capacityRecords)
+{
+	uint64_t total = offsets[n];
+	if (total > capacityRecords) total = capacityRecords;
+	if (blockIdx.x == 0 && threadIdx.x == 0) ((unsigned long long*)buf)[0] = total;
+	float4 *out = buf + 1;
+	uint64_t totalQ = total * 2;
+	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < totalQ; q += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t rcd = q >> 1;
+		uint32_t lo = 0, hi = n;
+		while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= rcd) lo = mid; else hi = mid; }
+		uint64_t k = rcd - offsets[lo];
+		uint32_t slotBase = tab.params[effects[lo]].slotBase;
+		out[q] = pool.vertices[8ull * (slotBase + k) + (q & 1u)];
+	}
+}
+
+// Fused all-gather + 4x expansion: every rank's run is read straight from (peer) memory over
+// NVLink with plain 256-bit loads on the IPC-mapped pointers and written four times into the local
+// draw stream (:607-665 layout), rank-major. One lane per record; the loads of a warp cover 1 KB of
+// contiguous peer memory, its stores 4 KB of contiguous local memory.
+struct PeerRuns { const float4 *buf[16]; uint32_t numRanks; };
+__global__ void __launch_bounds__(256) k_expand_from_peers(PeerRuns runs, float4 *out, uint64_t capacityRecords, unsigned long long *totalOut)
+{
+	__shared__ unsigned long long sOffset[17];
+	if (threadIdx.x == 0) {
+		unsigned long long run = 0;
+		for (uint32_t r = 0; r < runs.numRanks; r++) {
+			sOffset[r] = run;
+			unsigned long long c;
+			asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(c) : "l"(runs.buf[r]) : "memory");
+			run += c;
+		}
+		sOffset[runs.numRanks] = run;
+		if (blockIdx.x == 0 && totalOut) *totalOut = run;
+	}
+	__syncthreads();
+	unsigned long long total = sOffset[runs.numRanks];
+	if (total > capacityRecords) total = capacityRecords;
+	for (unsigned long long base = (unsigned long long)blockIdx.x * 1024; base < total; base += (unsigned long long)gridDim.x * 1024) {
+		float4 a[4], b[4];
+		bool ok[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			unsigned long long i = base + u * 256 + threadIdx.x;
+			ok[u] = i < total;
+			if (ok[u]) {
+				uint32_t r = 0;
+				while (r + 1 < runs.numRanks && sOffset[r + 1] <= i) r++;
+				const float4 *src = runs.buf[r] + 1 + 2ull * (i - sOffset[r]);
+				asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+					: "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w), "=f"(b[u].x), "=f"(b[u].y), "=f"(b[u].z), "=f"(b[u].w) : "l"(src));
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			if (!ok[u]) continue;
+			float4 *d = out + 8ull * (base + u * 256 + threadIdx.x);
+			st_record(d, a[u], b[u]); st_record(d + 2, a[u], b[u]); st_record(d + 4, a[u], b[u]); st_record(d + 6, a[u], b[u]);
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------
 // Launch wrappers
 // ---------------------------------------------------------------------------
@@ -987,6 +1053,20 @@ void launch_pack_runs(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &ta
 {
 	if (!n) return;
 	k_pack_runs<<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, out, capacityRecords);
+}
+
+void launch_pack_runs_buf(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,
+	const uint64_t *offsets, void *buf, uint64_t capacityRecords, uint32_t numSms)
+{
+	k_pack_runs_buf<<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, (float4*)buf, capacityRecords);
+}
+
+void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numSms)
+{
+	PeerRuns runs;
+	runs.numRanks = numRanks;
+	for (uint32_t r = 0; r < 16; r++) runs.buf[r] = r < numRanks ? (const float4*)bufs[r] : nullptr;
+	k_expand_from_peers<<<numSms * 8, 256, 0, st>>>(runs, out, capacityRecords, (unsigned long long*)totalOut);
 }
 
 void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numRecords, float4 *out, uint32_t numSms)

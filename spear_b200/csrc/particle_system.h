@@ -206,6 +206,8 @@ struct Context {
 	// ---- sort scratch
 	DeviceArray<uint32_t> dSortHist, dSortLookback;
 	DeviceArray<uint64_t> dRunOffsets;
+	DeviceArray<uint32_t> packListD;      // effect list of the last sprRunBufferPack (device)
+	std::vector<uint32_t> packList;       // ... and its host copy
 
 	explicit Context(const SprContextDesc &desc);
 	~Context();

@@ -25,6 +25,8 @@ EXPORTS = [
     "sprReadVertexStream", "sprReadSlots", "sprReadStreamSlots", "sprGetRngState", "sprGetEffectTypeLut",
     "sprGetEffectTypeUbo", "sprGetEffectDeviceView", "sprPackRuns", "sprExpandRuns",
     "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType", "sprRenderMainBatch", "sprContextGetTotals",
+    "sprRunBufferCreate", "sprRunBufferDestroy", "sprRunBufferGetIpcHandle", "sprRunBufferOpenPeer", "sprRunBufferClosePeer",
+    "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers",
 ]
 
 
@@ -69,6 +71,15 @@ def _load():
     lib.sprExpandRuns.argtypes = [vp, vp, u64, vp]
     lib.sprBakeEffectType.argtypes = [P(abi.ParticleSystemComponent), u32, vp, P(abi.VertexTypeUbo)]
     lib.sprContextGetTotals.argtypes = [vp, P(u64), P(u64)]
+    lib.sprRunBufferCreate.argtypes = [vp, u64, P(vp)]
+    lib.sprRunBufferDestroy.argtypes = [vp]
+    lib.sprRunBufferGetIpcHandle.argtypes = [vp, vp]
+    lib.sprRunBufferOpenPeer.argtypes = [vp, vp, P(vp)]
+    lib.sprRunBufferClosePeer.argtypes = [vp, vp]
+    lib.sprRunBufferDevicePtr.restype = vp
+    lib.sprRunBufferDevicePtr.argtypes = [vp]
+    lib.sprRunBufferPack.argtypes = [vp, P(vp), P(u32), u32, vp]
+    lib.sprExpandFromPeers.argtypes = [vp, P(vp), u32, vp, u64, vp]
     lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
     lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
     return lib
@@ -197,6 +208,41 @@ class ParticleContext:
         _check(lib.sprPackRuns(self.h, handles, p, n, device_out, capacity_records, device_counts,
                                C.byref(total) if want_total else None))
         return total.value
+
+    # ---- fused gather + expansion over peer memory (see include/spear_particles.h)
+    def run_buffer_create(self, capacity_records):
+        h = C.c_void_p()
+        _check(lib.sprRunBufferCreate(self.h, capacity_records, C.byref(h)))
+        return h
+
+    def run_buffer_ipc_handle(self, buf):
+        out = (C.c_uint8 * 64)()
+        _check(lib.sprRunBufferGetIpcHandle(buf, out))
+        return bytes(out)
+
+    def run_buffer_open_peer(self, handle_bytes):
+        arr = (C.c_uint8 * 64).from_buffer_copy(handle_bytes)
+        p = C.c_void_p()
+        _check(lib.sprRunBufferOpenPeer(self.h, arr, C.byref(p)))
+        return p.value
+
+    def run_buffer_ptr(self, buf):
+        return lib.sprRunBufferDevicePtr(buf)
+
+    def make_pack_list(self, systems, effect_ids):
+        n = len(systems)
+        handles = (C.c_void_p * n)(*[s.h for s in systems])
+        arr = np.ascontiguousarray(effect_ids, dtype=np.uint32)
+        return (handles, arr, arr.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+
+    def run_buffer_pack(self, pack_list, buf):
+        handles, _arr, p, n = pack_list
+        _check(lib.sprRunBufferPack(self.h, handles, p, n, buf))
+
+    def expand_from_peers(self, buffer_ptrs, device_vertices_out, capacity_records, device_total=None):
+        n = len(buffer_ptrs)
+        arr = (C.c_void_p * n)(*buffer_ptrs)
+        _check(lib.sprExpandFromPeers(self.h, arr, n, device_vertices_out, capacity_records, device_total))
 
     def expand_runs(self, device_records, num_records, device_vertices_out):
         _check(lib.sprExpandRuns(self.h, device_records, num_records, device_vertices_out))

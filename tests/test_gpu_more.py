@@ -259,3 +259,32 @@ def test_type_lut_and_ubo(oracle_port):
         ref = o.type_lut(t)
         assert np.array_equal(lut, ref)
         assert bytes(ubo) == bytes(o.type_ubo(t))
+
+
+def test_pack_and_fused_expand_from_run_buffers(oracle_port):
+    """sprRunBufferPack + sprExpandFromPeers with two run buffers of the same GPU standing in for two
+    ranks: the assembled stream is run 0 then run 1, each equal to the effects' own vertex streams."""
+    import torch
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 16)
+    try:
+        s = ctx.create_system((1, 11, 3, 4))
+        comps = [S.comp_c2(k, burst=700 + 100 * k, churn=True) for k in range(4)]
+        ids = [s.add_effect(c, abi.make_transform((k, 0, 0))) for k, c in enumerate(comps)]
+        for f in range(5):
+            s.update(ids, abi.make_frame_args(0.0175, f * 0.0175, f, camera=CAMERA))
+        streams = [s.read_stream(e) for e in ids]
+        cap = 8192
+        bufs = [ctx.run_buffer_create(cap) for _ in range(2)]
+        ctx.run_buffer_pack(ctx.make_pack_list([s, s], ids[:2]), bufs[0])
+        ctx.run_buffer_pack(ctx.make_pack_list([s, s], ids[2:]), bufs[1])
+        total = sum(len(st) for st in streams) // 4
+        out = torch.zeros((2 * cap * 4, 8), dtype=torch.float32, device="cuda")
+        tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ctx.expand_from_peers([ctx.run_buffer_ptr(b) for b in bufs], out.data_ptr(), 2 * cap, tot.data_ptr())
+        ctx.synchronize(); torch.cuda.synchronize()
+        assert int(tot.item()) == total
+        got = out[:total * 4].cpu().numpy().tobytes()
+        assert got == b"".join(st.tobytes() for st in streams)
+    finally:
+        ctx.close()
