@@ -385,8 +385,8 @@ SPR_API int sprRunBufferCreate(SprContext *c, uint64_t capacityRecords, SprRunBu
 	return guarded([&] {
 		SPR_CUDA(cudaSetDevice(c->ctx.device));
 		SprRunBuffer *b = new SprRunBuffer{ &c->ctx, nullptr, capacityRecords };
-		SPR_CUDA(cudaMalloc(&b->dev, 16 + capacityRecords * 32)); // plain cudaMalloc: exportable through CUDA IPC
-		SPR_CUDA(cudaMemsetAsync(b->dev, 0, 16, c->ctx.stream));
+		SPR_CUDA(cudaMalloc(&b->dev, 32 + capacityRecords * 32)); // plain cudaMalloc: exportable through CUDA IPC
+		SPR_CUDA(cudaMemsetAsync(b->dev, 0, 32, c->ctx.stream));
 		*out = b;
 	});
 }

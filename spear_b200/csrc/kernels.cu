@@ -891,7 +891,8 @@ __global__ void __launch_bounds__(256) k_expand_runs(const float4 *records, uint
 	}
 }
 
-// Run buffer layout: 16-byte header {uint64 count, uint64 pad} followed by `count` 32-byte records.
+// Run buffer layout: 32-byte header {uint64 count, pad} followed by `count` 32-byte records
+// (32-byte aligned, so that a record moves with one 256-bit access).
 // Same as k_pack_runs, but the record count goes into the header of the destination buffer.
 __global__ void __launch_bounds__(256) k_pack_runs_buf(PoolPtrs pool, TablePtrs tab, const uint32_t *effects, uint32_t n,
 	const uint64_t *offsets, float4 *buf, uint64_t capacityRecords)
@@ -899,7 +900,7 @@ __global__ void __launch_bounds__(256) k_pack_runs_buf(PoolPtrs pool, TablePtrs 
 	uint64_t total = offsets[n];
 	if (total > capacityRecords) total = capacityRecords;
 	if (blockIdx.x == 0 && threadIdx.x == 0) ((unsigned long long*)buf)[0] = total;
-	float4 *out = buf + 1;
+	float4 *out = buf + 2;
 	uint64_t totalQ = total * 2;
 	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < totalQ; q += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t rcd = q >> 1;
@@ -943,7 +944,7 @@ __global__ void __launch_bounds__(256) k_expand_from_peers(PeerRuns runs, float4
 			if (ok[u]) {
 				uint32_t r = 0;
 				while (r + 1 < runs.numRanks && sOffset[r + 1] <= i) r++;
-				const float4 *src = runs.buf[r] + 1 + 2ull * (i - sOffset[r]);
+				const float4 *src = runs.buf[r] + 2 + 2ull * (i - sOffset[r]);
 				asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 					: "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w), "=f"(b[u].x), "=f"(b[u].y), "=f"(b[u].z), "=f"(b[u].w) : "l"(src));
 			}
