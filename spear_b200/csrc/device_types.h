@@ -172,9 +172,6 @@ struct TablePtrs {
 	const TypeDev *types;
 	SystemDev *systems;
 	PlanRec *plans;
-	uint32_t *effectStamp;    // frame stamp of the last plan that covers the effect
-	uint32_t *effectPlanBase;
-	uint32_t *effectNumSubsteps;
 	RoundConsts *roundConsts; // per effect, rewritten every sub-step round by k_emit_warp
 	uint32_t *effectAnyDead;  // per effect: some slot was freed in this round (lets k_dead_append skip its scan)
 };

@@ -5,16 +5,17 @@
 // parity needs every multiply-add to round twice).
 //
 // Per frame (one set of launches covers every system of the context):
-//   k_plan            one thread per system: spawn control flow + RNG stream offsets
+//   k_plan              one warp per system: spawn control flow + RNG stream offsets
 //   per sub-step round:
-//     k_emit_warp     one warp per active effect: timer spawns (+ small bursts)
-//     k_emit_burst    one thread per burst spawn of large bursts
-//     k_integrate     one warp per 128-slot granule, one CTA per 1024-slot pool tile:
-//                     integrate + alive/dead ballot ranks + chained look-back across the
-//                     tiles of a large effect + free-list append + 4x vertex expansion
-//                     (or depth key/slot pair emission in sort mode) + bounds
-//   k_finalize        prevEmitterToWorld = emitterToWorld (:668)
-// Sort mode adds the segmented radix sort (sort.cuh) and k_expand_sorted.
+//     k_emit_warp       one warp per active effect: timer spawns (+ small bursts), RoundConsts digest
+//     k_emit_burst      one thread per burst spawn of large bursts
+//     k_integrate_pass  one warp per 128-slot granule, pure streaming: integrate, ballots, (depth key),
+//                       bounds; single-granule effects are finished in the warp
+//     k_dead_append     one warp per 1024-slot tile over the ballots: free-list append, counts,
+//                       (stream mode) stream ranks; chained look-back across the tiles of a large effect
+//   stream mode:        k_expand_stream   4x vertex expansion in slot order
+//   sort mode:          sort.cu           segmented radix sort + k_expand_sorted
+//   k_finalize          prevEmitterToWorld = emitterToWorld (:668)
 //
 // Everything order-sensitive (compaction order, free-list order, spawn->slot
 // assignment, RNG offsets) is a scan, never an atomic.
@@ -187,9 +188,6 @@ __global__ void __launch_bounds__(128) k_plan(TablePtrs tab, const SystemWork *w
 			const EffectParams &P = tab.params[ae.effect];
 			const EffectState &S = tab.state[ae.effect];
 			const TypeDev &T = tab.types[P.typeIdx];
-			tab.effectStamp[ae.effect] = stamp;
-			tab.effectPlanBase[ae.effect] = ae.planBase;
-			tab.effectNumSubsteps[ae.effect] = ae.numSubsteps;
 			spawnTimer = S.spawnTimer; emitOnTimer = S.emitOnTimer;
 			stopEmit = S.stopEmit; firstEmit = S.firstEmit; parity = S.parity;
 			dt = P.timeStep; hostStop = P.hostStopEmit;

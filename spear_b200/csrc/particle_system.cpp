@@ -78,7 +78,6 @@ TablePtrs Context::tablePtrs()
 	TablePtrs t;
 	t.params = dParams.ptr; t.state = dState.ptr; t.types = dTypes.ptr; t.systems = dSystems.ptr;
 	t.plans = dPlans.ptr;
-	t.effectStamp = dEffectStamp.ptr; t.effectPlanBase = dEffectPlanBase.ptr; t.effectNumSubsteps = dEffectNumSubsteps.ptr;
 	t.roundConsts = dRoundConsts.ptr;
 	t.effectAnyDead = dEffectAnyDead.ptr;
 	return t;
@@ -159,9 +158,6 @@ uint32_t Context::allocEffectGlobal()
 		size_t keep = numEffectGlobals - 1;
 		dParams.reserve(numEffectGlobals, keep, stream);
 		dState.reserve(numEffectGlobals, keep, stream);
-		dEffectStamp.reserve(numEffectGlobals, keep, stream);
-		dEffectPlanBase.reserve(numEffectGlobals, keep, stream);
-		dEffectNumSubsteps.reserve(numEffectGlobals, keep, stream);
 		dRoundConsts.reserve(numEffectGlobals, keep, stream);
 		dEffectAnyDead.reserve(numEffectGlobals, keep, stream);
 	}
@@ -270,9 +266,7 @@ struct BlobWriter {
 
 void Context::flushUploads()
 {
-	UpdateRequest none = { nullptr, nullptr, 0, nullptr };
-	(void)none;
-	update(nullptr, 0);
+	update(nullptr, 0); // an empty frame: only the pending table uploads are applied
 }
 
 void Context::update(const UpdateRequest *reqs, uint32_t numReqs)

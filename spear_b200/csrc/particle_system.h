@@ -160,7 +160,6 @@ struct Context {
 	// ---- tables
 	DeviceArray<EffectParams> dParams;
 	DeviceArray<EffectState> dState;
-	DeviceArray<uint32_t> dEffectStamp, dEffectPlanBase, dEffectNumSubsteps;
 	DeviceArray<RoundConsts> dRoundConsts;
 	DeviceArray<uint32_t> dEffectAnyDead;
 	DeviceArray<TypeDev> dTypes;

@@ -252,6 +252,14 @@ def scenarios():
     out.append(Scenario("multi", (1, 2024, 3, 4), multi, frames=50, dt=0.0171))
     out.append(Scenario("multi_bigdt", (1, 2025, 3, 4), multi[:5] + [(comp_c5(), _tr())], frames=12, dt=0.25))
     out.append(Scenario("churn_c5", (1, 7, 3, 4), [(comp_c5(), _tr((k, 0, 0))) for k in range(12)], frames=20))
+    # nothing to simulate: no burst and a first timer spawn far in the future, then a dt of 0
+    idle = abi.make_component(timeStep=0.02, spawnTime=5.0, lifeTime=0.5, emitPosition=dict(boxExtent=(1, 1, 1)))
+    out.append(Scenario("idle_then_zero_dt", (1, 3, 3, 4), [(idle, _tr()), (comp_point(), _tr((1, 1, 1)))], frames=8, dt=0.0))
+    # the frame dt is clamped to 0.1 (ParticleSystem.cpp:810): many sub-steps per frame with a small timeStep
+    fast = abi.make_component(timeStep=0.004, burstAmount=40, spawnTime=0.0007, spawnTimeVariance=0.0004, lifeTime=0.05,
+                              lifeTimeVariance=0.05, gravity=(0, -9.81, 0), emitPosition=dict(sphere=dict(minRadius=0.1, maxRadius=0.5)),
+                              emitVelocity=dict(boxExtent=(2, 2, 2)))
+    out.append(Scenario("clamped_dt_many_substeps", (1, 31, 3, 4), [(fast, _tr((0, 1, 0), q, 1.0)), (comp_c5(), _tr((1, 0, 0)))], frames=6, dt=1.0))
     # removal / id reuse / prepareForRemove
     out.append(Scenario("remove_reuse", (1, 99, 3, 4),
                         [(comp_fountain(), _tr()), (comp_c5(), _tr((1, 0, 0))), (comp_timed_emitter(), _tr((2, 0, 0)))],

@@ -288,3 +288,53 @@ def test_pack_and_fused_expand_from_run_buffers(oracle_port):
         assert got == b"".join(st.tobytes() for st in streams)
     finally:
         ctx.close()
+
+
+def test_type_and_effect_id_recycling(oracle_port):
+    """Dense u32 ids recycled LIFO, types keyed by descriptor identity and refcounted
+    (ParticleSystem.cpp:242-246, :682-728, :733-737, :796-806)."""
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 16)
+    try:
+        s, o = ctx.create_system((1, 9, 3, 4)), orc.OracleSystem(oracle_port, (1, 9, 3, 4))
+        comps = [S.comp_fountain(), S.comp_c5(), S.comp_point(), S.comp_timed_emitter(), S.comp_c1(burst=30)]
+        log_s, log_o = [], []
+        for sysm, log in ((s, log_s), (o, log_o)):
+            log.append(sysm.reserve_type(comps[0]))          # 0
+            log.append(sysm.reserve_type(comps[1]))          # 1
+            log.append(sysm.reserve_type(comps[0]))          # 0 again (refcount 2)
+            sysm.release_type(comps[0])
+            sysm.release_type(comps[0])                      # type 0 freed
+            log.append(sysm.reserve_type(comps[2]))          # reuses 0
+            e = [sysm.add_effect(comps[k], abi.make_transform((k, 0, 0))) for k in (1, 2, 3)]
+            log += e
+            sysm.remove(e[1])
+            sysm.remove(e[0])
+            log.append(sysm.add_effect(comps[4], abi.make_transform()))   # reuses e[0]
+            log.append(sysm.add_effect(comps[3], abi.make_transform()))   # reuses e[1]
+            log.append(sysm.add_effect(comps[0], abi.make_transform()))   # new id
+            ids = sorted(set(log[-3:] + [e[2]]))
+            for f in range(10):
+                sysm.update(ids, abi.make_frame_args(0.02, f * 0.02, f))
+            log.append([sysm.effect_info(i).typeId for i in ids])
+        assert log_s == log_o
+        ids = sorted(set(log_s[-4:-1] + [log_s[6]]))
+        S.assert_snapshots_equal(S.snapshot(o, ids), S.snapshot(s, ids), "after recycling")
+    finally:
+        ctx.close()
+
+
+def test_update_with_nothing_active():
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 16)
+    try:
+        s = ctx.create_system((1, 2, 3, 4))
+        s.update([], abi.make_frame_args(0.016))
+        e = s.add_effect(S.comp_point())
+        s.update([], abi.make_frame_args(0.016))
+        info = s.effect_info(e)
+        assert (info.slotCount, info.aliveCount, info.simSteps, info.firstEmit) == (0, 0, 0, 1)
+        recs, n = s.render([e], __import__("tests_render_args").make_render_args())
+        assert recs == [] and n == 0
+    finally:
+        ctx.close()
