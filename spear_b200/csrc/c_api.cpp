@@ -67,7 +67,7 @@ SPR_API void *sprContextStream(SprContext *ctx) { return ctx ? (void*)ctx->ctx.s
 SPR_API uint64_t sprContextLaunchCount(SprContext *ctx) { return ctx ? ctx->ctx.launchCount : 0; }
 
 static const char *const kKernelNames[16] = {
-	"k_scatter_words", "k_plan", "k_emit_warp", "k_emit_burst", "k_integrate", "k_finalize", "sort", "k_gather_render",
+	"k_scatter_words", "k_plan", "k_emit_warp", "k_emit_burst", "k_integrate", "k_finalize", "k_stream_fused", "k_gather_render",
 	"k_pack_runs", "k_expand_runs", "k_sort_hist", "k_sort_scan", "k_sort_pass", "k_expand_sorted", "k_dead_append", "k_expand_stream" };
 
 SPR_API int sprContextEnableKernelTiming(SprContext *ctx, int enable)

@@ -765,6 +765,225 @@ __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs ta
 	}
 }
 
+// ---------------------------------------------------------------------------
+// Stream mode, one pass: k_stream_fused
+// ---------------------------------------------------------------------------
+// The strict drop-in stream (ascending slot order, :611-665) needs, for every live slot, the number
+// of live slots before it in the effect -- a scan across the whole effect -- before its 128 bytes of
+// vertices can be placed. Doing that inside the streaming pass saves the second read of the record
+// (188 B instead of 224 B per particle-step) but puts a chained look-back on the critical path.
+// This kernel hides it by software pipelining inside persistent CTAs:
+//   iteration i, phase A (tile i): load, integrate, store state, ballots, stage the live records of
+//       each warp contiguously in shared memory (two stage buffers), publish the tile's alive / dead
+//       aggregates for the chained scan -- nothing in phase A waits on another CTA;
+//   iteration i, phase B (tile i-1): resolve that tile's look-back (by now its predecessors, which
+//       were processed one iteration ago by the neighbouring CTAs, have published), then expand the
+//       staged records 4x with 512-byte warp stores, append the freed slots, publish the counts.
+// A ninth warp per CTA does nothing but the chained scan: it resolves tile i-1 while the eight
+// worker warps run phase A of tile i, so the look-back latency never stalls a barrier.
+// Persistent grid = resident CTAs only, so every predecessor a CTA waits on is running.
+
+struct FusedTileMeta {        // per stage buffer, written in phase A, read in phase B
+	uint32_t owner[8];        // effect of each warp's granule (kNoOwner when the warp had nothing to do)
+	uint32_t nAlive[8], nDead[8];
+	uint32_t deadMask[8][4];
+	uint32_t localBase[8];
+	uint32_t slotBase[8], slotsPost[8], topPost[8], flags[8];
+	uint32_t tile;            // pool tile index, 0xffffffff when the buffer is empty
+	uint32_t large;           // the tile belongs to one large effect
+	uint32_t exclA, exclD;    // resolved look-back
+};
+
+__device__ inline void tile_lookback2(unsigned long long *stA, unsigned long long *stD, uint32_t poolTile, uint32_t tileIdx,
+	uint32_t aggA, uint32_t aggD, uint32_t epoch, uint32_t lane, uint32_t &exclA, uint32_t &exclD)
+{
+	// the aggregates were already published in phase A; resolve both chains independently
+	const unsigned long long tag = (unsigned long long)epoch << 34;
+	const unsigned long long fIncl = 2ull << 32;
+	exclA = 0; exclD = 0;
+	if (tileIdx != 0) {
+		int32_t rel = (int32_t)tileIdx - 1 - (int32_t)lane;
+		bool doneA = false, doneD = false;
+		while (!doneA || !doneD) {
+			unsigned long long va = tag | fIncl, vd = tag | fIncl; // virtual zero prefix in front of tile 0
+			if (rel >= 0) {
+				uint32_t t = poolTile - (tileIdx - (uint32_t)rel);
+				if (!doneA) do { va = ld_status(stA + t); } while ((va >> 34) != epoch);
+				if (!doneD) do { vd = ld_status(stD + t); } while ((vd >> 34) != epoch);
+			}
+			if (!doneA) {
+				uint32_t incl = __ballot_sync(FULL_MASK, ((va >> 32) & 3u) == 2u);
+				uint32_t upTo = incl ? (uint32_t)(__ffs(incl) - 1) : 31u;
+				exclA += __reduce_add_sync(FULL_MASK, lane <= upTo ? (uint32_t)va : 0u);
+				doneA = incl != 0;
+			}
+			if (!doneD) {
+				uint32_t incl = __ballot_sync(FULL_MASK, ((vd >> 32) & 3u) == 2u);
+				uint32_t upTo = incl ? (uint32_t)(__ffs(incl) - 1) : 31u;
+				exclD += __reduce_add_sync(FULL_MASK, lane <= upTo ? (uint32_t)vd : 0u);
+				doneD = incl != 0;
+			}
+			rel -= 32;
+		}
+	}
+	if (lane == 0) { st_status(stA + poolTile, tag | fIncl | (exclA + aggA)); st_status(stD + poolTile, tag | fIncl | (exclD + aggD)); }
+}
+
+template <bool GP>
+__global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles)
+{
+	extern __shared__ float4 sStageAll[];              // [2][8 warps][256 float4] = 64 KB
+	__shared__ FusedTileMeta sMeta[2];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t ltMask = (1u << lane) - 1u;
+	const unsigned long long tag = (unsigned long long)epoch << 34;
+
+	if (threadIdx.x < 2) sMeta[threadIdx.x].tile = 0xffffffffu;
+	__syncthreads();
+
+	for (uint32_t it = 0, tile = blockIdx.x; ; it++, tile += gridDim.x) {
+		const uint32_t cur = it & 1u;
+		FusedTileMeta &M = sMeta[cur];
+		FusedTileMeta &Q = sMeta[cur ^ 1u];
+		// ---------------- scan warp: look-back of the tile staged one iteration ago, overlapping phase A
+		if (warp == 8) {
+			if (it > 0 && Q.tile != 0xffffffffu && Q.large) {
+				uint32_t tA = 0, tD = 0;
+				for (uint32_t w = 0; w < 8; w++) if (Q.owner[w] != kNoOwner) { tA += Q.nAlive[w]; tD += Q.nDead[w]; }
+				uint32_t first = 0;
+				while (Q.owner[first] == kNoOwner) first++;
+				uint32_t tileIdx = (Q.tile * kTileSlots - Q.slotBase[first]) / kTileSlots;
+				uint32_t eA, eD;
+				tile_lookback2(pool.tileStatusAlive, pool.tileStatusDead, Q.tile, tileIdx, tA, tD, epoch, lane, eA, eD);
+				if (lane == 0) { Q.exclA = eA; Q.exclD = eD; }
+			}
+		}
+		// ---------------- phase A (worker warps): tile `tile` into stage buffer `cur`
+		if (tile < numPoolTiles && warp < 8) {
+			const uint32_t granule = tile * 8 + warp;
+			uint32_t g = pool.granuleOwner[granule];
+			bool active = false;
+			uint32_t nA = 0, nD = 0, dmask[4] = { 0, 0, 0, 0 };
+			RoundConsts rc;
+			rc.slotBase = 0; rc.slotsPost = 0; rc.topPost = 0; rc.flags = 0;
+			uint32_t localBase = 0;
+			if (g != kNoOwner) {
+				float4 a[4], b[4];
+				float4 *slotPtr = pool.state + 2ull * ((uint64_t)granule * kGranuleSlots + lane);
+#pragma unroll
+				for (int r = 0; r < 4; r++) ld_record(slotPtr + r * 64, a[r], b[r]);
+				rc = tab.roundConsts[g];
+				uint32_t curBound = 0;
+				if (lane < 8) curBound = lane < 4 ? tab.state[g].boundsMin[lane] : tab.state[g].boundsMax[lane - 4];
+				localBase = granule * kGranuleSlots - rc.slotBase;
+				active = rc.stamp == stamp && rc.round == round && localBase < rc.slotsPost;
+				if (active) {
+					StepConsts c;
+					step_consts_from(c, rc, tab, g);
+					uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
+					uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
+					float4 *stage = sStageAll + (cur * 8 + warp) * 256;
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						bool alive = false, dead = false, touched = false;
+						float4 ra = a[r], rb = b[r];
+						if (localBase + r * 32 + lane < rc.slotsPost) {
+							integrate_slot<GP>(c, ra, rb, alive, dead, touched);
+							if (touched) st_record(slotPtr + r * 64, ra, rb);
+						}
+						uint32_t am = __ballot_sync(FULL_MASK, alive);
+						dmask[r] = __ballot_sync(FULL_MASK, dead);
+						if (alive) {
+							uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z), el = enc_float(ra.w);
+							mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez); mnl = min(mnl, el);
+							mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez); mxl = max(mxl, el);
+							uint32_t k = nA + __popc(am & ltMask);
+							stage[2 * k] = ra;
+							stage[2 * k + 1] = rb;
+						}
+						nA += __popc(am);
+						nD += __popc(dmask[r]);
+					}
+					if (nA) {
+						mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny);
+						mnz = __reduce_min_sync(FULL_MASK, mnz); mnl = __reduce_min_sync(FULL_MASK, mnl);
+						mxx = __reduce_max_sync(FULL_MASK, mxx); mxy = __reduce_max_sync(FULL_MASK, mxy);
+						mxz = __reduce_max_sync(FULL_MASK, mxz); mxl = __reduce_max_sync(FULL_MASK, mxl);
+						if (lane < 8) {
+							uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz : lane == 3 ? mnl
+								: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : mxl;
+							uint32_t *addr = lane < 4 ? &tab.state[g].boundsMin[lane] : &tab.state[g].boundsMax[lane - 4];
+							if (lane < 4) { if (v < curBound) atomicMin(addr, v); }
+							else { if (v > curBound) atomicMax(addr, v); }
+						}
+					}
+				}
+			}
+			if (lane == 0) {
+				M.owner[warp] = active ? g : kNoOwner;
+				M.nAlive[warp] = nA; M.nDead[warp] = nD;
+				M.localBase[warp] = localBase;
+				M.slotBase[warp] = rc.slotBase; M.slotsPost[warp] = rc.slotsPost; M.topPost[warp] = rc.topPost; M.flags[warp] = rc.flags;
+			}
+			if (lane < 4) M.deadMask[warp][lane] = lane == 0 ? dmask[0] : lane == 1 ? dmask[1] : lane == 2 ? dmask[2] : dmask[3];
+		}
+		__syncthreads();
+		if (tile < numPoolTiles && warp == 8) {
+			// publish the tile's aggregates (large effects only: small ones never cross a tile)
+			bool anyActive = false, large = false;
+			uint32_t tA = 0, tD = 0;
+			for (uint32_t w = 0; w < 8; w++) {
+				if (M.owner[w] != kNoOwner) { anyActive = true; large = (M.flags[w] & 2u) != 0; tA += M.nAlive[w]; tD += M.nDead[w]; }
+			}
+			if (lane == 0) {
+				M.tile = anyActive ? tile : 0xffffffffu;
+				M.large = large ? 1u : 0u;
+				if (anyActive && large) {
+					st_status(pool.tileStatusAlive + tile, tag | (1ull << 32) | tA);
+					st_status(pool.tileStatusDead + tile, tag | (1ull << 32) | tD);
+				}
+			}
+		} else if (tile >= numPoolTiles && threadIdx.x == 0) {
+			M.tile = 0xffffffffu;
+		}
+
+		// ---------------- phase B (worker warps): the tile staged one iteration ago (buffer cur ^ 1)
+		if (it > 0 && warp < 8 && Q.tile != 0xffffffffu && Q.owner[warp] != kNoOwner) {
+			const uint32_t g = Q.owner[warp];
+			uint32_t baseA = Q.large ? Q.exclA : 0u, baseD = Q.large ? Q.exclD : 0u;
+			for (uint32_t w = 0; w < warp; w++) if (Q.owner[w] == g) { baseA += Q.nAlive[w]; baseD += Q.nDead[w]; }
+			const uint32_t nA = Q.nAlive[warp], nD = Q.nDead[warp];
+			const uint32_t slotBase = Q.slotBase[warp], slotsPost = Q.slotsPost[warp], topPost = Q.topPost[warp];
+			const uint32_t localBase = Q.localBase[warp], flags = Q.flags[warp];
+			// free-list append in ascending slot order (:556-567), behind the post-emission stack
+			if (nD) {
+				uint32_t run = baseD;
+#pragma unroll
+				for (int r = 0; r < 4; r++) {
+					uint32_t dm = Q.deadMask[warp][r];
+					if (dm >> lane & 1u) pool.freeStack[slotBase + topPost + run + __popc(dm & ltMask)] = localBase + r * 32 + lane;
+					run += __popc(dm);
+				}
+			}
+			if (localBase == 0 && (flags & 8u) && lane < topPost) pool.freeStack[slotBase + lane] = slotsPost - 4 + lane; // :491-493
+			// 4x expansion of the staged run with fully coalesced 512-byte warp stores (:611-665)
+			const float4 *stage = sStageAll + ((cur ^ 1u) * 8 + warp) * 256;
+			float4 *dst = pool.vertices + 8ull * (slotBase + baseA);
+			const uint32_t total = nA * 8;
+			for (uint32_t q = lane; q < total; q += 32) dst[q] = stage[((q >> 3) << 1) | (q & 1u)];
+			// the warp that holds the last slot publishes the effect's new counts (:670)
+			if (lane == 0 && slotsPost - 1 - localBase < kGranuleSlots) {
+				EffectState &S = tab.state[g];
+				S.aliveCount = baseA + nA;
+				S.freeCount[(flags & 1u) ^ 1u] = topPost + baseD + nD;
+				S.slotCount[(flags & 1u) ^ 1u] = slotsPost;
+			}
+		}
+		if (tile >= numPoolTiles) break;
+		__syncthreads(); // the buffer just drained is the next iteration's phase-A target
+	}
+}
+
 // Stream mode: the 4x vertex expansion in ascending slot order (:607-665). One warp per granule,
 // no dependency on any other warp: the rank of a word's first live particle comes from
 // k_dead_append, the rest is a popcount. A lane re-reads its 32-byte record (256-bit, streaming) and
@@ -1022,6 +1241,30 @@ void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &
 	if (!numPoolTiles) return;
 	if (aliveScan) k_dead_append<true><<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
 	else k_dead_append<false><<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
+}
+
+uint32_t launch_stream_fused(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
+	uint32_t epoch, bool gravityPoints, uint32_t numSms)
+{
+	if (!numPoolTiles) return 0;
+	static int ctasPerSm[2] = { 0, 0 };
+	const size_t smem = 2 * 8 * 256 * sizeof(float4);
+	const int v = gravityPoints ? 1 : 0;
+	if (!ctasPerSm[v]) {
+		if (v) {
+			cudaFuncSetAttribute(k_stream_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm[v], k_stream_fused<true>, 288, smem);
+		} else {
+			cudaFuncSetAttribute(k_stream_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm[v], k_stream_fused<false>, 288, smem);
+		}
+		if (ctasPerSm[v] < 1) ctasPerSm[v] = 1;
+	}
+	uint32_t grid = numSms * (uint32_t)ctasPerSm[v]; // persistent: resident CTAs only (the chained scan needs its predecessors running)
+	if (grid > numPoolTiles) grid = numPoolTiles;
+	if (v) k_stream_fused<true><<<grid, 288, smem, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
+	else k_stream_fused<false><<<grid, 288, smem, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
+	return grid;
 }
 
 void launch_expand_stream(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp)

@@ -46,6 +46,7 @@ Context::Context(const SprContextDesc &desc)
 	else { SPR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); ownStream = true; }
 	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[0], cudaEventDisableTiming));
 	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[1], cudaEventDisableTiming));
+	streamFused = getenv("SPR_STREAM_TWO_PASS") == nullptr; // SPR_STREAM_TWO_PASS=1 selects the two-pass stream mode (A/B measurement)
 	freeRanges.resize(33);
 	ensurePool(desc.initialSlotCapacity ? desc.initialSlotCapacity : (1u << 20));
 }
@@ -207,7 +208,7 @@ void Context::ensureOwned(uint32_t g, uint32_t slotUpperBound)
 
 // Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
 enum { kKScatter = 0, kKPlan, kKEmit, kKEmitBurst, kKIntegrate, kKFinalize, kKSort, kKGather, kKPack, kKExpandRuns,
-	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15 };
+	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15, kKStreamFused = 6 };
 
 cudaEvent_t Context::timingBegin(int kernel)
 {
@@ -452,10 +453,15 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			SPR_CUDA(cudaMemsetAsync(dTileStatus[1], 0, poolCapacity / kTileSlots * 8, stream));
 			epoch = 1;
 		}
-		TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, numTinyEffects != 0, camera));
-		TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch, !sortMode));
+		if (!sortMode && streamFused) {
+			// stream mode, one pass: integrate + ranks + free list + 4x expansion in a software-pipelined persistent kernel
+			TIMED(kKStreamFused, launch_stream_fused(stream, pool, tab, poolTiles, frameStamp, round, epoch, typesWithGravityPoints != 0, numSms));
+		} else {
+			TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, numTinyEffects != 0, camera));
+			TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch, !sortMode));
+		}
 	}
-	if (!sortMode) TIMED(kKExpandStream, launch_expand_stream(stream, pool, tab, poolTiles, frameStamp));
+	if (!sortMode && !streamFused) TIMED(kKExpandStream, launch_expand_stream(stream, pool, tab, poolTiles, frameStamp));
 	TIMED(kKFinalize, launch_finalize(stream, tab, dEntries, nEntries));
 
 	if (sortMode && !segEffects.empty()) {
