@@ -841,6 +841,19 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 	if (threadIdx.x < 2) sMeta[threadIdx.x].tile = 0xffffffffu;
 	__syncthreads();
 
+	// the records of the NEXT tile are requested before phase B of the current iteration, so their
+	// DRAM latency hides behind the expansion stores
+	float4 a[4], b[4];
+	uint32_t gNext = kNoOwner;
+	if (warp < 8 && blockIdx.x < numPoolTiles) {
+		gNext = pool.granuleOwner[blockIdx.x * 8 + warp];
+		if (gNext != kNoOwner) {
+			const float4 *p = pool.state + 2ull * ((uint64_t)(blockIdx.x * 8 + warp) * kGranuleSlots + lane);
+#pragma unroll
+			for (int r = 0; r < 4; r++) ld_record(p + r * 64, a[r], b[r]);
+		}
+	}
+
 	for (uint32_t it = 0, tile = blockIdx.x; ; it++, tile += gridDim.x) {
 		const uint32_t cur = it & 1u;
 		FusedTileMeta &M = sMeta[cur];
@@ -861,17 +874,14 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 		// ---------------- phase A (worker warps): tile `tile` into stage buffer `cur`
 		if (tile < numPoolTiles && warp < 8) {
 			const uint32_t granule = tile * 8 + warp;
-			uint32_t g = pool.granuleOwner[granule];
+			const uint32_t g = gNext;
 			bool active = false;
 			uint32_t nA = 0, nD = 0, dmask[4] = { 0, 0, 0, 0 };
 			RoundConsts rc;
 			rc.slotBase = 0; rc.slotsPost = 0; rc.topPost = 0; rc.flags = 0;
 			uint32_t localBase = 0;
 			if (g != kNoOwner) {
-				float4 a[4], b[4];
 				float4 *slotPtr = pool.state + 2ull * ((uint64_t)granule * kGranuleSlots + lane);
-#pragma unroll
-				for (int r = 0; r < 4; r++) ld_record(slotPtr + r * 64, a[r], b[r]);
 				rc = tab.roundConsts[g];
 				uint32_t curBound = 0;
 				if (lane < 8) curBound = lane < 4 ? tab.state[g].boundsMin[lane] : tab.state[g].boundsMax[lane - 4];
@@ -947,6 +957,19 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 			M.tile = 0xffffffffu;
 		}
 
+		// ---------------- prefetch (worker warps): owner and records of this CTA's next tile
+		if (warp < 8) {
+			const uint32_t nextTile = tile + gridDim.x;
+			gNext = kNoOwner;
+			if (tile < numPoolTiles && nextTile < numPoolTiles) {
+				gNext = pool.granuleOwner[nextTile * 8 + warp];
+				if (gNext != kNoOwner) {
+					const float4 *p = pool.state + 2ull * ((uint64_t)(nextTile * 8 + warp) * kGranuleSlots + lane);
+#pragma unroll
+					for (int r = 0; r < 4; r++) ld_record(p + r * 64, a[r], b[r]);
+				}
+			}
+		}
 		// ---------------- phase B (worker warps): the tile staged one iteration ago (buffer cur ^ 1)
 		if (it > 0 && warp < 8 && Q.tile != 0xffffffffu && Q.owner[warp] != kNoOwner) {
 			const uint32_t g = Q.owner[warp];
