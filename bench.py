@@ -457,12 +457,28 @@ def run_ours(args, rank, world):
                           "matches_nccl_path_bit_for_bit": f_ok == world,
                           "note": "step + sprRunBufferPack + 4-byte all_reduce barrier + sprExpandFromPeers: ONE kernel per rank reads every rank's run from IPC-mapped peer memory over NVLink and writes the 4x expanded draw stream locally"},
                 "nvlink_bytes_in_per_gpu_per_step": nv}
+        if world == 1 and sorted_mode and not args.no_stream_mode:
+            # the strict drop-in stream (ascending slot order, no per-particle sort) on the same workload,
+            # measured by the same script in a fresh process right after this one releases the GPU
+            out["stream_mode"] = "pending"
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(name, seconds=15.0)
-        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+    if rank == 0:
+        if out.get("stream_mode") == "pending":
+            try:
+                cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--no-sort", "--no-cpu-baseline", "--no-stream-mode",
+                       "--steps", str(args.steps), "--warmup", str(args.warmup)]
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+                sm = json.loads(r.stdout.strip().splitlines()[-1])
+                out["stream_mode"] = {"value": sm["value"], "unit": UNIT, "ms_per_step": sm["ms_per_step"], "e2e": sm["e2e"]["value"],
+                                      "roofline": sm["roofline"], "kernels": sm["kernels"], "gpu_launches": sm["gpu_launches"],
+                                      "note": "same workload with SPR_CTX_SORT_PARTICLES off: update + compact + 4x billboard expansion in ascending slot order (the reference's own stream order)"}
+            except Exception as ex:  # noqa: BLE001
+                out["stream_mode"] = {"error": str(ex)[:200]}
+        print(json.dumps(out))
 
 
 # ---------------------------------------------------------------------------
@@ -568,6 +584,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-sort", action="store_true", help="strict drop-in stream (slot order), no per-particle depth sort")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream-mode", action="store_true", help="skip the extra stream-mode (no sort) measurement at N=1")
     ap.add_argument("--no-kernel-timing", action="store_true", help="no per-launch CUDA events inside the timed region (no roofline object)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
