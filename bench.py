@@ -347,7 +347,7 @@ def run_ours(args, rank, world):
                     step()
                 ctx.run_buffer_pack(pack_list, bufs[k])
                 dist.all_reduce(flag)           # stream-ordered cross-rank barrier: every rank's pack is complete
-                ctx.expand_from_peers(peer_ptrs[k], verts_f.data_ptr(), world * cap, total_dev.data_ptr())
+                ctx.expand_from_peers(peer_ptrs[k], verts_f.data_ptr(), world * cap, total_dev.data_ptr(), my_rank=rank)
 
             def timed(fn):
                 for _ in range(2):

@@ -464,8 +464,9 @@ SPR_API void *sprRunBufferDevicePtr(SprRunBuffer *buf);
 SPR_API int sprRunBufferPack(SprContext *ctx, SprSystem *const *systems, const uint32_t *effectIds, uint32_t numEffects, SprRunBuffer *buf);
 /* bufferPtrs[r] = run buffer of rank r (own pointer for the own rank, mapped pointers for peers), rank-major
  * output: deviceVerticesOut receives 4 vertices per record of rank 0's run, then rank 1's, ...
- * deviceTotalRecords (may be NULL) receives the total record count (device uint64). */
-SPR_API int sprExpandFromPeers(SprContext *ctx, void *const *bufferPtrs, uint32_t numRanks,
+ * deviceTotalRecords (may be NULL) receives the total record count (device uint64). myRank only staggers the
+ * order in which the peers are read (every GPU starts on a different peer and reads all of them concurrently). */
+SPR_API int sprExpandFromPeers(SprContext *ctx, void *const *bufferPtrs, uint32_t numRanks, uint32_t myRank,
 	SprGpuParticle *deviceVerticesOut, uint64_t capacityRecords, uint64_t *deviceTotalRecords);
 
 #ifdef __cplusplus

@@ -449,12 +449,12 @@ SPR_API int sprRunBufferPack(SprContext *c, SprSystem *const *systems, const uin
 	});
 }
 
-SPR_API int sprExpandFromPeers(SprContext *c, void *const *bufferPtrs, uint32_t numRanks, SprGpuParticle *deviceVerticesOut,
+SPR_API int sprExpandFromPeers(SprContext *c, void *const *bufferPtrs, uint32_t numRanks, uint32_t myRank, SprGpuParticle *deviceVerticesOut,
 	uint64_t capacityRecords, uint64_t *deviceTotalRecords)
 {
-	REQUIRE(c && bufferPtrs && deviceVerticesOut && numRanks >= 1 && numRanks <= 16);
+	REQUIRE(c && bufferPtrs && deviceVerticesOut && numRanks >= 1 && numRanks <= 16 && myRank < numRanks);
 	return guarded([&] {
-		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms);
+		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, myRank, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms);
 		c->ctx.launchCount++;
 		SPR_CUDA(cudaGetLastError());
 	});

@@ -79,7 +79,7 @@ def _load():
     lib.sprRunBufferDevicePtr.restype = vp
     lib.sprRunBufferDevicePtr.argtypes = [vp]
     lib.sprRunBufferPack.argtypes = [vp, P(vp), P(u32), u32, vp]
-    lib.sprExpandFromPeers.argtypes = [vp, P(vp), u32, vp, u64, vp]
+    lib.sprExpandFromPeers.argtypes = [vp, P(vp), u32, u32, vp, u64, vp]
     lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
     lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
     return lib
@@ -239,10 +239,10 @@ class ParticleContext:
         handles, _arr, p, n = pack_list
         _check(lib.sprRunBufferPack(self.h, handles, p, n, buf))
 
-    def expand_from_peers(self, buffer_ptrs, device_vertices_out, capacity_records, device_total=None):
+    def expand_from_peers(self, buffer_ptrs, device_vertices_out, capacity_records, device_total=None, my_rank=0):
         n = len(buffer_ptrs)
         arr = (C.c_void_p * n)(*buffer_ptrs)
-        _check(lib.sprExpandFromPeers(self.h, arr, n, device_vertices_out, capacity_records, device_total))
+        _check(lib.sprExpandFromPeers(self.h, arr, n, my_rank, device_vertices_out, capacity_records, device_total))
 
     def expand_runs(self, device_records, num_records, device_vertices_out):
         _check(lib.sprExpandRuns(self.h, device_records, num_records, device_vertices_out))
