@@ -30,6 +30,8 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("SPEAR_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
+ADAPTER_SRC = os.path.join(HERE, "..", "integration", "ParticleSystemB200.cpp")
+PRODUCT_DIR = os.path.join(HERE, "..", "spear_b200")
 
 BASE_FLAGS = [
     "-O2", "-DNDEBUG", "-DSP_NO_APP=1", "-msse4.1", "-fno-math-errno",
@@ -71,9 +73,14 @@ def _compile(args):
 
 
 def build(force=False, verbose=True):
-    targets = [os.path.join(OUT, "libspear_ref.so"), os.path.join(OUT, "libspear_ref_scalar.so")]
+    targets = [os.path.join(OUT, "libspear_ref.so"), os.path.join(OUT, "libspear_ref_scalar.so"), os.path.join(OUT, "libspear_adapter.so")]
     srcs = [os.path.join(HERE, "ref_harness.cpp"), os.path.join(HERE, "oracle_api.h"),
-            os.path.join(HERE, "..", "include", "spear_particles.h"), os.path.abspath(__file__)]
+            os.path.join(HERE, "..", "include", "spear_particles.h"), os.path.abspath(__file__), ADAPTER_SRC]
+    prod = os.path.join(PRODUCT_DIR, "libspear_particles.so")
+    if os.path.isfile(prod):
+        srcs.append(prod)
+    else:
+        targets = targets[:2]
     if not force and all(os.path.isfile(t) for t in targets):
         newest = max(os.path.getmtime(s) for s in srcs)
         if all(os.path.getmtime(t) >= newest for t in targets):
@@ -85,7 +92,7 @@ def build(force=False, verbose=True):
     try:
         mirror = _make_shim_tree(tmp)
         inc = ["-I" + mirror, "-I" + os.path.join(REF, "src"), "-isystem", os.path.join(REF, "src", "ext"),
-               "-I" + HERE]
+               "-I" + HERE, "-I" + os.path.join(HERE, "..", "include")]
         sf_units = sorted(f for f in os.listdir(os.path.join(mirror, "sf")) if f.endswith(".cpp"))
         # File/Process/Thread/License/Reflection are not needed by the path; skip what does not link cleanly.
         skip = {"File.cpp", "Process.cpp", "License.cpp"}
@@ -97,17 +104,26 @@ def build(force=False, verbose=True):
         units.append((os.path.join(REF, "src", "client", "Transform.cpp"), True))
         units.append((os.path.join(REF, "src", "sp", "Srgb.cpp"), True))
         units.append((os.path.join(HERE, "ref_harness.cpp"), True))
-        for variant, extra in (("", []), ("_scalar", ["-DSF_FLOAT4_FORCE_SCALAR=1"])):
+        for variant, extra in (("", []), ("_scalar", ["-DSF_FLOAT4_FORCE_SCALAR=1"]), ("_adapter", ["-DSPR_ADAPTER=1"])):
             jobs = []
-            for i, (path, is_cxx) in enumerate(units):
+            vunits = list(units)
+            if variant == "_adapter":
+                # the literal drop-in: integration/ParticleSystemB200.cpp (cl::ParticleSystem over the C ABI) instead
+                # of the reference's ParticleSystem.cpp, linked against the product library
+                if not os.path.isfile(os.path.join(PRODUCT_DIR, "libspear_particles.so")):
+                    continue
+                vunits.append((ADAPTER_SRC, True))
+            for i, (path, is_cxx) in enumerate(vunits):
                 obj = os.path.join(tmp, "o%s_%d.o" % (variant, i))
                 cc = ["g++"] + CXX_FLAGS if is_cxx else ["gcc"]
                 vis = ["-fvisibility=hidden"] if path.endswith("ref_harness.cpp") else []
                 jobs.append((cc + BASE_FLAGS + extra + vis + inc + ["-c", path, "-o", obj], obj))
             with concurrent.futures.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
                 objs = list(ex.map(_compile, jobs))
-            so = os.path.join(OUT, "libspear_ref%s.so" % variant)
+            so = os.path.join(OUT, "libspear_adapter.so" if variant == "_adapter" else "libspear_ref%s.so" % variant)
             link = ["g++", "-shared", "-o", so] + objs + ["-lpthread", "-Wl,--no-undefined"]
+            if variant == "_adapter":
+                link += ["-L" + PRODUCT_DIR, "-lspear_particles", "-Wl,-rpath,$ORIGIN/../../spear_b200"]
             r = subprocess.run(link, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("link failed:\n" + r.stderr[-6000:])

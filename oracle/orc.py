@@ -22,6 +22,9 @@ _PATHS = {
     "reference": os.path.join(HERE, "_ref", "libspear_ref.so"),
     "reference_scalar": os.path.join(HERE, "_ref", "libspear_ref_scalar.so"),
     "port": os.path.join(HERE, "libspear_oracle.so"),
+    # not an oracle: integration/ParticleSystemB200.cpp (cl::ParticleSystem over the product's C ABI) behind the same
+    # harness, built against the reference headers -- the thing under test in tests/test_gpu_adapter.py
+    "adapter": os.path.join(HERE, "_ref", "libspear_adapter.so"),
 }
 
 GPU_PARTICLE_DTYPE = np.dtype([("pos", "<f4", 3), ("life", "<f4"), ("vel", "<f4", 3), ("seed", "<f4")])

@@ -8,7 +8,25 @@
 // the reference files are compiled where they lie and only the resulting
 // library lands in oracle/_ref/.
 
+#ifdef SPR_ADAPTER
+// Adapter variant (kind "adapter"): the same harness drives integration/ParticleSystemB200.cpp, the
+// cl::ParticleSystem implementation that forwards to libspear_particles.so, through the reference's
+// own types; read-backs go through the C ABI instead of the reference's internals.
+#include "client/ParticleSystem.h"
+#include "client/VisFogSystem.h"
+#include "client/ParticleTexture.h"
+#include "sf/Frustum.h"
+#include "sf/Float4.h"
+#include "sp/Asset.h"
+#include "sp/Renderer.h"
+#include "game/shader/GameShaders.h"
+#include "game/shader/Particle.h"
+#include "spear_particles.h"
+namespace cl { SprSystem *sprAdapterSystem(ParticleSystem *ps); SprContext *sprAdapterContext(ParticleSystem *ps);
+	const SprDrawRecord *sprAdapterLastRecords(ParticleSystem *ps, uint32_t *numSorted); }
+#else
 #include "client/ParticleSystem.cpp"
+#endif
 
 #include "client/AreaSystem.h"
 #include "sf/Geometry.h"
@@ -177,7 +195,12 @@ struct RefSystem
 {
 	cl::Systems systems;
 	sf::Box<cl::ParticleSystem> ps;
+#ifdef SPR_ADAPTER
+	SprSystem *spr = nullptr;
+	std::vector<uint32_t> lastSorted;
+#else
 	cl::ParticleSystemImp *imp = nullptr;
+#endif
 	std::unordered_map<const SprParticleSystemComponent*, sf::Box<sv::ParticleSystemComponent>> comps;
 	std::unordered_map<uint32_t, std::vector<uint8_t>> luts;
 	std::vector<uint64_t> simSteps;
@@ -281,6 +304,9 @@ cl::FrameArgs convertFrameArgs(const SprFrameArgs &a)
 	return f;
 }
 
+#ifdef SPR_ADAPTER
+void countSteps(RefSystem *, const uint32_t *, uint32_t, float) { } // the library counts sim steps itself
+#else
 void countSteps(RefSystem *rs, const uint32_t *ids, uint32_t n, float dt)
 {
 	float clampedDt = sf::min(dt, 0.1f);
@@ -293,6 +319,7 @@ void countSteps(RefSystem *rs, const uint32_t *ids, uint32_t n, float dt)
 		while (td >= e.timeStep) { rs->simSteps[id]++; td = td - e.timeStep; }
 	}
 }
+#endif
 
 }
 
@@ -302,7 +329,11 @@ void countSteps(RefSystem *rs, const uint32_t *ids, uint32_t n, float dt)
 
 extern "C" {
 
+#ifdef SPR_ADAPTER
+const char *orc_kind(void) { return "adapter"; }
+#else
 const char *orc_kind(void) { return "reference"; }
+#endif
 
 void *orc_create(const SprSystemsDesc *desc)
 {
@@ -313,7 +344,12 @@ void *orc_create(const SprSystemsDesc *desc)
 	for (int i = 0; i < 4; i++) d.seed[i] = desc->seed[i];
 	rs->systems.area = sf::box<StubAreaSystem>();
 	rs->ps = cl::ParticleSystem::create(d);
+#ifdef SPR_ADAPTER
+	rs->spr = cl::sprAdapterSystem(rs->ps.ptr);
+	if (!rs->spr) { delete rs; return nullptr; }
+#else
 	rs->imp = (cl::ParticleSystemImp*)rs->ps.ptr;
+#endif
 	rs->systems.particle = rs->ps;
 	return rs;
 }
@@ -342,7 +378,9 @@ uint32_t orc_add_effect(void *sys, uint32_t entityId, uint8_t componentIndex,
 	g_lutCaptured = false;
 	rs->ps->addEffect(rs->systems, entityId, componentIndex, getComponent(rs, c), convertTransform(*transform));
 	uint32_t effectId = cl::g_lastAddedEffectId;
+#ifndef SPR_ADAPTER
 	if (g_lutCaptured) rs->luts[rs->imp->effects[effectId].typeId] = std::vector<uint8_t>(g_lastLut, g_lastLut + SPR_SPLINE_LUT_BYTES);
+#endif
 	if (rs->simSteps.size() <= effectId) rs->simSteps.resize(effectId + 1, 0);
 	rs->simSteps[effectId] = 0;
 	return effectId;
@@ -358,7 +396,7 @@ void orc_update_transform(void *sys, uint32_t effectId, const SprTransformUpdate
 	cl::EntityComponent ec = { };
 	ec.system = rs->ps.ptr;
 	ec.userId = effectId;
-	rs->imp->updateTransform(rs->systems, 0, ec, u);
+	((cl::EntitySystem*)rs->ps.ptr)->updateTransform(rs->systems, 0, ec, u);
 }
 
 int orc_prepare_for_remove(void *sys, uint32_t effectId, const SprFrameArgs *args)
@@ -367,7 +405,7 @@ int orc_prepare_for_remove(void *sys, uint32_t effectId, const SprFrameArgs *arg
 	cl::EntityComponent ec = { };
 	ec.system = rs->ps.ptr;
 	ec.userId = effectId;
-	return rs->imp->prepareForRemove(rs->systems, 0, ec, convertFrameArgs(*args)) ? 1 : 0;
+	return ((cl::EntitySystem*)rs->ps.ptr)->prepareForRemove(rs->systems, 0, ec, convertFrameArgs(*args)) ? 1 : 0;
 }
 
 void orc_remove(void *sys, uint32_t effectId)
@@ -376,7 +414,7 @@ void orc_remove(void *sys, uint32_t effectId)
 	cl::EntityComponent ec = { };
 	ec.system = rs->ps.ptr;
 	ec.userId = effectId;
-	rs->imp->remove(rs->systems, 0, ec);
+	((cl::EntitySystem*)rs->ps.ptr)->remove(rs->systems, 0, ec);
 }
 
 void orc_update(void *sys, const uint32_t *activeIds, uint32_t numActive, const SprFrameArgs *args)
@@ -404,6 +442,47 @@ uint32_t orc_render(void *sys, const uint32_t *visibleIds, uint32_t numVisible,
 	g_draws.clear();
 	memset(&g_curDraw, 0, sizeof(g_curDraw));
 	rs->ps->renderMain(&rs->visFog, rs->areas, ra);
+#ifdef SPR_ADAPTER
+	uint32_t nSorted = 0;
+	const SprDrawRecord *last = cl::sprAdapterLastRecords(rs->ps.ptr, &nSorted);
+	if (numSorted) *numSorted = nSorted;
+	uint32_t n = 0;
+	for (size_t i = 0; i < g_draws.size() && n < capacity; i++, n++) {
+		const CapturedDraw &d = g_draws[i];
+		SprDrawRecord &r = out[n];
+		memset(&r, 0, sizeof(r));
+		r.effectId = last[i].effectId;           // which effect a draw belongs to is not visible in the sg_* calls
+		r.typeId = last[i].typeId;
+		r.numParticles = d.numElements / 6;      // everything else is what the adapter really submitted
+		r.typeUboChanged = d.typeUboChanged;
+		r.vertexByteOffset = d.vertexOffset;
+		r.instanceUbo = d.instanceUbo;
+	}
+	return n;
+}
+
+void orc_effect_info(void *sys, uint32_t effectId, SprEffectInfo *out) { sprGetEffectInfo(((RefSystem*)sys)->spr, effectId, out); }
+
+uint32_t orc_read_free(void *sys, uint32_t effectId, uint32_t *out, uint32_t capacity)
+{
+	uint32_t n = 0; sprReadFreeIndices(((RefSystem*)sys)->spr, effectId, out, capacity, &n); return n;
+}
+
+uint32_t orc_read_stream(void *sys, uint32_t effectId, SprGpuParticle *out, uint32_t capacityVertices)
+{
+	uint32_t n = 0; sprReadVertexStream(((RefSystem*)sys)->spr, effectId, out, capacityVertices, &n); return n;
+}
+
+uint32_t orc_read_slots(void *sys, uint32_t effectId, SprGpuParticle *out, uint32_t capacitySlots)
+{
+	uint32_t n = 0; sprReadSlots(((RefSystem*)sys)->spr, effectId, out, capacitySlots, &n); return n;
+}
+
+void orc_rng_state(void *sys, uint64_t outStateInc[2]) { sprGetRngState(((RefSystem*)sys)->spr, outStateInc); }
+void orc_type_lut(void *sys, uint32_t typeId, uint8_t out[SPR_SPLINE_LUT_BYTES]) { sprGetEffectTypeLut(((RefSystem*)sys)->spr, typeId, out); }
+void orc_type_ubo(void *sys, uint32_t typeId, SprVertexTypeUbo *out) { sprGetEffectTypeUbo(((RefSystem*)sys)->spr, typeId, out); }
+
+#else
 	if (numSorted) *numSorted = rs->imp->sortedEffects.size;
 	uint32_t n = 0;
 	// Draw k corresponds to sortedEffects[k] (the loop at ParticleSystem.cpp:851 only
@@ -503,6 +582,8 @@ void orc_type_ubo(void *sys, uint32_t typeId, SprVertexTypeUbo *out)
 	memcpy(out, &rs->imp->types[typeId].typeUbo, sizeof(SprVertexTypeUbo));
 }
 
+#endif
+
 void orc_make_frustum(const SprMat44 *worldToClip, float clipNearW, SprFrustum *out)
 {
 	sf::Mat44 m;
@@ -527,7 +608,9 @@ double orc_bench_steps(void *sys, const uint32_t *activeIds, uint32_t numActive,
 		fa.gameTime += (double)fa.dt;
 		countSteps(rs, activeIds, numActive, fa.dt);
 		rs->ps->updateParticles(rs->areas, fa);
+#ifndef SPR_ADAPTER
 		for (uint32_t i = 0; i < numActive; i++) total += rs->imp->effects[activeIds[i]].gpuParticles.size / 4;
+#endif
 	}
 	auto t1 = std::chrono::steady_clock::now();
 	if (particleSteps) *particleSteps += total;
