@@ -1277,23 +1277,25 @@ void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &
 	else k_dead_append<false><<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
 }
 
+// Per-device kernel attributes (dynamic shared memory of the fused stream kernel) and its resident
+// CTA count; called once per context, after cudaSetDevice.
+void configure_stream_fused(int ctasPerSm[2])
+{
+	const size_t smem = 2 * 8 * 256 * sizeof(float4);
+	cudaFuncSetAttribute(k_stream_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaFuncSetAttribute(k_stream_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm[0], k_stream_fused<false>, 288, smem);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm[1], k_stream_fused<true>, 288, smem);
+	if (ctasPerSm[0] < 1) ctasPerSm[0] = 1;
+	if (ctasPerSm[1] < 1) ctasPerSm[1] = 1;
+}
+
 uint32_t launch_stream_fused(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool gravityPoints, uint32_t numSms)
+	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2])
 {
 	if (!numPoolTiles) return 0;
-	static int ctasPerSm[2] = { 0, 0 };
 	const size_t smem = 2 * 8 * 256 * sizeof(float4);
 	const int v = gravityPoints ? 1 : 0;
-	if (!ctasPerSm[v]) {
-		if (v) {
-			cudaFuncSetAttribute(k_stream_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm[v], k_stream_fused<true>, 288, smem);
-		} else {
-			cudaFuncSetAttribute(k_stream_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm[v], k_stream_fused<false>, 288, smem);
-		}
-		if (ctasPerSm[v] < 1) ctasPerSm[v] = 1;
-	}
 	uint32_t grid = numSms * (uint32_t)ctasPerSm[v]; // persistent: resident CTAs only (the chained scan needs its predecessors running)
 	if (grid > numPoolTiles) grid = numPoolTiles;
 	if (v) k_stream_fused<true><<<grid, 288, smem, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);

@@ -24,8 +24,10 @@ void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &t
 void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
 	uint32_t epoch, bool sortMode, bool gravityPoints, bool tinyEffects, const float camera[3]);
 void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch, bool aliveScan);
+void configure_stream_fused(int ctasPerSm[2]);
+void configure_sort_kernels();
 uint32_t launch_stream_fused(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool gravityPoints, uint32_t numSms);
+	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2]);
 void launch_expand_stream(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp);
 void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive);
 void launch_gather_render(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, RenderGather *out);

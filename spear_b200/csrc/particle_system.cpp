@@ -47,6 +47,8 @@ Context::Context(const SprContextDesc &desc)
 	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[0], cudaEventDisableTiming));
 	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[1], cudaEventDisableTiming));
 	streamFused = getenv("SPR_STREAM_TWO_PASS") == nullptr; // SPR_STREAM_TWO_PASS=1 selects the two-pass stream mode (A/B measurement)
+	configure_stream_fused(streamFusedCtasPerSm);
+	configure_sort_kernels();
 	freeRanges.resize(33);
 	ensurePool(desc.initialSlotCapacity ? desc.initialSlotCapacity : (1u << 20));
 }
@@ -276,8 +278,12 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	const bool sortMode = (flags & SPR_CTX_SORT_PARTICLES) != 0;
 
 	// ---- host pass: sub-step counts (ParticleSystem.cpp:810-820) and capacity bounds
+	size_t totalActive = 0;
+	for (uint32_t r = 0; r < numReqs; r++) totalActive += reqs[r].numActive;
 	std::vector<ActiveEntry> entries;
 	std::vector<SystemWork> work;
+	entries.reserve(totalActive);
+	work.reserve(numReqs);
 	std::vector<BurstJob> burstJobs;
 	struct Resolve { HostEffect *E; uint32_t add; };
 	std::vector<Resolve> resolve;
@@ -322,7 +328,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				E.simSteps += nsub;
 				totalSimSteps += nsub;
 				E.uploadFrameIndex = 0;                      // :679
-				E.boundsToWorld = E.particlesToWorld;        // gpuBounds uses the matrix of the simulated step (:675-677)
+				if (type.comp->localSpace) E.boundsToWorld = E.particlesToWorld; // gpuBounds uses the matrix of the simulated step (:675-677)
 			}
 			entries.push_back(ae);
 		}
@@ -455,7 +461,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		}
 		if (!sortMode && streamFused) {
 			// stream mode, one pass: integrate + ranks + free list + 4x expansion in a software-pipelined persistent kernel
-			TIMED(kKStreamFused, launch_stream_fused(stream, pool, tab, poolTiles, frameStamp, round, epoch, typesWithGravityPoints != 0, numSms));
+			TIMED(kKStreamFused, launch_stream_fused(stream, pool, tab, poolTiles, frameStamp, round, epoch, typesWithGravityPoints != 0, numSms, streamFusedCtasPerSm));
 		} else {
 			TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, numTinyEffects != 0, camera));
 			TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch, !sortMode));
@@ -704,8 +710,8 @@ void ParticleSystem::updateParticles(const uint32_t *activeIds, uint32_t numActi
 }
 
 namespace {
-struct SortedEffect { // :225-239
-	double renderOrder; uint32_t tiebreaker; float depth; uint32_t effectId;
+struct SortedEffect { // :225-239 (+ the particle count read back from the device, not part of the order)
+	double renderOrder; uint32_t tiebreaker; float depth; uint32_t effectId; uint32_t numParticles;
 	bool operator<(const SortedEffect &rhs) const {
 		if (renderOrder != rhs.renderOrder) return renderOrder < rhs.renderOrder;
 		if (tiebreaker != rhs.tiebreaker) return tiebreaker < rhs.tiebreaker;
@@ -763,8 +769,7 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 	const uint64_t frame = bufferFrameIndex;
 
 	std::vector<SortedEffect> sorted;
-	std::vector<uint32_t> sortedCount;
-	std::unordered_map<uint32_t, uint32_t> countOf;
+	sorted.reserve(numVisible);
 	for (uint32_t i = 0; i < numVisible; i++) {                           // :835-846
 		uint32_t effectId = visibleIds[i];
 		const HostEffect &E = effects[effectId];
@@ -778,8 +783,8 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 		float dx = args.cameraPosition.x - E.origin.x, dy = args.cameraPosition.y - E.origin.y, dz = args.cameraPosition.z - E.origin.z;
 		s.depth = dx*dx + dy*dy + dz*dz;                                  // sf::lengthSq, :844
 		s.effectId = effectId;
+		s.numParticles = numParticles;
 		sorted.push_back(s);
-		countOf[effectId] = numParticles;
 	}
 	std::sort(sorted.begin(), sorted.end());                              // :848 (strict total order)
 
@@ -788,7 +793,7 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 	for (const SortedEffect &s : sorted) {                                // :851-902
 		HostEffect &E = effects[s.effectId];
 		const HostType &type = types[E.typeId];
-		uint32_t numParticles = countOf[s.effectId];
+		uint32_t numParticles = s.numParticles;
 		if (frame - E.uploadFrameIndex >= ctx->maxParticleCacheFrames) {  // :861-867
 			if (numParticles >= frameParticlesLeft) break;               // `return`, :862
 			frameParticlesLeft -= numParticles;

@@ -186,6 +186,7 @@ struct Context {
 	PinnedArray<RenderGather> gatherH;
 	DeviceArray<RenderGather> gatherD;
 	DeviceArray<uint32_t> gatherIdxD;
+	int streamFusedCtasPerSm[2] = { 1, 1 };
 	bool streamFused = true;               // stream mode: one-pass pipelined kernel (default) or integrate + dead_append + expand
 	uint32_t numTinyEffects = 0;          // live effects whose whole range is one 128-slot granule
 	uint32_t typesWithGravityPoints = 0; // live effect types with gravityPoints (selects the kernel variant)

@@ -280,16 +280,17 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	}
 }
 
+// Per-device kernel attributes; called once per context: 4 CTAs x 43 KB of shared memory per SM.
+void configure_sort_kernels()
+{
+	cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &sc,
 	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles, const SortTimingHooks *hooks)
 {
 	if (!numSegments || !numTiles) return 0;
-	static bool carveoutSet = false;
-	if (!carveoutSet) { // 4 CTAs x 43 KB of shared memory per SM
-		cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-		carveoutSet = true;
-	}
 	void *tok = nullptr;
 #define T_BEGIN(k) do { if (hooks) tok = hooks->begin(hooks->ctx, k); } while (0)
 #define T_END(k) do { if (hooks) hooks->end(hooks->ctx, k, tok); } while (0)
