@@ -338,3 +338,38 @@ def test_update_with_nothing_active():
         assert recs == [] and n == 0
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("sort", [False, True], ids=["stream", "sorted"])
+def test_c2_full_size_bit_exact(oracle_port, sort):
+    """BASELINE configs[1] at its full size: 64 emitters x 16k particles, 4 effect types, one shared RNG,
+    gravity/drag, bit-exact against the oracle (stream mode) / its stable depth sort (sort mode)."""
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=sort, initial_slot_capacity=1 << 21)
+    try:
+        seed = (1, 2, 3, 4)
+        s, o = ctx.create_system(seed), orc.OracleSystem(oracle_port, seed)
+        comps = [S.comp_c2(k, burst=16384, churn=True) for k in range(4)]
+        ids = []
+        for i in range(64):
+            tr = abi.make_transform((4.0 * (i % 8), 0.0, 4.0 * (i // 8)))
+            e1, e2 = s.add_effect(comps[i % 4], tr), o.add_effect(comps[i % 4], tr)
+            assert e1 == e2
+            ids.append(e1)
+        for frame in range(5):
+            fa = abi.make_frame_args(0.0175, game_time=frame * 0.0175, frame_index=frame, camera=CAMERA)
+            s.update(ids, fa); o.update(ids, fa)
+        assert s.rng_state() == o.rng_state()
+        total = 0
+        for e in ids:
+            a, b = S.info_tuple(o.effect_info(e)), S.info_tuple(s.effect_info(e))
+            assert a == b, "effect %d" % e
+            total += a["aliveCount"]
+            ref = o.read_stream(e)
+            if sort:
+                ref, _ = expected_sorted(ref)
+            assert ref.tobytes() == s.read_stream(e).tobytes(), "effect %d stream" % e
+            assert np.array_equal(o.read_free(e), s.read_free(e))
+        assert total >= 64 * 16384
+    finally:
+        ctx.close()
