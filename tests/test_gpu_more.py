@@ -373,3 +373,57 @@ def test_c2_full_size_bit_exact(oracle_port, sort):
         assert total >= 64 * 16384
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+@pytest.mark.parametrize("sort", [False, True], ids=["stream", "sorted"])
+def test_random_api_sequence(oracle_port, seed, sort):
+    """Randomised host-API sequence (add / remove / move / prepareForRemove / partial active lists / varying dt)
+    mirrored on the oracle: exercises id recycling, slot-range reuse, effect relocation and pool growth."""
+    import random
+    rnd = random.Random(seed)
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=sort, initial_slot_capacity=1 << 12)
+    try:
+        sseed = (1, 100 + seed, 3, 4)
+        s, o = ctx.create_system(sseed), orc.OracleSystem(oracle_port, sseed)
+        comps = [S.comp_fountain(), S.comp_c5(), S.comp_point(), S.comp_timed_emitter(), S.comp_c1(burst=700), S.comp_local_space(),
+                 S.comp_c2(1, burst=2500, churn=True), S.comp_c2(2, burst=90, churn=True), S.comp_no_emit()]
+        live, transforms, t = [], {}, 0.0
+        for frame in range(70):
+            r = rnd.random()
+            if (r < 0.25 and len(live) < 14) or not live:
+                comp = rnd.choice(comps)
+                tr = abi.make_transform((rnd.uniform(-5, 5), rnd.uniform(0, 2), rnd.uniform(-5, 5)), (0, 0, 0, 1), rnd.choice([1.0, 0.5, 2.0]))
+                e1, e2 = s.add_effect(comp, tr), o.add_effect(comp, tr)
+                assert e1 == e2
+                live.append(e1); transforms[e1] = tr
+            elif r < 0.35 and len(live) > 2:
+                e = live.pop(rnd.randrange(len(live)))
+                s.remove(e); o.remove(e)
+            elif r < 0.55:
+                e = rnd.choice(live)
+                tr = abi.make_transform((rnd.uniform(-5, 5), rnd.uniform(0, 2), rnd.uniform(-5, 5)), (0, 0.38268343, 0, 0.92387953), 1.0)
+                u = S.transform_update(transforms[e], tr)
+                s.update_transform(e, u); o.update_transform(e, u)
+                transforms[e] = tr
+            dt = rnd.choice([0.016, 0.02, 0.033, 0.005, 0.12])
+            fa = abi.make_frame_args(dt, game_time=t, frame_index=frame, camera=CAMERA)
+            if r > 0.9:
+                e = rnd.choice(live)
+                assert s.prepare_for_remove(e, fa) == o.prepare_for_remove(e, fa)
+            active = [e for e in live if rnd.random() < 0.85]
+            s.update(active, fa); o.update(active, fa)
+            t += dt
+            if frame % 7 == 6 or frame == 69:
+                a, b = S.snapshot(o, live), S.snapshot(s, live)
+                if sort:
+                    assert a["rng"] == b["rng"]
+                    for e in live:
+                        assert a[e]["info"] == b[e]["info"], "frame %d effect %d" % (frame, e)
+                        assert np.array_equal(a[e]["free"], b[e]["free"])
+                        assert expected_sorted(a[e]["stream"])[0].tobytes() == b[e]["stream"].tobytes(), "frame %d effect %d" % (frame, e)
+                else:
+                    S.assert_snapshots_equal(a, b, "seed %d frame %d" % (seed, frame))
+    finally:
+        ctx.close()
