@@ -463,8 +463,8 @@ def run_ours(args, rank, world):
         roof = None
         if dom:
             roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": profiled_traffic(dom) if name == "c3" and sorted_mode else None,
-                    "traffic_source": "profiles/r01_ncu_c3_sorted_step.md (ncu --set full, bytes per launch)" if name == "c3" and sorted_mode else None,
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": profiled_traffic(dom) if name == "c3" else None,
+                    "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram bytes per launch)" if name == "c3" else None,
                     "peak_source": peak_src,
                     "alg_bytes_per_particle": alg_key[dom],
                     "step": {"alg_bytes_per_particle_step": alg, "achieved": value / world * alg / 1e9,
