@@ -85,7 +85,7 @@ struct EffectState {
 	uint32_t aliveCount;          // gpuParticles.size / 4
 	uint32_t boundsMin[4];        // order-preserving uint encoding of min(px,py,pz,life), :532
 	uint32_t boundsMax[4];
-	uint32_t _pad[1];
+	uint32_t keyMin;              // sort mode: smallest depth key of the step (the radix sort runs on key - keyMin)
 };
 
 struct SystemDev {

@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab,
 		uint32_t pinf = 0xff800000u /* enc(+inf) */, ninf = 0x007fffffu /* enc(-inf) */;
 #pragma unroll
 		for (int k = 0; k < 4; k++) { S.boundsMin[k] = pinf; S.boundsMax[k] = ninf; }
+		S.keyMin = 0xffffffffu;
 		uint32_t slots = c.blocks * 4, topPost = c.top - (n <= c.top ? n : c.top);
 		if (n > c.top) { uint32_t nb = (n - c.top + 3) >> 2; slots += 4 * nb; topPost = nb * 4 - (n - c.top); }
 		uint32_t par = (rec->flags >> 1) & 1u;
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 	for (int r = 0; r < 4; r++) ld_record(slotPtr + r * 64, a[r], b[r]);
 	const RoundConsts rc = tab.roundConsts[g];
 	uint32_t curBound = 0;
-	if (lane < 8) curBound = lane < 4 ? tab.state[g].boundsMin[lane] : tab.state[g].boundsMax[lane - 4];
+	if (lane < (KEYS ? 9 : 8)) curBound = (&tab.state[g].boundsMin[0])[lane]; // boundsMin[4], boundsMax[4], keyMin are contiguous
 	if (rc.stamp != stamp || rc.round != round) return;
 	const uint32_t slotBase = rc.slotBase;
 	const uint32_t localBase = granule * kGranuleSlots - slotBase;
@@ -549,9 +550,11 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 	step_consts_from(c, rc, tab, g);
 	struct { uint32_t slotsPost; } pe = { rc.slotsPost };
 
-	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
-	uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
-	uint32_t anyAlive = 0, anyDead = 0;
+	// running min / max of the live positions (:532, :611-665; the reference also tracks the life lane of its
+	// Float4 min / max, but gpuBounds only ever uses xyz, :672-677)
+	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu;
+	uint32_t mxx = 0, mxy = 0, mxz = 0;
+	uint32_t anyAlive = 0, anyDead = 0, keyMin = 0xffffffffu;
 	uint32_t *keyPtr = pool.keys + slotBase + localBase + lane;
 	const uint32_t maskWord = (slotBase + localBase) >> 5;
 	const bool tiny = TINY && (rc.flags & 16u); // the whole effect is this one granule: sort and expand in the warp
@@ -566,12 +569,13 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 		}
 		key[r] = 0;
 		if (alive) {
-			uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z), el = enc_float(ra.w);
-			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez); mnl = min(mnl, el);
-			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez); mxl = max(mxl, el);
+			uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z);
+			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez);
+			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez);
 			if (KEYS) {
 				float dx = camX - ra.x, dy = camY - ra.y, dz = camZ - ra.z;
 				key[r] = ~enc_float(dx*dx + dy*dy + dz*dz);       // sf::lengthSq (src/sf/Vector.h:99), descending
+				keyMin = min(keyMin, key[r]);
 				if (!tiny) keyPtr[r * 32] = key[r];
 			}
 		}
@@ -629,15 +633,14 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 	}
 	if (anyDead && lane == 0 && !tiny) tab.effectAnyDead[g] = 1; // idempotent flag, a plain store is enough
 	if (anyAlive) {
-		mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny);
-		mnz = __reduce_min_sync(FULL_MASK, mnz); mnl = __reduce_min_sync(FULL_MASK, mnl);
-		mxx = __reduce_max_sync(FULL_MASK, mxx); mxy = __reduce_max_sync(FULL_MASK, mxy);
-		mxz = __reduce_max_sync(FULL_MASK, mxz); mxl = __reduce_max_sync(FULL_MASK, mxl);
-		if (lane < 8) {
-			uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz : lane == 3 ? mnl
-				: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : mxl;
-			uint32_t *addr = lane < 4 ? &c.S->boundsMin[lane] : &c.S->boundsMax[lane - 4];
-			if (lane < 4) { if (v < curBound) atomicMin(addr, v); }
+		mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny); mnz = __reduce_min_sync(FULL_MASK, mnz);
+		mxx = __reduce_max_sync(FULL_MASK, mxx); mxy = __reduce_max_sync(FULL_MASK, mxy); mxz = __reduce_max_sync(FULL_MASK, mxz);
+		if (KEYS) keyMin = __reduce_min_sync(FULL_MASK, keyMin);
+		if (lane < (KEYS ? 9 : 7) && (lane & 3u) != 3u) { // lanes 0-2: boundsMin, 4-6: boundsMax, 8: keyMin
+			uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz
+				: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : keyMin;
+			uint32_t *addr = &c.S->boundsMin[0] + lane;
+			if (lane < 4 || lane == 8) { if (v < curBound) atomicMin(addr, v); }
 			else { if (v > curBound) atomicMax(addr, v); }
 		}
 	}
@@ -890,8 +893,8 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 				if (active) {
 					StepConsts c;
 					step_consts_from(c, rc, tab, g);
-					uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu, mnl = 0xffffffffu;
-					uint32_t mxx = 0, mxy = 0, mxz = 0, mxl = 0;
+					uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu;
+					uint32_t mxx = 0, mxy = 0, mxz = 0;
 					float4 *stage = sStageAll + (cur * 8 + warp) * 256;
 #pragma unroll
 					for (int r = 0; r < 4; r++) {
@@ -904,9 +907,9 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 						uint32_t am = __ballot_sync(FULL_MASK, alive);
 						dmask[r] = __ballot_sync(FULL_MASK, dead);
 						if (alive) {
-							uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z), el = enc_float(ra.w);
-							mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez); mnl = min(mnl, el);
-							mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez); mxl = max(mxl, el);
+							uint32_t ex = enc_float(ra.x), ey = enc_float(ra.y), ez = enc_float(ra.z);
+							mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez);
+							mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez);
 							uint32_t k = nA + __popc(am & ltMask);
 							stage[2 * k] = ra;
 							stage[2 * k + 1] = rb;
@@ -915,13 +918,11 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 						nD += __popc(dmask[r]);
 					}
 					if (nA) {
-						mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny);
-						mnz = __reduce_min_sync(FULL_MASK, mnz); mnl = __reduce_min_sync(FULL_MASK, mnl);
-						mxx = __reduce_max_sync(FULL_MASK, mxx); mxy = __reduce_max_sync(FULL_MASK, mxy);
-						mxz = __reduce_max_sync(FULL_MASK, mxz); mxl = __reduce_max_sync(FULL_MASK, mxl);
-						if (lane < 8) {
-							uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz : lane == 3 ? mnl
-								: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : mxl;
+						mnx = __reduce_min_sync(FULL_MASK, mnx); mny = __reduce_min_sync(FULL_MASK, mny); mnz = __reduce_min_sync(FULL_MASK, mnz);
+						mxx = __reduce_max_sync(FULL_MASK, mxx); mxy = __reduce_max_sync(FULL_MASK, mxy); mxz = __reduce_max_sync(FULL_MASK, mxz);
+						if (lane < 7 && lane != 3) {
+							uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz
+								: lane == 4 ? mxx : lane == 5 ? mxy : mxz;
 							uint32_t *addr = lane < 4 ? &tab.state[g].boundsMin[lane] : &tab.state[g].boundsMax[lane - 4];
 							if (lane < 4) { if (v < curBound) atomicMin(addr, v); }
 							else { if (v > curBound) atomicMax(addr, v); }

@@ -43,7 +43,7 @@ void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numReco
 // followed by the 4x expansion in sorted order.
 struct SortScratch {
 	uint32_t *keysAlt, *valsAlt;     // ping-pong buffers, same indexing as PoolPtrs::keys/vals
-	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases
+	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases, then [numSegments] pass masks
 	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
 };
 // Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted).

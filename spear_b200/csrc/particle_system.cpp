@@ -419,8 +419,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 
 	const uint32_t nParams = (uint32_t)dirtyParams.size(), nState = (uint32_t)initStateIdx.size();
 	const uint32_t nTypes = (uint32_t)typeIdx.size(), nSys = (uint32_t)systemIdx.size(), nOwner = (uint32_t)ownerJobs.size();
-	dirtyParams.clear(); initStateIdx.clear(); initStateVal.clear(); typeIdx.clear(); typeVal.clear();
-	systemIdx.clear(); systemVal.clear(); ownerJobs.clear();
+	dirtyParams.clear(); ownerJobs.clear();
+	clearUploads(initStateIdx, initStatePos); initStateVal.clear();
+	clearUploads(typeIdx, typePos); typeVal.clear();
+	clearUploads(systemIdx, systemPos); systemVal.clear();
 
 	if (bw.size) {
 		SPR_CUDA(cudaMemcpyAsync(stagingD.ptr, stagingH[par].ptr, bw.size, cudaMemcpyHostToDevice, stream));
@@ -473,7 +475,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	if (sortMode && !segEffects.empty()) {
 		SortScratch sc;
 		sc.keysAlt = dKeys[1]; sc.valsAlt = dVals[1];
-		dSortHist.reserve(segEffects.size() * 4 * 256, 0, stream);
+		dSortHist.reserve(segEffects.size() * (4 * 256 + 1), 0, stream);
 		dSortLookback.reserve(sortTiles.size() * 4 * 256 + 1, 0, stream);
 		sc.hist = dSortHist.ptr; sc.lookback = dSortLookback.ptr;
 		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(kKSortBase + k); },
@@ -515,8 +517,7 @@ ParticleSystem::ParticleSystem(Context *c, const SprSystemsDesc &desc)
 	SystemDev sd;
 	sd.rngState = desc.seed[1];            // sf::Random(desc.seed[1], 581271), :267; ctor src/sf/Random.h:11
 	sd.rngInc = 581271ull | 1ull;
-	ctx->systemIdx.push_back(systemIdx);
-	ctx->systemVal.push_back(sd);
+	Context::queueUpload(ctx->systemIdx, ctx->systemVal, ctx->systemPos, systemIdx, sd);
 }
 
 ParticleSystem::~ParticleSystem()
@@ -585,8 +586,7 @@ uint32_t ParticleSystem::reserveEffectType(const SprParticleSystemComponent *c)
 		}
 		type.hasGravityPoints = td.numGravityPoints != 0;
 		if (type.hasGravityPoints) ctx->typesWithGravityPoints++;
-		ctx->typeIdx.push_back(type.global);
-		ctx->typeVal.push_back(td);
+		Context::queueUpload(ctx->typeIdx, ctx->typeVal, ctx->typePos, type.global, td);
 	} else {
 		typeId = it->second;
 	}
@@ -654,8 +654,7 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 	memset(&S, 0, sizeof(S));
 	S.firstEmit = 1;
 	S.emitOnTimer = c->emitterOnTime;                                      // :750
-	ctx->initStateIdx.push_back(E.global);
-	ctx->initStateVal.push_back(S);
+	Context::queueUpload(ctx->initStateIdx, ctx->initStateVal, ctx->initStatePos, E.global, S);
 	ctx->markParamsDirty(E.global);
 	return effectId;
 }

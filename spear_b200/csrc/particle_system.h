@@ -177,6 +177,19 @@ struct Context {
 	std::vector<uint32_t> typeIdx; std::vector<TypeDev> typeVal;
 	std::vector<uint32_t> systemIdx; std::vector<SystemDev> systemVal;
 	std::vector<FillJob> ownerJobs;
+	// One launch scatters a whole pending list in parallel, so an index may appear in it only once: a
+	// recycled index (type / effect / system removed and re-added before the next submit) replaces its
+	// pending value instead of being queued a second time. pos[i] = 1 + position of i in the list.
+	std::vector<uint32_t> initStatePos, typePos, systemPos;
+	template <typename T>
+	static void queueUpload(std::vector<uint32_t> &idx, std::vector<T> &val, std::vector<uint32_t> &pos, uint32_t i, const T &v)
+	{
+		if (pos.size() <= i) pos.resize((size_t)i + 1, 0);
+		if (pos[i]) { val[pos[i] - 1] = v; return; }
+		idx.push_back(i); val.push_back(v);
+		pos[i] = (uint32_t)idx.size();
+	}
+	static void clearUploads(std::vector<uint32_t> &idx, std::vector<uint32_t> &pos) { for (uint32_t i : idx) pos[i] = 0; idx.clear(); }
 
 	// ---- per-frame staging
 	PinnedArray<uint8_t> stagingH[2];

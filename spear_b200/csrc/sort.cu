@@ -9,7 +9,8 @@
 // exactly that order.
 //
 //   k_sort_hist    per tile: digit histograms of all four passes (keys read once)
-//   k_sort_scan    per (segment, pass): exclusive scan of the 256 bins -> digit bases
+//   k_sort_scan    per (segment, pass): exclusive scan of the 256 bins -> digit bases; marks the
+//                  passes whose digit is constant over the segment (they are skipped)
 //   k_sort_pass    x4: rank keys inside a 4096-key tile (warp match ranking, stable),
 //                  chained look-back per digit across the tiles of the segment,
 //                  stage the tile in shared memory in sorted order, coalesced scatter
@@ -44,9 +45,10 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 	const uint32_t segBase = tab.params[g].slotBase;
 	const uint32_t *keys = pool.keys + segBase + begin;
 	const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5);
+	const uint32_t keyMin = S.keyMin; // digits are taken from key - keyMin: same order, fewer significant bits
 	for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
 		if (!((mask[i >> 5] >> (i & 31)) & 1u)) continue;
-		uint32_t k = keys[i];
+		uint32_t k = keys[i] - keyMin;
 		atomicAdd(&sHist[0 * 256 + (k & 255u)], 1u);
 		atomicAdd(&sHist[1 * 256 + ((k >> 8) & 255u)], 1u);
 		atomicAdd(&sHist[2 * 256 + ((k >> 16) & 255u)], 1u);
@@ -60,15 +62,21 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 	}
 }
 
-// one warp per (segment, pass)
-__global__ void k_sort_scan(TablePtrs tab, const uint32_t *segEffects, uint32_t *hist, uint32_t numRows)
+// one warp per (segment, pass). passMask[segment] (zeroed with the histograms) gets bit p when pass p has
+// to run: pass 0 always (its scatter is the compaction), a later pass only when its digit is not the same
+// for every key of the segment. The digits are those of key - keyMin (EffectState::keyMin, the smallest key of
+// the step: same order, fewer significant bits), and the depths of one effect are floats from a narrow range
+// -- under 2^24 distinct values unless the effect spans more than about two octaves of squared distance --,
+// so the top digit is normally 0 everywhere and that pass would move every pair to where it already is.
+__global__ void k_sort_scan(TablePtrs tab, const uint32_t *segEffects, uint32_t *hist, uint32_t *passMask, uint32_t numRows)
 {
 	uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (row >= numRows) return;
 	uint32_t *h = hist + (size_t)row * 256;
-	uint32_t v[8], sum = 0;
+	uint32_t v[8], sum = 0, big = 0;
 #pragma unroll
-	for (int i = 0; i < 8; i++) { v[i] = h[lane * 8 + i]; sum += v[i]; }
+	for (int i = 0; i < 8; i++) { v[i] = h[lane * 8 + i]; sum += v[i]; big = max(big, v[i]); }
+	big = __reduce_max_sync(FULL_MASK, big);
 	uint32_t incl = sum;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += o; }
@@ -77,6 +85,7 @@ __global__ void k_sort_scan(TablePtrs tab, const uint32_t *segEffects, uint32_t 
 	for (int i = 0; i < 8; i++) { h[lane * 8 + i] = run; run += v[i]; }
 	// the bins of any pass add up to the number of live particles (gpuParticles.size / 4, :670)
 	if ((row & 3u) == 0 && lane == 31) tab.state[segEffects[row >> 2]].aliveCount = run;
+	if (lane == 31 && ((row & 3u) == 0 || big != run)) atomicOr(&passMask[row >> 2], 1u << (row & 3u));
 }
 
 __device__ inline uint32_t ld_relaxed_u32(const uint32_t *p)
@@ -92,10 +101,12 @@ __device__ inline void st_relaxed_u32(uint32_t *p, uint32_t v)
 
 // One radix pass over digit `shift/8`. lookback: [numTiles][256] status words of THIS pass,
 // zero-initialised; word = [31:30] flag (1 aggregate, 2 inclusive prefix), [29:0] count.
+// The pairs ping-pong between buffer 0 (PoolPtrs::keys/vals) and buffer 1 (the Alt pair): a segment that has
+// executed e passes so far has its pairs in buffer e & 1.
 template <bool FIRST>
 __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
-	const uint32_t *keysIn, const uint32_t *valsIn, uint32_t *keysOut, uint32_t *valsOut,
-	const uint32_t *hist, uint32_t *lookback, uint32_t pass)
+	uint32_t *keys0, uint32_t *vals0, uint32_t *keys1, uint32_t *vals1,
+	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t pass)
 {
 	__shared__ uint32_t sKeys[kSortTileKeys];
 	__shared__ uint32_t sVals[kSortTileKeys];
@@ -108,6 +119,11 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const SortTile st = tiles[blockIdx.x];
 	const uint32_t g = segEffects[st.effect];
+	const uint32_t runMask = FIRST ? 1u : passMask[st.effect];
+	if (!FIRST && !((runMask >> pass) & 1u)) return; // constant digit: nothing would move
+	const bool srcIs1 = !FIRST && (__popc(runMask & ((1u << pass) - 1u)) & 1u);
+	const uint32_t *keysIn = srcIs1 ? keys1 : keys0, *valsIn = srcIs1 ? vals1 : vals0;
+	uint32_t *keysOut = srcIs1 ? keys0 : keys1, *valsOut = srcIs1 ? vals0 : vals1;
 	// the first pass reads the keys in SLOT space (holes masked out by the alive ballots) and its
 	// scatter compacts them; later passes run on the dense (key, slot) pairs
 	const uint32_t alive = FIRST ? tab.state[g].slotCount[tab.state[g].parity] : tab.state[g].aliveCount;
@@ -116,6 +132,7 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	const uint32_t count = min(kSortTileKeys, alive - begin);
 	const uint32_t segBase = tab.params[g].slotBase;
 	const uint32_t shift = pass * 8;
+	const uint32_t keyMin = tab.state[g].keyMin;
 	const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5) + warp * (kWarpKeys / 32);
 
 	for (uint32_t i = tid; i < 8 * 256; i += kSortThreads) { sCnt[i] = 0; sVals[i] = 0; sVals[i + 8 * 256] = 0; }
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
 		uint32_t *match = (i & 1u) ? match1 : match0;
 		bool ok = (okBits >> i) & 1u;
-		uint32_t d = (key[i] >> shift) & 255u;
+		uint32_t d = ((key[i] - keyMin) >> shift) & 255u;
 		if (ok) atomicOr(&match[d], 1u << lane);
 		__syncwarp();
 		uint32_t peers = ok ? match[d] : 0u;
@@ -197,7 +214,7 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 #pragma unroll
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
 		if ((okBits >> i) & 1u) {
-			uint32_t d = (key[i] >> shift) & 255u;
+			uint32_t d = ((key[i] - keyMin) >> shift) & 255u;
 			uint32_t rk = (i & 1u) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
 			uint32_t pos = sTileExcl[d] + sCnt[warp * 256 + d] + rk;
 			sKeys[pos] = key[i];
@@ -225,7 +242,7 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	const uint32_t tileCount = sTileCount;
 	for (uint32_t j = tid; j < tileCount; j += kSortThreads) {
 		uint32_t k = sKeys[j];
-		uint32_t d = (k >> shift) & 255u;
+		uint32_t d = ((k - keyMin) >> shift) & 255u;
 		uint32_t dst = (uint32_t)(sGlobal[d] + (int32_t)j);
 		kout[dst] = k;
 		vout[dst] = sVals[j];
@@ -247,7 +264,8 @@ __device__ inline void st_record_cs(float4 *p, const float4 &a, const float4 &b)
 		:: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
 }
 
-__global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles)
+__global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
+	const uint32_t *valsAlt, const uint32_t *passMask)
 {
 	// four CTAs per 4096-key sort tile: 1024 particles per CTA, 4 per thread, all gathers in flight at once
 	SortTile st = tiles[blockIdx.x >> 2];
@@ -257,7 +275,10 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	if (begin >= alive) return;
 	uint32_t count = min(1024u, alive - begin);
 	uint32_t segBase = tab.params[g].slotBase;
-	const uint32_t *vals = pool.vals + segBase + begin;
+	// an odd number of executed passes leaves the sorted slots in the Alt buffer: copy them to PoolPtrs::vals on
+	// the way (the parity read-back sprReadStreamSlots reads them there)
+	const bool fromAlt = __popc(passMask[st.effect]) & 1u;
+	const uint32_t *vals = (fromAlt ? valsAlt : pool.vals) + segBase + begin;
 	const float4 *state = pool.state + 2ull * segBase;
 	float4 *dst = pool.vertices + 8ull * (segBase + begin);
 	uint32_t slot[4];
@@ -266,6 +287,7 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	for (int u = 0; u < 4; u++) {
 		uint32_t i = u * 256 + threadIdx.x;
 		slot[u] = i < count ? vals[i] : 0xffffffffu;
+		if (fromAlt && i < count) pool.vals[segBase + begin + i] = slot[u];
 	}
 #pragma unroll
 	for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_cg(state + 2ull * slot[u], a[u], b[u]);
@@ -294,26 +316,27 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 	void *tok = nullptr;
 #define T_BEGIN(k) do { if (hooks) tok = hooks->begin(hooks->ctx, k); } while (0)
 #define T_END(k) do { if (hooks) hooks->end(hooks->ctx, k, tok); } while (0)
-	cudaMemsetAsync(sc.hist, 0, (size_t)numSegments * 1024 * sizeof(uint32_t), st);
+	uint32_t *passMask = sc.hist + (size_t)numSegments * 1024; // [numSegments], cleared together with the histograms
+	cudaMemsetAsync(sc.hist, 0, (size_t)numSegments * 1025 * sizeof(uint32_t), st);
 	cudaMemsetAsync(sc.lookback, 0, (size_t)numTiles * 4 * 256 * sizeof(uint32_t), st);
 	T_BEGIN(0);
 	k_sort_hist<<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, sc.hist);
 	T_END(0);
 	uint32_t rows = numSegments * 4;
 	T_BEGIN(1);
-	k_sort_scan<<<(rows * 32 + 255) / 256, 256, 0, st>>>(tab, segEffects, sc.hist, rows);
+	k_sort_scan<<<(rows * 32 + 255) / 256, 256, 0, st>>>(tab, segEffects, sc.hist, passMask, rows);
 	T_END(1);
 	uint32_t *kbuf[2] = { pool.keys, sc.keysAlt };
 	uint32_t *vbuf[2] = { pool.vals, sc.valsAlt };
 	for (uint32_t p = 0; p < 4; p++) {
 		T_BEGIN(2);
-		if (p == 0) k_sort_pass<true><<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, sc.lookback, p);
-		else k_sort_pass<false><<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, kbuf[p & 1], vbuf[p & 1], kbuf[(p & 1) ^ 1], vbuf[(p & 1) ^ 1],
-			sc.hist, sc.lookback + (size_t)p * numTiles * 256, p);
+		if (p == 0) k_sort_pass<true><<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, sc.lookback, p);
+		else k_sort_pass<false><<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1],
+			sc.hist, passMask, sc.lookback + (size_t)p * numTiles * 256, p);
 		T_END(2);
 	}
 	T_BEGIN(3);
-	k_expand_sorted<<<numTiles * 4, 256, 0, st>>>(pool, tab, segEffects, tiles);
+	k_expand_sorted<<<numTiles * 4, 256, 0, st>>>(pool, tab, segEffects, tiles, sc.valsAlt, passMask);
 	T_END(3);
 	return 7;
 }

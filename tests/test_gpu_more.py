@@ -290,9 +290,12 @@ def test_pack_and_fused_expand_from_run_buffers(oracle_port):
         ctx.close()
 
 
-def test_type_and_effect_id_recycling(oracle_port):
+@pytest.mark.parametrize("attempt", range(4))
+def test_type_and_effect_id_recycling(oracle_port, attempt):
     """Dense u32 ids recycled LIFO, types keyed by descriptor identity and refcounted
-    (ParticleSystem.cpp:242-246, :682-728, :733-737, :796-806)."""
+    (ParticleSystem.cpp:242-246, :682-728, :733-737, :796-806). Several attempts: a type / effect index
+    that is freed and reused before the next submit is uploaded once, with its last value (two uploads
+    of one index in the same parallel scatter were a race that only showed up now and then)."""
     P = _particles()
     ctx = P.ParticleContext(initial_slot_capacity=1 << 16)
     try:
