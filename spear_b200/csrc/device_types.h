@@ -85,8 +85,17 @@ struct EffectState {
 	uint32_t aliveCount;          // gpuParticles.size / 4
 	uint32_t boundsMin[4];        // order-preserving uint encoding of min(px,py,pz,life), :532
 	uint32_t boundsMax[4];
-	uint32_t keyMin;              // sort mode: smallest depth key of the step (the radix sort runs on key - keyMin)
+	uint32_t keyMin[8];           // sort mode: smallest depth key of the step = min over the 8 words (one per warp position
+	                              // in the CTA, so that the first wave of atomics does not pile up on one address);
+	                              // the radix sort runs on key - keyMin
 };
+
+__host__ __device__ inline uint32_t effect_key_min(const EffectState &S)
+{
+	uint32_t m = S.keyMin[0];
+	for (int i = 1; i < 8; i++) m = S.keyMin[i] < m ? S.keyMin[i] : m;
+	return m;
+}
 
 struct SystemDev {
 	uint64_t rngState, rngInc;    // updateCtx.rng, :251,:267

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab,
 		uint32_t pinf = 0xff800000u /* enc(+inf) */, ninf = 0x007fffffu /* enc(-inf) */;
 #pragma unroll
 		for (int k = 0; k < 4; k++) { S.boundsMin[k] = pinf; S.boundsMax[k] = ninf; }
-		S.keyMin = 0xffffffffu;
+		for (int k = 0; k < 8; k++) S.keyMin[k] = 0xffffffffu;
 		uint32_t slots = c.blocks * 4, topPost = c.top - (n <= c.top ? n : c.top);
 		if (n > c.top) { uint32_t nb = (n - c.top + 3) >> 2; slots += 4 * nb; topPost = nb * 4 - (n - c.top); }
 		uint32_t par = (rec->flags >> 1) & 1u;
@@ -531,17 +531,14 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 	const uint32_t granule = blockIdx.x * 8 + warp;
 	uint32_t g = pool.granuleOwner[granule];
 	if (g == kNoOwner) return;
-	// Everything that depends only on the owner is requested at once: the effect's round record,
-	// its current bounds (a stale value is a valid filter for the min/max atomics, they only ever
-	// tighten) and the 128 slot records, whose address is a function of the granule alone.
+	// Everything that depends only on the owner is requested at once: the effect's round record
+	// and the 128 slot records, whose address is a function of the granule alone.
 	// Ownership covers only the slots the effect can have reached, so these loads are rarely wasted.
 	float4 a[4], b[4];
 	float4 *slotPtr = pool.state + 2ull * ((uint64_t)granule * kGranuleSlots + lane);
 #pragma unroll
 	for (int r = 0; r < 4; r++) ld_record(slotPtr + r * 64, a[r], b[r]);
 	const RoundConsts rc = tab.roundConsts[g];
-	uint32_t curBound = 0;
-	if (lane < (KEYS ? 9 : 8)) curBound = (&tab.state[g].boundsMin[0])[lane]; // boundsMin[4], boundsMax[4], keyMin are contiguous
 	if (rc.stamp != stamp || rc.round != round) return;
 	const uint32_t slotBase = rc.slotBase;
 	const uint32_t localBase = granule * kGranuleSlots - slotBase;
@@ -555,7 +552,7 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 	uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mnz = 0xffffffffu;
 	uint32_t mxx = 0, mxy = 0, mxz = 0;
 	uint32_t anyAlive = 0, anyDead = 0, keyMin = 0xffffffffu;
-	uint32_t *keyPtr = pool.keys + slotBase + localBase + lane;
+	const uint32_t keyIdx = slotBase + localBase + lane; // indices, not pointers: one live register each
 	const uint32_t maskWord = (slotBase + localBase) >> 5;
 	const bool tiny = TINY && (rc.flags & 16u); // the whole effect is this one granule: sort and expand in the warp
 	uint32_t am[4], dm[4], key[4];
@@ -576,7 +573,7 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 				float dx = camX - ra.x, dy = camY - ra.y, dz = camZ - ra.z;
 				key[r] = ~enc_float(dx*dx + dy*dy + dz*dz);       // sf::lengthSq (src/sf/Vector.h:99), descending
 				keyMin = min(keyMin, key[r]);
-				if (!tiny) keyPtr[r * 32] = key[r];
+				if (!tiny) pool.keys[keyIdx + r * 32] = key[r];
 			}
 		}
 		if (TINY) { a[r] = ra; b[r] = rb; }
@@ -639,7 +636,9 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 		if (lane < (KEYS ? 9 : 7) && (lane & 3u) != 3u) { // lanes 0-2: boundsMin, 4-6: boundsMax, 8: keyMin
 			uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz
 				: lane == 4 ? mxx : lane == 5 ? mxy : lane == 6 ? mxz : keyMin;
-			uint32_t *addr = &c.S->boundsMin[0] + lane;
+			uint32_t *addr = &c.S->boundsMin[0] + (lane < 8 ? lane : 8 + warp); // boundsMin[4], boundsMax[4], keyMin[8] are contiguous
+			// the current value (read at L2, where the atomics land) filters out almost every atomic: the bounds only ever tighten
+			const uint32_t curBound = __ldcg(addr);
 			if (lane < 4 || lane == 8) { if (v < curBound) atomicMin(addr, v); }
 			else { if (v > curBound) atomicMax(addr, v); }
 		}
@@ -886,8 +885,6 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 			if (g != kNoOwner) {
 				float4 *slotPtr = pool.state + 2ull * ((uint64_t)granule * kGranuleSlots + lane);
 				rc = tab.roundConsts[g];
-				uint32_t curBound = 0;
-				if (lane < 8) curBound = lane < 4 ? tab.state[g].boundsMin[lane] : tab.state[g].boundsMax[lane - 4];
 				localBase = granule * kGranuleSlots - rc.slotBase;
 				active = rc.stamp == stamp && rc.round == round && localBase < rc.slotsPost;
 				if (active) {
@@ -924,6 +921,7 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 							uint32_t v = lane == 0 ? mnx : lane == 1 ? mny : lane == 2 ? mnz
 								: lane == 4 ? mxx : lane == 5 ? mxy : mxz;
 							uint32_t *addr = lane < 4 ? &tab.state[g].boundsMin[lane] : &tab.state[g].boundsMax[lane - 4];
+							const uint32_t curBound = __ldcg(addr); // read late and at L2: filters out almost every atomic (the bounds only tighten)
 							if (lane < 4) { if (v < curBound) atomicMin(addr, v); }
 							else { if (v > curBound) atomicMax(addr, v); }
 						}

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 	const uint32_t segBase = tab.params[g].slotBase;
 	const uint32_t *keys = pool.keys + segBase + begin;
 	const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5);
-	const uint32_t keyMin = S.keyMin; // digits are taken from key - keyMin: same order, fewer significant bits
+	const uint32_t keyMin = effect_key_min(S); // digits are taken from key - keyMin: same order, fewer significant bits
 	for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) {
 		if (!((mask[i >> 5] >> (i & 31)) & 1u)) continue;
 		uint32_t k = keys[i] - keyMin;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	const uint32_t count = min(kSortTileKeys, alive - begin);
 	const uint32_t segBase = tab.params[g].slotBase;
 	const uint32_t shift = pass * 8;
-	const uint32_t keyMin = tab.state[g].keyMin;
+	const uint32_t keyMin = effect_key_min(tab.state[g]);
 	const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5) + warp * (kWarpKeys / 32);
 
 	for (uint32_t i = tid; i < 8 * 256; i += kSortThreads) { sCnt[i] = 0; sVals[i] = 0; sVals[i + 8 * 256] = 0; }
