@@ -29,6 +29,7 @@ namespace spr {
 static const uint32_t kSortThreads = 256;
 static const uint32_t kItemsPerThread = kSortTileKeys / kSortThreads; // 16
 static const uint32_t kWarpKeys = kSortTileKeys / 8;                  // 512 keys per warp
+static const uint32_t kLook = 8;                                      // status words fetched per look-back batch
 
 __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t *hist)
 {
@@ -186,12 +187,23 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 		st_relaxed_u32(lb, (2u << 30) | total);
 	} else {
 		st_relaxed_u32(lb, (1u << 30) | total);
+		// walk back over the predecessors' status words of this digit, kLook at a time: the loads of one batch are
+		// independent, so a long walk costs one L2 round trip per batch instead of one per tile
 		const uint32_t *p = lb - 256; // tiles of one segment are consecutive in the tile table
-		for (uint32_t t = st.tile; t > 0; t--, p -= 256) {
-			uint32_t v;
-			do { v = ld_relaxed_u32(p); } while ((v >> 30) == 0);
-			excl += v & 0x3fffffffu;
-			if ((v >> 30) == 2u) break;
+		bool found = false;
+		for (uint32_t t = st.tile; t > 0 && !found; ) {
+			const uint32_t n = t < kLook ? t : kLook;
+			uint32_t v[kLook];
+#pragma unroll
+			for (uint32_t i = 0; i < kLook; i++) v[i] = i < n ? ld_relaxed_u32(p - i * 256) : (2u << 30);
+#pragma unroll
+			for (uint32_t i = 0; i < kLook; i++) {
+				if (found) break;
+				while ((v[i] >> 30) == 0) v[i] = ld_relaxed_u32(p - i * 256);
+				excl += v[i] & 0x3fffffffu;
+				found = (v[i] >> 30) == 2u;
+			}
+			p -= kLook * 256; t -= n;
 		}
 		st_relaxed_u32(lb, (2u << 30) | (excl + total));
 	}
