@@ -521,7 +521,7 @@ def run_ours(args, rank, world):
             try:
                 cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--no-sort", "--no-cpu-baseline", "--no-stream-mode",
                        "--steps", str(args.steps), "--warmup", str(args.warmup)]
-                r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
                 sm = json.loads(r.stdout.strip().splitlines()[-1])
                 out["stream_mode"] = {"value": sm["value"], "unit": UNIT, "ms_per_step": sm["ms_per_step"], "e2e": sm["e2e"]["value"],
                                       "roofline": sm["roofline"], "kernels": sm["kernels"], "gpu_launches": sm["gpu_launches"],
@@ -647,4 +647,8 @@ def main():
 
 
 if __name__ == "__main__":
+    # a run that stops making progress dumps every thread's stack to stderr and exits instead of sitting on the GPU box
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(int(os.environ.get("SPR_BENCH_WATCHDOG_S", "900")), exit=True)
     main()

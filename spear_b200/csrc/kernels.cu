@@ -420,6 +420,12 @@ __global__ void __launch_bounds__(256) k_emit_burst(PoolPtrs pool, TablePtrs tab
 // k_integrate (:526-666)
 // ---------------------------------------------------------------------------
 
+// A chained scan only ever waits for a predecessor that is already running (tiles are dispatched in order and the
+// persistent kernels launch resident CTAs only), so a wait is a few microseconds. Should that assumption ever break,
+// the wait traps after ~2^24 polls: the launch fails with an error the host reports, instead of hanging the GPU.
+static const uint32_t kMaxSpins = 1u << 24;
+__device__ __forceinline__ void spin_guard(uint32_t &spins) { if (++spins > kMaxSpins) __trap(); }
+
 __device__ inline unsigned long long ld_status(const unsigned long long *p)
 {
 	unsigned long long v;
@@ -656,7 +662,7 @@ __device__ inline uint32_t tile_lookback1(unsigned long long *st, uint32_t poolT
 	int32_t rel = (int32_t)tileIdx - 1 - (int32_t)lane;
 	for (;;) {
 		unsigned long long v = tag | fIncl;
-		if (rel >= 0) { uint32_t t = poolTile - (tileIdx - (uint32_t)rel); do { v = ld_status(st + t); } while ((v >> 34) != epoch); }
+		if (rel >= 0) { uint32_t t = poolTile - (tileIdx - (uint32_t)rel); uint32_t spins = 0; do { v = ld_status(st + t); spin_guard(spins); } while ((v >> 34) != epoch); }
 		uint32_t incl = __ballot_sync(FULL_MASK, ((v >> 32) & 3u) == 2u);
 		uint32_t upTo = incl ? (uint32_t)(__ffs(incl) - 1) : 31u;
 		excl += __reduce_add_sync(FULL_MASK, lane <= upTo ? (uint32_t)v : 0u);
@@ -810,8 +816,9 @@ __device__ inline void tile_lookback2(unsigned long long *stA, unsigned long lon
 			unsigned long long va = tag | fIncl, vd = tag | fIncl; // virtual zero prefix in front of tile 0
 			if (rel >= 0) {
 				uint32_t t = poolTile - (tileIdx - (uint32_t)rel);
-				if (!doneA) do { va = ld_status(stA + t); } while ((va >> 34) != epoch);
-				if (!doneD) do { vd = ld_status(stD + t); } while ((vd >> 34) != epoch);
+				uint32_t spins = 0;
+				if (!doneA) do { va = ld_status(stA + t); spin_guard(spins); } while ((va >> 34) != epoch);
+				if (!doneD) do { vd = ld_status(stD + t); spin_guard(spins); } while ((vd >> 34) != epoch);
 			}
 			if (!doneA) {
 				uint32_t incl = __ballot_sync(FULL_MASK, ((va >> 32) & 3u) == 2u);

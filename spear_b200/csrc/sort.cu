@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 #pragma unroll
 			for (uint32_t i = 0; i < kLook; i++) {
 				if (found) break;
-				while ((v[i] >> 30) == 0) v[i] = ld_relaxed_u32(p - i * 256);
+				// (a predecessor tile is always already running; trap instead of hanging if that ever breaks)
+				for (uint32_t spins = 0; (v[i] >> 30) == 0; ) { v[i] = ld_relaxed_u32(p - i * 256); if (++spins > (1u << 24)) __trap(); }
 				excl += v[i] & 0x3fffffffu;
 				found = (v[i] >> 30) == 2u;
 			}
