@@ -309,6 +309,31 @@ def run_ours(args, rank, world):
     h2d = n_eff * 16 + len(systems) * 16 + n_eff * 4  # ActiveEntry + SystemWork per frame, ids for the gather
     d2h = n_eff * 60                                   # RenderGather per visible effect
 
+    # ---- vertex stage: Particle.glsl `vs` over the draw records of the last frame, N=1 only.
+    # 32 B read + 4 x 64 B written per particle; timed alone (it is not part of `value`).
+    vertex_stage = None
+    if world == 1 and not args.no_vertex_stage and len(outs) == 1 and n_alive * 256 < 40e9:
+        recs = [outs[0].records[i] for i in range(outs[0].numRecords)]
+        nv = 4 * sum(r.numParticles for r in recs)
+        shaded = torch.empty((nv, 16), dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            systems[0].shade_vertices(recs, shaded.data_ptr(), nv)
+        ctx.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        v0.record(ext)
+        for _ in range(reps):
+            systems[0].shade_vertices(recs, shaded.data_ptr(), nv)
+        v1.record(ext)
+        ctx.synchronize(); torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1) / reps
+        peak_v, _src = measured_peak()
+        vertex_stage = {"kernel": "k_shade_vertices", "ms_per_launch": vms, "vertices": nv, "particles_per_s": nv / 4 / (vms * 1e-3),
+                        "alg_bytes_per_particle": 288.0, "achieved_gbs": nv / 4 * 288.0 / (vms * 1e-3) / 1e9,
+                        "frac": nv / 4 * 288.0 / (vms * 1e-3) / 1e9 / peak_v,
+                        "note": "sprShadeVertices over the frame's draw records: gl_Position, uv0, uv1, colour, params (64 B) for 4 vertices per particle"}
+        del shaded
+
     # ---- multi-GPU draw-stream assembly: every rank ends up with the whole draw stream (4 vertices per
     # particle, rank-major). Two implementations, both timed:
     #   nccl : sprPackRuns -> NCCL all_gather of the 32-byte records -> sprExpandRuns
@@ -488,6 +513,8 @@ def run_ours(args, rank, world):
             "kernels": kern,
             "kernel_timing": "CUDA event pair around every launch, over the same K steps repeated immediately after the timed region",
         }
+        if vertex_stage is not None:
+            out["vertex_stage"] = vertex_stage
         if gather is not None:
             nv = gather["nvlink_bytes_in_per_step"]
             out["gather"] = {
@@ -519,7 +546,7 @@ def run_ours(args, rank, world):
     if rank == 0:
         if out.get("stream_mode") == "pending":
             try:
-                cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--no-sort", "--no-cpu-baseline", "--no-stream-mode",
+                cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--no-sort", "--no-cpu-baseline", "--no-stream-mode", "--no-vertex-stage",
                        "--steps", str(args.steps), "--warmup", str(args.warmup)]
                 r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
                 sm = json.loads(r.stdout.strip().splitlines()[-1])
@@ -635,6 +662,7 @@ def main():
     ap.add_argument("--no-sort", action="store_true", help="strict drop-in stream (slot order), no per-particle depth sort")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream-mode", action="store_true", help="skip the extra stream-mode (no sort) measurement at N=1")
+    ap.add_argument("--no-vertex-stage", action="store_true", help="skip the extra vertex-stage (sprShadeVertices) measurement at N=1")
     ap.add_argument("--no-kernel-timing", action="store_true", help="no per-launch CUDA events inside the timed region (no roofline object)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -420,6 +420,36 @@ SPR_API int sprGetEffectTypeUbo(SprSystem *sys, uint32_t typeId, SprVertexTypeUb
 SPR_API int sprBakeEffectType(const SprParticleSystemComponent *c, uint32_t typeId,
 	uint8_t outLut[SPR_SPLINE_LUT_BYTES], SprVertexTypeUbo *outUbo);
 
+/* ------------------------------------------------------------------------ */
+/* Vertex stage                                       */
+/* ------------------------------------------------------------------------ */
+
+/* What the reference's vertex shader writes for one vertex
+ * (src/game/shader/Particle.glsl:73-140: gl_Position, v_Uv0, v_Uv1, flat v_Color, flat v_Params). */
+typedef struct SprShadedVertex {
+	float position[4];
+	float uv0[2];
+	float uv1[2];
+	float color[4];
+	float params[4];
+} SprShadedVertex;
+
+/* u_VisFogTexture (Particle.glsl:13, :43-50): RG8 unorm texels, row major, bilinear,
+ * clamp-to-edge. A DEVICE pointer; the image belongs to the caller (cl::VisFogSystem is outside the path). */
+typedef struct SprFogImage {
+	const void *deviceTexels;
+	uint32_t width, height;
+} SprFogImage;
+
+/* Runs Particle.glsl `vs` (src/game/shader/Particle.glsl:73-140) over the draw records sprRenderMain
+ * returned (ParticleSystem.cpp:851-901): record r contributes 4 * numParticles vertices, in record order,
+ * particle k of it at vertices 4k..4k+3 (corner = vertex & 3, Particle.glsl:91), written to the DEVICE
+ * buffer `deviceOut` (capacityVertices entries; records that do not fit are cut off at a quad boundary).
+ * `fog` may be NULL: every particle fully visible. Stream-ordered on the context's stream, not
+ * synchronised. Texture filtering is done in float (hardware quantises the weights to 8 bits). */
+SPR_API int sprShadeVertices(SprSystem *sys, const SprDrawRecord *records, uint32_t numRecords, const SprFogImage *fog,
+	SprShadedVertex *deviceOut, uint64_t capacityVertices, uint64_t *outNumVertices);
+
 /* Device pointers for zero-copy consumers (benchmarks, the multi-GPU gather). */
 typedef struct SprEffectDeviceView {
 	const SprGpuParticle *vertices;    /* DEVICE: effect's run, 4 vertices per particle */

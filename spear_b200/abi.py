@@ -155,6 +155,16 @@ class DrawRecord(C.Structure):
                 ("typeUboChanged", C.c_uint32), ("vertexByteOffset", C.c_uint64), ("instanceUbo", VertexInstanceUbo)]
 
 
+class ShadedVertex(C.Structure):
+    """SprShadedVertex: the outputs of Particle.glsl `vs` for one vertex (64 bytes)."""
+    _fields_ = [("position", C.c_float * 4), ("uv0", C.c_float * 2), ("uv1", C.c_float * 2),
+                ("color", C.c_float * 4), ("params", C.c_float * 4)]
+
+
+class FogImage(C.Structure):
+    _fields_ = [("deviceTexels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
 class RenderOutput(C.Structure):
     _fields_ = [("deviceVertices", C.c_void_p), ("records", C.POINTER(DrawRecord)), ("numRecords", C.c_uint32),
                 ("numSortedEffects", C.c_uint32)]

@@ -309,6 +309,17 @@ SPR_API int sprGetRngState(SprSystem *sys, uint64_t outStateInc[2])
 	});
 }
 
+SPR_API int sprShadeVertices(SprSystem *sys, const SprDrawRecord *records, uint32_t numRecords, const SprFogImage *fog,
+	SprShadedVertex *deviceOut, uint64_t capacityVertices, uint64_t *outNumVertices)
+{
+	REQUIRE(sys && (records || !numRecords) && (deviceOut || !capacityVertices));
+	REQUIRE(!fog || (fog->deviceTexels && fog->width && fog->height));
+	return guarded([&] {
+		uint64_t n = sys->sys.shadeVertices(records, numRecords, fog, deviceOut, capacityVertices);
+		if (outNumVertices) *outNumVertices = n;
+	});
+}
+
 SPR_API int sprGetEffectTypeLut(SprSystem *sys, uint32_t typeId, uint8_t out[SPR_SPLINE_LUT_BYTES])
 {
 	REQUIRE(sys && out && typeId < sys->sys.types.size() && sys->sys.types[typeId].comp);

@@ -156,6 +156,19 @@ struct BurstJob {
 
 struct FillJob { uint32_t start, count, value, _pad; };
 
+// One draw record for the vertex-stage kernel (vertex_stage.cu): `numParticles` quads read from stream record
+// `srcRecord` (32-byte units), written from vertex `dstVertex` on, by CTAs [firstBlock, firstBlock + ceil(n / 256)).
+struct ShadeJob {
+	uint64_t srcRecord;
+	uint64_t dstVertex;
+	uint32_t numParticles;
+	uint32_t lutIndex;        // which 128-word LUT of the call's LUT table (one per distinct effect type)
+	uint32_t firstBlock;
+	uint32_t _pad;
+	float instance[40];       // Particle_VertexInstance_t, 160 bytes (ParticleSystem.cpp:871-876)
+	float type[24];           // Particle_VertexType_t, 96 bytes (:312-321, :410-419)
+};
+
 // Sort tile: `tile`-th 4096-key tile of effect `effect`'s pair segment.
 struct SortTile { uint32_t effect; uint32_t tile; };
 

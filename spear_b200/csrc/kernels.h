@@ -39,6 +39,10 @@ void launch_pack_runs_buf(cudaStream_t st, const PoolPtrs &pool, const TablePtrs
 void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numSms);
 void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numRecords, float4 *out, uint32_t numSms);
 
+// vertex_stage.cu: Particle.glsl `vs` over draw records
+void launch_shade_vertices(cudaStream_t st, const float4 *vertices, const ShadeJob *jobs, uint32_t numJobs, uint32_t totalBlocks,
+	const uint32_t *luts, const uint8_t *fogTexels, uint32_t fogW, uint32_t fogH, float4 *out, uint64_t capacityVertices);
+
 // sort.cu: segmented stable LSD radix sort of the (key, slot) pairs of the listed effects
 // followed by the 4x expansion in sorted order.
 struct SortScratch {

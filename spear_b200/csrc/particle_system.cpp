@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <map>
+#include <unordered_map>
 #include <stdlib.h>
 #include <string.h>
 
@@ -817,6 +818,60 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 	out.records = drawRecords.data();
 	out.numRecords = (uint32_t)drawRecords.size();
 	out.numSortedEffects = (uint32_t)sorted.size();
+}
+
+// ---------------------------------------------------------------------------
+// Vertex stage
+// ---------------------------------------------------------------------------
+
+uint64_t ParticleSystem::shadeVertices(const SprDrawRecord *records, uint32_t numRecords, const SprFogImage *fog, SprShadedVertex *deviceOut, uint64_t capacityVertices)
+{
+	static_assert(sizeof(SprVertexInstanceUbo) == 160 && sizeof(SprVertexTypeUbo) == 96, "UBO layouts of src/game/shader/Particle.h:100-125");
+	static_assert(sizeof(SprShadedVertex) == 64, "four float4 per shaded vertex");
+	if (!numRecords) return 0;
+	SPR_CUDA(cudaSetDevice(ctx->device));
+	std::vector<ShadeJob> jobs;
+	std::vector<uint32_t> luts;                         // 128 words per distinct effect type
+	std::unordered_map<uint32_t, uint32_t> lutOfType;
+	uint64_t vertex = 0;
+	uint32_t blocks = 0;
+	for (uint32_t r = 0; r < numRecords; r++) {
+		const SprDrawRecord &d = records[r];
+		if (d.typeId >= types.size() || !types[d.typeId].comp) throw std::runtime_error("sprShadeVertices: record with an unknown effect type");
+		uint64_t n = d.numParticles;
+		if (vertex + 4 * n > capacityVertices) n = (capacityVertices - vertex) / 4;
+		if (!n) break;
+		auto it = lutOfType.find(d.typeId);
+		if (it == lutOfType.end()) {
+			it = lutOfType.emplace(d.typeId, (uint32_t)(luts.size() / 128)).first;
+			const uint8_t *lut = types[d.typeId].lut;
+			for (uint32_t i = 0; i < 128; i++) luts.push_back((uint32_t)lut[4 * i] | (uint32_t)lut[4 * i + 1] << 8 | (uint32_t)lut[4 * i + 2] << 16 | (uint32_t)lut[4 * i + 3] << 24);
+		}
+		ShadeJob j;
+		memset(&j, 0, sizeof(j));
+		j.srcRecord = d.vertexByteOffset / sizeof(SprGpuParticle);
+		j.dstVertex = vertex;
+		j.numParticles = (uint32_t)n;
+		j.lutIndex = it->second;
+		j.firstBlock = blocks;
+		memcpy(j.instance, &d.instanceUbo, sizeof(j.instance));
+		memcpy(j.type, &types[d.typeId].typeUbo, sizeof(j.type));
+		jobs.push_back(j);
+		blocks += (uint32_t)((n + 255) / 256);
+		vertex += 4 * n;
+	}
+	if (jobs.empty()) return 0;
+	const size_t jobBytes = jobs.size() * sizeof(ShadeJob), lutBytes = luts.size() * sizeof(uint32_t);
+	ctx->shadeBlobD.reserve(jobBytes + lutBytes, 0, ctx->stream);
+	// pageable sources: the copies are staged by the runtime before the calls return
+	SPR_CUDA(cudaMemcpyAsync(ctx->shadeBlobD.ptr, jobs.data(), jobBytes, cudaMemcpyHostToDevice, ctx->stream));
+	SPR_CUDA(cudaMemcpyAsync(ctx->shadeBlobD.ptr + jobBytes, luts.data(), lutBytes, cudaMemcpyHostToDevice, ctx->stream));
+	launch_shade_vertices(ctx->stream, (const float4*)ctx->dVertices, (const ShadeJob*)ctx->shadeBlobD.ptr, (uint32_t)jobs.size(), blocks,
+		(const uint32_t*)(ctx->shadeBlobD.ptr + jobBytes), fog ? (const uint8_t*)fog->deviceTexels : nullptr, fog ? fog->width : 0, fog ? fog->height : 0,
+		(float4*)deviceOut, capacityVertices);
+	ctx->launchCount++;
+	SPR_CUDA(cudaGetLastError());
+	return vertex;
 }
 
 } // namespace spr

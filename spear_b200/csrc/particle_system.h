@@ -119,6 +119,8 @@ struct ParticleSystem {
 	void updateParticles(const uint32_t *activeIds, uint32_t numActive, const SprFrameArgs &args); // :808-822
 	void renderMain(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, SprRenderOutput &out); // :824-903
 
+	// Particle.glsl `vs` over draw records (vertex_stage.cu); returns the number of vertices written
+	uint64_t shadeVertices(const SprDrawRecord *records, uint32_t numRecords, const SprFogImage *fog, SprShadedVertex *deviceOut, uint64_t capacityVertices);
 	void renderMainWith(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, const RenderGather *got, SprRenderOutput &out);
 	void releaseEffectTypeImp(uint32_t typeId);                        // :682-692
 };
@@ -219,6 +221,7 @@ struct Context {
 
 	// ---- sort scratch
 	DeviceArray<uint32_t> dSortHist, dSortLookback;
+	DeviceArray<uint8_t> shadeBlobD;      // job table + LUT table of the last sprShadeVertices
 	DeviceArray<uint64_t> dRunOffsets;
 	DeviceArray<uint32_t> packListD;      // effect list of the last sprRunBufferPack (device)
 	std::vector<uint32_t> packList;       // ... and its host copy

@@ -26,7 +26,7 @@ EXPORTS = [
     "sprGetEffectTypeUbo", "sprGetEffectDeviceView", "sprPackRuns", "sprExpandRuns",
     "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType", "sprRenderMainBatch", "sprContextGetTotals",
     "sprRunBufferCreate", "sprRunBufferDestroy", "sprRunBufferGetIpcHandle", "sprRunBufferOpenPeer", "sprRunBufferClosePeer",
-    "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers",
+    "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers", "sprShadeVertices",
 ]
 
 
@@ -80,6 +80,7 @@ def _load():
     lib.sprRunBufferDevicePtr.argtypes = [vp]
     lib.sprRunBufferPack.argtypes = [vp, P(vp), P(u32), u32, vp]
     lib.sprExpandFromPeers.argtypes = [vp, P(vp), u32, u32, vp, u64, vp]
+    lib.sprShadeVertices.argtypes = [vp, P(abi.DrawRecord), u32, P(abi.FogImage), vp, u64, P(u64)]
     lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
     lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
     return lib
@@ -308,6 +309,15 @@ class ParticleSystem:
             recs.append(r)
         self.last_device_vertices = out.deviceVertices
         return recs, out.numSortedEffects
+
+    def shade_vertices(self, records, device_out, capacity_vertices, fog=None):
+        """Particle.glsl `vs` over draw records (sprShadeVertices); device_out is a device pointer with room for
+        capacity_vertices SprShadedVertex. Returns the number of vertices written (stream-ordered, not synchronised)."""
+        n = len(records)
+        arr = (abi.DrawRecord * max(n, 1))(*records)
+        total = C.c_uint64(0)
+        _check(lib.sprShadeVertices(self.h, arr, n, C.byref(fog) if fog is not None else None, device_out, capacity_vertices, C.byref(total)))
+        return total.value
 
     def effect_info(self, effect_id):
         info = abi.EffectInfo()

@@ -1,0 +1,111 @@
+"""CPU: known answers for oracle/vertex_stage.py (the numpy restatement of Particle.glsl `vs`,
+src/game/shader/Particle.glsl:73-140). The reference has no CPU code or golden vectors for its
+vertex stage, so these hand-computed cases are what the restatement is checked against."""
+import numpy as np
+
+from oracle import vertex_stage as VS
+
+F = np.float32
+IDENT = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+
+
+def _instance(inv_delta=0.0, aspect=0.5, p2w=IDENT, w2c=IDENT, fog_mad=(0, 0, 0, 0)):
+    return np.array(list(p2w) + list(w2c) + list(fog_mad) + [inv_delta, aspect, 0, 0], dtype=F)
+
+
+def _type(frame_count=(1, 1), frame_rate=0.0, rot=(0, 0, 0, 0), start_frame=0.0, scale=(2.0, 0.0), life=(4.0, 0.0), rel=0.0):
+    t = np.zeros(24, dtype=F)
+    t[0:2] = frame_count; t[2] = frame_rate; t[4:8] = rot; t[9] = start_frame
+    t[16:18] = scale; t[18:20] = life; t[20] = rel
+    return t
+
+
+def _lut(spline=(255, 255, 255, 255), grad=(255, 255, 255, 0)):
+    lut = np.zeros((2, 64, 4), dtype=np.uint8)
+    lut[0, :] = spline
+    lut[1, :] = grad
+    return lut.reshape(-1)
+
+
+def _particle(pos=(1, 2, 3), life=0.5, vel=(0, 0, 0), seed=0.0):
+    return np.array([list(pos) + [life] + list(vel) + [seed]], dtype=F)
+
+
+def test_corners_and_clip_position():
+    # rotation 0: axisX = (1, 0), axisY = (0, -1); scale 2 -> corner offsets (+-2, +-2) * (0.5 * aspect, 0.5)
+    out = VS.shade(_particle(), _instance(aspect=0.5), _type(), _lut())
+    assert out.shape == (4, 16)
+    want_xy = [(1 - 0.5, 2 + 1), (1 + 0.5, 2 + 1), (1 - 0.5, 2 - 1), (1 + 0.5, 2 - 1)]  # corners (u, v) = (0,0) (1,0) (0,1) (1,1)
+    for c in range(4):
+        assert tuple(out[c, 0:2]) == want_xy[c]
+        assert tuple(out[c, 2:4]) == (3.0, 1.0)
+        assert tuple(out[c, 8:12]) == (1.0, 1.0, 1.0, 1.0)       # white gradient, alpha = spline.y = 1
+        assert tuple(out[c, 12:16]) == (0.0, 1.0, 1.0, 0.0)      # frameD, spline.z, erode (spline.w = 1 -> 1), 0
+
+
+def test_dead_quad_collapses():
+    # lifeLeft = life + invDelta / total <= 0 -> gl_Position = 0 (Particle.glsl:113-115)
+    out = VS.shade(_particle(life=-0.25), _instance(inv_delta=1.0), _type(life=(4.0, 0.0)), _lut())
+    assert np.all(out[:, 0:4] == 0.0)
+    out = VS.shade(_particle(life=-0.2), _instance(inv_delta=1.0), _type(life=(4.0, 0.0)), _lut())
+    assert np.all(out[:, 3] == 1.0)  # -0.2 + 0.25 > 0: alive
+
+
+def test_back_extrapolation_and_particle_to_world():
+    # world = M * p with a translation (5, 0, 0); position -= velocity * invDelta (:89); velocity ignores translation
+    m = list(IDENT); m[12] = 5.0
+    out = VS.shade(_particle(pos=(1, 2, 3), vel=(2, 0, -4)), _instance(inv_delta=0.5, p2w=m), _type(scale=(0.0, 0.0)), _lut())
+    assert tuple(out[0, 0:4]) == (1 + 5 - 1.0, 2.0, 3 + 2.0, 1.0)
+
+
+def test_seed_unpack_drives_scale_and_rotation():
+    seed = 1 + 64 * 2 + 4096 * 3 + 262144 * 4   # four 6-bit fields (:87): s = (1, 2, 3, 4) / 64
+    t = _type(scale=(1.0, 64.0), rot=(0.0, 0.0, 0.0, 0.0))
+    out = VS.shade(_particle(seed=float(seed)), _instance(aspect=1.0), t, _lut())
+    # scale = 1 + (1/64) * 64 = 2 -> x offset of corner 1 = +2 * 0.5
+    assert out[1, 0] - out[0, 0] == 2.0
+    # rotation = base + variance * (s.z * 2 - 1) with s.z = 3/64, lifeTime-independent part only
+    t = _type(scale=(2.0, 0.0), rot=(0.0, np.pi, 0.0, 0.0))
+    out = VS.shade(_particle(seed=float(seed)), _instance(aspect=1.0), t, _lut())
+    rot = F(np.pi) * (F(3 / 64) * F(2) - F(1))
+    ox, oy = F(-2.0), F(-2.0)
+    want = F(1) + (ox * np.cos(rot) + oy * np.sin(rot)) * F(0.5)
+    assert abs(out[0, 0] - want) < 1e-6
+
+
+def test_flipbook_frames():
+    # lifeTime 0.5, total 4 s -> absolute 2 s * 8 fps = frame 16 of a 4 x 2 sheet: (0, 0), next (1, 0)
+    out = VS.shade(_particle(), _instance(), _type(frame_count=(4, 2), frame_rate=8.0), _lut())
+    assert tuple(out[0, 4:8]) == (0.0, 0.0, 0.25, 0.0)
+    assert tuple(out[3, 4:8]) == (0.25, 0.5, 0.5, 0.5)
+    assert out[0, 12] == 0.0
+    # relative frame rate: frame = lifeTime * rate = 0.5 * 5 = 2.5 -> frame 2, blend 0.5
+    out = VS.shade(_particle(), _instance(), _type(frame_count=(4, 2), frame_rate=5.0, rel=1.0), _lut())
+    assert tuple(out[0, 4:8]) == (0.5, 0.0, 0.75, 0.0) and out[0, 12] == 0.5
+
+
+def test_lut_lerp_srgb_and_erosion():
+    lut = np.zeros((2, 64, 4), dtype=np.uint8)
+    lut[0, :, 0] = 255
+    lut[0, :, 1] = np.arange(64) * 4          # alpha ramps 0, 4, 8, ...
+    lut[0, :, 3] = 51                          # erosion 0.2 -> erode = 5
+    lut[1, :, 0] = 128                         # sRGB 128 -> linear 0.2158605
+    lut[1, :, 1] = 255
+    # lifeTime = 0.5 -> texel coordinate 31.5: alpha = lerp(124, 128, 0.5) / 255
+    out = VS.shade(_particle(life=0.5), _instance(), _type(), lut.reshape(-1))
+    assert abs(out[0, 11] - 126 / 255) < 1e-7
+    assert abs(out[0, 8] - 0.2158605) < 1e-6 and out[0, 9] == 1.0 and out[0, 10] == 0.0
+    assert abs(out[0, 14] - 5.0) < 1e-5
+    # the ends of the row clamp: lifeTime >= 1 samples texel 63 exactly
+    out = VS.shade(_particle(life=-1.0), _instance(), _type(), lut.reshape(-1))
+    assert abs(out[0, 11] - 252 / 255) < 1e-7
+
+
+def test_vis_fog():
+    fog = np.zeros((1, 1, 2), dtype=np.uint8)
+    fog[0, 0] = (255, 128)       # visible (t = 1), u = 128 / 255 -> colour * u^2
+    out = VS.shade(_particle(), _instance(fog_mad=(0.1, 0.1, 0.5, 0.5)), _type(), _lut(), fog=fog)
+    assert abs(out[0, 8] - (128 / 255) ** 2) < 1e-6
+    fog[0, 0] = (114, 255)       # 114/255 = 0.447 < 0.45 -> t = 0 -> black
+    out = VS.shade(_particle(), _instance(fog_mad=(0.1, 0.1, 0.5, 0.5)), _type(), _lut(), fog=fog)
+    assert out[0, 8] == 0.0 and out[0, 11] == 1.0   # alpha is not fogged
