@@ -539,14 +539,22 @@ def run_ours(args, rank, world):
             out["stream_mode"] = "pending"
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(name, seconds=15.0)
+    billboards = None
+    if world == 1 and not args.no_billboards:
+        try:
+            billboards = bench_billboards(ctx)
+        except Exception as ex:  # noqa: BLE001
+            billboards = {"error": str(ex)[:300]}
     if world > 1:
         ctx_b.close()
         dist.destroy_process_group()
     ctx.close()
     if rank == 0:
+        if billboards is not None:
+            out["billboards"] = billboards
         if out.get("stream_mode") == "pending":
             try:
-                cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--no-sort", "--no-cpu-baseline", "--no-stream-mode", "--no-vertex-stage",
+                cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--no-sort", "--no-cpu-baseline", "--no-stream-mode", "--no-vertex-stage", "--no-billboards",
                        "--steps", str(args.steps), "--warmup", str(args.warmup)]
                 r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
                 sm = json.loads(r.stdout.strip().splitlines()[-1])
@@ -556,6 +564,71 @@ def run_ours(args, rank, world):
             except Exception as ex:  # noqa: BLE001
                 out["stream_mode"] = {"error": str(ex)[:200]}
         print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------
+# billboards: one frame of cl::BillboardSystem through the C ABI, N=1 only
+# ---------------------------------------------------------------------------
+
+def bench_billboards(ctx, n=1 << 20, frames=5):
+    """addBillboard x n + renderMain per frame with host buffers in and the host draw list out (so the H2D copy of
+    the frame's billboards and the D2H copy of the atlas list are inside the time), budget = n. The reference's own
+    BillboardSystem.cpp (oracle/_ref) is timed beside it on the same frame when that library is present."""
+    import ctypes as C
+    import numpy as np
+    from spear_b200 import abi, particles
+    from tests_render_args import make_render_args
+    rng = np.random.default_rng(3)
+    arr = np.zeros(n, dtype=np.dtype(abi.Billboard))
+    arr["sprite"]["atlas"] = rng.integers(1, 9, size=n)
+    arr["sprite"]["maxVert"]["x"] = 1.0; arr["sprite"]["maxVert"]["y"] = 1.0
+    arr["sprite"]["vertUvScale"]["x"] = 0.25; arr["sprite"]["vertUvScale"]["y"] = 0.25
+    tr = np.zeros((n, 12), dtype=np.float32)
+    tr[:, 0] = tr[:, 4] = tr[:, 8] = 1.0
+    tr[:, 9:12] = rng.uniform(-50, 50, size=(n, 3))
+    arr["transform"] = tr
+    for k in "xyzw":
+        arr["color"][k] = 1.0
+    arr["depth"] = rng.uniform(0, 100, size=n).astype(np.float32)
+    for f in ("anchor",):
+        arr[f]["x"] = 0.5; arr[f]["y"] = 0.5
+    arr["cropMax"]["x"] = 1.0; arr["cropMax"]["y"] = 1.0
+    ptr = arr.ctypes.data_as(C.POINTER(abi.Billboard))
+    ra = make_render_args()
+    bs = particles.BillboardSystem(ctx, max_billboards_per_frame=n)
+    out = abi.BillboardOutput()
+    times = []
+    launches0 = ctx.launch_count
+    for _ in range(frames + 2):
+        t0 = time.perf_counter()
+        particles._check(particles.lib.sprBillboardAdd(bs.h, ptr, n))
+        particles._check(particles.lib.sprBillboardRenderMain(bs.h, C.byref(ra), C.byref(out)))
+        times.append(time.perf_counter() - t0)
+    quads, draws = out.numQuads, out.numDraws
+    launches = (ctx.launch_count - launches0) // (frames + 2)
+    bs.close()
+    ms = sorted(times[2:])[len(times[2:]) // 2] * 1e3
+    res = {"billboards_per_frame": n, "budget": n, "quads": int(quads), "draws": int(draws), "ms_per_frame": ms,
+           "billboards_per_s": n / (ms * 1e-3), "h2d_bytes_per_frame": int(n * 120), "d2h_bytes_per_frame": int(quads * 8 + 4),
+           "gpu_launches_per_frame": int(launches),
+           "note": "sprBillboardAdd + sprBillboardRenderMain per frame, host arrays in, host draw list out (median of %d frames)" % frames}
+    try:
+        from oracle import billboards as B
+        if B.have_reference():
+            o = B.BillboardOracle()
+            ct = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                o.lib.orc_bb_add(o.h, ptr, n)
+                # the reference cuts the frame at 4096 billboards (:10, :121-123): its sort still runs over all n
+                q = o.lib.orc_bb_render(o.h, C.byref(ra), None, 0, None, 0, None, None)
+                ct.append(time.perf_counter() - t0)
+            o.close()
+            res["cpu_reference"] = {"ms_per_frame": sorted(ct)[1] * 1e3, "quads": int(q), "cores": 1, "kind": "reference",
+                                    "note": "oracle/_ref: the reference's BillboardSystem.cpp on the same frame (sorts all n, expands its budget of 4096)"}
+    except Exception as ex:  # noqa: BLE001
+        res["cpu_reference"] = {"error": str(ex)[:200]}
+    return res
 
 
 # ---------------------------------------------------------------------------
@@ -662,6 +735,7 @@ def main():
     ap.add_argument("--no-sort", action="store_true", help="strict drop-in stream (slot order), no per-particle depth sort")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream-mode", action="store_true", help="skip the extra stream-mode (no sort) measurement at N=1")
+    ap.add_argument("--no-billboards", action="store_true", help="skip the extra cl::BillboardSystem (row N4) measurement at N=1")
     ap.add_argument("--no-vertex-stage", action="store_true", help="skip the extra vertex-stage (sprShadeVertices) measurement at N=1")
     ap.add_argument("--no-kernel-timing", action="store_true", help="no per-launch CUDA events inside the timed region (no roofline object)")
     args = ap.parse_args()

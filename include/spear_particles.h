@@ -450,6 +450,65 @@ typedef struct SprFogImage {
 SPR_API int sprShadeVertices(SprSystem *sys, const SprDrawRecord *records, uint32_t numRecords, const SprFogImage *fog,
 	SprShadedVertex *deviceOut, uint64_t capacityVertices, uint64_t *outNumVertices);
 
+/* ------------------------------------------------------------------------ */
+/* Billboards: cl::BillboardSystem                    */
+/* ------------------------------------------------------------------------ */
+
+typedef struct SprBillboardSystem SprBillboardSystem;
+
+/* The fields of a loaded sp::Sprite that BillboardSystem::renderMain reads (src/sp/Sprite.h:44-57,
+ * src/client/BillboardSystem.cpp:126-143). atlas is an opaque id (the sp::Atlas pointer); 0 = sprite
+ * missing or not loaded: addBillboard drops the billboard (:82, :100). */
+typedef struct SprSprite {
+	uint64_t atlas;
+	SprVec2 minVert, maxVert;
+	SprVec2 vertUvScale, vertUvBias;
+} SprSprite;
+
+/* cl::Billboard (src/client/BillboardSystem.h:9-18). transform is sf::Mat34: column major,
+ * m00 m10 m20 | m01 m11 m21 | m02 m12 m22 | m03 m13 m23 (src/sf/Matrix.h:86-97). */
+typedef struct SprBillboard {
+	SprSprite sprite;
+	float transform[12];
+	SprVec4 color;
+	float depth;
+	SprVec2 anchor, cropMin, cropMax;
+} SprBillboard;
+
+/* BillboardVertex (src/client/BillboardSystem.cpp:53-58), 24 bytes. */
+typedef struct SprBillboardVertex {
+	float position[3];
+	float texCoord[2];
+	uint32_t color;                    /* packColor(), :12-28 */
+} SprBillboardVertex;
+
+/* One sg_draw of renderMain (:198-203, :213-225): `count` quads of one atlas from quad `firstQuad` on. */
+typedef struct SprBillboardDraw {
+	uint64_t atlas;
+	uint32_t count;
+	uint32_t firstQuad;
+} SprBillboardDraw;
+
+typedef struct SprBillboardOutput {
+	const SprBillboardVertex *deviceVertices; /* DEVICE pointer: 4 vertices per quad, sorted (:163-196) */
+	uint32_t numQuads;
+	uint32_t numDraws;
+	const SprBillboardDraw *draws;     /* HOST pointer, valid until the next call on the system */
+	float worldToClip[16];             /* Billboard_Vertex_t (:208-210) */
+} SprBillboardOutput;
+
+/* BillboardSystem::create (src/client/BillboardSystem.h:22). maxBillboardsPerFrame 0 = the reference's 4096 (:10). */
+SPR_API int sprBillboardSystemCreate(SprContext *ctx, uint32_t maxBillboardsPerFrame, SprBillboardSystem **out);
+SPR_API int sprBillboardSystemDestroy(SprBillboardSystem *sys);
+/* addBillboard (:80-117), `count` times in array order; the 4-argument overload of the reference is the
+ * same call with anchor 0.5, crop [0, 1]. Host only: the frame's billboards go to the device in renderMain. */
+SPR_API int sprBillboardAdd(SprBillboardSystem *sys, const SprBillboard *billboards, uint32_t count);
+/* renderMain (:119-228): sort by (depth, insertion index), cut to the frame budget, crop, expand;
+ * clears the frame's billboards. Synchronises the context stream (the draw list is host data). */
+SPR_API int sprBillboardRenderMain(SprBillboardSystem *sys, const SprRenderArgs *args, SprBillboardOutput *out);
+/* Parity read-back: host copy of the vertex buffer of the last renderMain (billboardVertices, :65). */
+SPR_API int sprBillboardReadVertices(SprBillboardSystem *sys, SprBillboardVertex *out, uint32_t capacityQuads, uint32_t *outQuads);
+
 /* Device pointers for zero-copy consumers (benchmarks, the multi-GPU gather). */
 typedef struct SprEffectDeviceView {
 	const SprGpuParticle *vertices;    /* DEVICE: effect's run, 4 vertices per particle */

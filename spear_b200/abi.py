@@ -165,6 +165,48 @@ class FogImage(C.Structure):
     _fields_ = [("deviceTexels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
 
 
+class Sprite(C.Structure):
+    """SprSprite: the sp::Sprite fields cl::BillboardSystem reads."""
+    _fields_ = [("atlas", C.c_uint64), ("minVert", Vec2), ("maxVert", Vec2), ("vertUvScale", Vec2), ("vertUvBias", Vec2)]
+
+
+class Billboard(C.Structure):
+    """SprBillboard = cl::Billboard (src/client/BillboardSystem.h:9-18)."""
+    _fields_ = [("sprite", Sprite), ("transform", C.c_float * 12), ("color", Vec4), ("depth", C.c_float),
+                ("anchor", Vec2), ("cropMin", Vec2), ("cropMax", Vec2)]
+
+
+class BillboardVertex(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("texCoord", C.c_float * 2), ("color", C.c_uint32)]
+
+
+class BillboardDraw(C.Structure):
+    _fields_ = [("atlas", C.c_uint64), ("count", C.c_uint32), ("firstQuad", C.c_uint32)]
+
+
+class BillboardOutput(C.Structure):
+    _fields_ = [("deviceVertices", C.c_void_p), ("numQuads", C.c_uint32), ("numDraws", C.c_uint32),
+                ("draws", C.POINTER(BillboardDraw)), ("worldToClip", C.c_float * 16)]
+
+
+BILLBOARD_VERTEX_DTYPE = [("position", "<f4", 3), ("texCoord", "<f4", 2), ("color", "<u4")]
+
+
+def make_billboard(atlas=1, min_vert=(0.0, 0.0), max_vert=(1.0, 1.0), uv_scale=(0.25, 0.25), uv_bias=(0.5, 0.25),
+                   transform=(1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0), color=(1, 1, 1, 1), depth=0.0,
+                   anchor=(0.5, 0.5), crop_min=(0.0, 0.0), crop_max=(1.0, 1.0)):
+    b = Billboard()
+    b.sprite = Sprite(int(atlas), Vec2(*map(float, min_vert)), Vec2(*map(float, max_vert)), Vec2(*map(float, uv_scale)), Vec2(*map(float, uv_bias)))
+    for i, v in enumerate(transform):
+        b.transform[i] = float(v)
+    b.color = Vec4(*map(float, color))
+    b.depth = float(depth)
+    b.anchor = Vec2(*map(float, anchor))
+    b.cropMin = Vec2(*map(float, crop_min))
+    b.cropMax = Vec2(*map(float, crop_max))
+    return b
+
+
 class RenderOutput(C.Structure):
     _fields_ = [("deviceVertices", C.c_void_p), ("records", C.POINTER(DrawRecord)), ("numRecords", C.c_uint32),
                 ("numSortedEffects", C.c_uint32)]

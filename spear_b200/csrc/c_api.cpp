@@ -9,6 +9,7 @@
 
 using namespace spr;
 
+struct SprBillboardSystem { BillboardSystem sys; SprBillboardSystem(Context *c, uint32_t n) : sys(c, n) { } };
 struct SprContext { Context ctx; explicit SprContext(const SprContextDesc &d) : ctx(d) { } };
 struct SprSystem { ParticleSystem sys; SprSystem(Context *c, const SprSystemsDesc &d) : sys(c, d) { } };
 
@@ -317,6 +318,46 @@ SPR_API int sprShadeVertices(SprSystem *sys, const SprDrawRecord *records, uint3
 	return guarded([&] {
 		uint64_t n = sys->sys.shadeVertices(records, numRecords, fog, deviceOut, capacityVertices);
 		if (outNumVertices) *outNumVertices = n;
+	});
+}
+
+SPR_API int sprBillboardSystemCreate(SprContext *ctx, uint32_t maxBillboardsPerFrame, SprBillboardSystem **out)
+{
+	REQUIRE(ctx && out);
+	return guarded([&] { *out = new SprBillboardSystem(&ctx->ctx, maxBillboardsPerFrame); });
+}
+
+SPR_API int sprBillboardSystemDestroy(SprBillboardSystem *sys)
+{
+	REQUIRE(sys);
+	return guarded([&] { cudaSetDevice(sys->sys.ctx->device); cudaStreamSynchronize(sys->sys.ctx->stream); delete sys; });
+}
+
+SPR_API int sprBillboardAdd(SprBillboardSystem *sys, const SprBillboard *billboards, uint32_t count)
+{
+	REQUIRE(sys && (billboards || !count));
+	return guarded([&] { sys->sys.add(billboards, count); });
+}
+
+SPR_API int sprBillboardRenderMain(SprBillboardSystem *sys, const SprRenderArgs *args, SprBillboardOutput *out)
+{
+	REQUIRE(sys && args && out);
+	return guarded([&] { sys->sys.renderMain(*args, *out); });
+}
+
+SPR_API int sprBillboardReadVertices(SprBillboardSystem *sys, SprBillboardVertex *out, uint32_t capacityQuads, uint32_t *outQuads)
+{
+	REQUIRE(sys && (out || !capacityQuads));
+	return guarded([&] {
+		BillboardSystem &b = sys->sys;
+		uint32_t n = (uint32_t)b.atlasH.size();
+		if (outQuads) *outQuads = n;
+		uint32_t m = n < capacityQuads ? n : capacityQuads;
+		if (m) {
+			SPR_CUDA(cudaSetDevice(b.ctx->device));
+			SPR_CUDA(cudaMemcpyAsync(out, b.dVerts.ptr, (size_t)m * 4 * sizeof(SprBillboardVertex), cudaMemcpyDeviceToHost, b.ctx->stream));
+			SPR_CUDA(cudaStreamSynchronize(b.ctx->stream));
+		}
 	});
 }
 

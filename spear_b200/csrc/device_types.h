@@ -172,6 +172,18 @@ struct ShadeJob {
 // Sort tile: `tile`-th 4096-key tile of effect `effect`'s pair segment.
 struct SortTile { uint32_t effect; uint32_t tile; };
 
+// One billboard of the frame (cl::BillboardSystemImp::BillboardImp + its BillboardOrder::depth,
+// src/client/BillboardSystem.cpp:30-51, with the sp::Sprite fields renderMain reads, src/sp/Sprite.h:44-57).
+struct BillboardDev {
+	unsigned long long atlas;   // sprite->atlas (opaque id)
+	float minVert[2], maxVert[2], vertUvScale[2], vertUvBias[2];
+	float transform[12];        // sf::Mat34, column major (src/sf/Matrix.h:86-97)
+	float anchor[2];
+	uint32_t color;             // packColor(), :17-28 (packed on the host at add time, like the reference)
+	float cropMin[2], cropMax[2];
+	float depth;
+};
+
 // Launch-constant pointers for the per-round kernels.
 struct PoolPtrs {
 	float4 *state;            // 2 float4 per slot

@@ -43,6 +43,15 @@ void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numReco
 void launch_shade_vertices(cudaStream_t st, const float4 *vertices, const ShadeJob *jobs, uint32_t numJobs, uint32_t totalBlocks,
 	const uint32_t *luts, const uint8_t *fogTexels, uint32_t fogW, uint32_t fogH, float4 *out, uint64_t capacityVertices);
 
+// billboards.cu: cl::BillboardSystem::renderMain: sort by (depth, index), cut, crop, expand
+struct BillboardScratch {
+	uint32_t *keys[2], *vals[2];     // [n] ping-pong pairs
+	uint32_t *tileHist;              // [256 * ceil(n / 1024)]
+	uint32_t *blockCounts;           // [ceil(min(n, budget) / 256)]
+};
+uint32_t launch_billboards(cudaStream_t st, const BillboardDev *bb, uint32_t n, uint32_t maxPerFrame, const BillboardScratch &scratch,
+	float *verts, unsigned long long *atlasOut, uint32_t *totalOut);
+
 // sort.cu: segmented stable LSD radix sort of the (key, slot) pairs of the listed effects
 // followed by the 4x expansion in sorted order.
 struct SortScratch {

@@ -874,4 +874,101 @@ uint64_t ParticleSystem::shadeVertices(const SprDrawRecord *records, uint32_t nu
 	return vertex;
 }
 
+// ---------------------------------------------------------------------------
+// BillboardSystem
+// ---------------------------------------------------------------------------
+
+BillboardSystem::BillboardSystem(Context *c, uint32_t maxBillboardsPerFrame)
+	: ctx(c), maxPerFrame(maxBillboardsPerFrame ? maxBillboardsPerFrame : 4096)
+{
+}
+
+// packChannel / packColor, BillboardSystem.cpp:12-28: sf::clamp((uint32_t)(f * 255.0f), 0u, 255u). The
+// float -> uint32_t conversion of a negative or huge value is undefined in C++; on x86-64 it is the low 32
+// bits of the 64-bit truncation (cvttss2si), reproduced here so that out-of-range colours pack alike.
+static uint32_t packChannel(float f)
+{
+	float v = f * 255.0f;
+	uint32_t u;
+	if (v >= -9223372036854775808.0f && v < 9223372036854775808.0f) u = (uint32_t)(uint64_t)(int64_t)v;
+	else u = 0; // cvttss2si's "integer indefinite" 0x8000000000000000 -> low word 0 (also NaN)
+	return u > 255u ? 255u : u;
+}
+
+void BillboardSystem::add(const SprBillboard *billboards, uint32_t count)
+{
+	if (pendingCount + count > pendingCapacity) {
+		// the frame's billboards are staged in pinned memory (one DMA in renderMain); nothing is in flight between frames
+		size_t cap = pendingCapacity ? pendingCapacity : 4096;
+		while (cap < pendingCount + count) cap *= 2;
+		BillboardDev *p = nullptr;
+		SPR_CUDA(cudaSetDevice(ctx->device));
+		SPR_CUDA(cudaMallocHost(&p, cap * sizeof(BillboardDev)));
+		if (pendingCount) memcpy(p, pending, pendingCount * sizeof(BillboardDev));
+		if (pending) cudaFreeHost(pending);
+		pending = p; pendingCapacity = cap;
+	}
+	for (uint32_t i = 0; i < count; i++) {
+		const SprBillboard &b = billboards[i];
+		if (!b.sprite.atlas) continue;                                  // !sprite || !sprite->isLoaded(), :82, :100
+		BillboardDev &d = pending[pendingCount++];
+		d.atlas = b.sprite.atlas;
+		d.minVert[0] = b.sprite.minVert.x; d.minVert[1] = b.sprite.minVert.y;
+		d.maxVert[0] = b.sprite.maxVert.x; d.maxVert[1] = b.sprite.maxVert.y;
+		d.vertUvScale[0] = b.sprite.vertUvScale.x; d.vertUvScale[1] = b.sprite.vertUvScale.y;
+		d.vertUvBias[0] = b.sprite.vertUvBias.x; d.vertUvBias[1] = b.sprite.vertUvBias.y;
+		memcpy(d.transform, b.transform, sizeof(d.transform));
+		d.anchor[0] = b.anchor.x; d.anchor[1] = b.anchor.y;
+		d.color = packChannel(b.color.x) | packChannel(b.color.y) << 8 | packChannel(b.color.z) << 16 | packChannel(b.color.w) << 24; // :22-28
+		d.cropMin[0] = b.cropMin.x; d.cropMin[1] = b.cropMin.y;
+		d.cropMax[0] = b.cropMax.x; d.cropMax[1] = b.cropMax.y;
+		d.depth = b.depth;                                              // order.index = billboards.size - 1 = its position here, :95, :115
+	}
+}
+
+void BillboardSystem::renderMain(const SprRenderArgs &args, SprBillboardOutput &out)
+{
+	SPR_CUDA(cudaSetDevice(ctx->device));
+	memset(&out, 0, sizeof(out));
+	memcpy(out.worldToClip, args.worldToClip.v, sizeof(out.worldToClip));   // :208-209
+	draws.clear();
+	atlasH.clear();
+	if (pendingCount > 0xffffffffull) throw std::runtime_error("more than 2^32 billboards in one frame");
+	const uint32_t n = (uint32_t)pendingCount;
+	if (!n) return;
+	cudaStream_t st = ctx->stream;
+	const uint32_t m = n < maxPerFrame ? n : maxPerFrame;
+	const uint32_t numTiles = (n + 1023) / 1024;
+	dBillboards.reserve(n, 0, st);
+	for (int i = 0; i < 2; i++) { dKeys[i].reserve(n, 0, st); dVals[i].reserve(n, 0, st); }
+	dTileHist.reserve((size_t)256 * numTiles, 0, st);
+	dBlockCounts.reserve((m + 255) / 256, 0, st);
+	dTotal.reserve(1, 0, st);
+	dVerts.reserve((size_t)m * 24, 0, st);
+	dAtlas.reserve(m, 0, st);
+	SPR_CUDA(cudaMemcpyAsync(dBillboards.ptr, pending, (size_t)n * sizeof(BillboardDev), cudaMemcpyHostToDevice, st));
+	BillboardScratch sc;
+	sc.keys[0] = dKeys[0].ptr; sc.keys[1] = dKeys[1].ptr; sc.vals[0] = dVals[0].ptr; sc.vals[1] = dVals[1].ptr;
+	sc.tileHist = dTileHist.ptr; sc.blockCounts = dBlockCounts.ptr;
+	ctx->launchCount += launch_billboards(st, dBillboards.ptr, n, maxPerFrame, sc, dVerts.ptr, dAtlas.ptr, dTotal.ptr);
+	SPR_CUDA(cudaGetLastError());
+	uint32_t total = 0;
+	SPR_CUDA(cudaMemcpyAsync(&total, dTotal.ptr, sizeof(total), cudaMemcpyDeviceToHost, st));
+	SPR_CUDA(cudaStreamSynchronize(st));
+	atlasH.resize(total);
+	if (total) {
+		SPR_CUDA(cudaMemcpyAsync(atlasH.data(), dAtlas.ptr, (size_t)total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		SPR_CUDA(cudaStreamSynchronize(st));
+	}
+	for (uint32_t q = 0; q < total; q++) {                              // :198-203
+		if (!draws.empty() && draws.back().atlas == atlasH[q]) draws.back().count++;
+		else draws.push_back({ atlasH[q], 1u, q });
+	}
+	out.deviceVertices = (const SprBillboardVertex*)dVerts.ptr;
+	out.numQuads = total;
+	out.numDraws = (uint32_t)draws.size();
+	out.draws = draws.data();
+	pendingCount = 0;                                                   // :227-228
+}
+
 } // namespace spr

@@ -247,4 +247,23 @@ struct Context {
 	void sync() { SPR_CUDA(cudaStreamSynchronize(stream)); }
 };
 
+// cl::BillboardSystem (src/client/BillboardSystem.{h,cpp}) over billboards.cu: SURVEY.md 8(f) row N4.
+struct BillboardSystem {
+	Context *ctx;
+	uint32_t maxPerFrame;                      // MaxBillboardsPerFrame, BillboardSystem.cpp:10
+	BillboardDev *pending = nullptr;           // billboards + billboardOrder of the frame (:61-62), in pinned host memory
+	size_t pendingCount = 0, pendingCapacity = 0;
+	~BillboardSystem() { if (pending) cudaFreeHost(pending); }
+	std::vector<SprBillboardDraw> draws;       // billboardDraws (:63)
+	std::vector<unsigned long long> atlasH;
+	DeviceArray<BillboardDev> dBillboards;
+	DeviceArray<uint32_t> dKeys[2], dVals[2], dTileHist, dBlockCounts, dTotal;
+	DeviceArray<float> dVerts;                 // billboardVertices (:65): 24 words per quad
+	DeviceArray<unsigned long long> dAtlas;
+
+	BillboardSystem(Context *c, uint32_t maxBillboardsPerFrame);
+	void add(const SprBillboard *billboards, uint32_t count);                 // :80-117
+	void renderMain(const SprRenderArgs &args, SprBillboardOutput &out);      // :119-228
+};
+
 } // namespace spr

@@ -27,6 +27,8 @@ EXPORTS = [
     "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType", "sprRenderMainBatch", "sprContextGetTotals",
     "sprRunBufferCreate", "sprRunBufferDestroy", "sprRunBufferGetIpcHandle", "sprRunBufferOpenPeer", "sprRunBufferClosePeer",
     "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers", "sprShadeVertices",
+    "sprBillboardSystemCreate", "sprBillboardSystemDestroy", "sprBillboardAdd", "sprBillboardRenderMain",
+    "sprBillboardReadVertices",
 ]
 
 
@@ -81,6 +83,11 @@ def _load():
     lib.sprRunBufferPack.argtypes = [vp, P(vp), P(u32), u32, vp]
     lib.sprExpandFromPeers.argtypes = [vp, P(vp), u32, u32, vp, u64, vp]
     lib.sprShadeVertices.argtypes = [vp, P(abi.DrawRecord), u32, P(abi.FogImage), vp, u64, P(u64)]
+    lib.sprBillboardSystemCreate.argtypes = [vp, u32, P(vp)]
+    lib.sprBillboardSystemDestroy.argtypes = [vp]
+    lib.sprBillboardAdd.argtypes = [vp, P(abi.Billboard), u32]
+    lib.sprBillboardRenderMain.argtypes = [vp, P(abi.RenderArgs), P(abi.BillboardOutput)]
+    lib.sprBillboardReadVertices.argtypes = [vp, vp, u32, P(u32)]
     lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
     lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
     return lib
@@ -247,6 +254,37 @@ class ParticleContext:
 
     def expand_runs(self, device_records, num_records, device_vertices_out):
         _check(lib.sprExpandRuns(self.h, device_records, num_records, device_vertices_out))
+
+
+class BillboardSystem:
+    """cl::BillboardSystem over the C ABI (same calls as oracle.orc.BillboardOracle)."""
+
+    def __init__(self, ctx, max_billboards_per_frame=0):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        _check(lib.sprBillboardSystemCreate(ctx.h, max_billboards_per_frame, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib.sprBillboardSystemDestroy(self.h)
+            self.h = None
+
+    def add(self, billboards):
+        n = len(billboards)
+        arr = (abi.Billboard * max(n, 1))(*billboards)
+        _check(lib.sprBillboardAdd(self.h, arr, n))
+
+    def render(self, render_args):
+        """renderMain: returns (vertices [4 * quads] structured array copied from the device, draws [(atlas, count, firstQuad)],
+        worldToClip)."""
+        out = abi.BillboardOutput()
+        _check(lib.sprBillboardRenderMain(self.h, C.byref(render_args), C.byref(out)))
+        verts = np.zeros(4 * out.numQuads, dtype=abi.BILLBOARD_VERTEX_DTYPE)
+        got = C.c_uint32(0)
+        _check(lib.sprBillboardReadVertices(self.h, verts.ctypes.data, out.numQuads, C.byref(got)))
+        assert got.value == out.numQuads
+        draws = [(out.draws[i].atlas, out.draws[i].count, out.draws[i].firstQuad) for i in range(out.numDraws)]
+        return verts, draws, list(out.worldToClip)
 
 
 class ParticleSystem:

@@ -1,0 +1,77 @@
+"""GPU: sprBillboard* (spear_b200/csrc/billboards.cu) against the golden vectors of the
+reference's cl::BillboardSystem and against the oracle on seeded frames: sort order, budget cut, crop, vertex
+bytes and the atlas draw list, all bit-exact."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import billboards as B
+from spear_b200 import abi
+from tests_render_args import make_render_args
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "billboards.json")))
+
+
+def _particles():
+    from spear_b200 import particles
+    return particles
+
+
+def test_billboards_match_golden_vectors():
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 12)
+    bs = P.BillboardSystem(ctx)
+    ra = make_render_args()
+    try:
+        for frame in GOLDEN["frames"]:
+            bs.add(B.random_frame(frame["seed"], frame["n"]))
+            verts, draws, w2c = bs.render(ra)
+            assert len(verts) // 4 == frame["quads"], "n=%d" % frame["n"]
+            assert [list(d) for d in draws] == frame["draws"], "n=%d" % frame["n"]
+            assert hashlib.sha256(verts.tobytes()).hexdigest() == frame["vertices_sha256"], "n=%d" % frame["n"]
+            assert w2c == list(ra.worldToClip.v)
+        verts, draws, _ = bs.render(ra)          # the frame was consumed (:227-228)
+        assert len(verts) == 0 and draws == []
+    finally:
+        bs.close(); ctx.close()
+
+
+@pytest.mark.parametrize("budget", [0, 100, 1 << 20])
+def test_billboards_match_oracle_with_budgets(budget):
+    """The frame budget is MaxBillboardsPerFrame = 4096 in the reference (:10); the port takes it as a parameter."""
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 12)
+    bs = P.BillboardSystem(ctx, max_billboards_per_frame=budget)
+    ra = make_render_args()
+    try:
+        for seed, n in [(21, 1), (22, 33), (23, 1023), (24, 3000), (25, 70000)]:
+            frame = B.random_frame(seed, n)
+            for lo in range(0, n, 7000):          # several addBillboard batches per frame
+                bs.add(frame[lo:lo + 7000])
+            verts, draws, _ = bs.render(ra)
+            pv, pd = B.port_render(frame, max_per_frame=budget or 4096)
+            assert len(verts) == len(pv), "seed %d" % seed
+            assert np.array_equal(verts.view(np.uint8), pv.view(np.uint8)), "seed %d" % seed
+            assert draws == pd
+    finally:
+        bs.close(); ctx.close()
+
+
+def test_billboards_all_equal_depth_keep_insertion_order():
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 12)
+    bs = P.BillboardSystem(ctx, max_billboards_per_frame=1 << 16)
+    try:
+        frame = [abi.make_billboard(atlas=1 + (i % 5), depth=3.5, transform=(1, 0, 0, 0, 1, 0, 0, 0, 1, float(i), 0, 0)) for i in range(5000)]
+        bs.add(frame)
+        verts, draws, _ = bs.render(make_render_args())
+        assert len(verts) == 4 * 5000
+        assert np.array_equal(verts["position"][::4, 0], np.arange(5000, dtype=np.float32) - 0.5)
+        assert [d[0] for d in draws] == [1 + (i % 5) for i in range(5000)]
+    finally:
+        bs.close(); ctx.close()
