@@ -309,6 +309,33 @@ def run_ours(args, rank, world):
     h2d = n_eff * 16 + len(systems) * 16 + n_eff * 4  # ActiveEntry + SystemWork per frame, ids for the gather
     d2h = n_eff * 60                                   # RenderGather per visible effect
 
+    # ---- e2e, strictest reading: the vertex stream itself is copied to (pinned) host memory every step as well,
+    # i.e. the product is used like the reference's CPU path, whose output array lives in host memory before
+    # sg_append_buffer uploads it. A GPU renderer never needs this copy; it is reported, not used as the headline.
+    e2e_host = None
+    if world == 1 and n_alive * 128 < 8e9 and len(all_effects) <= 256:
+        import ctypes as C
+        hostbuf = torch.empty(int(n_alive * 1.02 + 4096) * 128, dtype=torch.uint8, pin_memory=True)
+        cap_vertices = hostbuf.numel() // 32
+        cnt = C.c_uint32(0)
+        hs0 = sim_steps()
+        th0 = time.perf_counter()
+        hsteps = min(args.steps, 3)
+        copied = 0
+        for _ in range(hsteps):
+            step()
+            ctx.render_prepared(batch, ra)
+            off = 0
+            for s_, e_ in all_effects:
+                particles._check(particles.lib.sprReadVertexStream(s_.h, e_, hostbuf.data_ptr() + off * 32, cap_vertices - off, C.byref(cnt)))
+                off += cnt.value
+            copied += off * 32
+        th1 = time.perf_counter()
+        e2e_host = {"value": (sim_steps() - hs0) * per_effect_alive / (th1 - th0), "unit": UNIT, "ms_per_step": (th1 - th0) * 1e3 / hsteps,
+                    "d2h_bytes_per_step": copied // hsteps,
+                    "note": "as e2e, plus sprReadVertexStream of every effect into pinned host memory each step (%d steps)" % hsteps}
+        del hostbuf
+
     # ---- vertex stage: Particle.glsl `vs` over the draw records of the last frame, N=1 only.
     # 32 B read + 4 x 64 B written per particle; timed alone (it is not part of `value`).
     vertex_stage = None
@@ -506,7 +533,8 @@ def run_ours(args, rank, world):
             "e2e": {"value": e2e_particle_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "note": "sprUpdateParticlesBatch + sprRenderMainBatch per step through the C ABI with host id lists in and host draw records out; "
-                            "the vertex stream stays in HBM where the renderer reads it (the reference uploads it with sg_append_buffer)"},
+                            "the vertex stream stays in HBM where the renderer reads it (the reference uploads it with sg_append_buffer)",
+                    "with_vertex_stream_to_host": e2e_host},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": roof,
