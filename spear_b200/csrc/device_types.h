@@ -208,6 +208,7 @@ struct TablePtrs {
 	PlanRec *plans;
 	RoundConsts *roundConsts; // per effect, rewritten every sub-step round by k_emit_warp
 	uint32_t *effectAnyDead;  // per effect: some slot was freed in this round (lets k_dead_append skip its scan)
+	unsigned long long *slotMirror; // per effect, in mapped host memory: frame stamp << 32 | slot count after the frame
 };
 
 } // namespace spr

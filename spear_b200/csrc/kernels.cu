@@ -1047,7 +1047,7 @@ __global__ void __launch_bounds__(256) k_expand_stream(PoolPtrs pool, TablePtrs 
 }
 
 // prevEmitterToWorld = emitterToWorld after the frame's sub-steps (:668)
-__global__ void k_finalize(TablePtrs tab, const ActiveEntry *active, uint32_t numActive)
+__global__ void k_finalize(TablePtrs tab, const ActiveEntry *active, uint32_t numActive, uint32_t stamp)
 {
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t a = t >> 4, i = t & 15;
@@ -1055,6 +1055,11 @@ __global__ void k_finalize(TablePtrs tab, const ActiveEntry *active, uint32_t nu
 	ActiveEntry ae = active[a];
 	if (ae.numSubsteps == 0) return;
 	tab.state[ae.effect].prevEmitterToWorld[i] = tab.params[ae.effect].emitterToWorld[i];
+	// the exact slot count after this frame, for the host's capacity bound (read there without synchronising)
+	if (i == 0) {
+		const EffectState &S = tab.state[ae.effect];
+		tab.slotMirror[ae.effect] = (unsigned long long)stamp << 32 | S.slotCount[S.parity];
+	}
 }
 
 // ---------------------------------------------------------------------------
@@ -1315,10 +1320,10 @@ void launch_expand_stream(cudaStream_t st, const PoolPtrs &pool, const TablePtrs
 	k_expand_stream<<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp);
 }
 
-void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive)
+void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t stamp)
 {
 	if (!numActive) return;
-	k_finalize<<<div_up((uint64_t)numActive * 16, 256), 256, 0, st>>>(tab, active, numActive);
+	k_finalize<<<div_up((uint64_t)numActive * 16, 256), 256, 0, st>>>(tab, active, numActive, stamp);
 }
 
 void launch_gather_render(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, RenderGather *out)

@@ -62,6 +62,7 @@ Context::~Context()
 	cudaFree(dKeys[0]); cudaFree(dKeys[1]); cudaFree(dVals[0]); cudaFree(dVals[1]);
 	cudaFree(dAliveMask); cudaFree(dDeadMask); cudaFree(dWordAliveBase);
 	cudaFree(dGranuleOwner); cudaFree(dTileStatus[0]); cudaFree(dTileStatus[1]);
+	if (slotMirror) cudaFreeHost(slotMirror);
 	cudaEventDestroy(stagingEvent[0]); cudaEventDestroy(stagingEvent[1]);
 	if (ownStream) cudaStreamDestroy(stream);
 }
@@ -84,6 +85,7 @@ TablePtrs Context::tablePtrs()
 	t.plans = dPlans.ptr;
 	t.roundConsts = dRoundConsts.ptr;
 	t.effectAnyDead = dEffectAnyDead.ptr;
+	t.slotMirror = slotMirror; // unified addressing: the pinned allocation is reachable from the device under the same pointer
 	return t;
 }
 
@@ -164,9 +166,26 @@ uint32_t Context::allocEffectGlobal()
 		dState.reserve(numEffectGlobals, keep, stream);
 		dRoundConsts.reserve(numEffectGlobals, keep, stream);
 		dEffectAnyDead.reserve(numEffectGlobals, keep, stream);
+		ensureSlotMirror(numEffectGlobals);
 	}
 	effectLive[g] = 1;
 	return g;
+}
+
+void Context::ensureSlotMirror(size_t numEffects)
+{
+	if (numEffects <= slotMirrorCapacity) return;
+	size_t cap = slotMirrorCapacity ? slotMirrorCapacity * 2 : 1024;
+	while (cap < numEffects) cap *= 2;
+	unsigned long long *p = nullptr;
+	SPR_CUDA(cudaHostAlloc(&p, cap * sizeof(unsigned long long), cudaHostAllocMapped));
+	memset(p, 0, cap * sizeof(unsigned long long));
+	if (slotMirror) {
+		SPR_CUDA(cudaStreamSynchronize(stream)); // frames in flight still write the old array
+		memcpy(p, slotMirror, slotMirrorCapacity * sizeof(unsigned long long));
+		cudaFreeHost(slotMirror);
+	}
+	slotMirror = p; slotMirrorCapacity = cap;
 }
 
 void Context::markParamsDirty(uint32_t g)
@@ -290,6 +309,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	std::vector<Resolve> resolve;
 	std::vector<uint32_t> resolveGlobals;
 	uint32_t numPlans = 0, maxSub = 0, burstBlocks = 0;
+	const uint32_t thisStamp = frameStamp + 1; // the stamp this frame gets if it simulates anything
 	float camera[3] = { 0, 0, 0 };
 	for (uint32_t r = 0; r < numReqs; r++) {
 		ParticleSystem *sys = reqs[r].system;
@@ -311,6 +331,25 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				uint32_t burst = E.firstEmit ? type.comp->burstAmount : 0;
 				// <= 20 timer spawns per sub-step (:478), each sub-step rounds up to one Particle4
 				uint64_t add = (uint64_t)nsub * (kMaxTimerSpawns + 3) + burst + 3;
+				{
+					// re-base the bound on the newest exact count the device has mirrored (no synchronisation: an older
+					// entry only means more allowances are added on top of it)
+					const unsigned long long m = ((volatile const unsigned long long*)slotMirror)[E.global];
+					const uint32_t mStamp = (uint32_t)(m >> 32);
+					if (mStamp > E.createdStamp && mStamp >= E.evictedStamp) {
+						uint64_t tight = (uint32_t)m;
+						for (uint32_t k = 0; k < E.recentCount; k++) if (E.recent[k].stamp > mStamp) tight += E.recent[k].add;
+						if (tight < E.slotUpperBound) E.slotUpperBound = (uint32_t)tight;
+					}
+					if (E.recentCount == 4) {
+						E.evictedStamp = E.recent[0].stamp;
+						E.recent[0] = E.recent[1]; E.recent[1] = E.recent[2]; E.recent[2] = E.recent[3];
+						E.recentCount = 3;
+					}
+					E.recent[E.recentCount].stamp = thisStamp;
+					E.recent[E.recentCount].add = add > 0xffffffffull ? 0xffffffffu : (uint32_t)add;
+					E.recentCount++;
+				}
 				uint64_t need = (uint64_t)E.slotUpperBound + add;
 				if (need > hParams[E.global].slotCapacity) {
 					if (E.simSteps == 0) { growEffect(E.global, pow2ceil(need), false); E.slotUpperBound = (uint32_t)need; ensureOwned(E.global, E.slotUpperBound); }
@@ -344,6 +383,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			uint64_t need = (uint64_t)got[i].slotCount + resolve[i].add;
 			if (need > hParams[E.global].slotCapacity) growEffect(E.global, pow2ceil(need * 2), true);
 			E.slotUpperBound = (uint32_t)need;
+			// the count just read is exact up to the last submitted frame: only this frame's allowance stays pending
+			E.recent[0] = E.recent[E.recentCount - 1];
+			E.recentCount = 1;
+			E.evictedStamp = frameStamp;
 			ensureOwned(E.global, E.slotUpperBound);
 		}
 	}
@@ -471,7 +514,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		}
 	}
 	if (!sortMode && !streamFused) TIMED(kKExpandStream, launch_expand_stream(stream, pool, tab, poolTiles, frameStamp));
-	TIMED(kKFinalize, launch_finalize(stream, tab, dEntries, nEntries));
+	TIMED(kKFinalize, launch_finalize(stream, tab, dEntries, nEntries, frameStamp));
 
 	if (sortMode && !segEffects.empty()) {
 		SortScratch sc;
@@ -634,6 +677,7 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 	E.boundsToWorld = identity34();
 	E.uploadFrameIndex = ctx->maxParticleCacheFrames;
 	E.global = ctx->allocEffectGlobal();
+	E.createdStamp = ctx->frameStamp; // mirror entries up to this frame belong to whoever had the index before
 
 	EffectParams &P = ctx->hParams[E.global];
 	memset(&P, 0, sizeof(P));

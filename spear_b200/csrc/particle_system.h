@@ -77,6 +77,14 @@ struct HostEffect {
 	bool instantDelete = false;
 	uint64_t simSteps = 0;
 	uint32_t slotUpperBound = 0;  // conservative bound of particles.size*4
+	// The device mirrors the exact slot count of every simulated effect to pinned host memory at the end of each
+	// frame (Context::slotMirror). The bound is re-based on the newest mirrored count plus the growth allowance of
+	// the frames submitted after it -- without that it only ever grows and a small long-lived effect would need a
+	// synchronous read-back every few frames.
+	uint32_t createdStamp = 0;    // frame stamp when the effect was added: older mirror entries belong to a previous owner of the index
+	uint32_t evictedStamp = 0;    // newest frame whose allowance is no longer in `recent`
+	struct { uint32_t stamp, add; } recent[4] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } }; // allowances of the last simulated frames
+	uint32_t recentCount = 0;
 	uint64_t uploadFrameIndex = 16;
 	SprMat34 boundsToWorld;       // particlesToWorld at the last simulated step (gpuBounds, :675-677)
 };
@@ -221,6 +229,9 @@ struct Context {
 
 	// ---- sort scratch
 	DeviceArray<uint32_t> dSortHist, dSortLookback;
+	unsigned long long *slotMirror = nullptr; // pinned + mapped, one word per effect: frame stamp << 32 | slot count (written by k_finalize)
+	size_t slotMirrorCapacity = 0;
+	void ensureSlotMirror(size_t numEffects);
 	DeviceArray<uint8_t> shadeBlobD;      // job table + LUT table of the last sprShadeVertices
 	DeviceArray<uint64_t> dRunOffsets;
 	DeviceArray<uint32_t> packListD;      // effect list of the last sprRunBufferPack (device)
