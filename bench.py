@@ -570,7 +570,7 @@ def run_ours(args, rank, world):
     billboards = None
     if world == 1 and not args.no_billboards:
         try:
-            billboards = bench_billboards(ctx)
+            billboards = bench_billboards(ctx, cpu_reference=not args.no_cpu_baseline)
         except Exception as ex:  # noqa: BLE001
             billboards = {"error": str(ex)[:300]}
     if world > 1:
@@ -598,7 +598,7 @@ def run_ours(args, rank, world):
 # billboards: one frame of cl::BillboardSystem through the C ABI, N=1 only
 # ---------------------------------------------------------------------------
 
-def bench_billboards(ctx, n=1 << 20, frames=5):
+def bench_billboards(ctx, n=1 << 20, frames=5, cpu_reference=True):
     """addBillboard x n + renderMain per frame with host buffers in and the host draw list out (so the H2D copy of
     the frame's billboards and the D2H copy of the atlas list are inside the time), budget = n. The reference's own
     BillboardSystem.cpp (oracle/_ref) is timed beside it on the same frame when that library is present."""
@@ -640,7 +640,10 @@ def bench_billboards(ctx, n=1 << 20, frames=5):
            "billboards_per_s": n / (ms * 1e-3), "h2d_bytes_per_frame": int(n * 120), "d2h_bytes_per_frame": int(quads * 8 + 4),
            "gpu_launches_per_frame": int(launches),
            "note": "sprBillboardAdd + sprBillboardRenderMain per frame, host arrays in, host draw list out (median of %d frames)" % frames}
+    if not cpu_reference:
+        return res
     try:
+        # CPU-baseline leg (the one place bench.py may execute oracle/): the reference's own BillboardSystem.cpp
         from oracle import billboards as B
         if B.have_reference():
             o = B.BillboardOracle()
