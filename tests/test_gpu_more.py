@@ -90,6 +90,44 @@ def test_sorted_large_effect(oracle_port):
         ctx.close()
 
 
+@pytest.mark.parametrize("sort", [False, True], ids=["stream", "sorted"])
+def test_effects_above_4gb_of_vertex_stream(oracle_port, sort):
+    """Maximum sizes: an idle 40M-particle effect is registered first, so every effect of the scenario lives
+    above slot 2^26 -- state float4 indices above 2^27, vertex byte offsets above 2^33, i.e. every 32-bit
+    index product in the kernels would overflow. The scenario must still match the oracle bit for bit."""
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=sort, initial_slot_capacity=1 << 12, max_particles_per_frame=1 << 30)
+    try:
+        sc = [s for s in S.scenarios() if s.name == "multi"][0]
+        ballast = abi.make_component(burstAmount=40_000_000, lifeTime=10.0)
+        o = orc.OracleSystem(oracle_port, sc.seed)
+        s = ctx.create_system(sc.seed)
+        assert o.add_effect(ballast) == s.add_effect(ballast) == 0      # never in an active list: it only occupies the range
+        ref = S.run_scenario(o, sc)
+        got = S.run_scenario(s, sc)
+        first = min(e for e in got[0] if e != "rng")
+        assert s.device_view(first).vertexByteOffset >= 1 << 33
+        for f, (a, b) in enumerate(zip(ref, got)):
+            if not sort:
+                S.assert_snapshots_equal(a, b, "high offsets frame %d" % f)
+                continue
+            assert a["rng"] == b["rng"]
+            for e in a:
+                if e == "rng":
+                    continue
+                assert a[e]["info"] == b[e]["info"], "frame %d effect %d" % (f, e)
+                assert np.array_equal(a[e]["free"], b[e]["free"])
+                exp, _ = expected_sorted(a[e]["stream"])
+                assert exp.tobytes() == b[e]["stream"].tobytes(), "frame %d effect %d sorted stream" % (f, e)
+        # the draw records carry the 64-bit offsets
+        from tests_render_args import make_render_args
+        ids = [e for e in got[-1] if e != "rng"]
+        recs, _ = s.render(ids, make_render_args())
+        assert recs and all(r.vertexByteOffset >= 1 << 33 for r in recs)
+    finally:
+        ctx.close()
+
+
 def test_many_systems_one_launch_set(oracle_port):
     """sprUpdateParticlesBatch: 24 independent systems (own RNG each, seed[1] = 2 + i) advance in one
     set of launches and each matches its own oracle instance."""
