@@ -128,6 +128,44 @@ def test_effects_above_4gb_of_vertex_stream(oracle_port, sort):
         ctx.close()
 
 
+def test_sorted_pass_skipping_shapes(oracle_port):
+    """The radix sort runs on key - keyMin and skips passes whose digit is constant: effects built so that 1, 2, 3 and
+    all 4 passes execute (odd counts leave the result in the other ping-pong buffer), checked against the stable
+    sort of the oracle's stream."""
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 12)
+    try:
+        still = dict(drag=0.0, gravity=(0, 0, 0), lifeTime=1e9, spawnTime=1e9, timeStep=1 / 60)
+        comps = [
+            # every particle at the same point: all keys equal, only pass 0 runs (ties -> slot order)
+            abi.make_component(burstAmount=3000, **still),
+            # a thin shell far away: squared distances differ in the low 16 bits only -> 2 passes
+            abi.make_component(burstAmount=5000, emitPosition=dict(boxExtent=(0.002, 0.002, 0.002)), **still),
+            # a box of a few metres seen from 40 m: < 2^24 distinct keys -> 3 passes
+            abi.make_component(burstAmount=20000, emitPosition=dict(boxExtent=(4, 2, 4)), emitVelocity=dict(boxExtent=(1, 1, 1)), **still),
+            # a cloud around the camera: squared distances from ~0 to ~10^5, every exponent -> 4 passes
+            abi.make_component(burstAmount=20000, emitPosition=dict(boxExtent=(400, 300, 400)), **still),
+        ]
+        trs = [abi.make_transform((1, 2, 3)), abi.make_transform((300, 2, 3)), abi.make_transform((1, 2, 3)), abi.make_transform(CAMERA)]
+        sseed = (1, 55, 3, 4)
+        s, o = ctx.create_system(sseed), orc.OracleSystem(oracle_port, sseed)
+        ids = [s.add_effect(c, t) for c, t in zip(comps, trs)]
+        assert ids == [o.add_effect(c, t) for c, t in zip(comps, trs)]
+        for f in range(4):
+            fa = abi.make_frame_args(1 / 55, game_time=f / 55, frame_index=f, camera=CAMERA)
+            s.update(ids, fa); o.update(ids, fa)
+            a, b = S.snapshot(o, ids), S.snapshot(s, ids)
+            assert a["rng"] == b["rng"]
+            for e in ids:
+                assert a[e]["info"] == b[e]["info"], "frame %d effect %d" % (f, e)
+                exp, _ = expected_sorted(a[e]["stream"])
+                assert exp.tobytes() == b[e]["stream"].tobytes(), "frame %d effect %d sorted stream" % (f, e)
+                slots = s.read_stream_slots(e)
+                assert len(slots) == a[e]["info"]["aliveCount"] and len(set(slots.tolist())) == len(slots)
+    finally:
+        ctx.close()
+
+
 def test_many_systems_one_launch_set(oracle_port):
     """sprUpdateParticlesBatch: 24 independent systems (own RNG each, seed[1] = 2 + i) advance in one
     set of launches and each matches its own oracle instance."""
