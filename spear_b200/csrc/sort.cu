@@ -263,14 +263,25 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 }
 
 // One lane per particle: a coalesced read of 32 slot indices, one 256-bit gather of the 32-byte
-// record per lane (L1 bypassed: a record is exactly one sector and is used once, a full-line L1
-// fill would quadruple the traffic), then the record is stored four times (:607-665). The four
-// 256-bit stores of a warp together fill 32 complete 128-byte lines.
+// record per lane, then the record is stored four times (:607-665). The four 256-bit stores of a
+// warp together fill 32 complete 128-byte lines.
+// A plain load that misses makes L2 fetch the whole 128-byte line from DRAM (4 sectors for one 32-byte
+// record: ncu lts__t_sectors_srcunit_tex_op_read = 4 per record, dram__bytes_read = 121 B per record).
+// That is what a small effect wants -- its few MB of state stay in L2 while it is gathered, so the other three
+// records of the line are hits a moment later -- but for an effect much larger than L2 they are evicted before
+// they are asked for. There the L2::64B prefetch-size hint (the smallest PTX offers) halves the DRAM read:
+// 1.21 -> 0.66 GB for 10M records (tools/gather_bench.cu, profiles/r01_gather_microbench.txt).
 __device__ inline void ld_record_cg(const float4 *p, float4 &a, float4 &b)
 {
 	asm("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
+__device__ inline void ld_record_64b(const float4 *p, float4 &a, float4 &b)
+{
+	asm("ld.global.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+static const uint32_t kLargeGatherSlots = 2u << 20; // 64 MB of slot state: beyond this the gather asks for half lines
 __device__ inline void st_record_cs(float4 *p, const float4 &a, const float4 &b)
 {
 	asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -302,8 +313,13 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 		slot[u] = i < count ? vals[i] : 0xffffffffu;
 		if (fromAlt && i < count) pool.vals[segBase + begin + i] = slot[u];
 	}
+	if (tab.state[g].slotCount[tab.state[g].parity] > kLargeGatherSlots) {
 #pragma unroll
-	for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_cg(state + 2ull * slot[u], a[u], b[u]);
+		for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_64b(state + 2ull * slot[u], a[u], b[u]);
+	} else {
+#pragma unroll
+		for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_cg(state + 2ull * slot[u], a[u], b[u]);
+	}
 #pragma unroll
 	for (int u = 0; u < 4; u++) {
 		if (slot[u] == 0xffffffffu) continue;

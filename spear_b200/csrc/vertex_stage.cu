@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(256) k_shade_vertices(const float4 *vertices, 
 
 	// a_PositionLife / a_VelocitySeed of the quad (its four stream records are identical: read the first)
 	const float4 *rec = vertices + 2ull * (J.srcRecord + 4ull * k);
-	const float4 pl = rec[0], vs = rec[1];
+	float4 pl, vs;
+	// one 32-byte record out of every 128-byte line: ask L2 for 64 bytes instead of the whole line
+	asm("ld.global.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(pl.x), "=f"(pl.y), "=f"(pl.z), "=f"(pl.w), "=f"(vs.x), "=f"(vs.y), "=f"(vs.z), "=f"(vs.w) : "l"(rec));
 	const float *M = J.instance;        // u_ParticleToWorld, column major
 	const float *W = J.instance + 16;   // u_WorldToClip
 	const float invDelta = J.instance[36], aspect = J.instance[37];

@@ -19,6 +19,13 @@ __device__ inline void ld32(const float4 *p, float4 &a, float4 &b)
 	if (MODE == 4) { asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w) : "l"(p));
 	                 asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p + 1)); }
 	if (MODE == 5) asm volatile("ld.global.lu.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w),"=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p));
+	// L2 prefetch-size hints (the smallest is 64 B) and eviction priorities
+	if (MODE == 6) asm volatile("ld.global.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w),"=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p));
+	if (MODE == 7) { asm volatile("ld.global.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w) : "l"(p));
+	                 asm volatile("ld.global.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p + 1)); }
+	if (MODE == 8) asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w),"=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p));
+	if (MODE == 9) { asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x),"=f"(a.y),"=f"(a.z),"=f"(a.w) : "l"(p));
+	                 asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x),"=f"(b.y),"=f"(b.z),"=f"(b.w) : "l"(p + 1)); }
 }
 
 template <int MODE, bool WRITE4>
@@ -69,6 +76,8 @@ int main()
 		printf("  gather+4x store : v8 %.3f  cg %.3f  cs %.3f  ldg2x %.3f  nc.noalloc %.3f  lu %.3f ms\n",
 			run<0, true>(state, idx, out, n), run<1, true>(state, idx, out, n), run<2, true>(state, idx, out, n), run<3, true>(state, idx, out, n), run<4, true>(state, idx, out, n), run<5, true>(state, idx, out, n));
 	}
+	printf("  gather+4x store, hints: L2::64B v8 %.3f  L2::64B 2xv4 %.3f  no_allocate+evict_first %.3f  volatile 2xv4 %.3f ms\n",
+		run<6, true>(state, idx, out, n), run<7, true>(state, idx, out, n), run<8, true>(state, idx, out, n), run<9, true>(state, idx, out, n));
 	// sorted (identity) order for reference
 	for (uint32_t i = 0; i < n; i++) h[i] = i;
 	CK(cudaMemcpy(idx, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
