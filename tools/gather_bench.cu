@@ -47,6 +47,58 @@ __global__ void __launch_bounds__(256) k_gather(const float4 *state, const uint3
 	}
 }
 
+// Variant: the gather goes global -> shared memory with cp.async (LDGSTS, 2 x 16 bytes per record, L1 bypassed, L2::64B
+// hint optional), so a thread can have PT records in flight without holding registers for them; each thread then
+// reads its own records back and stores them 4x.
+template <int PT, bool HINT>
+__global__ void __launch_bounds__(256) k_gather_cpasync(const float4 *state, const uint32_t *idx, float4 *out, uint32_t n)
+{
+	extern __shared__ float4 sm[];
+	const uint32_t base = blockIdx.x * 256 * PT;
+#pragma unroll
+	for (int u = 0; u < PT; u++) {
+		uint32_t i = base + u * 256 + threadIdx.x;
+		if (i < n) {
+			const float4 *src = state + 2ull * idx[i];
+			uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm + 2 * (u * 256 + threadIdx.x));
+			if (HINT) {
+				asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+				asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"(dst + 16), "l"(src + 1) : "memory");
+			} else {
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16), "l"(src + 1) : "memory");
+			}
+		}
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+	for (int u = 0; u < PT; u++) {
+		uint32_t i = base + u * 256 + threadIdx.x;
+		if (i >= n) continue;
+		float4 a = sm[2 * (u * 256 + threadIdx.x)], b = sm[2 * (u * 256 + threadIdx.x) + 1];
+		float4 *d = out + 8ull * i;
+		asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(d), "f"(a.x),"f"(a.y),"f"(a.z),"f"(a.w),"f"(b.x),"f"(b.y),"f"(b.z),"f"(b.w) : "memory");
+		asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(d + 2), "f"(a.x),"f"(a.y),"f"(a.z),"f"(a.w),"f"(b.x),"f"(b.y),"f"(b.z),"f"(b.w) : "memory");
+		asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(d + 4), "f"(a.x),"f"(a.y),"f"(a.z),"f"(a.w),"f"(b.x),"f"(b.y),"f"(b.z),"f"(b.w) : "memory");
+		asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(d + 6), "f"(a.x),"f"(a.y),"f"(a.z),"f"(a.w),"f"(b.x),"f"(b.y),"f"(b.z),"f"(b.w) : "memory");
+	}
+}
+
+template <int PT, bool HINT>
+float run_cpasync(const float4 *state, const uint32_t *idx, float4 *out, uint32_t n)
+{
+	const size_t smem = (size_t)256 * PT * 32;
+	cudaFuncSetAttribute(k_gather_cpasync<PT, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	uint32_t grid = (n + 256 * PT - 1) / (256 * PT);
+	for (int i = 0; i < 2; i++) k_gather_cpasync<PT, HINT><<<grid, 256, smem>>>(state, idx, out, n);
+	cudaEventRecord(e0);
+	for (int i = 0; i < 5; i++) k_gather_cpasync<PT, HINT><<<grid, 256, smem>>>(state, idx, out, n);
+	cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+	float ms; cudaEventElapsedTime(&ms, e0, e1); return ms / 5;
+}
+
 template <int MODE, bool W4>
 float run(const float4 *state, const uint32_t *idx, float4 *out, uint32_t n)
 {
@@ -78,6 +130,9 @@ int main()
 	}
 	printf("  gather+4x store, hints: L2::64B v8 %.3f  L2::64B 2xv4 %.3f  no_allocate+evict_first %.3f  volatile 2xv4 %.3f ms\n",
 		run<6, true>(state, idx, out, n), run<7, true>(state, idx, out, n), run<8, true>(state, idx, out, n), run<9, true>(state, idx, out, n));
+	printf("  gather+4x store through cp.async -> smem: PT=4 %.3f (L2::64B %.3f)  PT=8 %.3f (L2::64B %.3f)  PT=16 %.3f (L2::64B %.3f) ms\n",
+		run_cpasync<4, false>(state, idx, out, n), run_cpasync<4, true>(state, idx, out, n), run_cpasync<8, false>(state, idx, out, n), run_cpasync<8, true>(state, idx, out, n),
+		run_cpasync<16, false>(state, idx, out, n), run_cpasync<16, true>(state, idx, out, n));
 	// sorted (identity) order for reference
 	for (uint32_t i = 0; i < n; i++) h[i] = i;
 	CK(cudaMemcpy(idx, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
