@@ -8,7 +8,9 @@
 #include "particle_system.h"
 
 #include <algorithm>
+#include <chrono>
 #include <map>
+#include <stdio.h>
 #include <unordered_map>
 #include <stdlib.h>
 #include <string.h>
@@ -296,6 +298,9 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 {
 	SPR_CUDA(cudaSetDevice(device));
 	const bool sortMode = (flags & SPR_CTX_SORT_PARTICLES) != 0;
+	static const bool hostTiming = getenv("SPR_HOST_TIMING") != nullptr; // debug aid: where a frame's host time goes
+	auto tNow = [] { return std::chrono::steady_clock::now(); };
+	auto t0 = tNow();
 
 	// ---- host pass: sub-step counts (ParticleSystem.cpp:810-820) and capacity bounds
 	size_t totalActive = 0;
@@ -391,6 +396,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		}
 	}
 
+	auto t1 = tNow();
 	// ---- sort-mode work lists
 	std::vector<uint32_t> segEffects;
 	std::vector<SortTile> sortTiles;
@@ -485,6 +491,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 
 	if (numPlans == 0) { SPR_CUDA(cudaGetLastError()); return; }
 
+	auto t2 = tNow();
 	// ---- the frame
 	frameStamp++;
 	dPlans.reserve(numPlans, 0, stream);
@@ -528,6 +535,13 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size(), timingEnabled ? &hooks : nullptr);
 	}
 #undef DPTR
+	if (hostTiming) {
+		auto t3 = tNow();
+		auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() * 1e-3; };
+		static double acc[3]; static int frames;
+		acc[0] += us(t0, t1); acc[1] += us(t1, t2); acc[2] += us(t2, t3);
+		if (++frames % 16 == 0) { fprintf(stderr, "[spr host] per frame: effect pass %.0f us, work lists + staging %.0f us, launches %.0f us\n", acc[0] / 16, acc[1] / 16, acc[2] / 16); acc[0] = acc[1] = acc[2] = 0; }
+	}
 	SPR_CUDA(cudaGetLastError());
 }
 
