@@ -195,39 +195,60 @@ __global__ void __launch_bounds__(128) k_plan(TablePtrs tab, const SystemWork *w
 			spawnTime = T.spawnTime; spawnVar = T.spawnTimeVariance;
 			mulKm1 = T.mulKm1; sumKm1 = T.sumKm1;
 		}
-		const uint32_t n = min(32u, sw.numActive - base);
-		for (uint32_t k = 0; k < n; k++) {
-			if (lane == k) {
-				for (uint32_t s = 0; s < ae.numSubsteps; s++) {
-					PlanRec &rec = tab.plans[ae.planBase + s];
-					uint32_t burst = 0, usePrev = (s == 0) ? 1u : 0u;
-					if (firstEmit) { burst = burstAmount; firstEmit = 0; usePrev = 0; }     // :457-464
-					if (emitOnTimer >= 0.0f) {                                              // :466-471
-						emitOnTimer -= dt;
-						if (emitOnTimer < 0.0f) stopEmit = 1;
-					}
-					const bool stop = stopEmit || hostStop;
-					spawnTimer -= dt;                                                        // :477
-					rec.rngState = rng.state;
-					rec.effect = ae.effect;
-					rec.burst = burst;
-					rec.dt = dt;
-					rec.spawnTimer0 = spawnTimer;
-					rec.flags = usePrev | ((parity & 1u) << 1);
-					if (burst) rng.advance((uint64_t)burst * (K - 1));                       // burst spawns draw first (:480-481)
-					uint32_t timer = 0;
-					int spawnsLeft = (int)kMaxTimerSpawns;
-					while (spawnTimer <= 0.0f && !stop) {                                    // :479-485
-						if (spawnsLeft-- <= 0) break;
-						spawnTimer += spawnTime + spawnVar * rng.nextFloat();
-						rec.timerVals[timer++] = spawnTimer;
-						rng.state = rng.state * mulKm1 + rng.inc * sumKm1;                   // the spawn's own K-1 draws
-					}
-					rec.timer = timer;
-					spawnTimer = sf_max(spawnTimer, 0.0f);                                   // :524
-					parity ^= 1u;
+		// The control loop of one effect (:457-485, :524). `rng` is only touched when something spawns.
+		auto run_effect = [&]() {
+			for (uint32_t s = 0; s < ae.numSubsteps; s++) {
+				PlanRec &rec = tab.plans[ae.planBase + s];
+				uint32_t burst = 0, usePrev = (s == 0) ? 1u : 0u;
+				if (firstEmit) { burst = burstAmount; firstEmit = 0; usePrev = 0; }     // :457-464
+				if (emitOnTimer >= 0.0f) {                                              // :466-471
+					emitOnTimer -= dt;
+					if (emitOnTimer < 0.0f) stopEmit = 1;
 				}
+				const bool stop = stopEmit || hostStop;
+				spawnTimer -= dt;                                                        // :477
+				rec.rngState = rng.state;
+				rec.effect = ae.effect;
+				rec.burst = burst;
+				rec.dt = dt;
+				rec.spawnTimer0 = spawnTimer;
+				rec.flags = usePrev | ((parity & 1u) << 1);
+				if (burst) rng.advance((uint64_t)burst * (K - 1));                       // burst spawns draw first (:480-481)
+				uint32_t timer = 0;
+				int spawnsLeft = (int)kMaxTimerSpawns;
+				while (spawnTimer <= 0.0f && !stop) {                                    // :479-485
+					if (spawnsLeft-- <= 0) break;
+					spawnTimer += spawnTime + spawnVar * rng.nextFloat();
+					rec.timerVals[timer++] = spawnTimer;
+					rng.state = rng.state * mulKm1 + rng.inc * sumKm1;                   // the spawn's own K-1 draws
+				}
+				rec.timer = timer;
+				spawnTimer = sf_max(spawnTimer, 0.0f);                                   // :524
+				parity ^= 1u;
 			}
+		};
+		// Most effects of a frame spawn nothing (the burst is over, the timer has not expired) and then draw nothing:
+		// a dry run of the same conditions on copies of the state tells, and those effects run their loop right away,
+		// all lanes at once (the rngState they record is never read: no spawn uses it). Only the effects that do
+		// spawn take turns on the RNG chain, in list order.
+		bool draws = false;
+		if (have) {
+			float st = spawnTimer, eo = emitOnTimer;
+			uint32_t se = stopEmit, fe = firstEmit;
+			for (uint32_t s = 0; s < ae.numSubsteps && !draws; s++) {
+				if (fe) { fe = 0; if (burstAmount) draws = true; }
+				if (eo >= 0.0f) { eo -= dt; if (eo < 0.0f) se = 1; }
+				st -= dt;
+				if (st <= 0.0f && !(se || hostStop)) draws = true;
+				st = sf_max(st, 0.0f);
+			}
+			if (!draws) run_effect();
+		}
+		uint32_t turn = __ballot_sync(FULL_MASK, draws);
+		while (turn) {
+			const uint32_t k = __ffs(turn) - 1;
+			turn &= turn - 1;
+			if (lane == k) run_effect();
 			rng.state = __shfl_sync(FULL_MASK, rng.state, k);
 		}
 		if (have && ae.numSubsteps) {
