@@ -161,6 +161,7 @@ uint32_t Context::allocEffectGlobal()
 		g = numEffectGlobals++;
 		hParams.resize(numEffectGlobals);
 		ownedSlots.resize(numEffectGlobals, 0);
+		slotCapacityOf.resize(numEffectGlobals, 0);
 		effectLive.resize(numEffectGlobals, 0);
 		dirtyParamsFlag.resize(numEffectGlobals, 0);
 		size_t keep = numEffectGlobals - 1;
@@ -213,6 +214,7 @@ void Context::growEffect(uint32_t g, uint32_t minCapacity, bool copyContents)
 	ownedSlots[g] = 0;
 	P.slotBase = newBase;
 	P.slotCapacity = newCap;
+	slotCapacityOf[g] = newCap;
 	ensureOwned(g, owned);
 	markParamsDirty(g);
 }
@@ -222,10 +224,10 @@ void Context::growEffect(uint32_t g, uint32_t minCapacity, bool copyContents)
 // loads as soon as they know a granule is owned, so owned-but-unused granules would be wasted reads.
 void Context::ensureOwned(uint32_t g, uint32_t slotUpperBound)
 {
-	const EffectParams &P = hParams[g];
 	uint64_t target = ((uint64_t)slotUpperBound + kTileSlots - 1) / kTileSlots * kTileSlots;
-	if (target > P.slotCapacity) target = P.slotCapacity;
-	if (target <= ownedSlots[g]) return;
+	if (target > slotCapacityOf[g]) target = slotCapacityOf[g];
+	if (target <= ownedSlots[g]) return;          // the common case, decided from the two dense per-effect arrays
+	const EffectParams &P = hParams[g];
 	ownerJobs.push_back({ (P.slotBase + ownedSlots[g]) / kGranuleSlots, (uint32_t)(target - ownedSlots[g]) / kGranuleSlots, g, 0 });
 	ownedSlots[g] = (uint32_t)target;
 }
@@ -356,7 +358,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 					E.recentCount++;
 				}
 				uint64_t need = (uint64_t)E.slotUpperBound + add;
-				if (need > hParams[E.global].slotCapacity) {
+				if (need > slotCapacityOf[E.global]) {
 					if (E.simSteps == 0) { growEffect(E.global, pow2ceil(need), false); E.slotUpperBound = (uint32_t)need; ensureOwned(E.global, E.slotUpperBound); }
 					else { resolve.push_back({ &E, (uint32_t)add }); resolveGlobals.push_back(E.global); }
 				} else {
@@ -707,6 +709,7 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 		writeColMajor44(entityToWorld, P.emitterToWorld);
 	}
 	P.slotBase = 0; P.slotCapacity = 0;
+	ctx->slotCapacityOf[E.global] = 0;
 	ctx->growEffect(E.global, pow2ceil((uint64_t)c->burstAmount + 64), false);
 
 	EffectState S;
@@ -754,6 +757,7 @@ void ParticleSystem::remove(uint32_t effectId)
 	if (P.slotCapacity) ctx->freeRange(P.slotBase, P.slotCapacity);
 	if (P.slotCapacity == kGranuleSlots) ctx->numTinyEffects--;
 	P.slotCapacity = 0;
+	ctx->slotCapacityOf[E.global] = 0;
 	ctx->ownedSlots[E.global] = 0;
 	ctx->freeEffectGlobals.push_back(E.global);
 	ctx->effectLive[E.global] = 0;

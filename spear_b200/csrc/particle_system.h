@@ -62,20 +62,17 @@ struct PinnedArray {
 	}
 };
 
-// Host mirror of one effect (ParticleSystemImp::Effect, ParticleSystem.cpp:186-218).
+// Host mirror of one effect (ParticleSystemImp::Effect, ParticleSystem.cpp:186-218). The fields the per-frame
+// pass of Context::update touches come first, so that a frame costs two cache lines per effect, not four.
 struct HostEffect {
-	bool inUse = false;
+	// ---- hot: read / written for every active effect every frame
 	uint32_t typeId = 0;          // system-local
 	uint32_t global = 0;          // context-wide effect index
-	SprVec3 origin = { 0, 0, 0 };
 	float timeDelta = 0.0f;
 	float timeStep = 0.0f;
 	double lastUpdateTime = 0.0;
-	SprMat34 particlesToWorld;
-	bool hostStopEmit = false;
-	bool firstEmit = true;        // host view: no sub-step simulated yet
-	bool instantDelete = false;
 	uint64_t simSteps = 0;
+	uint64_t uploadFrameIndex = 16;
 	uint32_t slotUpperBound = 0;  // conservative bound of particles.size*4
 	// The device mirrors the exact slot count of every simulated effect to pinned host memory at the end of each
 	// frame (Context::slotMirror). The bound is re-based on the newest mirrored count plus the growth allowance of
@@ -83,9 +80,15 @@ struct HostEffect {
 	// synchronous read-back every few frames.
 	uint32_t createdStamp = 0;    // frame stamp when the effect was added: older mirror entries belong to a previous owner of the index
 	uint32_t evictedStamp = 0;    // newest frame whose allowance is no longer in `recent`
-	struct { uint32_t stamp, add; } recent[4] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } }; // allowances of the last simulated frames
 	uint32_t recentCount = 0;
-	uint64_t uploadFrameIndex = 16;
+	struct { uint32_t stamp, add; } recent[4] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } }; // allowances of the last simulated frames
+	bool firstEmit = true;        // host view: no sub-step simulated yet
+	bool inUse = false;
+	bool hostStopEmit = false;
+	bool instantDelete = false;
+	// ---- cold: transforms (render, updateTransform, localSpace bounds)
+	SprVec3 origin = { 0, 0, 0 };
+	SprMat34 particlesToWorld;
 	SprMat34 boundsToWorld;       // particlesToWorld at the last simulated step (gpuBounds, :675-677)
 };
 
@@ -177,6 +180,7 @@ struct Context {
 	DeviceArray<PlanRec> dPlans;
 	std::vector<EffectParams> hParams;    // host copy, indexed by global effect index
 	std::vector<uint32_t> ownedSlots;     // per effect: slots [0, ownedSlots) have their granuleOwner entries set
+	std::vector<uint32_t> slotCapacityOf; // per effect: copy of hParams[g].slotCapacity, dense (the per-frame pass reads only this)
 	std::vector<uint32_t> freeEffectGlobals, freeTypeGlobals, freeSystemGlobals;
 	uint32_t numEffectGlobals = 0, numTypeGlobals = 0, numSystemGlobals = 0;
 
