@@ -405,7 +405,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	if (sortMode) {
 		for (const ActiveEntry &ae : entries) {
 			if (!ae.numSubsteps) continue;
-			if (hParams[ae.effect].slotCapacity == kGranuleSlots) continue; // sorted and expanded inside k_integrate_sort
+			if (slotCapacityOf[ae.effect] == kGranuleSlots) continue; // sorted and expanded inside k_integrate_sort
 			segEffects.push_back(ae.effect);
 		}
 	}
@@ -420,7 +420,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		+ entries.size() * sizeof(ActiveEntry) + work.size() * sizeof(SystemWork) + burstJobs.size() * sizeof(BurstJob)
 		+ segEffects.size() * sizeof(uint32_t);
 	if (sortMode) {
-		for (uint32_t g : segEffects) bound += ((size_t)hParams[g].slotCapacity / kSortTileKeys + 1) * sizeof(SortTile);
+		for (uint32_t g : segEffects) bound += ((size_t)slotCapacityOf[g] / kSortTileKeys + 1) * sizeof(SortTile);
 	}
 	bound += 16 * 16;
 	int par = stagingParity; stagingParity ^= 1;
@@ -460,8 +460,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	size_t oBurst = bw.put(burstJobs.data(), burstJobs.size());
 	if (sortMode) {
 		for (size_t s = 0; s < segEffects.size(); s++) {
-			const EffectParams &P = hParams[segEffects[s]];
-			uint32_t tiles = (P.slotCapacity + kSortTileKeys - 1) / kSortTileKeys;
+			uint32_t tiles = (slotCapacityOf[segEffects[s]] + kSortTileKeys - 1) / kSortTileKeys;
 			for (uint32_t t = 0; t < tiles; t++) sortTiles.push_back({ (uint32_t)s, t });
 		}
 	}
