@@ -421,6 +421,27 @@ SPR_API int sprBakeEffectType(const SprParticleSystemComponent *c, uint32_t type
 	uint8_t outLut[SPR_SPLINE_LUT_BYTES], SprVertexTypeUbo *outUbo);
 
 /* ------------------------------------------------------------------------ */
+/* Descriptors from the reference's on-disk format    */
+/* ------------------------------------------------------------------------ */
+
+typedef struct SprDescriptorSet SprDescriptorSet;
+
+/* Reads effect descriptors from JSON in the format sp::writeJson produces over the reflection table of
+ * sv::ParticleSystemComponent (src/server/ServerStateReflection.cpp:321-363) with the lenient dialect of
+ * loadConfig (src/server/ServerState.cpp:786-796: bare keys, comments, missing / trailing commas): a prefab
+ * ({ components: [ { type: "ParticleSystem", .. }, .. ] }, sv::Prefab, ServerState.h:568-572), one tagged
+ * component, or a bare component object. sp::readJson's rules apply (src/sp/Json.cpp:116-270): absent fields keep
+ * their defaults, unknown keys are ignored, a value of the wrong type or an unknown component type fails the load
+ * (SPR_ERR_INVALID_ARGUMENT, text in sprGetLastError). Host only, no GPU needed. The set owns the descriptors and
+ * their arrays; their addresses are stable, so they can be passed to sprReserveEffectType / sprAddEffect. */
+SPR_API int sprDescriptorsFromJson(const char *json, size_t length, SprDescriptorSet **out);
+SPR_API uint32_t sprDescriptorCount(const SprDescriptorSet *set);
+SPR_API const SprParticleSystemComponent *sprDescriptorGet(const SprDescriptorSet *set, uint32_t index);
+/* sf::Symbol texture of descriptor `index` ("" when absent); SprParticleSystemComponent::texture is its FNV-1a 64 hash. */
+SPR_API const char *sprDescriptorTextureName(const SprDescriptorSet *set, uint32_t index);
+SPR_API void sprDescriptorsFree(SprDescriptorSet *set);
+
+/* ------------------------------------------------------------------------ */
 /* Vertex stage                                       */
 /* ------------------------------------------------------------------------ */
 

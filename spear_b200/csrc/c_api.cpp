@@ -310,6 +310,22 @@ SPR_API int sprGetRngState(SprSystem *sys, uint64_t outStateInc[2])
 	});
 }
 
+SPR_API int sprDescriptorsFromJson(const char *json, size_t length, SprDescriptorSet **out)
+{
+	REQUIRE(json && out);
+	return guarded([&] {
+		std::string error;
+		DescriptorSet *set = descriptorsFromJson(json, length, error);
+		if (!set) throw std::invalid_argument(error);
+		*out = (SprDescriptorSet*)set;
+	});
+}
+
+SPR_API uint32_t sprDescriptorCount(const SprDescriptorSet *set) { return set ? descriptorCount((const DescriptorSet*)set) : 0; }
+SPR_API const SprParticleSystemComponent *sprDescriptorGet(const SprDescriptorSet *set, uint32_t index) { return set ? descriptorGet((const DescriptorSet*)set, index) : nullptr; }
+SPR_API const char *sprDescriptorTextureName(const SprDescriptorSet *set, uint32_t index) { return set ? descriptorTexture((const DescriptorSet*)set, index) : nullptr; }
+SPR_API void sprDescriptorsFree(SprDescriptorSet *set) { if (set) descriptorsFree((DescriptorSet*)set); }
+
 SPR_API int sprShadeVertices(SprSystem *sys, const SprDrawRecord *records, uint32_t numRecords, const SprFogImage *fog,
 	SprShadedVertex *deviceOut, uint64_t capacityVertices, uint64_t *outNumVertices)
 {

@@ -281,4 +281,12 @@ struct BillboardSystem {
 	void renderMain(const SprRenderArgs &args, SprBillboardOutput &out);      // :119-228
 };
 
+// descriptor_json.cpp: effect descriptors from the reference's JSON prefab format
+struct DescriptorSet;
+DescriptorSet *descriptorsFromJson(const char *json, size_t length, std::string &error);
+uint32_t descriptorCount(const DescriptorSet *s);
+const SprParticleSystemComponent *descriptorGet(const DescriptorSet *s, uint32_t i);
+const char *descriptorTexture(const DescriptorSet *s, uint32_t i);
+void descriptorsFree(DescriptorSet *s);
+
 } // namespace spr

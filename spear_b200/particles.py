@@ -29,6 +29,7 @@ EXPORTS = [
     "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers", "sprShadeVertices",
     "sprBillboardSystemCreate", "sprBillboardSystemDestroy", "sprBillboardAdd", "sprBillboardRenderMain",
     "sprBillboardReadVertices",
+    "sprDescriptorsFromJson", "sprDescriptorCount", "sprDescriptorGet", "sprDescriptorTextureName", "sprDescriptorsFree",
 ]
 
 
@@ -88,6 +89,14 @@ def _load():
     lib.sprBillboardAdd.argtypes = [vp, P(abi.Billboard), u32]
     lib.sprBillboardRenderMain.argtypes = [vp, P(abi.RenderArgs), P(abi.BillboardOutput)]
     lib.sprBillboardReadVertices.argtypes = [vp, vp, u32, P(u32)]
+    lib.sprDescriptorsFromJson.argtypes = [C.c_char_p, C.c_size_t, P(vp)]
+    lib.sprDescriptorCount.restype = u32
+    lib.sprDescriptorCount.argtypes = [vp]
+    lib.sprDescriptorGet.restype = P(abi.ParticleSystemComponent)
+    lib.sprDescriptorGet.argtypes = [vp, u32]
+    lib.sprDescriptorTextureName.restype = C.c_char_p
+    lib.sprDescriptorTextureName.argtypes = [vp, u32]
+    lib.sprDescriptorsFree.argtypes = [vp]
     lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
     lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
     return lib
@@ -254,6 +263,38 @@ class ParticleContext:
 
     def expand_runs(self, device_records, num_records, device_vertices_out):
         _check(lib.sprExpandRuns(self.h, device_records, num_records, device_vertices_out))
+
+
+class DescriptorSet:
+    """Effect descriptors read from the reference's JSON prefab format (sprDescriptorsFromJson; host only).
+    The descriptors live as long as this object: keep it while effects created from them exist."""
+
+    def __init__(self, json_text):
+        data = json_text.encode() if isinstance(json_text, str) else bytes(json_text)
+        self.h = C.c_void_p()
+        _check(lib.sprDescriptorsFromJson(data, len(data), C.byref(self.h)))
+
+    def __len__(self):
+        return lib.sprDescriptorCount(self.h)
+
+    def __getitem__(self, i):
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return lib.sprDescriptorGet(self.h, i).contents
+
+    def texture_name(self, i):
+        return lib.sprDescriptorTextureName(self.h, i).decode()
+
+    def close(self):
+        if self.h:
+            lib.sprDescriptorsFree(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BillboardSystem:

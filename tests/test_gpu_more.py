@@ -518,3 +518,34 @@ def test_random_api_sequence(oracle_port, seed, sort):
                     S.assert_snapshots_equal(a, b, "seed %d frame %d" % (seed, frame))
     finally:
         ctx.close()
+
+
+def test_effects_from_json_descriptors(oracle_port):
+    """Row N3 end to end: descriptors loaded from the reference's JSON prefab format drive the C ABI (the loaded
+    descriptor's address is the effect type key) and simulate exactly like the oracle given the same values."""
+    import json as _json
+    P = _particles()
+    text = [c for c in _json.load(open(os.path.join(os.path.dirname(__file__), "golden", "descriptors.json")))["cases"]
+            if c["name"] == "canonical_compact"][0]["json"]
+    ds = P.DescriptorSet(text)
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 12)
+    try:
+        assert len(ds) == 7
+        seed = (1, 321, 3, 4)
+        s, o = ctx.create_system(seed), orc.OracleSystem(oracle_port, seed)
+        ids = []
+        for i in range(len(ds)):
+            tr = abi.make_transform((2.0 * i, 0.5, -1.0 * i))
+            e1, e2 = s.add_effect(ds[i], tr), o.add_effect(ds[i], tr)
+            assert e1 == e2
+            ids.append(e1)
+        assert s.add_effect(ds[0], abi.make_transform((9, 9, 9))) == o.add_effect(ds[0], abi.make_transform((9, 9, 9)))   # same descriptor -> same type
+        ids.append(len(ids))
+        assert s.effect_info(ids[-1]).typeId == s.effect_info(ids[0]).typeId
+        for f in range(25):
+            fa = abi.make_frame_args(0.02, game_time=f * 0.02, frame_index=f, camera=CAMERA)
+            s.update(ids, fa); o.update(ids, fa)
+        S.assert_snapshots_equal(S.snapshot(o, ids), S.snapshot(s, ids), "json descriptors")
+    finally:
+        ctx.close()
+        ds.close()
