@@ -421,6 +421,19 @@ SPR_API int sprBakeEffectType(const SprParticleSystemComponent *c, uint32_t type
 	uint8_t outLut[SPR_SPLINE_LUT_BYTES], SprVertexTypeUbo *outUbo);
 
 /* ------------------------------------------------------------------------ */
+/* Area query                                         */
+/* ------------------------------------------------------------------------ */
+
+/* The effects of `sys` whose sphere area intersects `frustum`: what cl::AreaSystem::queryFrustum
+ * (src/client/AreaSystem.cpp:139-170, sf::Frustum::intersects(Sphere), src/sf/Frustum.h:42-58) returns for the
+ * AreaGroup::ParticleEffect spheres the particle system registers -- centre = the effect's transform position at
+ * addEffect / the last updateTransform, radius = the descriptor's updateRadius (ParticleSystem.cpp:762-763,
+ * :782-783, removed at :801). The ids come back in ascending order (the reference's order is that of its spatial
+ * tree); these are the lists sprUpdateParticles / sprRenderMain take. outCount is the full count even when it
+ * exceeds `capacity`. Synchronises the context stream. */
+SPR_API int sprQueryEffects(SprSystem *sys, const SprFrustum *frustum, uint32_t *outIds, uint32_t capacity, uint32_t *outCount);
+
+/* ------------------------------------------------------------------------ */
 /* Descriptors from the reference's on-disk format    */
 /* ------------------------------------------------------------------------ */
 

@@ -74,15 +74,15 @@ def _compile(args):
 
 def build(force=False, verbose=True):
     targets = [os.path.join(OUT, "libspear_ref.so"), os.path.join(OUT, "libspear_ref_scalar.so"), os.path.join(OUT, "libspear_ref_billboard.so"),
-               os.path.join(OUT, "libspear_ref_json.so"), os.path.join(OUT, "libspear_adapter.so")]
-    srcs = [os.path.join(HERE, "ref_harness.cpp"), os.path.join(HERE, "ref_billboard_harness.cpp"), os.path.join(HERE, "ref_json_harness.cpp"),
+               os.path.join(OUT, "libspear_ref_json.so"), os.path.join(OUT, "libspear_ref_area.so"), os.path.join(OUT, "libspear_adapter.so")]
+    srcs = [os.path.join(HERE, "ref_harness.cpp"), os.path.join(HERE, "ref_billboard_harness.cpp"), os.path.join(HERE, "ref_json_harness.cpp"), os.path.join(HERE, "ref_area_harness.cpp"),
             os.path.join(HERE, "oracle_api.h"),
             os.path.join(HERE, "..", "include", "spear_particles.h"), os.path.abspath(__file__), ADAPTER_SRC]
     prod = os.path.join(PRODUCT_DIR, "libspear_particles.so")
     if os.path.isfile(prod):
         srcs.append(prod)
     else:
-        targets = targets[:4]
+        targets = targets[:5]
     if not force and all(os.path.isfile(t) for t in targets):
         newest = max(os.path.getmtime(s) for s in srcs)
         if all(os.path.getmtime(t) >= newest for t in targets):
@@ -106,7 +106,7 @@ def build(force=False, verbose=True):
         units.append((os.path.join(REF, "src", "client", "Transform.cpp"), True))
         units.append((os.path.join(REF, "src", "sp", "Srgb.cpp"), True))
         units.append((os.path.join(HERE, "ref_harness.cpp"), True))
-        for variant, extra in (("", []), ("_scalar", ["-DSF_FLOAT4_FORCE_SCALAR=1"]), ("_billboard", []), ("_json", []), ("_adapter", ["-DSPR_ADAPTER=1"])):
+        for variant, extra in (("", []), ("_scalar", ["-DSF_FLOAT4_FORCE_SCALAR=1"]), ("_billboard", []), ("_json", []), ("_area", []), ("_adapter", ["-DSPR_ADAPTER=1"])):
             jobs = []
             vunits = list(units)
             if variant == "_billboard":
@@ -119,6 +119,11 @@ def build(force=False, verbose=True):
                 for rel in (("server", "ServerStateReflection.cpp"), ("sp", "Json.cpp"), ("ext", "json_input_impl.cpp"), ("ext", "json_output.cpp")):
                     vunits.append((os.path.join(REF, "src", *rel), True))
                 vunits.append((os.path.join(HERE, "ref_json_harness.cpp"), True))
+            if variant == "_area":
+                # the reference's cl::AreaSystem (src/client/AreaSystem.cpp) behind its own small harness
+                vunits = [u for u in units if not u[0].endswith(("ref_harness.cpp", "BSpline.cpp", "Transform.cpp", "Srgb.cpp"))]
+                vunits.append((os.path.join(REF, "src", "client", "AreaSystem.cpp"), True))
+                vunits.append((os.path.join(HERE, "ref_area_harness.cpp"), True))
             if variant == "_adapter":
                 # the literal drop-in: integration/ParticleSystemB200.cpp (cl::ParticleSystem over the C ABI) instead
                 # of the reference's ParticleSystem.cpp, linked against the product library
@@ -128,7 +133,7 @@ def build(force=False, verbose=True):
             for i, (path, is_cxx) in enumerate(vunits):
                 obj = os.path.join(tmp, "o%s_%d.o" % (variant, i))
                 cc = ["g++"] + CXX_FLAGS if is_cxx else ["gcc"]
-                vis = ["-fvisibility=hidden"] if path.endswith(("ref_harness.cpp", "ref_billboard_harness.cpp", "ref_json_harness.cpp")) else []
+                vis = ["-fvisibility=hidden"] if path.endswith(("ref_harness.cpp", "ref_billboard_harness.cpp", "ref_json_harness.cpp", "ref_area_harness.cpp")) else []
                 jobs.append((cc + BASE_FLAGS + extra + vis + inc + ["-c", path, "-o", obj], obj))
             with concurrent.futures.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
                 objs = list(ex.map(_compile, jobs))

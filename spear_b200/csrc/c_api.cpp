@@ -326,6 +326,15 @@ SPR_API const SprParticleSystemComponent *sprDescriptorGet(const SprDescriptorSe
 SPR_API const char *sprDescriptorTextureName(const SprDescriptorSet *set, uint32_t index) { return set ? descriptorTexture((const DescriptorSet*)set, index) : nullptr; }
 SPR_API void sprDescriptorsFree(SprDescriptorSet *set) { if (set) descriptorsFree((DescriptorSet*)set); }
 
+SPR_API int sprQueryEffects(SprSystem *sys, const SprFrustum *frustum, uint32_t *outIds, uint32_t capacity, uint32_t *outCount)
+{
+	REQUIRE(sys && frustum && (outIds || !capacity));
+	return guarded([&] {
+		uint32_t n = sys->sys.queryEffects(*frustum, outIds, capacity);
+		if (outCount) *outCount = n;
+	});
+}
+
 SPR_API int sprShadeVertices(SprSystem *sys, const SprDrawRecord *records, uint32_t numRecords, const SprFogImage *fog,
 	SprShadedVertex *deviceOut, uint64_t capacityVertices, uint64_t *outNumVertices)
 {

@@ -69,7 +69,10 @@ struct EffectParams {
 	float gravity[3];
 	float emitterToWorld[16]; // column-major 4x4, :200
 	uint32_t hostStopEmit;  // prepareForRemove, :791
-	uint32_t _pad[3];
+	uint32_t effectId;      // system-local id (what the area / visibility lists carry)
+	uint32_t live;          // 0 once the effect is removed
+	uint32_t _pad;
+	float areaSphere[4];    // the effect's sphere area: transform position + updateRadius (:762-763, :782-783)
 };
 
 // Device-owned per-effect state.

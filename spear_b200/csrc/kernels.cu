@@ -22,6 +22,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "device_types.h"
 #include "kernels.h"
@@ -1108,6 +1109,46 @@ __global__ void k_gather_render(TablePtrs tab, const uint32_t *effects, uint32_t
 }
 
 // ---------------------------------------------------------------------------
+// Area query: which effects' sphere areas intersect a frustum
+// (AreaSystem::queryFrustum, src/client/AreaSystem.cpp:139-170, over the spheres the particle system registers,
+// ParticleSystem.cpp:762-763, :782-783; sf::Frustum::intersects(Sphere), src/sf/Frustum.h:42-58)
+// ---------------------------------------------------------------------------
+
+struct FrustumDev { float side[4][4], caps[4][4]; }; // SprFrustum: side[k][j] = component k of plane j
+
+__global__ void __launch_bounds__(256) k_query_frustum(TablePtrs tab, uint32_t numGlobals, uint32_t systemIdx, FrustumDev f,
+	uint32_t *outIds, uint32_t capacity, uint32_t *outCount)
+{
+	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+	bool hit = false;
+	uint32_t id = 0;
+	if (g < numGlobals) {
+		const EffectParams &P = tab.params[g];
+		if (P.live && P.systemIdx == systemIdx) {
+			id = P.effectId;
+			const float ox = P.areaSphere[0], oy = P.areaSphere[1], oz = P.areaSphere[2], r = P.areaSphere[3];
+			hit = true;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				// so = side[3] + r; so += side[0] * o.x; so += side[1] * o.y; so += side[2] * o.z (Frustum.h:44-55), same for caps
+				float so = f.side[3][j] + r, co = f.caps[3][j] + r;
+				so += f.side[0][j] * ox; co += f.caps[0][j] * ox;
+				so += f.side[1][j] * oy; co += f.caps[1][j] * oy;
+				so += f.side[2][j] * oz; co += f.caps[2][j] * oz;
+				hit = hit && (so < co ? so : co) > 0.0f; // so.min(co).allGreaterThanZero(), :57
+			}
+		}
+	}
+	const uint32_t ballot = __ballot_sync(FULL_MASK, hit);
+	if (!ballot) return;
+	uint32_t base = 0;
+	if (lane == 0) base = atomicAdd(outCount, __popc(ballot));
+	base = __shfl_sync(FULL_MASK, base, 0);
+	const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
+	if (hit && pos < capacity) outIds[pos] = id;
+}
+
+// ---------------------------------------------------------------------------
 // Multi-GPU run packing / expansion
 // ---------------------------------------------------------------------------
 
@@ -1345,6 +1386,15 @@ void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *a
 {
 	if (!numActive) return;
 	k_finalize<<<div_up((uint64_t)numActive * 16, 256), 256, 0, st>>>(tab, active, numActive, stamp);
+}
+
+void launch_query_frustum(cudaStream_t st, const TablePtrs &tab, uint32_t numGlobals, uint32_t systemIdx, const float frustum[32],
+	uint32_t *outIds, uint32_t capacity, uint32_t *outCount)
+{
+	if (!numGlobals) return;
+	FrustumDev f;
+	memcpy(&f, frustum, sizeof(f));
+	k_query_frustum<<<div_up(numGlobals, 256), 256, 0, st>>>(tab, numGlobals, systemIdx, f, outIds, capacity, outCount);
 }
 
 void launch_gather_render(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, RenderGather *out)

@@ -30,6 +30,8 @@ uint32_t launch_stream_fused(cudaStream_t st, const PoolPtrs &pool, const TableP
 	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2]);
 void launch_expand_stream(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp);
 void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t stamp);
+void launch_query_frustum(cudaStream_t st, const TablePtrs &tab, uint32_t numGlobals, uint32_t systemIdx, const float frustum[32],
+	uint32_t *outIds, uint32_t capacity, uint32_t *outCount);
 void launch_gather_render(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, RenderGather *out);
 void launch_run_offsets(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, uint64_t *offsets, uint32_t *counts);
 void launch_pack_runs(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,

@@ -700,6 +700,11 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 	P.systemIdx = systemIdx;
 	P.timeStep = E.timeStep;
 	P.gravity[0] = c->gravity.x; P.gravity[1] = c->gravity.y; P.gravity[2] = c->gravity.z;
+	P.effectId = effectId;
+	P.live = 1;
+	// the sphere area the reference registers with the area system (:762-763)
+	P.areaSphere[0] = transform.position.x; P.areaSphere[1] = transform.position.y; P.areaSphere[2] = transform.position.z;
+	P.areaSphere[3] = c->updateRadius;
 	SprMat34 entityToWorld = transformToMatrix(transform);
 	if (c->localSpace) {                                                  // :755-760
 		writeColMajor44(identity34(), P.emitterToWorld);
@@ -724,13 +729,17 @@ void ParticleSystem::updateTransform(uint32_t effectId, const SprTransformUpdate
 {
 	HostEffect &E = effects[effectId];
 	const HostType &type = types[E.typeId];
+	EffectParams &P = ctx->hParams[E.global];
 	if (type.comp->localSpace) {
 		E.particlesToWorld = update.entityToWorld;
 	} else {
-		writeColMajor44(update.entityToWorld, ctx->hParams[E.global].emitterToWorld);
-		ctx->markParamsDirty(E.global);
+		writeColMajor44(update.entityToWorld, P.emitterToWorld);
 	}
 	E.origin = update.transform.position;
+	// updateSphereArea(areaId, { position, type.updateRadius }), :782-783
+	P.areaSphere[0] = update.transform.position.x; P.areaSphere[1] = update.transform.position.y; P.areaSphere[2] = update.transform.position.z;
+	P.areaSphere[3] = type.comp->updateRadius;
+	ctx->markParamsDirty(E.global);
 }
 
 bool ParticleSystem::prepareForRemove(uint32_t effectId, const SprFrameArgs &args)
@@ -756,6 +765,8 @@ void ParticleSystem::remove(uint32_t effectId)
 	if (P.slotCapacity) ctx->freeRange(P.slotBase, P.slotCapacity);
 	if (P.slotCapacity == kGranuleSlots) ctx->numTinyEffects--;
 	P.slotCapacity = 0;
+	P.live = 0;                       // removeSphereArea, :801
+	ctx->markParamsDirty(E.global);
 	ctx->slotCapacityOf[E.global] = 0;
 	ctx->ownedSlots[E.global] = 0;
 	ctx->freeEffectGlobals.push_back(E.global);
@@ -1030,6 +1041,34 @@ void BillboardSystem::renderMain(const SprRenderArgs &args, SprBillboardOutput &
 	out.numDraws = (uint32_t)draws.size();
 	out.draws = draws.data();
 	pendingCount = 0;                                                   // :227-228
+}
+
+// ---------------------------------------------------------------------------
+// Area query
+// ---------------------------------------------------------------------------
+
+uint32_t ParticleSystem::queryEffects(const SprFrustum &frustum, uint32_t *outIds, uint32_t capacity)
+{
+	SPR_CUDA(cudaSetDevice(ctx->device));
+	if (!ctx->dirtyParams.empty() || !ctx->initStateIdx.empty() || !ctx->typeIdx.empty() || !ctx->systemIdx.empty() || !ctx->ownerJobs.empty()) ctx->flushUploads();
+	const uint32_t n = ctx->numEffectGlobals;
+	if (!n) return 0;
+	ctx->queryD.reserve((size_t)n + 1, 0, ctx->stream);
+	SPR_CUDA(cudaMemsetAsync(ctx->queryD.ptr, 0, sizeof(uint32_t), ctx->stream));
+	launch_query_frustum(ctx->stream, ctx->tablePtrs(), n, systemIdx, &frustum.side[0][0], ctx->queryD.ptr + 1, n, ctx->queryD.ptr);
+	ctx->launchCount++;
+	SPR_CUDA(cudaGetLastError());
+	std::vector<uint32_t> host((size_t)n + 1);
+	SPR_CUDA(cudaMemcpyAsync(host.data(), ctx->queryD.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	SPR_CUDA(cudaStreamSynchronize(ctx->stream));
+	const uint32_t count = host[0];
+	if (count) {
+		SPR_CUDA(cudaMemcpyAsync(host.data() + 1, ctx->queryD.ptr + 1, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		SPR_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	std::sort(host.begin() + 1, host.begin() + 1 + count); // ascending effect id: the defined order of this query
+	for (uint32_t i = 0; i < count && i < capacity; i++) outIds[i] = host[1 + i];
+	return count;
 }
 
 } // namespace spr

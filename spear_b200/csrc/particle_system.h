@@ -130,6 +130,8 @@ struct ParticleSystem {
 	void updateParticles(const uint32_t *activeIds, uint32_t numActive, const SprFrameArgs &args); // :808-822
 	void renderMain(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, SprRenderOutput &out); // :824-903
 
+	// effects whose sphere area intersects the frustum, ascending ids (AreaSystem::queryFrustum over the particle spheres); returns the count
+	uint32_t queryEffects(const SprFrustum &frustum, uint32_t *outIds, uint32_t capacity);
 	// Particle.glsl `vs` over draw records (vertex_stage.cu); returns the number of vertices written
 	uint64_t shadeVertices(const SprDrawRecord *records, uint32_t numRecords, const SprFogImage *fog, SprShadedVertex *deviceOut, uint64_t capacityVertices);
 	void renderMainWith(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, const RenderGather *got, SprRenderOutput &out);
@@ -236,6 +238,7 @@ struct Context {
 	unsigned long long *slotMirror = nullptr; // pinned + mapped, one word per effect: frame stamp << 32 | slot count (written by k_finalize)
 	size_t slotMirrorCapacity = 0;
 	void ensureSlotMirror(size_t numEffects);
+	DeviceArray<uint32_t> queryD;         // [count, ids...] of the last sprQueryEffects
 	DeviceArray<uint8_t> shadeBlobD;      // job table + LUT table of the last sprShadeVertices
 	DeviceArray<uint64_t> dRunOffsets;
 	DeviceArray<uint32_t> packListD;      // effect list of the last sprRunBufferPack (device)

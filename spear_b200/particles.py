@@ -30,6 +30,7 @@ EXPORTS = [
     "sprBillboardSystemCreate", "sprBillboardSystemDestroy", "sprBillboardAdd", "sprBillboardRenderMain",
     "sprBillboardReadVertices",
     "sprDescriptorsFromJson", "sprDescriptorCount", "sprDescriptorGet", "sprDescriptorTextureName", "sprDescriptorsFree",
+    "sprQueryEffects",
 ]
 
 
@@ -97,6 +98,7 @@ def _load():
     lib.sprDescriptorTextureName.restype = C.c_char_p
     lib.sprDescriptorTextureName.argtypes = [vp, u32]
     lib.sprDescriptorsFree.argtypes = [vp]
+    lib.sprQueryEffects.argtypes = [vp, P(abi.Frustum), P(u32), u32, P(u32)]
     lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
     lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
     return lib
@@ -388,6 +390,17 @@ class ParticleSystem:
             recs.append(r)
         self.last_device_vertices = out.deviceVertices
         return recs, out.numSortedEffects
+
+    def query_effects(self, frustum, capacity=None):
+        """Ids of the effects whose sphere area intersects `frustum`, ascending (sprQueryEffects =
+        AreaSystem::queryFrustum over the particle spheres, src/client/AreaSystem.cpp:139-170)."""
+        count = C.c_uint32(0)
+        if capacity is None:
+            _check(lib.sprQueryEffects(self.h, C.byref(frustum), None, 0, C.byref(count)))
+            capacity = count.value
+        out = np.zeros(max(capacity, 1), dtype=np.uint32)
+        _check(lib.sprQueryEffects(self.h, C.byref(frustum), out.ctypes.data_as(C.POINTER(C.c_uint32)), capacity, C.byref(count)))
+        return out[:min(count.value, capacity)].copy(), count.value
 
     def shade_vertices(self, records, device_out, capacity_vertices, fog=None):
         """Particle.glsl `vs` over draw records (sprShadeVertices); device_out is a device pointer with room for

@@ -54,3 +54,11 @@ def make_render_args(camera=CAMERA, target=(14.0, 0.0, 14.0)):
     ra.frustum = frustum_from_matrix(list(ra.worldToClip.v))
     ra.visFogWorldMad = abi.Vec4(0.1, 0.2, 0.3, 0.4)
     return ra
+
+
+def area_test_frusta():
+    """Four frusta for the area-query tests (row N5): the bench camera, a top-down view, a near-horizontal view
+    from inside the scene, and a narrow view from far away."""
+    views = [((16.0, 20.0, -30.0), (14.0, 0.0, 14.0)), ((0.5, 80.0, 0.25), (0.0, 0.0, 0.0)),
+             ((-20.0, 2.0, 5.0), (30.0, 1.0, -10.0)), ((150.0, 40.0, 150.0), (0.0, 0.0, 0.0))]
+    return [make_render_args(camera=c, target=t).frustum for c, t in views]
