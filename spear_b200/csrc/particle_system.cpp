@@ -546,19 +546,34 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	SPR_CUDA(cudaGetLastError());
 }
 
-void Context::gatherEffects(const uint32_t *globals, uint32_t n, RenderGather *out)
+uint32_t *Context::gatherIndexBuffer(uint32_t n)
 {
-	if (!n) return;
+	gatherIdxH.reserve(n ? n : 1);
+	return gatherIdxH.ptr;
+}
+
+// Counts + bounds of the n effects whose context-wide indices the caller wrote into gatherIndexBuffer(n): one H2D
+// of the indices, one kernel, one D2H, all through pinned memory. The result stays valid until the next gather.
+const RenderGather *Context::gatherSubmit(uint32_t n)
+{
+	if (!n) return gatherH.ptr;
 	SPR_CUDA(cudaSetDevice(device));
 	if (!dirtyParams.empty() || !initStateIdx.empty() || !typeIdx.empty() || !systemIdx.empty() || !ownerJobs.empty()) flushUploads();
 	gatherIdxD.reserve(n, 0, stream);
 	gatherD.reserve(n, 0, stream);
 	gatherH.reserve(n);
-	SPR_CUDA(cudaMemcpyAsync(gatherIdxD.ptr, globals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+	SPR_CUDA(cudaMemcpyAsync(gatherIdxD.ptr, gatherIdxH.ptr, n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
 	launch_gather_render(stream, tablePtrs(), gatherIdxD.ptr, n, gatherD.ptr); launchCount++;
 	SPR_CUDA(cudaMemcpyAsync(gatherH.ptr, gatherD.ptr, n * sizeof(RenderGather), cudaMemcpyDeviceToHost, stream));
 	SPR_CUDA(cudaStreamSynchronize(stream));
-	memcpy(out, gatherH.ptr, n * sizeof(RenderGather));
+	return gatherH.ptr;
+}
+
+void Context::gatherEffects(const uint32_t *globals, uint32_t n, RenderGather *out)
+{
+	if (!n) return;
+	memcpy(gatherIndexBuffer(n), globals, n * sizeof(uint32_t));
+	memcpy(out, gatherSubmit(n), n * sizeof(RenderGather));
 }
 
 // ---------------------------------------------------------------------------
@@ -781,19 +796,6 @@ void ParticleSystem::updateParticles(const uint32_t *activeIds, uint32_t numActi
 	ctx->update(&req, 1);
 }
 
-namespace {
-struct SortedEffect { // :225-239 (+ the particle count read back from the device, not part of the order)
-	double renderOrder; uint32_t tiebreaker; float depth; uint32_t effectId; uint32_t numParticles;
-	bool operator<(const SortedEffect &rhs) const {
-		if (renderOrder != rhs.renderOrder) return renderOrder < rhs.renderOrder;
-		if (tiebreaker != rhs.tiebreaker) return tiebreaker < rhs.tiebreaker;
-		if (depth != rhs.depth) return depth < rhs.depth;
-		if (effectId != rhs.effectId) return effectId < rhs.effectId;
-		return false;
-	}
-};
-}
-
 SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const HostEffect &E)
 {
 	// :672-677
@@ -810,26 +812,31 @@ SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const H
 
 void ParticleSystem::renderMain(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, SprRenderOutput &out)
 {
-	std::vector<uint32_t> globals(numVisible);
+	uint32_t *globals = ctx->gatherIndexBuffer(numVisible);
 	for (uint32_t i = 0; i < numVisible; i++) globals[i] = effects[visibleIds[i]].global;
-	std::vector<RenderGather> got(numVisible);
-	ctx->gatherEffects(globals.data(), numVisible, got.data());
-	renderMainWith(visibleIds, numVisible, args, got.data(), out);
+	renderMainWith(visibleIds, numVisible, args, ctx->gatherSubmit(numVisible), out);
 }
 
-// renderMain for many systems with ONE device read-back (counts + bounds of every visible effect).
+// renderMain for many systems with ONE device read-back (counts + bounds of every visible effect); the indices go
+// out of and the records come back into pinned memory that the per-system passes read in place.
 void Context::renderBatch(ParticleSystem *const *systems, uint32_t numSystems, const uint32_t *const *visibleIds,
 	const uint32_t *numVisible, const SprRenderArgs *args, size_t argsStride, SprRenderOutput *outs)
 {
-	std::vector<uint32_t> globals;
-	for (uint32_t s = 0; s < numSystems; s++)
-		for (uint32_t i = 0; i < numVisible[s]; i++) globals.push_back(systems[s]->effects[visibleIds[s][i]].global);
-	std::vector<RenderGather> got(globals.size());
-	gatherEffects(globals.data(), (uint32_t)globals.size(), got.data());
+	uint64_t total = 0;
+	for (uint32_t s = 0; s < numSystems; s++) total += numVisible[s];
+	if (total > 0xffffffffull) throw std::runtime_error("renderBatch: more than 2^32 visible effects");
+	uint32_t *globals = gatherIndexBuffer((uint32_t)total);
+	size_t n = 0;
+	for (uint32_t s = 0; s < numSystems; s++) {
+		const std::vector<HostEffect> &effects = systems[s]->effects;
+		const uint32_t *ids = visibleIds[s];
+		for (uint32_t i = 0; i < numVisible[s]; i++) globals[n++] = effects[ids[i]].global;
+	}
+	const RenderGather *got = gatherSubmit((uint32_t)total);
 	size_t off = 0;
 	for (uint32_t s = 0; s < numSystems; s++) {
 		const SprRenderArgs &a = *(const SprRenderArgs*)((const char*)args + argsStride * s);
-		systems[s]->renderMainWith(visibleIds[s], numVisible[s], a, got.data() + off, outs[s]);
+		systems[s]->renderMainWith(visibleIds[s], numVisible[s], a, got + off, outs[s]);
 		off += numVisible[s];
 	}
 }
@@ -840,7 +847,8 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 	bufferFrameIndex++;                                                   // :831
 	const uint64_t frame = bufferFrameIndex;
 
-	std::vector<SortedEffect> sorted;
+	std::vector<SortedEffect> &sorted = sortedScratch;
+	sorted.clear();
 	sorted.reserve(numVisible);
 	for (uint32_t i = 0; i < numVisible; i++) {                           // :835-846
 		uint32_t effectId = visibleIds[i];
@@ -861,31 +869,30 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 	std::sort(sorted.begin(), sorted.end());                              // :848 (strict total order)
 
 	drawRecords.clear();
-	uint32_t prevTypeId = ~0u;
+	drawRecords.resize(sorted.size());                                    // value-initialised: every record starts zeroed
+	uint32_t prevTypeId = ~0u, numRecords = 0;
+	const float aspect = args.viewToClip.v[0] / args.viewToClip.v[5];
 	for (const SortedEffect &s : sorted) {                                // :851-902
 		HostEffect &E = effects[s.effectId];
-		const HostType &type = types[E.typeId];
 		uint32_t numParticles = s.numParticles;
 		if (frame - E.uploadFrameIndex >= ctx->maxParticleCacheFrames) {  // :861-867
 			if (numParticles >= frameParticlesLeft) break;               // `return`, :862
 			frameParticlesLeft -= numParticles;
 			E.uploadFrameIndex = frame;
 		}
-		SprDrawRecord r;
-		memset(&r, 0, sizeof(r));
+		SprDrawRecord &r = drawRecords[numRecords++];                     // filled in place
 		r.effectId = s.effectId;
 		r.typeId = E.typeId;
 		r.numParticles = numParticles;
 		r.vertexByteOffset = (uint64_t)ctx->hParams[E.global].slotBase * 128ull;
 		writeColMajor44(E.particlesToWorld, r.instanceUbo.u_ParticleToWorld); // :871-876
 		memcpy(r.instanceUbo.u_WorldToClip, args.worldToClip.v, sizeof(float) * 16);
-		r.instanceUbo.u_Aspect = args.viewToClip.v[0] / args.viewToClip.v[5];
+		r.instanceUbo.u_Aspect = aspect;
 		r.instanceUbo.u_InvDelta = E.timeStep - E.timeDelta;
 		r.instanceUbo.u_VisFogMad = args.visFogWorldMad;
 		if (E.typeId != prevTypeId) { r.typeUboChanged = 1; prevTypeId = E.typeId; } // :880-883
-		(void)type;
-		drawRecords.push_back(r);
 	}
+	drawRecords.resize(numRecords);
 	out.deviceVertices = (const SprGpuParticle*)ctx->dVertices;
 	out.records = drawRecords.data();
 	out.numRecords = (uint32_t)drawRecords.size();

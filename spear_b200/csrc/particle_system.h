@@ -104,6 +104,17 @@ struct HostType {
 	uint8_t lut[SPR_SPLINE_LUT_BYTES];
 };
 
+struct SortedEffect { // :225-239 (+ the particle count read back from the device, not part of the order)
+	double renderOrder; uint32_t tiebreaker; float depth; uint32_t effectId; uint32_t numParticles;
+	bool operator<(const SortedEffect &rhs) const {
+		if (renderOrder != rhs.renderOrder) return renderOrder < rhs.renderOrder;
+		if (tiebreaker != rhs.tiebreaker) return tiebreaker < rhs.tiebreaker;
+		if (depth != rhs.depth) return depth < rhs.depth;
+		if (effectId != rhs.effectId) return effectId < rhs.effectId;
+		return false;
+	}
+};
+
 struct Context;
 
 struct ParticleSystem {
@@ -117,6 +128,7 @@ struct ParticleSystem {
 	std::unordered_map<const void*, uint32_t> componentToType; // :246
 	uint64_t bufferFrameIndex;                // :263
 	std::vector<SprDrawRecord> drawRecords;
+	std::vector<SortedEffect> sortedScratch;  // renderMain's sort array, kept between frames
 
 	ParticleSystem(Context *ctx, const SprSystemsDesc &desc); // :265-267
 	~ParticleSystem();
@@ -213,6 +225,7 @@ struct Context {
 	cudaEvent_t stagingEvent[2] = { nullptr, nullptr };
 	int stagingParity = 0;
 	PinnedArray<RenderGather> gatherH;
+	PinnedArray<uint32_t> gatherIdxH;
 	DeviceArray<RenderGather> gatherD;
 	DeviceArray<uint32_t> gatherIdxD;
 	int streamFusedCtasPerSm[2] = { 1, 1 };
@@ -259,6 +272,8 @@ struct Context {
 	void flushUploads();
 	void update(const UpdateRequest *reqs, uint32_t numReqs);
 	void gatherEffects(const uint32_t *globals, uint32_t n, RenderGather *out); // synchronous read-back
+	uint32_t *gatherIndexBuffer(uint32_t n);           // pinned: the caller writes n context-wide effect indices here ...
+	const RenderGather *gatherSubmit(uint32_t n);      // ... and gets their records back in pinned memory (valid until the next gather)
 	void renderBatch(ParticleSystem *const *systems, uint32_t numSystems, const uint32_t *const *visibleIds,
 		const uint32_t *numVisible, const SprRenderArgs *args, size_t argsStride, SprRenderOutput *outs);
 	void growEffect(uint32_t g, uint32_t minCapacity, bool copyContents);
