@@ -26,6 +26,7 @@
 
 #include "device_types.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace spr {
 
@@ -139,6 +140,7 @@ __device__ inline uint32_t enc_float(float f) { uint32_t u = __float_as_uint(f);
 
 __global__ void k_fill_jobs(uint32_t *dst, const FillJob *jobs, uint32_t numJobs)
 {
+	pdl_enter();
 	uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
 	for (uint32_t j = warp; j < numJobs; j += numWarps) {
@@ -150,6 +152,7 @@ __global__ void k_fill_jobs(uint32_t *dst, const FillJob *jobs, uint32_t numJobs
 // dst[idx[i]] = src[i] for structs of `words` 32-bit words
 __global__ void k_scatter_words(uint32_t *dst, const uint32_t *idx, const uint32_t *src, uint32_t n, uint32_t words)
 {
+	pdl_enter();
 	uint64_t total = (uint64_t)n * words;
 	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
 		uint32_t i = (uint32_t)(t / words), w = (uint32_t)(t % words);
@@ -170,6 +173,7 @@ __global__ void k_scatter_words(uint32_t *dst, const uint32_t *idx, const uint32
 // its own plan records and state back in parallel.
 __global__ void __launch_bounds__(128) k_plan(TablePtrs tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp)
 {
+	pdl_enter();
 	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (w >= numWork) return;
 	const SystemWork sw = work[w];
@@ -378,6 +382,7 @@ __device__ inline void emit_init_leftover(const EmitCtx &c, const PoolPtrs &pool
 // the wide kernel. Also resets the per-step bounds and handles the empty-effect corner.
 __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
 {
+	pdl_enter();
 	uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (a >= numActive) return;
 	ActiveEntry ae = active[a];
@@ -422,6 +427,7 @@ __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab,
 // One thread per burst spawn, for bursts too large for one warp.
 __global__ void __launch_bounds__(256) k_emit_burst(PoolPtrs pool, TablePtrs tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs)
 {
+	pdl_enter();
 	// find the job of this CTA (jobs are sorted by firstBlock; numJobs is small)
 	uint32_t lo = 0, hi = numJobs;
 	while (hi - lo > 1) {
@@ -555,6 +561,7 @@ template <bool GP, bool TINY, bool KEYS>
 __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round,
 	float camX, float camY, float camZ)
 {
+	pdl_enter();
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t granule = blockIdx.x * 8 + warp;
 	uint32_t g = pool.granuleOwner[granule];
@@ -703,6 +710,7 @@ __device__ inline uint32_t tile_lookback1(unsigned long long *st, uint32_t poolT
 template <bool ALIVE>
 __global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles)
 {
+	pdl_enter();
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t poolTile = blockIdx.x * 4 + (threadIdx.x >> 5);
 	if (poolTile >= numPoolTiles) return;
@@ -863,6 +871,7 @@ __device__ inline void tile_lookback2(unsigned long long *stA, unsigned long lon
 template <bool GP>
 __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles)
 {
+	pdl_enter();
 	extern __shared__ float4 sStageAll[];              // [2][8 warps][256 float4] = 64 KB
 	__shared__ FusedTileMeta sMeta[2];
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1041,6 +1050,7 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 // stores it four times; for a dense population the 32 lanes fill 4 KB of contiguous vertex stream.
 __global__ void __launch_bounds__(256) k_expand_stream(PoolPtrs pool, TablePtrs tab, uint32_t stamp)
 {
+	pdl_enter();
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t granule = blockIdx.x * 8 + warp;
 	uint32_t g = pool.granuleOwner[granule];
@@ -1071,6 +1081,7 @@ __global__ void __launch_bounds__(256) k_expand_stream(PoolPtrs pool, TablePtrs 
 // prevEmitterToWorld = emitterToWorld after the frame's sub-steps (:668)
 __global__ void k_finalize(TablePtrs tab, const ActiveEntry *active, uint32_t numActive, uint32_t stamp)
 {
+	pdl_enter();
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t a = t >> 4, i = t & 15;
 	if (a >= numActive) return;
@@ -1092,6 +1103,7 @@ __device__ inline float dec_float(uint32_t u) { return __uint_as_float((u & 0x80
 
 __global__ void k_gather_render(TablePtrs tab, const uint32_t *effects, uint32_t n, RenderGather *out)
 {
+	pdl_enter();
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const EffectState &S = tab.state[effects[i]];
@@ -1119,6 +1131,7 @@ struct FrustumDev { float side[4][4], caps[4][4]; }; // SprFrustum: side[k][j] =
 __global__ void __launch_bounds__(256) k_query_frustum(TablePtrs tab, uint32_t numGlobals, uint32_t systemIdx, FrustumDev f,
 	uint32_t *outIds, uint32_t capacity, uint32_t *outCount)
 {
+	pdl_enter();
 	const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
 	bool hit = false;
 	uint32_t id = 0;
@@ -1155,6 +1168,7 @@ __global__ void __launch_bounds__(256) k_query_frustum(TablePtrs tab, uint32_t n
 // offsets[i] = sum of aliveCount of effects[0..i), offsets[n] = total (single CTA; n is small)
 __global__ void k_run_offsets(TablePtrs tab, const uint32_t *effects, uint32_t n, uint64_t *offsets, uint32_t *counts)
 {
+	pdl_enter();
 	__shared__ uint64_t sWarp[32];
 	__shared__ uint64_t sCarry;
 	if (threadIdx.x == 0) sCarry = 0;
@@ -1182,6 +1196,7 @@ __global__ void k_run_offsets(TablePtrs tab, const uint32_t *effects, uint32_t n
 __global__ void __launch_bounds__(256) k_pack_runs(PoolPtrs pool, TablePtrs tab, const uint32_t *effects, uint32_t n,
 	const uint64_t *offsets, float4 *out, uint64_t capacityRecords)
 {
+	pdl_enter();
 	uint64_t total = offsets[n];
 	if (total > capacityRecords) total = capacityRecords;
 	uint64_t totalQ = total * 2;
@@ -1198,6 +1213,7 @@ __global__ void __launch_bounds__(256) k_pack_runs(PoolPtrs pool, TablePtrs tab,
 // 4x expansion of gathered 32-byte records into the vertex layout (:611-665)
 __global__ void __launch_bounds__(256) k_expand_runs(const float4 *records, uint64_t numRecords, float4 *out)
 {
+	pdl_enter();
 	uint64_t totalQ = numRecords * 8;
 	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < totalQ; q += (uint64_t)gridDim.x * blockDim.x) {
 		out[q] = records[((q >> 3) << 1) | (q & 1u)];
@@ -1210,6 +1226,7 @@ __global__ void __launch_bounds__(256) k_expand_runs(const float4 *records, uint
 __global__ void __launch_bounds__(256) k_pack_runs_buf(PoolPtrs pool, TablePtrs tab, const uint32_t *effects, uint32_t n,
 	const uint64_t *offsets, float4 *buf, uint64_t capacityRecords)
 {
+	pdl_enter();
 	uint64_t total = offsets[n];
 	if (total > capacityRecords) total = capacityRecords;
 	if (blockIdx.x == 0 && threadIdx.x == 0) ((unsigned long long*)buf)[0] = total;
@@ -1232,6 +1249,7 @@ __global__ void __launch_bounds__(256) k_pack_runs_buf(PoolPtrs pool, TablePtrs 
 struct PeerRuns { const float4 *buf[16]; uint32_t numRanks; uint32_t myRank; };
 __global__ void __launch_bounds__(256) k_expand_from_peers(PeerRuns runs, float4 *out, uint64_t capacityRecords, unsigned long long *totalOut)
 {
+	pdl_enter();
 	__shared__ unsigned long long sOffset[17];
 	__shared__ unsigned long long sMaxChunks;
 	if (threadIdx.x == 0) {
@@ -1293,7 +1311,7 @@ void launch_fill_jobs(cudaStream_t st, uint32_t *dst, const FillJob *jobs, uint3
 	if (!numJobs) return;
 	uint32_t blocks = div_up((uint64_t)numJobs * 32, 256);
 	if (blocks > 4096) blocks = 4096;
-	k_fill_jobs<<<blocks, 256, 0, st>>>(dst, jobs, numJobs);
+	launch_chain(k_fill_jobs, blocks, 256, 0, st, dst, jobs, numJobs);
 }
 
 void launch_scatter_words(cudaStream_t st, void *dst, const uint32_t *idx, const void *src, uint32_t n, uint32_t words)
@@ -1301,25 +1319,25 @@ void launch_scatter_words(cudaStream_t st, void *dst, const uint32_t *idx, const
 	if (!n) return;
 	uint32_t blocks = div_up((uint64_t)n * words, 256);
 	if (blocks > 8192) blocks = 8192;
-	k_scatter_words<<<blocks, 256, 0, st>>>((uint32_t*)dst, idx, (const uint32_t*)src, n, words);
+	launch_chain(k_scatter_words, blocks, 256, 0, st, (uint32_t*)dst, idx, (const uint32_t*)src, n, words);
 }
 
 void launch_plan(cudaStream_t st, const TablePtrs &tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp)
 {
 	if (!numWork) return;
-	k_plan<<<div_up((uint64_t)numWork * 32, 128), 128, 0, st>>>(tab, work, numWork, active, stamp);
+	launch_chain(k_plan, div_up((uint64_t)numWork * 32, 128), 128, 0, st, tab, work, numWork, active, stamp);
 }
 
 void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
 {
 	if (!numActive) return;
-	k_emit_warp<<<div_up((uint64_t)numActive * 32, 256), 256, 0, st>>>(pool, tab, active, numActive, round, stamp);
+	launch_chain(k_emit_warp, div_up((uint64_t)numActive * 32, 256), 256, 0, st, pool, tab, active, numActive, round, stamp);
 }
 
 void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs, uint32_t totalBlocks)
 {
 	if (!numJobs || !totalBlocks) return;
-	k_emit_burst<<<totalBlocks, 256, 0, st>>>(pool, tab, active, jobs, numJobs);
+	launch_chain(k_emit_burst, totalBlocks, 256, 0, st, pool, tab, active, jobs, numJobs);
 }
 
 void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
@@ -1328,7 +1346,7 @@ void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &ta
 	if (!numPoolTiles) return;
 	(void)epoch;
 	const float cx = camera[0], cy = camera[1], cz = camera[2];
-#define SPR_LAUNCH_PASS(GP, TINY, KEYS) k_integrate_pass<GP, TINY, KEYS><<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp, round, cx, cy, cz)
+#define SPR_LAUNCH_PASS(GP, TINY, KEYS) launch_chain(k_integrate_pass<GP, TINY, KEYS>, numPoolTiles, 256, 0, st, pool, tab, stamp, round, cx, cy, cz)
 	int variant = (gravityPoints ? 4 : 0) | (tinyEffects ? 2 : 0) | (sortMode ? 1 : 0);
 	switch (variant) {
 	case 0: SPR_LAUNCH_PASS(false, false, false); break;
@@ -1346,8 +1364,8 @@ void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &ta
 void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch, bool aliveScan)
 {
 	if (!numPoolTiles) return;
-	if (aliveScan) k_dead_append<true><<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
-	else k_dead_append<false><<<div_up(numPoolTiles, 4), 128, 0, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
+	if (aliveScan) launch_chain(k_dead_append<true>, div_up(numPoolTiles, 4), 128, 0, st, pool, tab, stamp, round, epoch, numPoolTiles);
+	else launch_chain(k_dead_append<false>, div_up(numPoolTiles, 4), 128, 0, st, pool, tab, stamp, round, epoch, numPoolTiles);
 }
 
 // Per-device kernel attributes (dynamic shared memory of the fused stream kernel) and its resident
@@ -1371,21 +1389,21 @@ uint32_t launch_stream_fused(cudaStream_t st, const PoolPtrs &pool, const TableP
 	const int v = gravityPoints ? 1 : 0;
 	uint32_t grid = numSms * (uint32_t)ctasPerSm[v]; // persistent: resident CTAs only (the chained scan needs its predecessors running)
 	if (grid > numPoolTiles) grid = numPoolTiles;
-	if (v) k_stream_fused<true><<<grid, 288, smem, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
-	else k_stream_fused<false><<<grid, 288, smem, st>>>(pool, tab, stamp, round, epoch, numPoolTiles);
+	if (v) launch_chain(k_stream_fused<true>, grid, 288, smem, st, pool, tab, stamp, round, epoch, numPoolTiles);
+	else launch_chain(k_stream_fused<false>, grid, 288, smem, st, pool, tab, stamp, round, epoch, numPoolTiles);
 	return grid;
 }
 
 void launch_expand_stream(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp)
 {
 	if (!numPoolTiles) return;
-	k_expand_stream<<<numPoolTiles, 256, 0, st>>>(pool, tab, stamp);
+	launch_chain(k_expand_stream, numPoolTiles, 256, 0, st, pool, tab, stamp);
 }
 
 void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t stamp)
 {
 	if (!numActive) return;
-	k_finalize<<<div_up((uint64_t)numActive * 16, 256), 256, 0, st>>>(tab, active, numActive, stamp);
+	launch_chain(k_finalize, div_up((uint64_t)numActive * 16, 256), 256, 0, st, tab, active, numActive, stamp);
 }
 
 void launch_query_frustum(cudaStream_t st, const TablePtrs &tab, uint32_t numGlobals, uint32_t systemIdx, const float frustum[32],

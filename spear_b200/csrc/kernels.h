@@ -67,6 +67,9 @@ struct SortTimingHooks {
 	void *(*begin)(void *ctx, int kernel);
 	void (*end)(void *ctx, int kernel, void *token);
 };
+// Zeroes the histograms, pass masks and status words of one frame's sort. Issued at the START of the frame (before
+// k_plan) so that no memset sits between the frame's kernels: the whole chain then launches programmatically (launch.h).
+void clear_sort_scratch(cudaStream_t st, const SortScratch &scratch, uint32_t numSegments, uint32_t numTiles);
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &scratch,
 	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles, const SortTimingHooks *hooks);
 

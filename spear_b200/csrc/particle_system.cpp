@@ -500,6 +500,14 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	TablePtrs tab = tablePtrs();
 	const ActiveEntry *dEntries = DPTR(ActiveEntry, oEntries);
 	const uint32_t nEntries = (uint32_t)entries.size();
+	SortScratch sortScratch = { nullptr, nullptr, nullptr, nullptr };
+	if (sortMode && !segEffects.empty()) {
+		sortScratch.keysAlt = dKeys[1]; sortScratch.valsAlt = dVals[1];
+		dSortHist.reserve(segEffects.size() * (4 * 256 + 1), 0, stream);
+		dSortLookback.reserve(sortTiles.size() * 4 * 256 + 1, 0, stream);
+		sortScratch.hist = dSortHist.ptr; sortScratch.lookback = dSortLookback.ptr;
+		clear_sort_scratch(stream, sortScratch, (uint32_t)segEffects.size(), (uint32_t)sortTiles.size());
+	}
 	TIMED(kKPlan, launch_plan(stream, tab, DPTR(SystemWork, oWork), (uint32_t)work.size(), dEntries, frameStamp));
 	const uint32_t poolTiles = (uint32_t)((poolUsed + kTileSlots - 1) / kTileSlots);
 	for (uint32_t round = 0; round < maxSub; round++) {
@@ -525,11 +533,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	TIMED(kKFinalize, launch_finalize(stream, tab, dEntries, nEntries, frameStamp));
 
 	if (sortMode && !segEffects.empty()) {
-		SortScratch sc;
-		sc.keysAlt = dKeys[1]; sc.valsAlt = dVals[1];
-		dSortHist.reserve(segEffects.size() * (4 * 256 + 1), 0, stream);
-		dSortLookback.reserve(sortTiles.size() * 4 * 256 + 1, 0, stream);
-		sc.hist = dSortHist.ptr; sc.lookback = dSortLookback.ptr;
+		const SortScratch &sc = sortScratch;
 		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(kKSortBase + k); },
 			[](void *c, int k, void *b) { ((Context*)c)->timingEnd(kKSortBase + k, (cudaEvent_t)b); } };
 		launchCount += launch_sort_and_expand(stream, pool, tab, sc, DPTR(uint32_t, oSeg), (uint32_t)segEffects.size(),

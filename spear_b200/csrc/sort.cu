@@ -21,6 +21,7 @@
 
 #include "device_types.h"
 #include "kernels.h"
+#include "launch.h"
 
 namespace spr {
 
@@ -33,6 +34,7 @@ static const uint32_t kLook = 8;                                      // status 
 
 __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t *hist)
 {
+	pdl_enter();
 	__shared__ uint32_t sHist[4 * 256];
 	SortTile st = tiles[blockIdx.x];
 	uint32_t g = segEffects[st.effect];
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 // so the top digit is normally 0 everywhere and that pass would move every pair to where it already is.
 __global__ void k_sort_scan(TablePtrs tab, const uint32_t *segEffects, uint32_t *hist, uint32_t *passMask, uint32_t numRows)
 {
+	pdl_enter();
 	uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (row >= numRows) return;
 	uint32_t *h = hist + (size_t)row * 256;
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	uint32_t *keys0, uint32_t *vals0, uint32_t *keys1, uint32_t *vals1,
 	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t pass)
 {
+	pdl_enter();
 	__shared__ uint32_t sKeys[kSortTileKeys];
 	__shared__ uint32_t sVals[kSortTileKeys];
 	__shared__ uint32_t sCnt[8 * 256];      // per-warp digit counts -> per-warp exclusive offsets
@@ -291,6 +295,7 @@ __device__ inline void st_record_cs(float4 *p, const float4 &a, const float4 &b)
 __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	const uint32_t *valsAlt, const uint32_t *passMask)
 {
+	pdl_enter();
 	// four CTAs per 4096-key sort tile: 1024 particles per CTA, 4 per thread, all gathers in flight at once
 	SortTile st = tiles[blockIdx.x >> 2];
 	uint32_t g = segEffects[st.effect];
@@ -338,6 +343,13 @@ void configure_sort_kernels()
 	cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+void clear_sort_scratch(cudaStream_t st, const SortScratch &sc, uint32_t numSegments, uint32_t numTiles)
+{
+	if (!numSegments || !numTiles) return;
+	cudaMemsetAsync(sc.hist, 0, (size_t)numSegments * 1025 * sizeof(uint32_t), st);
+	cudaMemsetAsync(sc.lookback, 0, (size_t)numTiles * 4 * 256 * sizeof(uint32_t), st);
+}
+
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &sc,
 	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles, const SortTimingHooks *hooks)
 {
@@ -345,27 +357,25 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 	void *tok = nullptr;
 #define T_BEGIN(k) do { if (hooks) tok = hooks->begin(hooks->ctx, k); } while (0)
 #define T_END(k) do { if (hooks) hooks->end(hooks->ctx, k, tok); } while (0)
-	uint32_t *passMask = sc.hist + (size_t)numSegments * 1024; // [numSegments], cleared together with the histograms
-	cudaMemsetAsync(sc.hist, 0, (size_t)numSegments * 1025 * sizeof(uint32_t), st);
-	cudaMemsetAsync(sc.lookback, 0, (size_t)numTiles * 4 * 256 * sizeof(uint32_t), st);
+	uint32_t *passMask = sc.hist + (size_t)numSegments * 1024; // [numSegments], cleared together with the histograms (clear_sort_scratch)
 	T_BEGIN(0);
-	k_sort_hist<<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, sc.hist);
+	launch_chain(k_sort_hist, numTiles, 256, 0, st, pool, tab, segEffects, tiles, sc.hist);
 	T_END(0);
 	uint32_t rows = numSegments * 4;
 	T_BEGIN(1);
-	k_sort_scan<<<(rows * 32 + 255) / 256, 256, 0, st>>>(tab, segEffects, sc.hist, passMask, rows);
+	launch_chain(k_sort_scan, (rows * 32 + 255) / 256, 256, 0, st, tab, segEffects, sc.hist, passMask, rows);
 	T_END(1);
 	uint32_t *kbuf[2] = { pool.keys, sc.keysAlt };
 	uint32_t *vbuf[2] = { pool.vals, sc.valsAlt };
 	for (uint32_t p = 0; p < 4; p++) {
 		T_BEGIN(2);
-		if (p == 0) k_sort_pass<true><<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, sc.lookback, p);
-		else k_sort_pass<false><<<numTiles, 256, 0, st>>>(pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1],
+		if (p == 0) launch_chain(k_sort_pass<true>, numTiles, 256, 0, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, sc.lookback, p);
+		else launch_chain(k_sort_pass<false>, numTiles, 256, 0, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1],
 			sc.hist, passMask, sc.lookback + (size_t)p * numTiles * 256, p);
 		T_END(2);
 	}
 	T_BEGIN(3);
-	k_expand_sorted<<<numTiles * 4, 256, 0, st>>>(pool, tab, segEffects, tiles, sc.valsAlt, passMask);
+	launch_chain(k_expand_sorted, numTiles * 4, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
 	T_END(3);
 	return 7;
 }
