@@ -61,7 +61,7 @@ struct SortScratch {
 	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases, then [numSegments] pass masks
 	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
 };
-// Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted).
+// Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted, 4 sort_small).
 struct SortTimingHooks {
 	void *ctx;
 	void *(*begin)(void *ctx, int kernel);
@@ -70,7 +70,11 @@ struct SortTimingHooks {
 // Zeroes the histograms, pass masks and status words of one frame's sort. Issued at the START of the frame (before
 // k_plan) so that no memset sits between the frame's kernels: the whole chain then launches programmatically (launch.h).
 void clear_sort_scratch(cudaStream_t st, const SortScratch &scratch, uint32_t numSegments, uint32_t numTiles);
+// segEffects / tiles list the tile-path ("big") effects first: [0, numBigSegments) / [0, numBigTiles) go through
+// hist + scan + 4 passes, the effects behind them (at most kSmallSortMax slots each) through k_sort_small, one CTA
+// per effect; k_expand_sorted then runs over all tiles. Returns the number of launches.
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &scratch,
-	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles, const SortTimingHooks *hooks);
+	const uint32_t *segEffects, uint32_t numSegments, uint32_t numBigSegments, const SortTile *tiles, uint32_t numTiles, uint32_t numBigTiles,
+	const SortTimingHooks *hooks);
 
 } // namespace spr

@@ -234,7 +234,7 @@ void Context::ensureOwned(uint32_t g, uint32_t slotUpperBound)
 
 // Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
 enum { kKScatter = 0, kKPlan, kKEmit, kKEmitBurst, kKIntegrate, kKFinalize, kKSort, kKGather, kKPack, kKExpandRuns,
-	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15, kKStreamFused = 6 };
+	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15, kKStreamFused = 6, kKSortSmall = 16 };
 
 cudaEvent_t Context::timingBegin(int kernel)
 {
@@ -402,12 +402,20 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	// ---- sort-mode work lists
 	std::vector<uint32_t> segEffects;
 	std::vector<SortTile> sortTiles;
+	uint32_t numBigSegments = 0, numBigTiles = 0;
 	if (sortMode) {
+		// tile-path effects first, then the ones one CTA sorts whole (k_sort_small): ownedSlots is the effect's slot
+		// bound rounded up to a tile, never below its real slot count
+		static const bool smallSort = !(getenv("SPR_SMALL_SORT") && getenv("SPR_SMALL_SORT")[0] == '0');
+		std::vector<uint32_t> small;
 		for (const ActiveEntry &ae : entries) {
 			if (!ae.numSubsteps) continue;
 			if (slotCapacityOf[ae.effect] == kGranuleSlots) continue; // sorted and expanded inside k_integrate_sort
-			segEffects.push_back(ae.effect);
+			if (smallSort && ownedSlots[ae.effect] <= kSmallSortMax) small.push_back(ae.effect);
+			else segEffects.push_back(ae.effect);
 		}
+		numBigSegments = (uint32_t)segEffects.size();
+		segEffects.insert(segEffects.end(), small.begin(), small.end());
 	}
 
 	// ---- staging blob
@@ -460,9 +468,13 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	size_t oBurst = bw.put(burstJobs.data(), burstJobs.size());
 	if (sortMode) {
 		for (size_t s = 0; s < segEffects.size(); s++) {
-			uint32_t tiles = (slotCapacityOf[segEffects[s]] + kSortTileKeys - 1) / kSortTileKeys;
+			if (s == numBigSegments) numBigTiles = (uint32_t)sortTiles.size();
+			// a small effect's live particles are below its slot bound: no expansion tiles beyond it
+			uint32_t span = s < numBigSegments ? slotCapacityOf[segEffects[s]] : ownedSlots[segEffects[s]];
+			uint32_t tiles = (span + kSortTileKeys - 1) / kSortTileKeys;
 			for (uint32_t t = 0; t < tiles; t++) sortTiles.push_back({ (uint32_t)s, t });
 		}
+		if (numBigSegments == segEffects.size()) numBigTiles = (uint32_t)sortTiles.size();
 	}
 	size_t oSeg = bw.put(segEffects.data(), segEffects.size());
 	size_t oTiles = bw.put(sortTiles.data(), sortTiles.size());
@@ -534,10 +546,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 
 	if (sortMode && !segEffects.empty()) {
 		const SortScratch &sc = sortScratch;
-		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(kKSortBase + k); },
-			[](void *c, int k, void *b) { ((Context*)c)->timingEnd(kKSortBase + k, (cudaEvent_t)b); } };
-		launchCount += launch_sort_and_expand(stream, pool, tab, sc, DPTR(uint32_t, oSeg), (uint32_t)segEffects.size(),
-			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size(), timingEnabled ? &hooks : nullptr);
+		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(k == 4 ? kKSortSmall : kKSortBase + k); },
+			[](void *c, int k, void *b) { ((Context*)c)->timingEnd(k == 4 ? kKSortSmall : kKSortBase + k, (cudaEvent_t)b); } };
+		launchCount += launch_sort_and_expand(stream, pool, tab, sc, DPTR(uint32_t, oSeg), (uint32_t)segEffects.size(), numBigSegments,
+			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size(), numBigTiles, timingEnabled ? &hooks : nullptr);
 	}
 #undef DPTR
 	if (hostTiming) {

@@ -240,8 +240,8 @@ struct Context {
 	bool timingEnabled = false;
 	std::vector<TimedLaunch> timedLaunches;
 	std::vector<cudaEvent_t> eventPool;
-	double kernelMs[16] = { 0 };
-	uint64_t kernelLaunches[16] = { 0 };
+	double kernelMs[17] = { 0 };
+	uint64_t kernelLaunches[17] = { 0 };
 	cudaEvent_t timingBegin(int kernel);
 	void timingEnd(int kernel, cudaEvent_t begin);
 	void resolveTimings();

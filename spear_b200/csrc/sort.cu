@@ -266,6 +266,159 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	}
 }
 
+// ---------------------------------------------------------------------------
+// Small segments: the whole sort of one effect in ONE CTA.
+//
+// An effect of up to kSmallSortMax slots (18432: the 16k-particle emitters of BASELINE configs[1] and everything
+// smaller down to the 128-slot effects k_integrate_pass finishes itself) does not need the tile machinery: its
+// (key, slot) pairs fit one CTA's registers and shared memory. One 1024-thread CTA per effect loads the keys in
+// slot space under the alive ballots, runs the LSD passes over the digits of key - keyMin that are not all zero
+// (same order as the tile path: stable, ascending), keeps keys in registers and permutes them through shared
+// memory between passes (the 16-bit local slot index travels with them), and writes the sorted slot list to
+// PoolPtrs::vals where k_expand_sorted reads it. No histogram kernel, no scan kernel, no look-back, no global
+// ping-pong: for configs[1] this replaces 6 launches (hist, scan, 4 passes: ~85 us) by one of ~15 us.
+// ---------------------------------------------------------------------------
+
+static const uint32_t kSmallThreads = 1024;
+static const uint32_t kSmallItems = kSmallSortMax / kSmallThreads; // 18 keys per thread at most
+static const uint32_t kSmallWarps = kSmallThreads / 32;
+// shared memory: keys (aliased by the per-warp peer-mask tables while ranking), 16-bit slots, per-warp digit counts
+static const size_t kSmallSmemBytes = kSmallSortMax * 4 + kSmallSortMax * 2 + kSmallWarps * 256 * 4;
+static_assert(kSmallItems * kSmallThreads == kSmallSortMax, "kSmallSortMax must be a multiple of the CTA size");
+static_assert(kSmallWarps * 512 * 4 <= kSmallSortMax * 4, "the peer-mask tables alias the key buffer");
+static_assert(kSmallSortMax <= 65536, "local slot indices are 16-bit");
+
+__global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects)
+{
+	pdl_enter();
+	extern __shared__ __align__(16) uint8_t sRaw[];
+	uint32_t *sKey = (uint32_t*)sRaw;                                  // [kSmallSortMax]
+	uint16_t *sVal = (uint16_t*)(sRaw + kSmallSortMax * 4);            // [kSmallSortMax]
+	uint32_t *sCnt = (uint32_t*)(sRaw + kSmallSortMax * 6);            // [kSmallWarps][256]
+	__shared__ uint32_t sBase[256];     // exclusive scan of the digit totals
+	__shared__ uint32_t sWarpSum[8];
+	__shared__ uint32_t sMaxRel, sTotal;
+
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t g = segEffects[blockIdx.x];
+	EffectState &S = tab.state[g];
+	const uint32_t slots = S.slotCount[S.parity];
+	if (slots > kSmallSortMax) __trap(); // the host routes an effect here only when its slot bound fits
+	const uint32_t segBase = tab.params[g].slotBase;
+	const uint32_t keyMin = effect_key_min(S);
+	// the CTA's keys are warp-striped: warp w owns [w * 32 * items, (w + 1) * 32 * items), item i of lane l is
+	// w * 32 * items + i * 32 + l -- ascending in (warp, item, lane), which is the order ranks are given in
+	const uint32_t items = (slots + kSmallThreads - 1) / kSmallThreads;
+	const uint32_t warpBegin = warp * 32 * items;
+
+	if (tid == 0) sMaxRel = 0;
+	__syncthreads();
+
+	uint32_t key[kSmallItems], rank2[kSmallItems / 2], val2[kSmallItems / 2];
+	uint32_t okBits = 0, maxRel = 0;
+	{
+		const uint32_t *kin = pool.keys + segBase;
+		const uint32_t *mask = pool.aliveMask + (segBase >> 5); // segBase is a multiple of 128
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			const uint32_t idx = warpBegin + i * 32 + lane;
+			bool ok = idx < slots;
+			if (ok) ok = (mask[idx >> 5] >> lane) & 1u;           // idx & 31 == lane
+			key[i] = ok ? kin[idx] - keyMin : 0u;
+			if (ok) { okBits |= 1u << i; maxRel = max(maxRel, key[i]); }
+			const uint32_t v = idx & 0xffffu;
+			if (i & 1u) val2[i >> 1] |= v << 16; else val2[i >> 1] = v;
+		}
+	}
+	maxRel = __reduce_max_sync(FULL_MASK, maxRel);
+	if (lane == 0 && maxRel) atomicMax(&sMaxRel, maxRel);
+	__syncthreads();
+	maxRel = sMaxRel;
+	const uint32_t numPasses = maxRel ? (32u - (uint32_t)__clz(maxRel) + 7u) / 8u : 1u; // pass 0 always runs: it compacts
+
+	uint32_t n = 0; // live keys; known after pass 0
+	for (uint32_t pass = 0; pass < numPasses; pass++) {
+		const uint32_t shift = pass * 8;
+		// ---- clear the per-warp digit counts and the peer-mask tables (aliased onto sKey, idle while the keys are in registers)
+		for (uint32_t i = tid; i < kSmallWarps * 256; i += kSmallThreads) { sCnt[i] = 0; sKey[i] = 0; sKey[i + kSmallWarps * 256] = 0; }
+		__syncthreads();
+		// ---- rank inside the warp (same scheme as k_sort_pass: one shared-memory atomicOr per lane finds the peers)
+		uint32_t *cnt = sCnt + warp * 256;
+		uint32_t *match0 = sKey + warp * 512, *match1 = match0 + 256;
+		const uint32_t ltMask = (1u << lane) - 1u;
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			uint32_t *match = (i & 1u) ? match1 : match0;
+			const bool ok = (okBits >> i) & 1u;
+			const uint32_t d = (key[i] >> shift) & 255u;
+			if (ok) atomicOr(&match[d], 1u << lane);
+			__syncwarp();
+			const uint32_t peers = ok ? match[d] : 0u;
+			const uint32_t before = ok ? cnt[d] : 0u;
+			__syncwarp();
+			const uint32_t rk = before + __popc(peers & ltMask);
+			if (ok && (peers & ltMask) == 0) { cnt[d] = before + __popc(peers); match[d] = 0; }
+			if (i & 1u) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
+		}
+		__syncthreads();
+		// ---- thread d < 256: exclusive offsets of digit d over the warps, then the exclusive scan over the digits
+		uint32_t total = 0;
+		if (tid < 256) {
+#pragma unroll 8
+			for (uint32_t w = 0; w < kSmallWarps; w++) { const uint32_t c = sCnt[w * 256 + tid]; sCnt[w * 256 + tid] = total; total += c; }
+			uint32_t incl = total;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += o; }
+			if (lane == 31) sWarpSum[warp] = incl;
+			total = incl - total; // exclusive inside the warp
+		}
+		__syncthreads();
+		if (tid < 256) {
+			uint32_t warpBase = 0;
+#pragma unroll
+			for (uint32_t w = 0; w < 8; w++) if (w < warp) warpBase += sWarpSum[w];
+			sBase[tid] = warpBase + total;
+			if (tid == 255) { uint32_t all = 0; for (uint32_t w = 0; w < 8; w++) all += sWarpSum[w]; sTotal = all; }
+		}
+		__syncthreads();
+		n = sTotal;
+		// ---- permute through shared memory: position = digit base + this warp's offset + rank in the warp
+		// (the peer-mask tables aliased onto sKey are dead since the barrier after the ranking loop)
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			if ((okBits >> i) & 1u) {
+				const uint32_t d = (key[i] >> shift) & 255u;
+				const uint32_t rk = (i & 1u) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
+				const uint32_t pos = sBase[d] + sCnt[warp * 256 + d] + rk;
+				sKey[pos] = key[i];
+				sVal[pos] = (uint16_t)((i & 1u) ? (val2[i >> 1] >> 16) : (val2[i >> 1] & 0xffffu));
+			}
+		}
+		__syncthreads();
+		if (pass + 1 == numPasses) break;
+		// ---- back into registers in the new order; after pass 0 the live keys are the first n
+		okBits = 0;
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			const uint32_t idx = warpBegin + i * 32 + lane;
+			const bool ok = idx < n;
+			key[i] = ok ? sKey[idx] : 0u;
+			const uint32_t v = ok ? sVal[idx] : 0u;
+			if (i & 1u) val2[i >> 1] |= v << 16; else val2[i >> 1] = v;
+			if (ok) okBits |= 1u << i;
+		}
+		__syncthreads(); // all reads done before the next pass clears the aliased tables
+	}
+	// ---- the sorted slot list (PoolPtrs::vals: what k_expand_sorted and sprReadStreamSlots read)
+	uint32_t *vout = pool.vals + segBase;
+	for (uint32_t j = tid; j < n; j += kSmallThreads) vout[j] = sVal[j];
+	if (tid == 0) S.aliveCount = n; // gpuParticles.size / 4 (:670); the tile path writes it in k_sort_scan
+}
+
 // One lane per particle: a coalesced read of 32 slot indices, one 256-bit gather of the 32-byte
 // record per lane, then the record is stored four times (:607-665). The four 256-bit stores of a
 // warp together fill 32 complete 128-byte lines.
@@ -341,6 +494,7 @@ void configure_sort_kernels()
 {
 	cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes);
 }
 
 void clear_sort_scratch(cudaStream_t st, const SortScratch &sc, uint32_t numSegments, uint32_t numTiles)
@@ -351,33 +505,45 @@ void clear_sort_scratch(cudaStream_t st, const SortScratch &sc, uint32_t numSegm
 }
 
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &sc,
-	const uint32_t *segEffects, uint32_t numSegments, const SortTile *tiles, uint32_t numTiles, const SortTimingHooks *hooks)
+	const uint32_t *segEffects, uint32_t numSegments, uint32_t numBigSegments, const SortTile *tiles, uint32_t numTiles, uint32_t numBigTiles,
+	const SortTimingHooks *hooks)
 {
 	if (!numSegments || !numTiles) return 0;
 	void *tok = nullptr;
 #define T_BEGIN(k) do { if (hooks) tok = hooks->begin(hooks->ctx, k); } while (0)
 #define T_END(k) do { if (hooks) hooks->end(hooks->ctx, k, tok); } while (0)
 	uint32_t *passMask = sc.hist + (size_t)numSegments * 1024; // [numSegments], cleared together with the histograms (clear_sort_scratch)
-	T_BEGIN(0);
-	launch_chain(k_sort_hist, numTiles, 256, 0, st, pool, tab, segEffects, tiles, sc.hist);
-	T_END(0);
-	uint32_t rows = numSegments * 4;
-	T_BEGIN(1);
-	launch_chain(k_sort_scan, (rows * 32 + 255) / 256, 256, 0, st, tab, segEffects, sc.hist, passMask, rows);
-	T_END(1);
-	uint32_t *kbuf[2] = { pool.keys, sc.keysAlt };
-	uint32_t *vbuf[2] = { pool.vals, sc.valsAlt };
-	for (uint32_t p = 0; p < 4; p++) {
-		T_BEGIN(2);
-		if (p == 0) launch_chain(k_sort_pass<true>, numTiles, 256, 0, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, sc.lookback, p);
-		else launch_chain(k_sort_pass<false>, numTiles, 256, 0, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1],
-			sc.hist, passMask, sc.lookback + (size_t)p * numTiles * 256, p);
-		T_END(2);
+	uint32_t launches = 0;
+	if (numBigSegments && numBigTiles) {
+		T_BEGIN(0);
+		launch_chain(k_sort_hist, numBigTiles, 256, 0, st, pool, tab, segEffects, tiles, sc.hist);
+		T_END(0);
+		uint32_t rows = numBigSegments * 4;
+		T_BEGIN(1);
+		launch_chain(k_sort_scan, (rows * 32 + 255) / 256, 256, 0, st, tab, segEffects, sc.hist, passMask, rows);
+		T_END(1);
+		uint32_t *kbuf[2] = { pool.keys, sc.keysAlt };
+		uint32_t *vbuf[2] = { pool.vals, sc.valsAlt };
+		for (uint32_t p = 0; p < 4; p++) {
+			T_BEGIN(2);
+			if (p == 0) launch_chain(k_sort_pass<true>, numBigTiles, 256, 0, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, sc.lookback, p);
+			else launch_chain(k_sort_pass<false>, numBigTiles, 256, 0, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1],
+				sc.hist, passMask, sc.lookback + (size_t)p * numBigTiles * 256, p);
+			T_END(2);
+		}
+		launches += 6;
+	}
+	if (numSegments > numBigSegments) {
+		// their pass masks stay 0 (cleared with the histograms): k_expand_sorted then reads PoolPtrs::vals
+		T_BEGIN(4);
+		launch_chain(k_sort_small, numSegments - numBigSegments, kSmallThreads, kSmallSmemBytes, st, pool, tab, segEffects + numBigSegments);
+		T_END(4);
+		launches++;
 	}
 	T_BEGIN(3);
 	launch_chain(k_expand_sorted, numTiles * 4, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
 	T_END(3);
-	return 7;
+	return launches + 1;
 }
 
 } // namespace spr

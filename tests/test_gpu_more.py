@@ -166,6 +166,53 @@ def test_sorted_pass_skipping_shapes(oracle_port):
         ctx.close()
 
 
+def test_sorted_small_effects_one_cta_path(oracle_port):
+    """Effects of at most 18432 slots are sorted whole by one CTA (k_sort_small): 1 to 18 keys per thread, 1 to 4
+    executed passes, next to a tile-path effect in the same frame, and an effect that grows across the limit while it
+    is simulated (one-CTA path first, tile path later) -- all against the stable sort of the oracle's stream."""
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 12)
+    try:
+        still = dict(drag=0.0, gravity=(0, 0, 0), lifeTime=1e9, spawnTime=1e9, timeStep=1 / 60)
+        comps = [
+            abi.make_component(burstAmount=700, **still),                                                               # 1 pass, 1 key per thread
+            abi.make_component(burstAmount=1025, emitPosition=dict(boxExtent=(0.002, 0.002, 0.002)), **still),           # 2 passes, 2 keys per thread
+            abi.make_component(burstAmount=18300, emitPosition=dict(boxExtent=(4, 2, 4)), emitVelocity=dict(boxExtent=(1, 1, 1)), **still),  # 3 passes, 18 keys per thread
+            abi.make_component(burstAmount=17000, emitPosition=dict(boxExtent=(400, 300, 400)), **still),                # 4 passes
+            abi.make_component(burstAmount=30000, emitPosition=dict(boxExtent=(4, 2, 4)), **still),                      # tile path, same frame
+            # grows by 20 particles per step from 18200: crosses the 18432-slot limit after a dozen steps; short lives
+            # keep holes in the slot range (the first pass compacts under the alive ballots)
+            abi.make_component(burstAmount=18200, spawnTime=1e-5, lifeTime=1e9, drag=0.1, gravity=(0, -9.81, 0), timeStep=1 / 60,
+                               emitPosition=dict(boxExtent=(3, 1, 3)), emitVelocity=dict(sphere=dict(minRadius=0.5, maxRadius=2.0))),
+            abi.make_component(burstAmount=4000, spawnTime=0.002, lifeTime=0.1, lifeTimeVariance=0.2, drag=0.1, gravity=(0, -9.81, 0), timeStep=1 / 60,
+                               emitPosition=dict(boxExtent=(3, 1, 3)), emitVelocity=dict(sphere=dict(minRadius=0.5, maxRadius=2.0))),
+        ]
+        trs = [abi.make_transform((1, 2, 3)), abi.make_transform((300, 2, 3)), abi.make_transform((1, 2, 3)), abi.make_transform(CAMERA),
+               abi.make_transform((5, 2, 3)), abi.make_transform((-4, 1, 6)), abi.make_transform((9, 1, -6))]
+        sseed = (1, 91, 3, 4)
+        s, o = ctx.create_system(sseed), orc.OracleSystem(oracle_port, sseed)
+        ids = [s.add_effect(c, t) for c, t in zip(comps, trs)]
+        assert ids == [o.add_effect(c, t) for c, t in zip(comps, trs)]
+        crossed = False
+        for f in range(24):
+            fa = abi.make_frame_args(1 / 55, game_time=f / 55, frame_index=f, camera=CAMERA)
+            s.update(ids, fa); o.update(ids, fa)
+            if f % 3 and f < 20:
+                continue
+            a, b = S.snapshot(o, ids), S.snapshot(s, ids)
+            assert a["rng"] == b["rng"]
+            for e in ids:
+                assert a[e]["info"] == b[e]["info"], "frame %d effect %d" % (f, e)
+                exp, _ = expected_sorted(a[e]["stream"])
+                assert exp.tobytes() == b[e]["stream"].tobytes(), "frame %d effect %d sorted stream" % (f, e)
+                slots = s.read_stream_slots(e)
+                assert len(slots) == a[e]["info"]["aliveCount"] and len(set(slots.tolist())) == len(slots)
+            crossed = crossed or a[ids[5]]["info"]["slotCount"] > 18432
+        assert crossed
+    finally:
+        ctx.close()
+
+
 def test_many_systems_one_launch_set(oracle_port):
     """sprUpdateParticlesBatch: 24 independent systems (own RNG each, seed[1] = 2 + i) advance in one
     set of launches and each matches its own oracle instance."""
