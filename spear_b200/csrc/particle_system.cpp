@@ -230,6 +230,7 @@ void Context::ensureOwned(uint32_t g, uint32_t slotUpperBound)
 	const EffectParams &P = hParams[g];
 	ownerJobs.push_back({ (P.slotBase + ownedSlots[g]) / kGranuleSlots, (uint32_t)(target - ownedSlots[g]) / kGranuleSlots, g, 0 });
 	ownedSlots[g] = (uint32_t)target;
+	if ((uint64_t)P.slotBase + target > poolOwnedEnd) poolOwnedEnd = (uint64_t)P.slotBase + target;
 }
 
 // Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
@@ -469,9 +470,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	if (sortMode) {
 		for (size_t s = 0; s < segEffects.size(); s++) {
 			if (s == numBigSegments) numBigTiles = (uint32_t)sortTiles.size();
-			// a small effect's live particles are below its slot bound: no expansion tiles beyond it
-			uint32_t span = s < numBigSegments ? slotCapacityOf[segEffects[s]] : ownedSlots[segEffects[s]];
-			uint32_t tiles = (span + kSortTileKeys - 1) / kSortTileKeys;
+			// tiles up to the effect's slot bound (ownedSlots: never below its real slot count), not up to its
+			// power-of-two capacity: C3's 10M slots are 2443 tiles of a 4096-tile range, and every empty CTA costs
+			// each of the seven sort kernels a scheduling slot
+			uint32_t tiles = (ownedSlots[segEffects[s]] + kSortTileKeys - 1) / kSortTileKeys;
 			for (uint32_t t = 0; t < tiles; t++) sortTiles.push_back({ (uint32_t)s, t });
 		}
 		if (numBigSegments == segEffects.size()) numBigTiles = (uint32_t)sortTiles.size();
@@ -521,7 +523,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		clear_sort_scratch(stream, sortScratch, (uint32_t)segEffects.size(), (uint32_t)sortTiles.size());
 	}
 	TIMED(kKPlan, launch_plan(stream, tab, DPTR(SystemWork, oWork), (uint32_t)work.size(), dEntries, frameStamp));
-	const uint32_t poolTiles = (uint32_t)((poolUsed + kTileSlots - 1) / kTileSlots);
+	// pool tiles up to the last owned granule, not up to the bump pointer: an effect's range is a power of two (C3: 10M
+	// slots own 9767 tiles of a 16384-tile range) and the tiles behind its slot bound would only be looked at and dropped
+	const uint64_t poolEnd = poolOwnedEnd < poolUsed ? poolOwnedEnd : poolUsed;
+	const uint32_t poolTiles = (uint32_t)((poolEnd + kTileSlots - 1) / kTileSlots);
 	for (uint32_t round = 0; round < maxSub; round++) {
 		TIMED(kKEmit, launch_emit_warp(stream, pool, tab, dEntries, nEntries, round, frameStamp));
 		if (round == 0 && !burstJobs.empty()) {

@@ -174,6 +174,7 @@ struct Context {
 	// ---- slot pool
 	uint64_t poolCapacity = 0;     // slots
 	uint64_t poolUsed = 0;         // bump pointer
+	uint64_t poolOwnedEnd = 0;     // end of the highest slot range any effect owns granules in: the per-frame kernels stop there
 	float4 *dSlotState = nullptr;
 	uint32_t *dFreeStack = nullptr;
 	float4 *dVertices = nullptr;

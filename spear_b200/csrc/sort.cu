@@ -317,15 +317,25 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, 
 	uint32_t key[kSmallItems], rank2[kSmallItems / 2], val2[kSmallItems / 2];
 	uint32_t okBits = 0, maxRel = 0;
 	{
+		// all loads first, with no branch between them (one memory round trip for the CTA, not one per item): lane l
+		// fetches the alive word of the warp's item l, every lane its raw keys -- a dead slot's key is stale, not unmapped
 		const uint32_t *kin = pool.keys + segBase;
 		const uint32_t *mask = pool.aliveMask + (segBase >> 5); // segBase is a multiple of 128
+		uint32_t myWord = 0;
+		if (lane < items && warpBegin + lane * 32 < slots) myWord = mask[(warpBegin >> 5) + lane];
 #pragma unroll
 		for (uint32_t i = 0; i < kSmallItems; i++) {
 			if (i >= items) break;
 			const uint32_t idx = warpBegin + i * 32 + lane;
-			bool ok = idx < slots;
-			if (ok) ok = (mask[idx >> 5] >> lane) & 1u;           // idx & 31 == lane
-			key[i] = ok ? kin[idx] - keyMin : 0u;
+			key[i] = idx < slots ? kin[idx] : 0u;
+		}
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			const uint32_t idx = warpBegin + i * 32 + lane;
+			const uint32_t word = __shfl_sync(FULL_MASK, myWord, i);       // bit `lane` of the word is slot idx
+			const bool ok = idx < slots && ((word >> lane) & 1u);
+			key[i] = ok ? key[i] - keyMin : 0u;
 			if (ok) { okBits |= 1u << i; maxRel = max(maxRel, key[i]); }
 			const uint32_t v = idx & 0xffffu;
 			if (i & 1u) val2[i >> 1] |= v << 16; else val2[i >> 1] = v;
