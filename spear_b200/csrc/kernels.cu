@@ -1283,6 +1283,7 @@ __global__ void __launch_bounds__(256) k_expand_from_peers(PeerRuns runs, float4
 		bool ok[4];
 #pragma unroll
 		for (int u = 0; u < 4; u++) {
+			a[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); b[u] = a[u];
 			unsigned long long i = base + u * 256 + threadIdx.x;
 			ok[u] = i < count;
 			if (ok[u]) {
@@ -1291,11 +1292,22 @@ __global__ void __launch_bounds__(256) k_expand_from_peers(PeerRuns runs, float4
 					: "l"(src + 2ull * (u * 256 + threadIdx.x)));
 			}
 		}
+		// transposed across the warp like k_expand_sorted: every store instruction covers 1 KB of consecutive bytes
+		const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
 		for (int u = 0; u < 4; u++) {
-			if (!ok[u]) continue;
-			float4 *d = dst + 8ull * (u * 256 + threadIdx.x);
-			st_record(d, a[u], b[u]); st_record(d + 2, a[u], b[u]); st_record(d + 4, a[u], b[u]); st_record(d + 6, a[u], b[u]);
+			const unsigned long long wbase = base + u * 256 + warp * 32;
+			if (wbase >= count) continue; // warp-uniform
+			const uint32_t cnt = count - wbase < 32 ? (uint32_t)(count - wbase) : 32u;
+			float4 *d = dst + 8ull * (u * 256 + warp * 32);
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const uint32_t p = k * 8 + (lane >> 2);
+				float4 x, y;
+				x.x = __shfl_sync(FULL_MASK, a[u].x, p); x.y = __shfl_sync(FULL_MASK, a[u].y, p); x.z = __shfl_sync(FULL_MASK, a[u].z, p); x.w = __shfl_sync(FULL_MASK, a[u].w, p);
+				y.x = __shfl_sync(FULL_MASK, b[u].x, p); y.y = __shfl_sync(FULL_MASK, b[u].y, p); y.z = __shfl_sync(FULL_MASK, b[u].z, p); y.w = __shfl_sync(FULL_MASK, b[u].w, p);
+				if (p < cnt) st_record(d + 2 * (k * 32 + lane), x, y);
+			}
 		}
 	}
 }
