@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) k_shade_vertices(const float4 *vertices, 
 {
 	__shared__ uint32_t sLut[128];
 	__shared__ ShadeJob sJob;
+	__shared__ __align__(16) float sStage[8][32 * 36]; // per warp: 32 lanes x 128 bytes at a 144-byte pitch
 	// job of this CTA: jobs are ordered by firstBlock
 	uint32_t lo = 0, hi = numJobs;
 	while (hi - lo > 1) {
@@ -96,15 +97,18 @@ __global__ void __launch_bounds__(256) k_shade_vertices(const float4 *vertices, 
 	__syncthreads();
 	const ShadeJob &J = sJob;
 	const uint32_t k = (blockIdx.x - J.firstBlock) * 256 + threadIdx.x;
-	if (k >= J.numParticles) return;
 	const uint64_t firstVertex = J.dstVertex + 4ull * k;
-	if (firstVertex + 4 > capacityVertices) return;
+	// a lane without a particle (or without room for its quad) stays for the warp-wide stores at the end and shades
+	// a record of zeros that is never written
+	const bool valid = k < J.numParticles && firstVertex + 4 <= capacityVertices;
+	const uint32_t validMask = __ballot_sync(0xffffffffu, valid);
+	if (!validMask) return;
 
 	// a_PositionLife / a_VelocitySeed of the quad (its four stream records are identical: read the first)
 	const float4 *rec = vertices + 2ull * (J.srcRecord + 4ull * k);
-	float4 pl, vs;
+	float4 pl = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vs = pl;
 	// one 32-byte record out of every 128-byte line: ask L2 for 64 bytes instead of the whole line
-	asm("ld.global.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	if (valid) asm("ld.global.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=f"(pl.x), "=f"(pl.y), "=f"(pl.z), "=f"(pl.w), "=f"(vs.x), "=f"(vs.y), "=f"(vs.z), "=f"(vs.w) : "l"(rec));
 	const float *M = J.instance;        // u_ParticleToWorld, column major
 	const float *W = J.instance + 16;   // u_WorldToClip
@@ -184,19 +188,42 @@ __global__ void __launch_bounds__(256) k_shade_vertices(const float4 *vertices, 
 	const float erode = splW < 1.0f ? 1.0f / fmaxf(splW, 0.01f) : 1.0f; // :130
 	const bool deadQuad = lifeLeft <= 0.0f;                               // :113-115
 
-	float4 *dst = out + 4ull * firstVertex;
+	// The quad's 256 bytes (4 vertices x {gl_Position, uv, uv | colour, params}) go out through a per-warp staging
+	// buffer, two corners at a time: every lane parks its 4 x 32 bytes (144-byte pitch: conflict-free both ways), then
+	// store i of lane l writes piece (i * 32 + l) & 3 of the quad of lane (i * 32 + l) >> 2 -- each store instruction
+	// of the warp covers 8 complete 128-byte lines instead of one 32-byte piece of 32 different lines
+	// (tools/expand_store_bench.cu: the strided form costs 4x the LSU wavefronts for the same bytes).
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	float *stage = sStage[warp];
+	float4 *mine = (float4*)(stage + lane * 36);
+	float4 *warpDst = out + 4ull * (firstVertex - 4ull * lane); // the quad of lane 0 (lanes hold consecutive particles)
 #pragma unroll
-	for (uint32_t corner = 0; corner < 4; corner++) {
-		const float u = (float)(corner & 1u), v = (float)((corner >> 1) & 1u); // :91
-		const float ox = (u * 2.0f - 1.0f) * scale, oy = (v * 2.0f - 1.0f) * scale; // :92, :103
-		float4 pos;
-		pos.x = nx + (ox * axx + oy * ayx) * (0.5f * aspect); // :111
-		pos.y = ny + (ox * axy + oy * ayy) * 0.5f;
-		pos.z = nz; pos.w = nw;
-		if (deadQuad) pos = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		// two 256-bit stores per vertex: {gl_Position, v_Uv0, v_Uv1} and {v_Color, v_Params}
-		st256(dst + 4 * corner, pos, make_float4((f0x + u) / frameCountX, (f0y + v) / frameCountY, (f1x + u) / frameCountX, (f1y + v) / frameCountY)); // :133-134
-		st256(dst + 4 * corner + 2, make_float4(cr, cg, cb, splY), make_float4(frameD, splZ, erode, 0.0f)); // :129, :135-138
+	for (uint32_t cp = 0; cp < 2; cp++) {
+#pragma unroll
+		for (uint32_t c = 0; c < 2; c++) {
+			const uint32_t corner = cp * 2 + c;
+			const float u = (float)(corner & 1u), v = (float)((corner >> 1) & 1u); // :91
+			const float ox = (u * 2.0f - 1.0f) * scale, oy = (v * 2.0f - 1.0f) * scale; // :92, :103
+			float4 pos;
+			pos.x = nx + (ox * axx + oy * ayx) * (0.5f * aspect); // :111
+			pos.y = ny + (ox * axy + oy * ayy) * 0.5f;
+			pos.z = nz; pos.w = nw;
+			if (deadQuad) pos = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			// per vertex: {gl_Position, v_Uv0, v_Uv1} and {v_Color, v_Params}
+			mine[c * 4 + 0] = pos;
+			mine[c * 4 + 1] = make_float4((f0x + u) / frameCountX, (f0y + v) / frameCountY, (f1x + u) / frameCountX, (f1y + v) / frameCountY); // :133-134
+			mine[c * 4 + 2] = make_float4(cr, cg, cb, splY);      // :129, :135-138
+			mine[c * 4 + 3] = make_float4(frameD, splZ, erode, 0.0f);
+		}
+		__syncwarp();
+#pragma unroll
+		for (uint32_t i = 0; i < 4; i++) {
+			const uint32_t q = i * 32 + lane, prod = q >> 2, piece = q & 3u;
+			const float4 *src = (const float4*)(stage + prod * 36 + piece * 8);
+			const float4 x = src[0], y = src[1];
+			if ((validMask >> prod) & 1u) st256(warpDst + 16ull * prod + cp * 8 + piece * 2, x, y);
+		}
+		__syncwarp();
 	}
 }
 
