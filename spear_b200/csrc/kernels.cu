@@ -404,6 +404,9 @@ __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab,
 		uint32_t slots = c.blocks * 4, topPost = c.top - (n <= c.top ? n : c.top);
 		if (n > c.top) { uint32_t nb = (n - c.top + 3) >> 2; slots += 4 * nb; topPost = nb * 4 - (n - c.top); }
 		uint32_t par = (rec->flags >> 1) & 1u;
+		// the host sizes every range from a conservative (or, for short-lived effects, proven) slot bound: an effect
+		// that outgrows it would write into its neighbour's slots -- stop the context instead
+		if (slots > c.P->slotCapacity) __trap();
 		if (slots == 0) { // nothing for k_integrate to do: carry the counts over
 			S.slotCount[par ^ 1u] = 0;
 			S.freeCount[par ^ 1u] = 0;

@@ -8,6 +8,7 @@
 #include "particle_system.h"
 
 #include <algorithm>
+#include <cmath>
 #include <chrono>
 #include <map>
 #include <stdio.h>
@@ -308,11 +309,20 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	// ---- host pass: sub-step counts (ParticleSystem.cpp:810-820) and capacity bounds
 	size_t totalActive = 0;
 	for (uint32_t r = 0; r < numReqs; r++) totalActive += reqs[r].numActive;
-	std::vector<ActiveEntry> entries;
-	std::vector<SystemWork> work;
+	// the frame's work lists live in the context between frames: a 100k-effect frame would otherwise allocate, fault in
+	// and release megabytes of vectors every call
+	// (update re-enters itself with an empty request list when a read-back in the middle of the host pass has to flush
+	// pending uploads, flushUploads(): the nested call gets lists of its own)
+	struct DepthGuard { int &d; DepthGuard(int &x) : d(x) { d++; } ~DepthGuard() { d--; } } depthGuard(updateDepth);
+	const bool nested = updateDepth > 1;
+	std::vector<ActiveEntry> nestedEntries; std::vector<SystemWork> nestedWork; std::vector<BurstJob> nestedBurstJobs;
+	std::vector<uint32_t> nestedSeg, nestedSmall; std::vector<SortTile> nestedTiles; std::vector<EffectParams> nestedParamVals;
+	std::vector<ActiveEntry> &entries = nested ? nestedEntries : scratchEntries;
+	std::vector<SystemWork> &work = nested ? nestedWork : scratchWork;
+	std::vector<BurstJob> &burstJobs = nested ? nestedBurstJobs : scratchBurstJobs;
+	entries.clear(); work.clear(); burstJobs.clear();
 	entries.reserve(totalActive);
 	work.reserve(numReqs);
-	std::vector<BurstJob> burstJobs;
 	struct Resolve { HostEffect *E; uint32_t add; };
 	std::vector<Resolve> resolve;
 	std::vector<uint32_t> resolveGlobals;
@@ -339,6 +349,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				uint32_t burst = E.firstEmit ? type.comp->burstAmount : 0;
 				// <= 20 timer spawns per sub-step (:478), each sub-step rounds up to one Particle4
 				uint64_t add = (uint64_t)nsub * (kMaxTimerSpawns + 3) + burst + 3;
+				if (!E.capacityFinal) {
 				{
 					// re-base the bound on the newest exact count the device has mirrored (no synchronisation: an older
 					// entry only means more allowances are added on top of it)
@@ -366,6 +377,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 					E.slotUpperBound = (uint32_t)need;
 					ensureOwned(E.global, E.slotUpperBound);
 				}
+				} // !capacityFinal
 				if (burst > 1024) {
 					ae.flags |= 1u;
 					uint32_t blocks = (burst + 255) / 256;
@@ -401,14 +413,16 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 
 	auto t1 = tNow();
 	// ---- sort-mode work lists
-	std::vector<uint32_t> segEffects;
-	std::vector<SortTile> sortTiles;
+	std::vector<uint32_t> &segEffects = nested ? nestedSeg : scratchSegEffects;
+	std::vector<SortTile> &sortTiles = nested ? nestedTiles : scratchSortTiles;
+	segEffects.clear(); sortTiles.clear();
 	uint32_t numBigSegments = 0, numBigTiles = 0;
 	if (sortMode) {
 		// tile-path effects first, then the ones one CTA sorts whole (k_sort_small): ownedSlots is the effect's slot
 		// bound rounded up to a tile, never below its real slot count
 		static const bool smallSort = !(getenv("SPR_SMALL_SORT") && getenv("SPR_SMALL_SORT")[0] == '0');
-		std::vector<uint32_t> small;
+		std::vector<uint32_t> &small = nested ? nestedSmall : scratchSmallEffects;
+		small.clear();
 		for (const ActiveEntry &ae : entries) {
 			if (!ae.numSubsteps) continue;
 			if (slotCapacityOf[ae.effect] == kGranuleSlots) continue; // sorted and expanded inside k_integrate_sort
@@ -438,7 +452,8 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	stagingD.reserve(bound, 0, stream);
 	BlobWriter bw(stagingH[par].ptr);
 
-	std::vector<EffectParams> paramVals(dirtyParams.size());
+	std::vector<EffectParams> &paramVals = nested ? nestedParamVals : scratchParamVals;
+	paramVals.resize(dirtyParams.size());
 	for (size_t i = 0; i < dirtyParams.size(); i++) { paramVals[i] = hParams[dirtyParams[i]]; dirtyParamsFlag[dirtyParams[i]] = 0; }
 	size_t oParamIdx = bw.put(dirtyParams.data(), dirtyParams.size());
 	size_t oParamVal = bw.put(paramVals.data(), paramVals.size());
@@ -751,6 +766,29 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 	P.slotBase = 0; P.slotCapacity = 0;
 	ctx->slotCapacityOf[E.global] = 0;
 	ctx->growEffect(E.global, pow2ceil((uint64_t)c->burstAmount + 64), false);
+	{
+		// A slot is held from the sub-step that spawns its particle until the integrate pass after the one in which its
+		// life reaches 0 (:556-567): life = 1 falls by timeStep / L per sub-step with L = lifeTime + seed * variance * 2^-24
+		// <= lifeTime + variance (:535, :596-605), and an effect's timeStep is never below its type's (:744). With at most
+		// 20 timer spawns per sub-step (:478) plus the one burst, the slot count can never exceed
+		//   burst + 20 * (floor(Lmax / typeTimeStep) + 4) + 4
+		// (two sub-steps of slack for rounding in the life accumulation, two for the spawn / free order inside a
+		// sub-step, +4 for the Particle4 granularity). When that fits the range just allocated, the per-frame capacity
+		// bookkeeping of Context::update (mirror read, allowances, growth checks) is skipped for this effect for good.
+		const double lmax = (double)c->lifeTime + (double)c->lifeTimeVariance;
+		if (c->lifeTime > 0.0f && c->lifeTimeVariance >= 0.0f && type.timeStep > 0.0f && std::isfinite(lmax)) {
+			const double steps = std::floor(lmax / (double)type.timeStep) + 4.0;
+			const double bound = (double)c->burstAmount + 20.0 * steps + 4.0;
+			// (only where owning the range up to the bound from the start costs at most one tile of slots the effect may
+			// never reach: the streaming kernels load every owned granule)
+			const uint32_t cap = ctx->slotCapacityOf[E.global];
+			if (bound <= (double)cap && (cap <= kTileSlots || 20.0 * steps + 8.0 <= (double)kTileSlots)) {
+				E.capacityFinal = true;
+				E.slotUpperBound = (uint32_t)bound;
+				ctx->ensureOwned(E.global, E.slotUpperBound);
+			}
+		}
+	}
 
 	EffectState S;
 	memset(&S, 0, sizeof(S));

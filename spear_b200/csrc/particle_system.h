@@ -86,6 +86,7 @@ struct HostEffect {
 	bool inUse = false;
 	bool hostStopEmit = false;
 	bool instantDelete = false;
+	bool capacityFinal = false;   // the slot count provably never exceeds the bound fixed at addEffect: no per-frame capacity bookkeeping
 	// ---- cold: transforms (render, updateTransform, localSpace bounds)
 	SprVec3 origin = { 0, 0, 0 };
 	SprMat34 particlesToWorld;
@@ -220,6 +221,14 @@ struct Context {
 	}
 	static void clearUploads(std::vector<uint32_t> &idx, std::vector<uint32_t> &pos) { for (uint32_t i : idx) pos[i] = 0; idx.clear(); }
 
+	// ---- per-frame work lists of Context::update (kept for their capacity)
+	std::vector<ActiveEntry> scratchEntries;
+	std::vector<SystemWork> scratchWork;
+	std::vector<BurstJob> scratchBurstJobs;
+	std::vector<uint32_t> scratchSegEffects, scratchSmallEffects;
+	std::vector<SortTile> scratchSortTiles;
+	std::vector<EffectParams> scratchParamVals;
+	int updateDepth = 0;
 	// ---- per-frame staging
 	PinnedArray<uint8_t> stagingH[2];
 	DeviceArray<uint8_t> stagingD;
