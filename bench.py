@@ -186,6 +186,8 @@ def run_ours(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.workload or ("c3" if world == 1 else "c4")
     wl = workload_components(name)
