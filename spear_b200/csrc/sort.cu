@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 		const uint32_t word = __shfl_sync(FULL_MASK, myWord, it);
 		if (i >= count || !((word >> lane) & 1u)) continue;
 		const uint32_t k = key[it] - keyMin;
+		// (one count per warp for the top digits, which are the same for most keys of an effect, was measured twice:
+		// slower -- same-address shared-memory atomics are not what this kernel waits for)
 		atomicAdd(&sHist[0 * 256 + (k & 255u)], 1u);
 		atomicAdd(&sHist[1 * 256 + ((k >> 8) & 255u)], 1u);
 		atomicAdd(&sHist[2 * 256 + ((k >> 16) & 255u)], 1u);
@@ -166,12 +168,25 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	uint32_t okBits = 0;
 	const uint32_t *kin = keysIn + segBase + begin;
 	const uint32_t *vin = valsIn + segBase + begin;
+	// every load of the tile is issued before anything depends on one: the first pass fetches the warp's 16 alive
+	// words with one coalesced load (lane i holds the word of item i) and its keys whether alive or not (a dead slot's
+	// key is stale, not unmapped)
+	uint32_t myWord = 0;
+	if (FIRST && lane < kItemsPerThread && warp * kWarpKeys + lane * 32 < count) myWord = mask[lane];
+#pragma unroll
+	for (uint32_t i = 0; i < kItemsPerThread; i++) {
+		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
+		key[i] = idx < count ? kin[idx] : 0xffffffffu;
+	}
 #pragma unroll
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
 		uint32_t idx = warp * kWarpKeys + i * 32 + lane;
 		bool ok = idx < count;
-		if (FIRST) ok = ok && ((mask[i] >> lane) & 1u);
-		key[i] = ok ? kin[idx] : 0xffffffffu;
+		if (FIRST) {
+			const uint32_t word = __shfl_sync(FULL_MASK, myWord, i);
+			ok = ok && ((word >> lane) & 1u);
+			if (!ok) key[i] = 0xffffffffu;
+		}
 		okBits |= (ok ? 1u : 0u) << i;
 	}
 	uint32_t *cnt = sCnt + warp * 256;
