@@ -213,6 +213,48 @@ def test_sorted_small_effects_one_cta_path(oracle_port):
         ctx.close()
 
 
+def test_render_batch_matches_per_system_render():
+    """sprRenderMainBatch is defined as sprRenderMain per system. 64 systems x 512 one-particle effects is above the
+    size where the batch's per-system passes run on several host threads: its draw records must be those of the
+    per-system calls on an identically built second context, field for field."""
+    from tests_render_args import make_render_args as fixed_camera_args
+    P = _particles()
+    comp = abi.make_component(timeStep=1 / 60, burstAmount=1, spawnTime=1e9, lifeTime=1e9, updateRadius=1.0)
+    comp2 = abi.make_component(timeStep=1 / 60, burstAmount=2, spawnTime=1e9, lifeTime=1e9, renderOrder=3)
+    ra = fixed_camera_args()
+    for k in range(4):  # an all-inclusive frustum
+        for pl in range(4):
+            ra.frustum.side[k][pl] = 1.0 if k == 3 else 0.0
+            ra.frustum.caps[k][pl] = 1.0 if k == 3 else 0.0
+    ctxs = [P.ParticleContext(initial_slot_capacity=1 << 16) for _ in range(2)]
+    try:
+        built = []
+        for ctx in ctxs:
+            rng = np.random.default_rng(3)
+            systems, ids = [], []
+            for i in range(64):
+                s = ctx.create_system((1, 2 + i, 3, 4))
+                my = [s.add_effect(comp if (e + i) % 5 else comp2, abi.make_transform(tuple(float(x) for x in rng.uniform(-30, 30, 3)))) for e in range(512)]
+                systems.append(s); ids.append(my)
+            fa = abi.make_frame_args(0.02, game_time=0.0, frame_index=0, camera=CAMERA)
+            ctx.update_batch(systems, ids, fa)
+            built.append((systems, ids))
+        (sa, ia), (sb, ib) = built
+        batch = ctxs[0].make_batch(sa, ia)
+        for frame in range(2):   # the second frame exercises the upload ring bookkeeping (uploadFrameIndex)
+            outs = ctxs[0].render_prepared(batch, ra)
+            for i in range(64):
+                recs, nsorted = sb[i].render(ib[i], ra)
+                assert outs[i].numRecords == len(recs) == 512 and outs[i].numSortedEffects == nsorted
+                got = bytes(C.string_at(outs[i].records, C.sizeof(abi.DrawRecord) * len(recs)))
+                want = b"".join(bytes(r) for r in recs)
+                # vertexByteOffset is a position in each context's own pool; both contexts were built identically
+                assert got == want, "system %d frame %d" % (i, frame)
+    finally:
+        for ctx in ctxs:
+            ctx.close()
+
+
 def test_many_systems_one_launch_set(oracle_port):
     """sprUpdateParticlesBatch: 24 independent systems (own RNG each, seed[1] = 2 + i) advance in one
     set of launches and each matches its own oracle instance."""
