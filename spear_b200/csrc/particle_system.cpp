@@ -333,22 +333,108 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	uint32_t numPlans = 0, maxSub = 0, burstBlocks = 0;
 	const uint32_t thisStamp = frameStamp + 1; // the stamp this frame gets if it simulates anything
 	float camera[3] = { 0, 0, 0 };
-	for (uint32_t r = 0; r < numReqs; r++) {
-		ParticleSystem *sys = reqs[r].system;
-		const SprFrameArgs &args = *reqs[r].args;
-		camera[0] = args.cameraPosition.x; camera[1] = args.cameraPosition.y; camera[2] = args.cameraPosition.z;
-		float clampedDt = args.dt < 0.1f ? args.dt : 0.1f; // sf::min(args.dt, 0.1f), :810
-		SystemWork sw = { sys->systemIdx, (uint32_t)entries.size(), reqs[r].numActive, 0 };
-		for (uint32_t i = 0; i < reqs[r].numActive; i++) {
-			HostEffect &E = sys->effects[reqs[r].activeIds[i]];
-			E.lastUpdateTime = args.gameTime;                // :814
-			E.timeDelta += clampedDt;                        // :816
-			uint32_t nsub = 0;
-			while (E.timeDelta >= E.timeStep) { nsub++; E.timeDelta -= E.timeStep; } // :817-820
-			ActiveEntry ae = { E.global, nsub, numPlans, 0 };
-			numPlans += nsub;
-			if (nsub > maxSub) maxSub = nsub;
-			if (nsub) {
+	if (numReqs) {
+		const SprFrameArgs &last = *reqs[numReqs - 1].args; // (every request overwrote the camera: the last one stands)
+		camera[0] = last.cameraPosition.x; camera[1] = last.cameraPosition.y; camera[2] = last.cameraPosition.z;
+	}
+	entries.resize(totalActive);
+	work.resize(numReqs);
+	{
+		uint32_t first = 0;
+		for (uint32_t r = 0; r < numReqs; r++) {
+			work[r] = { reqs[r].system->systemIdx, first, reqs[r].numActive, 0 };
+			first += reqs[r].numActive;
+		}
+	}
+
+	// Phase 1, per effect and touching nothing but the effect itself: timeDelta accumulation and the sub-step count
+	// (:814-820), the frame's ActiveEntry, and -- for an effect whose slot range is final and whose burst is small --
+	// the rest of its bookkeeping. Effects that may have to grow, own more granules, read the slot mirror or take the
+	// wide burst kernel are only noted here and finished in phase 2, in request order, on the calling thread.
+	// Requests are whole systems, so a large frame (C5: 100k effects in 1000 systems) splits phase 1 over a few host
+	// threads by contiguous request ranges; SPR_UPDATE_THREADS=1 keeps it on the calling thread.
+	struct Slow { uint32_t entry; uint32_t req; HostEffect *E; };
+	struct Part { std::vector<Slow> slow; uint64_t simSteps = 0; uint32_t maxSub = 0; };
+	auto phase1 = [&](uint32_t r0, uint32_t r1, Part &part) {
+		for (uint32_t r = r0; r < r1; r++) {
+			ParticleSystem *sys = reqs[r].system;
+			const SprFrameArgs &args = *reqs[r].args;
+			const float clampedDt = args.dt < 0.1f ? args.dt : 0.1f; // sf::min(args.dt, 0.1f), :810
+			ActiveEntry *out = entries.data() + work[r].firstActive;
+			for (uint32_t i = 0; i < reqs[r].numActive; i++) {
+				HostEffect &E = sys->effects[reqs[r].activeIds[i]];
+				E.lastUpdateTime = args.gameTime;                // :814
+				E.timeDelta += clampedDt;                        // :816
+				uint32_t nsub = 0;
+				while (E.timeDelta >= E.timeStep) { nsub++; E.timeDelta -= E.timeStep; } // :817-820
+				out[i] = { E.global, nsub, 0, 0 };
+				if (!nsub) continue;
+				if (nsub > part.maxSub) part.maxSub = nsub;
+				const HostType &type = sys->types[E.typeId];
+				if (!E.capacityFinal || (E.firstEmit && type.comp->burstAmount > 1024)) {
+					part.slow.push_back({ work[r].firstActive + i, r, &E });
+					continue;
+				}
+				E.firstEmit = false;
+				E.simSteps += nsub;
+				part.simSteps += nsub;
+				E.uploadFrameIndex = 0;                          // :679
+				if (type.comp->localSpace) E.boundsToWorld = E.particlesToWorld; // gpuBounds uses the matrix of the simulated step (:675-677)
+			}
+		}
+	};
+	static const uint32_t maxUpdateThreads = [] {
+		if (const char *e = getenv("SPR_UPDATE_THREADS")) { int v = atoi(e); return (uint32_t)(v < 1 ? 1 : v > 64 ? 64 : v); }
+		unsigned hw = std::thread::hardware_concurrency();
+		return hw >= 8 ? 4u : 1u;
+	}();
+	uint32_t nt = (totalActive >= 32768 && numReqs >= 64) ? maxUpdateThreads : 1;
+	if (nt > 1) {
+		// a system named by two requests would be touched by two threads: such a frame stays on one thread
+		const uint64_t stamp = ++batchStamp;
+		for (uint32_t r = 0; r < numReqs && nt > 1; r++) {
+			if (reqs[r].system->batchStamp == stamp) nt = 1;
+			reqs[r].system->batchStamp = stamp;
+		}
+	}
+	std::vector<Part> parts(nt);
+	if (nt <= 1) {
+		phase1(0, numReqs, parts[0]);
+	} else {
+		// contiguous request ranges of about equal effect counts, so that the parts' slow lists concatenate in request order
+		std::vector<uint32_t> cut(nt + 1, numReqs);
+		cut[0] = 0;
+		{
+			size_t seen = 0; uint32_t t = 1;
+			for (uint32_t r = 0; r < numReqs && t < nt; r++) {
+				seen += reqs[r].numActive;
+				if (seen * nt >= totalActive * t) cut[t++] = r + 1;
+			}
+		}
+		std::exception_ptr failure;
+		std::mutex failureLock;
+		auto run = [&](uint32_t t) {
+			try { phase1(cut[t], cut[t + 1], parts[t]); }
+			catch (...) { std::lock_guard<std::mutex> lock(failureLock); if (!failure) failure = std::current_exception(); }
+		};
+		std::vector<std::thread> helpers;
+		helpers.reserve(nt - 1);
+		for (uint32_t t = 1; t < nt; t++) helpers.emplace_back(run, t);
+		run(0);
+		for (std::thread &th : helpers) th.join();
+		if (failure) std::rethrow_exception(failure);
+	}
+
+	// Phase 2: everything that touches the context (ranges, granule ownership, the slot mirror, burst jobs), in request order
+	for (Part &part : parts) {
+		totalSimSteps += part.simSteps;
+		if (part.maxSub > maxSub) maxSub = part.maxSub;
+		for (const Slow &sl : part.slow) {
+			ParticleSystem *sys = reqs[sl.req].system;
+			HostEffect &E = *sl.E;
+			ActiveEntry &ae = entries[sl.entry];
+			const uint32_t nsub = ae.numSubsteps;
+			{
 				const HostType &type = sys->types[E.typeId];
 				uint32_t burst = E.firstEmit ? type.comp->burstAmount : 0;
 				// <= 20 timer spawns per sub-step (:478), each sub-step rounds up to one Particle4
@@ -385,7 +471,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				if (burst > 1024) {
 					ae.flags |= 1u;
 					uint32_t blocks = (burst + 255) / 256;
-					burstJobs.push_back({ (uint32_t)entries.size(), burstBlocks, blocks, 0 });
+					burstJobs.push_back({ sl.entry, burstBlocks, blocks, 0 });
 					burstBlocks += blocks;
 				}
 				E.firstEmit = false;
@@ -394,10 +480,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				E.uploadFrameIndex = 0;                      // :679
 				if (type.comp->localSpace) E.boundsToWorld = E.particlesToWorld; // gpuBounds uses the matrix of the simulated step (:675-677)
 			}
-			entries.push_back(ae);
 		}
-		work.push_back(sw);
 	}
+	// Phase 3: plan records are numbered in entry order
+	for (ActiveEntry &ae : entries) { ae.planBase = numPlans; numPlans += ae.numSubsteps; }
 	if (!resolve.empty()) {
 		// the conservative bound ran out: read the exact slot counts back (rare) and grow if needed
 		std::vector<RenderGather> got(resolve.size());

@@ -130,6 +130,7 @@ struct ParticleSystem {
 	uint64_t bufferFrameIndex;                // :263
 	std::vector<SprDrawRecord> drawRecords;
 	std::vector<SortedEffect> sortedScratch;  // renderMain's sort array, kept between frames
+	uint64_t batchStamp = 0;                  // Context::update: the last call that named this system
 
 	ParticleSystem(Context *ctx, const SprSystemsDesc &desc); // :265-267
 	~ParticleSystem();
@@ -229,6 +230,7 @@ struct Context {
 	std::vector<SortTile> scratchSortTiles;
 	std::vector<EffectParams> scratchParamVals;
 	int updateDepth = 0;
+	uint64_t batchStamp = 0;           // numbers the update calls that look for a system named twice
 	// ---- per-frame staging
 	PinnedArray<uint8_t> stagingH[2];
 	DeviceArray<uint8_t> stagingD;

@@ -213,6 +213,41 @@ def test_sorted_small_effects_one_cta_path(oracle_port):
         ctx.close()
 
 
+def test_large_batch_host_threads_match_oracle(oracle_port):
+    """A frame of 64 systems x 512 effects is above the size where sprUpdateParticlesBatch splits its per-effect host
+    pass over several threads (contiguous request ranges). Mostly short-lived effects whose slot range is final
+    (finished on the worker threads), with growing and bursting effects in between (noted by the workers, finished
+    in request order on the calling thread): RNG state of every system, and full snapshots of every 8th, against
+    one oracle instance per system."""
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 18)
+    try:
+        comps = [S.comp_c5(), S.comp_fountain(), S.comp_c2(1, burst=1500, churn=True)]
+        systems, oracles, ids = [], [], []
+        for i in range(64):
+            seed = (1, 500 + i, 3, 4)
+            s, o = ctx.create_system(seed), orc.OracleSystem(oracle_port, seed)
+            my = []
+            for e in range(512):
+                comp = comps[0] if (e + i) % 37 else comps[1 + (e & 1)]
+                tr = abi.make_transform((i * 0.5, (e & 15) * 0.25, e * 0.01))
+                e1, e2 = s.add_effect(comp, tr), o.add_effect(comp, tr)
+                assert e1 == e2
+                my.append(e1)
+            systems.append(s); oracles.append(o); ids.append(my)
+        for frame in range(5):
+            fa = abi.make_frame_args(0.0172, game_time=frame * 0.0172, frame_index=frame)
+            ctx.update_batch(systems, ids, fa)
+            for o, my in zip(oracles, ids):
+                o.update(my, fa)
+        for i, (s, o, my) in enumerate(zip(systems, oracles, ids)):
+            assert s.rng_state() == o.rng_state(), "system %d rng" % i
+            if i % 8 == 0:
+                S.assert_snapshots_equal(S.snapshot(o, my), S.snapshot(s, my), "system %d" % i)
+    finally:
+        ctx.close()
+
+
 def test_render_batch_matches_per_system_render():
     """sprRenderMainBatch is defined as sprRenderMain per system. 64 systems x 512 one-particle effects is above the
     size where the batch's per-system passes run on several host threads: its draw records must be those of the
