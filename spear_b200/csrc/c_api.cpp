@@ -222,7 +222,7 @@ SPR_API int sprGetEffectInfo(SprSystem *sys, uint32_t effectId, SprEffectInfo *o
 		out->stopEmit = (g.stopEmit || E.hostStopEmit) ? 1 : 0;
 		out->firstEmit = (uint8_t)g.firstEmit;
 		out->instantDelete = E.instantDelete ? 1 : 0;
-		out->gpuBounds = boundsFromGather(g, sys->sys.types[E.typeId], E);
+		out->gpuBounds = boundsFromGather(g, sys->sys.types[E.typeId], sys->sys.effectsCold[effectId]);
 		out->lastUpdateTime = E.lastUpdateTime;
 		out->simSteps = E.simSteps;
 	});

@@ -327,7 +327,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	entries.clear(); work.clear(); burstJobs.clear();
 	entries.reserve(totalActive);
 	work.reserve(numReqs);
-	struct Resolve { HostEffect *E; uint32_t add; };
+	struct Resolve { HostEffect *E; HostEffectCold *C; uint32_t add; };
 	std::vector<Resolve> resolve;
 	std::vector<uint32_t> resolveGlobals;
 	uint32_t numPlans = 0, maxSub = 0, burstBlocks = 0;
@@ -351,9 +351,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	// (:814-820), the frame's ActiveEntry, and -- for an effect whose slot range is final and whose burst is small --
 	// the rest of its bookkeeping. Effects that may have to grow, own more granules, read the slot mirror or take the
 	// wide burst kernel are only noted here and finished in phase 2, in request order, on the calling thread.
-	// Requests are whole systems, so a large frame (C5: 100k effects in 1000 systems) splits phase 1 over a few host
-	// threads by contiguous request ranges; SPR_UPDATE_THREADS=1 keeps it on the calling thread.
-	struct Slow { uint32_t entry; uint32_t req; HostEffect *E; };
+	struct Slow { uint32_t entry; uint32_t req; HostEffect *E; HostEffectCold *C; };
 	struct Part { std::vector<Slow> slow; uint64_t simSteps = 0; uint32_t maxSub = 0; };
 	auto phase1 = [&](uint32_t r0, uint32_t r1, Part &part) {
 		for (uint32_t r = r0; r < r1; r++) {
@@ -372,58 +370,22 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				if (nsub > part.maxSub) part.maxSub = nsub;
 				const HostType &type = sys->types[E.typeId];
 				if (!E.capacityFinal || (E.firstEmit && type.comp->burstAmount > 1024)) {
-					part.slow.push_back({ work[r].firstActive + i, r, &E });
+					part.slow.push_back({ work[r].firstActive + i, r, &E, &sys->effectsCold[reqs[r].activeIds[i]] });
 					continue;
 				}
 				E.firstEmit = false;
 				E.simSteps += nsub;
 				part.simSteps += nsub;
 				E.uploadFrameIndex = 0;                          // :679
-				if (type.comp->localSpace) E.boundsToWorld = E.particlesToWorld; // gpuBounds uses the matrix of the simulated step (:675-677)
+				if (type.comp->localSpace) { HostEffectCold &C = sys->effectsCold[reqs[r].activeIds[i]]; C.boundsToWorld = C.particlesToWorld; } // gpuBounds uses the matrix of the simulated step (:675-677)
 			}
 		}
 	};
-	static const uint32_t maxUpdateThreads = [] {
-		if (const char *e = getenv("SPR_UPDATE_THREADS")) { int v = atoi(e); return (uint32_t)(v < 1 ? 1 : v > 64 ? 64 : v); }
-		unsigned hw = std::thread::hardware_concurrency();
-		return hw >= 8 ? 4u : 1u;
-	}();
-	uint32_t nt = (totalActive >= 32768 && numReqs >= 64) ? maxUpdateThreads : 1;
-	if (nt > 1) {
-		// a system named by two requests would be touched by two threads: such a frame stays on one thread
-		const uint64_t stamp = ++batchStamp;
-		for (uint32_t r = 0; r < numReqs && nt > 1; r++) {
-			if (reqs[r].system->batchStamp == stamp) nt = 1;
-			reqs[r].system->batchStamp = stamp;
-		}
-	}
-	std::vector<Part> parts(nt);
-	if (nt <= 1) {
-		phase1(0, numReqs, parts[0]);
-	} else {
-		// contiguous request ranges of about equal effect counts, so that the parts' slow lists concatenate in request order
-		std::vector<uint32_t> cut(nt + 1, numReqs);
-		cut[0] = 0;
-		{
-			size_t seen = 0; uint32_t t = 1;
-			for (uint32_t r = 0; r < numReqs && t < nt; r++) {
-				seen += reqs[r].numActive;
-				if (seen * nt >= totalActive * t) cut[t++] = r + 1;
-			}
-		}
-		std::exception_ptr failure;
-		std::mutex failureLock;
-		auto run = [&](uint32_t t) {
-			try { phase1(cut[t], cut[t + 1], parts[t]); }
-			catch (...) { std::lock_guard<std::mutex> lock(failureLock); if (!failure) failure = std::current_exception(); }
-		};
-		std::vector<std::thread> helpers;
-		helpers.reserve(nt - 1);
-		for (uint32_t t = 1; t < nt; t++) helpers.emplace_back(run, t);
-		run(0);
-		for (std::thread &th : helpers) th.join();
-		if (failure) std::rethrow_exception(failure);
-	}
+	// (phase 1 on several host threads, by contiguous request ranges, was measured on the 100k-effect C5 frame: 0.90 ->
+	// 0.75 ms with 4 threads, no gain in the step once the threads' start-up is paid -- the pass streams the effect
+	// mirror through one core at memory speed, so the mirror was split into a 48-byte hot half instead)
+	std::vector<Part> parts(1);
+	phase1(0, numReqs, parts[0]);
 
 	// Phase 2: everything that touches the context (ranges, granule ownership, the slot mirror, burst jobs), in request order
 	for (Part &part : parts) {
@@ -432,6 +394,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		for (const Slow &sl : part.slow) {
 			ParticleSystem *sys = reqs[sl.req].system;
 			HostEffect &E = *sl.E;
+			HostEffectCold &C = *sl.C;
 			ActiveEntry &ae = entries[sl.entry];
 			const uint32_t nsub = ae.numSubsteps;
 			{
@@ -445,27 +408,27 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 					// entry only means more allowances are added on top of it)
 					const unsigned long long m = ((volatile const unsigned long long*)slotMirror)[E.global];
 					const uint32_t mStamp = (uint32_t)(m >> 32);
-					if (mStamp > E.createdStamp && mStamp >= E.evictedStamp) {
+					if (mStamp > C.createdStamp && mStamp >= C.evictedStamp) {
 						uint64_t tight = (uint32_t)m;
-						for (uint32_t k = 0; k < E.recentCount; k++) if (E.recent[k].stamp > mStamp) tight += E.recent[k].add;
-						if (tight < E.slotUpperBound) E.slotUpperBound = (uint32_t)tight;
+						for (uint32_t k = 0; k < C.recentCount; k++) if (C.recent[k].stamp > mStamp) tight += C.recent[k].add;
+						if (tight < C.slotUpperBound) C.slotUpperBound = (uint32_t)tight;
 					}
-					if (E.recentCount == 4) {
-						E.evictedStamp = E.recent[0].stamp;
-						E.recent[0] = E.recent[1]; E.recent[1] = E.recent[2]; E.recent[2] = E.recent[3];
-						E.recentCount = 3;
+					if (C.recentCount == 4) {
+						C.evictedStamp = C.recent[0].stamp;
+						C.recent[0] = C.recent[1]; C.recent[1] = C.recent[2]; C.recent[2] = C.recent[3];
+						C.recentCount = 3;
 					}
-					E.recent[E.recentCount].stamp = thisStamp;
-					E.recent[E.recentCount].add = add > 0xffffffffull ? 0xffffffffu : (uint32_t)add;
-					E.recentCount++;
+					C.recent[C.recentCount].stamp = thisStamp;
+					C.recent[C.recentCount].add = add > 0xffffffffull ? 0xffffffffu : (uint32_t)add;
+					C.recentCount++;
 				}
-				uint64_t need = (uint64_t)E.slotUpperBound + add;
+				uint64_t need = (uint64_t)C.slotUpperBound + add;
 				if (need > slotCapacityOf[E.global]) {
-					if (E.simSteps == 0) { growEffect(E.global, pow2ceil(need), false); E.slotUpperBound = (uint32_t)need; ensureOwned(E.global, E.slotUpperBound); }
-					else { resolve.push_back({ &E, (uint32_t)add }); resolveGlobals.push_back(E.global); }
+					if (E.simSteps == 0) { growEffect(E.global, pow2ceil(need), false); C.slotUpperBound = (uint32_t)need; ensureOwned(E.global, C.slotUpperBound); }
+					else { resolve.push_back({ &E, &C, (uint32_t)add }); resolveGlobals.push_back(E.global); }
 				} else {
-					E.slotUpperBound = (uint32_t)need;
-					ensureOwned(E.global, E.slotUpperBound);
+					C.slotUpperBound = (uint32_t)need;
+					ensureOwned(E.global, C.slotUpperBound);
 				}
 				} // !capacityFinal
 				if (burst > 1024) {
@@ -478,7 +441,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				E.simSteps += nsub;
 				totalSimSteps += nsub;
 				E.uploadFrameIndex = 0;                      // :679
-				if (type.comp->localSpace) E.boundsToWorld = E.particlesToWorld; // gpuBounds uses the matrix of the simulated step (:675-677)
+				if (type.comp->localSpace) C.boundsToWorld = C.particlesToWorld; // gpuBounds uses the matrix of the simulated step (:675-677)
 			}
 		}
 	}
@@ -490,14 +453,15 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		gatherEffects(resolveGlobals.data(), (uint32_t)resolve.size(), got.data());
 		for (size_t i = 0; i < resolve.size(); i++) {
 			HostEffect &E = *resolve[i].E;
+			HostEffectCold &C = *resolve[i].C;
 			uint64_t need = (uint64_t)got[i].slotCount + resolve[i].add;
 			if (need > hParams[E.global].slotCapacity) growEffect(E.global, pow2ceil(need * 2), true);
-			E.slotUpperBound = (uint32_t)need;
+			C.slotUpperBound = (uint32_t)need;
 			// the count just read is exact up to the last submitted frame: only this frame's allowance stays pending
-			E.recent[0] = E.recent[E.recentCount - 1];
-			E.recentCount = 1;
-			E.evictedStamp = frameStamp;
-			ensureOwned(E.global, E.slotUpperBound);
+			C.recent[0] = C.recent[C.recentCount - 1];
+			C.recentCount = 1;
+			C.evictedStamp = frameStamp;
+			ensureOwned(E.global, C.slotUpperBound);
 		}
 	}
 
@@ -817,23 +781,25 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 	(void)entityId; (void)componentIndex;
 	uint32_t effectId;
 	if (!freeEffectIds.empty()) { effectId = freeEffectIds.back(); freeEffectIds.pop_back(); }
-	else { effectId = (uint32_t)effects.size(); effects.emplace_back(); }
+	else { effectId = (uint32_t)effects.size(); effects.emplace_back(); effectsCold.emplace_back(); }
 
 	uint32_t typeId = reserveEffectType(c);
 	const HostType &type = types[typeId];
 
 	HostEffect &E = effects[effectId];
+	HostEffectCold &C = effectsCold[effectId];
 	E = HostEffect();
+	C = HostEffectCold();
 	E.inUse = true;
 	E.typeId = typeId;
 	E.timeStep = type.timeStep * (1.0f + initRng.nextFloat() * 0.1f);   // :744
-	E.origin = transform.position;
+	C.origin = transform.position;
 	E.instantDelete = c->instantDelete != 0;
-	E.particlesToWorld = identity34();
-	E.boundsToWorld = identity34();
+	C.particlesToWorld = identity34();
+	C.boundsToWorld = identity34();
 	E.uploadFrameIndex = ctx->maxParticleCacheFrames;
 	E.global = ctx->allocEffectGlobal();
-	E.createdStamp = ctx->frameStamp; // mirror entries up to this frame belong to whoever had the index before
+	C.createdStamp = ctx->frameStamp; // mirror entries up to this frame belong to whoever had the index before
 
 	EffectParams &P = ctx->hParams[E.global];
 	memset(&P, 0, sizeof(P));
@@ -849,7 +815,7 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 	SprMat34 entityToWorld = transformToMatrix(transform);
 	if (c->localSpace) {                                                  // :755-760
 		writeColMajor44(identity34(), P.emitterToWorld);
-		E.particlesToWorld = entityToWorld;
+		C.particlesToWorld = entityToWorld;
 	} else {
 		writeColMajor44(entityToWorld, P.emitterToWorld);
 	}
@@ -874,8 +840,8 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 			const uint32_t cap = ctx->slotCapacityOf[E.global];
 			if (bound <= (double)cap && (cap <= kTileSlots || 20.0 * steps + 8.0 <= (double)kTileSlots)) {
 				E.capacityFinal = true;
-				E.slotUpperBound = (uint32_t)bound;
-				ctx->ensureOwned(E.global, E.slotUpperBound);
+				C.slotUpperBound = (uint32_t)bound;
+				ctx->ensureOwned(E.global, C.slotUpperBound);
 			}
 		}
 	}
@@ -892,14 +858,15 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 void ParticleSystem::updateTransform(uint32_t effectId, const SprTransformUpdate &update)
 {
 	HostEffect &E = effects[effectId];
+	HostEffectCold &C = effectsCold[effectId];
 	const HostType &type = types[E.typeId];
 	EffectParams &P = ctx->hParams[E.global];
 	if (type.comp->localSpace) {
-		E.particlesToWorld = update.entityToWorld;
+		C.particlesToWorld = update.entityToWorld;
 	} else {
 		writeColMajor44(update.entityToWorld, P.emitterToWorld);
 	}
-	E.origin = update.transform.position;
+	C.origin = update.transform.position;
 	// updateSphereArea(areaId, { position, type.updateRadius }), :782-783
 	P.areaSphere[0] = update.transform.position.x; P.areaSphere[1] = update.transform.position.y; P.areaSphere[2] = update.transform.position.z;
 	P.areaSphere[3] = type.comp->updateRadius;
@@ -945,7 +912,7 @@ void ParticleSystem::updateParticles(const uint32_t *activeIds, uint32_t numActi
 	ctx->update(&req, 1);
 }
 
-SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const HostEffect &E)
+SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const HostEffectCold &C)
 {
 	// :672-677
 	SprBounds3 b;
@@ -955,7 +922,7 @@ SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const H
 	b.extent.x = (g.boundsMax[0] - g.boundsMin[0]) * 0.5f + type.comp->cullPadding;
 	b.extent.y = (g.boundsMax[1] - g.boundsMin[1]) * 0.5f + type.comp->cullPadding;
 	b.extent.z = (g.boundsMax[2] - g.boundsMin[2]) * 0.5f + type.comp->cullPadding;
-	if (type.comp->localSpace) b = transformBounds(E.boundsToWorld, b);
+	if (type.comp->localSpace) b = transformBounds(C.boundsToWorld, b);
 	return b;
 }
 
@@ -1046,11 +1013,12 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 		const HostType &type = types[E.typeId];
 		uint32_t numParticles = got[i].aliveCount;
 		if (numParticles == 0) continue;
-		if (!frustumIntersects(args.frustum, boundsFromGather(got[i], type, E))) continue;
+		if (!frustumIntersects(args.frustum, boundsFromGather(got[i], type, effectsCold[effectId]))) continue;
 		SortedEffect s;
 		s.renderOrder = type.renderOrder;
 		s.tiebreaker = type.tiebreaker;
-		float dx = args.cameraPosition.x - E.origin.x, dy = args.cameraPosition.y - E.origin.y, dz = args.cameraPosition.z - E.origin.z;
+		const HostEffectCold &C = effectsCold[effectId];
+		float dx = args.cameraPosition.x - C.origin.x, dy = args.cameraPosition.y - C.origin.y, dz = args.cameraPosition.z - C.origin.z;
 		s.depth = dx*dx + dy*dy + dz*dz;                                  // sf::lengthSq, :844
 		s.effectId = effectId;
 		s.numParticles = numParticles;
@@ -1075,7 +1043,7 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 		r.typeId = E.typeId;
 		r.numParticles = numParticles;
 		r.vertexByteOffset = (uint64_t)ctx->hParams[E.global].slotBase * 128ull;
-		writeColMajor44(E.particlesToWorld, r.instanceUbo.u_ParticleToWorld); // :871-876
+		writeColMajor44(effectsCold[s.effectId].particlesToWorld, r.instanceUbo.u_ParticleToWorld); // :871-876
 		memcpy(r.instanceUbo.u_WorldToClip, args.worldToClip.v, sizeof(float) * 16);
 		r.instanceUbo.u_Aspect = aspect;
 		r.instanceUbo.u_InvDelta = E.timeStep - E.timeDelta;

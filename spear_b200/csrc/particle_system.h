@@ -62,10 +62,11 @@ struct PinnedArray {
 	}
 };
 
-// Host mirror of one effect (ParticleSystemImp::Effect, ParticleSystem.cpp:186-218). The fields the per-frame
-// pass of Context::update touches come first, so that a frame costs two cache lines per effect, not four.
+// Host mirror of one effect (ParticleSystemImp::Effect, ParticleSystem.cpp:186-218), split in two parallel arrays.
+// HostEffect holds what the per-frame pass of Context::update reads and writes for EVERY active effect (48 bytes: a
+// 100k-effect frame streams 5 MB through the host instead of the 21 MB of the whole mirror); HostEffectCold holds the
+// capacity bookkeeping (only effects that can still grow) and the transforms (render, updateTransform, localSpace bounds).
 struct HostEffect {
-	// ---- hot: read / written for every active effect every frame
 	uint32_t typeId = 0;          // system-local
 	uint32_t global = 0;          // context-wide effect index
 	float timeDelta = 0.0f;
@@ -73,6 +74,14 @@ struct HostEffect {
 	double lastUpdateTime = 0.0;
 	uint64_t simSteps = 0;
 	uint64_t uploadFrameIndex = 16;
+	bool firstEmit = true;        // host view: no sub-step simulated yet
+	bool inUse = false;
+	bool hostStopEmit = false;
+	bool instantDelete = false;
+	bool capacityFinal = false;   // the slot count provably never exceeds the bound fixed at addEffect: no per-frame capacity bookkeeping
+};
+
+struct HostEffectCold {
 	uint32_t slotUpperBound = 0;  // conservative bound of particles.size*4
 	// The device mirrors the exact slot count of every simulated effect to pinned host memory at the end of each
 	// frame (Context::slotMirror). The bound is re-based on the newest mirrored count plus the growth allowance of
@@ -82,12 +91,6 @@ struct HostEffect {
 	uint32_t evictedStamp = 0;    // newest frame whose allowance is no longer in `recent`
 	uint32_t recentCount = 0;
 	struct { uint32_t stamp, add; } recent[4] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } }; // allowances of the last simulated frames
-	bool firstEmit = true;        // host view: no sub-step simulated yet
-	bool inUse = false;
-	bool hostStopEmit = false;
-	bool instantDelete = false;
-	bool capacityFinal = false;   // the slot count provably never exceeds the bound fixed at addEffect: no per-frame capacity bookkeeping
-	// ---- cold: transforms (render, updateTransform, localSpace bounds)
 	SprVec3 origin = { 0, 0, 0 };
 	SprMat34 particlesToWorld;
 	SprMat34 boundsToWorld;       // particlesToWorld at the last simulated step (gpuBounds, :675-677)
@@ -122,7 +125,8 @@ struct ParticleSystem {
 	Context *ctx;
 	uint32_t systemIdx;           // context-wide
 	HostRng initRng;              // :250
-	std::vector<HostEffect> effects;          // :241
+	std::vector<HostEffect> effects;          // :241 (hot half)
+	std::vector<HostEffectCold> effectsCold;  // :241 (cold half, same index)
 	std::vector<uint32_t> freeEffectIds;      // :242
 	std::vector<HostType> types;              // :244
 	std::vector<uint32_t> freeTypeIds;        // :245
@@ -130,7 +134,6 @@ struct ParticleSystem {
 	uint64_t bufferFrameIndex;                // :263
 	std::vector<SprDrawRecord> drawRecords;
 	std::vector<SortedEffect> sortedScratch;  // renderMain's sort array, kept between frames
-	uint64_t batchStamp = 0;                  // Context::update: the last call that named this system
 
 	ParticleSystem(Context *ctx, const SprSystemsDesc &desc); // :265-267
 	~ParticleSystem();
@@ -152,7 +155,7 @@ struct ParticleSystem {
 	void releaseEffectTypeImp(uint32_t typeId);                        // :682-692
 };
 
-SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const HostEffect &E); // gpuBounds, :672-677
+SprBounds3 boundsFromGather(const RenderGather &g, const HostType &type, const HostEffectCold &C); // gpuBounds, :672-677
 
 struct UpdateRequest {
 	ParticleSystem *system;
@@ -230,7 +233,6 @@ struct Context {
 	std::vector<SortTile> scratchSortTiles;
 	std::vector<EffectParams> scratchParamVals;
 	int updateDepth = 0;
-	uint64_t batchStamp = 0;           // numbers the update calls that look for a system named twice
 	// ---- per-frame staging
 	PinnedArray<uint8_t> stagingH[2];
 	DeviceArray<uint8_t> stagingD;

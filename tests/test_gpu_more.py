@@ -213,12 +213,11 @@ def test_sorted_small_effects_one_cta_path(oracle_port):
         ctx.close()
 
 
-def test_large_batch_host_threads_match_oracle(oracle_port):
-    """A frame of 64 systems x 512 effects is above the size where sprUpdateParticlesBatch splits its per-effect host
-    pass over several threads (contiguous request ranges). Mostly short-lived effects whose slot range is final
-    (finished on the worker threads), with growing and bursting effects in between (noted by the workers, finished
-    in request order on the calling thread): RNG state of every system, and full snapshots of every 8th, against
-    one oracle instance per system."""
+def test_large_batch_matches_oracle(oracle_port):
+    """A frame of 64 systems x 512 effects through sprUpdateParticlesBatch: mostly short-lived effects whose slot range
+    is final (finished in the first phase of the host pass), with growing and bursting effects in between (noted
+    there, finished in request order in the second phase): RNG state of every system, and full snapshots of every
+    8th, against one oracle instance per system."""
     P = _particles()
     ctx = P.ParticleContext(initial_slot_capacity=1 << 18)
     try:
