@@ -185,9 +185,13 @@ def run_ours(args, rank, world):
 
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
+    json_fd = None
     if world > 1:
-        # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version line to the process's stdout (whatever NCCL_DEBUG_FILE says): from here on file
+        # descriptor 1 is stderr for every library in the process, and the one JSON line goes to the saved stdout
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.workload or ("c3" if world == 1 else "c4")
     wl = workload_components(name)
@@ -593,7 +597,11 @@ def run_ours(args, rank, world):
                                       "note": "same workload with SPR_CTX_SORT_PARTICLES off: update + compact + 4x billboard expansion in ascending slot order (the reference's own stream order)"}
             except Exception as ex:  # noqa: BLE001
                 out["stream_mode"] = {"error": str(ex)[:200]}
-        print(json.dumps(out))
+        if json_fd is None:
+            print(json.dumps(out))
+        else:
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 # ---------------------------------------------------------------------------
