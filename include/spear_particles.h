@@ -390,7 +390,9 @@ SPR_API int sprRenderMain(SprSystem *sys, const uint32_t *visibleIds, uint32_t n
 
 /* renderMain for many systems of one context with a single device read-back. Equivalent to
  * sprRenderMain(systems[i], visibleIds[i], numVisible[i], &args[i], &outs[i]) for every i;
- * pass argsStride = 0 when the RenderArgs are shared. */
+ * pass argsStride = 0 when the RenderArgs are shared. A batch of at least 32768 visible effects in at least 64
+ * systems builds its draw records on a few helper threads (joined before the call returns; SPR_RENDER_THREADS=1 in the
+ * environment keeps everything on the calling thread, and so does a batch that names a system twice). */
 SPR_API int sprRenderMainBatch(SprContext *ctx, SprSystem *const *systems, uint32_t numSystems,
 	const uint32_t *const *visibleIds, const uint32_t *numVisible,
 	const SprRenderArgs *args, size_t argsStride, SprRenderOutput *outs);

@@ -960,6 +960,14 @@ void Context::renderBatch(ParticleSystem *const *systems, uint32_t numSystems, c
 	const uint32_t kChunk = 16;
 	uint32_t nt = (total >= 32768 && numSystems >= 4 * kChunk) ? maxThreads : 1;
 	if (nt > (numSystems + kChunk - 1) / kChunk) nt = (numSystems + kChunk - 1) / kChunk;
+	if (nt > 1) {
+		// a system named twice would be written by two threads: such a batch stays on the calling thread
+		const uint64_t stamp = ++renderBatchStamp;
+		for (uint32_t s = 0; s < numSystems; s++) {
+			if (systems[s]->renderBatchStamp == stamp) { nt = 1; break; }
+			systems[s]->renderBatchStamp = stamp;
+		}
+	}
 	if (nt <= 1) {
 		size_t off = 0;
 		for (uint32_t s = 0; s < numSystems; s++) {

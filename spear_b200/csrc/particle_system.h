@@ -134,6 +134,7 @@ struct ParticleSystem {
 	uint64_t bufferFrameIndex;                // :263
 	std::vector<SprDrawRecord> drawRecords;
 	std::vector<SortedEffect> sortedScratch;  // renderMain's sort array, kept between frames
+	uint64_t renderBatchStamp = 0;            // Context::renderBatch: the last threaded batch that named this system
 
 	ParticleSystem(Context *ctx, const SprSystemsDesc &desc); // :265-267
 	~ParticleSystem();
@@ -233,6 +234,7 @@ struct Context {
 	std::vector<SortTile> scratchSortTiles;
 	std::vector<EffectParams> scratchParamVals;
 	int updateDepth = 0;
+	uint64_t renderBatchStamp = 0;     // numbers the threaded render batches (a system named twice keeps the batch on one thread)
 	// ---- per-frame staging
 	PinnedArray<uint8_t> stagingH[2];
 	DeviceArray<uint8_t> stagingD;
