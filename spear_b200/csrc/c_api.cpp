@@ -375,7 +375,7 @@ SPR_API int sprBillboardReadVertices(SprBillboardSystem *sys, SprBillboardVertex
 	REQUIRE(sys && (out || !capacityQuads));
 	return guarded([&] {
 		BillboardSystem &b = sys->sys;
-		uint32_t n = (uint32_t)b.atlasH.size();
+		uint32_t n = b.lastQuads;
 		if (outQuads) *outQuads = n;
 		uint32_t m = n < capacityQuads ? n : capacityQuads;
 		if (m) {

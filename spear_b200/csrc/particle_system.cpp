@@ -1153,22 +1153,52 @@ void BillboardSystem::add(const SprBillboard *billboards, uint32_t count)
 		if (pending) cudaFreeHost(pending);
 		pending = p; pendingCapacity = cap;
 	}
-	for (uint32_t i = 0; i < count; i++) {
-		const SprBillboard &b = billboards[i];
-		if (!b.sprite.atlas) continue;                                  // !sprite || !sprite->isLoaded(), :82, :100
-		BillboardDev &d = pending[pendingCount++];
-		d.atlas = b.sprite.atlas;
-		d.minVert[0] = b.sprite.minVert.x; d.minVert[1] = b.sprite.minVert.y;
-		d.maxVert[0] = b.sprite.maxVert.x; d.maxVert[1] = b.sprite.maxVert.y;
-		d.vertUvScale[0] = b.sprite.vertUvScale.x; d.vertUvScale[1] = b.sprite.vertUvScale.y;
-		d.vertUvBias[0] = b.sprite.vertUvBias.x; d.vertUvBias[1] = b.sprite.vertUvBias.y;
-		memcpy(d.transform, b.transform, sizeof(d.transform));
-		d.anchor[0] = b.anchor.x; d.anchor[1] = b.anchor.y;
-		d.color = packChannel(b.color.x) | packChannel(b.color.y) << 8 | packChannel(b.color.z) << 16 | packChannel(b.color.w) << 24; // :22-28
-		d.cropMin[0] = b.cropMin.x; d.cropMin[1] = b.cropMin.y;
-		d.cropMax[0] = b.cropMax.x; d.cropMax[1] = b.cropMax.y;
-		d.depth = b.depth;                                              // order.index = billboards.size - 1 = its position here, :95, :115
+	auto convert = [&](uint32_t i0, uint32_t i1, BillboardDev *dst) {
+		for (uint32_t i = i0; i < i1; i++) {
+			const SprBillboard &b = billboards[i];
+			if (!b.sprite.atlas) continue;                              // !sprite || !sprite->isLoaded(), :82, :100
+			BillboardDev &d = *dst++;
+			d.atlas = b.sprite.atlas;
+			d.minVert[0] = b.sprite.minVert.x; d.minVert[1] = b.sprite.minVert.y;
+			d.maxVert[0] = b.sprite.maxVert.x; d.maxVert[1] = b.sprite.maxVert.y;
+			d.vertUvScale[0] = b.sprite.vertUvScale.x; d.vertUvScale[1] = b.sprite.vertUvScale.y;
+			d.vertUvBias[0] = b.sprite.vertUvBias.x; d.vertUvBias[1] = b.sprite.vertUvBias.y;
+			memcpy(d.transform, b.transform, sizeof(d.transform));
+			d.anchor[0] = b.anchor.x; d.anchor[1] = b.anchor.y;
+			d.color = packChannel(b.color.x) | packChannel(b.color.y) << 8 | packChannel(b.color.z) << 16 | packChannel(b.color.w) << 24; // :22-28
+			d.cropMin[0] = b.cropMin.x; d.cropMin[1] = b.cropMin.y;
+			d.cropMax[0] = b.cropMax.x; d.cropMax[1] = b.cropMax.y;
+			d.depth = b.depth;                                          // order.index = billboards.size - 1 = its position here, :95, :115
+		}
+		return dst;
+	};
+	// A large call (the 1M-billboard frame: 220 MB through the host) is converted by a few threads: each counts the
+	// loaded sprites of its range, the counts give every range its place in the staging array, then the ranges are
+	// converted side by side -- the order of the billboards is the order of the call either way.
+	static const uint32_t maxThreads = [] {
+		if (const char *e = getenv("SPR_RENDER_THREADS")) { int v = atoi(e); return (uint32_t)(v < 1 ? 1 : v > 64 ? 64 : v); }
+		unsigned hw = std::thread::hardware_concurrency();
+		return hw >= 16 ? 8u : hw >= 8 ? 4u : 1u;
+	}();
+	const uint32_t nt = count >= 65536 ? maxThreads : 1;
+	if (nt <= 1) {
+		pendingCount = (size_t)(convert(0, count, pending + pendingCount) - pending);
+		return;
 	}
+	std::vector<uint32_t> cut(nt + 1), valid(nt, 0);
+	for (uint32_t t = 0; t <= nt; t++) cut[t] = (uint32_t)((uint64_t)count * t / nt);
+	auto run = [&](auto &&fn) {
+		std::vector<std::thread> helpers;
+		helpers.reserve(nt - 1);
+		for (uint32_t t = 1; t < nt; t++) helpers.emplace_back(fn, t);
+		fn(0u);
+		for (std::thread &th : helpers) th.join();
+	};
+	run([&](uint32_t t) { uint32_t v = 0; for (uint32_t i = cut[t]; i < cut[t + 1]; i++) v += billboards[i].sprite.atlas != 0; valid[t] = v; });
+	std::vector<size_t> first(nt + 1, pendingCount);
+	for (uint32_t t = 0; t < nt; t++) first[t + 1] = first[t] + valid[t];
+	run([&](uint32_t t) { convert(cut[t], cut[t + 1], pending + first[t]); });
+	pendingCount = first[nt];
 }
 
 void BillboardSystem::renderMain(const SprRenderArgs &args, SprBillboardOutput &out)
@@ -1177,7 +1207,7 @@ void BillboardSystem::renderMain(const SprRenderArgs &args, SprBillboardOutput &
 	memset(&out, 0, sizeof(out));
 	memcpy(out.worldToClip, args.worldToClip.v, sizeof(out.worldToClip));   // :208-209
 	draws.clear();
-	atlasH.clear();
+	lastQuads = 0;
 	if (pendingCount > 0xffffffffull) throw std::runtime_error("more than 2^32 billboards in one frame");
 	const uint32_t n = (uint32_t)pendingCount;
 	if (!n) return;
@@ -1200,15 +1230,17 @@ void BillboardSystem::renderMain(const SprRenderArgs &args, SprBillboardOutput &
 	uint32_t total = 0;
 	SPR_CUDA(cudaMemcpyAsync(&total, dTotal.ptr, sizeof(total), cudaMemcpyDeviceToHost, st));
 	SPR_CUDA(cudaStreamSynchronize(st));
-	atlasH.resize(total);
+	atlasPinned.reserve(total ? total : 1);
 	if (total) {
-		SPR_CUDA(cudaMemcpyAsync(atlasH.data(), dAtlas.ptr, (size_t)total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		SPR_CUDA(cudaMemcpyAsync(atlasPinned.ptr, dAtlas.ptr, (size_t)total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 		SPR_CUDA(cudaStreamSynchronize(st));
 	}
+	const unsigned long long *atlasOf = atlasPinned.ptr;
 	for (uint32_t q = 0; q < total; q++) {                              // :198-203
-		if (!draws.empty() && draws.back().atlas == atlasH[q]) draws.back().count++;
-		else draws.push_back({ atlasH[q], 1u, q });
+		if (!draws.empty() && draws.back().atlas == atlasOf[q]) draws.back().count++;
+		else draws.push_back({ atlasOf[q], 1u, q });
 	}
+	lastQuads = total;
 	out.deviceVertices = (const SprBillboardVertex*)dVerts.ptr;
 	out.numQuads = total;
 	out.numDraws = (uint32_t)draws.size();

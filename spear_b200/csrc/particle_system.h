@@ -304,7 +304,8 @@ struct BillboardSystem {
 	size_t pendingCount = 0, pendingCapacity = 0;
 	~BillboardSystem() { if (pending) cudaFreeHost(pending); }
 	std::vector<SprBillboardDraw> draws;       // billboardDraws (:63)
-	std::vector<unsigned long long> atlasH;
+	PinnedArray<unsigned long long> atlasPinned; // the frame's atlas id per quad, read back for the draw list
+	uint32_t lastQuads = 0;                    // quads of the last renderMain (sprBillboardReadVertices)
 	DeviceArray<BillboardDev> dBillboards;
 	DeviceArray<uint32_t> dKeys[2], dVals[2], dTileHist, dBlockCounts, dTotal;
 	DeviceArray<float> dVerts;                 // billboardVertices (:65): 24 words per quad

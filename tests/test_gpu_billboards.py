@@ -75,3 +75,26 @@ def test_billboards_all_equal_depth_keep_insertion_order():
         assert [d[0] for d in draws] == [1 + (i % 5) for i in range(5000)]
     finally:
         bs.close(); ctx.close()
+
+
+def test_large_add_call_matches_chunked_adds():
+    """sprBillboardAdd converts a call of 65536 billboards or more on several host threads (counts of loaded sprites
+    per range, then the ranges side by side): the frame must be the one that the same billboards give when they are
+    added in small calls, null sprites included."""
+    P = _particles()
+    base = B.random_frame(21, 4096)
+    frame = base * 20                      # 81920 billboards, ~3 % of them without a sprite
+    ra = make_render_args()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 12)
+    one, many = P.BillboardSystem(ctx, max_billboards_per_frame=1 << 20), P.BillboardSystem(ctx, max_billboards_per_frame=1 << 20)
+    try:
+        one.add(frame)
+        for k in range(0, len(frame), 20480):
+            many.add(frame[k:k + 20480])
+        v1, d1, _ = one.render(ra)
+        v2, d2, _ = many.render(ra)
+        assert len(v1) == len(v2) and len(v1) // 4 > 60000
+        assert d1 == d2
+        assert v1.tobytes() == v2.tobytes()
+    finally:
+        one.close(); many.close(); ctx.close()
