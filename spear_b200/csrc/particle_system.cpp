@@ -397,32 +397,29 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			HostEffectCold &C = *sl.C;
 			ActiveEntry &ae = entries[sl.entry];
 			const uint32_t nsub = ae.numSubsteps;
-			{
-				const HostType &type = sys->types[E.typeId];
-				uint32_t burst = E.firstEmit ? type.comp->burstAmount : 0;
-				// <= 20 timer spawns per sub-step (:478), each sub-step rounds up to one Particle4
-				uint64_t add = (uint64_t)nsub * (kMaxTimerSpawns + 3) + burst + 3;
-				if (!E.capacityFinal) {
-				{
-					// re-base the bound on the newest exact count the device has mirrored (no synchronisation: an older
-					// entry only means more allowances are added on top of it)
-					const unsigned long long m = ((volatile const unsigned long long*)slotMirror)[E.global];
-					const uint32_t mStamp = (uint32_t)(m >> 32);
-					if (mStamp > C.createdStamp && mStamp >= C.evictedStamp) {
-						uint64_t tight = (uint32_t)m;
-						for (uint32_t k = 0; k < C.recentCount; k++) if (C.recent[k].stamp > mStamp) tight += C.recent[k].add;
-						if (tight < C.slotUpperBound) C.slotUpperBound = (uint32_t)tight;
-					}
-					if (C.recentCount == 4) {
-						C.evictedStamp = C.recent[0].stamp;
-						C.recent[0] = C.recent[1]; C.recent[1] = C.recent[2]; C.recent[2] = C.recent[3];
-						C.recentCount = 3;
-					}
-					C.recent[C.recentCount].stamp = thisStamp;
-					C.recent[C.recentCount].add = add > 0xffffffffull ? 0xffffffffu : (uint32_t)add;
-					C.recentCount++;
+			const HostType &type = sys->types[E.typeId];
+			const uint32_t burst = E.firstEmit ? type.comp->burstAmount : 0;
+			// <= 20 timer spawns per sub-step (:478), each sub-step rounds up to one Particle4
+			const uint64_t add = (uint64_t)nsub * (kMaxTimerSpawns + 3) + burst + 3;
+			if (!E.capacityFinal) {
+				// re-base the bound on the newest exact count the device has mirrored (no synchronisation: an older
+				// entry only means more allowances are added on top of it)
+				const unsigned long long m = ((volatile const unsigned long long*)slotMirror)[E.global];
+				const uint32_t mStamp = (uint32_t)(m >> 32);
+				if (mStamp > C.createdStamp && mStamp >= C.evictedStamp) {
+					uint64_t tight = (uint32_t)m;
+					for (uint32_t k = 0; k < C.recentCount; k++) if (C.recent[k].stamp > mStamp) tight += C.recent[k].add;
+					if (tight < C.slotUpperBound) C.slotUpperBound = (uint32_t)tight;
 				}
-				uint64_t need = (uint64_t)C.slotUpperBound + add;
+				if (C.recentCount == 4) {
+					C.evictedStamp = C.recent[0].stamp;
+					C.recent[0] = C.recent[1]; C.recent[1] = C.recent[2]; C.recent[2] = C.recent[3];
+					C.recentCount = 3;
+				}
+				C.recent[C.recentCount].stamp = thisStamp;
+				C.recent[C.recentCount].add = add > 0xffffffffull ? 0xffffffffu : (uint32_t)add;
+				C.recentCount++;
+				const uint64_t need = (uint64_t)C.slotUpperBound + add;
 				if (need > slotCapacityOf[E.global]) {
 					if (E.simSteps == 0) { growEffect(E.global, pow2ceil(need), false); C.slotUpperBound = (uint32_t)need; ensureOwned(E.global, C.slotUpperBound); }
 					else { resolve.push_back({ &E, &C, (uint32_t)add }); resolveGlobals.push_back(E.global); }
@@ -430,19 +427,18 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 					C.slotUpperBound = (uint32_t)need;
 					ensureOwned(E.global, C.slotUpperBound);
 				}
-				} // !capacityFinal
-				if (burst > 1024) {
-					ae.flags |= 1u;
-					uint32_t blocks = (burst + 255) / 256;
-					burstJobs.push_back({ sl.entry, burstBlocks, blocks, 0 });
-					burstBlocks += blocks;
-				}
-				E.firstEmit = false;
-				E.simSteps += nsub;
-				totalSimSteps += nsub;
-				E.uploadFrameIndex = 0;                      // :679
-				if (type.comp->localSpace) C.boundsToWorld = C.particlesToWorld; // gpuBounds uses the matrix of the simulated step (:675-677)
 			}
+			if (burst > 1024) {
+				ae.flags |= 1u;
+				uint32_t blocks = (burst + 255) / 256;
+				burstJobs.push_back({ sl.entry, burstBlocks, blocks, 0 });
+				burstBlocks += blocks;
+			}
+			E.firstEmit = false;
+			E.simSteps += nsub;
+			totalSimSteps += nsub;
+			E.uploadFrameIndex = 0;                          // :679
+			if (type.comp->localSpace) C.boundsToWorld = C.particlesToWorld; // gpuBounds uses the matrix of the simulated step (:675-677)
 		}
 	}
 	// Phase 3: plan records are numbered in entry order
