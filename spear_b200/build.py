@@ -34,13 +34,14 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("SPR_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DSPR_SORT_PROFILE for an instrumented experiment build
     objs = []
     procs = []
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     for s in SOURCES:
         obj = os.path.join(bdir, s + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

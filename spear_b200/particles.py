@@ -180,11 +180,11 @@ class ParticleContext:
 
     def kernel_times(self, reset=True):
         """{kernel name: (total ms, launches)} measured with CUDA events on the context stream."""
-        names = (C.c_char_p * 16)()
-        ms = (C.c_double * 16)()
-        launches = (C.c_uint64 * 16)()
+        names = (C.c_char_p * 24)()
+        ms = (C.c_double * 24)()
+        launches = (C.c_uint64 * 24)()
         n = C.c_uint32()
-        _check(lib.sprContextGetKernelTimes(self.h, 1 if reset else 0, names, ms, launches, 16, C.byref(n)))
+        _check(lib.sprContextGetKernelTimes(self.h, 1 if reset else 0, names, ms, launches, 24, C.byref(n)))
         return {names[i].decode(): (ms[i], int(launches[i])) for i in range(n.value)}
 
     def create_system(self, seed=(1, 2, 3, 4)):
