@@ -39,7 +39,7 @@ UNIT = "particle-steps/s"
 ALG_BYTES_SORTED = 220.0   # 60 update + 32 re-read in sorted order + 128 vertices
 ALG_BYTES_UNSORTED = 188.0
 # per-kernel algorithmic bytes per particle (DESIGN.md "Kernels"): pairs (key,slot) are excluded by section 8(d)
-KERNEL_ALG_BYTES = {"k_integrate": 60.0, "k_expand_sorted": 160.0, "k_expand_scatter": 160.0, "k_expand_stream": 160.0, "k_stream_fused": 188.0}
+KERNEL_ALG_BYTES = {"k_integrate": 60.0, "k_expand_sorted": 160.0, "k_expand_stream": 160.0, "k_stream_fused": 188.0}
 
 
 def profiled_traffic(kernel):

@@ -67,9 +67,9 @@ SPR_API int sprContextSynchronize(SprContext *ctx) { REQUIRE(ctx); return guarde
 SPR_API void *sprContextStream(SprContext *ctx) { return ctx ? (void*)ctx->ctx.stream : nullptr; }
 SPR_API uint64_t sprContextLaunchCount(SprContext *ctx) { return ctx ? ctx->ctx.launchCount : 0; }
 
-static const char *const kKernelNames[kNumKernelClasses] = {
+static const char *const kKernelNames[17] = {
 	"k_scatter_words", "k_plan", "k_emit_warp", "k_emit_burst", "k_integrate", "k_finalize", "k_stream_fused", "k_gather_render",
-	"k_pack_runs", "k_expand_runs", "k_sort_hist", "k_sort_scan", "k_sort_pass", "k_expand_sorted", "k_dead_append", "k_expand_stream", "k_sort_small", "k_expand_scatter" };
+	"k_pack_runs", "k_expand_runs", "k_sort_hist", "k_sort_scan", "k_sort_pass", "k_expand_sorted", "k_dead_append", "k_expand_stream", "k_sort_small" };
 
 SPR_API int sprContextEnableKernelTiming(SprContext *ctx, int enable)
 {
@@ -83,13 +83,13 @@ SPR_API int sprContextGetKernelTimes(SprContext *ctx, int reset, const char **na
 	return guarded([&] {
 		ctx->ctx.resolveTimings();
 		uint32_t n = 0;
-		for (int k = 0; k < kNumKernelClasses; k++) {
+		for (int k = 0; k < 17; k++) {
 			if (!ctx->ctx.kernelLaunches[k]) continue;
 			if (n < capacity) { if (names) names[n] = kKernelNames[k]; if (ms) ms[n] = ctx->ctx.kernelMs[k]; if (launches) launches[n] = ctx->ctx.kernelLaunches[k]; }
 			n++;
 		}
 		*outCount = n;
-		if (reset) for (int k = 0; k < kNumKernelClasses; k++) { ctx->ctx.kernelMs[k] = 0; ctx->ctx.kernelLaunches[k] = 0; }
+		if (reset) for (int k = 0; k < 17; k++) { ctx->ctx.kernelMs[k] = 0; ctx->ctx.kernelLaunches[k] = 0; }
 	});
 }
 
@@ -282,8 +282,6 @@ SPR_API int sprReadStreamSlots(SprSystem *sys, uint32_t effectId, uint32_t *out,
 		uint32_t m = g.aliveCount < capacity ? g.aliveCount : capacity;
 		if (!m || !out) return;
 		if (ctx->flags & SPR_CTX_SORT_PARTICLES) {
-			// an effect on the scatter expansion keeps rankOf[slot], not the sorted slot list: invert it for the read-back
-			if (ctx->sortedLarge[E.global]) { launch_invert_rank(ctx->stream, ctx->poolPtrs(), P.slotBase, g.slotCount, ctx->dRankOf); ctx->launchCount++; }
 			SPR_CUDA(cudaMemcpyAsync(out, ctx->dVals[0] + P.slotBase, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
 			SPR_CUDA(cudaStreamSynchronize(ctx->stream));
 		} else {

@@ -19,8 +19,10 @@ static const uint32_t kGranuleSlots = 128;     // slots per warp
 static const uint32_t kTileSlots = 1024;       // slots per CTA (8 warps)
 static const uint32_t kMaxTimerSpawns = 20;    // ParticleSystem.cpp:478
 static const uint32_t kNoOwner = 0xffffffffu;
-static const uint32_t kSortTileKeys = 4096;    // keys per CTA in the radix sort passes
-static const uint32_t kSegLargeFlag = 0x80000000u; // sort segment list: the effect's 4x expansion runs in slot order with scattered line writes
+#ifndef SPR_SORT_TILE_KEYS
+#define SPR_SORT_TILE_KEYS 4096
+#endif
+static const uint32_t kSortTileKeys = SPR_SORT_TILE_KEYS; // keys per CTA in the radix sort passes (16 per thread)
 static const uint32_t kSmallSortMax = 18432;   // an effect of at most this many slots is sorted by ONE CTA (k_sort_small)
 
 static const float kHugeLife = 1e20f;          // ParticleSystem.cpp:27

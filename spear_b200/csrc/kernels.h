@@ -60,9 +60,8 @@ struct SortScratch {
 	uint32_t *keysAlt, *valsAlt;     // ping-pong buffers, same indexing as PoolPtrs::keys/vals
 	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases, then [numSegments] pass masks
 	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
-	uint32_t *rankOf;                // per pool slot: depth rank of the slot's particle (effects on the scatter expansion only)
 };
-// Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted, 4 sort_small, 5 expand_scatter).
+// Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted, 4 sort_small).
 struct SortTimingHooks {
 	void *ctx;
 	void *(*begin)(void *ctx, int kernel);
@@ -73,12 +72,9 @@ struct SortTimingHooks {
 void clear_sort_scratch(cudaStream_t st, const SortScratch &scratch, uint32_t numSegments, uint32_t numTiles);
 // segEffects / tiles list the tile-path ("big") effects first: [0, numBigSegments) / [0, numBigTiles) go through
 // hist + scan + 4 passes, the effects behind them (at most kSmallSortMax slots each) through k_sort_small, one CTA
-// per effect. The first numLargeTiles tiles belong to effects flagged kSegLargeFlag in segEffects: they are expanded in
-// slot order by k_expand_scatter (from SortScratch::rankOf), every other tile by k_expand_sorted. Returns the number of launches.
+// per effect; k_expand_sorted then runs over all tiles. Returns the number of launches.
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &scratch,
 	const uint32_t *segEffects, uint32_t numSegments, uint32_t numBigSegments, const SortTile *tiles, uint32_t numTiles, uint32_t numBigTiles,
-	uint32_t numLargeTiles, const SortTimingHooks *hooks);
-// sorted slot list of an effect on the scatter expansion, rebuilt from rankOf into PoolPtrs::vals (read-back only)
-void launch_invert_rank(cudaStream_t st, const PoolPtrs &pool, uint32_t segBase, uint32_t slots, const uint32_t *rankOf);
+	const SortTimingHooks *hooks);
 
 } // namespace spr

@@ -55,8 +55,6 @@ Context::Context(const SprContextDesc &desc)
 	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[0], cudaEventDisableTiming));
 	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[1], cudaEventDisableTiming));
 	streamFused = getenv("SPR_STREAM_TWO_PASS") == nullptr; // SPR_STREAM_TWO_PASS=1 selects the two-pass stream mode (A/B measurement)
-	// SPR_LARGE_SLOTS=n moves the scatter-expansion threshold (tests run the path on small effects; 0 turns it off)
-	if (const char *e = getenv("SPR_LARGE_SLOTS")) { long long v = atoll(e); largeScatterSlots = v <= 0 ? 0xffffffffu : (uint32_t)v; }
 	configure_stream_fused(streamFusedCtasPerSm);
 	configure_sort_kernels();
 	freeRanges.resize(33);
@@ -64,7 +62,7 @@ Context::Context(const SprContextDesc &desc)
 }
 
 #ifdef SPR_SORT_PROFILE
-void sort_profile_dump();
+void sort_profile_dump(); // sort.cu, instrumented experiment builds only (SPR_EXTRA_NVCC_FLAGS=-DSPR_SORT_PROFILE)
 #endif
 
 Context::~Context()
@@ -75,7 +73,7 @@ Context::~Context()
 	sort_profile_dump();
 #endif
 	cudaFree(dSlotState); cudaFree(dFreeStack); cudaFree(dVertices);
-	cudaFree(dKeys[0]); cudaFree(dKeys[1]); cudaFree(dVals[0]); cudaFree(dVals[1]); cudaFree(dRankOf);
+	cudaFree(dKeys[0]); cudaFree(dKeys[1]); cudaFree(dVals[0]); cudaFree(dVals[1]);
 	cudaFree(dAliveMask); cudaFree(dDeadMask); cudaFree(dWordAliveBase);
 	cudaFree(dGranuleOwner); cudaFree(dTileStatus[0]); cudaFree(dTileStatus[1]);
 	if (slotMirror) cudaFreeHost(slotMirror);
@@ -135,7 +133,6 @@ void Context::ensurePool(uint64_t slots)
 			regrow(dKeys[i], poolCapacity, cap, 0, -1, stream);
 			regrow(dVals[i], poolCapacity, cap, i == 0 ? used : 0, -1, stream); // vals[0] holds the sorted slot order of every effect
 		}
-		regrow(dRankOf, poolCapacity, cap, used, -1, stream);
 	}
 	{
 		// the ballots (and, in stream mode, the word ranks) are rewritten by every simulated step, but an
@@ -178,7 +175,6 @@ uint32_t Context::allocEffectGlobal()
 		ownedSlots.resize(numEffectGlobals, 0);
 		slotCapacityOf.resize(numEffectGlobals, 0);
 		effectLive.resize(numEffectGlobals, 0);
-		sortedLarge.resize(numEffectGlobals, 0);
 		dirtyParamsFlag.resize(numEffectGlobals, 0);
 		size_t keep = numEffectGlobals - 1;
 		dParams.reserve(numEffectGlobals, keep, stream);
@@ -251,8 +247,7 @@ void Context::ensureOwned(uint32_t g, uint32_t slotUpperBound)
 
 // Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
 enum { kKScatter = 0, kKPlan, kKEmit, kKEmitBurst, kKIntegrate, kKFinalize, kKSort, kKGather, kKPack, kKExpandRuns,
-	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15, kKStreamFused = 6, kKSortSmall = 16, kKExpandScatter = 17 };
-static int sortTimingClass(int k) { return k == 4 ? kKSortSmall : k == 5 ? kKExpandScatter : kKSortBase + k; }
+	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15, kKStreamFused = 6, kKSortSmall = 16 };
 
 cudaEvent_t Context::timingBegin(int kernel)
 {
@@ -478,7 +473,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	std::vector<uint32_t> &segEffects = nested ? nestedSeg : scratchSegEffects;
 	std::vector<SortTile> &sortTiles = nested ? nestedTiles : scratchSortTiles;
 	segEffects.clear(); sortTiles.clear();
-	uint32_t numBigSegments = 0, numBigTiles = 0, numLargeSegments = 0, numLargeTiles = 0;
+	uint32_t numBigSegments = 0, numBigTiles = 0;
 	if (sortMode) {
 		// tile-path effects first, then the ones one CTA sorts whole (k_sort_small): ownedSlots is the effect's slot
 		// bound rounded up to a tile, never below its real slot count
@@ -488,19 +483,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		for (const ActiveEntry &ae : entries) {
 			if (!ae.numSubsteps) continue;
 			if (slotCapacityOf[ae.effect] == kGranuleSlots) continue; // sorted and expanded inside k_integrate_sort
-			sortedLarge[ae.effect] = 0;
 			if (smallSort && ownedSlots[ae.effect] <= kSmallSortMax) small.push_back(ae.effect);
 			else segEffects.push_back(ae.effect);
 		}
 		numBigSegments = (uint32_t)segEffects.size();
-		// effects whose state is far larger than L2 first: their 4x expansion runs in slot order with scattered line
-		// writes (k_expand_scatter) over a prefix of the tile list, everything else in rank order (k_expand_sorted)
-		auto isLarge = [&](uint32_t g) { return ownedSlots[g] > largeScatterSlots; };
-		std::stable_partition(segEffects.begin(), segEffects.end(), isLarge);
-		while (numLargeSegments < numBigSegments && isLarge(segEffects[numLargeSegments])) {
-			sortedLarge[segEffects[numLargeSegments]] = 1;
-			segEffects[numLargeSegments++] |= kSegLargeFlag;
-		}
 		segEffects.insert(segEffects.end(), small.begin(), small.end());
 	}
 
@@ -514,7 +500,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		+ entries.size() * sizeof(ActiveEntry) + work.size() * sizeof(SystemWork) + burstJobs.size() * sizeof(BurstJob)
 		+ segEffects.size() * sizeof(uint32_t);
 	if (sortMode) {
-		for (uint32_t g : segEffects) bound += ((size_t)slotCapacityOf[g & ~kSegLargeFlag] / kSortTileKeys + 1) * sizeof(SortTile);
+		for (uint32_t g : segEffects) bound += ((size_t)slotCapacityOf[g] / kSortTileKeys + 1) * sizeof(SortTile);
 	}
 	bound += 16 * 16;
 	int par = stagingParity; stagingParity ^= 1;
@@ -556,15 +542,13 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	if (sortMode) {
 		for (size_t s = 0; s < segEffects.size(); s++) {
 			if (s == numBigSegments) numBigTiles = (uint32_t)sortTiles.size();
-			if (s == numLargeSegments) numLargeTiles = (uint32_t)sortTiles.size();
 			// tiles up to the effect's slot bound (ownedSlots: never below its real slot count), not up to its
 			// power-of-two capacity: C3's 10M slots are 2443 tiles of a 4096-tile range, and every empty CTA costs
 			// each of the seven sort kernels a scheduling slot
-			uint32_t tiles = (ownedSlots[segEffects[s] & ~kSegLargeFlag] + kSortTileKeys - 1) / kSortTileKeys;
+			uint32_t tiles = (ownedSlots[segEffects[s]] + kSortTileKeys - 1) / kSortTileKeys;
 			for (uint32_t t = 0; t < tiles; t++) sortTiles.push_back({ (uint32_t)s, t });
 		}
 		if (numBigSegments == segEffects.size()) numBigTiles = (uint32_t)sortTiles.size();
-		if (numLargeSegments == segEffects.size()) numLargeTiles = (uint32_t)sortTiles.size();
 	}
 	size_t oSeg = bw.put(segEffects.data(), segEffects.size());
 	size_t oTiles = bw.put(sortTiles.data(), sortTiles.size());
@@ -602,9 +586,9 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	TablePtrs tab = tablePtrs();
 	const ActiveEntry *dEntries = DPTR(ActiveEntry, oEntries);
 	const uint32_t nEntries = (uint32_t)entries.size();
-	SortScratch sortScratch = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	SortScratch sortScratch = { nullptr, nullptr, nullptr, nullptr };
 	if (sortMode && !segEffects.empty()) {
-		sortScratch.keysAlt = dKeys[1]; sortScratch.valsAlt = dVals[1]; sortScratch.rankOf = dRankOf;
+		sortScratch.keysAlt = dKeys[1]; sortScratch.valsAlt = dVals[1];
 		dSortHist.reserve(segEffects.size() * (4 * 256 + 1), 0, stream);
 		dSortLookback.reserve(sortTiles.size() * 4 * 256 + 1, 0, stream);
 		sortScratch.hist = dSortHist.ptr; sortScratch.lookback = dSortLookback.ptr;
@@ -639,10 +623,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 
 	if (sortMode && !segEffects.empty()) {
 		const SortScratch &sc = sortScratch;
-		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(sortTimingClass(k)); },
-			[](void *c, int k, void *b) { ((Context*)c)->timingEnd(sortTimingClass(k), (cudaEvent_t)b); } };
+		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(k == 4 ? kKSortSmall : kKSortBase + k); },
+			[](void *c, int k, void *b) { ((Context*)c)->timingEnd(k == 4 ? kKSortSmall : kKSortBase + k, (cudaEvent_t)b); } };
 		launchCount += launch_sort_and_expand(stream, pool, tab, sc, DPTR(uint32_t, oSeg), (uint32_t)segEffects.size(), numBigSegments,
-			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size(), numBigTiles, numLargeTiles, timingEnabled ? &hooks : nullptr);
+			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size(), numBigTiles, timingEnabled ? &hooks : nullptr);
 	}
 #undef DPTR
 	if (hostTiming) {

@@ -24,8 +24,6 @@
 
 namespace spr {
 
-static const int kNumKernelClasses = 18; // timing classes of Context::kernelMs (names: c_api.cpp kKernelNames)
-
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 
 #define SPR_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) throw spr::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
@@ -188,9 +186,6 @@ struct Context {
 	float4 *dVertices = nullptr;
 	uint32_t *dKeys[2] = { nullptr, nullptr };
 	uint32_t *dVals[2] = { nullptr, nullptr };
-	uint32_t *dRankOf = nullptr;           // sort mode: depth rank per slot, written by the last radix pass of effects on the scatter expansion
-	uint32_t largeScatterSlots = 2u << 20; // effects whose slot bound exceeds this (64 MB of state: well beyond what L2 keeps) take the scatter expansion
-	std::vector<uint8_t> sortedLarge;      // per effect: its last sort left rankOf, not the sorted slot list (sprReadStreamSlots rebuilds it)
 	uint32_t *dAliveMask = nullptr, *dDeadMask = nullptr, *dWordAliveBase = nullptr;
 	uint32_t *dGranuleOwner = nullptr;
 	unsigned long long *dTileStatus[2] = { nullptr, nullptr };
@@ -261,8 +256,8 @@ struct Context {
 	bool timingEnabled = false;
 	std::vector<TimedLaunch> timedLaunches;
 	std::vector<cudaEvent_t> eventPool;
-	double kernelMs[kNumKernelClasses] = { 0 };
-	uint64_t kernelLaunches[kNumKernelClasses] = { 0 };
+	double kernelMs[17] = { 0 };
+	uint64_t kernelLaunches[17] = { 0 };
 	cudaEvent_t timingBegin(int kernel);
 	void timingEnd(int kernel, cudaEvent_t begin);
 	void resolveTimings();

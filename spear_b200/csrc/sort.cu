@@ -29,23 +29,22 @@ namespace spr {
 
 #define FULL_MASK 0xffffffffu
 
-static const uint32_t kSortThreads = 256;
-static const uint32_t kItemsPerThread = kSortTileKeys / kSortThreads; // 16
-static const uint32_t kWarpKeys = kSortTileKeys / 8;                  // 512 keys per warp
+static const uint32_t kItemsPerThread = 16;                           // keys per thread of a pass CTA
+static const uint32_t kSortThreads = kSortTileKeys / kItemsPerThread; // 256 threads for 4096-key tiles, 512 for 8192
+static const uint32_t kSortWarps = kSortThreads / 32;
+static const uint32_t kWarpKeys = 32 * kItemsPerThread;               // 512 keys per warp
+static const uint32_t kHistItems = kSortTileKeys / 256;               // keys per thread of the (256-thread) histogram CTA
+static const uint32_t kExpandPerTile = kSortTileKeys / 1024;          // k_expand_sorted CTAs per sort tile
 static const uint32_t kLook = 8;                                      // status words fetched per look-back batch
-
-// A segment-list entry is the context-wide effect index; bit 31 marks an effect that takes the scatter expansion
-// (k_expand_scatter: its last radix pass writes rankOf[slot] instead of the sorted pairs). The host decides from its
-// slot bound, so every kernel of the frame sees the same answer.
-__device__ __forceinline__ uint32_t seg_effect(uint32_t e) { return e & ~kSegLargeFlag; }
-__device__ __forceinline__ bool seg_large(uint32_t e) { return (e & kSegLargeFlag) != 0; }
+static const size_t kPassSmemBytes = (2 * kSortTileKeys + kSortWarps * 256) * sizeof(uint32_t); // keys, values, per-warp digit counts
+static_assert(kSortThreads >= 256 && kSortThreads <= 1024 && kHistItems <= 32, "sort tile: 4096 to 16384 keys");
 
 __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t *hist)
 {
 	pdl_enter();
 	__shared__ uint32_t sHist[4 * 256];
 	SortTile st = tiles[blockIdx.x];
-	uint32_t g = seg_effect(segEffects[st.effect]);
+	uint32_t g = segEffects[st.effect];
 	const EffectState &S = tab.state[g];
 	uint32_t slots = S.slotCount[S.parity];
 	uint32_t begin = st.tile * kSortTileKeys;
@@ -60,19 +59,19 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 	// All loads of the tile first and with no branch between them -- one memory round trip per CTA instead of one per
 	// key (alive word -> branch -> key was two dependent loads, sixteen times over: the kernel took the same 42 us for
 	// 1M and for 10M keys). Key i = tid + 256 * it sits in alive word warp + 8 * it, bit lane: lane l < 16 fetches the
-	// word of iteration l, a dead slot's key is stale but mapped.
+	// word of iteration l (lane l < kHistItems), a dead slot's key is stale but mapped.
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	uint32_t myWord = 0;
-	if (lane < kItemsPerThread && (warp + 8 * lane) * 32 < count) myWord = mask[warp + 8 * lane];
-	uint32_t key[kItemsPerThread];
+	if (lane < kHistItems && (warp + 8 * lane) * 32 < count) myWord = mask[warp + 8 * lane];
+	uint32_t key[kHistItems];
 #pragma unroll
-	for (uint32_t it = 0; it < kItemsPerThread; it++) {
-		const uint32_t i = threadIdx.x + it * kSortThreads;
+	for (uint32_t it = 0; it < kHistItems; it++) {
+		const uint32_t i = threadIdx.x + it * 256u;
 		key[it] = i < count ? keys[i] : 0u;
 	}
 #pragma unroll
-	for (uint32_t it = 0; it < kItemsPerThread; it++) {
-		const uint32_t i = threadIdx.x + it * kSortThreads;
+	for (uint32_t it = 0; it < kHistItems; it++) {
+		const uint32_t i = threadIdx.x + it * 256u;
 		const uint32_t word = __shfl_sync(FULL_MASK, myWord, it);
 		if (i >= count || !((word >> lane) & 1u)) continue;
 		const uint32_t k = key[it] - keyMin;
@@ -114,7 +113,7 @@ __global__ void k_sort_scan(TablePtrs tab, const uint32_t *segEffects, uint32_t 
 #pragma unroll
 	for (int i = 0; i < 8; i++) { h[lane * 8 + i] = run; run += v[i]; }
 	// the bins of any pass add up to the number of live particles (gpuParticles.size / 4, :670)
-	if ((row & 3u) == 0 && lane == 31) tab.state[seg_effect(segEffects[row >> 2])].aliveCount = run;
+	if ((row & 3u) == 0 && lane == 31) tab.state[segEffects[row >> 2]].aliveCount = run;
 	if (lane == 31 && ((row & 3u) == 0 || big != run)) atomicOr(&passMask[row >> 2], 1u << (row & 3u));
 }
 
@@ -134,9 +133,7 @@ __device__ inline void st_relaxed_u32(uint32_t *p, uint32_t v)
 // The pairs ping-pong between buffer 0 (PoolPtrs::keys/vals) and buffer 1 (the Alt pair): a segment that has
 // executed e passes so far has its pairs in buffer e & 1.
 // The LAST executed pass of a segment (the highest bit of its pass mask) has no reader for its keys: it writes only
-// the sorted slots -- or, for an effect on the scatter expansion (seg_large), nothing but rankOf[slot] = rank, the
-// inverse permutation k_expand_scatter needs.
-// RANK2: two keys per ranking round (four peer-mask tables per warp) instead of one.
+// the sorted slots.
 #ifdef SPR_SORT_PROFILE
 __device__ unsigned long long g_sortProf[16];
 #define PROF_T(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_sortProf[i], (unsigned long long)(t_ - profT)); profT = t_; } } while (0)
@@ -144,23 +141,23 @@ __device__ unsigned long long g_sortProf[16];
 #define PROF_T(i) do { } while (0)
 #endif
 
-template <bool FIRST, bool RANK2>
-__global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
-	uint32_t *keys0, uint32_t *vals0, uint32_t *keys1, uint32_t *vals1, uint32_t *rankOf,
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
+	uint32_t *keys0, uint32_t *vals0, uint32_t *keys1, uint32_t *vals1,
 	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t pass)
 {
 	pdl_enter();
-	__shared__ uint32_t sKeys[kSortTileKeys];
-	__shared__ uint32_t sVals[kSortTileKeys];
-	__shared__ uint32_t sCnt[8 * 256];      // per-warp digit counts -> staging position of the warp's first key of each digit
-	__shared__ int32_t sGlobal[256];        // global position of local index j with digit d: sGlobal[d] + j
+	extern __shared__ __align__(16) uint32_t sPassDyn[];
+	uint32_t *sKeys = sPassDyn;                         // [kSortTileKeys]
+	uint32_t *sVals = sPassDyn + kSortTileKeys;         // [kSortTileKeys]
+	uint32_t *sCnt = sPassDyn + 2 * kSortTileKeys;      // [kSortWarps][256] per-warp digit counts -> staging position of the warp's first key of each digit
+	__shared__ int32_t sGlobal[256];            // global position of local index j with digit d: sGlobal[d] + j
 	__shared__ uint32_t sWarpSum[8];
 	__shared__ uint32_t sTileCount;
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const SortTile st = tiles[blockIdx.x];
-	const uint32_t segEntry = segEffects[st.effect];
-	const uint32_t g = seg_effect(segEntry);
+	const uint32_t g = segEffects[st.effect];
 	const uint32_t runMask = passMask[st.effect] | 1u; // pass 0 always runs: its scatter is the compaction
 	if (!FIRST && !((runMask >> pass) & 1u)) return; // constant digit: nothing would move
 	const bool isLast = (runMask >> (pass + 1u)) == 0u;
@@ -181,15 +178,13 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 #ifdef SPR_SORT_PROFILE
 	long long profT = clock64();
 #endif
-	for (uint32_t i = tid; i < 8 * 256; i += kSortThreads) {
-		sCnt[i] = 0; sVals[i] = 0; sVals[i + 8 * 256] = 0;
-		if (RANK2) { sKeys[i] = 0; sKeys[i + 8 * 256] = 0; }
-	}
+	// per-warp digit counts and the two per-warp peer-mask tables (aliased onto sVals, idle until staging)
+	for (uint32_t i = tid; i < kSortWarps * 256; i += kSortThreads) { sCnt[i] = 0; sVals[i] = 0; sVals[i + kSortWarps * 256] = 0; }
 	__syncthreads();
 	PROF_T(0);
 
 	// ---- load keys (warp-striped: warp w owns keys [w*512, w*512+512) of the tile) and rank them.
-	// Register diet for 4 CTAs/SM: ranks and staging positions are 16-bit and packed in pairs, the
+	// Register diet: ranks and staging positions are 16-bit and packed in pairs, the
 	// slot values are only fetched once the keys have been staged.
 	uint32_t key[kItemsPerThread], rank2[kItemsPerThread / 2];
 	uint32_t okBits = 0;
@@ -224,99 +219,79 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 	const uint32_t ltMask = (1u << lane) - 1u;
 	// Peers of a lane = lanes of the warp with the same digit, found with one shared-memory atomicOr
 	// per lane into a per-warp mask table (measured 14 % faster per pass than MATCH.ANY, whose cost
-	// grows with the number of distinct digits in the warp). The leader clears its entry after reading it, and the
-	// tables are used by alternate rounds, so two __syncwarp()s pass before an entry's next use.
-	if (!RANK2) {
-		uint32_t *match0 = sVals + warp * 512, *match1 = match0 + 256; // sVals is idle until staging
+	// grows with the number of distinct digits in the warp). Two tables used by alternate rounds:
+	// the leader clears its entry after reading it, and two __syncwarp()s pass before its next use.
+	// (two keys per round through four tables -- half the warp barriers -- was measured 4 % slower:
+	// profiles/r02_sort_experiments.md)
+	uint32_t *match0 = sVals + warp * 512, *match1 = match0 + 256;
 #pragma unroll
-		for (uint32_t i = 0; i < kItemsPerThread; i++) {
-			uint32_t *match = (i & 1u) ? match1 : match0;
-			bool ok = (okBits >> i) & 1u;
-			uint32_t d = ((key[i] - keyMin) >> shift) & 255u;
-			if (ok) atomicOr(&match[d], 1u << lane);
-			__syncwarp();
-			uint32_t peers = ok ? match[d] : 0u;
-			uint32_t before = ok ? cnt[d] : 0u;
-			__syncwarp();
-			uint32_t rk = before + __popc(peers & ltMask);
-			if (ok && (peers & ltMask) == 0) { cnt[d] = before + __popc(peers); match[d] = 0; }
-			if (i & 1u) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
-		}
-	} else {
-		// Two keys per round: item 2r goes through table X0, item 2r + 1 through X1 (both of pair A in even rounds, of
-		// pair B in odd ones: sVals and sKeys are idle until staging). The rank of item 2r + 1 counts the peers of its
-		// digit among the round's first items (X0[d1]) on top of the running count; when both items of a round hold
-		// the same digit only the second group's leader writes the count (it carries both), so no two lanes store to
-		// one counter in a round. Half the warp barriers of the one-key loop, and the two atomics overlap.
-#pragma unroll
-		for (uint32_t r = 0; r < kItemsPerThread / 2; r++) {
-			uint32_t *x0 = ((r & 1u) ? sKeys : sVals) + warp * 512, *x1 = x0 + 256;
-			const bool ok0 = (okBits >> (2 * r)) & 1u, ok1 = (okBits >> (2 * r + 1)) & 1u;
-			const uint32_t d0 = ((key[2 * r] - keyMin) >> shift) & 255u, d1 = ((key[2 * r + 1] - keyMin) >> shift) & 255u;
-			if (ok0) atomicOr(&x0[d0], 1u << lane);
-			if (ok1) atomicOr(&x1[d1], 1u << lane);
-			__syncwarp();
-			const uint32_t p0 = ok0 ? x0[d0] : 0u, c0 = ok0 ? cnt[d0] : 0u, n0 = ok0 ? x1[d0] : 0u;
-			const uint32_t p1 = ok1 ? x1[d1] : 0u, c1 = ok1 ? cnt[d1] : 0u, q1 = ok1 ? x0[d1] : 0u;
-			__syncwarp();
-			const uint32_t rk0 = c0 + __popc(p0 & ltMask);
-			const uint32_t rk1 = c1 + __popc(q1) + __popc(p1 & ltMask);
-			if (ok0 && (p0 & ltMask) == 0) { if (!n0) cnt[d0] = c0 + __popc(p0); x0[d0] = 0; }
-			if (ok1 && (p1 & ltMask) == 0) { cnt[d1] = c1 + __popc(q1) + __popc(p1); x1[d1] = 0; }
-			rank2[r] = rk0 | rk1 << 16;
-		}
+	for (uint32_t i = 0; i < kItemsPerThread; i++) {
+		uint32_t *match = (i & 1u) ? match1 : match0;
+		bool ok = (okBits >> i) & 1u;
+		uint32_t d = ((key[i] - keyMin) >> shift) & 255u;
+		if (ok) atomicOr(&match[d], 1u << lane);
+		__syncwarp();
+		uint32_t peers = ok ? match[d] : 0u;
+		uint32_t before = ok ? cnt[d] : 0u;
+		__syncwarp();
+		uint32_t rk = before + __popc(peers & ltMask);
+		if (ok && (peers & ltMask) == 0) { cnt[d] = before + __popc(peers); match[d] = 0; }
+		if (i & 1u) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
 	}
 	PROF_T(2);
 	__syncthreads();
 	PROF_T(3);
 
-	// ---- thread d: per-warp exclusive offsets of digit d, tile count, chained look-back
-	uint32_t total = 0;
+	// ---- thread d < 256: per-warp exclusive offsets of digit d, tile count, chained look-back
+	uint32_t total = 0, excl = 0, incl = 0;
+	if (tid < 256) {
 #pragma unroll
-	for (uint32_t w = 0; w < 8; w++) { uint32_t c = sCnt[w * 256 + tid]; sCnt[w * 256 + tid] = total; total += c; }
-	uint32_t *lb = lookback + (size_t)blockIdx.x * 256 + tid;
-	uint32_t excl = 0;
-	if (st.tile == 0) {
-		st_relaxed_u32(lb, (2u << 30) | total);
-	} else {
-		st_relaxed_u32(lb, (1u << 30) | total);
-		// walk back over the predecessors' status words of this digit, kLook at a time: the loads of one batch are
-		// independent, so a long walk costs one L2 round trip per batch instead of one per tile
-		const uint32_t *p = lb - 256; // tiles of one segment are consecutive in the tile table
-		bool found = false;
-		for (uint32_t t = st.tile; t > 0 && !found; ) {
-			const uint32_t n = t < kLook ? t : kLook;
-			uint32_t v[kLook];
+		for (uint32_t w = 0; w < kSortWarps; w++) { uint32_t c = sCnt[w * 256 + tid]; sCnt[w * 256 + tid] = total; total += c; }
+		uint32_t *lb = lookback + (size_t)blockIdx.x * 256 + tid;
+		if (st.tile == 0) {
+			st_relaxed_u32(lb, (2u << 30) | total);
+		} else {
+			st_relaxed_u32(lb, (1u << 30) | total);
+			// walk back over the predecessors' status words of this digit, kLook at a time: the loads of one batch are
+			// independent, so a long walk costs one L2 round trip per batch instead of one per tile
+			const uint32_t *p = lb - 256; // tiles of one segment are consecutive in the tile table
+			bool found = false;
+			for (uint32_t t = st.tile; t > 0 && !found; ) {
+				const uint32_t n = t < kLook ? t : kLook;
+				uint32_t v[kLook];
 #pragma unroll
-			for (uint32_t i = 0; i < kLook; i++) v[i] = i < n ? ld_relaxed_u32(p - i * 256) : (2u << 30);
+				for (uint32_t i = 0; i < kLook; i++) v[i] = i < n ? ld_relaxed_u32(p - i * 256) : (2u << 30);
 #pragma unroll
-			for (uint32_t i = 0; i < kLook; i++) {
-				if (found) break;
-				// (a predecessor tile is always already running; trap instead of hanging if that ever breaks)
-				for (uint32_t spins = 0; (v[i] >> 30) == 0; ) { v[i] = ld_relaxed_u32(p - i * 256); if (++spins > (1u << 24)) __trap(); }
-				excl += v[i] & 0x3fffffffu;
-				found = (v[i] >> 30) == 2u;
+				for (uint32_t i = 0; i < kLook; i++) {
+					if (found) break;
+					// (a predecessor tile is always already running; trap instead of hanging if that ever breaks)
+					for (uint32_t spins = 0; (v[i] >> 30) == 0; ) { v[i] = ld_relaxed_u32(p - i * 256); if (++spins > (1u << 24)) __trap(); }
+					excl += v[i] & 0x3fffffffu;
+					found = (v[i] >> 30) == 2u;
+				}
+				p -= kLook * 256; t -= n;
 			}
-			p -= kLook * 256; t -= n;
+			st_relaxed_u32(lb, (2u << 30) | (excl + total));
 		}
-		st_relaxed_u32(lb, (2u << 30) | (excl + total));
+		PROF_T(4);
+		// exclusive scan of the 256 digit counts of the tile
+		incl = total;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += o; }
+		if (lane == 31) sWarpSum[warp] = incl;
 	}
-	PROF_T(4);
-	// exclusive scan of the 256 digit counts of the tile
-	uint32_t incl = total;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += o; }
-	if (lane == 31) sWarpSum[warp] = incl;
 	__syncthreads();
-	uint32_t warpBase = 0;
+	if (tid < 256) {
+		uint32_t warpBase = 0;
 #pragma unroll
-	for (uint32_t w = 0; w < 8; w++) if (w < warp) warpBase += sWarpSum[w];
-	const uint32_t tileExcl = warpBase + incl - total;
-	// staging position of warp w's first key of digit d: one table read per key when the tile is staged
+		for (uint32_t w = 0; w < 8; w++) if (w < warp) warpBase += sWarpSum[w];
+		const uint32_t tileExcl = warpBase + incl - total;
+		// staging position of warp w's first key of digit d: one table read per key when the tile is staged
 #pragma unroll
-	for (uint32_t w = 0; w < 8; w++) sCnt[w * 256 + tid] += tileExcl;
-	if (tid == 255) sTileCount = tileExcl + total;
-	sGlobal[tid] = (int32_t)(hist[((size_t)st.effect * 4 + pass) * 256 + tid] + excl) - (int32_t)tileExcl;
+		for (uint32_t w = 0; w < kSortWarps; w++) sCnt[w * 256 + tid] += tileExcl;
+		if (tid == 255) sTileCount = tileExcl + total;
+		sGlobal[tid] = (int32_t)(hist[((size_t)st.effect * 4 + pass) * 256 + tid] + excl) - (int32_t)tileExcl;
+	}
 	__syncthreads();
 	PROF_T(5);
 
@@ -350,9 +325,9 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 
 	// ---- scatter: consecutive threads write consecutive addresses inside each digit run
 	const uint32_t tileCount = sTileCount;
+	uint32_t *vout = valsOut + segBase;
 	if (!isLast) {
 		uint32_t *kout = keysOut + segBase;
-		uint32_t *vout = valsOut + segBase;
 		for (uint32_t j = tid; j < tileCount; j += kSortThreads) {
 			uint32_t k = sKeys[j];
 			uint32_t d = ((k - keyMin) >> shift) & 255u;
@@ -360,17 +335,10 @@ __global__ void __launch_bounds__(256, 4) k_sort_pass(PoolPtrs pool, TablePtrs t
 			kout[dst] = k;
 			vout[dst] = sVals[j];
 		}
-	} else if (!seg_large(segEntry)) {
-		uint32_t *vout = valsOut + segBase;
+	} else {
 		for (uint32_t j = tid; j < tileCount; j += kSortThreads) {
 			uint32_t d = ((sKeys[j] - keyMin) >> shift) & 255u;
 			vout[(uint32_t)(sGlobal[d] + (int32_t)j)] = sVals[j];
-		}
-	} else {
-		uint32_t *rout = rankOf + segBase;
-		for (uint32_t j = tid; j < tileCount; j += kSortThreads) {
-			uint32_t d = ((sKeys[j] - keyMin) >> shift) & 255u;
-			rout[sVals[j]] = (uint32_t)(sGlobal[d] + (int32_t)j);
 		}
 	}
 	PROF_T(8);
@@ -429,7 +397,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, 
 	__shared__ uint32_t sMaxRel, sTotal;
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t g = seg_effect(segEffects[blockIdx.x]);
+	const uint32_t g = segEffects[blockIdx.x];
 	EffectState &S = tab.state[g];
 	const uint32_t slots = S.slotCount[S.parity];
 	if (slots > kSmallSortMax) __trap(); // the host routes an effect here only when its slot bound fits
@@ -588,11 +556,11 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	const uint32_t *valsAlt, const uint32_t *passMask)
 {
 	pdl_enter();
-	// four CTAs per 4096-key sort tile: 1024 particles per CTA, 4 per thread, all gathers in flight at once
-	SortTile st = tiles[blockIdx.x >> 2];
-	uint32_t g = seg_effect(segEffects[st.effect]);
+	// kExpandPerTile CTAs per sort tile: 1024 particles per CTA, 4 per thread, all gathers in flight at once
+	SortTile st = tiles[blockIdx.x / kExpandPerTile];
+	uint32_t g = segEffects[st.effect];
 	uint32_t alive = tab.state[g].aliveCount;
-	uint32_t begin = st.tile * kSortTileKeys + (blockIdx.x & 3u) * 1024u;
+	uint32_t begin = st.tile * kSortTileKeys + (blockIdx.x % kExpandPerTile) * 1024u;
 	if (begin >= alive) return;
 	uint32_t count = min(1024u, alive - begin);
 	uint32_t segBase = tab.params[g].slotBase;
@@ -640,63 +608,13 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	}
 }
 
-// The 4x expansion of an effect whose state is much larger than L2, in SLOT order: the state is read sequentially (one
-// DRAM sector per record, every byte used) and each particle's 128 bytes are written as one full line at its depth
-// rank, rankOf[slot], which the last radix pass left behind. A random full-line write costs the memory system less
-// than the random 32-byte read of the rank-order gather (which fetches 64 bytes per record and is limited by the
-// activate rate, not by bandwidth): tools/scatter_bench.cu, 10M particles: 0.345 ms against 0.413 ms.
-// Eight lanes share a particle: each writes one 16-byte piece of its line, so a store instruction of the warp covers
-// four whole lines (one lane writing its particle's four 32-byte copies was 2.2x slower in the same benchmark).
-__global__ void __launch_bounds__(256) k_expand_scatter(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, const uint32_t *rankOf)
-{
-	pdl_enter();
-	// four CTAs per 4096-slot sort tile: 1024 slots per CTA, 32 slots per iteration of the CTA
-	const SortTile st = tiles[blockIdx.x >> 2];
-	const uint32_t g = seg_effect(segEffects[st.effect]);
-	const uint32_t slots = tab.state[g].slotCount[tab.state[g].parity];
-	const uint32_t begin = st.tile * kSortTileKeys + (blockIdx.x & 3u) * 1024u;
-	if (begin >= slots) return;
-	const uint32_t segBase = tab.params[g].slotBase;
-	const float4 *state = pool.state + 2ull * (segBase + begin);
-	const uint32_t *rank = rankOf + segBase + begin;
-	const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5); // begin is a multiple of 1024
-	float4 *dst = pool.vertices + 8ull * segBase;
-	const uint32_t piece = threadIdx.x & 7u, sub = threadIdx.x >> 3; // 32 slots per iteration: slot = it * 32 + sub
-	const uint32_t words = min(32u, (slots - begin + 31u) >> 5);
-#pragma unroll 4
-	for (uint32_t it = 0; it < 32; it++) {
-		if (it >= words) break;
-		const uint32_t word = __ldg(mask + it);            // one alive word per iteration of the CTA
-		const uint32_t slot = it * 32 + sub;
-		if (!((word >> sub) & 1u)) continue;                // dead or free slot (slots behind the effect's end carry no bit)
-		const float4 v = __ldcs(state + 2ull * slot + (piece & 1u));
-		const uint32_t r = __ldg(rank + slot);
-		__stcs(dst + 8ull * r + piece, v);
-	}
-}
-
-// rankOf -> sorted slot list (PoolPtrs::vals) of one effect on the scatter expansion, for the parity read-back
-// sprReadStreamSlots only.
-__global__ void k_invert_rank(PoolPtrs pool, uint32_t segBase, uint32_t slots, const uint32_t *rankOf)
-{
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= slots) return;
-	if ((pool.aliveMask[(segBase + i) >> 5] >> (i & 31u)) & 1u) pool.vals[segBase + rankOf[segBase + i]] = i;
-}
-
-void launch_invert_rank(cudaStream_t st, const PoolPtrs &pool, uint32_t segBase, uint32_t slots, const uint32_t *rankOf)
-{
-	if (!slots) return;
-	k_invert_rank<<<(slots + 255) / 256, 256, 0, st>>>(pool, segBase, slots, rankOf);
-}
-
 // Per-device kernel attributes; called once per context: 4 CTAs x 43 KB of shared memory per SM.
 void configure_sort_kernels()
 {
-	cudaFuncSetAttribute(k_sort_pass<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-	cudaFuncSetAttribute(k_sort_pass<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-	cudaFuncSetAttribute(k_sort_pass<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-	cudaFuncSetAttribute(k_sort_pass<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassSmemBytes);
+	cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassSmemBytes);
 	cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes);
 }
 
@@ -709,15 +627,13 @@ void clear_sort_scratch(cudaStream_t st, const SortScratch &sc, uint32_t numSegm
 
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &sc,
 	const uint32_t *segEffects, uint32_t numSegments, uint32_t numBigSegments, const SortTile *tiles, uint32_t numTiles, uint32_t numBigTiles,
-	uint32_t numLargeTiles, const SortTimingHooks *hooks)
+	const SortTimingHooks *hooks)
 {
 	if (!numSegments || !numTiles) return 0;
 	void *tok = nullptr;
 #define T_BEGIN(k) do { if (hooks) tok = hooks->begin(hooks->ctx, k); } while (0)
 #define T_END(k) do { if (hooks) hooks->end(hooks->ctx, k, tok); } while (0)
 	uint32_t *passMask = sc.hist + (size_t)numSegments * 1024; // [numSegments], cleared together with the histograms (clear_sort_scratch)
-	// SPR_SORT_RANK=1: one key per ranking round (the round-1 loop), kept for A/B runs
-	static const bool rank2 = !(getenv("SPR_SORT_RANK") && getenv("SPR_SORT_RANK")[0] == '1');
 	uint32_t launches = 0;
 	if (numBigSegments && numBigTiles) {
 		T_BEGIN(0);
@@ -732,10 +648,8 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 		for (uint32_t p = 0; p < 4; p++) {
 			T_BEGIN(2);
 			uint32_t *lb = sc.lookback + (size_t)p * numBigTiles * 256;
-#define SPR_PASS(F, R) launch_chain(k_sort_pass<F, R>, numBigTiles, 256, 0, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.rankOf, sc.hist, passMask, lb, p)
-			if (p == 0) { if (rank2) SPR_PASS(true, true); else SPR_PASS(true, false); }
-			else { if (rank2) SPR_PASS(false, true); else SPR_PASS(false, false); }
-#undef SPR_PASS
+			if (p == 0) launch_chain(k_sort_pass<true>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, p);
+			else launch_chain(k_sort_pass<false>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, p);
 			T_END(2);
 		}
 		launches += 6;
@@ -747,20 +661,10 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 		T_END(4);
 		launches++;
 	}
-	// the tiles of the effects on the scatter expansion come first in the list
-	if (numLargeTiles) {
-		T_BEGIN(5);
-		launch_chain(k_expand_scatter, numLargeTiles * 4, 256, 0, st, pool, tab, segEffects, tiles, (const uint32_t*)sc.rankOf);
-		T_END(5);
-		launches++;
-	}
-	if (numTiles > numLargeTiles) {
-		T_BEGIN(3);
-		launch_chain(k_expand_sorted, (numTiles - numLargeTiles) * 4, 256, 0, st, pool, tab, segEffects, tiles + numLargeTiles, sc.valsAlt, passMask);
-		T_END(3);
-		launches++;
-	}
-	return launches;
+	T_BEGIN(3);
+	launch_chain(k_expand_sorted, numTiles * kExpandPerTile, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
+	T_END(3);
+	return launches + 1;
 }
 
 } // namespace spr

@@ -14,6 +14,9 @@ from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspear_particles.so")
+# A/B measurement aid: SPR_LIB_VARIANT=name loads spear_b200/libspear_particles.name.so (an experiment build of the same sources)
+if os.environ.get("SPR_LIB_VARIANT"):
+    LIB_PATH = LIB_PATH[:-3] + "." + os.environ["SPR_LIB_VARIANT"] + ".so"
 
 GPU_PARTICLE_DTYPE = np.dtype([("pos", "<f4", 3), ("life", "<f4"), ("vel", "<f4", 3), ("seed", "<f4")])
 

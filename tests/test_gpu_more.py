@@ -166,52 +166,6 @@ def test_sorted_pass_skipping_shapes(oracle_port):
         ctx.close()
 
 
-def test_sorted_scatter_expansion_path(oracle_port, monkeypatch):
-    """Effects beyond Context::largeScatterSlots are expanded in slot order from rankOf[slot] (k_expand_scatter; the last
-    executed radix pass writes the inverse permutation instead of the sorted pairs). The threshold is moved down to
-    40000 slots (SPR_LARGE_SLOTS) so that the path runs on effects the oracle finishes at once: 1, 2, 3 and 4 executed
-    passes (any of them can be the last one), a churning effect with holes and re-used slots, next to a tile-path effect
-    below the threshold and a one-CTA effect in the same frame. sprReadStreamSlots of such an effect is rebuilt from
-    rankOf: slot list and stream must name the same records."""
-    monkeypatch.setenv("SPR_LARGE_SLOTS", "40000")
-    P = _particles()
-    ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 12)
-    try:
-        still = dict(drag=0.0, gravity=(0, 0, 0), lifeTime=1e9, spawnTime=1e9, timeStep=1 / 60)
-        comps = [
-            abi.make_component(burstAmount=50000, **still),                                                               # all keys equal: pass 0 is the last
-            abi.make_component(burstAmount=45000, emitPosition=dict(boxExtent=(0.002, 0.002, 0.002)), **still),           # 2 passes
-            abi.make_component(burstAmount=60000, emitPosition=dict(boxExtent=(4, 2, 4)), emitVelocity=dict(boxExtent=(1, 1, 1)), **still),  # 3 passes
-            abi.make_component(burstAmount=47000, emitPosition=dict(boxExtent=(400, 300, 400)), **still),                # 4 passes
-            comp_big(70_000),                                                                                             # deaths, holes, re-used slots
-            abi.make_component(burstAmount=30000, emitPosition=dict(boxExtent=(4, 2, 4)), **still),                      # tile path below the threshold
-            abi.make_component(burstAmount=9000, emitPosition=dict(boxExtent=(4, 2, 4)), **still),                       # one-CTA path
-        ]
-        trs = [abi.make_transform((1, 2, 3)), abi.make_transform((300, 2, 3)), abi.make_transform((1, 2, 3)), abi.make_transform(CAMERA),
-               abi.make_transform((2, 1, 4)), abi.make_transform((5, 2, 3)), abi.make_transform((-4, 1, 6))]
-        sseed = (1, 4242, 3, 4)
-        s, o = ctx.create_system(sseed), orc.OracleSystem(oracle_port, sseed)
-        ids = [s.add_effect(c, t) for c, t in zip(comps, trs)]
-        assert ids == [o.add_effect(c, t) for c, t in zip(comps, trs)]
-        for f in range(6):
-            fa = abi.make_frame_args(1 / 55, game_time=f / 55, frame_index=f, camera=CAMERA)
-            s.update(ids, fa); o.update(ids, fa)
-            a, b = S.snapshot(o, ids), S.snapshot(s, ids)
-            assert a["rng"] == b["rng"]
-            for e in ids:
-                assert a[e]["info"] == b[e]["info"], "frame %d effect %d" % (f, e)
-                assert np.array_equal(a[e]["free"], b[e]["free"])
-                exp, _ = expected_sorted(a[e]["stream"])
-                assert exp.tobytes() == b[e]["stream"].tobytes(), "frame %d effect %d sorted stream" % (f, e)
-                slots = s.read_stream_slots(e)
-                assert len(slots) == a[e]["info"]["aliveCount"]
-                state = s.read_slots(e)
-                assert state[slots].tobytes() == b[e]["stream"][::4].tobytes(), "frame %d effect %d slot list" % (f, e)
-        assert b[ids[4]]["info"]["freeCount"] > 1000
-    finally:
-        ctx.close()
-
-
 def test_sorted_small_effects_one_cta_path(oracle_port):
     """Effects of at most 18432 slots are sorted whole by one CTA (k_sort_small): 1 to 18 keys per thread, 1 to 4
     executed passes, next to a tile-path effect in the same frame, and an effect that grows across the limit while it
