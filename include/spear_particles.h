@@ -273,6 +273,10 @@ typedef struct SprDrawRecord {
 	uint32_t numParticles;             /* sg_draw(0, numParticles*6, 1), :901 */
 	uint32_t typeUboChanged;           /* 1 when the reference re-applies the type UBO, :880-883 */
 	uint64_t vertexByteOffset;         /* offset of the effect's run inside the device vertex stream */
+	uint32_t uploadedThisFrame;        /* 1 when the reference would sg_append_buffer the effect's stream in this renderMain
+	                                      (its cached copy is older than maxParticleCacheFrames, :861-867) */
+	uint32_t uploadRingSlot;           /* uploadFrameIndex % maxParticleCacheFrames: which of the reference's vertex
+	                                      buffers holds the effect's newest upload (:869) */
 	SprVertexInstanceUbo instanceUbo;  /* :871-876 */
 } SprDrawRecord;
 

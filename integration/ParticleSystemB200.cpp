@@ -13,6 +13,7 @@
 #include "client/ParticleSystem.h"
 
 #include "client/AreaSystem.h"
+#include "client/ParticleTexture.h"
 #include "client/VisFogSystem.h"
 #include "sf/Frustum.h"
 #include "sp/Renderer.h"
@@ -77,19 +78,60 @@ struct ParticleSystemB200 final : ParticleSystem
 	SprSystem *sys = nullptr;
 	std::unordered_map<const sv::ParticleSystemComponent*, std::unique_ptr<ComponentPod>> pods;
 	std::vector<uint32_t> areaIds;
-	sp::Pipeline particlePipe;
+	std::vector<float> updateRadius;        // per effect: the descriptor's updateRadius (EffectType::updateRadius, ParticleSystem.cpp:303)
 	std::vector<SprDrawRecord> lastRecords; // last renderMain, for tools that want to know which effect a draw was
 	uint32_t lastNumSorted = 0;
+
+	// The renderer side of the reference object (ParticleSystem.cpp:24-25, :253-263)
+	static constexpr uint32_t MaxParticlesPerFrame = 4 * 1024;
+	static constexpr uint32_t MaxParticleCacheFrames = 16;
+	static constexpr uint32_t SplineSampleRate = 64, SplineAtlasWidth = 8, SplineAtlasHeight = 256, SplineCountPerType = 2;
+	sp::Texture splineTexture;
+	sp::Buffer vertexBuffers[MaxParticleCacheFrames];
+	sp::Pipeline particlePipe;
+	struct TypeSide { const void *owner = nullptr; sp::Ref<ParticleTexture> texture; }; // what initEffectType keeps outside the C ABI
+	std::vector<TypeSide> typeSide;
+	std::vector<uint32_t> uploadByteOffset; // per effect: Effect::uploadByteOffset (:196)
+	std::vector<SprGpuParticle> staging;    // host copy of one effect's stream on its way into sg_append_buffer
 
 	ParticleSystemB200(const SystemsDesc &desc)
 	{
 		SprContextDesc cd;
-		memset(&cd, 0, sizeof(cd));   // defaults: 4096 particles per frame, 16 cache frames (ParticleSystem.cpp:24-25)
+		memset(&cd, 0, sizeof(cd));
+		cd.maxParticlesPerFrame = MaxParticlesPerFrame;
+		cd.maxParticleCacheFrames = MaxParticleCacheFrames;
 		sprContextCreate(&cd, &ctx);
 		SprSystemsDesc sd;
 		memset(&sd, 0, sizeof(sd));
 		for (int i = 0; i < 4; i++) sd.seed[i] = desc.seed[i];
 		sprSystemCreate(ctx, &sd, &sys);
+
+		// the 16-deep ring of dynamic vertex buffers, the pipeline and the spline atlas, as the reference sets them up (:268-295)
+		for (uint32_t i = 0; i < MaxParticleCacheFrames; i++) {
+			sf::SmallStringBuf<128> name;
+			name.format("particle vertexBuffer %u", i);
+			vertexBuffers[i].initDynamicVertex(name.data, sizeof(SprGpuParticle) * 4 * MaxParticlesPerFrame);
+		}
+		{
+			uint32_t flags = sp::PipeIndex16|sp::PipeDepthTest|sp::PipeBlendPremultiply;
+			sg_pipeline_desc &d = particlePipe.init(gameShaders.particle, flags);
+			d.blend.src_factor_alpha = SG_BLENDFACTOR_ZERO;
+			d.blend.dst_factor_alpha = SG_BLENDFACTOR_ONE;
+			d.layout.attrs[0].format = SG_VERTEXFORMAT_FLOAT4;
+			d.layout.attrs[1].format = SG_VERTEXFORMAT_FLOAT4;
+		}
+		{
+			sg_image_desc d = { };
+			d.usage = SG_USAGE_IMMUTABLE;
+			d.bqq_copy_target = true;
+			d.pixel_format = SG_PIXELFORMAT_RGBA8;
+			d.mag_filter = SG_FILTER_LINEAR;
+			d.min_filter = SG_FILTER_LINEAR;
+			d.width = SplineSampleRate * SplineAtlasWidth;
+			d.height = SplineAtlasHeight * SplineCountPerType;
+			d.label = "ParticleSystem splineTexture";
+			splineTexture.init(d);
+		}
 	}
 
 	~ParticleSystemB200()
@@ -145,12 +187,59 @@ struct ParticleSystemB200 final : ParticleSystem
 		return &slot->pod;
 	}
 
+	// The part of initEffectType that stays on the renderer's side (ParticleSystem.cpp:302, :421-449): the type's
+	// texture reference and its two LUT rows copied into the spline atlas at the type's cell. The library bakes the
+	// rows (sprGetEffectTypeLut); a type id is (re)initialised whenever another descriptor takes it over.
+	void initTypeSide(uint32_t typeId, const sf::Box<sv::ParticleSystemComponent> &c)
+	{
+		if (typeSide.size() <= typeId) typeSide.resize(typeId + 1);
+		TypeSide &side = typeSide[typeId];
+		if (side.owner == (const void*)c.ptr) return;
+		side.owner = (const void*)c.ptr;
+		side.texture.load(c->texture);
+
+		uint8_t splineTex[SPR_SPLINE_LUT_BYTES];
+		sprGetEffectTypeLut(sys, typeId, splineTex);
+		uint32_t atlasX = typeId / SplineAtlasHeight;
+		uint32_t atlasY = typeId % SplineAtlasHeight;
+		uint32_t x = atlasX * SplineSampleRate;
+		uint32_t y = atlasY * SplineCountPerType;
+
+		sg_image_desc d = { };
+		d.width = SplineSampleRate;
+		d.height = SplineCountPerType;
+		d.pixel_format = SG_PIXELFORMAT_RGBA8;
+		d.content.subimage[0][0].ptr = splineTex;
+		d.content.subimage[0][0].size = sizeof(splineTex);
+		sg_image stagingImage = sg_make_image(&d);
+		{
+			sg_bqq_subimage_rect rect;
+			rect.src_x = 0;
+			rect.src_y = 0;
+			rect.dst_x = (int)x;
+			rect.dst_y = (int)y;
+			rect.dst_z = 0;
+			rect.width = (int)SplineSampleRate;
+			rect.height = (int)SplineCountPerType;
+
+			sg_bqq_subimage_copy_desc desc;
+			desc.dst_image = splineTexture.image;
+			desc.src_image = stagingImage;
+			desc.rects = &rect;
+			desc.num_rects = 1;
+			desc.num_mips = 1;
+			sg_bqq_copy_subimages(&desc);
+		}
+		sg_destroy_image(stagingImage);
+	}
+
 	// -- cl::ParticleSystem
 
 	virtual uint32_t reserveEffectType(Systems &, const sf::Box<sv::ParticleSystemComponent> &c) override
 	{
 		uint32_t typeId = 0;
 		sprReserveEffectType(sys, pod(c), &typeId);
+		initTypeSide(typeId, c);
 		return typeId;
 	}
 
@@ -164,6 +253,17 @@ struct ParticleSystemB200 final : ParticleSystem
 		SprTransform t = convertTransform(transform);
 		uint32_t effectId = 0;
 		sprAddEffect(sys, entityId, componentIndex, pod(c), &t, &effectId);
+		{
+			// addEffect reserves the effect's type itself (:739); while the effect holds that reference a reserve /
+			// release pair only reads the id back
+			uint32_t typeId = 0;
+			sprReserveEffectType(sys, pod(c), &typeId);
+			sprReleaseEffectType(sys, pod(c));
+			initTypeSide(typeId, c);
+		}
+		if (updateRadius.size() <= effectId) { updateRadius.resize(effectId + 1, 0.0f); uploadByteOffset.resize(effectId + 1, 0); }
+		updateRadius[effectId] = c->updateRadius;
+		uploadByteOffset[effectId] = 0;
 		sf::Sphere sphere = { transform.position, c->updateRadius };
 		uint32_t areaId = systems.area->addSphereArea(AreaGroup::ParticleEffect, effectId, sphere, Area::Activate | Area::Visibility);
 		if (areaIds.size() <= effectId) areaIds.resize(effectId + 1);
@@ -203,6 +303,18 @@ struct ParticleSystemB200 final : ParticleSystem
 
 		for (uint32_t i = 0; i < out.numRecords; i++) {
 			const SprDrawRecord &d = out.records[i];
+
+			// The library has made the reference's upload decision (cache age and the per-frame budget, :861-863): an
+			// effect whose cached copy is stale comes back to the host -- at most MaxParticlesPerFrame particles a frame,
+			// 512 KB -- and goes into this frame's ring buffer exactly as the reference's own array does (:865).
+			if (d.uploadedThisFrame) {
+				staging.resize((size_t)d.numParticles * 4);
+				uint32_t numVertices = 0;
+				sprReadVertexStream(sys, d.effectId, staging.data(), (uint32_t)staging.size(), &numVertices);
+				uploadByteOffset[d.effectId] = (uint32_t)sg_append_buffer(vertexBuffers[d.uploadRingSlot].buffer, staging.data(), (int)(staging.size() * sizeof(SprGpuParticle)));
+			}
+			sp::Buffer &vertexBuffer = vertexBuffers[d.uploadRingSlot];
+
 			particlePipe.bind();
 			if (d.typeUboChanged) {
 				SprVertexTypeUbo typeUbo;
@@ -210,11 +322,20 @@ struct ParticleSystemB200 final : ParticleSystem
 				sg_apply_uniforms(SG_SHADERSTAGE_VS, SLOT_Particle_VertexType, &typeUbo, sizeof(typeUbo));
 			}
 			sg_apply_uniforms(SG_SHADERSTAGE_VS, SLOT_Particle_VertexInstance, &d.instanceUbo, sizeof(d.instanceUbo));
-			// The vertices live in GPU memory at out.deviceVertices + d.vertexByteOffset. A real renderer binds
-			// that range through CUDA-graphics interop; the sokol bindings below carry the offset only.
+
+			sg_image image = ParticleTexture::defaultImage;
+			const TypeSide &side = typeSide[d.typeId];
+			if (side.texture.isLoaded() && side.texture->image.id) {
+				image = side.texture->image;
+			}
+
 			sg_bindings binds = { };
-			binds.vertex_buffer_offsets[0] = (int)d.vertexByteOffset;
+			binds.vertex_buffers[0] = vertexBuffer.buffer;
+			binds.vertex_buffer_offsets[0] = (int)uploadByteOffset[d.effectId];
 			binds.index_buffer = sp::getSharedQuadIndexBuffer();
+			binds.vs_images[SLOT_Particle_u_SplineTexture] = splineTexture.image;
+			binds.vs_images[SLOT_Particle_u_VisFogTexture] = visFog.image;
+			binds.fs_images[SLOT_Particle_u_Texture] = image;
 			sg_apply_bindings(&binds);
 			sg_draw(0, (int)d.numParticles * 6, 1);
 		}
@@ -229,8 +350,9 @@ struct ParticleSystemB200 final : ParticleSystem
 		u.transform = convertTransform(update.transform);
 		memcpy(u.entityToWorld.v, update.entityToWorld.v, sizeof(float) * 12);
 		sprUpdateTransform(sys, ec.userId, &u);
-		// updateRadius is a property of the descriptor; the area system keeps the sphere (ParticleSystem.cpp:782-783)
-		(void)systems;
+		// the activation / visibility sphere follows the emitter (ParticleSystem.cpp:782-783)
+		sf::Sphere sphere = { update.transform.position, ec.userId < updateRadius.size() ? updateRadius[ec.userId] : 0.0f };
+		if (ec.userId < areaIds.size()) systems.area->updateSphereArea(areaIds[ec.userId], sphere);
 	}
 
 	bool prepareForRemove(Systems &, uint32_t, const EntityComponent &ec, const FrameArgs &frameArgs) override

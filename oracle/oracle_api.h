@@ -42,6 +42,16 @@ ORC_API void orc_update(void *sys, const uint32_t *activeIds, uint32_t numActive
 ORC_API uint32_t orc_render(void *sys, const uint32_t *visibleIds, uint32_t numVisible,
 	const SprRenderArgs *args, SprDrawRecord *out, uint32_t capacity, uint32_t *numSorted);
 
+/* What the last orc_render handed to sokol (reference harness and adapter harness only; the plain-C port has no
+ * renderer side): one entry per sg_draw with the bindings applied for it, and one per sg_append_buffer call. */
+typedef struct OrcDrawCapture { uint32_t vertexBufferRing, vertexOffset, indexBuffer, vsSplineImage, vsVisFogImage, fsTextureImage, numElements, _pad; } OrcDrawCapture;
+typedef struct OrcAppendCapture { uint32_t bufferRing, offset, numBytes, _pad; uint64_t fnv1a64; } OrcAppendCapture;
+ORC_API uint32_t orc_render_capture(void *sys, OrcDrawCapture *draws, uint32_t capDraws, OrcAppendCapture *appends, uint32_t capAppends, uint32_t *numAppends);
+/* The 512 x 512 RGBA8 spline atlas as the sg_make_image / sg_bqq_copy_subimages calls left it; returns 0 if untouched. */
+ORC_API int orc_read_atlas(void *sys, uint8_t *out);
+/* Sphere areas registered with the harness's area system: 5 floats each {effect id, x, y, z, radius}; returns the count. */
+ORC_API uint32_t orc_area_spheres(void *sys, float *out, uint32_t capacity);
+
 ORC_API void orc_effect_info(void *sys, uint32_t effectId, SprEffectInfo *out);
 ORC_API uint32_t orc_read_free(void *sys, uint32_t effectId, uint32_t *out, uint32_t capacity);
 ORC_API uint32_t orc_read_stream(void *sys, uint32_t effectId, SprGpuParticle *out, uint32_t capacityVertices);

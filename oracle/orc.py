@@ -29,6 +29,19 @@ _PATHS = {
 
 GPU_PARTICLE_DTYPE = np.dtype([("pos", "<f4", 3), ("life", "<f4"), ("vel", "<f4", 3), ("seed", "<f4")])
 
+
+
+class DrawCapture(C.Structure):
+    """OrcDrawCapture (oracle_api.h): the bindings applied for one sg_draw of the last orc_render."""
+    _fields_ = [("vertexBufferRing", C.c_uint32), ("vertexOffset", C.c_uint32), ("indexBuffer", C.c_uint32), ("vsSplineImage", C.c_uint32),
+                ("vsVisFogImage", C.c_uint32), ("fsTextureImage", C.c_uint32), ("numElements", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class AppendCapture(C.Structure):
+    """OrcAppendCapture: one sg_append_buffer call of the last orc_render."""
+    _fields_ = [("bufferRing", C.c_uint32), ("offset", C.c_uint32), ("numBytes", C.c_uint32), ("_pad", C.c_uint32), ("fnv1a64", C.c_uint64)]
+
+
 _libs = {}
 
 
@@ -73,6 +86,13 @@ def _load(kind):
     lib.orc_type_lut.argtypes = [vp, u32, vp]
     lib.orc_type_ubo.argtypes = [vp, u32, C.POINTER(abi.VertexTypeUbo)]
     lib.orc_make_frustum.argtypes = [C.POINTER(abi.Mat44), C.c_float, C.POINTER(abi.Frustum)]
+    if hasattr(lib, "orc_render_capture"):   # reference and adapter harnesses only (the plain-C port has no renderer side)
+        lib.orc_render_capture.restype = u32
+        lib.orc_render_capture.argtypes = [vp, C.POINTER(DrawCapture), u32, C.POINTER(AppendCapture), u32, C.POINTER(u32)]
+        lib.orc_read_atlas.restype = C.c_int
+        lib.orc_read_atlas.argtypes = [vp, vp]
+        lib.orc_area_spheres.restype = u32
+        lib.orc_area_spheres.argtypes = [vp, C.POINTER(C.c_float), u32]
     lib.orc_bench_steps.restype = C.c_double
     lib.orc_bench_steps.argtypes = [vp, C.POINTER(u32), u32, C.POINTER(abi.FrameArgs), u32, C.POINTER(C.c_uint64)]
     _libs[kind] = lib
@@ -137,6 +157,27 @@ class OracleSystem:
         nsorted = C.c_uint32(0)
         n = self.lib.orc_render(self.h, p, len(arr), C.byref(render_args), recs, cap, C.byref(nsorted))
         return [recs[i] for i in range(n)], nsorted.value
+
+    def render_capture(self):
+        """(draws, appends) of the last render(): what went through sg_apply_bindings + sg_draw and sg_append_buffer."""
+        draws = (DrawCapture * 256)()
+        appends = (AppendCapture * 256)()
+        na = C.c_uint32(0)
+        nd = self.lib.orc_render_capture(self.h, draws, 256, appends, 256, C.byref(na))
+        assert nd <= 256 and na.value <= 256
+        return ([dict(ring=d.vertexBufferRing, offset=d.vertexOffset, index=d.indexBuffer, vs=[d.vsSplineImage, d.vsVisFogImage],
+                      fs=d.fsTextureImage, elements=d.numElements) for d in draws[:nd]],
+                [dict(ring=a.bufferRing, offset=a.offset, bytes=a.numBytes, hash="%016x" % a.fnv1a64) for a in appends[:na.value]])
+
+    def read_atlas(self):
+        """The 512 x 512 RGBA8 spline atlas as the sg_* calls left it (None if never written)."""
+        out = np.zeros((512, 512, 4), dtype=np.uint8)
+        return out if self.lib.orc_read_atlas(self.h, out.ctypes.data) else None
+
+    def area_spheres(self):
+        buf = (C.c_float * (5 * 256))()
+        n = self.lib.orc_area_spheres(self.h, buf, 256)
+        return [[float(buf[5 * i + k]) for k in range(5)] for i in range(min(n, 256))]
 
     def effect_info(self, effect_id):
         info = abi.EffectInfo()

@@ -32,6 +32,7 @@ namespace cl { SprSystem *sprAdapterSystem(ParticleSystem *ps); SprContext *sprA
 #include "sf/Geometry.h"
 
 #include <chrono>
+#include <map>
 #include <unordered_map>
 #include <vector>
 #include <string.h>
@@ -47,12 +48,15 @@ void GameShaders::load() { }
 
 namespace sp {
 
-sg_buffer g_hackSharedQuadIndexBuffer;
+sg_buffer g_hackSharedQuadIndexBuffer = { 7777 };
 
 Buffer::Buffer() { }
 Buffer::~Buffer() { }
 void Buffer::reset() { }
-void Buffer::initDynamicVertex(const char *, size_t) { static uint32_t next; buffer.id = ++next; }
+// dynamic vertex buffers get the ids 1000, 1001, ... in creation order: a system's ring (ParticleSystem.cpp:268-272)
+// is [first id of the system, +16)
+static uint32_t g_nextVertexBufferId = 1000;
+void Buffer::initDynamicVertex(const char *, size_t) { buffer.id = g_nextVertexBufferId++; }
 
 Pipeline::Pipeline() { }
 Pipeline::~Pipeline() { }
@@ -75,6 +79,7 @@ Asset::~Asset() { }
 Asset *Asset::impCreate(AssetType *, const sf::Symbol &, const AssetProps &) { return nullptr; }
 bool Asset::isLoaded() const { return false; }
 void Asset::release() { }
+void Asset::retain() { }
 
 }
 
@@ -107,10 +112,27 @@ struct CapturedDraw
 	uint32_t numElements;
 	uint32_t vertexBuffer;
 	uint32_t vertexOffset;
+	uint32_t indexBuffer, vsImage0, vsImage1, fsImage0;
 };
 static std::vector<CapturedDraw> g_draws;
 static CapturedDraw g_curDraw;
-static uint32_t g_appendOffsets[64];
+// what sg_append_buffer was given during the last renderMain (ParticleSystem.cpp:865)
+struct CapturedAppend { uint32_t buffer, offset, numBytes; uint64_t hash; };
+static std::vector<CapturedAppend> g_appends;
+static std::unordered_map<uint32_t, uint32_t> g_appendOffsets;
+// the spline atlas as the sg_make_image / sg_bqq_copy_subimages calls leave it (:253-258, :421-449): 512 x 512 RGBA8
+static const uint32_t kAtlasRes = 512;
+static std::vector<uint8_t> *g_curAtlas;     // atlas of the system whose call is in progress
+static std::vector<uint8_t> g_stagingContent; // content of the last sg_make_image
+static uint32_t g_stagingW, g_stagingH;
+
+static uint64_t fnv1a64(const void *data, size_t n)
+{
+	uint64_t h = 0xcbf29ce484222325ull;
+	const uint8_t *p = (const uint8_t*)data;
+	for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 0x100000001b3ull;
+	return h;
+}
 
 extern "C" {
 
@@ -120,21 +142,46 @@ sg_image sg_make_image(const sg_image_desc *desc)
 		memcpy(g_lastLut, desc->content.subimage[0][0].ptr, SPR_SPLINE_LUT_BYTES);
 		g_lutCaptured = true;
 	}
+	g_stagingContent.clear();
+	if (desc->content.subimage[0][0].ptr) {
+		const uint8_t *p = (const uint8_t*)desc->content.subimage[0][0].ptr;
+		g_stagingContent.assign(p, p + desc->content.subimage[0][0].size);
+	}
+	g_stagingW = (uint32_t)desc->width; g_stagingH = (uint32_t)desc->height;
 	sg_image img; img.id = 2; return img;
 }
 void sg_destroy_image(sg_image) { }
-void sg_bqq_copy_subimages(const sg_bqq_subimage_copy_desc *) { }
-int sg_append_buffer(sg_buffer buf, const void *, int numBytes)
+void sg_bqq_copy_subimages(const sg_bqq_subimage_copy_desc *d)
 {
-	uint32_t &off = g_appendOffsets[buf.id % 64];
+	if (!g_curAtlas || d->dst_image.id != 1 || d->src_image.id != 2) return;
+	if (g_curAtlas->empty()) g_curAtlas->assign((size_t)kAtlasRes * kAtlasRes * 4, 0);
+	for (int r = 0; r < d->num_rects; r++) {
+		const sg_bqq_subimage_rect &rc = d->rects[r];
+		for (int y = 0; y < rc.height; y++) {
+			for (int x = 0; x < rc.width; x++) {
+				size_t src = ((size_t)(rc.src_y + y) * g_stagingW + (size_t)(rc.src_x + x)) * 4;
+				size_t dst = ((size_t)(rc.dst_y + y) * kAtlasRes + (size_t)(rc.dst_x + x)) * 4;
+				if (src + 4 <= g_stagingContent.size() && dst + 4 <= g_curAtlas->size()) memcpy(g_curAtlas->data() + dst, g_stagingContent.data() + src, 4);
+			}
+		}
+	}
+}
+int sg_append_buffer(sg_buffer buf, const void *data, int numBytes)
+{
+	uint32_t &off = g_appendOffsets[buf.id];
 	int r = (int)off;
 	off += (uint32_t)numBytes;
+	g_appends.push_back({ buf.id, (uint32_t)r, (uint32_t)numBytes, fnv1a64(data, (size_t)numBytes) });
 	return r;
 }
 void sg_apply_bindings(const sg_bindings *b)
 {
 	g_curDraw.vertexBuffer = b->vertex_buffers[0].id;
 	g_curDraw.vertexOffset = (uint32_t)b->vertex_buffer_offsets[0];
+	g_curDraw.indexBuffer = b->index_buffer.id;
+	g_curDraw.vsImage0 = b->vs_images[SLOT_Particle_u_SplineTexture].id;
+	g_curDraw.vsImage1 = b->vs_images[SLOT_Particle_u_VisFogTexture].id;
+	g_curDraw.fsImage0 = b->fs_images[SLOT_Particle_u_Texture].id;
 }
 void sg_apply_uniforms(sg_shader_stage, int slot, const void *data, int numBytes)
 {
@@ -171,11 +218,16 @@ struct StubAreaSystem final : cl::AreaSystem
 	void updateBoxArea(uint32_t, const sf::Bounds3 &) override { }
 	void updateBoxArea(uint32_t, const sf::Bounds3 &, const sf::Mat34 &) override { }
 	void removeBoxArea(uint32_t) override { }
-	uint32_t addSphereArea(cl::AreaGroup, uint32_t, const sf::Sphere &, uint32_t) override { return nextId++; }
+	// the sphere areas the particle system registers and keeps current (ParticleSystem.cpp:762-763, :782-783, :801)
+	struct SphereArea { uint32_t userId; float x, y, z, r; };
+	std::map<uint32_t, SphereArea> spheres;
+	uint32_t addSphereArea(cl::AreaGroup, uint32_t userId, const sf::Sphere &s, uint32_t) override
+	{ spheres[nextId] = { userId, s.origin.x, s.origin.y, s.origin.z, s.radius }; return nextId++; }
 	uint32_t addSphereArea(cl::AreaGroup, uint32_t, const sf::Sphere &, const sf::Mat34 &, uint32_t) override { return nextId++; }
-	void updateSphereArea(uint32_t, const sf::Sphere &) override { }
+	void updateSphereArea(uint32_t areaId, const sf::Sphere &s) override
+	{ auto it = spheres.find(areaId); if (it != spheres.end()) { it->second.x = s.origin.x; it->second.y = s.origin.y; it->second.z = s.origin.z; it->second.r = s.radius; } }
 	void updateSphereArea(uint32_t, const sf::Sphere &, const sf::Mat34 &) override { }
-	void removeSphereArea(uint32_t) override { }
+	void removeSphereArea(uint32_t areaId) override { spheres.erase(areaId); }
 	void optimize() override { }
 	void queryFrustum(sf::Array<cl::Area> &, uint32_t, const sf::Frustum &) const override { }
 	void queryFrustumBounds(sf::Array<cl::AreaBounds> &, uint32_t, const sf::Frustum &) const override { }
@@ -203,6 +255,8 @@ struct RefSystem
 #endif
 	std::unordered_map<const SprParticleSystemComponent*, sf::Box<sv::ParticleSystemComponent>> comps;
 	std::unordered_map<uint32_t, std::vector<uint8_t>> luts;
+	std::vector<uint8_t> atlas;          // spline atlas texels as the sg_* calls of this system left them
+	uint32_t firstVertexBuffer = 0;      // id of ring buffer 0 of this system
 	std::vector<uint64_t> simSteps;
 	cl::VisibleAreas areas;
 	StubVisFog visFog;
@@ -343,6 +397,8 @@ void *orc_create(const SprSystemsDesc *desc)
 	d.persist.zoom = desc->persistZoom;
 	for (int i = 0; i < 4; i++) d.seed[i] = desc->seed[i];
 	rs->systems.area = sf::box<StubAreaSystem>();
+	rs->firstVertexBuffer = sp::g_nextVertexBufferId;
+	g_curAtlas = &rs->atlas;
 	rs->ps = cl::ParticleSystem::create(d);
 #ifdef SPR_ADAPTER
 	rs->spr = cl::sprAdapterSystem(rs->ps.ptr);
@@ -354,12 +410,13 @@ void *orc_create(const SprSystemsDesc *desc)
 	return rs;
 }
 
-void orc_destroy(void *sys) { delete (RefSystem*)sys; }
+void orc_destroy(void *sys) { if (g_curAtlas == &((RefSystem*)sys)->atlas) g_curAtlas = nullptr; delete (RefSystem*)sys; }
 
 uint32_t orc_reserve_type(void *sys, const SprParticleSystemComponent *c)
 {
 	RefSystem *rs = (RefSystem*)sys;
 	g_lutCaptured = false;
+	g_curAtlas = &rs->atlas;
 	uint32_t typeId = rs->ps->reserveEffectType(rs->systems, getComponent(rs, c));
 	if (g_lutCaptured) rs->luts[typeId] = std::vector<uint8_t>(g_lastLut, g_lastLut + SPR_SPLINE_LUT_BYTES);
 	return typeId;
@@ -376,6 +433,7 @@ uint32_t orc_add_effect(void *sys, uint32_t entityId, uint8_t componentIndex,
 {
 	RefSystem *rs = (RefSystem*)sys;
 	g_lutCaptured = false;
+	g_curAtlas = &rs->atlas;
 	rs->ps->addEffect(rs->systems, entityId, componentIndex, getComponent(rs, c), convertTransform(*transform));
 	uint32_t effectId = cl::g_lastAddedEffectId;
 #ifndef SPR_ADAPTER
@@ -440,6 +498,7 @@ uint32_t orc_render(void *sys, const uint32_t *visibleIds, uint32_t numVisible,
 	}
 	rs->visFog.worldMad = sf::Vec4(args->visFogWorldMad.x, args->visFogWorldMad.y, args->visFogWorldMad.z, args->visFogWorldMad.w);
 	g_draws.clear();
+	g_appends.clear();
 	memset(&g_curDraw, 0, sizeof(g_curDraw));
 	rs->ps->renderMain(&rs->visFog, rs->areas, ra);
 #ifdef SPR_ADAPTER
@@ -583,6 +642,46 @@ void orc_type_ubo(void *sys, uint32_t typeId, SprVertexTypeUbo *out)
 }
 
 #endif
+
+// What the last orc_render submitted through sg_append_buffer / sg_apply_bindings, for the adapter-against-reference
+// comparison of row N1. Vertex buffers are reported as ring indices 0..15 of the system (0xffffffff = none bound).
+uint32_t orc_render_capture(void *sys, OrcDrawCapture *draws, uint32_t capDraws, OrcAppendCapture *appends, uint32_t capAppends, uint32_t *numAppends)
+{
+	RefSystem *rs = (RefSystem*)sys;
+	auto ring = [&](uint32_t id) { return id >= rs->firstVertexBuffer && id < rs->firstVertexBuffer + 64 ? id - rs->firstVertexBuffer : 0xffffffffu; };
+	uint32_t n = 0;
+	for (; n < g_draws.size() && n < capDraws; n++) {
+		const CapturedDraw &d = g_draws[n];
+		draws[n] = { ring(d.vertexBuffer), d.vertexOffset, d.indexBuffer, d.vsImage0, d.vsImage1, d.fsImage0, d.numElements, 0 };
+	}
+	uint32_t m = 0;
+	for (; m < g_appends.size() && m < capAppends; m++) appends[m] = { ring(g_appends[m].buffer), g_appends[m].offset, g_appends[m].numBytes, 0, g_appends[m].hash };
+	if (numAppends) *numAppends = (uint32_t)g_appends.size();
+	return (uint32_t)g_draws.size();
+}
+
+// The sphere areas currently registered with the (stub) area system: 5 floats per area {effect id, x, y, z, radius},
+// ascending area id. Returns the number of areas.
+uint32_t orc_area_spheres(void *sys, float *out, uint32_t capacity)
+{
+	RefSystem *rs = (RefSystem*)sys;
+	StubAreaSystem *area = (StubAreaSystem*)rs->systems.area.ptr;
+	uint32_t n = 0;
+	for (const auto &kv : area->spheres) {
+		if (n < capacity) { float *o = out + 5 * n; o[0] = (float)kv.second.userId; o[1] = kv.second.x; o[2] = kv.second.y; o[3] = kv.second.z; o[4] = kv.second.r; }
+		n++;
+	}
+	return n;
+}
+
+// The 512 x 512 RGBA8 spline atlas (ParticleSystem.cpp:253-258, :421-449); returns 0 when nothing was ever copied into it.
+int orc_read_atlas(void *sys, uint8_t *out)
+{
+	RefSystem *rs = (RefSystem*)sys;
+	if (rs->atlas.empty()) { memset(out, 0, (size_t)kAtlasRes * kAtlasRes * 4); return 0; }
+	memcpy(out, rs->atlas.data(), rs->atlas.size());
+	return 1;
+}
 
 void orc_make_frustum(const SprMat44 *worldToClip, float clipNearW, SprFrustum *out)
 {

@@ -152,7 +152,8 @@ class FrameArgs(C.Structure):
 
 class DrawRecord(C.Structure):
     _fields_ = [("effectId", C.c_uint32), ("typeId", C.c_uint32), ("numParticles", C.c_uint32),
-                ("typeUboChanged", C.c_uint32), ("vertexByteOffset", C.c_uint64), ("instanceUbo", VertexInstanceUbo)]
+                ("typeUboChanged", C.c_uint32), ("vertexByteOffset", C.c_uint64), ("uploadedThisFrame", C.c_uint32),
+                ("uploadRingSlot", C.c_uint32), ("instanceUbo", VertexInstanceUbo)]
 
 
 class ShadedVertex(C.Structure):

@@ -1044,12 +1044,16 @@ void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisi
 	for (const SortedEffect &s : sorted) {                                // :851-902
 		HostEffect &E = effects[s.effectId];
 		uint32_t numParticles = s.numParticles;
+		bool uploaded = false;
 		if (frame - E.uploadFrameIndex >= ctx->maxParticleCacheFrames) {  // :861-867
 			if (numParticles >= frameParticlesLeft) break;               // `return`, :862
 			frameParticlesLeft -= numParticles;
 			E.uploadFrameIndex = frame;
+			uploaded = true;
 		}
 		SprDrawRecord &r = drawRecords[numRecords++];                     // filled in place
+		r.uploadedThisFrame = uploaded ? 1u : 0u;
+		r.uploadRingSlot = (uint32_t)(E.uploadFrameIndex % ctx->maxParticleCacheFrames); // :869
 		r.effectId = s.effectId;
 		r.typeId = E.typeId;
 		r.numParticles = numParticles;

@@ -62,6 +62,54 @@ def render_scene(system):
     return frames
 
 
+def render_capture_scene(o):
+    """Row N1: what the renderer side of cl::ParticleSystem hands to sokol over 40 frames -- the bytes appended to the
+    16-deep vertex-buffer ring (ParticleSystem.cpp:861-867: re-upload when the cached copy is 16 frames old, per-frame
+    budget of 4096 particles with the early `return`), the bindings of every draw (:892-899), the spline atlas texels
+    (:421-449, with a type id released and taken over by another descriptor) and the sphere areas kept current by
+    updateTransform (:782-783). `o` is an OracleSystem of kind "reference" or "adapter"."""
+    comps = [S.comp_c2(k, burst=420, churn=True) for k in range(4)] + [S.comp_local_space()]
+    ids = []
+    for i in range(12):
+        tr = abi.make_transform((4.0 * (i % 4), 0.0, 4.0 * (i // 4)), (0, 0.38268343, 0, 0.92387953), 1.0)
+        ids.append(o.add_effect(comps[i % len(comps)], tr))
+    extra = abi.make_component(timeStep=1 / 60, burstAmount=300, spawnTime=0.01, lifeTime=0.5, renderOrder=2.0,
+                               emitPosition=dict(boxExtent=(1, 1, 1)), scaleSpline=[(0, 1), (1, 0)], gradient=dict(points=[(0, (0.2, 0.4, 1.0))]))
+    other = abi.make_component(timeStep=1 / 60, burstAmount=200, spawnTime=1e9, lifeTime=3.0, renderOrder=-1.0,
+                               emitPosition=dict(sphere=dict(minRadius=0.1, maxRadius=1.0)), alphaSpline=[(0, 0.3), (1, 0.9)])
+    ra = make_render_args()
+    frames = []
+    where = {}
+    for frame in range(40):
+        if frame == 5:
+            ids.append(o.add_effect(extra, abi.make_transform((1, 1, 1))))
+        if frame == 12:                       # the only effect of `extra` goes away: its type id is free again ...
+            o.remove(ids.pop())
+        if frame == 14:                       # ... and `other` takes it over: its LUT rows replace the cell's texels
+            ids.append(o.add_effect(other, abi.make_transform((2, 0, 2))))
+        if frame in (3, 9, 21):               # moving emitters: the area spheres follow
+            for e in ids[:4]:
+                tr = abi.make_transform((0.5 * frame + e, 0.25 * e, -1.0 * e), (0, 0, 0, 1), 1.0 + 0.1 * e)
+                o.update_transform(e, S.transform_update(where.get(e, abi.make_transform()), tr))
+                where[e] = tr
+        fa = abi.make_frame_args(0.0171, game_time=frame * 0.0171, frame_index=frame, camera=S.CAMERA)
+        # from frame 18 on every other effect stops being simulated: its cached upload is drawn from the ring slot it
+        # went into and is appended again once it is 16 frames old
+        o.update(ids if frame < 18 else ids[::2], fa)
+        vis = ids if frame % 2 == 0 else ids[::-1]
+        recs, nsorted = o.render(vis, ra, capacity=64)
+        draws, appends = o.render_capture()
+        frames.append(dict(numSorted=nsorted, draws=draws, appends=appends, records=[
+            dict(effectId=r.effectId, typeId=r.typeId, numParticles=r.numParticles, typeUboChanged=r.typeUboChanged,
+                 ubo=hashlib.sha256(bytes(r.instanceUbo)[:152]).hexdigest()[:16]) for r in recs]))
+    atlas = o.read_atlas()
+    assert atlas is not None
+    atlas[1::2, :, 3] = 0                     # gradient rows: the alpha byte is uninitialised stack in the reference (:326, :366-400)
+    used = sorted(set(int(y) // 2 + 256 * (int(x) // 64) for y, x in zip(*np.nonzero(atlas.any(axis=2)))))
+    return dict(frames=frames, atlas=hashlib.sha256(atlas.tobytes()).hexdigest(), atlasCells=used,
+                spheres=[[S.f32_bits(v) for v in s] for s in o.area_spheres()])
+
+
 def main():
     build_ref.build(verbose=False)
     out = {}
@@ -123,6 +171,7 @@ def main():
     dump("rng.json", dict(rows=rows, after50="%016x" % r2.s))
 
     dump("render.json", render_scene(orc.OracleSystem("reference", (1, 5, 3, 4))))
+    dump("render_capture.json", render_capture_scene(orc.OracleSystem("reference", (1, 6, 3, 4))))
 
 
 if __name__ == "__main__":

@@ -44,3 +44,25 @@ def test_adapter_render_main_matches_reference_golden(adapter):
         assert render_scene(o) == g
     finally:
         o.close()
+
+
+def test_adapter_renderer_side_matches_reference_capture(adapter):
+    """Everything the adapter hands to sokol, against the reference's own calls captured by the same harness stubs
+    (tests/golden/render_capture.json): the bytes appended to the 16-deep vertex-buffer ring and the offsets returned
+    (ParticleSystem.cpp:861-867), the buffer / offset / index buffer / images bound for every draw (:892-899), the
+    draw sizes, the spline atlas texels after initEffectType's sg_make_image + sg_bqq_copy_subimages (:421-449, gradient
+    alpha bytes masked: uninitialised in the reference) and the sphere areas after updateTransform (:782-783)."""
+    from golden.make_golden import render_capture_scene
+    g = json.load(open(os.path.join(GOLDEN, "render_capture.json")))
+    o = orc.OracleSystem(adapter, (1, 6, 3, 4))
+    try:
+        got = render_capture_scene(o)
+    finally:
+        o.close()
+    assert got["atlasCells"] == g["atlasCells"] and got["atlas"] == g["atlas"]
+    assert got["spheres"] == g["spheres"]
+    for f, (a, b) in enumerate(zip(g["frames"], got["frames"])):
+        assert a["records"] == b["records"], "frame %d draw records" % f
+        assert a["appends"] == b["appends"], "frame %d sg_append_buffer calls" % f
+        assert a["draws"] == b["draws"], "frame %d bindings" % f
+    assert len(g["frames"]) == len(got["frames"]) == 40

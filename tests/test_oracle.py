@@ -112,3 +112,12 @@ def test_sorted_order_oracle_is_a_permutation(oracle_port):
     assert sorted(order.tolist()) == list(range(len(st) // 4))
     k = S.sort_key(exp[::4])
     assert (k[1:] >= k[:-1]).all()
+
+
+def test_reference_renderer_capture_is_reproducible(oracle_ref):
+    """tests/golden/render_capture.json (row N1: what cl::ParticleSystem::renderMain hands to sokol) comes out of the
+    reference build again, bit for bit -- the adapter on the GPU box is compared with this file."""
+    import json
+    from golden.make_golden import render_capture_scene
+    got = render_capture_scene(orc.OracleSystem(oracle_ref, (1, 6, 3, 4)))
+    assert json.loads(json.dumps(got)) == golden("render_capture.json")
