@@ -238,20 +238,31 @@ def run_ours(args, rank, world):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- timed region: exactly K steps, CUDA events on the launching stream
-    steps0, launches0 = sim_steps(), ctx.launch_count
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- timed regions: exactly K steps each, CUDA events on the launching stream, barrier + synchronize on both
+    # sides. The region is repeated `--repeats` times back to back (the workload is steady: same population, same
+    # launches) and `value` is the MEDIAN region; every region's time is listed under "repeats".
+    regions = []
     tw0 = time.perf_counter()
-    ev0.record(ext)
-    for _ in range(args.steps):
-        step()
-    ev1.record(ext)
-    barrier()
+    for _ in range(max(1, args.repeats)):
+        steps0, launches0 = sim_steps(), ctx.launch_count
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(ext)
+        for _ in range(args.steps):
+            step()
+        ev1.record(ext)
+        barrier()
+        r_ms = ev0.elapsed_time(ev1)
+        if world > 1:   # the region's time is the slowest rank's
+            t_r = torch.tensor([r_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_r, op=dist.ReduceOp.MAX)
+            r_ms = float(t_r.item())
+        regions.append((r_ms, ctx.launch_count - launches0, sim_steps() - steps0))
     tw1 = time.perf_counter()
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count - launches0
-    effect_steps = sim_steps() - steps0
+    ms, launches, effect_steps = sorted(regions)[len(regions) // 2]
+    repeats = {"n": len(regions), "ms_per_step": [r[0] / args.steps for r in regions], "median_ms_per_step": ms / args.steps,
+               "min_ms_per_step": min(r[0] for r in regions) / args.steps, "max_ms_per_step": max(r[0] for r in regions) / args.steps,
+               "note": "value and ms_per_step are the median of these regions of exactly %d steps each" % args.steps}
     # per-kernel durations: the same K steps again, immediately, with a CUDA event pair around every launch
     # (the events cost 5-40 % of the step on these short kernels, so they are kept out of `value`'s region)
     ktimes = {}
@@ -279,9 +290,6 @@ def run_ours(args, rank, world):
     else:
         steps_after_clock_loop = False
     # every effect holds a constant population in the timed window; sub-steps are counted exactly
-    particle_steps = 0
-    for s, e in all_effects:
-        pass
     per_effect_alive = n_alive / len(all_effects)
     particle_steps = effect_steps * per_effect_alive
 
@@ -542,6 +550,7 @@ def run_ours(args, rank, world):
                             "the vertex stream stays in HBM where the renderer reads it (the reference uploads it with sg_append_buffer)",
                     "with_vertex_stream_to_host": e2e_host},
             "gpu_launches": int(launches_all),
+            "repeats": repeats,
             "clocks": clocks,
             "roofline": roof,
             "kernels": kern,
@@ -706,13 +715,19 @@ def cpu_run(name, steps, warmup, procs, scale=1.0):
     kind = "reference" if orc.have("reference") else "port"
     if kind == "port":
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    # instance 0 runs in THIS process (the reference library is loaded here, where the driver's loaded-library record
+    # looks), the other instances in forked children of it
+    orc._load(kind)
     ctxm = mp.get_context("fork")
     q = ctxm.Queue()
-    ps = [ctxm.Process(target=_cpu_worker, args=(kind, name, i, steps, warmup, scale, q)) for i in range(procs)]
+    ps = [ctxm.Process(target=_cpu_worker, args=(kind, name, i, steps, warmup, scale, q)) for i in range(1, procs)]
     t0 = time.perf_counter()
     for p in ps:
         p.start()
-    res = [q.get() for _ in ps]
+    import queue as _queue
+    local = _queue.Queue()
+    _cpu_worker(kind, name, 0, steps, warmup, scale, local)
+    res = [local.get()] + [q.get() for _ in ps]
     for p in ps:
         p.join()
     wall = time.perf_counter() - t0
@@ -771,6 +786,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps each; value = the median region")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-sort", action="store_true", help="strict drop-in stream (slot order), no per-particle depth sort")

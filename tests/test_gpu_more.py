@@ -47,7 +47,7 @@ def test_large_effect_multi_tile(oracle_port):
         ctx.close()
 
 
-@pytest.mark.parametrize("name", ["c1_small", "fountain", "multi", "churn_c5", "remove_reuse"])
+@pytest.mark.parametrize("name", ["c1_small", "fountain", "multi", "churn_c5", "remove_reuse", "gravity_points"])
 def test_sorted_stream_is_stable_depth_sort_of_reference_stream(oracle_port, name):
     P = _particles()
     sc = [s for s in S.scenarios() if s.name == name][0]
