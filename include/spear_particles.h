@@ -375,14 +375,20 @@ SPR_API int sprPrepareForRemove(SprSystem *sys, uint32_t effectId, const SprFram
 SPR_API int sprRemoveEffect(SprSystem *sys, uint32_t effectId);
 
 /* updateParticles(const VisibleAreas &active, const FrameArgs&), ParticleSystem.h:18,
- * ParticleSystem.cpp:808-822. activeIds = active.get(AreaGroup::ParticleEffect). */
+ * ParticleSystem.cpp:808-822. activeIds = active.get(AreaGroup::ParticleEffect).
+ * Every id must name a live effect (SPR_ERR_INVALID_ARGUMENT otherwise). An id listed twice in one list is refused with
+ * SPR_ERR_UNSUPPORTED before anything is changed: the reference would run that effect's sub-step loop once per entry
+ * (:812-821), the device plan is per effect. */
 SPR_API int sprUpdateParticles(SprSystem *sys, const uint32_t *activeIds, uint32_t numActive,
 	const SprFrameArgs *args);
 
 /* Same call for many independent systems of one context in ONE set of kernel
  * launches (each system keeps its own RNG and id spaces, ParticleSystem.cpp:241-251).
  * Equivalent to calling sprUpdateParticles(systems[i], activeIds[i], numActive[i], &args[i])
- * for i = 0..numSystems-1. If args is shared, pass argsStride = 0. */
+ * for i = 0..numSystems-1. If args is shared, pass argsStride = 0.
+ * A system listed twice is refused (SPR_ERR_UNSUPPORTED: its effects share one RNG stream, merge the lists); ids are
+ * checked as in sprUpdateParticles. With SPR_CTX_SORT_PARTICLES the depth keys of the whole batch are taken from ONE
+ * camera, args[numSystems-1].cameraPosition (a batch is one view); dt and gameTime are per system. */
 SPR_API int sprUpdateParticlesBatch(SprContext *ctx, SprSystem *const *systems, uint32_t numSystems,
 	const uint32_t *const *activeIds, const uint32_t *numActive,
 	const SprFrameArgs *args, size_t argsStride);
@@ -549,7 +555,13 @@ SPR_API int sprBillboardRenderMain(SprBillboardSystem *sys, const SprRenderArgs 
 /* Parity read-back: host copy of the vertex buffer of the last renderMain (billboardVertices, :65). */
 SPR_API int sprBillboardReadVertices(SprBillboardSystem *sys, SprBillboardVertex *out, uint32_t capacityQuads, uint32_t *outQuads);
 
-/* Device pointers for zero-copy consumers (benchmarks, the multi-GPU gather). */
+/* Device pointers for zero-copy consumers (benchmarks, the multi-GPU gather).
+ * LIFETIME of every device pointer and offset this API hands out (SprRenderOutput::deviceVertices,
+ * SprDrawRecord::vertexByteOffset, the fields below): valid until the next sprAddEffect or sprUpdateParticles[Batch] on
+ * the context. Those calls may grow the slot pool (all pool arrays are re-allocated) or move an effect that outgrew its
+ * slot range (its slotBase and with it its vertex offset change). A context created with initialSlotCapacity large
+ * enough for everything it will hold never re-allocates the pool; an effect whose particle count is bounded by its
+ * descriptor (burst + 20 spawns per step over its lifetime) never moves. */
 typedef struct SprEffectDeviceView {
 	const SprGpuParticle *vertices;    /* DEVICE: effect's run, 4 vertices per particle */
 	const SprGpuParticle *slots;       /* DEVICE: slot state */

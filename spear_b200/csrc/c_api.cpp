@@ -20,6 +20,7 @@ static int guarded(F &&f)
 {
 	try { f(); return SPR_OK; }
 	catch (const CudaError &e) { g_lastError = e.what(); return SPR_ERR_CUDA; }
+	catch (const Unsupported &e) { g_lastError = e.what(); return SPR_ERR_UNSUPPORTED; }
 	catch (const std::bad_alloc &) { g_lastError = "out of host memory"; return SPR_ERR_OUT_OF_MEMORY; }
 	catch (const std::exception &e) { g_lastError = e.what(); return SPR_ERR_INVALID_ARGUMENT; }
 }
@@ -158,8 +159,7 @@ SPR_API int sprRemoveEffect(SprSystem *sys, uint32_t effectId)
 SPR_API int sprUpdateParticles(SprSystem *sys, const uint32_t *activeIds, uint32_t numActive, const SprFrameArgs *args)
 {
 	REQUIRE(sys && args && (activeIds || numActive == 0));
-	for (uint32_t i = 0; i < numActive; i++) REQUIRE(validEffect(sys, activeIds[i]));
-	return guarded([&] { sys->sys.updateParticles(activeIds, numActive, *args); });
+	return guarded([&] { sys->sys.updateParticles(activeIds, numActive, *args); }); // ids are checked by Context::validateRequests
 }
 
 SPR_API int sprUpdateParticlesBatch(SprContext *ctx, SprSystem *const *systems, uint32_t numSystems,
@@ -232,6 +232,7 @@ static int readRange(SprSystem *sys, uint32_t effectId, int what, void *out, uin
 {
 	return guarded([&] {
 		Context *ctx = sys->sys.ctx;
+		SPR_CUDA(cudaSetDevice(ctx->device));
 		const HostEffect &E = sys->sys.effects[effectId];
 		RenderGather g;
 		ctx->gatherEffects(&E.global, 1, &g);
@@ -471,7 +472,7 @@ SPR_API int sprRunBufferCreate(SprContext *c, uint64_t capacityRecords, SprRunBu
 SPR_API int sprRunBufferDestroy(SprRunBuffer *buf)
 {
 	REQUIRE(buf);
-	return guarded([&] { cudaStreamSynchronize(buf->ctx->stream); cudaFree(buf->dev); delete buf; });
+	return guarded([&] { SPR_CUDA(cudaSetDevice(buf->ctx->device)); cudaStreamSynchronize(buf->ctx->stream); cudaFree(buf->dev); delete buf; });
 }
 
 SPR_API void *sprRunBufferDevicePtr(SprRunBuffer *buf) { return buf ? buf->dev : nullptr; }
@@ -480,7 +481,7 @@ SPR_API int sprRunBufferGetIpcHandle(SprRunBuffer *buf, uint8_t outHandle[SPR_IP
 {
 	REQUIRE(buf && outHandle);
 	static_assert(sizeof(cudaIpcMemHandle_t) == SPR_IPC_HANDLE_BYTES, "ipc handle size");
-	return guarded([&] { cudaIpcMemHandle_t h; SPR_CUDA(cudaIpcGetMemHandle(&h, buf->dev)); memcpy(outHandle, &h, sizeof(h)); });
+	return guarded([&] { SPR_CUDA(cudaSetDevice(buf->ctx->device)); cudaIpcMemHandle_t h; SPR_CUDA(cudaIpcGetMemHandle(&h, buf->dev)); memcpy(outHandle, &h, sizeof(h)); });
 }
 
 SPR_API int sprRunBufferOpenPeer(SprContext *c, const uint8_t handle[SPR_IPC_HANDLE_BYTES], void **outDevicePtr)
@@ -531,6 +532,7 @@ SPR_API int sprExpandFromPeers(SprContext *c, void *const *bufferPtrs, uint32_t 
 {
 	REQUIRE(c && bufferPtrs && deviceVerticesOut && numRanks >= 1 && numRanks <= 16 && myRank < numRanks);
 	return guarded([&] {
+		SPR_CUDA(cudaSetDevice(c->ctx.device));
 		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, myRank, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms);
 		c->ctx.launchCount++;
 		SPR_CUDA(cudaGetLastError());
@@ -541,6 +543,7 @@ SPR_API int sprExpandRuns(SprContext *c, const SprGpuParticle *deviceRecords, ui
 {
 	REQUIRE(c && deviceRecords && deviceVerticesOut);
 	return guarded([&] {
+		SPR_CUDA(cudaSetDevice(c->ctx.device));
 		launch_expand_runs(c->ctx.stream, (const float4*)deviceRecords, numRecords, (float4*)deviceVerticesOut, c->ctx.numSms);
 		c->ctx.launchCount++;
 		SPR_CUDA(cudaGetLastError());

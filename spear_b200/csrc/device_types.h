@@ -23,6 +23,21 @@ static const uint32_t kNoOwner = 0xffffffffu;
 #define SPR_SORT_TILE_KEYS 4096
 #endif
 static const uint32_t kSortTileKeys = SPR_SORT_TILE_KEYS; // keys per CTA in the radix sort passes (16 per thread)
+// Forward progress of the chained scans (look-back over the status words of lower-numbered tiles).
+//  * k_stream_fused is PERSISTENT (one wave of CTAs, several tiles each): its tiles are always handed out by an atomic
+//    ticket, in the order the CTAs get to them, so a look-back only waits for tiles whose CTAs are running -- however
+//    many of its CTAs the device can hold while other contexts / streams use it.
+//  * k_sort_pass and k_dead_append launch ONE CTA (warp) PER TILE and take tile = block index. A tile waits only for
+//    lower block indices of its own grid; the hardware work distributor hands the CTAs of a grid out in ascending linear
+//    block index and never evicts a running CTA in favour of another one of the same grid (compute preemption swaps
+//    whole contexts), so every tile waited for is running or finished, whatever else shares the device. That is the
+//    dispatch order every non-ticketed decoupled look-back relies on; it is observed behaviour, not a documented
+//    guarantee, so -DSPR_STRICT_TILE_TICKETS=1 builds these two kernels with tickets as well (same results; measured
+//    on the 10M-particle sorted step: 0.777 -> 0.825 ms, the ticket's L2 round trip sits in front of every tile's
+//    dependent loads -- profiles/r02_sort_experiments.md). A wait that outlasts 2^24 polls traps either way.
+#ifndef SPR_STRICT_TILE_TICKETS
+#define SPR_STRICT_TILE_TICKETS 0
+#endif
 static const uint32_t kSmallSortMax = 18432;   // an effect of at most this many slots is sorted by ONE CTA (k_sort_small)
 
 static const float kHugeLife = 1e20f;          // ParticleSystem.cpp:27
@@ -205,6 +220,9 @@ struct PoolPtrs {
 	const uint32_t *granuleOwner;
 	unsigned long long *tileStatusAlive;
 	unsigned long long *tileStatusDead;
+	unsigned long long *tickets;      // [2] monotonic tile tickets of the chained-scan kernels (0: k_stream_fused, 1: k_dead_append):
+	                                  // a CTA / warp takes its tile in the order it STARTS, so a look-back only ever waits for
+	                                  // tiles whose owners are already running, whatever else occupies the device
 };
 
 struct TablePtrs {

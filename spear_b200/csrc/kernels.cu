@@ -451,9 +451,10 @@ __global__ void __launch_bounds__(256) k_emit_burst(PoolPtrs pool, TablePtrs tab
 // k_integrate (:526-666)
 // ---------------------------------------------------------------------------
 
-// A chained scan only ever waits for a predecessor that is already running (tiles are dispatched in order and the
-// persistent kernels launch resident CTAs only), so a wait is a few microseconds. Should that assumption ever break,
-// the wait traps after ~2^24 polls: the launch fails with an error the host reports, instead of hanging the GPU.
+// A chained scan only ever waits for a predecessor that is already running: tiles are handed out by an atomic ticket in
+// the order their CTAs (warps) start, never by block index, so the owner of every lower-numbered tile is resident
+// whatever else shares the device (other contexts, other streams, a programmatically launched successor). A wait is a
+// few microseconds; the trap after ~2^24 polls only turns a bug into an error the host reports instead of a hang.
 static const uint32_t kMaxSpins = 1u << 24;
 __device__ __forceinline__ void spin_guard(uint32_t &spins) { if (++spins > kMaxSpins) __trap(); }
 
@@ -711,11 +712,20 @@ __device__ inline uint32_t tile_lookback1(unsigned long long *st, uint32_t poolT
 // One warp per 1024-slot pool tile, lane = one mask word; chained look-back across the tiles of a
 // large effect. Touches 8 bytes per 32 slots, so the chain is cheap.
 template <bool ALIVE>
-__global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles)
+__global__ void __launch_bounds__(128) k_dead_append(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles,
+	unsigned long long ticketBase)
 {
 	pdl_enter();
 	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t poolTile = blockIdx.x * 4 + (threadIdx.x >> 5);
+#if SPR_STRICT_TILE_TICKETS
+	// the warp's tile = its ticket (every launched warp takes exactly one: the host advances ticketBase by the warp count)
+	unsigned long long ticket = 0;
+	if (lane == 0) ticket = atomicAdd(pool.tickets + 1, 1ull) - ticketBase;
+	const uint32_t poolTile = (uint32_t)__shfl_sync(FULL_MASK, ticket, 0);
+#else
+	const uint32_t poolTile = blockIdx.x * 4 + (threadIdx.x >> 5); // waits only for lower block indices (device_types.h, SPR_STRICT_TILE_TICKETS)
+	(void)ticketBase;
+#endif
 	if (poolTile >= numPoolTiles) return;
 	const uint32_t granule = poolTile * 8 + (lane >> 2);
 	uint32_t g = pool.granuleOwner[granule];
@@ -872,35 +882,55 @@ __device__ inline void tile_lookback2(unsigned long long *stA, unsigned long lon
 }
 
 template <bool GP>
-__global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles)
+__global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round, uint32_t epoch, uint32_t numPoolTiles,
+	unsigned long long ticketBase)
 {
 	pdl_enter();
 	extern __shared__ float4 sStageAll[];              // [2][8 warps][256 float4] = 64 KB
 	__shared__ FusedTileMeta sMeta[2];
+	__shared__ uint32_t sTicket[2];                    // tile of iteration it (parity it & 1), claimed one iteration ahead
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t ltMask = (1u << lane) - 1u;
 	const unsigned long long tag = (unsigned long long)epoch << 34;
 
+	// Tiles are claimed with an atomic ticket, in the order the CTAs get to them: every tile below a claimed one belongs
+	// to a CTA that is running, so the chained look-back cannot wait for a CTA that was never scheduled. A CTA claims
+	// until its ticket runs past the last tile: numPoolTiles + gridDim tickets per launch (the host's ticketBase).
 	if (threadIdx.x < 2) sMeta[threadIdx.x].tile = 0xffffffffu;
+	if (threadIdx.x == 0) {
+		const unsigned long long t = atomicAdd(pool.tickets + 0, 1ull) - ticketBase;
+		sTicket[0] = t < numPoolTiles ? (uint32_t)t : 0xffffffffu;
+	}
 	__syncthreads();
 
 	// the records of the NEXT tile are requested before phase B of the current iteration, so their
 	// DRAM latency hides behind the expansion stores
 	float4 a[4], b[4];
 	uint32_t gNext = kNoOwner;
-	if (warp < 8 && blockIdx.x < numPoolTiles) {
-		gNext = pool.granuleOwner[blockIdx.x * 8 + warp];
+	if (warp < 8 && sTicket[0] < numPoolTiles) {
+		const uint32_t first = sTicket[0];
+		gNext = pool.granuleOwner[first * 8 + warp];
 		if (gNext != kNoOwner) {
-			const float4 *p = pool.state + 2ull * ((uint64_t)(blockIdx.x * 8 + warp) * kGranuleSlots + lane);
+			const float4 *p = pool.state + 2ull * ((uint64_t)(first * 8 + warp) * kGranuleSlots + lane);
 #pragma unroll
 			for (int r = 0; r < 4; r++) ld_record(p + r * 64, a[r], b[r]);
 		}
 	}
 
-	for (uint32_t it = 0, tile = blockIdx.x; ; it++, tile += gridDim.x) {
+	for (uint32_t it = 0; ; it++) {
 		const uint32_t cur = it & 1u;
+		const uint32_t tile = sTicket[cur];            // 0xffffffff once the tickets have run out
 		FusedTileMeta &M = sMeta[cur];
 		FusedTileMeta &Q = sMeta[cur ^ 1u];
+		// claim the tile of the next iteration now: it is read (for the prefetch) behind the barrier that ends phase A
+		if (threadIdx.x == 0) {
+			uint32_t next = 0xffffffffu;
+			if (tile < numPoolTiles) {
+				const unsigned long long t = atomicAdd(pool.tickets + 0, 1ull) - ticketBase;
+				if (t < numPoolTiles) next = (uint32_t)t;
+			}
+			sTicket[cur ^ 1u] = next;
+		}
 		// ---------------- scan warp: look-back of the tile staged one iteration ago, overlapping phase A
 		if (warp == 8) {
 			if (it > 0 && Q.tile != 0xffffffffu && Q.large) {
@@ -999,7 +1029,7 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 
 		// ---------------- prefetch (worker warps): owner and records of this CTA's next tile
 		if (warp < 8) {
-			const uint32_t nextTile = tile + gridDim.x;
+			const uint32_t nextTile = sTicket[cur ^ 1u];
 			gNext = kNoOwner;
 			if (tile < numPoolTiles && nextTile < numPoolTiles) {
 				gNext = pool.granuleOwner[nextTile * 8 + warp];
@@ -1376,11 +1406,14 @@ void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &ta
 #undef SPR_LAUNCH_PASS
 }
 
-void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch, bool aliveScan)
+void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch, bool aliveScan,
+	uint64_t &ticketBase)
 {
 	if (!numPoolTiles) return;
-	if (aliveScan) launch_chain(k_dead_append<true>, div_up(numPoolTiles, 4), 128, 0, st, pool, tab, stamp, round, epoch, numPoolTiles);
-	else launch_chain(k_dead_append<false>, div_up(numPoolTiles, 4), 128, 0, st, pool, tab, stamp, round, epoch, numPoolTiles);
+	const uint32_t blocks = div_up(numPoolTiles, 4);
+	if (aliveScan) launch_chain(k_dead_append<true>, blocks, 128, 0, st, pool, tab, stamp, round, epoch, numPoolTiles, (unsigned long long)ticketBase);
+	else launch_chain(k_dead_append<false>, blocks, 128, 0, st, pool, tab, stamp, round, epoch, numPoolTiles, (unsigned long long)ticketBase);
+	ticketBase += (uint64_t)blocks * 4; // one ticket per launched warp
 }
 
 // Per-device kernel attributes (dynamic shared memory of the fused stream kernel) and its resident
@@ -1397,15 +1430,16 @@ void configure_stream_fused(int ctasPerSm[2])
 }
 
 uint32_t launch_stream_fused(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2])
+	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2], uint64_t &ticketBase)
 {
 	if (!numPoolTiles) return 0;
 	const size_t smem = 2 * 8 * 256 * sizeof(float4);
 	const int v = gravityPoints ? 1 : 0;
-	uint32_t grid = numSms * (uint32_t)ctasPerSm[v]; // persistent: resident CTAs only (the chained scan needs its predecessors running)
+	uint32_t grid = numSms * (uint32_t)ctasPerSm[v]; // persistent: one wave of CTAs when the device is otherwise idle (tiles go by ticket, so fewer resident CTAs are fine too)
 	if (grid > numPoolTiles) grid = numPoolTiles;
-	if (v) launch_chain(k_stream_fused<true>, grid, 288, smem, st, pool, tab, stamp, round, epoch, numPoolTiles);
-	else launch_chain(k_stream_fused<false>, grid, 288, smem, st, pool, tab, stamp, round, epoch, numPoolTiles);
+	if (v) launch_chain(k_stream_fused<true>, grid, 288, smem, st, pool, tab, stamp, round, epoch, numPoolTiles, (unsigned long long)ticketBase);
+	else launch_chain(k_stream_fused<false>, grid, 288, smem, st, pool, tab, stamp, round, epoch, numPoolTiles, (unsigned long long)ticketBase);
+	ticketBase += (uint64_t)numPoolTiles + grid; // every CTA claims until its ticket runs past the last tile
 	return grid;
 }
 

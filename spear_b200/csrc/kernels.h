@@ -23,11 +23,13 @@ void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &ta
 void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs, uint32_t totalBlocks);
 void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
 	uint32_t epoch, bool sortMode, bool gravityPoints, bool tinyEffects, const float camera[3]);
-void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch, bool aliveScan);
+// ticketBase: the context's running count of tickets handed out by launches of the kernel so far (PoolPtrs::tickets)
+void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch, bool aliveScan,
+	uint64_t &ticketBase);
 void configure_stream_fused(int ctasPerSm[2]);
 void configure_sort_kernels();
 uint32_t launch_stream_fused(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2]);
+	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2], uint64_t &ticketBase);
 void launch_expand_stream(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp);
 void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t stamp);
 void launch_query_frustum(cudaStream_t st, const TablePtrs &tab, uint32_t numGlobals, uint32_t systemIdx, const float frustum[32],
@@ -58,7 +60,7 @@ uint32_t launch_billboards(cudaStream_t st, const BillboardDev *bb, uint32_t n, 
 // followed by the 4x expansion in sorted order.
 struct SortScratch {
 	uint32_t *keysAlt, *valsAlt;     // ping-pong buffers, same indexing as PoolPtrs::keys/vals
-	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases, then [numSegments] pass masks
+	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases, then [numSegments] pass masks, then [4] pass tickets
 	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
 };
 // Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted, 4 sort_small).

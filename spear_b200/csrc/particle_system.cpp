@@ -58,6 +58,8 @@ Context::Context(const SprContextDesc &desc)
 	configure_stream_fused(streamFusedCtasPerSm);
 	configure_sort_kernels();
 	freeRanges.resize(33);
+	SPR_CUDA(cudaMalloc(&dTickets, 2 * sizeof(unsigned long long)));
+	SPR_CUDA(cudaMemsetAsync(dTickets, 0, 2 * sizeof(unsigned long long), stream));
 	ensurePool(desc.initialSlotCapacity ? desc.initialSlotCapacity : (1u << 20));
 }
 
@@ -75,7 +77,7 @@ Context::~Context()
 	cudaFree(dSlotState); cudaFree(dFreeStack); cudaFree(dVertices);
 	cudaFree(dKeys[0]); cudaFree(dKeys[1]); cudaFree(dVals[0]); cudaFree(dVals[1]);
 	cudaFree(dAliveMask); cudaFree(dDeadMask); cudaFree(dWordAliveBase);
-	cudaFree(dGranuleOwner); cudaFree(dTileStatus[0]); cudaFree(dTileStatus[1]);
+	cudaFree(dGranuleOwner); cudaFree(dTileStatus[0]); cudaFree(dTileStatus[1]); cudaFree(dTickets);
 	if (slotMirror) cudaFreeHost(slotMirror);
 	cudaEventDestroy(stagingEvent[0]); cudaEventDestroy(stagingEvent[1]);
 	if (ownStream) cudaStreamDestroy(stream);
@@ -89,6 +91,7 @@ PoolPtrs Context::poolPtrs() const
 	p.aliveMask = dAliveMask; p.deadMask = dDeadMask; p.wordAliveBase = dWordAliveBase;
 	p.granuleOwner = dGranuleOwner;
 	p.tileStatusAlive = dTileStatus[0]; p.tileStatusDead = dTileStatus[1];
+	p.tickets = dTickets;
 	return p;
 }
 
@@ -309,9 +312,37 @@ void Context::flushUploads()
 	update(nullptr, 0); // an empty frame: only the pending table uploads are applied
 }
 
+// Argument check of an update call, before anything is changed: every id names a live effect, no id is listed twice
+// in one system's list, no system is listed twice. The reference simulates a repeated id twice (its loop runs per list
+// entry, ParticleSystem.cpp:812-821); the device plan works per effect, so that case is refused (SPR_ERR_UNSUPPORTED)
+// instead of silently diverging.
+void Context::validateRequests(const UpdateRequest *reqs, uint32_t numReqs)
+{
+	if (++updateMark >= ParticleSystem::kMarkFree - 1) { // the 32-bit mark wrapped: forget every old mark
+		for (ParticleSystem *s : systemsAlive) { s->systemMark = 0; for (uint32_t &m : s->activeMark) if (m != ParticleSystem::kMarkFree) m = 0; }
+		updateMark = 1;
+	}
+	const uint32_t mark = updateMark;
+	for (uint32_t r = 0; r < numReqs; r++) {
+		ParticleSystem *sys = reqs[r].system;
+		if (sys->systemMark == mark) throw Unsupported("a system is listed twice in one batched update (its effects share one RNG stream: merge the lists)");
+		sys->systemMark = mark;
+		if (reqs[r].numActive && !reqs[r].activeIds) throw std::invalid_argument("active id list is NULL");
+		uint32_t *marks = sys->activeMark.data();
+		const size_t n = sys->activeMark.size();
+		for (uint32_t i = 0; i < reqs[r].numActive; i++) {
+			const uint32_t id = reqs[r].activeIds[i];
+			if (id >= n || marks[id] == ParticleSystem::kMarkFree) throw std::invalid_argument("active list names an effect id that is not in use");
+			if (marks[id] == mark) throw Unsupported("an effect id is listed twice in one active list (the reference would simulate it twice, ParticleSystem.cpp:812-821; not supported)");
+			marks[id] = mark;
+		}
+	}
+}
+
 void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 {
 	SPR_CUDA(cudaSetDevice(device));
+	validateRequests(reqs, numReqs);
 	const bool sortMode = (flags & SPR_CTX_SORT_PARTICLES) != 0;
 	static const bool hostTiming = getenv("SPR_HOST_TIMING") != nullptr; // debug aid: where a frame's host time goes
 	auto tNow = [] { return std::chrono::steady_clock::now(); };
@@ -589,7 +620,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	SortScratch sortScratch = { nullptr, nullptr, nullptr, nullptr };
 	if (sortMode && !segEffects.empty()) {
 		sortScratch.keysAlt = dKeys[1]; sortScratch.valsAlt = dVals[1];
-		dSortHist.reserve(segEffects.size() * (4 * 256 + 1), 0, stream);
+		dSortHist.reserve(segEffects.size() * (4 * 256 + 1) + 4, 0, stream); // histograms, pass masks, four pass tickets
 		dSortLookback.reserve(sortTiles.size() * 4 * 256 + 1, 0, stream);
 		sortScratch.hist = dSortHist.ptr; sortScratch.lookback = dSortLookback.ptr;
 		clear_sort_scratch(stream, sortScratch, (uint32_t)segEffects.size(), (uint32_t)sortTiles.size());
@@ -612,10 +643,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		}
 		if (!sortMode && streamFused) {
 			// stream mode, one pass: integrate + ranks + free list + 4x expansion in a software-pipelined persistent kernel
-			TIMED(kKStreamFused, launch_stream_fused(stream, pool, tab, poolTiles, frameStamp, round, epoch, typesWithGravityPoints != 0, numSms, streamFusedCtasPerSm));
+			TIMED(kKStreamFused, launch_stream_fused(stream, pool, tab, poolTiles, frameStamp, round, epoch, typesWithGravityPoints != 0, numSms, streamFusedCtasPerSm, ticketBase[0]));
 		} else {
 			TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, numTinyEffects != 0, camera));
-			TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch, !sortMode));
+			TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch, !sortMode, ticketBase[1]));
 		}
 	}
 	if (!sortMode && !streamFused) TIMED(kKExpandStream, launch_expand_stream(stream, pool, tab, poolTiles, frameStamp));
@@ -685,6 +716,7 @@ ParticleSystem::ParticleSystem(Context *c, const SprSystemsDesc &desc)
 	sd.rngState = desc.seed[1];            // sf::Random(desc.seed[1], 581271), :267; ctor src/sf/Random.h:11
 	sd.rngInc = 581271ull | 1ull;
 	Context::queueUpload(ctx->systemIdx, ctx->systemVal, ctx->systemPos, systemIdx, sd);
+	ctx->systemsAlive.push_back(this);
 }
 
 ParticleSystem::~ParticleSystem()
@@ -692,6 +724,7 @@ ParticleSystem::~ParticleSystem()
 	for (uint32_t id = 0; id < effects.size(); id++) if (effects[id].inUse) remove(id);
 	for (HostType &t : types) if (t.comp) { if (t.hasGravityPoints) ctx->typesWithGravityPoints--; ctx->freeTypeGlobals.push_back(t.global); t.comp = nullptr; }
 	ctx->freeSystemGlobals.push_back(systemIdx);
+	ctx->systemsAlive.erase(std::find(ctx->systemsAlive.begin(), ctx->systemsAlive.end(), this));
 }
 
 uint32_t ParticleSystem::reserveEffectType(const SprParticleSystemComponent *c)
@@ -784,7 +817,8 @@ uint32_t ParticleSystem::addEffect(uint32_t entityId, uint8_t componentIndex, co
 	(void)entityId; (void)componentIndex;
 	uint32_t effectId;
 	if (!freeEffectIds.empty()) { effectId = freeEffectIds.back(); freeEffectIds.pop_back(); }
-	else { effectId = (uint32_t)effects.size(); effects.emplace_back(); effectsCold.emplace_back(); }
+	else { effectId = (uint32_t)effects.size(); effects.emplace_back(); effectsCold.emplace_back(); activeMark.push_back(kMarkFree); }
+	activeMark[effectId] = 0;
 
 	uint32_t typeId = reserveEffectType(c);
 	const HostType &type = types[typeId];
@@ -906,6 +940,7 @@ void ParticleSystem::remove(uint32_t effectId)
 	ctx->freeEffectGlobals.push_back(E.global);
 	ctx->effectLive[E.global] = 0;
 	E = HostEffect();
+	activeMark[effectId] = kMarkFree;
 	freeEffectIds.push_back(effectId);
 }
 

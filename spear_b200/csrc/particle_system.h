@@ -25,6 +25,7 @@
 namespace spr {
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; }; // -> SPR_ERR_UNSUPPORTED
 
 #define SPR_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) throw spr::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 
@@ -128,6 +129,11 @@ struct ParticleSystem {
 	std::vector<HostEffect> effects;          // :241 (hot half)
 	std::vector<HostEffectCold> effectsCold;  // :241 (cold half, same index)
 	std::vector<uint32_t> freeEffectIds;      // :242
+	// per effect id: the mark of the last update call that listed it (kMarkFree while the id is not in use). One 4-byte
+	// look-up per listed id validates the id and finds an id listed twice, before the call changes anything.
+	static constexpr uint32_t kMarkFree = 0xffffffffu;
+	std::vector<uint32_t> activeMark;
+	uint32_t systemMark = 0;                  // the mark of the last update call that listed this system
 	std::vector<HostType> types;              // :244
 	std::vector<uint32_t> freeTypeIds;        // :245
 	std::unordered_map<const void*, uint32_t> componentToType; // :246
@@ -189,6 +195,8 @@ struct Context {
 	uint32_t *dAliveMask = nullptr, *dDeadMask = nullptr, *dWordAliveBase = nullptr;
 	uint32_t *dGranuleOwner = nullptr;
 	unsigned long long *dTileStatus[2] = { nullptr, nullptr };
+	unsigned long long *dTickets = nullptr;    // [2] monotonic tile tickets (PoolPtrs::tickets) ...
+	uint64_t ticketBase[2] = { 0, 0 };         // ... and how many of them the launches issued so far have taken
 	std::vector<std::vector<uint32_t>> freeRanges; // per log2(capacity): free slotBase values
 
 	// ---- tables
@@ -234,6 +242,9 @@ struct Context {
 	std::vector<SortTile> scratchSortTiles;
 	std::vector<EffectParams> scratchParamVals;
 	int updateDepth = 0;
+	uint32_t updateMark = 0;               // numbers the update calls (ParticleSystem::activeMark / systemMark)
+	std::vector<ParticleSystem*> systemsAlive; // every system of the context (marks are wiped when updateMark wraps)
+	void validateRequests(const UpdateRequest *reqs, uint32_t numReqs);
 	uint64_t renderBatchStamp = 0;     // numbers the threaded render batches (a system named twice keeps the batch on one thread)
 	// ---- per-frame staging
 	PinnedArray<uint8_t> stagingH[2];

@@ -144,7 +144,7 @@ __device__ unsigned long long g_sortProf[16];
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	uint32_t *keys0, uint32_t *vals0, uint32_t *keys1, uint32_t *vals1,
-	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t pass)
+	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t *ticket, uint32_t pass)
 {
 	pdl_enter();
 	extern __shared__ __align__(16) uint32_t sPassDyn[];
@@ -153,10 +153,22 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass
 	uint32_t *sCnt = sPassDyn + 2 * kSortTileKeys;      // [kSortWarps][256] per-warp digit counts -> staging position of the warp's first key of each digit
 	__shared__ int32_t sGlobal[256];            // global position of local index j with digit d: sGlobal[d] + j
 	__shared__ uint32_t sWarpSum[8];
-	__shared__ uint32_t sTileCount;
+	__shared__ uint32_t sTileCount, sTicket;
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const SortTile st = tiles[blockIdx.x];
+#if SPR_STRICT_TILE_TICKETS
+	// The CTA's place in the tile table is a ticket, taken in the order the CTAs start (not the block index): the
+	// chained look-back below then only ever waits for tiles whose CTAs are already running.
+	if (tid == 0) sTicket = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const uint32_t tileSlot = sTicket;
+#else
+	// Tile = block index: the look-back below waits only for lower block indices of this grid, which the hardware
+	// dispatched before this CTA (forward-progress argument: device_types.h, SPR_STRICT_TILE_TICKETS).
+	const uint32_t tileSlot = blockIdx.x;
+	(void)ticket; (void)sTicket;
+#endif
+	const SortTile st = tiles[tileSlot];
 	const uint32_t g = segEffects[st.effect];
 	const uint32_t runMask = passMask[st.effect] | 1u; // pass 0 always runs: its scatter is the compaction
 	if (!FIRST && !((runMask >> pass) & 1u)) return; // constant digit: nothing would move
@@ -247,7 +259,7 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass
 	if (tid < 256) {
 #pragma unroll
 		for (uint32_t w = 0; w < kSortWarps; w++) { uint32_t c = sCnt[w * 256 + tid]; sCnt[w * 256 + tid] = total; total += c; }
-		uint32_t *lb = lookback + (size_t)blockIdx.x * 256 + tid;
+		uint32_t *lb = lookback + (size_t)tileSlot * 256 + tid;
 		if (st.tile == 0) {
 			st_relaxed_u32(lb, (2u << 30) | total);
 		} else {
@@ -621,7 +633,7 @@ void configure_sort_kernels()
 void clear_sort_scratch(cudaStream_t st, const SortScratch &sc, uint32_t numSegments, uint32_t numTiles)
 {
 	if (!numSegments || !numTiles) return;
-	cudaMemsetAsync(sc.hist, 0, (size_t)numSegments * 1025 * sizeof(uint32_t), st);
+	cudaMemsetAsync(sc.hist, 0, ((size_t)numSegments * 1025 + 4) * sizeof(uint32_t), st); // histograms, pass masks, the four pass tickets
 	cudaMemsetAsync(sc.lookback, 0, (size_t)numTiles * 4 * 256 * sizeof(uint32_t), st);
 }
 
@@ -634,6 +646,7 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 #define T_BEGIN(k) do { if (hooks) tok = hooks->begin(hooks->ctx, k); } while (0)
 #define T_END(k) do { if (hooks) hooks->end(hooks->ctx, k, tok); } while (0)
 	uint32_t *passMask = sc.hist + (size_t)numSegments * 1024; // [numSegments], cleared together with the histograms (clear_sort_scratch)
+	uint32_t *tickets = passMask + numSegments;                 // [4] one tile ticket per pass, cleared with them
 	uint32_t launches = 0;
 	if (numBigSegments && numBigTiles) {
 		T_BEGIN(0);
@@ -648,8 +661,8 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 		for (uint32_t p = 0; p < 4; p++) {
 			T_BEGIN(2);
 			uint32_t *lb = sc.lookback + (size_t)p * numBigTiles * 256;
-			if (p == 0) launch_chain(k_sort_pass<true>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, p);
-			else launch_chain(k_sort_pass<false>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, p);
+			if (p == 0) launch_chain(k_sort_pass<true>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, tickets + p, p);
+			else launch_chain(k_sort_pass<false>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, tickets + p, p);
 			T_END(2);
 		}
 		launches += 6;

@@ -672,3 +672,76 @@ def test_effects_from_json_descriptors(oracle_port):
     finally:
         ctx.close()
         ds.close()
+
+
+def test_repeated_and_invalid_ids_are_refused(oracle_port):
+    """ParticleSystem.cpp:812-821 would run a repeated id's sub-step loop once per entry; the device plan is per
+    effect, so the call is refused (SPR_ERR_UNSUPPORTED = -5) BEFORE anything changes: the frames around the refused
+    calls still match the oracle, which never sees them."""
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 14)
+    try:
+        seed = (1, 2, 3, 4)
+        s, o = ctx.create_system(seed), orc.OracleSystem(oracle_port, seed)
+        s2 = ctx.create_system((5, 6, 7, 8))
+        comp = S.comp_c1(burst=300)
+        ids = [s.add_effect(comp, abi.make_transform((k, 0, 0))) for k in range(3)]
+        assert ids == [o.add_effect(comp, abi.make_transform((k, 0, 0))) for k in range(3)]
+        other = [s2.add_effect(comp, abi.make_transform((0, 0, 0)))]
+        dt = s.effect_info(ids[0]).timeStep
+        for frame in range(6):
+            fa = abi.make_frame_args(dt, game_time=frame * dt, frame_index=frame)
+            with pytest.raises(P.SpearError, match="status -5"):
+                s.update([ids[0], ids[1], ids[0]], fa)
+            with pytest.raises(P.SpearError, match="status -5"):
+                ctx.update_batch([s, s2, s], [ids[:1], other, ids[1:]], fa)
+            with pytest.raises(P.SpearError, match="status -1"):
+                s.update([ids[0], 17], fa)
+            with pytest.raises(P.SpearError, match="status -1"):
+                ctx.update_batch([s, s2], [ids, [3]], fa)
+            s.update(ids, fa); o.update(ids, fa)
+            S.assert_snapshots_equal(S.snapshot(o, ids), S.snapshot(s, ids), "after refused calls, frame %d" % frame)
+        # a removed id is refused as well, and accepted again once it is reused
+        s.remove(ids[1]); o.remove(ids[1])
+        fa = abi.make_frame_args(dt, game_time=6 * dt, frame_index=6)
+        with pytest.raises(P.SpearError, match="status -1"):
+            s.update(ids, fa)
+        again = s.add_effect(comp, abi.make_transform((9, 0, 0)))
+        assert again == o.add_effect(comp, abi.make_transform((9, 0, 0))) == ids[1]
+        s.update(ids, fa); o.update(ids, fa)
+        S.assert_snapshots_equal(S.snapshot(o, ids), S.snapshot(s, ids), "after id reuse")
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("sort", [False, True], ids=["stream", "sorted"])
+def test_two_contexts_share_the_device(oracle_port, sort):
+    """Two contexts on their own streams run their frames concurrently on one GPU. The chained scans hand their tiles
+    out by ticket (the order the CTAs start), so neither context's look-back can wait for a CTA the other context's
+    kernels keep off the SMs; both must match their oracles bit for bit."""
+    P = _particles()
+    ctxs = [P.ParticleContext(sort_particles=sort, initial_slot_capacity=1 << 16) for _ in range(2)]
+    try:
+        pairs = []
+        for k, ctx in enumerate(ctxs):
+            seed = (3, 100 + k, 5, 6)
+            s, o = ctx.create_system(seed), orc.OracleSystem(oracle_port, seed)
+            comp = comp_big(150_000 + 50_000 * k)
+            assert s.add_effect(comp, abi.make_transform((1, 2, 3))) == o.add_effect(comp, abi.make_transform((1, 2, 3))) == 0
+            pairs.append((s, o))
+        dt = pairs[0][0].effect_info(0).timeStep
+        for frame in range(8):
+            fa = abi.make_frame_args(dt, game_time=frame * dt, frame_index=frame, camera=S.CAMERA)
+            for s, _ in pairs:       # asynchronous: both contexts' kernels are in flight together
+                s.update([0], fa)
+            for _, o in pairs:
+                o.update([0], fa)
+        for k, (s, o) in enumerate(pairs):
+            a, b = S.snapshot(o, [0]), S.snapshot(s, [0])
+            assert a[0]["info"] == b[0]["info"] and a["rng"] == b["rng"]
+            assert np.array_equal(a[0]["free"], b[0]["free"])
+            exp = expected_sorted(a[0]["stream"])[0] if sort else a[0]["stream"]
+            assert exp.tobytes() == b[0]["stream"].tobytes(), "context %d" % k
+    finally:
+        for ctx in ctxs:
+            ctx.close()
