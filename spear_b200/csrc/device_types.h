@@ -136,7 +136,7 @@ struct ActiveEntry {
 	uint32_t effect;        // context-wide effect index
 	uint32_t numSubsteps;
 	uint32_t planBase;      // first PlanRec of this effect in the frame
-	uint32_t flags;         // bit0: burst handled by the wide burst kernel
+	uint32_t flags;         // bit0: burst handled by the wide burst kernel; bit1: the host wants the exact slot count mirrored (its capacity bound is not final)
 };
 
 // Spawn plan of one simulateParticlesImp call (one effect, one sub-step), written by

@@ -28,8 +28,12 @@ void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &
 	uint64_t &ticketBase);
 void configure_stream_fused(int ctasPerSm[2]);
 void configure_sort_kernels();
+// An encoded CUtensorMap of the vertex pool, opaque to the host layer (cuda.h stays out of its headers).
+struct alignas(64) VertexTensorMap { unsigned char bytes[128]; };
+bool encode_vertex_map(VertexTensorMap *out, void *vertices, uint64_t slots);
+// vertexMap: nullptr = expansion stores through the LSU; else full granules leave through bulk tensor stores (TMA)
 uint32_t launch_stream_fused(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2], uint64_t &ticketBase);
+	uint32_t epoch, bool gravityPoints, uint32_t numSms, const int ctasPerSm[2], uint64_t &ticketBase, const VertexTensorMap *vertexMap);
 void launch_expand_stream(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp);
 void launch_finalize(cudaStream_t st, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t stamp);
 void launch_query_frustum(cudaStream_t st, const TablePtrs &tab, uint32_t numGlobals, uint32_t systemIdx, const float frustum[32],

@@ -56,6 +56,7 @@ Context::Context(const SprContextDesc &desc)
 	SPR_CUDA(cudaEventCreateWithFlags(&stagingEvent[1], cudaEventDisableTiming));
 	streamFused = getenv("SPR_STREAM_TWO_PASS") == nullptr; // SPR_STREAM_TWO_PASS=1 selects the two-pass stream mode (A/B measurement)
 	configure_stream_fused(streamFusedCtasPerSm);
+	{ const char *e = getenv("SPR_STREAM_TMA"); streamTma = !(e && e[0] == '0'); }
 	configure_sort_kernels();
 	freeRanges.resize(33);
 	SPR_CUDA(cudaMalloc(&dTickets, 2 * sizeof(unsigned long long)));
@@ -145,6 +146,7 @@ void Context::ensurePool(uint64_t slots)
 		if (!(flags & SPR_CTX_SORT_PARTICLES)) regrow(dWordAliveBase, poolCapacity / 32, cap / 32, poolCapacity / 32, 0, stream);
 	}
 	poolCapacity = cap;
+	vertexMapValid = streamTma && !(flags & SPR_CTX_SORT_PARTICLES) && encode_vertex_map(&vertexMap, dVertices, poolCapacity);
 }
 
 uint32_t Context::allocRange(uint32_t capacity)
@@ -440,6 +442,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			// <= 20 timer spawns per sub-step (:478), each sub-step rounds up to one Particle4
 			const uint64_t add = (uint64_t)nsub * (kMaxTimerSpawns + 3) + burst + 3;
 			if (!E.capacityFinal) {
+				ae.flags |= 2u; // k_finalize mirrors the exact slot count of this frame
 				// re-base the bound on the newest exact count the device has mirrored (no synchronisation: an older
 				// entry only means more allowances are added on top of it)
 				const unsigned long long m = ((volatile const unsigned long long*)slotMirror)[E.global];
@@ -643,7 +646,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		}
 		if (!sortMode && streamFused) {
 			// stream mode, one pass: integrate + ranks + free list + 4x expansion in a software-pipelined persistent kernel
-			TIMED(kKStreamFused, launch_stream_fused(stream, pool, tab, poolTiles, frameStamp, round, epoch, typesWithGravityPoints != 0, numSms, streamFusedCtasPerSm, ticketBase[0]));
+			TIMED(kKStreamFused, launch_stream_fused(stream, pool, tab, poolTiles, frameStamp, round, epoch, typesWithGravityPoints != 0, numSms, streamFusedCtasPerSm, ticketBase[0], vertexMapValid ? &vertexMap : nullptr));
 		} else {
 			TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, numTinyEffects != 0, camera));
 			TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch, !sortMode, ticketBase[1]));

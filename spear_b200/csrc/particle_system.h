@@ -256,6 +256,9 @@ struct Context {
 	DeviceArray<RenderGather> gatherD;
 	DeviceArray<uint32_t> gatherIdxD;
 	int streamFusedCtasPerSm[2] = { 1, 1 };
+	VertexTensorMap vertexMap;                 // tensor map of dVertices for k_stream_fused's bulk stores (re-encoded when the pool grows)
+	bool vertexMapValid = false;
+	bool streamTma = true;                     // SPR_STREAM_TMA=0: expansion stores through the LSU (A/B)
 	bool streamFused = true;               // stream mode: one-pass pipelined kernel (default) or integrate + dead_append + expand
 	uint32_t numTinyEffects = 0;          // live effects whose whole range is one 128-slot granule
 	uint32_t typesWithGravityPoints = 0; // live effect types with gravityPoints (selects the kernel variant)
