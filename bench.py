@@ -44,13 +44,19 @@ ALG_BYTES_UNSORTED = 188.0
 KERNEL_ALG_BYTES = {"k_integrate": 60.0, "k_expand_sorted": 160.0, "k_expand_stream": 160.0, "k_stream_fused": 188.0}
 
 
+TRAFFIC_FILES = ("r02_traffic.json", "r01_traffic.json")   # newest committed capture first
+
+
 def profiled_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (C3 only)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        return json.load(open(p)).get(kernel)
-    except Exception:
-        return None
+    for name in TRAFFIC_FILES:
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
+            if v is not None:
+                return v, "profiles/%s (ncu --set full, dram bytes per launch)" % name
+        except Exception:
+            pass
+    return None, None
 
 
 def measured_peak():
@@ -453,9 +459,12 @@ def run_ours(args, rank, world):
                 ev_free[k ^ 1].record(ext_b)
                 ctx_b.expand_from_peers(peer_ptrs[k], verts_f.data_ptr(), world * cap, total_dev.data_ptr(), my_rank=rank)
 
-            def timed_overlapped():
+            def timed_overlapped(share):
                 """`--repeats` regions of exactly K steps each (simulation of frame k+1 under the assembly of frame k);
-                every region ends when the LAST assembly has finished on every rank. Returns the median region."""
+                every region ends when the LAST assembly has finished on every rank. Returns the median region.
+                share = resident CTAs per SM of the assembly kernel (sprContextSetAssemblyShare): it is NVLink-bound with
+                2 CTAs per SM as with 8, and what it leaves free runs the next frame's simulation."""
+                ctx_b.set_assembly_share(share)
                 for _ in range(3):
                     ostep()
                 regs = []
@@ -480,8 +489,24 @@ def run_ours(args, rank, world):
 
             gms, gps = timed(gstep)
             fms, fps = timed(fstep)
-            (oms, ops, olaunches), o_regions = timed_overlapped()
+            by_share = {}
+            for share in [int(x) for x in args.assembly_shares.split(",")]:
+                by_share[share] = timed_overlapped(share)
+            best_share = min(by_share, key=lambda k: by_share[k][0][0])
+            (oms, ops, olaunches), o_regions = by_share[best_share]
             ctx_b.synchronize()
+            # the assembly kernel alone, all ranks pulling at the same time (a 4-byte all_reduce lines them up): the
+            # NVLink roofline of sprExpandFromPeers
+            ak = []
+            for _ in range(args.steps):
+                dist.all_reduce(flag)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(ext)
+                ctx.expand_from_peers(peer_ptrs[(kstep[0] - 1) & 1], verts_f.data_ptr(), world * cap, total_dev.data_ptr(), my_rank=rank)
+                a1.record(ext)
+                ak.append((a0, a1))
+            barrier()
+            assembly_kernel_ms = sum(a.elapsed_time(b) for a, b in ak) / len(ak)
             # same state through both paths: the fused stream must equal the NCCL one (padding removed)
             ctx.pack_runs(sys_list, eff_list, mine.data_ptr(), cap, None, want_total=False)
             dist.all_gather_into_tensor(allrec, mine)
@@ -502,13 +527,15 @@ def run_ours(args, rank, world):
                   "fused_particle_steps_this_rank": fps, "fused_matches_nccl": ok,
                   "overlapped_ms_per_step": oms / args.steps, "overlapped_particle_steps_this_rank": ops,
                   "overlapped_launches_this_rank": olaunches, "overlapped_regions_ms_per_step": o_regions,
+                  "overlapped_share": best_share, "overlapped_by_share": {str(k): v[0][0] / args.steps for k, v in by_share.items()},
+                  "assembly_kernel_ms": assembly_kernel_ms,
                   "nvlink_bytes_in_per_step": int(sum(c for r, c in enumerate(counts) if r != rank) * 32)}
 
     # ---- max over ranks / aggregate
     if world > 1:
-        t = torch.tensor([ms, e2e_ms, gather["ms_per_step"] * args.steps, gather["fused_ms_per_step"] * args.steps], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_ms, gather["ms_per_step"] * args.steps, gather["fused_ms_per_step"] * args.steps, gather["assembly_kernel_ms"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, gms_tot, fms_tot = [float(x) for x in t.tolist()]
+        ms, e2e_ms, gms_tot, fms_tot, akms = [float(x) for x in t.tolist()]
         c = torch.tensor([particle_steps, e2e_particle_steps, gather["particle_steps_this_rank"], float(launches),
                           gather["fused_particle_steps_this_rank"], 1.0 if gather["fused_matches_nccl"] else 0.0,
                           gather["overlapped_particle_steps_this_rank"], float(gather["overlapped_launches_this_rank"])], dtype=torch.float64, device="cuda")
@@ -539,8 +566,8 @@ def run_ours(args, rank, world):
         roof = None
         if dom:
             roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": profiled_traffic(dom) if name == "c3" else None,
-                    "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram bytes per launch)" if name == "c3" else None,
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": profiled_traffic(dom)[0] if name == "c3" else None,
+                    "traffic_source": profiled_traffic(dom)[1] if name == "c3" else None,
                     "peak_source": peak_src,
                     "alg_bytes_per_particle": alg_key[dom],
                     "step": {"alg_bytes_per_particle_step": alg, "achieved": value / world * alg / 1e9,
@@ -593,14 +620,19 @@ def run_ours(args, rank, world):
                 "fused": {"value_with_gather": f_total_ps / (fms_tot * 1e-3), "ms_per_step": fms_tot / args.steps,
                           "assembly_ms": (fms_tot - ms) / args.steps,
                           "nvlink_gbs_in_per_gpu_during_assembly": nv / max((fms_tot - ms) / args.steps * 1e-3, 1e-9) / 1e9,
-                          "nvlink_roofline": {"peak_gbs": 770.0, "peak_source": "B200_PROFILING.md measured peer copy per direction",
-                                              "frac": nv / max((fms_tot - ms) / args.steps * 1e-3, 1e-9) / 1e9 / 770.0},
+                          "nvlink_roofline": {"kernel": "k_expand_from_peers", "ms_per_launch": akms, "achieved_gbs": nv / (akms * 1e-3) / 1e9,
+                                              "peak_gbs": 770.0, "peak_source": "B200_PROFILING.md measured peer copy per direction",
+                                              "frac": nv / (akms * 1e-3) / 1e9 / 770.0,
+                                              "note": "the assembly kernel alone (CUDA events, max over ranks, all ranks pulling at once); all-pull-all with no stores at all "
+                                                      "tops out at ~655 GB/s on this box (profiles/r02_peer_allgather_microbench_8gpu.txt)"},
                           "matches_nccl_path_bit_for_bit": f_ok == world,
                           "note": "step + sprRunBufferPack + 4-byte all_reduce barrier + sprExpandFromPeers: ONE kernel per rank reads every rank's run from IPC-mapped peer memory over NVLink and writes the 4x expanded draw stream locally"},
                 "fused_overlapped": {"value_with_gather": o_total_ps / (oms * 1e-3), "ms_per_step": oms / args.steps,
                                      "nvlink_gbs_in_per_gpu": nv / (oms / args.steps * 1e-3) / 1e9,
                                      "nvlink_roofline_frac": nv / (oms / args.steps * 1e-3) / 1e9 / 770.0,
-                                     "note": "the fused assembly of frame k runs on a second stream while frame k+1 is simulated (double-buffered run buffers)"},
+                                     "assembly_ctas_per_sm": gather["overlapped_share"], "ms_per_step_by_assembly_share": gather["overlapped_by_share"],
+                                     "note": "the fused assembly of frame k runs on a second stream while frame k+1 is simulated (double-buffered run buffers); "
+                                             "the assembly kernel keeps a fixed share of every SM (sprContextSetAssemblyShare), the best share of --assembly-shares is reported"},
                 "nvlink_bytes_in_per_gpu_per_step": nv}
         if world == 1 and sorted_mode and not args.no_stream_mode:
             # the strict drop-in stream (ascending slot order, no per-particle sort) on the same workload,
@@ -834,6 +866,7 @@ def main():
     ap.add_argument("--no-stream-mode", action="store_true", help="skip the extra stream-mode (no sort) measurement at N=1")
     ap.add_argument("--no-billboards", action="store_true", help="skip the extra cl::BillboardSystem (row N4) measurement at N=1")
     ap.add_argument("--no-vertex-stage", action="store_true", help="skip the extra vertex-stage (sprShadeVertices) measurement at N=1")
+    ap.add_argument("--assembly-shares", default="1,2,3,8", help="N > 1: CTAs per SM of the peer-memory assembly kernel to try in the overlapped run (best one is reported)")
     ap.add_argument("--no-c4-slice", action="store_true", help="skip the extra C4-slice measurement (the N > 1 per-GPU workload) at N=1")
     ap.add_argument("--no-kernel-timing", action="store_true", help="no per-launch CUDA events inside the timed region (no roofline object)")
     args = ap.parse_args()

@@ -609,6 +609,12 @@ SPR_API int sprRunBufferPack(SprContext *ctx, SprSystem *const *systems, const u
  * order in which the peers are read (every GPU starts on a different peer and reads all of them concurrently). */
 SPR_API int sprExpandFromPeers(SprContext *ctx, void *const *bufferPtrs, uint32_t numRanks, uint32_t myRank,
 	SprGpuParticle *deviceVerticesOut, uint64_t capacityRecords, uint64_t *deviceTotalRecords);
+/* How much of the GPU sprExpandFromPeers takes: resident CTAs (256 threads) per SM of its persistent grid, 1..8
+ * (0 = default 8, the whole GPU). The assembly is bound by NVLink (all GPUs pulling from all: ~650 GB/s into each GPU
+ * whether 2 or 8 CTAs per SM pull, profiles/r02_peer_allgather_microbench_8gpu.txt), so a caller that runs it on a second
+ * context / stream under the next frame's simulation gives it a small share and leaves the rest of every SM to the
+ * simulation kernels (bench.py: gather.fused_overlapped). */
+SPR_API int sprContextSetAssemblyShare(SprContext *ctx, uint32_t ctasPerSm);
 
 #ifdef __cplusplus
 }

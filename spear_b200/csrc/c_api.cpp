@@ -533,10 +533,17 @@ SPR_API int sprExpandFromPeers(SprContext *c, void *const *bufferPtrs, uint32_t 
 	REQUIRE(c && bufferPtrs && deviceVerticesOut && numRanks >= 1 && numRanks <= 16 && myRank < numRanks);
 	return guarded([&] {
 		SPR_CUDA(cudaSetDevice(c->ctx.device));
-		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, myRank, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms);
+		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, myRank, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms * c->ctx.assemblyCtasPerSm);
 		c->ctx.launchCount++;
 		SPR_CUDA(cudaGetLastError());
 	});
+}
+
+SPR_API int sprContextSetAssemblyShare(SprContext *c, uint32_t ctasPerSm)
+{
+	REQUIRE(c && ctasPerSm <= 8);
+	c->ctx.assemblyCtasPerSm = ctasPerSm ? ctasPerSm : 8;
+	return SPR_OK;
 }
 
 SPR_API int sprExpandRuns(SprContext *c, const SprGpuParticle *deviceRecords, uint64_t numRecords, SprGpuParticle *deviceVerticesOut)

@@ -904,6 +904,16 @@ __device__ __forceinline__ void tma_store_granule(const CUtensorMap *map, const 
 __device__ __forceinline__ void tma_wait_stage_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// The record prefetch is speculative in the first sub-step of a frame (every owned granule is almost certainly
+// simulated); later rounds exist for the few effects that owe more than one sub-step (C5: one in ten), so there the
+// round record is looked at first -- 8 bytes instead of 4 KB for every effect that is done. (Phase A repeats the test on
+// the full record and never touches the registers of a granule that is not active.)
+__device__ __forceinline__ bool round_wants(const TablePtrs &tab, uint32_t g, uint32_t stamp, uint32_t round)
+{
+	if (round == 0) return true;
+	return tab.roundConsts[g].stamp == stamp && tab.roundConsts[g].round == round;
+}
+
 // The next pool tile with an owner, by ticket. Tiles nobody owns (the tail of every power-of-two slot range behind the
 // effect's slot bound: 63 of 128 tiles in a 65536-particle effect) are consumed right here: as iterations of their
 // own they cost nothing, but they let CTAs run ahead of the ones working on real tiles, and a CTA that is early at its
@@ -947,7 +957,7 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 	if (warp < 8 && sTicket[0] < numPoolTiles) {
 		const uint32_t first = sTicket[0];
 		gNext = pool.granuleOwner[first * 8 + warp];
-		if (gNext != kNoOwner) {
+		if (gNext != kNoOwner && round_wants(tab, gNext, stamp, round)) {
 			const float4 *p = pool.state + 2ull * ((uint64_t)(first * 8 + warp) * kGranuleSlots + lane);
 #pragma unroll
 			for (int r = 0; r < 4; r++) ld_record(p + r * 64, a[r], b[r]);
@@ -1071,7 +1081,7 @@ __global__ void __launch_bounds__(288, 3) k_stream_fused(PoolPtrs pool, TablePtr
 			gNext = kNoOwner;
 			if (tile < numPoolTiles && nextTile < numPoolTiles) {
 				gNext = pool.granuleOwner[nextTile * 8 + warp];
-				if (gNext != kNoOwner) {
+				if (gNext != kNoOwner && round_wants(tab, gNext, stamp, round)) {
 					const float4 *p = pool.state + 2ull * ((uint64_t)(nextTile * 8 + warp) * kGranuleSlots + lane);
 #pragma unroll
 					for (int r = 0; r < 4; r++) ld_record(p + r * 64, a[r], b[r]);
@@ -1563,13 +1573,13 @@ void launch_pack_runs_buf(cudaStream_t st, const PoolPtrs &pool, const TablePtrs
 	k_pack_runs_buf<<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, (float4*)buf, capacityRecords);
 }
 
-void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numSms)
+void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numCtas)
 {
 	PeerRuns runs;
 	runs.numRanks = numRanks;
 	runs.myRank = myRank;
 	for (uint32_t r = 0; r < 16; r++) runs.buf[r] = r < numRanks ? (const float4*)bufs[r] : nullptr;
-	k_expand_from_peers<<<numSms * 8, 256, 0, st>>>(runs, out, capacityRecords, (unsigned long long*)totalOut);
+	k_expand_from_peers<<<numCtas, 256, 0, st>>>(runs, out, capacityRecords, (unsigned long long*)totalOut); // persistent: grid-stride over 1024-record chunks
 }
 
 void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numRecords, float4 *out, uint32_t numSms)

@@ -29,7 +29,7 @@ EXPORTS = [
     "sprGetEffectTypeUbo", "sprGetEffectDeviceView", "sprPackRuns", "sprExpandRuns",
     "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType", "sprRenderMainBatch", "sprContextGetTotals",
     "sprRunBufferCreate", "sprRunBufferDestroy", "sprRunBufferGetIpcHandle", "sprRunBufferOpenPeer", "sprRunBufferClosePeer",
-    "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers", "sprShadeVertices",
+    "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers", "sprContextSetAssemblyShare", "sprShadeVertices",
     "sprBillboardSystemCreate", "sprBillboardSystemDestroy", "sprBillboardAdd", "sprBillboardRenderMain",
     "sprBillboardReadVertices",
     "sprDescriptorsFromJson", "sprDescriptorCount", "sprDescriptorGet", "sprDescriptorTextureName", "sprDescriptorsFree",
@@ -87,6 +87,7 @@ def _load():
     lib.sprRunBufferDevicePtr.argtypes = [vp]
     lib.sprRunBufferPack.argtypes = [vp, P(vp), P(u32), u32, vp]
     lib.sprExpandFromPeers.argtypes = [vp, P(vp), u32, u32, vp, u64, vp]
+    lib.sprContextSetAssemblyShare.argtypes = [vp, u32]
     lib.sprShadeVertices.argtypes = [vp, P(abi.DrawRecord), u32, P(abi.FogImage), vp, u64, P(u64)]
     lib.sprBillboardSystemCreate.argtypes = [vp, u32, P(vp)]
     lib.sprBillboardSystemDestroy.argtypes = [vp]
@@ -265,6 +266,10 @@ class ParticleContext:
         n = len(buffer_ptrs)
         arr = (C.c_void_p * n)(*buffer_ptrs)
         _check(lib.sprExpandFromPeers(self.h, arr, n, my_rank, device_vertices_out, capacity_records, device_total))
+
+    def set_assembly_share(self, ctas_per_sm):
+        """Resident CTAs per SM of expand_from_peers (0 = the whole GPU)."""
+        _check(lib.sprContextSetAssemblyShare(self.h, ctas_per_sm))
 
     def expand_runs(self, device_records, num_records, device_vertices_out):
         _check(lib.sprExpandRuns(self.h, device_records, num_records, device_vertices_out))
