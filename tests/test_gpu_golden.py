@@ -38,11 +38,9 @@ def test_c1_full_600_steps(ctx):
     g = json.load(open(os.path.join(GOLDEN, "c1_full.json")))
     s = ctx.create_system((1, 2, 3, 4))
     e = s.add_effect(S.comp_c1(), abi.make_transform((1, 2, 3)))
-    dt, total = s.effect_info(e).timeStep, 0
+    dt = s.effect_info(e).timeStep
     for i in range(600):
         s.update([e], abi.make_frame_args(dt, game_time=i * dt, frame_index=i))
-        if i % 50 == 49:
-            pass
     info = s.effect_info(e)
     assert (info.slotCount, info.aliveCount, info.freeCount) == (g["slotCount"], g["aliveCount"], g["freeCount"]) == (13224, 4012, 9212)
     assert "%016x" % s.rng_state()[0] == g["rng"]
