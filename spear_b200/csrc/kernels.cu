@@ -617,8 +617,7 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez);
 			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez);
 			if (KEYS) {
-				float dx = camX - ra.x, dy = camY - ra.y, dz = camZ - ra.z;
-				key[r] = ~enc_float(dx*dx + dy*dy + dz*dz);       // sf::lengthSq (src/sf/Vector.h:99), descending
+				key[r] = depth_key(ra.x, ra.y, ra.z, camX, camY, camZ); // sf::lengthSq (src/sf/Vector.h:99), descending
 				keyMin = min(keyMin, key[r]);
 				if (!tiny) pool.keys[keyIdx + r * 32] = key[r];
 			}
