@@ -407,11 +407,6 @@ SPR_API int sprRenderMainBatch(SprContext *ctx, SprSystem *const *systems, uint3
 	const uint32_t *const *visibleIds, const uint32_t *numVisible,
 	const SprRenderArgs *args, size_t argsStride, SprRenderOutput *outs);
 
-/* Sort mode, large effects (no reference counterpart): how many per-effect depth sorts so far went through the depth
- * buckets (out[0]) and how many had depth quantiles but fell back to the radix passes because a bucket outgrew its CTA
- * (out[1]) -- same results either way. Synchronises the context stream. */
-SPR_API int sprContextGetDepthBucketStats(SprContext *ctx, uint64_t out[2]);
-
 /* ------------------------------------------------------------------------ */
 /* Parity read-backs (host copies; each synchronises the context stream)      */
 /* ------------------------------------------------------------------------ */

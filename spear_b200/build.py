@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspear_particles.so")
-SOURCES = ["kernels.cu", "sort.cu", "depth_buckets.cu", "vertex_stage.cu", "billboards.cu", "particle_system.cpp", "descriptor_json.cpp", "c_api.cpp"]
+SOURCES = ["kernels.cu", "sort.cu", "vertex_stage.cu", "billboards.cu", "particle_system.cpp", "descriptor_json.cpp", "c_api.cpp"]
 HEADERS = ["launch.h", "device_types.h", "kernels.h", "host_math.h", "particle_system.h", os.path.join("..", "..", "include", "spear_particles.h")]
 
 NVCC_FLAGS = [

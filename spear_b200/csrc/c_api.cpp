@@ -68,10 +68,9 @@ SPR_API int sprContextSynchronize(SprContext *ctx) { REQUIRE(ctx); return guarde
 SPR_API void *sprContextStream(SprContext *ctx) { return ctx ? (void*)ctx->ctx.stream : nullptr; }
 SPR_API uint64_t sprContextLaunchCount(SprContext *ctx) { return ctx ? ctx->ctx.launchCount : 0; }
 
-static const char *const kKernelNames[Context::kNumKernelClasses] = {
+static const char *const kKernelNames[17] = {
 	"k_scatter_words", "k_plan", "k_emit_warp", "k_emit_burst", "k_integrate", "k_finalize", "k_stream_fused", "k_gather_render",
-	"k_pack_runs", "k_expand_runs", "k_sort_hist", "k_sort_scan", "k_sort_pass", "k_expand_sorted", "k_dead_append", "k_expand_stream", "k_sort_small",
-	"k_bucket_hist", "k_bucket_scan", "k_bucket_scatter", "k_bucket_finish", "k_bucket_splitters" };
+	"k_pack_runs", "k_expand_runs", "k_sort_hist", "k_sort_scan", "k_sort_pass", "k_expand_sorted", "k_dead_append", "k_expand_stream", "k_sort_small" };
 
 SPR_API int sprContextEnableKernelTiming(SprContext *ctx, int enable)
 {
@@ -85,28 +84,13 @@ SPR_API int sprContextGetKernelTimes(SprContext *ctx, int reset, const char **na
 	return guarded([&] {
 		ctx->ctx.resolveTimings();
 		uint32_t n = 0;
-		for (int k = 0; k < Context::kNumKernelClasses; k++) {
+		for (int k = 0; k < 17; k++) {
 			if (!ctx->ctx.kernelLaunches[k]) continue;
 			if (n < capacity) { if (names) names[n] = kKernelNames[k]; if (ms) ms[n] = ctx->ctx.kernelMs[k]; if (launches) launches[n] = ctx->ctx.kernelLaunches[k]; }
 			n++;
 		}
 		*outCount = n;
-		if (reset) for (int k = 0; k < Context::kNumKernelClasses; k++) { ctx->ctx.kernelMs[k] = 0; ctx->ctx.kernelLaunches[k] = 0; }
-	});
-}
-
-SPR_API int sprContextGetDepthBucketStats(SprContext *ctx, uint64_t out[2])
-{
-	REQUIRE(ctx && out);
-	return guarded([&] {
-		out[0] = out[1] = 0;
-		Context &c = ctx->ctx;
-		SPR_CUDA(cudaSetDevice(c.device));
-		if (!c.dBktStats.ptr) return;
-		unsigned long long h[2] = { 0, 0 };
-		SPR_CUDA(cudaMemcpyAsync(h, c.dBktStats.ptr, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
-		SPR_CUDA(cudaStreamSynchronize(c.stream));
-		out[0] = h[0]; out[1] = h[1];
+		if (reset) for (int k = 0; k < 17; k++) { ctx->ctx.kernelMs[k] = 0; ctx->ctx.kernelLaunches[k] = 0; }
 	});
 }
 
@@ -299,7 +283,8 @@ SPR_API int sprReadStreamSlots(SprSystem *sys, uint32_t effectId, uint32_t *out,
 		uint32_t m = g.aliveCount < capacity ? g.aliveCount : capacity;
 		if (!m || !out) return;
 		if (ctx->flags & SPR_CTX_SORT_PARTICLES) {
-			ctx->readSortedSlots(E.global, g.aliveCount, g.slotCount, out, m);
+			SPR_CUDA(cudaMemcpyAsync(out, ctx->dVals[0] + P.slotBase, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			SPR_CUDA(cudaStreamSynchronize(ctx->stream));
 		} else {
 			// stream order is ascending slot order over the live slots (ParticleSystem.cpp:611-665)
 			std::vector<SprGpuParticle> slots(g.slotCount);

@@ -39,13 +39,6 @@ static const uint32_t kSortTileKeys = SPR_SORT_TILE_KEYS; // keys per CTA in the
 #define SPR_STRICT_TILE_TICKETS 0
 #endif
 static const uint32_t kSmallSortMax = 18432;   // an effect of at most this many slots is sorted by ONE CTA (k_sort_small)
-// Depth buckets (depth_buckets.cu): a tile-path effect whose previous frame left depth quantiles ("splitters") has its
-// records partitioned into at most kMaxBins buckets of about kBucketTarget particles, each finished by one CTA.
-static const uint32_t kMaxBins = 2048;         // buckets per effect
-static const uint32_t kBucketCap = 9216;       // particles one CTA of k_bucket_finish sorts (512 threads x 18)
-static const uint32_t kBucketTarget = 4608;    // the host asks for ceil(slot bound / kBucketTarget) buckets
-static const uint32_t kLutCells = 4096;        // cells of the key -> bucket look-up table in front of the splitter search
-static const uint32_t kChunkTiles = 64;        // sort tiles per chunk of the two-level scan of the per-tile bucket counts
 
 static const float kHugeLife = 1e20f;          // ParticleSystem.cpp:27
 static const float kHugeLifeCmp = 1e19f;       // ParticleSystem.cpp:28
@@ -128,8 +121,8 @@ __host__ __device__ inline uint32_t effect_key_min(const EffectState &S)
 
 #ifdef __CUDACC__
 // Depth key of a live particle: ~enc(|camera - p|^2), sf::lengthSq (src/sf/Vector.h:99) in its operation order; an
-// ascending stable sort of the keys is back to front with ties by slot (BillboardSystem.cpp:41-51). ONE definition:
-// k_integrate_pass writes it per slot, the depth-bucket kernels recompute it from the moved record and must get the same bits.
+// ascending stable sort of the keys is back to front with ties by slot (BillboardSystem.cpp:41-51). ONE definition for
+// every kernel that needs the key of a record.
 __device__ __forceinline__ uint32_t depth_key(float px, float py, float pz, float camX, float camY, float camZ)
 {
 	const float dx = camX - px, dy = camY - py, dz = camZ - pz;
@@ -212,21 +205,6 @@ struct ShadeJob {
 
 // Sort tile: `tile`-th 4096-key tile of effect `effect`'s pair segment.
 struct SortTile { uint32_t effect; uint32_t tile; };
-
-// Depth buckets: one tile-path segment's view of the frame (host built).
-struct BucketSeg {
-	uint32_t bins;          // buckets of the splitter table read this frame; 0: none, the radix passes sort this effect
-	uint32_t nextBins;      // buckets of the table written for the next frame; 0: none
-	uint32_t table;         // the effect's pair of splitter tables: words [table * 2 * kMaxBins, +2 * kMaxBins)
-	uint32_t parity;        // which of the two is read this frame (the other one is written)
-	uint32_t firstRow;      // the segment's first row in the per-tile tables (= index of its first tile in the tile list)
-	uint32_t firstChunk;    // ... and in the per-chunk tables
-	uint32_t numTiles;
-	uint32_t _pad;
-};
-// kChunkTiles consecutive tiles of one segment
-struct BucketChunk { uint32_t seg, firstRow, numTiles, row; };
-struct BucketJob { uint32_t seg, bin; };
 
 // One billboard of the frame (cl::BillboardSystemImp::BillboardImp + its BillboardOrder::depth,
 // src/client/BillboardSystem.cpp:30-51, with the sp::Sprite fields renderMain reads, src/sp/Sprite.h:44-57).

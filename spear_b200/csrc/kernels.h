@@ -67,37 +67,7 @@ struct SortScratch {
 	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases, then [numSegments] pass masks, then [4] pass tickets
 	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
 };
-// depth_buckets.cu: everything the depth-bucket path of one frame needs (built by Context::update).
-struct BucketArgs {
-	bool anyBins;                    // some segment has a splitter table to read: the front kernels run
-	bool anyNextBins;                // some segment gets a table for the next frame
-	bool allBins;                    // every tile-path segment has a table to read
-	uint32_t stride;                 // row length of the per-tile / per-chunk / per-segment tables: power of two >= 32, >= every segment's bins
-	uint32_t numChunks, numJobs;
-	const BucketSeg *segs;           // [numBigSegments]
-	const BucketChunk *chunks;       // [numChunks]
-	const BucketJob *jobs;           // [numJobs] one per (segment, bucket)
-	uint32_t *splitters;             // [tables][2][kMaxBins]
-	uint16_t *lut;                   // [tables][2][kLutCells + 2] key cell -> bucket of the cell's first key
-	uint32_t *lutMeta;               // [tables][2][4] lo, shift of the look-up table
-	uint16_t *binId;                 // per pool slot: its bucket this frame, 0xffff when it holds no live particle
-	uint16_t *tileCnt;               // [numBigTiles][stride]
-	uint32_t *tileOff;               // [numBigTiles][stride]
-	uint32_t *chunkOff;              // [numChunks][stride]
-	uint32_t *bucketBase, *bucketCount; // [numBigSegments][stride]
-	uint32_t *bucketOk;              // [numSegments] verdict per segment, zeroed at the start of the frame
-	unsigned long long *stats;       // [2] running count of the verdicts: fits / fell back
-	float4 *part;                    // per pool slot: the records partitioned by bucket (same indexing as PoolPtrs::state)
-	float camera[3];
-};
-struct SortTimingHooks;
-void configure_bucket_kernels();
-uint32_t launch_depth_buckets(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const BucketArgs &bk,
-	const uint32_t *segEffects, uint32_t numBigSegments, const SortTile *tiles, uint32_t numBigTiles, const SortTimingHooks *hooks);
-uint32_t launch_bucket_splitters(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const BucketArgs &bk,
-	const uint32_t *segEffects, uint32_t numBigSegments, const SortTimingHooks *hooks);
-// Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted, 4 sort_small,
-// 5 bucket_hist, 6 bucket_scan (both), 7 bucket_scatter, 8 bucket_finish, 9 bucket_splitters).
+// Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted, 4 sort_small).
 struct SortTimingHooks {
 	void *ctx;
 	void *(*begin)(void *ctx, int kernel);
@@ -111,6 +81,6 @@ void clear_sort_scratch(cudaStream_t st, const SortScratch &scratch, uint32_t nu
 // per effect; k_expand_sorted then runs over all tiles. Returns the number of launches.
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &scratch,
 	const uint32_t *segEffects, uint32_t numSegments, uint32_t numBigSegments, const SortTile *tiles, uint32_t numTiles, uint32_t numBigTiles,
-	const SortTimingHooks *hooks, const BucketArgs *buckets);
+	const SortTimingHooks *hooks);
 
 } // namespace spr

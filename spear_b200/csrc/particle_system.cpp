@@ -58,8 +58,6 @@ Context::Context(const SprContextDesc &desc)
 	configure_stream_fused(streamFusedCtasPerSm);
 	{ const char *e = getenv("SPR_STREAM_TMA"); streamTma = !(e && e[0] == '0'); }
 	configure_sort_kernels();
-	configure_bucket_kernels();
-	{ const char *e = getenv("SPR_DEPTH_BUCKETS"); depthBuckets = !(e && e[0] == '0'); }
 	freeRanges.resize(33);
 	SPR_CUDA(cudaMalloc(&dTickets, 2 * sizeof(unsigned long long)));
 	SPR_CUDA(cudaMemsetAsync(dTickets, 0, 2 * sizeof(unsigned long long), stream));
@@ -79,7 +77,6 @@ Context::~Context()
 #endif
 	cudaFree(dSlotState); cudaFree(dFreeStack); cudaFree(dVertices);
 	cudaFree(dKeys[0]); cudaFree(dKeys[1]); cudaFree(dVals[0]); cudaFree(dVals[1]);
-	cudaFree(dBinId); cudaFree(dPart);
 	cudaFree(dAliveMask); cudaFree(dDeadMask); cudaFree(dWordAliveBase);
 	cudaFree(dGranuleOwner); cudaFree(dTileStatus[0]); cudaFree(dTileStatus[1]); cudaFree(dTickets);
 	if (slotMirror) cudaFreeHost(slotMirror);
@@ -140,10 +137,6 @@ void Context::ensurePool(uint64_t slots)
 			regrow(dKeys[i], poolCapacity, cap, 0, -1, stream);
 			regrow(dVals[i], poolCapacity, cap, i == 0 ? used : 0, -1, stream); // vals[0] holds the sorted slot order of every effect
 		}
-		if (depthBuckets) {
-			regrow(dBinId, poolCapacity, cap, used, -1, stream); // (read together with vals[0] by the parity read-back)
-			regrow(dPart, poolCapacity * 2, cap * 2, 0, -1, stream);
-		}
 	}
 	{
 		// the ballots (and, in stream mode, the word ranks) are rewritten by every simulated step, but an
@@ -194,11 +187,7 @@ uint32_t Context::allocEffectGlobal()
 		dRoundConsts.reserve(numEffectGlobals, keep, stream);
 		dEffectAnyDead.reserve(numEffectGlobals, keep, stream);
 		ensureSlotMirror(numEffectGlobals);
-		splitterTable.resize(numEffectGlobals, kNoOwner);
-		splitterBins.resize(numEffectGlobals, 0);
-		splitterParity.resize(numEffectGlobals, 0);
 	}
-	splitterBins[g] = 0; // depth quantiles belong to the effect that produced them
 	effectLive[g] = 1;
 	return g;
 }
@@ -263,8 +252,7 @@ void Context::ensureOwned(uint32_t g, uint32_t slotUpperBound)
 
 // Kernel classes for the optional timing hooks (names in c_api.cpp: sprKernelName).
 enum { kKScatter = 0, kKPlan, kKEmit, kKEmitBurst, kKIntegrate, kKFinalize, kKSort, kKGather, kKPack, kKExpandRuns,
-	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15, kKStreamFused = 6, kKSortSmall = 16,
-	kKBucketBase = 17 /* + 0 hist, 1 scans, 2 scatter, 3 finish, 4 splitters */ };
+	kKSortBase = 10 /* + 0 hist, 1 scan, 2 pass, 3 expand_sorted */, kKDeadAppend = 14, kKExpandStream = 15, kKStreamFused = 6, kKSortSmall = 16 };
 
 cudaEvent_t Context::timingBegin(int kernel)
 {
@@ -535,63 +523,6 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		numBigSegments = (uint32_t)segEffects.size();
 		segEffects.insert(segEffects.end(), small.begin(), small.end());
 	}
-	if (sortMode) {
-		for (size_t s = 0; s < segEffects.size(); s++) {
-			if (s == numBigSegments) numBigTiles = (uint32_t)sortTiles.size();
-			// tiles up to the effect's slot bound (ownedSlots: never below its real slot count), not up to its
-			// power-of-two capacity: C3's 10M slots are 2443 tiles of a 4096-tile range, and every empty CTA costs
-			// each of the seven sort kernels a scheduling slot
-			uint32_t tiles = (ownedSlots[segEffects[s]] + kSortTileKeys - 1) / kSortTileKeys;
-			for (uint32_t t = 0; t < tiles; t++) sortTiles.push_back({ (uint32_t)s, t });
-		}
-		if (numBigSegments == segEffects.size()) numBigTiles = (uint32_t)sortTiles.size();
-	}
-	// ---- depth buckets: a tile-path effect whose last sorted frame left depth quantiles on the device is partitioned by
-	// them (depth_buckets.cu); every tile-path effect of the frame leaves quantiles for its next one
-	std::vector<BucketSeg> nestedBktSegs; std::vector<BucketChunk> nestedBktChunks; std::vector<BucketJob> nestedBktJobs;
-	std::vector<BucketSeg> &bucketSegs = nested ? nestedBktSegs : scratchBucketSegs;
-	std::vector<BucketChunk> &bucketChunks = nested ? nestedBktChunks : scratchBucketChunks;
-	std::vector<BucketJob> &bucketJobs = nested ? nestedBktJobs : scratchBucketJobs;
-	bucketSegs.clear(); bucketChunks.clear(); bucketJobs.clear();
-	uint32_t bucketStride = 32;
-	bool anyBins = false, anyNextBins = false;
-	if (sortMode && depthBuckets && numBigSegments) {
-		uint32_t row = 0;
-		for (uint32_t s = 0; s < numBigSegments; s++) {
-			const uint32_t g = segEffects[s];
-			const uint32_t tiles = (ownedSlots[g] + kSortTileKeys - 1) / kSortTileKeys;
-			// an effect too large for kMaxBins buckets of a CTA's capacity stays on the radix path
-			const bool eligible = (uint64_t)ownedSlots[g] <= (uint64_t)kMaxBins * kBucketTarget * 3 / 2;
-			BucketSeg bs;
-			memset(&bs, 0, sizeof(bs));
-			bs.bins = eligible ? splitterBins[g] : 0;
-			uint32_t want = (ownedSlots[g] + kBucketTarget - 1) / kBucketTarget;
-			bs.nextBins = eligible ? (want < 2 ? 2 : want > kMaxBins ? kMaxBins : want) : 0;
-			if (eligible && splitterTable[g] == kNoOwner) {
-				splitterTable[g] = numSplitterTables++;
-				dSplitters.reserve((size_t)numSplitterTables * 2 * kMaxBins, (size_t)(numSplitterTables - 1) * 2 * kMaxBins, stream);
-				dSplitLut.reserve((size_t)numSplitterTables * 2 * (kLutCells + 2), (size_t)(numSplitterTables - 1) * 2 * (kLutCells + 2), stream);
-				dSplitLutMeta.reserve((size_t)numSplitterTables * 8, (size_t)(numSplitterTables - 1) * 8, stream);
-			}
-			bs.table = eligible ? splitterTable[g] : 0;
-			bs.parity = splitterParity[g];
-			bs.firstRow = row;
-			bs.firstChunk = (uint32_t)bucketChunks.size();
-			bs.numTiles = tiles;
-			bucketSegs.push_back(bs);
-			if (bs.bins) {
-				anyBins = true;
-				while (bucketStride < bs.bins) bucketStride *= 2;
-				for (uint32_t b = 0; b < bs.bins; b++) bucketJobs.push_back({ s, b });
-			}
-			for (uint32_t t = 0; t < tiles; t += kChunkTiles)
-				bucketChunks.push_back({ s, row + t, tiles - t < kChunkTiles ? tiles - t : kChunkTiles, (uint32_t)bucketChunks.size() });
-			row += tiles;
-			// this frame writes the other table of the pair (k_bucket_finish or k_bucket_splitters)
-			if (bs.nextBins) { anyNextBins = true; splitterBins[g] = bs.nextBins; splitterParity[g] ^= 1; }
-			else splitterBins[g] = 0;
-		}
-	}
 
 	// ---- staging blob
 	size_t bound = 256
@@ -605,8 +536,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	if (sortMode) {
 		for (uint32_t g : segEffects) bound += ((size_t)slotCapacityOf[g] / kSortTileKeys + 1) * sizeof(SortTile);
 	}
-	bound += bucketSegs.size() * sizeof(BucketSeg) + bucketChunks.size() * sizeof(BucketChunk) + bucketJobs.size() * sizeof(BucketJob);
-	bound += 20 * 16;
+	bound += 16 * 16;
 	int par = stagingParity; stagingParity ^= 1;
 	SPR_CUDA(cudaEventSynchronize(stagingEvent[par]));
 	stagingH[par].reserve(bound);
@@ -643,11 +573,19 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	size_t oEntries = bw.put(entries.data(), entries.size());
 	size_t oWork = bw.put(work.data(), work.size());
 	size_t oBurst = bw.put(burstJobs.data(), burstJobs.size());
+	if (sortMode) {
+		for (size_t s = 0; s < segEffects.size(); s++) {
+			if (s == numBigSegments) numBigTiles = (uint32_t)sortTiles.size();
+			// tiles up to the effect's slot bound (ownedSlots: never below its real slot count), not up to its
+			// power-of-two capacity: C3's 10M slots are 2443 tiles of a 4096-tile range, and every empty CTA costs
+			// each of the seven sort kernels a scheduling slot
+			uint32_t tiles = (ownedSlots[segEffects[s]] + kSortTileKeys - 1) / kSortTileKeys;
+			for (uint32_t t = 0; t < tiles; t++) sortTiles.push_back({ (uint32_t)s, t });
+		}
+		if (numBigSegments == segEffects.size()) numBigTiles = (uint32_t)sortTiles.size();
+	}
 	size_t oSeg = bw.put(segEffects.data(), segEffects.size());
 	size_t oTiles = bw.put(sortTiles.data(), sortTiles.size());
-	size_t oBktSegs = bw.put(bucketSegs.data(), bucketSegs.size());
-	size_t oBktChunks = bw.put(bucketChunks.data(), bucketChunks.size());
-	size_t oBktJobs = bw.put(bucketJobs.data(), bucketJobs.size());
 	if (bw.size > bound) throw std::runtime_error("staging blob overflow");
 
 	const uint32_t nParams = (uint32_t)dirtyParams.size(), nState = (uint32_t)initStateIdx.size();
@@ -690,36 +628,6 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		sortScratch.hist = dSortHist.ptr; sortScratch.lookback = dSortLookback.ptr;
 		clear_sort_scratch(stream, sortScratch, (uint32_t)segEffects.size(), (uint32_t)sortTiles.size());
 	}
-	BucketArgs bucketArgs;
-	memset(&bucketArgs, 0, sizeof(bucketArgs));
-	const bool useBuckets = sortMode && !bucketSegs.empty() && (anyBins || anyNextBins);
-	if (useBuckets) {
-		bucketArgs.anyBins = anyBins; bucketArgs.anyNextBins = anyNextBins;
-		bucketArgs.allBins = true;
-		for (const BucketSeg &bs : bucketSegs) if (!bs.bins) bucketArgs.allBins = false;
-		bucketArgs.stride = bucketStride;
-		bucketArgs.numChunks = (uint32_t)bucketChunks.size(); bucketArgs.numJobs = (uint32_t)bucketJobs.size();
-		bucketArgs.segs = (const BucketSeg*)(stagingD.ptr + oBktSegs);
-		bucketArgs.chunks = (const BucketChunk*)(stagingD.ptr + oBktChunks);
-		bucketArgs.jobs = (const BucketJob*)(stagingD.ptr + oBktJobs);
-		bucketArgs.splitters = dSplitters.ptr; bucketArgs.lut = dSplitLut.ptr; bucketArgs.lutMeta = dSplitLutMeta.ptr;
-		bucketArgs.binId = dBinId; bucketArgs.part = dPart;
-		dBktOk.reserve(segEffects.size(), 0, stream);
-		dBktStats.reserve(2, 0, stream);
-		bucketArgs.stats = dBktStats.ptr;
-		bucketArgs.bucketOk = dBktOk.ptr;
-		SPR_CUDA(cudaMemsetAsync(dBktOk.ptr, 0, segEffects.size() * sizeof(uint32_t), stream)); // start of the frame: no memset inside the kernel chain
-		if (anyBins) {
-			dBktTileCnt.reserve((size_t)numBigTiles * bucketStride, 0, stream);
-			dBktTileOff.reserve((size_t)numBigTiles * bucketStride, 0, stream);
-			dBktChunkOff.reserve(bucketChunks.size() * (size_t)bucketStride, 0, stream);
-			dBktBase.reserve((size_t)numBigSegments * bucketStride, 0, stream);
-			dBktCount.reserve((size_t)numBigSegments * bucketStride, 0, stream);
-			bucketArgs.tileCnt = dBktTileCnt.ptr; bucketArgs.tileOff = dBktTileOff.ptr; bucketArgs.chunkOff = dBktChunkOff.ptr;
-			bucketArgs.bucketBase = dBktBase.ptr; bucketArgs.bucketCount = dBktCount.ptr;
-		}
-		bucketArgs.camera[0] = camera[0]; bucketArgs.camera[1] = camera[1]; bucketArgs.camera[2] = camera[2];
-	}
 	TIMED(kKPlan, launch_plan(stream, tab, DPTR(SystemWork, oWork), (uint32_t)work.size(), dEntries, frameStamp));
 	// pool tiles up to the last owned granule, not up to the bump pointer: an effect's range is a power of two (C3: 10M
 	// slots own 9767 tiles of a 16384-tile range) and the tiles behind its slot bound would only be looked at and dropped
@@ -749,10 +657,10 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 
 	if (sortMode && !segEffects.empty()) {
 		const SortScratch &sc = sortScratch;
-		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(k >= 5 ? kKBucketBase + k - 5 : k == 4 ? kKSortSmall : kKSortBase + k); },
-			[](void *c, int k, void *b) { ((Context*)c)->timingEnd(k >= 5 ? kKBucketBase + k - 5 : k == 4 ? kKSortSmall : kKSortBase + k, (cudaEvent_t)b); } };
+		SortTimingHooks hooks = { this, [](void *c, int k) -> void* { return (void*)((Context*)c)->timingBegin(k == 4 ? kKSortSmall : kKSortBase + k); },
+			[](void *c, int k, void *b) { ((Context*)c)->timingEnd(k == 4 ? kKSortSmall : kKSortBase + k, (cudaEvent_t)b); } };
 		launchCount += launch_sort_and_expand(stream, pool, tab, sc, DPTR(uint32_t, oSeg), (uint32_t)segEffects.size(), numBigSegments,
-			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size(), numBigTiles, timingEnabled ? &hooks : nullptr, useBuckets ? &bucketArgs : nullptr);
+			DPTR(SortTile, oTiles), (uint32_t)sortTiles.size(), numBigTiles, timingEnabled ? &hooks : nullptr);
 	}
 #undef DPTR
 	if (hostTiming) {
@@ -763,31 +671,6 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		if (++frames % 16 == 0) { fprintf(stderr, "[spr host] per frame: effect pass %.0f us, work lists + staging %.0f us, launches %.0f us\n", acc[0] / 16, acc[1] / 16, acc[2] / 16); acc[0] = acc[1] = acc[2] = 0; }
 	}
 	SPR_CUDA(cudaGetLastError());
-}
-
-// The stream order of effect g as slot indices. The radix path and k_sort_small leave the sorted slots in vals[0]; the
-// depth-bucket path leaves, per stream rank, the record's ARRIVAL index in the partitioned records (bit 31 set). Arrival
-// order inside a bucket is ascending slot order, so the a-th arrival of bucket b is the a-th live slot whose bucket id is
-// b, and bucket b starts where the buckets before it end: the bucket ids and the alive ballots of the effect's last sorted
-// frame turn the indices back into slots.
-void Context::readSortedSlots(uint32_t g, uint32_t aliveCount, uint32_t slotCount, uint32_t *out, uint32_t m)
-{
-	const EffectParams &P = hParams[g];
-	std::vector<uint32_t> vals(aliveCount);
-	SPR_CUDA(cudaMemcpyAsync(vals.data(), dVals[0] + P.slotBase, (size_t)aliveCount * 4, cudaMemcpyDeviceToHost, stream));
-	SPR_CUDA(cudaStreamSynchronize(stream));
-	if (!aliveCount || !(vals[0] & 0x80000000u)) { memcpy(out, vals.data(), (size_t)m * 4); return; }
-	std::vector<uint16_t> ids(slotCount);
-	std::vector<uint32_t> alive((slotCount + 31) / 32);
-	SPR_CUDA(cudaMemcpyAsync(ids.data(), dBinId + P.slotBase, (size_t)slotCount * 2, cudaMemcpyDeviceToHost, stream));
-	SPR_CUDA(cudaMemcpyAsync(alive.data(), dAliveMask + P.slotBase / 32, alive.size() * 4, cudaMemcpyDeviceToHost, stream));
-	SPR_CUDA(cudaStreamSynchronize(stream));
-	std::vector<uint32_t> start(kMaxBins + 1, 0);
-	for (uint32_t i = 0; i < slotCount; i++) if ((alive[i >> 5] >> (i & 31)) & 1u) start[ids[i] + 1]++;
-	for (uint32_t b = 0; b < kMaxBins; b++) start[b + 1] += start[b];
-	std::vector<uint32_t> slotOfArrival(aliveCount);
-	for (uint32_t i = 0; i < slotCount; i++) if ((alive[i >> 5] >> (i & 31)) & 1u) slotOfArrival[start[ids[i]]++] = i;
-	for (uint32_t r = 0; r < m; r++) out[r] = slotOfArrival[vals[r] & 0x7fffffffu];
 }
 
 uint32_t *Context::gatherIndexBuffer(uint32_t n)

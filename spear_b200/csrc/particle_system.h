@@ -271,34 +271,14 @@ struct Context {
 	bool timingEnabled = false;
 	std::vector<TimedLaunch> timedLaunches;
 	std::vector<cudaEvent_t> eventPool;
-	static const int kNumKernelClasses = 22;
-	double kernelMs[kNumKernelClasses] = { 0 };
-	uint64_t kernelLaunches[kNumKernelClasses] = { 0 };
+	double kernelMs[17] = { 0 };
+	uint64_t kernelLaunches[17] = { 0 };
 	cudaEvent_t timingBegin(int kernel);
 	void timingEnd(int kernel, cudaEvent_t begin);
 	void resolveTimings();
 
 	// ---- sort scratch
 	DeviceArray<uint32_t> dSortHist, dSortLookback;
-	// ---- depth buckets (depth_buckets.cu): tile-path effects with depth quantiles from their last sorted frame
-	bool depthBuckets = true;              // SPR_DEPTH_BUCKETS=0: every tile-path effect through the radix passes (A/B)
-	uint16_t *dBinId = nullptr;            // per pool slot: bucket of the slot's particle in the effect's last sorted frame
-	float4 *dPart = nullptr;               // per pool slot: the records partitioned by bucket
-	DeviceArray<uint32_t> dSplitters;      // [numSplitterTables][2][kMaxBins]
-	DeviceArray<uint16_t> dSplitLut;       // [numSplitterTables][2][kLutCells + 2]
-	DeviceArray<uint32_t> dSplitLutMeta;   // [numSplitterTables][2][4]
-	uint32_t numSplitterTables = 0;
-	std::vector<uint32_t> splitterTable;   // per effect global: its pair of tables, kNoOwner while it never needed one
-	std::vector<uint32_t> splitterBins;    // per effect global: buckets of the table the device holds for the next sorted frame (0: none)
-	std::vector<uint8_t> splitterParity;   // per effect global: which of the two tables that is
-	DeviceArray<uint16_t> dBktTileCnt;
-	DeviceArray<uint32_t> dBktTileOff, dBktChunkOff, dBktBase, dBktCount, dBktOk;
-	DeviceArray<unsigned long long> dBktStats; // [2] verdicts so far: fits / fell back (sprContextGetDepthBucketStats)
-	std::vector<BucketSeg> scratchBucketSegs;
-	std::vector<BucketChunk> scratchBucketChunks;
-	std::vector<BucketJob> scratchBucketJobs;
-	// parity read-back: the stream order of an effect as slot indices (sprReadStreamSlots), whichever path sorted it
-	void readSortedSlots(uint32_t g, uint32_t aliveCount, uint32_t slotCount, uint32_t *out, uint32_t m);
 	unsigned long long *slotMirror = nullptr; // pinned + mapped, one word per effect: frame stamp << 32 | slot count (written by k_finalize)
 	size_t slotMirrorCapacity = 0;
 	void ensureSlotMirror(size_t numEffects);

@@ -39,15 +39,11 @@ static const uint32_t kLook = 8;                                      // status 
 static const size_t kPassSmemBytes = (2 * kSortTileKeys + kSortWarps * 256) * sizeof(uint32_t); // keys, values, per-warp digit counts
 static_assert(kSortThreads >= 256 && kSortThreads <= 1024 && kHistItems <= 32, "sort tile: 4096 to 16384 keys");
 
-// bucketOk (all kernels of the radix path): per segment, 1 when the depth-bucket path (depth_buckets.cu) has sorted and
-// expanded the effect this frame -- the radix path then leaves it alone. nullptr: no bucket path in this context.
-__global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t *hist,
-	const uint32_t *bucketOk)
+__global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t *hist)
 {
 	pdl_enter();
 	__shared__ uint32_t sHist[4 * 256];
 	SortTile st = tiles[blockIdx.x];
-	if (bucketOk && bucketOk[st.effect]) return;
 	uint32_t g = segEffects[st.effect];
 	const EffectState &S = tab.state[g];
 	uint32_t slots = S.slotCount[S.parity];
@@ -100,12 +96,11 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 // the step: same order, fewer significant bits), and the depths of one effect are floats from a narrow range
 // -- under 2^24 distinct values unless the effect spans more than about two octaves of squared distance --,
 // so the top digit is normally 0 everywhere and that pass would move every pair to where it already is.
-__global__ void k_sort_scan(TablePtrs tab, const uint32_t *segEffects, uint32_t *hist, uint32_t *passMask, uint32_t numRows, const uint32_t *bucketOk)
+__global__ void k_sort_scan(TablePtrs tab, const uint32_t *segEffects, uint32_t *hist, uint32_t *passMask, uint32_t numRows)
 {
 	pdl_enter();
 	uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (row >= numRows) return;
-	if (bucketOk && bucketOk[row >> 2]) return;
 	uint32_t *h = hist + (size_t)row * 256;
 	uint32_t v[8], sum = 0, big = 0;
 #pragma unroll
@@ -149,7 +144,7 @@ __device__ unsigned long long g_sortProf[16];
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	uint32_t *keys0, uint32_t *vals0, uint32_t *keys1, uint32_t *vals1,
-	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t *ticket, uint32_t pass, const uint32_t *bucketOk)
+	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t *ticket, uint32_t pass)
 {
 	pdl_enter();
 	extern __shared__ __align__(16) uint32_t sPassDyn[];
@@ -174,7 +169,6 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass
 	(void)ticket; (void)sTicket;
 #endif
 	const SortTile st = tiles[tileSlot];
-	if (bucketOk && bucketOk[st.effect]) return;
 	const uint32_t g = segEffects[st.effect];
 	const uint32_t runMask = passMask[st.effect] | 1u; // pass 0 always runs: its scatter is the compaction
 	if (!FIRST && !((runMask >> pass) & 1u)) return; // constant digit: nothing would move
@@ -571,12 +565,11 @@ __device__ inline void st_record_cs(float4 *p, const float4 &a, const float4 &b)
 }
 
 __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
-	const uint32_t *valsAlt, const uint32_t *passMask, const uint32_t *bucketOk)
+	const uint32_t *valsAlt, const uint32_t *passMask)
 {
 	pdl_enter();
 	// kExpandPerTile CTAs per sort tile: 1024 particles per CTA, 4 per thread, all gathers in flight at once
 	SortTile st = tiles[blockIdx.x / kExpandPerTile];
-	if (bucketOk && bucketOk[st.effect]) return;
 	uint32_t g = segEffects[st.effect];
 	uint32_t alive = tab.state[g].aliveCount;
 	uint32_t begin = st.tile * kSortTileKeys + (blockIdx.x % kExpandPerTile) * 1024u;
@@ -646,7 +639,7 @@ void clear_sort_scratch(cudaStream_t st, const SortScratch &sc, uint32_t numSegm
 
 uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SortScratch &sc,
 	const uint32_t *segEffects, uint32_t numSegments, uint32_t numBigSegments, const SortTile *tiles, uint32_t numTiles, uint32_t numBigTiles,
-	const SortTimingHooks *hooks, const BucketArgs *buckets)
+	const SortTimingHooks *hooks)
 {
 	if (!numSegments || !numTiles) return 0;
 	void *tok = nullptr;
@@ -655,28 +648,21 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 	uint32_t *passMask = sc.hist + (size_t)numSegments * 1024; // [numSegments], cleared together with the histograms (clear_sort_scratch)
 	uint32_t *tickets = passMask + numSegments;                 // [4] one tile ticket per pass, cleared with them
 	uint32_t launches = 0;
-	// effects with depth quantiles from their last frame go through the depth buckets first; the radix path below then
-	// only works on the segments whose verdict (bucketOk) is no
-	const uint32_t *bucketOk = buckets && buckets->anyBins ? buckets->bucketOk : nullptr;
-	if (buckets) launches += launch_depth_buckets(st, pool, tab, *buckets, segEffects, numBigSegments, tiles, numBigTiles, hooks);
-	// EXPERIMENT (unsafe, timing only): no radix launches behind the depth buckets
-	static const bool noFallback = getenv("SPR_BUCKET_NO_FALLBACK") != nullptr;
-	const bool skipRadix = noFallback && buckets && buckets->anyBins && buckets->allBins;
-	if (numBigSegments && numBigTiles && !skipRadix) {
+	if (numBigSegments && numBigTiles) {
 		T_BEGIN(0);
-		launch_chain(k_sort_hist, numBigTiles, 256, 0, st, pool, tab, segEffects, tiles, sc.hist, bucketOk);
+		launch_chain(k_sort_hist, numBigTiles, 256, 0, st, pool, tab, segEffects, tiles, sc.hist);
 		T_END(0);
 		uint32_t rows = numBigSegments * 4;
 		T_BEGIN(1);
-		launch_chain(k_sort_scan, (rows * 32 + 255) / 256, 256, 0, st, tab, segEffects, sc.hist, passMask, rows, bucketOk);
+		launch_chain(k_sort_scan, (rows * 32 + 255) / 256, 256, 0, st, tab, segEffects, sc.hist, passMask, rows);
 		T_END(1);
 		uint32_t *kbuf[2] = { pool.keys, sc.keysAlt };
 		uint32_t *vbuf[2] = { pool.vals, sc.valsAlt };
 		for (uint32_t p = 0; p < 4; p++) {
 			T_BEGIN(2);
 			uint32_t *lb = sc.lookback + (size_t)p * numBigTiles * 256;
-			if (p == 0) launch_chain(k_sort_pass<true>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, tickets + p, p, bucketOk);
-			else launch_chain(k_sort_pass<false>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, tickets + p, p, bucketOk);
+			if (p == 0) launch_chain(k_sort_pass<true>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, tickets + p, p);
+			else launch_chain(k_sort_pass<false>, numBigTiles, kSortThreads, kPassSmemBytes, st, pool, tab, segEffects, tiles, kbuf[0], vbuf[0], kbuf[1], vbuf[1], sc.hist, passMask, lb, tickets + p, p);
 			T_END(2);
 		}
 		launches += 6;
@@ -688,14 +674,10 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 		T_END(4);
 		launches++;
 	}
-	if (!(skipRadix && numSegments == numBigSegments)) {
 	T_BEGIN(3);
-	launch_chain(k_expand_sorted, numTiles * kExpandPerTile, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask, bucketOk);
+	launch_chain(k_expand_sorted, numTiles * kExpandPerTile, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
 	T_END(3);
-	launches++;
-	}
-	if (buckets) launches += launch_bucket_splitters(st, pool, tab, *buckets, segEffects, numBigSegments, hooks);
-	return launches;
+	return launches + 1;
 }
 
 } // namespace spr

@@ -33,7 +33,7 @@ EXPORTS = [
     "sprBillboardSystemCreate", "sprBillboardSystemDestroy", "sprBillboardAdd", "sprBillboardRenderMain",
     "sprBillboardReadVertices",
     "sprDescriptorsFromJson", "sprDescriptorCount", "sprDescriptorGet", "sprDescriptorTextureName", "sprDescriptorsFree",
-    "sprQueryEffects", "sprContextGetDepthBucketStats",
+    "sprQueryEffects",
 ]
 
 
@@ -105,7 +105,6 @@ def _load():
     lib.sprQueryEffects.argtypes = [vp, P(abi.Frustum), P(u32), u32, P(u32)]
     lib.sprContextEnableKernelTiming.argtypes = [vp, C.c_int]
     lib.sprContextGetKernelTimes.argtypes = [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64), u32, P(u32)]
-    lib.sprContextGetDepthBucketStats.argtypes = [vp, P(u64)]
     return lib
 
 
@@ -182,12 +181,6 @@ class ParticleContext:
 
     def enable_kernel_timing(self, enable=True):
         _check(lib.sprContextEnableKernelTiming(self.h, 1 if enable else 0))
-
-    def depth_bucket_stats(self):
-        """(per-effect depth sorts through the depth buckets, sorts that fell back to the radix passes)"""
-        out = (C.c_uint64 * 2)()
-        _check(lib.sprContextGetDepthBucketStats(self.h, out))
-        return int(out[0]), int(out[1])
 
     def kernel_times(self, reset=True):
         """{kernel name: (total ms, launches)} measured with CUDA events on the context stream."""
