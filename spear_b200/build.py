@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspear_particles.so")
 SOURCES = ["kernels.cu", "sort.cu", "vertex_stage.cu", "billboards.cu", "particle_system.cpp", "descriptor_json.cpp", "c_api.cpp"]
-HEADERS = ["launch.h", "device_types.h", "kernels.h", "host_math.h", "particle_system.h", os.path.join("..", "..", "include", "spear_particles.h")]
+HEADERS = ["launch.h", "host_pool.h", "device_types.h", "kernels.h", "host_math.h", "particle_system.h", os.path.join("..", "..", "include", "spear_particles.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

@@ -325,29 +325,66 @@ void Context::validateRequests(const UpdateRequest *reqs, uint32_t numReqs)
 		updateMark = 1;
 	}
 	const uint32_t mark = updateMark;
+	size_t totalActive = 0;
 	for (uint32_t r = 0; r < numReqs; r++) {
 		ParticleSystem *sys = reqs[r].system;
 		if (sys->systemMark == mark) throw Unsupported("a system is listed twice in one batched update (its effects share one RNG stream: merge the lists)");
 		sys->systemMark = mark;
 		if (reqs[r].numActive && !reqs[r].activeIds) throw std::invalid_argument("active id list is NULL");
-		uint32_t *marks = sys->activeMark.data();
-		const size_t n = sys->activeMark.size();
-		for (uint32_t i = 0; i < reqs[r].numActive; i++) {
-			const uint32_t id = reqs[r].activeIds[i];
-			if (id >= n || marks[id] == ParticleSystem::kMarkFree) throw std::invalid_argument("active list names an effect id that is not in use");
-			if (marks[id] == mark) throw Unsupported("an effect id is listed twice in one active list (the reference would simulate it twice, ParticleSystem.cpp:812-821; not supported)");
-			marks[id] = mark;
-		}
+		totalActive += reqs[r].numActive;
 	}
+	// the id marks belong to one system each: a large frame checks its lists on several host threads
+	auto checkIds = [&](uint32_t r0, uint32_t r1) {
+		for (uint32_t r = r0; r < r1; r++) {
+			ParticleSystem *sys = reqs[r].system;
+			uint32_t *marks = sys->activeMark.data();
+			const size_t n = sys->activeMark.size();
+			for (uint32_t i = 0; i < reqs[r].numActive; i++) {
+				const uint32_t id = reqs[r].activeIds[i];
+				if (id >= n || marks[id] == ParticleSystem::kMarkFree) throw std::invalid_argument("active list names an effect id that is not in use");
+				if (marks[id] == mark) throw Unsupported("an effect id is listed twice in one active list (the reference would simulate it twice, ParticleSystem.cpp:812-821; not supported)");
+				marks[id] = mark;
+			}
+		}
+	};
+	const uint32_t nt = hostPassThreads(totalActive, numReqs);
+	if (nt <= 1) { checkIds(0, numReqs); return; }
+	std::vector<uint32_t> cut = splitRequests(reqs, numReqs, nt);
+	hostPool.run(nt, [&](uint32_t t) { checkIds(cut[t], cut[t + 1]); });
+}
+
+// Host threads for a per-effect pass over `totalActive` listed effects in `numReqs` systems (1 = the calling thread).
+uint32_t Context::hostPassThreads(size_t totalActive, uint32_t numReqs) const
+{
+	if (totalActive < 16384 || numReqs < 16) return 1;
+	const uint32_t most = HostPool::maxThreads() < 4 ? HostPool::maxThreads() : 4; // the pass streams ~60 bytes per effect: four cores are at memory speed
+	return most < numReqs ? most : numReqs;
+}
+
+// Cuts the request list into nt contiguous ranges of about the same number of listed effects.
+std::vector<uint32_t> Context::splitRequests(const UpdateRequest *reqs, uint32_t numReqs, uint32_t nt)
+{
+	size_t total = 0;
+	for (uint32_t r = 0; r < numReqs; r++) total += reqs[r].numActive;
+	std::vector<uint32_t> cut(nt + 1, numReqs);
+	cut[0] = 0;
+	size_t run = 0;
+	uint32_t t = 1;
+	for (uint32_t r = 0; r < numReqs && t < nt; r++) {
+		run += reqs[r].numActive;
+		while (t < nt && run >= total * t / nt) cut[t++] = r + 1;
+	}
+	return cut;
 }
 
 void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 {
 	SPR_CUDA(cudaSetDevice(device));
-	validateRequests(reqs, numReqs);
-	const bool sortMode = (flags & SPR_CTX_SORT_PARTICLES) != 0;
 	static const bool hostTiming = getenv("SPR_HOST_TIMING") != nullptr; // debug aid: where a frame's host time goes
 	auto tNow = [] { return std::chrono::steady_clock::now(); };
+	auto tv = tNow();
+	validateRequests(reqs, numReqs);
+	const bool sortMode = (flags & SPR_CTX_SORT_PARTICLES) != 0;
 	auto t0 = tNow();
 
 	// ---- host pass: sub-step counts (ParticleSystem.cpp:810-820) and capacity bounds
@@ -424,9 +461,18 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	// (phase 1 on several host threads, by contiguous request ranges, was measured on the 100k-effect C5 frame: 0.90 ->
 	// 0.75 ms with 4 threads, no gain in the step once the threads' start-up is paid -- the pass streams the effect
 	// mirror through one core at memory speed, so the mirror was split into a 48-byte hot half instead)
-	std::vector<Part> parts(1);
-	phase1(0, numReqs, parts[0]);
+	// Since the persistent workers of Context::hostPool the threads' start-up is no longer paid per frame: a frame of
+	// >= 16384 listed effects runs this pass on up to four of them, by contiguous request ranges (phase 2 below walks the
+	// parts in order, so everything that touches the context still happens in request order on the calling thread).
+	const uint32_t passThreads = nested ? 1u : hostPassThreads(totalActive, numReqs);
+	std::vector<Part> parts(passThreads);
+	if (passThreads <= 1) phase1(0, numReqs, parts[0]);
+	else {
+		const std::vector<uint32_t> cut = splitRequests(reqs, numReqs, passThreads);
+		hostPool.run(passThreads, [&](uint32_t t) { phase1(cut[t], cut[t + 1], parts[t]); });
+	}
 
+	auto tp1 = tNow();
 	// Phase 2: everything that touches the context (ranges, granule ownership, the slot mirror, burst jobs), in request order
 	for (Part &part : parts) {
 		totalSimSteps += part.simSteps;
@@ -666,9 +712,13 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	if (hostTiming) {
 		auto t3 = tNow();
 		auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() * 1e-3; };
-		static double acc[3]; static int frames;
-		acc[0] += us(t0, t1); acc[1] += us(t1, t2); acc[2] += us(t2, t3);
-		if (++frames % 16 == 0) { fprintf(stderr, "[spr host] per frame: effect pass %.0f us, work lists + staging %.0f us, launches %.0f us\n", acc[0] / 16, acc[1] / 16, acc[2] / 16); acc[0] = acc[1] = acc[2] = 0; }
+		static double acc[5]; static int frames;
+		acc[0] += us(t0, t1); acc[1] += us(t1, t2); acc[2] += us(t2, t3); acc[3] += us(tv, t0); acc[4] += us(t0, tp1);
+		if (++frames % 16 == 0) {
+			fprintf(stderr, "[spr host] per frame: id check %.0f us, effect pass %.0f us (phase 1: %.0f us), work lists + staging %.0f us, launches %.0f us\n",
+				acc[3] / 16, acc[0] / 16, acc[4] / 16, acc[1] / 16, acc[2] / 16);
+			for (double &a : acc) a = 0;
+		}
 	}
 	SPR_CUDA(cudaGetLastError());
 }
@@ -993,11 +1043,7 @@ void Context::renderBatch(ParticleSystem *const *systems, uint32_t numSystems, c
 	// The per-system passes (effect sort, draw records) touch nothing but their own system: a frame with tens of
 	// thousands of visible effects in many systems (C5: 100k effects, 20 MB of draw records) is split over a few host
 	// threads, 16 systems at a time. SPR_RENDER_THREADS=1 keeps everything on the calling thread.
-	static const uint32_t maxThreads = [] {
-		if (const char *e = getenv("SPR_RENDER_THREADS")) { int v = atoi(e); return (uint32_t)(v < 1 ? 1 : v > 64 ? 64 : v); }
-		unsigned hw = std::thread::hardware_concurrency();
-		return hw >= 16 ? 8u : hw >= 8 ? 4u : 1u;
-	}();
+	const uint32_t maxThreads = HostPool::maxThreads();
 	const uint32_t kChunk = 16;
 	uint32_t nt = (total >= 32768 && numSystems >= 4 * kChunk) ? maxThreads : 1;
 	if (nt > (numSystems + kChunk - 1) / kChunk) nt = (numSystems + kChunk - 1) / kChunk;
@@ -1021,30 +1067,17 @@ void Context::renderBatch(ParticleSystem *const *systems, uint32_t numSystems, c
 	std::vector<size_t> offs(numSystems);
 	{ size_t off = 0; for (uint32_t s = 0; s < numSystems; s++) { offs[s] = off; off += numVisible[s]; } }
 	std::atomic<uint32_t> next(0);
-	std::exception_ptr failure;
-	std::mutex failureLock;
-	auto worker = [&] {
-		try {
-			for (;;) {
-				const uint32_t s0 = next.fetch_add(kChunk);
-				if (s0 >= numSystems) break;
-				const uint32_t s1 = s0 + kChunk < numSystems ? s0 + kChunk : numSystems;
-				for (uint32_t s = s0; s < s1; s++) {
-					const SprRenderArgs &a = *(const SprRenderArgs*)((const char*)args + argsStride * s);
-					systems[s]->renderMainWith(visibleIds[s], numVisible[s], a, got + offs[s], outs[s]);
-				}
+	hostPool.run(nt, [&](uint32_t) {
+		for (;;) {
+			const uint32_t s0 = next.fetch_add(kChunk);
+			if (s0 >= numSystems) break;
+			const uint32_t s1 = s0 + kChunk < numSystems ? s0 + kChunk : numSystems;
+			for (uint32_t s = s0; s < s1; s++) {
+				const SprRenderArgs &a = *(const SprRenderArgs*)((const char*)args + argsStride * s);
+				systems[s]->renderMainWith(visibleIds[s], numVisible[s], a, got + offs[s], outs[s]);
 			}
-		} catch (...) {
-			std::lock_guard<std::mutex> lock(failureLock);
-			if (!failure) failure = std::current_exception();
 		}
-	};
-	std::vector<std::thread> helpers;
-	helpers.reserve(nt - 1);
-	for (uint32_t t = 1; t < nt; t++) helpers.emplace_back(worker);
-	worker();
-	for (std::thread &t : helpers) t.join();
-	if (failure) std::rethrow_exception(failure);
+	});
 }
 
 void ParticleSystem::renderMainWith(const uint32_t *visibleIds, uint32_t numVisible, const SprRenderArgs &args, const RenderGather *got, SprRenderOutput &out)
@@ -1220,25 +1253,14 @@ void BillboardSystem::add(const SprBillboard *billboards, uint32_t count)
 	// A large call (the 1M-billboard frame: 220 MB through the host) is converted by a few threads: each counts the
 	// loaded sprites of its range, the counts give every range its place in the staging array, then the ranges are
 	// converted side by side -- the order of the billboards is the order of the call either way.
-	static const uint32_t maxThreads = [] {
-		if (const char *e = getenv("SPR_RENDER_THREADS")) { int v = atoi(e); return (uint32_t)(v < 1 ? 1 : v > 64 ? 64 : v); }
-		unsigned hw = std::thread::hardware_concurrency();
-		return hw >= 16 ? 8u : hw >= 8 ? 4u : 1u;
-	}();
-	const uint32_t nt = count >= 65536 ? maxThreads : 1;
+	const uint32_t nt = count >= 65536 ? HostPool::maxThreads() : 1;
 	if (nt <= 1) {
 		pendingCount = (size_t)(convert(0, count, pending + pendingCount) - pending);
 		return;
 	}
 	std::vector<uint32_t> cut(nt + 1), valid(nt, 0);
 	for (uint32_t t = 0; t <= nt; t++) cut[t] = (uint32_t)((uint64_t)count * t / nt);
-	auto run = [&](auto &&fn) {
-		std::vector<std::thread> helpers;
-		helpers.reserve(nt - 1);
-		for (uint32_t t = 1; t < nt; t++) helpers.emplace_back(fn, t);
-		fn(0u);
-		for (std::thread &th : helpers) th.join();
-	};
+	auto run = [&](auto &&fn) { ctx->hostPool.run(nt, fn); };
 	run([&](uint32_t t) { uint32_t v = 0; for (uint32_t i = cut[t]; i < cut[t + 1]; i++) v += billboards[i].sprite.atlas != 0; valid[t] = v; });
 	std::vector<size_t> first(nt + 1, pendingCount);
 	for (uint32_t t = 0; t < nt; t++) first[t + 1] = first[t] + valid[t];

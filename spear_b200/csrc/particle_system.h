@@ -20,6 +20,7 @@
 #include "../../include/spear_particles.h"
 #include "device_types.h"
 #include "host_math.h"
+#include "host_pool.h"
 #include "kernels.h"
 
 namespace spr {
@@ -246,6 +247,9 @@ struct Context {
 	uint32_t updateMark = 0;               // numbers the update calls (ParticleSystem::activeMark / systemMark)
 	std::vector<ParticleSystem*> systemsAlive; // every system of the context (marks are wiped when updateMark wraps)
 	void validateRequests(const UpdateRequest *reqs, uint32_t numReqs);
+	HostPool hostPool;                     // persistent workers for the large per-system / per-effect host passes
+	uint32_t hostPassThreads(size_t totalActive, uint32_t numReqs) const;
+	static std::vector<uint32_t> splitRequests(const UpdateRequest *reqs, uint32_t numReqs, uint32_t nt);
 	uint64_t renderBatchStamp = 0;     // numbers the threaded render batches (a system named twice keeps the batch on one thread)
 	// ---- per-frame staging
 	PinnedArray<uint8_t> stagingH[2];
