@@ -90,6 +90,36 @@ def test_sorted_large_effect(oracle_port):
         ctx.close()
 
 
+def test_sorted_with_a_moving_camera(oracle_port):
+    """The depth keys follow the camera of every frame: a camera that drifts, sits inside the cloud, is far away (the
+    keys' top digits become constant: pass skipping) and jumps between frames, over a tile-path effect (70k slots), a
+    one-CTA effect (6000) and a one-granule effect (40) of one system. Every frame's stream is the stable depth sort of
+    the oracle's stream under THAT frame's camera."""
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 16)
+    try:
+        seed = (9, 8, 7, 6)
+        effects = [(comp_big(70_000), abi.make_transform((1, 2, 3))), (comp_big(6_000), abi.make_transform((-4, 1, 2))),
+                   (S.comp_c5(), abi.make_transform((2, 0, -1)))]
+        o = orc.OracleSystem(oracle_port, seed)
+        s = ctx.create_system(seed)
+        ids = [s.add_effect(c, t) for c, t in effects]
+        assert ids == [o.add_effect(c, t) for c, t in effects]
+        cameras = [(16.0, 20.0, -30.0), (15.5, 19.0, -29.0), (1.0, 2.0, 3.0), (1.5, 2.5, 2.0), (4000.0, 3000.0, -9000.0),
+                   (-60.0, 5.0, 12.0), (16.0, 20.0, -30.0), (0.0, 0.0, 0.0), (1e6, 1e6, 1e6), (2.0, 3.0, 4.0)]
+        dt = 1 / 60
+        for f, cam in enumerate(cameras):
+            fa = abi.make_frame_args(dt, game_time=f * dt, frame_index=f, camera=cam)
+            s.update(ids, fa); o.update(ids, fa)
+            a, b = S.snapshot(o, ids), S.snapshot(s, ids)
+            for e in ids:
+                assert a[e]["info"] == b[e]["info"], "frame %d effect %d" % (f, e)
+                exp, order = expected_sorted(a[e]["stream"], cam)
+                assert exp.tobytes() == b[e]["stream"].tobytes(), "frame %d effect %d sorted stream under camera %r" % (f, e, cam)
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("sort", [False, True], ids=["stream", "sorted"])
 def test_effects_above_4gb_of_vertex_stream(oracle_port, sort):
     """Maximum sizes: an idle 40M-particle effect is registered first, so every effect of the scenario lives
