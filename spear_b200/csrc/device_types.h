@@ -72,6 +72,8 @@ struct TypeDev {
 	uint32_t burstAmount;
 	uint32_t drawsPerSpawn;           // K: RNG draws of one timer spawn; a burst spawn uses K-1
 	uint64_t mulKm1, sumKm1;          // LCG jump by K-1 draws: s' = s*mulKm1 + inc*sumKm1
+	uint64_t mulJK[kMaxTimerSpawns + 1], sumJK[kMaxTimerSpawns + 1]; // LCG jump by j*K draws, j = 0..20: the state in front of
+	                                  // the j-th timer spawn of a sub-step (k_plan evaluates the <= 20 timer draws side by side)
 	float drag, lifeTime, lifeTimeVariance /* pre-scaled by 2^-24, :535 */, cullPadding;
 	uint32_t numGravityPoints;
 	uint32_t localSpace;

@@ -251,12 +251,73 @@ __global__ void __launch_bounds__(128) k_plan(TablePtrs tab, const SystemWork *w
 			}
 			if (!draws) run_effect();
 		}
+		// The effects that draw take turns, in list order, but the whole WARP runs each turn: all lanes hold the turn's
+		// effect (broadcast), lane j evaluates the j-th timer draw of the sub-step from the state jumped ahead by j * K
+		// draws (TypeDev::mulJK), and only the <= 20 float additions that decide how many of them happen stay sequential --
+		// instead of one lane walking 20 dependent 64-bit multiply-adds per sub-step while 31 wait (C5: 100 effects x 20
+		// spawns per system and frame).
 		uint32_t turn = __ballot_sync(FULL_MASK, draws);
+		const uint32_t myTypeIdx = have ? tab.params[ae.effect].typeIdx : 0u;
 		while (turn) {
 			const uint32_t k = __ffs(turn) - 1;
 			turn &= turn - 1;
-			if (lane == k) run_effect();
-			rng.state = __shfl_sync(FULL_MASK, rng.state, k);
+			// the turn's effect, in every lane
+			const uint32_t tEffect = __shfl_sync(FULL_MASK, ae.effect, k), tSub = __shfl_sync(FULL_MASK, ae.numSubsteps, k), tPlan = __shfl_sync(FULL_MASK, ae.planBase, k);
+			float tSpawnTimer = __shfl_sync(FULL_MASK, spawnTimer, k), tEmitOn = __shfl_sync(FULL_MASK, emitOnTimer, k);
+			uint32_t tStopEmit = __shfl_sync(FULL_MASK, stopEmit, k), tFirst = __shfl_sync(FULL_MASK, firstEmit, k), tParity = __shfl_sync(FULL_MASK, parity, k);
+			const uint32_t tHostStop = __shfl_sync(FULL_MASK, hostStop, k), tK = __shfl_sync(FULL_MASK, K, k), tBurstAmount = __shfl_sync(FULL_MASK, burstAmount, k);
+			const float tDt = __shfl_sync(FULL_MASK, dt, k), tSpawnTime = __shfl_sync(FULL_MASK, spawnTime, k), tSpawnVar = __shfl_sync(FULL_MASK, spawnVar, k);
+			const TypeDev &TT = tab.types[__shfl_sync(FULL_MASK, myTypeIdx, k)];
+			const uint32_t jl = lane <= kMaxTimerSpawns ? lane : kMaxTimerSpawns;
+			const uint64_t mulJ = TT.mulJK[jl], sumJ = TT.sumJK[jl];
+			for (uint32_t s = 0; s < tSub; s++) {
+				PlanRec &rec = tab.plans[tPlan + s];
+				uint32_t burst = 0, usePrev = (s == 0) ? 1u : 0u;
+				if (tFirst) { burst = tBurstAmount; tFirst = 0; usePrev = 0; }          // :457-464
+				if (tEmitOn >= 0.0f) {                                                  // :466-471
+					tEmitOn -= tDt;
+					if (tEmitOn < 0.0f) tStopEmit = 1;
+				}
+				const bool stop = tStopEmit || tHostStop;
+				tSpawnTimer -= tDt;                                                      // :477
+				if (lane == 0) {
+					rec.rngState = rng.state;
+					rec.effect = tEffect;
+					rec.burst = burst;
+					rec.dt = tDt;
+					rec.spawnTimer0 = tSpawnTimer;
+					rec.flags = usePrev | ((tParity & 1u) << 1);
+				}
+				if (burst) rng.advance((uint64_t)burst * (tK - 1));                      // burst spawns draw first (:480-481)
+				// lane j: the draw of the j-th timer spawn, were it to happen (:484): state jumped by j * K draws
+				const float myInc = tSpawnTime + tSpawnVar * (__uint2float_rn(pcg_output(rng.state * mulJ + rng.inc * sumJ)) * 2.3283064365386963e-10f);
+				uint32_t timer = 0;
+				if (tSpawnTimer <= 0.0f && !stop) {
+					float inc[kMaxTimerSpawns];
+#pragma unroll
+					for (uint32_t j = 0; j < kMaxTimerSpawns; j++) inc[j] = __shfl_sync(FULL_MASK, myInc, j);
+					// :479-485, at most 20 spawns: spawn j happens while the timer is <= 0. The chain of additions runs
+					// unconditionally (the values behind the last spawn are simply not used), so that only the 20 float
+					// additions depend on one another, not 20 x (compare -> add).
+					float mine = 0.0f, t = tSpawnTimer;
+					bool going = true;
+#pragma unroll
+					for (uint32_t j = 0; j < kMaxTimerSpawns; j++) {
+						going = going && t <= 0.0f;
+						t += inc[j];
+						if (going) { tSpawnTimer = t; timer = j + 1; }
+						if (lane == j) mine = t;
+					}
+					if (lane < timer) rec.timerVals[lane] = mine;
+					// the state behind `timer` spawns of K draws each
+					const uint64_t mulN = __shfl_sync(FULL_MASK, mulJ, timer), sumN = __shfl_sync(FULL_MASK, sumJ, timer);
+					rng.state = rng.state * mulN + rng.inc * sumN;
+				}
+				if (lane == 0) rec.timer = timer;
+				tSpawnTimer = sf_max(tSpawnTimer, 0.0f);                                 // :524
+				tParity ^= 1u;
+			}
+			if (lane == k) { spawnTimer = tSpawnTimer; emitOnTimer = tEmitOn; stopEmit = tStopEmit; firstEmit = tFirst; parity = tParity; }
 		}
 		if (have && ae.numSubsteps) {
 			EffectState &S = tab.state[ae.effect];
@@ -662,6 +723,8 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 #pragma unroll
 		for (int r = 0; r < 4; r++) {
 			if (am[r] >> lane & 1u) {
+				// (writing these through a per-warp staging buffer in transposed order, as k_expand_sorted does, was measured
+				// on C5's 100k one-granule effects: no change -- this path is bound by its per-warp latency chain, not by the LSU)
 				float4 *d = pool.vertices + 8ull * (slotBase + rank[r]);
 				st_record(d, a[r], b[r]); st_record(d + 2, a[r], b[r]); st_record(d + 4, a[r], b[r]); st_record(d + 6, a[r], b[r]);
 				if (KEYS) pool.vals[slotBase + rank[r]] = r * 32 + lane;

@@ -823,6 +823,7 @@ uint32_t ParticleSystem::reserveEffectType(const SprParticleSystemComponent *c)
 		// draws of one timer spawn: timer + position + velocity + seed (:484, :498-499, :522)
 		td.drawsPerSpawn = 1 + drawsOfSampler(td.emitPosition) + drawsOfSampler(td.emitVelocity) + 1;
 		lcgJump(td.drawsPerSpawn - 1, td.mulKm1, td.sumKm1);
+		for (uint32_t j = 0; j <= kMaxTimerSpawns; j++) lcgJump((uint64_t)j * td.drawsPerSpawn, td.mulJK[j], td.sumJK[j]);
 		td.drag = c->drag;
 		td.lifeTime = c->lifeTime;
 		td.lifeTimeVariance = c->lifeTimeVariance * (1.0f / 16777216.0f);   // :535
