@@ -387,8 +387,8 @@ SPR_API int sprUpdateParticles(SprSystem *sys, const uint32_t *activeIds, uint32
  * Equivalent to calling sprUpdateParticles(systems[i], activeIds[i], numActive[i], &args[i])
  * for i = 0..numSystems-1. If args is shared, pass argsStride = 0.
  * A system listed twice is refused (SPR_ERR_UNSUPPORTED: its effects share one RNG stream, merge the lists); ids are
- * checked as in sprUpdateParticles. With SPR_CTX_SORT_PARTICLES the depth keys of the whole batch are taken from ONE
- * camera, args[numSystems-1].cameraPosition (a batch is one view); dt and gameTime are per system. */
+ * checked as in sprUpdateParticles. dt, gameTime and -- with SPR_CTX_SORT_PARTICLES -- the camera of the depth keys are
+ * per system: every system is sorted towards its own args[i].cameraPosition. */
 SPR_API int sprUpdateParticlesBatch(SprContext *ctx, SprSystem *const *systems, uint32_t numSystems,
 	const uint32_t *const *activeIds, const uint32_t *numActive,
 	const SprFrameArgs *args, size_t argsStride);

@@ -143,6 +143,8 @@ struct SystemWork {
 	uint32_t firstActive;   // index into the frame's active arrays
 	uint32_t numActive;
 	uint32_t _pad;
+	float camera[3];        // sort mode: the request's FrameArgs::mainRenderArgs.cameraPosition (depth keys of this system's particles)
+	uint32_t _pad2;
 };
 
 // One active effect of the frame (host computed: sub-step count from timeDelta, :816-820).
@@ -150,7 +152,8 @@ struct ActiveEntry {
 	uint32_t effect;        // context-wide effect index
 	uint32_t numSubsteps;
 	uint32_t planBase;      // first PlanRec of this effect in the frame
-	uint32_t flags;         // bit0: burst handled by the wide burst kernel; bit1: the host wants the exact slot count mirrored (its capacity bound is not final)
+	uint32_t flags;         // bit0: burst handled by the wide burst kernel; bit1: the host wants the exact slot count mirrored (its capacity bound is not final);
+	                        // [31:2]: index of the effect's system in the frame's SystemWork list
 };
 
 // Spawn plan of one simulateParticlesImp call (one effect, one sub-step), written by
@@ -179,7 +182,10 @@ struct __align__(16) RoundConsts {
 	float dt, drag, lifeTime, lifeVar;
 	float gx, gy, gz;
 	uint32_t _pad;
+	float camX, camY, camZ; // sort mode: the camera of the effect's system in this frame (depth keys)
+	uint32_t _pad2;
 };
+static_assert(sizeof(RoundConsts) == 80, "RoundConsts is read as five 16-byte words");
 
 // A job of the wide burst-emission kernel: `count` burst spawns of active entry `entry`
 // starting at CTA `firstBlock`.

@@ -443,7 +443,7 @@ __device__ inline void emit_init_leftover(const EmitCtx &c, const PoolPtrs &pool
 
 // One warp per active effect: all timer spawns, and the burst unless it is flagged for
 // the wide kernel. Also resets the per-step bounds and handles the empty-effect corner.
-__global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
+__global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab, const SystemWork *work, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
 {
 	pdl_enter();
 	uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -485,6 +485,9 @@ __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab,
 		rc.dt = rec->dt; rc.drag = c.T->drag; rc.lifeTime = c.T->lifeTime; rc.lifeVar = c.T->lifeTimeVariance;
 		rc.gx = c.P->gravity[0]; rc.gy = c.P->gravity[1]; rc.gz = c.P->gravity[2];
 		rc._pad = 0;
+		const SystemWork &sw = work[ae.flags >> 2];
+		rc.camX = sw.camera[0]; rc.camY = sw.camera[1]; rc.camZ = sw.camera[2];
+		rc._pad2 = 0;
 		tab.roundConsts[rec->effect] = rc;
 		tab.effectAnyDead[rec->effect] = 0;
 	}
@@ -625,8 +628,7 @@ __device__ __forceinline__ void step_consts_from(StepConsts &c, const RoundConst
 // dense by construction, i.e. it IS the compaction) or k_expand_stream (slot-order stream).
 // Effects that fit one granule (TINY) are finished right here, inside the warp.
 template <bool GP, bool TINY, bool KEYS>
-__global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round,
-	float camX, float camY, float camZ)
+__global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(PoolPtrs pool, TablePtrs tab, uint32_t stamp, uint32_t round)
 {
 	pdl_enter();
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -678,7 +680,7 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 			mnx = min(mnx, ex); mny = min(mny, ey); mnz = min(mnz, ez);
 			mxx = max(mxx, ex); mxy = max(mxy, ey); mxz = max(mxz, ez);
 			if (KEYS) {
-				key[r] = depth_key(ra.x, ra.y, ra.z, camX, camY, camZ); // sf::lengthSq (src/sf/Vector.h:99), descending
+				key[r] = depth_key(ra.x, ra.y, ra.z, rc.camX, rc.camY, rc.camZ); // sf::lengthSq (src/sf/Vector.h:99), descending
 				keyMin = min(keyMin, key[r]);
 				if (!tiny) pool.keys[keyIdx + r * 32] = key[r];
 			}
@@ -1488,10 +1490,10 @@ void launch_plan(cudaStream_t st, const TablePtrs &tab, const SystemWork *work, 
 	launch_chain(k_plan, div_up((uint64_t)numWork * 32, 128), 128, 0, st, tab, work, numWork, active, stamp);
 }
 
-void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
+void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SystemWork *work, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
 {
 	if (!numActive) return;
-	launch_chain(k_emit_warp, div_up((uint64_t)numActive * 32, 256), 256, 0, st, pool, tab, active, numActive, round, stamp);
+	launch_chain(k_emit_warp, div_up((uint64_t)numActive * 32, 256), 256, 0, st, pool, tab, work, active, numActive, round, stamp);
 }
 
 void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs, uint32_t totalBlocks)
@@ -1501,12 +1503,11 @@ void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &t
 }
 
 void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool sortMode, bool gravityPoints, bool tinyEffects, const float camera[3])
+	uint32_t epoch, bool sortMode, bool gravityPoints, bool tinyEffects)
 {
 	if (!numPoolTiles) return;
 	(void)epoch;
-	const float cx = camera[0], cy = camera[1], cz = camera[2];
-#define SPR_LAUNCH_PASS(GP, TINY, KEYS) launch_chain(k_integrate_pass<GP, TINY, KEYS>, numPoolTiles, 256, 0, st, pool, tab, stamp, round, cx, cy, cz)
+#define SPR_LAUNCH_PASS(GP, TINY, KEYS) launch_chain(k_integrate_pass<GP, TINY, KEYS>, numPoolTiles, 256, 0, st, pool, tab, stamp, round)
 	int variant = (gravityPoints ? 4 : 0) | (tinyEffects ? 2 : 0) | (sortMode ? 1 : 0);
 	switch (variant) {
 	case 0: SPR_LAUNCH_PASS(false, false, false); break;

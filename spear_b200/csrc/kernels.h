@@ -19,10 +19,10 @@ struct RenderGather {
 void launch_fill_jobs(cudaStream_t st, uint32_t *dst, const FillJob *jobs, uint32_t numJobs);
 void launch_scatter_words(cudaStream_t st, void *dst, const uint32_t *idx, const void *src, uint32_t n, uint32_t words);
 void launch_plan(cudaStream_t st, const TablePtrs &tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp);
-void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp);
+void launch_emit_warp(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const SystemWork *work, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp);
 void launch_emit_burst(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const ActiveEntry *active, const BurstJob *jobs, uint32_t numJobs, uint32_t totalBlocks);
 void launch_integrate(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round,
-	uint32_t epoch, bool sortMode, bool gravityPoints, bool tinyEffects, const float camera[3]);
+	uint32_t epoch, bool sortMode, bool gravityPoints, bool tinyEffects);
 // ticketBase: the context's running count of tickets handed out by launches of the kernel so far (PoolPtrs::tickets)
 void launch_dead_append(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, uint32_t numPoolTiles, uint32_t stamp, uint32_t round, uint32_t epoch, bool aliveScan,
 	uint64_t &ticketBase);

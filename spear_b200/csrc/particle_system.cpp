@@ -189,6 +189,7 @@ uint32_t Context::allocEffectGlobal()
 		ensureSlotMirror(numEffectGlobals);
 	}
 	effectLive[g] = 1;
+	numLiveEffects++;
 	return g;
 }
 
@@ -409,17 +410,14 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	std::vector<uint32_t> resolveGlobals;
 	uint32_t numPlans = 0, maxSub = 0, burstBlocks = 0;
 	const uint32_t thisStamp = frameStamp + 1; // the stamp this frame gets if it simulates anything
-	float camera[3] = { 0, 0, 0 };
-	if (numReqs) {
-		const SprFrameArgs &last = *reqs[numReqs - 1].args; // (every request overwrote the camera: the last one stands)
-		camera[0] = last.cameraPosition.x; camera[1] = last.cameraPosition.y; camera[2] = last.cameraPosition.z;
-	}
 	entries.resize(totalActive);
 	work.resize(numReqs);
 	{
 		uint32_t first = 0;
 		for (uint32_t r = 0; r < numReqs; r++) {
-			work[r] = { reqs[r].system->systemIdx, first, reqs[r].numActive, 0 };
+			// every system is sorted towards the camera of its own request (a batch is equivalent to the per-system calls)
+			const SprVec3 &cam = reqs[r].args->cameraPosition;
+			work[r] = { reqs[r].system->systemIdx, first, reqs[r].numActive, 0, { cam.x, cam.y, cam.z }, 0 };
 			first += reqs[r].numActive;
 		}
 	}
@@ -442,7 +440,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 				E.timeDelta += clampedDt;                        // :816
 				uint32_t nsub = 0;
 				while (E.timeDelta >= E.timeStep) { nsub++; E.timeDelta -= E.timeStep; } // :817-820
-				out[i] = { E.global, nsub, 0, 0 };
+				out[i] = { E.global, nsub, 0, r << 2 }; // flags [31:2]: the effect's system in the work list
 				if (!nsub) continue;
 				if (nsub > part.maxSub) part.maxSub = nsub;
 				const HostType &type = sys->types[E.typeId];
@@ -554,7 +552,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	std::vector<SortTile> &sortTiles = nested ? nestedTiles : scratchSortTiles;
 	segEffects.clear(); sortTiles.clear();
 	uint32_t numBigSegments = 0, numBigTiles = 0;
-	if (sortMode) {
+	if (sortMode && numTinyEffects != numLiveEffects) { // (one-granule effects are sorted inside k_integrate_pass: a context of nothing else has no lists to build)
 		// tile-path effects first, then the ones one CTA sorts whole (k_sort_small): ownedSlots is the effect's slot
 		// bound rounded up to a tile, never below its real slot count
 		static const bool smallSort = !(getenv("SPR_SMALL_SORT") && getenv("SPR_SMALL_SORT")[0] == '0');
@@ -680,7 +678,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	const uint64_t poolEnd = poolOwnedEnd < poolUsed ? poolOwnedEnd : poolUsed;
 	const uint32_t poolTiles = (uint32_t)((poolEnd + kTileSlots - 1) / kTileSlots);
 	for (uint32_t round = 0; round < maxSub; round++) {
-		TIMED(kKEmit, launch_emit_warp(stream, pool, tab, dEntries, nEntries, round, frameStamp));
+		TIMED(kKEmit, launch_emit_warp(stream, pool, tab, DPTR(SystemWork, oWork), dEntries, nEntries, round, frameStamp));
 		if (round == 0 && !burstJobs.empty()) {
 			TIMED(kKEmitBurst, launch_emit_burst(stream, pool, tab, dEntries, DPTR(BurstJob, oBurst), (uint32_t)burstJobs.size(), burstBlocks));
 		}
@@ -694,7 +692,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 			// stream mode, one pass: integrate + ranks + free list + 4x expansion in a software-pipelined persistent kernel
 			TIMED(kKStreamFused, launch_stream_fused(stream, pool, tab, poolTiles, frameStamp, round, epoch, typesWithGravityPoints != 0, numSms, streamFusedCtasPerSm, ticketBase[0], vertexMapValid ? &vertexMap : nullptr));
 		} else {
-			TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, numTinyEffects != 0, camera));
+			TIMED(kKIntegrate, launch_integrate(stream, pool, tab, poolTiles, frameStamp, round, epoch, sortMode, typesWithGravityPoints != 0, numTinyEffects != 0));
 			TIMED(kKDeadAppend, launch_dead_append(stream, pool, tab, poolTiles, frameStamp, round, epoch, !sortMode, ticketBase[1]));
 		}
 	}
@@ -993,6 +991,7 @@ void ParticleSystem::remove(uint32_t effectId)
 	ctx->ownedSlots[E.global] = 0;
 	ctx->freeEffectGlobals.push_back(E.global);
 	ctx->effectLive[E.global] = 0;
+	ctx->numLiveEffects--;
 	E = HostEffect();
 	activeMark[effectId] = kMarkFree;
 	freeEffectIds.push_back(effectId);

@@ -266,6 +266,7 @@ struct Context {
 	bool streamTma = true;                     // SPR_STREAM_TMA=0: expansion stores through the LSU (A/B)
 	bool streamFused = true;               // stream mode: one-pass pipelined kernel (default) or integrate + dead_append + expand
 	uint32_t numTinyEffects = 0;          // live effects whose whole range is one 128-slot granule
+	uint32_t numLiveEffects = 0;          // live effects of every size
 	uint32_t typesWithGravityPoints = 0; // live effect types with gravityPoints (selects the kernel variant)
 	uint32_t frameStamp = 0;
 	uint32_t epoch = 0;

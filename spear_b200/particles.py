@@ -201,6 +201,11 @@ class ParticleContext:
         arrs = [np.ascontiguousarray(ids, dtype=np.uint32) for ids in id_lists]
         ptrs = (C.POINTER(C.c_uint32) * n)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in arrs])
         counts = (C.c_uint32 * n)(*[len(a) for a in arrs])
+        if isinstance(frame_args, (list, tuple)):   # one FrameArgs per system
+            assert len(frame_args) == n
+            arr = (type(frame_args[0]) * n)(*frame_args)
+            _check(lib.sprUpdateParticlesBatch(self.h, handles, n, ptrs, counts, arr, C.sizeof(type(frame_args[0]))))
+            return
         _check(lib.sprUpdateParticlesBatch(self.h, handles, n, ptrs, counts, C.byref(frame_args), 0))
 
     def make_batch(self, systems, id_lists):

@@ -120,6 +120,53 @@ def test_sorted_with_a_moving_camera(oracle_port):
         ctx.close()
 
 
+def test_batched_update_sorts_every_system_towards_its_own_camera(oracle_port):
+    """sprUpdateParticlesBatch with one FrameArgs per system (argsStride != 0): dt, game time and the camera of the depth
+    keys are per system -- the batch equals the per-system calls. Three systems with the same effects, different cameras
+    and time steps; one of them is also driven alone in a second context and must give the same bytes."""
+    P = _particles()
+    ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 16)
+    solo = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 16)
+    try:
+        effects = [(comp_big(30_000), abi.make_transform((1, 2, 3))), (comp_big(3_000), abi.make_transform((-4, 1, 2))),
+                   (S.comp_c5(), abi.make_transform((2, 0, -1)))]
+        seeds = [(1, 2, 3, 4), (5, 6, 7, 8), (9, 10, 11, 12)]
+        cams = [(16.0, 20.0, -30.0), (-3.0, 1.0, 2.0), (500.0, -40.0, 90.0)]
+        dts = [1 / 60, 1 / 45, 1 / 75]
+        oracles, systems, ids = [], [], []
+        for sd in seeds:
+            o = orc.OracleSystem(oracle_port, sd); s = ctx.create_system(sd)
+            my = [s.add_effect(c, t) for c, t in effects]
+            assert my == [o.add_effect(c, t) for c, t in effects]
+            oracles.append(o); systems.append(s); ids.append(my)
+        s1 = solo.create_system(seeds[1])
+        ids1 = [s1.add_effect(c, t) for c, t in effects]
+        sorted_under = {}   # (system, effect) -> (simSteps, camera of the last frame that simulated the effect: a frame
+                            # whose dt does not reach the effect's time step leaves its stream as it is)
+        for f in range(8):
+            fas = [abi.make_frame_args(dts[i], game_time=f * dts[i], frame_index=f, camera=(cams[i][0] + f, cams[i][1], cams[i][2])) for i in range(3)]
+            ctx.update_batch(systems, ids, fas)
+            s1.update(ids1, fas[1])
+            for i in range(3):
+                oracles[i].update(ids[i], fas[i])
+                a, b = S.snapshot(oracles[i], ids[i]), S.snapshot(systems[i], ids[i])
+                for e in ids[i]:
+                    assert a[e]["info"] == b[e]["info"], "frame %d system %d effect %d" % (f, i, e)
+                    steps = a[e]["info"]["simSteps"]
+                    if sorted_under.get((i, e), (0, None))[0] != steps:
+                        sorted_under[(i, e)] = (steps, (cams[i][0] + f, cams[i][1], cams[i][2]))
+                    if steps == 0:
+                        continue
+                    exp, _ = expected_sorted(a[e]["stream"], sorted_under[(i, e)][1])
+                    assert exp.tobytes() == b[e]["stream"].tobytes(), "frame %d system %d effect %d" % (f, i, e)
+            c = S.snapshot(s1, ids1)
+            b = S.snapshot(systems[1], ids[1])
+            for e in ids1:
+                assert c[e]["stream"].tobytes() == b[e]["stream"].tobytes(), "frame %d: batch differs from the per-system call" % f
+    finally:
+        ctx.close(); solo.close()
+
+
 @pytest.mark.parametrize("sort", [False, True], ids=["stream", "sorted"])
 def test_effects_above_4gb_of_vertex_stream(oracle_port, sort):
     """Maximum sizes: an idle 40M-particle effect is registered first, so every effect of the scenario lives
