@@ -725,11 +725,34 @@ def bench_billboards(ctx, n=1 << 20, frames=5, cpu_reference=True):
         times.append(time.perf_counter() - t0)
     quads, draws = out.numQuads, out.numDraws
     launches = (ctx.launch_count - launches0) // (frames + 2)
-    bs.close()
     ms = sorted(times[2:])[len(times[2:]) // 2] * 1e3
+    # the same frame as packed billboards (sprBillboardPack once, outside the time): from pinned host memory (one DMA, no
+    # per-billboard host work) and from device memory (a producer on the GPU / billboards that do not change: read in place)
+    packed_ms = {}
+    try:
+        import torch
+        pk = (abi.BillboardPacked * n)()
+        got = C.c_uint32(0)
+        particles._check(particles.lib.sprBillboardPack(ptr, n, pk, C.byref(got)))
+        host = torch.from_numpy(np.frombuffer(pk, dtype=np.uint8, count=got.value * 120).copy()).pin_memory()
+        dev = host.cuda()
+        torch.cuda.synchronize()
+        for kind, address, on_device in (("pinned_host", host.data_ptr(), 0), ("device", dev.data_ptr(), 1)):
+            tt = []
+            for _ in range(frames + 2):
+                t0 = time.perf_counter()
+                particles._check(particles.lib.sprBillboardAddPacked(bs.h, C.c_void_p(address), got.value, on_device))
+                particles._check(particles.lib.sprBillboardRenderMain(bs.h, C.byref(ra), C.byref(out)))
+                tt.append(time.perf_counter() - t0)
+            assert out.numQuads == quads and out.numDraws == draws
+            packed_ms[kind] = sorted(tt[2:])[len(tt[2:]) // 2] * 1e3
+    except Exception as ex:  # noqa: BLE001
+        packed_ms = {"error": str(ex)[:200]}
+    bs.close()
     res = {"billboards_per_frame": n, "budget": n, "quads": int(quads), "draws": int(draws), "ms_per_frame": ms,
-           "billboards_per_s": n / (ms * 1e-3), "h2d_bytes_per_frame": int(n * 120), "d2h_bytes_per_frame": int(quads * 8 + 4),
+           "billboards_per_s": n / (ms * 1e-3), "h2d_bytes_per_frame": int(n * 120), "d2h_bytes_per_frame": int(draws * 16 + 8),
            "gpu_launches_per_frame": int(launches),
+           "packed_input_ms_per_frame": packed_ms,
            "note": "sprBillboardAdd + sprBillboardRenderMain per frame, host arrays in, host draw list out (median of %d frames)" % frames}
     if not cpu_reference:
         return res

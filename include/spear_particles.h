@@ -549,6 +549,28 @@ SPR_API int sprBillboardSystemDestroy(SprBillboardSystem *sys);
 /* addBillboard (:80-117), `count` times in array order; the 4-argument overload of the reference is the
  * same call with anchor 0.5, crop [0, 1]. Host only: the frame's billboards go to the device in renderMain. */
 SPR_API int sprBillboardAdd(SprBillboardSystem *sys, const SprBillboard *billboards, uint32_t count);
+/* The same billboard in the form the device reads (120 bytes): what sprBillboardAdd makes of an SprBillboard with a
+ * loaded sprite -- the sprite's fields, the transform, the colour packed by packColor() (:12-28), anchor, crop, depth. */
+typedef struct SprBillboardPacked {
+	uint64_t atlas;                    /* sprite->atlas, not 0 */
+	float minVert[2], maxVert[2], vertUvScale[2], vertUvBias[2];
+	float transform[12];               /* sf::Mat34, column major */
+	float anchor[2];
+	uint32_t color;
+	float cropMin[2], cropMax[2];
+	float depth;
+} SprBillboardPacked;
+/* Host-side conversion (no system, no device): packs `count` billboards in order, skipping those without a loaded
+ * sprite like addBillboard does (:82, :100); *outCount = entries written to `out` (room for `count`). */
+SPR_API int sprBillboardPack(const SprBillboard *billboards, uint32_t count, SprBillboardPacked *out, uint32_t *outCount);
+#define SPR_MEMORY_HOST 0
+#define SPR_MEMORY_DEVICE 1
+/* addBillboard for billboards that are already packed, `count` times in array order, in host memory (pinned memory
+ * copies at the rate of the bus; no per-billboard host work) or in device memory of the context's GPU (a producer on the
+ * GPU, or billboards that do not change between frames: nothing crosses the bus). May be mixed with sprBillboardAdd:
+ * the frame's billboards are those of all calls in call order. The array is read by sprBillboardRenderMain: it must
+ * stay valid and unchanged until that call returns. */
+SPR_API int sprBillboardAddPacked(SprBillboardSystem *sys, const SprBillboardPacked *packed, uint32_t count, int memory);
 /* renderMain (:119-228): sort by (depth, insertion index), cut to the frame budget, crop, expand;
  * clears the frame's billboards. Synchronises the context stream (the draw list is host data). */
 SPR_API int sprBillboardRenderMain(SprBillboardSystem *sys, const SprRenderArgs *args, SprBillboardOutput *out);

@@ -177,6 +177,13 @@ class Billboard(C.Structure):
                 ("anchor", Vec2), ("cropMin", Vec2), ("cropMax", Vec2)]
 
 
+class BillboardPacked(C.Structure):
+    """SprBillboardPacked: the billboard as the device reads it (120 bytes)."""
+    _fields_ = [("atlas", C.c_uint64), ("minVert", C.c_float * 2), ("maxVert", C.c_float * 2), ("vertUvScale", C.c_float * 2),
+                ("vertUvBias", C.c_float * 2), ("transform", C.c_float * 12), ("anchor", C.c_float * 2), ("color", C.c_uint32),
+                ("cropMin", C.c_float * 2), ("cropMax", C.c_float * 2), ("depth", C.c_float)]
+
+
 class BillboardVertex(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("texCoord", C.c_float * 2), ("color", C.c_uint32)]
 

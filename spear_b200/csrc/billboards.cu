@@ -186,10 +186,43 @@ __global__ void __launch_bounds__(kBbThreads) k_bb_expand(const BillboardDev *bb
 	atlasOut[pos] = b.atlas;
 }
 
+// ---- the draw list (:198-203): runs of equal atlas over the expanded quads, built where the atlas ids are.
+// k_bb_run_count: quad q starts a run when it is the first one or its atlas differs from quad q - 1's -> per-block counts;
+// k_bb_run_write (after the scan of the counts): run r = (atlas, first quad); k_bb_run_lengths: count = next run's first
+// quad - this one's. `total` (the number of quads) is only known on the device: the grids cover the frame's budget.
+__global__ void __launch_bounds__(kBbThreads) k_bb_run_count(const unsigned long long *atlas, const uint32_t *total, uint32_t *blockCounts)
+{
+	const uint32_t q = blockIdx.x * kBbThreads + threadIdx.x, n = *total;
+	const bool start = q < n && (q == 0 || atlas[q] != atlas[q - 1]);
+	const uint32_t cnt = __syncthreads_count(start);
+	if (threadIdx.x == 0) blockCounts[blockIdx.x] = cnt;
+}
+
+__global__ void __launch_bounds__(kBbThreads) k_bb_run_write(const unsigned long long *atlas, const uint32_t *total, const uint32_t *blockOffsets, BillboardDrawDev *draws)
+{
+	__shared__ uint32_t sWarp[8];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t q = blockIdx.x * kBbThreads + tid, n = *total;
+	const bool start = q < n && (q == 0 || atlas[q] != atlas[q - 1]);
+	const uint32_t ballot = __ballot_sync(FULL_MASK, start);
+	if (lane == 0) sWarp[warp] = __popc(ballot);
+	__syncthreads();
+	uint32_t pos = blockOffsets[blockIdx.x] + __popc(ballot & ((1u << lane) - 1u));
+	for (uint32_t w = 0; w < warp; w++) pos += sWarp[w];
+	if (start) { draws[pos].atlas = atlas[q]; draws[pos].firstQuad = q; }
+}
+
+__global__ void __launch_bounds__(256) k_bb_run_lengths(BillboardDrawDev *draws, const uint32_t *numRuns, const uint32_t *total)
+{
+	const uint32_t r = blockIdx.x * 256 + threadIdx.x, n = *numRuns;
+	if (r >= n) return;
+	draws[r].count = (r + 1 < n ? draws[r + 1].firstQuad : *total) - draws[r].firstQuad;
+}
+
 static inline uint32_t bb_div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 uint32_t launch_billboards(cudaStream_t st, const BillboardDev *bb, uint32_t n, uint32_t maxPerFrame, const BillboardScratch &sc,
-	float *verts, unsigned long long *atlasOut, uint32_t *totalOut)
+	float *verts, unsigned long long *atlasOut, uint32_t *totalOut, BillboardDrawDev *drawsOut)
 {
 	if (!n) return 0;
 	uint32_t launches = 0;
@@ -208,7 +241,12 @@ uint32_t launch_billboards(cudaStream_t st, const BillboardDev *bb, uint32_t n, 
 	k_bb_count<<<blocks, kBbThreads, 0, st>>>(bb, sc.vals[0], m, sc.blockCounts);
 	k_bb_scan<<<1, 1024, 0, st>>>(sc.blockCounts, blocks, totalOut);
 	k_bb_expand<<<blocks, kBbThreads, 0, st>>>(bb, sc.vals[0], m, sc.blockCounts, verts, atlasOut);
-	return launches + 3;
+	// totalOut[0] = quads, totalOut[1] = draws
+	k_bb_run_count<<<blocks, kBbThreads, 0, st>>>(atlasOut, totalOut, sc.blockCounts);
+	k_bb_scan<<<1, 1024, 0, st>>>(sc.blockCounts, blocks, totalOut + 1);
+	k_bb_run_write<<<blocks, kBbThreads, 0, st>>>(atlasOut, totalOut, sc.blockCounts, drawsOut);
+	k_bb_run_lengths<<<bb_div_up(m, 256), 256, 0, st>>>(drawsOut, totalOut + 1, totalOut);
+	return launches + 7;
 }
 
 } // namespace spr

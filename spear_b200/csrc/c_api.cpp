@@ -365,6 +365,21 @@ SPR_API int sprBillboardAdd(SprBillboardSystem *sys, const SprBillboard *billboa
 	return guarded([&] { sys->sys.add(billboards, count); });
 }
 
+SPR_API int sprBillboardPack(const SprBillboard *billboards, uint32_t count, SprBillboardPacked *out, uint32_t *outCount)
+{
+	REQUIRE((billboards && out) || !count);
+	return guarded([&] {
+		BillboardDev *end = BillboardSystem::pack(billboards, 0, count, (BillboardDev*)out);
+		if (outCount) *outCount = (uint32_t)(end - (BillboardDev*)out);
+	});
+}
+
+SPR_API int sprBillboardAddPacked(SprBillboardSystem *sys, const SprBillboardPacked *packed, uint32_t count, int memory)
+{
+	REQUIRE(sys && (packed || !count) && (memory == SPR_MEMORY_HOST || memory == SPR_MEMORY_DEVICE));
+	return guarded([&] { sys->sys.addPacked((const BillboardDev*)packed, count, memory == SPR_MEMORY_DEVICE); });
+}
+
 SPR_API int sprBillboardRenderMain(SprBillboardSystem *sys, const SprRenderArgs *args, SprBillboardOutput *out)
 {
 	REQUIRE(sys && args && out);

@@ -226,6 +226,9 @@ struct BillboardDev {
 	float depth;
 };
 
+// One sg_draw of cl::BillboardSystem::renderMain (:198-203): `count` quads of one atlas from quad `firstQuad` on (= SprBillboardDraw)
+struct BillboardDrawDev { unsigned long long atlas; uint32_t count, firstQuad; };
+
 // Launch-constant pointers for the per-round kernels.
 struct PoolPtrs {
 	float4 *state;            // 2 float4 per slot

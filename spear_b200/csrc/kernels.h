@@ -58,7 +58,7 @@ struct BillboardScratch {
 	uint32_t *blockCounts;           // [ceil(min(n, budget) / 256)]
 };
 uint32_t launch_billboards(cudaStream_t st, const BillboardDev *bb, uint32_t n, uint32_t maxPerFrame, const BillboardScratch &scratch,
-	float *verts, unsigned long long *atlasOut, uint32_t *totalOut);
+	float *verts, unsigned long long *atlasOut, uint32_t *totalOut /* [2]: quads, draws */, BillboardDrawDev *drawsOut /* room for min(n, maxPerFrame) */);
 
 // sort.cu: segmented stable LSD radix sort of the (key, slot) pairs of the listed effects
 // followed by the 4x expansion in sorted order.

@@ -1218,6 +1218,39 @@ static uint32_t packChannel(float f)
 	return u > 255u ? 255u : u;
 }
 
+static_assert(sizeof(SprBillboardPacked) == sizeof(BillboardDev) && offsetof(SprBillboardPacked, transform) == offsetof(BillboardDev, transform)
+	&& offsetof(SprBillboardPacked, color) == offsetof(BillboardDev, color) && offsetof(SprBillboardPacked, depth) == offsetof(BillboardDev, depth),
+	"SprBillboardPacked is BillboardDev");
+
+// addBillboard's conversion (:80-117) of billboards [i0, i1) into packed form; returns the end of what it wrote
+BillboardDev *BillboardSystem::pack(const SprBillboard *billboards, uint32_t i0, uint32_t i1, BillboardDev *dst)
+{
+	for (uint32_t i = i0; i < i1; i++) {
+		const SprBillboard &b = billboards[i];
+		if (!b.sprite.atlas) continue;                              // !sprite || !sprite->isLoaded(), :82, :100
+		BillboardDev &d = *dst++;
+		d.atlas = b.sprite.atlas;
+		d.minVert[0] = b.sprite.minVert.x; d.minVert[1] = b.sprite.minVert.y;
+		d.maxVert[0] = b.sprite.maxVert.x; d.maxVert[1] = b.sprite.maxVert.y;
+		d.vertUvScale[0] = b.sprite.vertUvScale.x; d.vertUvScale[1] = b.sprite.vertUvScale.y;
+		d.vertUvBias[0] = b.sprite.vertUvBias.x; d.vertUvBias[1] = b.sprite.vertUvBias.y;
+		memcpy(d.transform, b.transform, sizeof(d.transform));
+		d.anchor[0] = b.anchor.x; d.anchor[1] = b.anchor.y;
+		d.color = packChannel(b.color.x) | packChannel(b.color.y) << 8 | packChannel(b.color.z) << 16 | packChannel(b.color.w) << 24; // :22-28
+		d.cropMin[0] = b.cropMin.x; d.cropMin[1] = b.cropMin.y;
+		d.cropMax[0] = b.cropMax.x; d.cropMax[1] = b.cropMax.y;
+		d.depth = b.depth;                                          // order.index = billboards.size - 1 = its position in the frame, :95, :115
+	}
+	return dst;
+}
+
+void BillboardSystem::addPacked(const BillboardDev *packed, uint32_t count, bool onDevice)
+{
+	if (!count) return;
+	segments.push_back({ onDevice ? 2 : 1, packed, 0, count });
+	frameCount += count;
+}
+
 void BillboardSystem::add(const SprBillboard *billboards, uint32_t count)
 {
 	if (pendingCount + count > pendingCapacity) {
@@ -1231,24 +1264,14 @@ void BillboardSystem::add(const SprBillboard *billboards, uint32_t count)
 		if (pending) cudaFreeHost(pending);
 		pending = p; pendingCapacity = cap;
 	}
-	auto convert = [&](uint32_t i0, uint32_t i1, BillboardDev *dst) {
-		for (uint32_t i = i0; i < i1; i++) {
-			const SprBillboard &b = billboards[i];
-			if (!b.sprite.atlas) continue;                              // !sprite || !sprite->isLoaded(), :82, :100
-			BillboardDev &d = *dst++;
-			d.atlas = b.sprite.atlas;
-			d.minVert[0] = b.sprite.minVert.x; d.minVert[1] = b.sprite.minVert.y;
-			d.maxVert[0] = b.sprite.maxVert.x; d.maxVert[1] = b.sprite.maxVert.y;
-			d.vertUvScale[0] = b.sprite.vertUvScale.x; d.vertUvScale[1] = b.sprite.vertUvScale.y;
-			d.vertUvBias[0] = b.sprite.vertUvBias.x; d.vertUvBias[1] = b.sprite.vertUvBias.y;
-			memcpy(d.transform, b.transform, sizeof(d.transform));
-			d.anchor[0] = b.anchor.x; d.anchor[1] = b.anchor.y;
-			d.color = packChannel(b.color.x) | packChannel(b.color.y) << 8 | packChannel(b.color.z) << 16 | packChannel(b.color.w) << 24; // :22-28
-			d.cropMin[0] = b.cropMin.x; d.cropMin[1] = b.cropMin.y;
-			d.cropMax[0] = b.cropMax.x; d.cropMax[1] = b.cropMax.y;
-			d.depth = b.depth;                                          // order.index = billboards.size - 1 = its position here, :95, :115
-		}
-		return dst;
+	auto convert = [&](uint32_t i0, uint32_t i1, BillboardDev *dst) { return pack(billboards, i0, i1, dst); };
+	const size_t before = pendingCount;
+	auto noteSegment = [&] { // the converted run joins the frame's list (merged with a converted run right before it)
+		const size_t added = pendingCount - before;
+		if (!added) return;
+		if (!segments.empty() && segments.back().kind == 0) segments.back().count += added;
+		else segments.push_back({ 0, nullptr, before, added });
+		frameCount += added;
 	};
 	// A large call (the 1M-billboard frame: 220 MB through the host) is converted by a few threads: each counts the
 	// loaded sprites of its range, the counts give every range its place in the staging array, then the ranges are
@@ -1256,6 +1279,7 @@ void BillboardSystem::add(const SprBillboard *billboards, uint32_t count)
 	const uint32_t nt = count >= 65536 ? HostPool::maxThreads() : 1;
 	if (nt <= 1) {
 		pendingCount = (size_t)(convert(0, count, pending + pendingCount) - pending);
+		noteSegment();
 		return;
 	}
 	std::vector<uint32_t> cut(nt + 1), valid(nt, 0);
@@ -1266,6 +1290,7 @@ void BillboardSystem::add(const SprBillboard *billboards, uint32_t count)
 	for (uint32_t t = 0; t < nt; t++) first[t + 1] = first[t] + valid[t];
 	run([&](uint32_t t) { convert(cut[t], cut[t + 1], pending + first[t]); });
 	pendingCount = first[nt];
+	noteSegment();
 }
 
 void BillboardSystem::renderMain(const SprRenderArgs &args, SprBillboardOutput &out)
@@ -1273,10 +1298,10 @@ void BillboardSystem::renderMain(const SprRenderArgs &args, SprBillboardOutput &
 	SPR_CUDA(cudaSetDevice(ctx->device));
 	memset(&out, 0, sizeof(out));
 	memcpy(out.worldToClip, args.worldToClip.v, sizeof(out.worldToClip));   // :208-209
-	draws.clear();
 	lastQuads = 0;
-	if (pendingCount > 0xffffffffull) throw std::runtime_error("more than 2^32 billboards in one frame");
-	const uint32_t n = (uint32_t)pendingCount;
+	if (frameCount > 0xffffffffull) throw std::runtime_error("more than 2^32 billboards in one frame");
+	const uint32_t n = (uint32_t)frameCount;
+	struct FrameReset { BillboardSystem &b; ~FrameReset() { b.pendingCount = 0; b.frameCount = 0; b.segments.clear(); } } frameReset { *this }; // :227-228
 	if (!n) return;
 	cudaStream_t st = ctx->stream;
 	const uint32_t m = n < maxPerFrame ? n : maxPerFrame;
@@ -1285,34 +1310,43 @@ void BillboardSystem::renderMain(const SprRenderArgs &args, SprBillboardOutput &
 	for (int i = 0; i < 2; i++) { dKeys[i].reserve(n, 0, st); dVals[i].reserve(n, 0, st); }
 	dTileHist.reserve((size_t)256 * numTiles, 0, st);
 	dBlockCounts.reserve((m + 255) / 256, 0, st);
-	dTotal.reserve(1, 0, st);
+	dTotal.reserve(2, 0, st);
 	dVerts.reserve((size_t)m * 24, 0, st);
 	dAtlas.reserve(m, 0, st);
-	SPR_CUDA(cudaMemcpyAsync(dBillboards.ptr, pending, (size_t)n * sizeof(BillboardDev), cudaMemcpyHostToDevice, st));
+	// the frame's billboards in call order: converted runs out of the pinned staging array, packed arrays straight from
+	// where the caller keeps them; a frame that is ONE packed device array is read in place
+	const BillboardDev *frame = dBillboards.ptr;
+	if (segments.size() == 1 && segments[0].kind == 2) frame = segments[0].src;
+	else {
+		size_t at = 0;
+		for (const Segment &sg : segments) {
+			const BillboardDev *src = sg.kind == 0 ? pending + sg.offset : sg.src;
+			SPR_CUDA(cudaMemcpyAsync(dBillboards.ptr + at, src, sg.count * sizeof(BillboardDev), sg.kind == 2 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+			at += sg.count;
+		}
+	}
 	BillboardScratch sc;
 	sc.keys[0] = dKeys[0].ptr; sc.keys[1] = dKeys[1].ptr; sc.vals[0] = dVals[0].ptr; sc.vals[1] = dVals[1].ptr;
 	sc.tileHist = dTileHist.ptr; sc.blockCounts = dBlockCounts.ptr;
-	ctx->launchCount += launch_billboards(st, dBillboards.ptr, n, maxPerFrame, sc, dVerts.ptr, dAtlas.ptr, dTotal.ptr);
+	dDraws.reserve(m, 0, st);
+	ctx->launchCount += launch_billboards(st, frame, n, maxPerFrame, sc, dVerts.ptr, dAtlas.ptr, dTotal.ptr, dDraws.ptr);
 	SPR_CUDA(cudaGetLastError());
-	uint32_t total = 0;
-	SPR_CUDA(cudaMemcpyAsync(&total, dTotal.ptr, sizeof(total), cudaMemcpyDeviceToHost, st));
+	// the draw list (:198-203, runs of equal atlas) is built on the device: two counts, then one copy of 16 bytes per draw
+	uint32_t totals[2] = { 0, 0 };
+	SPR_CUDA(cudaMemcpyAsync(totals, dTotal.ptr, sizeof(totals), cudaMemcpyDeviceToHost, st));
 	SPR_CUDA(cudaStreamSynchronize(st));
-	atlasPinned.reserve(total ? total : 1);
-	if (total) {
-		SPR_CUDA(cudaMemcpyAsync(atlasPinned.ptr, dAtlas.ptr, (size_t)total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	const uint32_t total = totals[0], numDraws = totals[1];
+	static_assert(sizeof(SprBillboardDraw) == sizeof(BillboardDrawDev), "SprBillboardDraw is BillboardDrawDev");
+	drawsPinned.reserve(numDraws ? numDraws : 1);
+	if (numDraws) {
+		SPR_CUDA(cudaMemcpyAsync(drawsPinned.ptr, dDraws.ptr, (size_t)numDraws * sizeof(SprBillboardDraw), cudaMemcpyDeviceToHost, st));
 		SPR_CUDA(cudaStreamSynchronize(st));
-	}
-	const unsigned long long *atlasOf = atlasPinned.ptr;
-	for (uint32_t q = 0; q < total; q++) {                              // :198-203
-		if (!draws.empty() && draws.back().atlas == atlasOf[q]) draws.back().count++;
-		else draws.push_back({ atlasOf[q], 1u, q });
 	}
 	lastQuads = total;
 	out.deviceVertices = (const SprBillboardVertex*)dVerts.ptr;
 	out.numQuads = total;
-	out.numDraws = (uint32_t)draws.size();
-	out.draws = draws.data();
-	pendingCount = 0;                                                   // :227-228
+	out.numDraws = numDraws;
+	out.draws = drawsPinned.ptr;
 }
 
 // ---------------------------------------------------------------------------

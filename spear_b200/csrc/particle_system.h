@@ -320,16 +320,22 @@ struct Context {
 struct BillboardSystem {
 	Context *ctx;
 	uint32_t maxPerFrame;                      // MaxBillboardsPerFrame, BillboardSystem.cpp:10
-	BillboardDev *pending = nullptr;           // billboards + billboardOrder of the frame (:61-62), in pinned host memory
+	BillboardDev *pending = nullptr;           // billboards + billboardOrder of the frame (:61-62) that came through add(), in pinned host memory
 	size_t pendingCount = 0, pendingCapacity = 0;
+	// The frame in call order: runs of converted billboards (in `pending`) and packed arrays of the caller (host or device)
+	struct Segment { int kind; const BillboardDev *src; size_t offset; size_t count; }; // kind 0: pending + offset, 1: caller's host array src, 2: caller's device array src
+	std::vector<Segment> segments;
+	size_t frameCount = 0;
+	void addPacked(const BillboardDev *packed, uint32_t count, bool onDevice);
+	static BillboardDev *pack(const SprBillboard *billboards, uint32_t i0, uint32_t i1, BillboardDev *dst);
 	~BillboardSystem() { if (pending) cudaFreeHost(pending); }
-	std::vector<SprBillboardDraw> draws;       // billboardDraws (:63)
-	PinnedArray<unsigned long long> atlasPinned; // the frame's atlas id per quad, read back for the draw list
+	PinnedArray<SprBillboardDraw> drawsPinned; // the frame's draw list, built on the device (k_bb_run_*) and read back
 	uint32_t lastQuads = 0;                    // quads of the last renderMain (sprBillboardReadVertices)
 	DeviceArray<BillboardDev> dBillboards;
 	DeviceArray<uint32_t> dKeys[2], dVals[2], dTileHist, dBlockCounts, dTotal;
 	DeviceArray<float> dVerts;                 // billboardVertices (:65): 24 words per quad
 	DeviceArray<unsigned long long> dAtlas;
+	DeviceArray<BillboardDrawDev> dDraws;
 
 	BillboardSystem(Context *c, uint32_t maxBillboardsPerFrame);
 	void add(const SprBillboard *billboards, uint32_t count);                 // :80-117

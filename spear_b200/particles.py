@@ -31,7 +31,7 @@ EXPORTS = [
     "sprRunBufferCreate", "sprRunBufferDestroy", "sprRunBufferGetIpcHandle", "sprRunBufferOpenPeer", "sprRunBufferClosePeer",
     "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers", "sprContextSetAssemblyShare", "sprShadeVertices",
     "sprBillboardSystemCreate", "sprBillboardSystemDestroy", "sprBillboardAdd", "sprBillboardRenderMain",
-    "sprBillboardReadVertices",
+    "sprBillboardReadVertices", "sprBillboardPack", "sprBillboardAddPacked",
     "sprDescriptorsFromJson", "sprDescriptorCount", "sprDescriptorGet", "sprDescriptorTextureName", "sprDescriptorsFree",
     "sprQueryEffects",
 ]
@@ -92,6 +92,8 @@ def _load():
     lib.sprBillboardSystemCreate.argtypes = [vp, u32, P(vp)]
     lib.sprBillboardSystemDestroy.argtypes = [vp]
     lib.sprBillboardAdd.argtypes = [vp, P(abi.Billboard), u32]
+    lib.sprBillboardPack.argtypes = [P(abi.Billboard), u32, P(abi.BillboardPacked), P(u32)]
+    lib.sprBillboardAddPacked.argtypes = [vp, vp, u32, C.c_int]
     lib.sprBillboardRenderMain.argtypes = [vp, P(abi.RenderArgs), P(abi.BillboardOutput)]
     lib.sprBillboardReadVertices.argtypes = [vp, vp, u32, P(u32)]
     lib.sprDescriptorsFromJson.argtypes = [C.c_char_p, C.c_size_t, P(vp)]
@@ -329,6 +331,21 @@ class BillboardSystem:
         n = len(billboards)
         arr = (abi.Billboard * max(n, 1))(*billboards)
         _check(lib.sprBillboardAdd(self.h, arr, n))
+
+    @staticmethod
+    def pack(billboards):
+        """sprBillboardPack: the ctypes array of SprBillboardPacked addBillboard would make of these (unloaded sprites dropped)."""
+        n = len(billboards)
+        arr = (abi.Billboard * max(n, 1))(*billboards)
+        out = (abi.BillboardPacked * max(n, 1))()
+        got = C.c_uint32(0)
+        _check(lib.sprBillboardPack(arr, n, out, C.byref(got)))
+        return out, got.value
+
+    def add_packed(self, pointer, count, device=False):
+        """sprBillboardAddPacked: `pointer` = address of `count` SprBillboardPacked in host (device=False) or device memory;
+        the caller keeps the array alive until render() returns."""
+        _check(lib.sprBillboardAddPacked(self.h, C.c_void_p(pointer), count, 1 if device else 0))
 
     def render(self, render_args):
         """renderMain: returns (vertices [4 * quads] structured array copied from the device, draws [(atlas, count, firstQuad)],

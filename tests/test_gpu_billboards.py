@@ -98,3 +98,48 @@ def test_large_add_call_matches_chunked_adds():
         assert v1.tobytes() == v2.tobytes()
     finally:
         one.close(); many.close(); ctx.close()
+
+
+def test_packed_billboards_from_host_and_device_memory_match_the_immediate_path():
+    """sprBillboardAddPacked: the same frame through sprBillboardAdd, as one packed array in device memory (read in place),
+    as a packed host array, and mixed with sprBillboardAdd calls in between (the frame is the calls in call order) gives
+    the same vertex bytes and draw list -- which the golden test ties to the reference."""
+    import ctypes as C
+    import torch
+    P = _particles()
+    ctx = P.ParticleContext(initial_slot_capacity=1 << 12)
+    ra = make_render_args()
+    try:
+        for budget, (seed, n) in [(0, (31, 5000)), (1 << 20, (32, 70000)), (100, (33, 777))]:
+            bs = P.BillboardSystem(ctx, max_billboards_per_frame=budget)
+            try:
+                frame = B.random_frame(seed, n)
+                bs.add(frame)
+                want_v, want_d, _ = bs.render(ra)
+                packed, m = P.BillboardSystem.pack(frame)
+                assert C.sizeof(abi.BillboardPacked) == 120 and 0 < m <= n
+                host = np.frombuffer(packed, dtype=np.uint8, count=m * 120).copy()
+                dev = torch.from_numpy(host).cuda()
+                torch.cuda.synchronize()
+                for variant in ("device", "host", "mixed"):
+                    if variant == "device":
+                        bs.add_packed(dev.data_ptr(), m, device=True)
+                    elif variant == "host":
+                        bs.add_packed(host.ctypes.data, m, device=False)
+                    else:
+                        # first third through the immediate path, the middle from device memory, the rest from host memory
+                        a = n // 3
+                        pa = P.BillboardSystem.pack(frame[:a])[1]            # packed entries the first third makes
+                        pb = pa + (m - pa) // 2
+                        bs.add(frame[:a])
+                        bs.add_packed(dev.data_ptr() + pa * 120, pb - pa, device=True)
+                        bs.add_packed(host.ctypes.data + pb * 120, m - pb, device=False)
+                    v, d, _ = bs.render(ra)
+                    assert d == want_d, "%s n=%d" % (variant, n)
+                    assert np.array_equal(v.view(np.uint8), want_v.view(np.uint8)), "%s n=%d" % (variant, n)
+                v, d, _ = bs.render(ra)
+                assert len(v) == 0 and d == []
+            finally:
+                bs.close()
+    finally:
+        ctx.close()
