@@ -17,7 +17,6 @@
 //   k_expand_sorted  rank r -> slot -> 32-byte record -> 4 x 32 B at rank r (:607-665)
 
 #include <cuda_runtime.h>
-#include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -377,77 +376,58 @@ void sort_profile_dump()
 #endif
 
 // ---------------------------------------------------------------------------
-// Small segments: the whole sort of one effect on chip, by ONE CTA or by a CLUSTER of two.
+// Small segments: the whole sort of one effect in ONE CTA.
 //
 // An effect of up to kSmallSortMax slots (18432: the 16k-particle emitters of BASELINE configs[1] and everything
 // smaller down to the 128-slot effects k_integrate_pass finishes itself) does not need the tile machinery: its
-// (key, slot) pairs fit registers and shared memory. The kernel is launched as clusters of two 1024-thread CTAs, one
-// cluster per effect. An effect of at most kSmallPart (9216) slots is sorted by CTA 0 alone (CTA 1 leaves at once); a
-// larger one by both: each CTA loads its half of the slots under the alive ballots, ranks its keys per digit
-// (stable, per-warp peer masks as k_sort_pass), the two CTAs exchange their 256 digit totals through distributed
-// shared memory, and every key is written to its place in the sorted sequence -- positions [0, H) live in CTA 0's
-// shared memory, [H, 2H) in CTA 1's, so about half of the stores cross to the other SM (st.shared::cluster). Two
-// cluster barriers per pass. With 64 emitters the sort keeps 128 SMs busy instead of 64 and every SM ranks half
-// as many keys: k_sort_small was the longest kernel of the configs[1] frame.
-// No histogram kernel, no scan kernel, no look-back, no global ping-pong.
+// (key, slot) pairs fit one CTA's registers and shared memory. One 1024-thread CTA per effect loads the keys in
+// slot space under the alive ballots, runs the LSD passes over the digits of key - keyMin that are not all zero
+// (same order as the tile path: stable, ascending), keeps keys in registers and permutes them through shared
+// memory between passes (the 16-bit local slot index travels with them), and writes the sorted slot list to
+// PoolPtrs::vals where k_expand_sorted reads it. No histogram kernel, no scan kernel, no look-back, no global
+// ping-pong: for configs[1] this replaces 6 launches (hist, scan, 4 passes: ~85 us) by one of ~15 us.
 // ---------------------------------------------------------------------------
 
 static const uint32_t kSmallThreads = 1024;
-static const uint32_t kSmallPart = kSmallSortMax / 2;              // keys one CTA holds
-static const uint32_t kSmallItems = kSmallPart / kSmallThreads;    // 9 keys per thread at most
+static const uint32_t kSmallItems = kSmallSortMax / kSmallThreads; // 18 keys per thread at most
 static const uint32_t kSmallWarps = kSmallThreads / 32;
-// shared memory: keys (aliased by the per-warp peer-mask table while ranking), 16-bit slots, per-warp digit counts
-static const size_t kSmallSmemBytes = kSmallPart * 4 + kSmallPart * 2 + kSmallWarps * 256 * 4;
-static_assert(kSmallItems * kSmallThreads == kSmallPart, "kSmallSortMax must be a multiple of twice the CTA size");
-static_assert(kSmallWarps * 256 * 4 <= kSmallPart * 4, "the peer-mask table aliases the key buffer");
+// shared memory: keys (aliased by the per-warp peer-mask tables while ranking), 16-bit slots, per-warp digit counts
+static const size_t kSmallSmemBytes = kSmallSortMax * 4 + kSmallSortMax * 2 + kSmallWarps * 256 * 4;
+static_assert(kSmallItems * kSmallThreads == kSmallSortMax, "kSmallSortMax must be a multiple of the CTA size");
+static_assert(kSmallWarps * 512 * 4 <= kSmallSortMax * 4, "the peer-mask tables alias the key buffer");
 static_assert(kSmallSortMax <= 65536, "local slot indices are 16-bit");
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects)
+__global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects)
 {
 	pdl_enter();
-	namespace cg = cooperative_groups;
-	cg::cluster_group cluster = cg::this_cluster();
 	extern __shared__ __align__(16) uint8_t sRaw[];
-	uint32_t *sKey = (uint32_t*)sRaw;                               // [kSmallPart]
-	uint16_t *sVal = (uint16_t*)(sRaw + kSmallPart * 4);            // [kSmallPart]
-	uint32_t *sCnt = (uint32_t*)(sRaw + kSmallPart * 6);            // [kSmallWarps][256]
-	__shared__ uint32_t sBase[256];     // where this CTA's keys of digit d start in the sorted sequence
-	__shared__ uint32_t sTot[256];      // this CTA's count of digit d (read by the other CTA)
+	uint32_t *sKey = (uint32_t*)sRaw;                                  // [kSmallSortMax]
+	uint16_t *sVal = (uint16_t*)(sRaw + kSmallSortMax * 4);            // [kSmallSortMax]
+	uint32_t *sCnt = (uint32_t*)(sRaw + kSmallSortMax * 6);            // [kSmallWarps][256]
+	__shared__ uint32_t sBase[256];     // exclusive scan of the digit totals
 	__shared__ uint32_t sWarpSum[8];
 	__shared__ uint32_t sMaxRel, sTotal;
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t part = cluster.block_rank();
-	const uint32_t g = segEffects[blockIdx.x >> 1];
+	const uint32_t g = segEffects[blockIdx.x];
 	EffectState &S = tab.state[g];
 	const uint32_t slots = S.slotCount[S.parity];
 	if (slots > kSmallSortMax) __trap(); // the host routes an effect here only when its slot bound fits
-	const uint32_t numParts = slots > kSmallPart ? 2u : 1u;
-	if (part >= numParts) return;        // (CTA 0 then never touches the cluster barrier)
-	const bool two = numParts == 2;
-	const uint32_t other = part ^ 1u;
-	uint32_t *peerKey = two ? cluster.map_shared_rank(sKey, other) : sKey;
-	uint16_t *peerVal = two ? cluster.map_shared_rank(sVal, other) : sVal;
-	const uint32_t *peerTot = two ? cluster.map_shared_rank(sTot, other) : sTot;
-	const uint32_t *peerMaxRel = two ? cluster.map_shared_rank(&sMaxRel, other) : &sMaxRel;
 	const uint32_t segBase = tab.params[g].slotBase;
 	const uint32_t keyMin = effect_key_min(S);
-	// Positions [0, count) of the current sequence (slots before the first pass, the live keys after it) are cut in
-	// numParts pieces of H = items * 1024: this CTA holds [part * H, part * H + H), warp-striped -- warp w owns
-	// [w * 32 * items, (w + 1) * 32 * items) of the piece, item i of lane l is w * 32 * items + i * 32 + l: ascending in
-	// (warp, item, lane), which is the order ranks are given in.
-	uint32_t items = ((slots + numParts - 1) / numParts + kSmallThreads - 1) / kSmallThreads;
-	uint32_t H = items * kSmallThreads;
+	// the CTA's keys are warp-striped: warp w owns [w * 32 * items, (w + 1) * 32 * items), item i of lane l is
+	// w * 32 * items + i * 32 + l -- ascending in (warp, item, lane), which is the order ranks are given in
+	const uint32_t items = (slots + kSmallThreads - 1) / kSmallThreads;
+	const uint32_t warpBegin = warp * 32 * items;
 
 	if (tid == 0) sMaxRel = 0;
 	__syncthreads();
 
-	uint32_t key[kSmallItems], rank2[(kSmallItems + 1) / 2], val2[(kSmallItems + 1) / 2];
+	uint32_t key[kSmallItems], rank2[kSmallItems / 2], val2[kSmallItems / 2];
 	uint32_t okBits = 0, maxRel = 0;
 	{
 		// all loads first, with no branch between them (one memory round trip for the CTA, not one per item): lane l
 		// fetches the alive word of the warp's item l, every lane its raw keys -- a dead slot's key is stale, not unmapped
-		const uint32_t warpBegin = part * H + warp * 32 * items;
 		const uint32_t *kin = pool.keys + segBase;
 		const uint32_t *mask = pool.aliveMask + (segBase >> 5); // segBase is a multiple of 128
 		uint32_t myWord = 0;
@@ -472,23 +452,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSmallThreads, 1) k_
 	}
 	maxRel = __reduce_max_sync(FULL_MASK, maxRel);
 	if (lane == 0 && maxRel) atomicMax(&sMaxRel, maxRel);
-	if (two) cluster.sync(); else __syncthreads();
-	maxRel = max(sMaxRel, *peerMaxRel);
+	__syncthreads();
+	maxRel = sMaxRel;
 	const uint32_t numPasses = maxRel ? (32u - (uint32_t)__clz(maxRel) + 7u) / 8u : 1u; // pass 0 always runs: it compacts
 
-	uint32_t n = 0; // live keys of the effect; known after pass 0
+	uint32_t n = 0; // live keys; known after pass 0
 	for (uint32_t pass = 0; pass < numPasses; pass++) {
 		const uint32_t shift = pass * 8;
-		// ---- clear the per-warp digit counts and the peer-mask table (aliased onto sKey, idle while the keys are in registers)
-		for (uint32_t i = tid; i < kSmallWarps * 256; i += kSmallThreads) { sCnt[i] = 0; sKey[i] = 0; }
+		// ---- clear the per-warp digit counts and the peer-mask tables (aliased onto sKey, idle while the keys are in registers)
+		for (uint32_t i = tid; i < kSmallWarps * 256; i += kSmallThreads) { sCnt[i] = 0; sKey[i] = 0; sKey[i + kSmallWarps * 256] = 0; }
 		__syncthreads();
-		// ---- rank inside the warp (k_sort_pass's scheme with one table: the leader's clear is fenced by a third __syncwarp)
+		// ---- rank inside the warp (same scheme as k_sort_pass: one shared-memory atomicOr per lane finds the peers)
 		uint32_t *cnt = sCnt + warp * 256;
-		uint32_t *match = sKey + warp * 256;
+		uint32_t *match0 = sKey + warp * 512, *match1 = match0 + 256;
 		const uint32_t ltMask = (1u << lane) - 1u;
 #pragma unroll
 		for (uint32_t i = 0; i < kSmallItems; i++) {
 			if (i >= items) break;
+			uint32_t *match = (i & 1u) ? match1 : match0;
 			const bool ok = (okBits >> i) & 1u;
 			const uint32_t d = (key[i] >> shift) & 255u;
 			if (ok) atomicOr(&match[d], 1u << lane);
@@ -498,45 +479,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSmallThreads, 1) k_
 			__syncwarp();
 			const uint32_t rk = before + __popc(peers & ltMask);
 			if (ok && (peers & ltMask) == 0) { cnt[d] = before + __popc(peers); match[d] = 0; }
-			__syncwarp();
 			if (i & 1u) rank2[i >> 1] |= rk << 16; else rank2[i >> 1] = rk;
 		}
 		__syncthreads();
-		// ---- thread d < 256: exclusive offsets of digit d over this CTA's warps; its total goes where the other CTA reads it
+		// ---- thread d < 256: exclusive offsets of digit d over the warps, then the exclusive scan over the digits
 		uint32_t total = 0;
 		if (tid < 256) {
 #pragma unroll 8
 			for (uint32_t w = 0; w < kSmallWarps; w++) { const uint32_t c = sCnt[w * 256 + tid]; sCnt[w * 256 + tid] = total; total += c; }
-			sTot[tid] = total;
-		}
-		// (also: both CTAs are done ranking, so the key buffers -- peer-mask tables until here -- may be written from either side)
-		if (two) cluster.sync(); else __syncthreads();
-		// ---- digit bases of the whole effect: exclusive scan over the digits of both CTAs' totals; CTA 1's keys of a
-		// digit come behind CTA 0's (its slots are the higher ones)
-		uint32_t theirs = 0;
-		if (tid < 256) {
-			theirs = two ? peerTot[tid] : 0u;
-			const uint32_t both = total + theirs;
-			uint32_t incl = both;
+			uint32_t incl = total;
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += o; }
 			if (lane == 31) sWarpSum[warp] = incl;
-			total = incl - both; // exclusive inside the warp
+			total = incl - total; // exclusive inside the warp
 		}
 		__syncthreads();
 		if (tid < 256) {
 			uint32_t warpBase = 0;
 #pragma unroll
 			for (uint32_t w = 0; w < 8; w++) if (w < warp) warpBase += sWarpSum[w];
-			sBase[tid] = warpBase + total + (part == 1 ? theirs : 0u);
+			sBase[tid] = warpBase + total;
 			if (tid == 255) { uint32_t all = 0; for (uint32_t w = 0; w < 8; w++) all += sWarpSum[w]; sTotal = all; }
 		}
 		__syncthreads();
 		n = sTotal;
-		const uint32_t itemsOut = ((n + numParts - 1) / numParts + kSmallThreads - 1) / kSmallThreads;
-		const uint32_t Hout = itemsOut * kSmallThreads;
-		// ---- permute: position in the sorted sequence = digit base + this warp's offset + rank in the warp; positions
-		// [0, Hout) are CTA 0's shared memory, the rest CTA 1's
+		// ---- permute through shared memory: position = digit base + this warp's offset + rank in the warp
+		// (the peer-mask tables aliased onto sKey are dead since the barrier after the ranking loop)
 #pragma unroll
 		for (uint32_t i = 0; i < kSmallItems; i++) {
 			if (i >= items) break;
@@ -544,35 +512,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSmallThreads, 1) k_
 				const uint32_t d = (key[i] >> shift) & 255u;
 				const uint32_t rk = (i & 1u) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
 				const uint32_t pos = sBase[d] + sCnt[warp * 256 + d] + rk;
-				const uint32_t tgt = pos >= Hout ? 1u : 0u, loc = pos - tgt * Hout;
-				uint32_t *kdst = tgt == part ? sKey : peerKey;
-				uint16_t *vdst = tgt == part ? sVal : peerVal;
-				if (pass + 1 < numPasses) kdst[loc] = key[i]; // after the last pass only the slot order is read
-				vdst[loc] = (uint16_t)((i & 1u) ? (val2[i >> 1] >> 16) : (val2[i >> 1] & 0xffffu));
+				if (pass + 1 < numPasses) sKey[pos] = key[i]; // after the last pass only the slot order is read
+				sVal[pos] = (uint16_t)((i & 1u) ? (val2[i >> 1] >> 16) : (val2[i >> 1] & 0xffffu));
 			}
 		}
-		if (two) cluster.sync(); else __syncthreads();
-		items = itemsOut; H = Hout;
+		__syncthreads();
 		if (pass + 1 == numPasses) break;
-		// ---- back into registers in the new order: this CTA's piece of the live keys
+		// ---- back into registers in the new order; after pass 0 the live keys are the first n
 		okBits = 0;
 #pragma unroll
 		for (uint32_t i = 0; i < kSmallItems; i++) {
 			if (i >= items) break;
-			const uint32_t idx = warp * 32 * items + i * 32 + lane;
-			const bool ok = part * H + idx < n;
+			const uint32_t idx = warpBegin + i * 32 + lane;
+			const bool ok = idx < n;
 			key[i] = ok ? sKey[idx] : 0u;
 			const uint32_t v = ok ? sVal[idx] : 0u;
 			if (i & 1u) val2[i >> 1] |= v << 16; else val2[i >> 1] = v;
 			if (ok) okBits |= 1u << i;
 		}
-		__syncthreads(); // all reads done before the next pass clears the aliased table
+		__syncthreads(); // all reads done before the next pass clears the aliased tables
 	}
-	// ---- the sorted slot list (PoolPtrs::vals: what k_expand_sorted and sprReadStreamSlots read): each CTA its piece
-	uint32_t *vout = pool.vals + segBase + part * H;
-	const uint32_t mine = n > part * H ? min(H, n - part * H) : 0u;
-	for (uint32_t j = tid; j < mine; j += kSmallThreads) vout[j] = sVal[j];
-	if (part == 0 && tid == 0) S.aliveCount = n; // gpuParticles.size / 4 (:670); the tile path writes it in k_sort_scan
+	// ---- the sorted slot list (PoolPtrs::vals: what k_expand_sorted and sprReadStreamSlots read)
+	uint32_t *vout = pool.vals + segBase;
+	for (uint32_t j = tid; j < n; j += kSmallThreads) vout[j] = sVal[j];
+	if (tid == 0) S.aliveCount = n; // gpuParticles.size / 4 (:670); the tile path writes it in k_sort_scan
 }
 
 // One lane per particle: a coalesced read of 32 slot indices, one 256-bit gather of the 32-byte
@@ -707,7 +670,7 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 	if (numSegments > numBigSegments) {
 		// their pass masks stay 0 (cleared with the histograms): k_expand_sorted then reads PoolPtrs::vals
 		T_BEGIN(4);
-		launch_chain(k_sort_small, 2 * (numSegments - numBigSegments), kSmallThreads, kSmallSmemBytes, st, pool, tab, segEffects + numBigSegments); // one cluster of two CTAs per effect
+		launch_chain(k_sort_small, numSegments - numBigSegments, kSmallThreads, kSmallSmemBytes, st, pool, tab, segEffects + numBigSegments);
 		T_END(4);
 		launches++;
 	}
