@@ -170,7 +170,7 @@ struct PlanRec {
 };
 
 // Everything a slot needs to know about its effect in one sub-step, digested by k_emit_warp into
-// one 64-byte record so that the streaming kernels reach their data loads after two dependent
+// one 80-byte record so that the streaming kernels reach their data loads after two dependent
 // loads (granule owner -> this record) instead of seven.
 struct __align__(16) RoundConsts {
 	uint32_t stamp, round;   // valid for this (frame stamp, sub-step round) only

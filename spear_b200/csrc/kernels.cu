@@ -170,9 +170,9 @@ __global__ void k_scatter_words(uint32_t *dst, const uint32_t *idx, const uint32
 
 // One WARP per system. The RNG chain makes the effects of a system sequential, but only the few
 // arithmetic steps of the spawn loop are: each lane first loads everything one effect needs (32
-// effects' dependent global loads in flight at once), then the lanes take turns running the control
-// loop on registers, handing the RNG state to the next lane by shuffle, and finally every lane writes
-// its own plan records and state back in parallel.
+// effects' dependent global loads in flight at once), then the effects that draw take turns in list order -- the whole
+// warp runs a turn, the timer draws of a sub-step side by side, the RNG state it leaves is the next turn's -- and
+// finally every lane writes its own effect's state back in parallel.
 __global__ void __launch_bounds__(128) k_plan(TablePtrs tab, const SystemWork *work, uint32_t numWork, const ActiveEntry *active, uint32_t stamp)
 {
 	pdl_enter();
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(256, (GP || TINY) ? 3 : 4) k_integrate_pass(Po
 	// and the 128 slot records, whose address is a function of the granule alone.
 	// Ownership covers only the slots the effect can have reached, so these loads are rarely wasted -- in the first
 	// sub-step of a frame. Later rounds exist for the few effects that owe more than one sub-step (C5: one effect in
-	// ten): there the round record is looked at first, 64 bytes instead of 4 KB for every effect that is done.
+	// ten): there the round record is looked at first, 80 bytes instead of 4 KB for every effect that is done.
 	if (round != 0) {
 		const uint32_t rStamp = tab.roundConsts[g].stamp, rRound = tab.roundConsts[g].round;
 		if (rStamp != stamp || rRound != round) return;
