@@ -1,15 +1,18 @@
 """TEST INFRASTRUCTURE ONLY: CPU restatement of the reference's particle vertex shader
 (`/root/reference/src/game/shader/Particle.glsl:73-140`, `vs main`), SURVEY.md 8(f) row N2.
 
-Parity status: UNPINNED. The reference has no CPU implementation of its vertex stage and no golden
-vectors for it, and the GLSL cannot be executed in this environment (no GL / no shader compiler), so this
-file is a line-by-line restatement of the shader in numpy float32, checked only against hand-computed
-known answers (tests/test_vertex_stage_oracle.py). Each block cites the shader lines it follows.
-Two things the shader leaves to the implementation are fixed here and in the CUDA kernel alike:
+Parity status: PINNED against the reference's own shader text. There is no GL driver in this environment
+(profiles/r02_probe_gl.md), so the GLSL 3.30 source the reference ships (Particle_vs_source_glsl330,
+src/game/shader/Particle.h:239) is executed on the CPU instead: oracle/glsl/build_glsl_vs.py decodes it out of the
+reference tree and compiles its body unchanged against a small GLSL-semantics header (oracle/glsl/glsl_shim.h) into
+oracle/_ref/libspear_ref_glslvs.so. tests/test_vertex_stage_oracle.py compares this restatement with that library
+(and with tests/golden/vertex_stage.json made from it) plus the hand-computed known answers: every output is
+bit-identical except where cos / sin / pow enter (numpy's float32 kernels against libm: a few ulp).
+What the shader leaves to the implementation is fixed the same way here, in the shim and in the CUDA kernel:
   * mat4 * vec4 is evaluated as ((c0*x + c1*y) + c2*z) + c3*w;
-  * `texture()` with SG_FILTER_LINEAR (ParticleSystem.cpp:287-288) is an exact float lerp of the two
-    neighbouring texels (graphics hardware quantises the weight to 8 bits: up to 1/256 of the
-    difference of two adjacent RGBA8 texels, < 1/255 in any channel).
+  * `texture()` with SG_FILTER_LINEAR (ParticleSystem.cpp:289-290) is the weighted sum of OpenGL 3.3 section 3.8.11
+    with exact float weights at the uv the shader computes from u_SplineMad, UNORM8 texel = c / 255 (graphics
+    hardware quantises the weights to 8 fractional bits: up to 1/256 of the difference of two adjacent texels).
 
 Never imported by the product package (spear_b200); used by tests/ only.
 """
@@ -38,29 +41,38 @@ def srgb_to_linear(x):
     return np.where(x <= F(0.04045), lo, hi).astype(F)
 
 
-def _lut_rows(lut_bytes):
-    lut = np.asarray(lut_bytes, dtype=np.uint8).reshape(2, 64, 4)
-    return lut.astype(F) * F(1.0 / 255.0)
+ATLAS_W, ATLAS_H = 512, 512  # ParticleSystem.cpp:253-258: 64 samples x 8 cells, 256 cells x 2 rows
+
+
+def _unorm(texels):
+    return (np.asarray(texels, dtype=np.uint8).astype(F) / F(255.0)).astype(F)
+
+
+def _weights(a, b):
+    """OpenGL 3.3 section 3.8.11, LINEAR: the four weights of the fractional parts (a, b) of the texel coordinate."""
+    one = F(1)
+    return ((one - a) * (one - b)).astype(F), (a * (one - b)).astype(F), ((one - a) * b).astype(F), (a * b).astype(F)
+
+
+def _bilinear(w, t00, t10, t01, t11):
+    return (((t00 * w[0] + t10 * w[1]) + t01 * w[2]) + t11 * w[3]).astype(F)
 
 
 def _fog_fetch(fog, u, v):
-    """textureLod(u_VisFogTexture, uv, 0).xy: RG8, bilinear, clamp to edge. fog: uint8 array [h, w, 2]."""
+    """textureLod(u_VisFogTexture, uv, 0).xy: RG8, LINEAR, clamp to edge. fog: uint8 array [h, w, 2]."""
     h, w = fog.shape[:2]
-    tex = fog.astype(F) * F(1.0 / 255.0)
-    x = u * F(w) - F(0.5)
-    y = v * F(h) - F(0.5)
+    tex = _unorm(fog)
+    x = (u * F(w) - F(0.5)).astype(F)
+    y = (v * F(h) - F(0.5)).astype(F)
     fx0, fy0 = np.floor(x), np.floor(y)
-    wx, wy = (x - fx0).astype(F), (y - fy0).astype(F)
+    wts = _weights((x - fx0).astype(F), (y - fy0).astype(F))
     x0 = fx0.astype(np.int64); y0 = fy0.astype(np.int64)
     x1, y1 = x0 + 1, y0 + 1
     x0 = np.clip(x0, 0, w - 1); x1 = np.clip(x1, 0, w - 1)
     y0 = np.clip(y0, 0, h - 1); y1 = np.clip(y1, 0, h - 1)
     out = []
     for k in range(2):
-        t00, t10, t01, t11 = tex[y0, x0, k], tex[y0, x1, k], tex[y1, x0, k], tex[y1, x1, k]
-        top = t00 + (t10 - t00) * wx
-        bot = t01 + (t11 - t01) * wx
-        out.append((top + (bot - top) * wy).astype(F))
+        out.append(_bilinear(wts, tex[y0, x0, k], tex[y0, x1, k], tex[y1, x0, k], tex[y1, x1, k]))
     return out[0], out[1]
 
 
@@ -77,6 +89,7 @@ def shade(particles, instance_ubo, type_ubo, lut_bytes, fog=None):
     fog_mad, inv_delta, aspect = I[32:36], I[36], I[37]
     frame_count = (T[0], T[1]); frame_rate_u = T[2]
     rc = T[4:8]; start_frame = T[9]
+    spline_mad = T[12:16]
     scale_base, scale_var, life_base, life_var, rel_frame_rate = T[16], T[17], T[18], T[19], T[20]
     pos, life, vel, seedp = p[:, 0:3], p[:, 3], p[:, 4:7], p[:, 7]
 
@@ -100,15 +113,28 @@ def shade(particles, instance_ubo, type_ubo, lut_bytes, fog=None):
     s = [_fract(np.floor(seedp * F(k)) * F(1.0 / 64.0)).astype(F) for k in (1.0, 1.0 / 64.0, 1.0 / 4096.0, 1.0 / 262144.0)]
     # :89
     wp = [(wp[i] - wv[i] * inv_delta).astype(F) for i in range(3)]
-    # :94-99
-    rows = _lut_rows(lut_bytes)
-    tx = _clamp01(life_time) * F(63)
-    tf = np.floor(tx)
-    i0 = np.minimum(tf.astype(np.int64), 63)
-    i1 = np.minimum(i0 + 1, 63)
-    f = (tx - tf).astype(F)
-    spline = [(rows[0, i0, c] + (rows[0, i1, c] - rows[0, i0, c]) * f).astype(F) for c in range(4)]
-    grad = [(rows[1, i0, c] + (rows[1, i1, c] - rows[1, i0, c]) * f).astype(F) for c in range(3)]
+    # :94-99 texture(u_SplineTexture, splineUv) and the gradient one row below: LINEAR over the 512 x 512 atlas at
+    # the uv the shader computes. Only the type's own cell (2 rows x 64 texels, `lut_bytes`) is held here: rows and
+    # columns are taken relative to the cell, whose first texel centre is u_SplineMad.zw (ParticleSystem.cpp:406-413),
+    # and clamped to it -- a neighbour outside the cell only ever has weight 0.
+    rows = _unorm(lut_bytes).reshape(2, 64, 4)
+    cell_x = int(np.floor(spline_mad[2] * F(ATLAS_W))); cell_y = int(np.floor(spline_mad[3] * F(ATLAS_H)))
+    su = (_clamp01(life_time) * spline_mad[0] + spline_mad[2]).astype(F)
+    sv = F(F(0) * spline_mad[1] + spline_mad[3])
+    gv = F(sv + spline_mad[1])
+    sx = (su * F(ATLAS_W) - F(0.5)).astype(F)
+    sy = F(sv * F(ATLAS_H) - F(0.5)); gy = F(gv * F(ATLAS_H) - F(0.5))
+    sfx = np.floor(sx); sfy = np.floor(sy); gfy = np.floor(gy)
+    c0 = np.clip(sfx.astype(np.int64) - cell_x, 0, 63); c1 = np.clip(sfx.astype(np.int64) + 1 - cell_x, 0, 63)
+    a = (sx - sfx).astype(F)
+
+    def fetch(y, fy):
+        r0 = min(max(int(fy) - cell_y, 0), 1); r1 = min(max(int(fy) + 1 - cell_y, 0), 1)
+        w = _weights(a, np.full_like(a, F(y - fy)))
+        return [_bilinear(w, rows[r0, c0, c], rows[r0, c1, c], rows[r1, c0, c], rows[r1, c1, c]) for c in range(4)]
+
+    spline = fetch(sy, sfy)
+    grad = fetch(gy, gfy)[:3]
     col = [srgb_to_linear(g) for g in grad]
     # :101-107
     scale = scale_base + s[0] * scale_var

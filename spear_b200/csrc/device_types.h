@@ -40,6 +40,8 @@ static const uint32_t kSortTileKeys = SPR_SORT_TILE_KEYS; // keys per CTA in the
 #endif
 static const uint32_t kSmallSortMax = 18432;   // an effect of at most this many slots is sorted by ONE CTA (k_sort_small)
 
+// spline atlas of the vertex stage (ParticleSystem.cpp:253-258): 64 samples per curve, 8 x 256 type cells of 2 rows
+static const uint32_t kSplineSamples = 64, kSplineAtlasTypesX = 8, kSplineAtlasTypesY = 256, kSplineRowsPerType = 2;
 static const float kHugeLife = 1e20f;          // ParticleSystem.cpp:27
 static const float kHugeLifeCmp = 1e19f;       // ParticleSystem.cpp:28
 

@@ -184,7 +184,8 @@ inline void bakeTypeUbo(SprVertexTypeUbo &u, uint32_t typeId, const SprParticleS
 	u.u_RotationControl.z = c.spin * kDegToRad;
 	u.u_RotationControl.w = c.spinVariance * kDegToRad;
 	if (c.randomStartFrame) u.u_StartFrame = 1.0f;
-	const uint32_t atlasHeight = 256, atlasWidth = 8, rowsPerType = 2;
+	const uint32_t atlasHeight = kSplineAtlasTypesY, atlasWidth = kSplineAtlasTypesX, rowsPerType = kSplineRowsPerType;
+	static_assert(SPR_SPLINE_SAMPLE_RATE == kSplineSamples, "one sample rate");
 	const float resX = (float)(SPR_SPLINE_SAMPLE_RATE * atlasWidth), resY = (float)(atlasHeight * rowsPerType);
 	uint32_t px = (typeId / atlasHeight) * SPR_SPLINE_SAMPLE_RATE, py = (typeId % atlasHeight) * rowsPerType;
 	u.u_SplineMad.x = (float)(SPR_SPLINE_SAMPLE_RATE - 1) / resX;

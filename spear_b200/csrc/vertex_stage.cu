@@ -12,10 +12,14 @@
 //   type (ParticleSystem.cpp:326-400) are staged in shared memory, the type and instance UBOs
 //   (:312-321, :410-419, :871-876) come from the job table.
 //
-// Texture filtering is restated in float: the spline atlas is sampled with SG_FILTER_LINEAR
-// (:287-288) at u = clamp(lifeTime) * 63/512 + (x + 0.5)/512 (:403-413), i.e. at texel coordinate
-// x + 63 * clamp(lifeTime) of the type's row: lerp of texels floor and floor + 1. Graphics hardware
-// quantises the lerp weight to 8 bits; this kernel (and its oracle, oracle/vertex_stage.py) do not.
+// Texture filtering follows OpenGL 3.3 section 3.8.11 (LINEAR, the filter of both images: ParticleSystem.cpp:289-290,
+// VisFogSystem.cpp:74-75) in float: texel coordinate u * width - 1/2, weights (1-a)(1-b), a(1-b), (1-a)b, ab with
+// a, b its fractional parts, UNORM8 texel = c / 255. The spline atlas is sampled at the uv the shader computes from
+// u_SplineMad (:403-413); the kernel holds only the type's own two rows, which is all such a uv can reach with a
+// non-zero weight (the row coordinate is an exact texel centre). Graphics hardware quantises the weights to 8
+// fractional bits; this kernel and its oracles do not. Pinned against the reference's shipped GLSL 3.30 text
+// executed on the CPU (oracle/glsl/, tests/test_gpu_vertex_stage.py): bit-identical except where cos / sin / pow
+// enter (gl_Position.xy, v_Color.rgb).
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,37 +46,50 @@ __device__ __forceinline__ void st256(float4 *p, const float4 &a, const float4 &
 		:: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
 }
 
-// lerp of two RGBA8 texels, channel c, as unorm floats
-__device__ __forceinline__ float lut_channel(uint32_t t0, uint32_t t1, int c, float f)
+// The four LINEAR weights of a texel coordinate pair (OpenGL 3.3, 3.8.11) and the weighted sum in the order the
+// specification writes it: tau = (1-a)(1-b) t00 + a(1-b) t10 + (1-a)b t01 + ab t11.
+struct BilinearWeights { float w00, w10, w01, w11; };
+__device__ __forceinline__ BilinearWeights bilinear_weights(float a, float b)
 {
-	float a = (float)((t0 >> (8 * c)) & 255u) * (1.0f / 255.0f);
-	float b = (float)((t1 >> (8 * c)) & 255u) * (1.0f / 255.0f);
-	return a + (b - a) * f;
+	BilinearWeights w;
+	w.w00 = (1.0f - a) * (1.0f - b); w.w10 = a * (1.0f - b); w.w01 = (1.0f - a) * b; w.w11 = a * b;
+	return w;
 }
+__device__ __forceinline__ float bilinear(const BilinearWeights &w, float t00, float t10, float t01, float t11)
+{
+	return ((t00 * w.w00 + t10 * w.w10) + t01 * w.w01) + t11 * w.w11;
+}
+// UNORM8 -> float: v / 255 correctly rounded, without the division: q = v * (1/255) is off by at most one ulp, one
+// Newton step on the remainder (two FMAs) lands on the IEEE quotient -- equal to v / 255.0f for all 256 values of v
+// (checked exhaustively on the host: tests/test_abi.py::test_unorm8_division_free).
+__device__ __forceinline__ float unorm8(uint32_t v)
+{
+	const float r = 1.0f / 255.0f;
+	const float x = (float)v, q = x * r;
+	return __fmaf_rn(__fmaf_rn(-q, 255.0f, x), r, q);
+}
+__device__ __forceinline__ float texel_channel(uint32_t t, int c) { return unorm8((t >> (8 * c)) & 255u); }
 
-// bilinear fetch of an RG8 image with clamp-to-edge addressing; returns (r, g) as unorm floats
+// LINEAR fetch of an RG8 image with clamp-to-edge addressing; returns (r, g)
 __device__ inline float2 fog_fetch(const uint8_t *texels, uint32_t w, uint32_t h, float u, float v)
 {
 	float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
 	float fx0 = floorf(x), fy0 = floorf(y);
-	float wx = x - fx0, wy = y - fy0;
+	const BilinearWeights bw = bilinear_weights(x - fx0, y - fy0);
 	int x0 = (int)fx0, y0 = (int)fy0;
 	int x1 = x0 + 1, y1 = y0 + 1;
 	x0 = min(max(x0, 0), (int)w - 1); x1 = min(max(x1, 0), (int)w - 1);
 	y0 = min(max(y0, 0), (int)h - 1); y1 = min(max(y1, 0), (int)h - 1);
-	float2 r;
 	float c[2];
 #pragma unroll
 	for (int k = 0; k < 2; k++) {
-		float t00 = (float)texels[2 * ((size_t)y0 * w + x0) + k] * (1.0f / 255.0f);
-		float t10 = (float)texels[2 * ((size_t)y0 * w + x1) + k] * (1.0f / 255.0f);
-		float t01 = (float)texels[2 * ((size_t)y1 * w + x0) + k] * (1.0f / 255.0f);
-		float t11 = (float)texels[2 * ((size_t)y1 * w + x1) + k] * (1.0f / 255.0f);
-		float top = t00 + (t10 - t00) * wx, bot = t01 + (t11 - t01) * wx;
-		c[k] = top + (bot - top) * wy;
+		float t00 = unorm8(texels[2 * ((size_t)y0 * w + x0) + k]);
+		float t10 = unorm8(texels[2 * ((size_t)y0 * w + x1) + k]);
+		float t01 = unorm8(texels[2 * ((size_t)y1 * w + x0) + k]);
+		float t11 = unorm8(texels[2 * ((size_t)y1 * w + x1) + k]);
+		c[k] = bilinear(bw, t00, t10, t01, t11);
 	}
-	r.x = c[0]; r.y = c[1];
-	return r;
+	return make_float2(c[0], c[1]);
 }
 
 __global__ void __launch_bounds__(256) k_shade_vertices(const float4 *vertices, const ShadeJob *jobs, uint32_t numJobs,
@@ -127,6 +144,7 @@ __global__ void __launch_bounds__(256) k_shade_vertices(const float4 *vertices, 
 	const float frameCountX = T[0], frameCountY = T[1], frameRateU = T[2];
 	const float rc0 = T[4], rc1 = T[5], rc2 = T[6], rc3 = T[7];
 	const float startFrame = T[9];
+	const float splineMadX = T[12], splineMadY = T[13], splineMadZ = T[14], splineMadW = T[15];
 	const float scaleBase = T[16], scaleVar = T[17], lifeBase = T[18], lifeVar = T[19], relFrameRate = T[20];
 
 	// :82-87
@@ -142,17 +160,43 @@ __global__ void __launch_bounds__(256) k_shade_vertices(const float4 *vertices, 
 	// :89
 	px -= vx * invDelta; py -= vy * invDelta; pz -= vz * invDelta;
 
-	// :94-99 LUT rows 0 (spline) and 1 (gradient) at texel coordinate 63 * clamp(lifeTime)
-	const float tx = clamp01(lifeTime) * 63.0f;
-	const float tf = floorf(tx);
-	const uint32_t i0 = min((uint32_t)tf, 63u), i1 = min(i0 + 1u, 63u);
-	const float f = tx - tf;
-	const uint32_t a0 = sLut[i0], a1 = sLut[i1], g0 = sLut[64 + i0], g1 = sLut[64 + i1];
-	const float splX = lut_channel(a0, a1, 0, f), splY = lut_channel(a0, a1, 1, f);
-	const float splZ = lut_channel(a0, a1, 2, f), splW = lut_channel(a0, a1, 3, f);
-	float cr = srgb_to_linear(lut_channel(g0, g1, 0, f));
-	float cg = srgb_to_linear(lut_channel(g0, g1, 1, f));
-	float cb = srgb_to_linear(lut_channel(g0, g1, 2, f));
+	// :94-99 texture(u_SplineTexture, splineUv) and the gradient one row below, LINEAR over the 512 x 512 atlas
+	// (ParticleSystem.cpp:253-258). The type's cell starts at the texel whose centre is u_SplineMad.zw (:406-413);
+	// rows and columns are taken relative to it and clamped to the cell -- a neighbour outside it only ever has
+	// weight 0 (column 64 at lifeTime = 1, the row under the gradient).
+	const float kAtlasW = (float)(kSplineSamples * kSplineAtlasTypesX), kAtlasH = (float)(kSplineAtlasTypesY * kSplineRowsPerType);
+	const int cellX = (int)floorf(splineMadZ * kAtlasW), cellY = (int)floorf(splineMadW * kAtlasH);
+	const float su = clamp01(lifeTime) * splineMadX + splineMadZ;
+	const float sv = 0.0f * splineMadY + splineMadW;
+	const float gv = sv + splineMadY;                                 // splineUv + vec2(0, u_SplineMad.y)
+	const float sx = su * kAtlasW - 0.5f, sy = sv * kAtlasH - 0.5f, gy = gv * kAtlasH - 0.5f;
+	const float sfx = floorf(sx), sfy = floorf(sy), gfy = floorf(gy);
+	const int c0 = min(max((int)sfx - cellX, 0), 63), c1 = min(max((int)sfx + 1 - cellX, 0), 63);
+	const int sr0 = min(max((int)sfy - cellY, 0), 1), sr1 = min(max((int)sfy + 1 - cellY, 0), 1);
+	const int gr0 = min(max((int)gfy - cellY, 0), 1), gr1 = min(max((int)gfy + 1 - cellY, 0), 1);
+	const float ca = sx - sfx, sb = sy - sfy, gb = gy - gfy;
+	float splX, splY, splZ, splW, cr, cg, cb;
+	if (sb == 0.0f && gb == 0.0f) {
+		// The row coordinate is an exact texel centre (always, for a UBO built as :406-413 builds it; uniform over the
+		// grid's job): the lower row's weights are (1-a) * 0 and a * 0, its terms add +0 to a non-negative sum, and the
+		// upper row's weights are (1-a) * 1 and a * 1. Same bits as the four-texel sum below with half the fetches.
+		const float w0 = 1.0f - ca, w1 = ca;
+		const uint32_t s0t = sLut[sr0 * 64 + c0], s1t = sLut[sr0 * 64 + c1], g0t = sLut[gr0 * 64 + c0], g1t = sLut[gr0 * 64 + c1];
+#define SPR_SAMPLE2(t0, t1, c) (texel_channel(t0, c) * w0 + texel_channel(t1, c) * w1)
+		splX = SPR_SAMPLE2(s0t, s1t, 0); splY = SPR_SAMPLE2(s0t, s1t, 1); splZ = SPR_SAMPLE2(s0t, s1t, 2); splW = SPR_SAMPLE2(s0t, s1t, 3);
+		cr = SPR_SAMPLE2(g0t, g1t, 0); cg = SPR_SAMPLE2(g0t, g1t, 1); cb = SPR_SAMPLE2(g0t, g1t, 2);
+#undef SPR_SAMPLE2
+	} else {
+		const BilinearWeights sw = bilinear_weights(ca, sb), gw = bilinear_weights(ca, gb);
+		const uint32_t s00 = sLut[sr0 * 64 + c0], s10 = sLut[sr0 * 64 + c1], s01 = sLut[sr1 * 64 + c0], s11 = sLut[sr1 * 64 + c1];
+		const uint32_t g00 = sLut[gr0 * 64 + c0], g10 = sLut[gr0 * 64 + c1], g01 = sLut[gr1 * 64 + c0], g11 = sLut[gr1 * 64 + c1];
+#define SPR_SAMPLE(w, t00, t10, t01, t11, c) bilinear(w, texel_channel(t00, c), texel_channel(t10, c), texel_channel(t01, c), texel_channel(t11, c))
+		splX = SPR_SAMPLE(sw, s00, s10, s01, s11, 0); splY = SPR_SAMPLE(sw, s00, s10, s01, s11, 1);
+		splZ = SPR_SAMPLE(sw, s00, s10, s01, s11, 2); splW = SPR_SAMPLE(sw, s00, s10, s01, s11, 3);
+		cr = SPR_SAMPLE(gw, g00, g10, g01, g11, 0); cg = SPR_SAMPLE(gw, g00, g10, g01, g11, 1); cb = SPR_SAMPLE(gw, g00, g10, g01, g11, 2);
+#undef SPR_SAMPLE
+	}
+	cr = srgb_to_linear(cr); cg = srgb_to_linear(cg); cb = srgb_to_linear(cb);
 
 	// :101-107
 	float scale = scaleBase + s0 * scaleVar;

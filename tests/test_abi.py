@@ -97,3 +97,29 @@ def test_bake_many_type_ids(particles):
         assert ubo.u_SplineMad.x == 63.0 / 512.0 and ubo.u_SplineMad.y == 1.0 / 512.0
         assert ubo.u_SplineMad.z == ((t // 256) * 64 + 0.5) / 512.0
         assert ubo.u_SplineMad.w == ((t % 256) * 2 + 0.5) / 512.0
+
+
+def _round_f32(fr):
+    """the float32 nearest to the exact rational `fr` (ties to even) -- one rounding, as an FMA does"""
+    from fractions import Fraction
+    c = np.float32(float(fr))
+    best = None
+    for cand in (np.nextafter(c, np.float32(-np.inf)), c, np.nextafter(c, np.float32(np.inf))):
+        err = abs(Fraction(float(cand)) - fr)
+        even = (int(np.float32(cand).view(np.uint32)) & 1) == 0
+        if best is None or err < best[0] or (err == best[0] and even):
+            best = (err, cand)
+    return np.float32(best[1])
+
+
+def test_unorm8_division_free():
+    """spear_b200/csrc/vertex_stage.cu unorm8(): q = v * (1/255), then fma(fma(-q, 255, v), 1/255, q) must be the
+    IEEE quotient v / 255 for every 8-bit v (what GL's UNORM8 -> float conversion and oracle/glsl/glsl_shim.h compute)."""
+    from fractions import Fraction
+    r = np.float32(1.0) / np.float32(255.0)
+    for v in range(256):
+        x = np.float32(v)
+        q = np.float32(x * r)
+        rem = _round_f32(Fraction(float(x)) - Fraction(float(q)) * 255)
+        got = _round_f32(Fraction(float(rem)) * Fraction(float(r)) + Fraction(float(q)))
+        assert got == np.float32(x / np.float32(255.0)), v

@@ -1,9 +1,11 @@
-"""GPU: sprShadeVertices (spear_b200/csrc/vertex_stage.cu) against the numpy restatement of
-Particle.glsl `vs` (oracle/vertex_stage.py) on the draw records of a rendered frame.
+"""GPU: sprShadeVertices (spear_b200/csrc/vertex_stage.cu) on the draw records of a rendered frame
+against (1) the reference's SHIPPED GLSL 3.30 vertex shader executed on the CPU (oracle/_ref/libspear_ref_glslvs.so:
+Particle_vs_source_glsl330 of src/game/shader/Particle.h:239 through oracle/glsl/glsl_shim.h, sampling the 512 x 512
+spline atlas the reference builds) and (2) the numpy restatement of Particle.glsl `vs` (oracle/vertex_stage.py).
 
-Tolerance (stated, floating point): everything the shader computes with IEEE add / mul / div only -- flip-book
-uvs, frame blend, additive, erosion, alpha, the dead-quad collapse -- must be bit-identical (the library is built
-with -fmad=false); gl_Position and the gradient colour go through cos / sin / pow, whose CUDA and numpy
+Tolerance (stated, floating point): everything the shader computes with IEEE add / mul / div only -- gl_Position.zw,
+flip-book uvs, frame blend, alpha, additive, erosion, the dead-quad collapse -- must be bit-identical (the library is
+built with -fmad=false); gl_Position.xy and the gradient colour go through cos / sin / pow, whose CUDA, libm and numpy
 implementations differ by a few ulp: |a - b| <= 2e-5 * max(1, |b|)."""
 import ctypes as C
 
@@ -11,6 +13,7 @@ import numpy as np
 import pytest
 
 import scenarios as S
+from oracle import glsl_vs as G
 from oracle import vertex_stage as VS
 from spear_b200 import abi
 from tests_render_args import make_render_args
@@ -71,6 +74,8 @@ def test_shade_vertices_matches_glsl_restatement(sort, with_fog):
             fog_t = torch.from_numpy(fog_np).cuda()
             fog = abi.FogImage(fog_t.data_ptr(), 32, 24)
         dead_quads = 0
+        shader_checked = 0
+        atlas = None
         # several frames with varying dt: u_InvDelta = timeStep - timeDelta changes every frame, and with it which
         # of the particles in their last step collapse (lifeLeft <= 0, Particle.glsl:113-115)
         for f in range(40, 52):
@@ -92,15 +97,26 @@ def test_shade_vertices_matches_glsl_restatement(sort, with_fog):
                 typ = np.frombuffer(bytes(s.type_ubo(r.typeId)), dtype=np.float32)[:24]
                 want = VS.shade(stream[::4], inst, typ, s.type_lut(r.typeId), fog=fog_np)
                 g = got[v0:v0 + 4 * r.numParticles]
-                exact_cols = [4, 5, 6, 7, 11, 12, 13, 14, 15]   # uv0, uv1, alpha, frameD, additive, erode, 0
+                exact_cols = [2, 3, 4, 5, 6, 7, 11, 12, 13, 14, 15]   # gl_Position.zw, uv0, uv1, alpha, frameD, additive, erode, 0
                 assert np.array_equal(g[:, exact_cols].view(np.uint32), want[:, exact_cols].view(np.uint32)), "frame %d effect %d: IEEE-only outputs differ" % (f, r.effectId)
                 ok = _close(g, want)
                 assert ok.all(), "frame %d effect %d: %d of %d floats off, worst %g" % (f, r.effectId, (~ok).sum(), ok.size, np.abs(g - want).max())
+                if G.have():
+                    # the reference's own shader text, sampling the atlas with every live type in its cell
+                    if atlas is None:
+                        atlas = G.atlas_from_luts({rr.typeId: s.type_lut(rr.typeId) for rr in recs})
+                    ref = G.shade(stream[::4], inst, typ, atlas, fog_np)
+                    assert np.array_equal(g[:, exact_cols].view(np.uint32), ref[:, exact_cols].view(np.uint32)), "frame %d effect %d: IEEE-only outputs differ from the executed GLSL" % (f, r.effectId)
+                    ok = _close(g, ref)
+                    assert ok.all(), "frame %d effect %d against the executed GLSL: %d floats off, worst %g" % (f, r.effectId, (~ok).sum(), np.abs(g - ref).max())
+                    shader_checked += 1
                 dead = np.all(want[:, 0:4] == 0.0, axis=1)
                 assert np.array_equal(np.all(g[:, 0:4] == 0.0, axis=1), dead)
                 dead_quads += int(dead.sum()) // 4
                 v0 += 4 * r.numParticles
         assert dead_quads > 0, "the scene should contain particles in their last step (collapsed quads)"
+        # oracle/_ref travels with the snapshot: on the GPU box the executed shader must have been the checker
+        assert shader_checked == 36 or not G.have()
     finally:
         ctx.close()
 

@@ -1,9 +1,24 @@
-"""CPU: known answers for oracle/vertex_stage.py (the numpy restatement of Particle.glsl `vs`,
-src/game/shader/Particle.glsl:73-140). The reference has no CPU code or golden vectors for its
-vertex stage, so these hand-computed cases are what the restatement is checked against."""
-import numpy as np
+"""CPU: oracle/vertex_stage.py (the numpy restatement of Particle.glsl `vs`, src/game/shader/Particle.glsl:73-140)
+against the reference's SHIPPED GLSL 3.30 text executed on the CPU (oracle/glsl/: Particle_vs_source_glsl330 of
+src/game/shader/Particle.h:239 compiled against a GLSL-semantics header; golden vectors of that run in
+tests/golden/vertex_stage.json), and against hand-computed known answers.
 
+Tolerance (floating point, stated): every output is bit-identical to the executed shader except gl_Position.xy
+(cos / sin of the rotation) and v_Color.rgb (pow of the sRGB decode), where numpy's float32 kernels and libm differ
+by a few ulp: |a - b| <= 4e-6 * max(1, |b|)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import glsl_vs as G
 from oracle import vertex_stage as VS
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vertex_stage.json")
+TRANSCENDENTAL_COLS = [0, 1, 8, 9, 10]   # gl_Position.xy, v_Color.rgb
+EXACT_COLS = [c for c in range(16) if c not in TRANSCENDENTAL_COLS]
 
 F = np.float32
 IDENT = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
@@ -16,6 +31,7 @@ def _instance(inv_delta=0.0, aspect=0.5, p2w=IDENT, w2c=IDENT, fog_mad=(0, 0, 0,
 def _type(frame_count=(1, 1), frame_rate=0.0, rot=(0, 0, 0, 0), start_frame=0.0, scale=(2.0, 0.0), life=(4.0, 0.0), rel=0.0):
     t = np.zeros(24, dtype=F)
     t[0:2] = frame_count; t[2] = frame_rate; t[4:8] = rot; t[9] = start_frame
+    t[12:16] = (F(63) / F(512), F(1) / F(512), F(0.5) / F(512), F(0.5) / F(512))   # u_SplineMad of type 0 (ParticleSystem.cpp:406-413)
     t[16:18] = scale; t[18:20] = life; t[20] = rel
     return t
 
@@ -109,3 +125,73 @@ def test_vis_fog():
     fog[0, 0] = (114, 255)       # 114/255 = 0.447 < 0.45 -> t = 0 -> black
     out = VS.shade(_particle(), _instance(fog_mad=(0.1, 0.1, 0.5, 0.5)), _type(), _lut(), fog=fog)
     assert out[0, 8] == 0.0 and out[0, 11] == 1.0   # alpha is not fogged
+
+
+def _hex(h, dtype, shape=None):
+    a = np.frombuffer(bytes.fromhex(h), dtype=dtype)
+    return a.reshape(shape) if shape else a
+
+
+def _golden_cases():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+def _case_inputs(c):
+    fog = None if c["fog"] is None else _hex(c["fog"]["texels"], np.uint8, (c["fog"]["height"], c["fog"]["width"], 2))
+    return (_hex(c["particles"], F, (c["num_particles"], 8)), _hex(c["instance_ubo"], F), _hex(c["type_ubo"], F), _hex(c["lut"], np.uint8), fog,
+            _hex(c["vertices"], F, (4 * c["num_particles"], 16)))
+
+
+def _assert_matches_shader(got, want, what):
+    assert np.array_equal(got[:, EXACT_COLS].view(np.uint32), want[:, EXACT_COLS].view(np.uint32)), "%s: an IEEE-only output differs from the executed shader" % what
+    ok = np.abs(got - want) <= 4e-6 * np.maximum(1.0, np.abs(want))
+    assert ok.all(), "%s: %d floats off, worst %g" % (what, (~ok).sum(), np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_restatement_matches_golden_of_the_executed_shader(idx):
+    doc = _golden_cases()
+    c = doc["cases"][idx]
+    p, inst, typ, lut, fog, want = _case_inputs(c)
+    got = VS.shade(p, inst, typ, lut, fog=fog)
+    _assert_matches_shader(got, want, c["name"])
+    # the cases cover the dead-quad collapse, both erosion branches and the clamped ends of the curve
+    if idx == 0:
+        all_want = np.concatenate([_case_inputs(k)[5] for k in doc["cases"]])
+        assert (np.all(all_want[:, 0:4] == 0.0, axis=1)).any() and (all_want[:, 14] == 1.0).any() and (all_want[:, 14] == 100.0).any()
+
+
+@pytest.mark.skipif(not G.have(), reason="oracle/_ref/libspear_ref_glslvs.so not built (needs /root/reference)")
+def test_executed_shader_reproduces_golden_and_is_the_shipped_text():
+    doc = _golden_cases()
+    src = G.source()
+    assert src.startswith("#version 330") and "a_PositionLife" in src and "u_SplineTexture" in src
+    assert hashlib.sha256(src.encode("ascii")).hexdigest() == doc["shader_sha256"] and len(src) == doc["shader_bytes"]
+    for c in doc["cases"]:
+        p, inst, typ, lut, fog, want = _case_inputs(c)
+        atlas = G.atlas_from_luts({c["type_id"]: lut})
+        got = G.shade(p, inst, typ, atlas, fog)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), c["name"]
+
+
+@pytest.mark.skipif(not G.have(), reason="oracle/_ref/libspear_ref_glslvs.so not built (needs /root/reference)")
+@pytest.mark.parametrize("type_id", [0, 255, 256, 1300, 2047])
+def test_restatement_matches_executed_shader_on_random_input(type_id):
+    rng = np.random.default_rng(type_id + 1)
+    n = 4000
+    lut = rng.integers(0, 256, size=512, dtype=np.uint8)          # worst case: neighbouring texels differ by up to 1.0
+    atlas = G.atlas_from_luts({type_id: lut, (type_id + 1) % 2048: rng.integers(0, 256, size=512, dtype=np.uint8),
+                               (type_id + 2047) % 2048: rng.integers(0, 256, size=512, dtype=np.uint8)})
+    p = np.zeros((n, 8), dtype=F)
+    p[:, 0:3] = rng.normal(0, 5, (n, 3)); p[:, 3] = rng.uniform(-0.05, 1.0, n)
+    p[:, 4:7] = rng.normal(0, 2, (n, 3)); p[:, 7] = np.floor(rng.uniform(0, 1 << 24, n))
+    p[:40, 3] = 1.0; p[40:80, 3] = 0.0
+    inst = np.zeros(40, dtype=F)
+    inst[0:16] = rng.normal(0, 1, 16); inst[16:32] = rng.normal(0, 1, 16)
+    inst[32:36] = (0.02, 0.03, 0.4, 0.3); inst[36] = 0.004; inst[37] = 0.5625
+    typ = _type(frame_count=(4, 2), frame_rate=12.0, rot=(0.5, 3.1, 1.5, 0.8), start_frame=1.0, scale=(0.6, 0.4), life=(0.8, F(0.5) * F(1 / 16777216.0)), rel=0.3)
+    typ[14] = (F((type_id // 256) * 64) + F(0.5)) / F(512); typ[15] = (F((type_id % 256) * 2) + F(0.5)) / F(512)
+    fog = rng.integers(0, 256, size=(24, 32, 2), dtype=np.uint8)
+    for fg in (None, fog):
+        _assert_matches_shader(VS.shade(p, inst, typ, lut, fog=fg), G.shade(p, inst, typ, atlas, fg), "type %d fog %s" % (type_id, fg is not None))
