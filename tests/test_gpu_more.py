@@ -263,9 +263,14 @@ def test_sorted_small_effects_one_cta_path(oracle_port):
                                emitPosition=dict(boxExtent=(3, 1, 3)), emitVelocity=dict(sphere=dict(minRadius=0.5, maxRadius=2.0))),
             abi.make_component(burstAmount=4000, spawnTime=0.002, lifeTime=0.1, lifeTimeVariance=0.2, drag=0.1, gravity=(0, -9.81, 0), timeStep=1 / 60,
                                emitPosition=dict(boxExtent=(3, 1, 3)), emitVelocity=dict(sphere=dict(minRadius=0.5, maxRadius=2.0))),
+            # a ball seen from outside: the depth histogram is a hump (full middle digits, thin ends), 3 significant bytes
+            abi.make_component(burstAmount=15000, emitPosition=dict(sphere=dict(minRadius=0.0, maxRadius=6.0)), **still),
+            # a few hundred keys spread over 3 bytes: most digit bins empty in every pass
+            abi.make_component(burstAmount=300, emitPosition=dict(boxExtent=(4, 2, 4)), **still),
         ]
         trs = [abi.make_transform((1, 2, 3)), abi.make_transform((300, 2, 3)), abi.make_transform((1, 2, 3)), abi.make_transform(CAMERA),
-               abi.make_transform((5, 2, 3)), abi.make_transform((-4, 1, 6)), abi.make_transform((9, 1, -6))]
+               abi.make_transform((5, 2, 3)), abi.make_transform((-4, 1, 6)), abi.make_transform((9, 1, -6)), abi.make_transform((-20, 3, 25)),
+               abi.make_transform((30, 0, 10))]
         sseed = (1, 91, 3, 4)
         s, o = ctx.create_system(sseed), orc.OracleSystem(oracle_port, sseed)
         ids = [s.add_effect(c, t) for c, t in zip(comps, trs)]
