@@ -29,7 +29,10 @@ namespace spr {
 
 #define FULL_MASK 0xffffffffu
 
-static const uint32_t kItemsPerThread = 16;                           // keys per thread of a pass CTA
+#ifndef SPR_SORT_ITEMS
+#define SPR_SORT_ITEMS 16
+#endif
+static const uint32_t kItemsPerThread = SPR_SORT_ITEMS;               // keys per thread of a pass CTA
 static const uint32_t kSortThreads = kSortTileKeys / kItemsPerThread; // 256 threads for 4096-key tiles, 512 for 8192
 static const uint32_t kSortWarps = kSortThreads / 32;
 static const uint32_t kWarpKeys = 32 * kItemsPerThread;               // 512 keys per warp
@@ -37,7 +40,11 @@ static const uint32_t kHistItems = kSortTileKeys / 256;               // keys pe
 static const uint32_t kExpandPerTile = kSortTileKeys / 1024;          // k_expand_sorted CTAs per sort tile
 static const uint32_t kLook = 8;                                      // status words fetched per look-back batch
 static const size_t kPassSmemBytes = (2 * kSortTileKeys + kSortWarps * 256) * sizeof(uint32_t); // keys, values, per-warp digit counts
+#ifndef SPR_SORT_MIN_CTAS
+#define SPR_SORT_MIN_CTAS (1024 / kSortThreads)
+#endif
 static_assert(kSortThreads >= 256 && kSortThreads <= 1024 && kHistItems <= 32, "sort tile: 4096 to 16384 keys");
+static_assert(kSortWarps * 512 <= 2 * kSortTileKeys, "the per-warp peer-mask tables alias the key / value staging buffers");
 
 __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t *hist)
 {
@@ -142,7 +149,7 @@ __device__ unsigned long long g_sortProf[16];
 #endif
 
 template <bool FIRST>
-__global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
+__global__ void __launch_bounds__(kSortThreads, SPR_SORT_MIN_CTAS) k_sort_pass(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	uint32_t *keys0, uint32_t *vals0, uint32_t *keys1, uint32_t *vals1,
 	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t *ticket, uint32_t pass)
 {
@@ -190,8 +197,8 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass
 #ifdef SPR_SORT_PROFILE
 	long long profT = clock64();
 #endif
-	// per-warp digit counts and the two per-warp peer-mask tables (aliased onto sVals, idle until staging)
-	for (uint32_t i = tid; i < kSortWarps * 256; i += kSortThreads) { sCnt[i] = 0; sVals[i] = 0; sVals[i + kSortWarps * 256] = 0; }
+	// per-warp digit counts and the two per-warp peer-mask tables (aliased onto sKeys / sVals, idle until staging)
+	for (uint32_t i = tid; i < kSortWarps * 256; i += kSortThreads) { sCnt[i] = 0; sPassDyn[i] = 0; sPassDyn[i + kSortWarps * 256] = 0; }
 	__syncthreads();
 	PROF_T(0);
 
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads) k_sort_pass
 	// the leader clears its entry after reading it, and two __syncwarp()s pass before its next use.
 	// (two keys per round through four tables -- half the warp barriers -- was measured 4 % slower:
 	// profiles/r02_sort_experiments.md)
-	uint32_t *match0 = sVals + warp * 512, *match1 = match0 + 256;
+	uint32_t *match0 = sPassDyn + warp * 512, *match1 = match0 + 256;
 #pragma unroll
 	for (uint32_t i = 0; i < kItemsPerThread; i++) {
 		uint32_t *match = (i & 1u) ? match1 : match0;
