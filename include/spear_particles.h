@@ -637,6 +637,15 @@ SPR_API int sprExpandFromPeers(SprContext *ctx, void *const *bufferPtrs, uint32_
  * context / stream under the next frame's simulation gives it a small share and leaves the rest of every SM to the
  * simulation kernels (bench.py: gather.fused_overlapped). */
 SPR_API int sprContextSetAssemblyShare(SprContext *ctx, uint32_t ctasPerSm);
+/* Deferred expansion (SPR_CTX_SORT_PARTICLES contexts only, else SPR_ERR_UNSUPPORTED), for pipelines whose consumer is the
+ * ASSEMBLED draw stream (sprPackRuns / sprRunBufferPack -> sprExpandRuns / sprExpandFromPeers), which contains this
+ * GPU's shard too: while on, sprUpdateParticles[Batch] emits, integrates, compacts and sorts as always but does not write
+ * the local 4x vertex stream, and the pack calls gather the sorted 32-byte records from the slot state (same bytes in
+ * the run). The local stream -- SprDrawRecord::vertexByteOffset, sprReadVertexStream, sprShadeVertices -- is stale for
+ * effects updated while it is on (effects that fit one 128-slot granule still write theirs); everything else (counts,
+ * bounds, free lists, sprReadStreamSlots) is as always. Saves the 128 bytes per particle the local expansion writes
+ * and the strided read of the pack: bench.py gather.fused_deferred. */
+SPR_API int sprContextSetDeferredExpansion(SprContext *ctx, int on);
 
 #ifdef __cplusplus
 }

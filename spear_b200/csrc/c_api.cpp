@@ -460,7 +460,7 @@ SPR_API int sprPackRuns(SprContext *c, SprSystem *const *systems, const uint32_t
 		SPR_CUDA(cudaMemcpyAsync(ctx->gatherIdxD.ptr, globals.data(), numEffects * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		launch_run_offsets(ctx->stream, ctx->tablePtrs(), ctx->gatherIdxD.ptr, numEffects, ctx->dRunOffsets.ptr, deviceCounts);
 		launch_pack_runs(ctx->stream, ctx->poolPtrs(), ctx->tablePtrs(), ctx->gatherIdxD.ptr, numEffects, ctx->dRunOffsets.ptr,
-			(float4*)deviceOut, capacityRecords, ctx->numSms);
+			(float4*)deviceOut, capacityRecords, ctx->numSms, ctx->deferExpansion);
 		ctx->launchCount += 2;
 		SPR_CUDA(cudaGetLastError());
 		if (outTotalRecords) {
@@ -536,7 +536,7 @@ SPR_API int sprRunBufferPack(SprContext *c, SprSystem *const *systems, const uin
 		}
 		launch_run_offsets(ctx->stream, ctx->tablePtrs(), ctx->packListD.ptr, numEffects, ctx->dRunOffsets.ptr, nullptr);
 		launch_pack_runs_buf(ctx->stream, ctx->poolPtrs(), ctx->tablePtrs(), ctx->packListD.ptr, numEffects, ctx->dRunOffsets.ptr,
-			buf->dev, buf->capacityRecords, ctx->numSms);
+			buf->dev, buf->capacityRecords, ctx->numSms, ctx->deferExpansion);
 		ctx->launchCount += 2;
 		SPR_CUDA(cudaGetLastError());
 	});
@@ -552,6 +552,14 @@ SPR_API int sprExpandFromPeers(SprContext *c, void *const *bufferPtrs, uint32_t 
 		c->ctx.launchCount++;
 		SPR_CUDA(cudaGetLastError());
 	});
+}
+
+SPR_API int sprContextSetDeferredExpansion(SprContext *c, int on)
+{
+	REQUIRE(c);
+	if (on && !(c->ctx.flags & SPR_CTX_SORT_PARTICLES)) { g_lastError = "deferred expansion needs SPR_CTX_SORT_PARTICLES"; return SPR_ERR_UNSUPPORTED; }
+	c->ctx.deferExpansion = on != 0;
+	return SPR_OK;
 }
 
 SPR_API int sprContextSetAssemblyShare(SprContext *c, uint32_t ctasPerSm)

@@ -1342,7 +1342,17 @@ __global__ void k_run_offsets(TablePtrs tab, const uint32_t *effects, uint32_t n
 	if (threadIdx.x == 0) offsets[n] = sCarry;
 }
 
-// out float4 q -> record q>>1 of the concatenated runs; source is every 4th vertex of the effect's stream
+// Half `half` of record k of an effect's run. FROM_STATE = false: every 4th vertex of the effect's stream;
+// true (deferred expansion: the local stream was not written): the slot record behind the k-th sorted slot.
+template <bool FROM_STATE>
+__device__ __forceinline__ float4 run_record_half(const PoolPtrs &pool, uint32_t slotBase, uint64_t k, uint32_t half)
+{
+	if (FROM_STATE) return pool.state[2ull * (slotBase + pool.vals[slotBase + k]) + half];
+	return pool.vertices[8ull * (slotBase + k) + half];
+}
+
+// out float4 q -> record q>>1 of the concatenated runs
+template <bool FROM_STATE>
 __global__ void __launch_bounds__(256) k_pack_runs(PoolPtrs pool, TablePtrs tab, const uint32_t *effects, uint32_t n,
 	const uint64_t *offsets, float4 *out, uint64_t capacityRecords)
 {
@@ -1356,7 +1366,7 @@ __global__ void __launch_bounds__(256) k_pack_runs(PoolPtrs pool, TablePtrs tab,
 		while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= rcd) lo = mid; else hi = mid; }
 		uint64_t k = rcd - offsets[lo];
 		uint32_t slotBase = tab.params[effects[lo]].slotBase;
-		out[q] = pool.vertices[8ull * (slotBase + k) + (q & 1u)];
+		out[q] = run_record_half<FROM_STATE>(pool, slotBase, k, (uint32_t)(q & 1u));
 	}
 }
 
@@ -1373,6 +1383,7 @@ __global__ void __launch_bounds__(256) k_expand_runs(const float4 *records, uint
 // Run buffer layout: 32-byte header {uint64 count, pad} followed by `count` 32-byte records
 // (32-byte aligned, so that a record moves with one 256-bit access).
 // Same as k_pack_runs, but the record count goes into the header of the destination buffer.
+template <bool FROM_STATE>
 __global__ void __launch_bounds__(256) k_pack_runs_buf(PoolPtrs pool, TablePtrs tab, const uint32_t *effects, uint32_t n,
 	const uint64_t *offsets, float4 *buf, uint64_t capacityRecords)
 {
@@ -1388,7 +1399,7 @@ __global__ void __launch_bounds__(256) k_pack_runs_buf(PoolPtrs pool, TablePtrs 
 		while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= rcd) lo = mid; else hi = mid; }
 		uint64_t k = rcd - offsets[lo];
 		uint32_t slotBase = tab.params[effects[lo]].slotBase;
-		out[q] = pool.vertices[8ull * (slotBase + k) + (q & 1u)];
+		out[q] = run_record_half<FROM_STATE>(pool, slotBase, k, (uint32_t)(q & 1u));
 	}
 }
 
@@ -1624,16 +1635,18 @@ void launch_run_offsets(cudaStream_t st, const TablePtrs &tab, const uint32_t *e
 }
 
 void launch_pack_runs(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,
-	const uint64_t *offsets, float4 *out, uint64_t capacityRecords, uint32_t numSms)
+	const uint64_t *offsets, float4 *out, uint64_t capacityRecords, uint32_t numSms, bool fromState)
 {
 	if (!n) return;
-	k_pack_runs<<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, out, capacityRecords);
+	if (fromState) k_pack_runs<true><<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, out, capacityRecords);
+	else k_pack_runs<false><<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, out, capacityRecords);
 }
 
 void launch_pack_runs_buf(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,
-	const uint64_t *offsets, void *buf, uint64_t capacityRecords, uint32_t numSms)
+	const uint64_t *offsets, void *buf, uint64_t capacityRecords, uint32_t numSms, bool fromState)
 {
-	k_pack_runs_buf<<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, (float4*)buf, capacityRecords);
+	if (fromState) k_pack_runs_buf<true><<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, (float4*)buf, capacityRecords);
+	else k_pack_runs_buf<false><<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, (float4*)buf, capacityRecords);
 }
 
 void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numCtas)

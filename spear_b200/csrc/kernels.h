@@ -41,9 +41,9 @@ void launch_query_frustum(cudaStream_t st, const TablePtrs &tab, uint32_t numGlo
 void launch_gather_render(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, RenderGather *out);
 void launch_run_offsets(cudaStream_t st, const TablePtrs &tab, const uint32_t *effects, uint32_t n, uint64_t *offsets, uint32_t *counts);
 void launch_pack_runs(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,
-	const uint64_t *offsets, float4 *out, uint64_t capacityRecords, uint32_t numSms);
+	const uint64_t *offsets, float4 *out, uint64_t capacityRecords, uint32_t numSms, bool fromState);
 void launch_pack_runs_buf(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,
-	const uint64_t *offsets, void *buf, uint64_t capacityRecords, uint32_t numSms);
+	const uint64_t *offsets, void *buf, uint64_t capacityRecords, uint32_t numSms, bool fromState);
 void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numCtas);
 void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numRecords, float4 *out, uint32_t numSms);
 
@@ -66,6 +66,7 @@ struct SortScratch {
 	uint32_t *keysAlt, *valsAlt;     // ping-pong buffers, same indexing as PoolPtrs::keys/vals
 	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases, then [numSegments] pass masks, then [4] pass tickets
 	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
+	bool deferExpansion;             // sprContextSetDeferredExpansion: sort, but leave the 4x expansion to the assembly
 };
 // Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted, 4 sort_small).
 struct SortTimingHooks {

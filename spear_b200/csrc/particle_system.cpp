@@ -664,7 +664,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	TablePtrs tab = tablePtrs();
 	const ActiveEntry *dEntries = DPTR(ActiveEntry, oEntries);
 	const uint32_t nEntries = (uint32_t)entries.size();
-	SortScratch sortScratch = { nullptr, nullptr, nullptr, nullptr };
+	SortScratch sortScratch = { nullptr, nullptr, nullptr, nullptr, deferExpansion };
 	if (sortMode && !segEffects.empty()) {
 		sortScratch.keysAlt = dKeys[1]; sortScratch.valsAlt = dVals[1];
 		dSortHist.reserve(segEffects.size() * (4 * 256 + 1) + 4, 0, stream); // histograms, pass masks, four pass tickets

@@ -180,6 +180,7 @@ struct Context {
 	cudaStream_t stream = nullptr;
 	bool ownStream = false;
 	uint32_t numSms = 148;
+	bool deferExpansion = false;               // sprContextSetDeferredExpansion (sort mode): updates sort but do not write the local vertex stream
 	uint32_t assemblyCtasPerSm = 8;            // sprContextSetAssemblyShare: resident CTAs per SM of sprExpandFromPeers
 	uint64_t launchCount = 0;
 	uint64_t totalSimSteps = 0;            // simulateParticlesImp calls issued so far (all effects)

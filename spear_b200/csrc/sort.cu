@@ -571,6 +571,9 @@ __device__ inline void st_record_cs(float4 *p, const float4 &a, const float4 &b)
 		:: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
 }
 
+// EXPAND = false (deferred expansion, sprContextSetDeferredExpansion): only the sorted slots are brought home to
+// PoolPtrs::vals; the records are gathered later by the pack kernels, straight into a run buffer.
+template <bool EXPAND>
 __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	const uint32_t *valsAlt, const uint32_t *passMask)
 {
@@ -586,6 +589,7 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	// an odd number of executed passes leaves the sorted slots in the Alt buffer: copy them to PoolPtrs::vals on
 	// the way (the parity read-back sprReadStreamSlots reads them there)
 	const bool fromAlt = __popc(passMask[st.effect]) & 1u;
+	if (!EXPAND && !fromAlt) return;
 	const uint32_t *vals = (fromAlt ? valsAlt : pool.vals) + segBase + begin;
 	const float4 *state = pool.state + 2ull * segBase;
 	float4 *dst = pool.vertices + 8ull * (segBase + begin);
@@ -598,6 +602,7 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 		slot[u] = i < count ? vals[i] : 0xffffffffu;
 		if (fromAlt && i < count) pool.vals[segBase + begin + i] = slot[u];
 	}
+	if (!EXPAND) return;
 	if (tab.state[g].slotCount[tab.state[g].parity] > kLargeGatherSlots) {
 #pragma unroll
 		for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_64b(state + 2ull * slot[u], a[u], b[u]);
@@ -682,7 +687,8 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 		launches++;
 	}
 	T_BEGIN(3);
-	launch_chain(k_expand_sorted, numTiles * kExpandPerTile, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
+	if (sc.deferExpansion) launch_chain(k_expand_sorted<false>, numTiles * kExpandPerTile, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
+	else launch_chain(k_expand_sorted<true>, numTiles * kExpandPerTile, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
 	T_END(3);
 	return launches + 1;
 }

@@ -572,6 +572,75 @@ def test_pack_and_fused_expand_from_run_buffers(oracle_port):
         ctx.close()
 
 
+def test_deferred_expansion_assembles_the_same_stream(oracle_port):
+    """sprContextSetDeferredExpansion: updates sort but do not write the local vertex stream, the pack calls gather the
+    sorted records from the slot state -- the assembled stream (sprRunBufferPack -> sprExpandFromPeers and sprPackRuns ->
+    sprExpandRuns) equals the one built from the local streams of an identical context, for one-granule, one-CTA and tile
+    path effects (odd and even numbers of executed radix passes), over frames with deaths and spawns; switching it off
+    again brings the local stream back with the next update; a stream-mode context refuses it."""
+    import torch
+    P = _particles()
+    ctxs = [P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 16) for _ in range(2)]
+    try:
+        still = dict(drag=0.0, gravity=(0, 0, 0), lifeTime=1e9, spawnTime=1e9, timeStep=1 / 60)
+        churn = dict(drag=0.1, gravity=(0, -9.81, 0), timeStep=1 / 60, emitPosition=dict(boxExtent=(3, 1, 3)),
+                     emitVelocity=dict(sphere=dict(minRadius=0.5, maxRadius=2.0)))
+        comps = [S.comp_c2(k, burst=700 + 100 * k, churn=True) for k in range(2)]
+        comps += [abi.make_component(burstAmount=4000, spawnTime=0.002, lifeTime=0.05, lifeTimeVariance=0.1, **churn),   # one CTA, deaths and spawns
+                  abi.make_component(burstAmount=60, **still),                                                      # one granule
+                  abi.make_component(burstAmount=30000, emitPosition=dict(boxExtent=(4, 2, 4)), **still),            # tile path, 3 passes
+                  abi.make_component(burstAmount=25000, emitPosition=dict(boxExtent=(0.002, 0.002, 0.002)), **still),  # tile path, 2 passes
+                  abi.make_component(burstAmount=40000, spawnTime=1e-4, lifeTime=0.06, lifeTimeVariance=0.1, **churn)]  # tile path, deaths and spawns
+        systems, idss = [], []
+        for ctx in ctxs:
+            s = ctx.create_system((1, 11, 3, 4))
+            systems.append(s)
+            idss.append([s.add_effect(c, abi.make_transform((k, 0, 300 if k == 5 else 0))) for k, c in enumerate(comps)])
+        assert idss[0] == idss[1]
+        ids = idss[0]
+        ctxs[1].set_deferred_expansion(True)
+        cap = 1 << 17
+        out = [torch.zeros((cap * 4, 8), dtype=torch.float32, device="cuda") for _ in range(2)]
+        tot = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(2)]
+        bufs = [ctx.run_buffer_create(cap) for ctx in ctxs]
+        rec = torch.zeros((cap, 8), dtype=torch.float32, device="cuda")
+        counts = []
+        for f in range(8):
+            fa = abi.make_frame_args(0.0175, f * 0.0175, f, camera=CAMERA)
+            for ctx, s, o, t, b in zip(ctxs, systems, out, tot, bufs):
+                s.update(ids, fa)
+                ctx.run_buffer_pack(ctx.make_pack_list([s] * len(ids), ids), b)
+                ctx.expand_from_peers([ctx.run_buffer_ptr(b)], o.data_ptr(), cap, t.data_ptr())
+                ctx.synchronize()
+            torch.cuda.synchronize()
+            n = int(tot[0].item())
+            assert n == int(tot[1].item()) and n > 50000
+            assert torch.equal(out[0][:4 * n], out[1][:4 * n]), "frame %d: deferred assembly differs" % f
+            # the unfused pair gives the same records
+            total = ctxs[1].pack_runs([systems[1]] * len(ids), ids, rec.data_ptr(), cap)
+            ctxs[1].synchronize(); torch.cuda.synchronize()
+            assert total == n and torch.equal(rec[:n], out[0][:4 * n:4])
+            for e in ids:   # the order read back per effect is the same in both contexts
+                assert np.array_equal(systems[0].read_stream_slots(e), systems[1].read_stream_slots(e))
+            counts.append(n)
+        assert min(counts) < max(counts) - 1000, "the population should change over the frames (deaths in the tile-path effect)"
+        ctxs[1].set_deferred_expansion(False)
+        fa = abi.make_frame_args(0.0175, 8 * 0.0175, 8, camera=CAMERA)
+        for s in systems:
+            s.update(ids, fa)
+        for e in ids:
+            assert systems[0].read_stream(e).tobytes() == systems[1].read_stream(e).tobytes()
+        plain = P.ParticleContext(initial_slot_capacity=1 << 12)
+        try:
+            with pytest.raises(Exception):
+                plain.set_deferred_expansion(True)
+        finally:
+            plain.close()
+    finally:
+        for ctx in ctxs:
+            ctx.close()
+
+
 @pytest.mark.parametrize("attempt", range(4))
 def test_type_and_effect_id_recycling(oracle_port, attempt):
     """Dense u32 ids recycled LIFO, types keyed by descriptor identity and refcounted
