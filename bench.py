@@ -523,7 +523,32 @@ def run_ours(args, rank, world):
                 ok = ok and bool(torch.equal(a, b))
                 off += c
             ok = ok and int(total_dev.item()) == sum(counts)
-        gather = {"ms_per_step": gms / args.steps, "particle_steps_this_rank": gps, "fused_ms_per_step": fms / args.steps,
+            # deferred expansion (sprContextSetDeferredExpansion): the consumer is the assembled stream, which holds this
+            # GPU's shard too, so the updates sort but do not write the local 4x stream and the pack gathers the sorted
+            # records from the slot state. Same overlapped pipeline, best share; then the same state through the NCCL pair
+            # and the fused kernel again (both now packing from the slot state) must give the same stream. That the pack
+            # from the slot state equals the pack from the local stream is tests/test_gpu_more.py::test_deferred_expansion_*.
+            ctx.set_deferred_expansion(True)
+            (dms, dps, dlaunches), d_regions = timed_overlapped(best_share)
+            ctx_b.synchronize()
+            ctx.pack_runs(sys_list, eff_list, mine.data_ptr(), cap, None, want_total=False)
+            dist.all_gather_into_tensor(allrec, mine)
+            ctx.expand_runs(allrec.data_ptr(), world * cap, verts.data_ptr())
+            fstep(do_step=False)
+            barrier()
+            ok_d, off = True, 0
+            for r, c in enumerate(counts):
+                a = verts_f[off * 4:(off + c) * 4].view(torch.int32)
+                b = verts[r * cap * 4:(r * cap + c) * 4].view(torch.int32)
+                ok_d = ok_d and bool(torch.equal(a, b))
+                off += c
+            ok_d = ok_d and int(total_dev.item()) == sum(counts)
+            ctx.set_deferred_expansion(False)
+            step()   # the local streams are current again
+            ctx.synchronize()
+        gather = {"deferred_ms_per_step": dms / args.steps, "deferred_particle_steps_this_rank": dps, "deferred_launches_this_rank": dlaunches,
+                  "deferred_regions_ms_per_step": d_regions, "deferred_matches_nccl": ok_d,
+                  "ms_per_step": gms / args.steps, "particle_steps_this_rank": gps, "fused_ms_per_step": fms / args.steps,
                   "fused_particle_steps_this_rank": fps, "fused_matches_nccl": ok,
                   "overlapped_ms_per_step": oms / args.steps, "overlapped_particle_steps_this_rank": ops,
                   "overlapped_launches_this_rank": olaunches, "overlapped_regions_ms_per_step": o_regions,
@@ -538,9 +563,12 @@ def run_ours(args, rank, world):
         ms, e2e_ms, gms_tot, fms_tot, akms = [float(x) for x in t.tolist()]
         c = torch.tensor([particle_steps, e2e_particle_steps, gather["particle_steps_this_rank"], float(launches),
                           gather["fused_particle_steps_this_rank"], 1.0 if gather["fused_matches_nccl"] else 0.0,
-                          gather["overlapped_particle_steps_this_rank"], float(gather["overlapped_launches_this_rank"])], dtype=torch.float64, device="cuda")
+                          gather["overlapped_particle_steps_this_rank"], float(gather["overlapped_launches_this_rank"]),
+                          gather["deferred_particle_steps_this_rank"], float(gather["deferred_launches_this_rank"]),
+                          1.0 if gather["deferred_matches_nccl"] else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        particle_steps, e2e_particle_steps, g_total_ps, launches_all, f_total_ps, f_ok, o_total_ps, o_launches_all = [float(x) for x in c.tolist()]
+        particle_steps, e2e_particle_steps, g_total_ps, launches_all, f_total_ps, f_ok, o_total_ps, o_launches_all, d_total_ps, d_launches_all, d_ok = [float(x) for x in c.tolist()]
+        dms = gather["deferred_ms_per_step"] * args.steps   # already the max over ranks (timed_overlapped reduces every region)
     else:
         launches_all = float(launches)
 
@@ -612,6 +640,16 @@ def run_ours(args, rank, world):
                                              "(peer-memory reads over NVLink fused with the 4x expansion), overlapped with the next step's simulation" % world)
             else:
                 out["config"]["assembly"] = "fused path did NOT match the NCCL path: value is compute only"
+            if f_ok == world and d_ok == world and dms < oms:
+                # the same pipeline without the redundant local stream (the assembled stream holds the local shard too)
+                out["value"] = d_total_ps / (dms * 1e-3)
+                out["ms_per_step"] = dms / args.steps
+                out["gpu_launches"] = int(d_launches_all)
+                out["repeats"] = {"n": len(gather["deferred_regions_ms_per_step"]), "ms_per_step": gather["deferred_regions_ms_per_step"],
+                                  "median_ms_per_step": dms / args.steps,
+                                  "note": "value and ms_per_step are the median of these regions of exactly %d steps each, max over ranks per region" % args.steps}
+                out["config"]["assembly"] += ("; deferred expansion: the updates sort but do not write the local 4x stream (the assembled stream contains this GPU's shard), "
+                                              "sprRunBufferPack gathers the sorted records from the slot state")
             nv = gather["nvlink_bytes_in_per_step"]
             out["gather"] = {
                 "unit": UNIT,
@@ -633,6 +671,12 @@ def run_ours(args, rank, world):
                                      "assembly_ctas_per_sm": gather["overlapped_share"], "ms_per_step_by_assembly_share": gather["overlapped_by_share"],
                                      "note": "the fused assembly of frame k runs on a second stream while frame k+1 is simulated (double-buffered run buffers); "
                                              "the assembly kernel keeps a fixed share of every SM (sprContextSetAssemblyShare), the best share of --assembly-shares is reported"},
+                "fused_deferred": {"value_with_gather": d_total_ps / (dms * 1e-3), "ms_per_step": dms / args.steps,
+                                   "assembly_ctas_per_sm": gather["overlapped_share"], "matches_nccl_path_bit_for_bit": d_ok == world,
+                                   "nvlink_gbs_in_per_gpu": nv / (dms / args.steps * 1e-3) / 1e9,
+                                   "nvlink_roofline_frac": nv / (dms / args.steps * 1e-3) / 1e9 / 770.0,
+                                   "note": "fused_overlapped with sprContextSetDeferredExpansion: update + compaction + sort per shard, NO local 4x expansion "
+                                           "(every GPU expands the whole assembled stream, its own shard included), the pack gathers the sorted records from the slot state"},
                 "nvlink_bytes_in_per_gpu_per_step": nv}
         if world == 1 and sorted_mode and not args.no_stream_mode:
             # the strict drop-in stream (ascending slot order, no per-particle sort) on the same workload,
