@@ -21,6 +21,18 @@ __device__ __forceinline__ void pdl_enter()
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The two halves of pdl_enter() for kernels that have work which depends on NOTHING the frame's earlier kernels write
+// (shared-memory clears, reads of the work lists the host uploaded before the chain started): that work goes between
+// pdl_launch_dependents() and pdl_wait() and overlaps the predecessor's tail. Everything a kernel of this frame may
+// have written -- and with it every early exit that depends on such data -- stays behind pdl_wait(): a CTA ahead of the
+// wait can be running while the predecessor of its predecessor is still at work.
+#ifdef SPR_NO_HOIST // A/B build: nothing runs ahead of the wait
+__device__ __forceinline__ void pdl_launch_dependents() { pdl_enter(); }
+__device__ __forceinline__ void pdl_wait() { }
+#else
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 #endif
 
 inline bool pdl_enabled()
