@@ -445,11 +445,12 @@ __device__ inline void emit_init_leftover(const EmitCtx &c, const PoolPtrs &pool
 // the wide kernel. Also resets the per-step bounds and handles the empty-effect corner.
 __global__ void __launch_bounds__(256) k_emit_warp(PoolPtrs pool, TablePtrs tab, const SystemWork *work, const ActiveEntry *active, uint32_t numActive, uint32_t round, uint32_t stamp)
 {
-	pdl_enter();
+	pdl_launch_dependents();
 	uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (a >= numActive) return;
-	ActiveEntry ae = active[a];
+	ActiveEntry ae = active[a];               // the entry list came with the frame's host-to-device copy: read (and left) ahead of the wait
 	if (round >= ae.numSubsteps) return;
+	pdl_wait();
 	const PlanRec *rec = &tab.plans[ae.planBase + round];
 	EmitCtx c;
 	emit_ctx_init(c, tab, rec);
@@ -1230,12 +1231,13 @@ __global__ void __launch_bounds__(256) k_expand_stream(PoolPtrs pool, TablePtrs 
 // prevEmitterToWorld = emitterToWorld after the frame's sub-steps (:668)
 __global__ void k_finalize(TablePtrs tab, const ActiveEntry *active, uint32_t numActive, uint32_t stamp)
 {
-	pdl_enter();
+	pdl_launch_dependents();
 	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t a = t >> 4, i = t & 15;
 	if (a >= numActive) return;
-	ActiveEntry ae = active[a];
+	ActiveEntry ae = active[a];               // host-uploaded entry list: read ahead of the wait
 	if (ae.numSubsteps == 0) return;
+	pdl_wait();
 	tab.state[ae.effect].prevEmitterToWorld[i] = tab.params[ae.effect].emitterToWorld[i];
 	// the exact slot count after this frame, for the host's capacity bound (read there without synchronising): only for
 	// effects whose bound is not final -- the mirror lives in pinned host memory, 8 bytes over PCIe per effect and frame

@@ -25,7 +25,10 @@ __device__ __forceinline__ void pdl_enter()
 // (shared-memory clears, reads of the work lists the host uploaded before the chain started): that work goes between
 // pdl_launch_dependents() and pdl_wait() and overlaps the predecessor's tail. Everything a kernel of this frame may
 // have written -- and with it every early exit that depends on such data -- stays behind pdl_wait(): a CTA ahead of the
-// wait can be running while the predecessor of its predecessor is still at work.
+// wait can be running while the predecessor of its predecessor is still at work (every kernel of the chain releases its
+// successor when it STARTS). Only what reached the device with the frame's host-to-device copy (tile table, segment
+// list, entry list) is read there: a kernel cannot be launched programmatically across a copy, so everything behind the
+// copy starts after it is complete. Tables written by the upload kernels (params, granule owners) are read behind the wait.
 #ifdef SPR_NO_HOIST // A/B build: nothing runs ahead of the wait
 __device__ __forceinline__ void pdl_launch_dependents() { pdl_enter(); }
 __device__ __forceinline__ void pdl_wait() { }

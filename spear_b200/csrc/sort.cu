@@ -55,10 +55,10 @@ __global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab,
 	for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) sHist[i] = 0;
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const uint32_t firstTile = blockIdx.x * kHistTilesPerCta;
-	SortTile st = tiles[firstTile];          // the work lists were uploaded before the frame's first kernel
+	SortTile st = tiles[firstTile];          // the work lists came with the frame's host-to-device copy, ahead of every kernel
 	uint32_t g = segEffects[st.effect];
-	uint32_t segBase = tab.params[g].slotBase;
 	pdl_wait();
+	uint32_t segBase = tab.params[g].slotBase;
 	__syncthreads();
 	bool any = false;
 	for (uint32_t t = 0; t < kHistTilesPerCta && firstTile + t < numTiles; t++) {
@@ -433,7 +433,7 @@ static_assert(kSmallSortMax <= 65536, "local slot indices are 16-bit");
 
 __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects)
 {
-	pdl_enter();
+	pdl_launch_dependents();
 	extern __shared__ __align__(16) uint8_t sRaw[];
 	uint32_t *sKey = (uint32_t*)sRaw;                                  // [kSmallSortMax]
 	uint16_t *sVal = (uint16_t*)(sRaw + kSmallSortMax * 4);            // [kSmallSortMax]
@@ -443,7 +443,9 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, 
 	__shared__ uint32_t sMaxRel, sTotal;
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t g = segEffects[blockIdx.x];
+	const uint32_t g = segEffects[blockIdx.x]; // host-uploaded list: read ahead of the wait
+	if (tid == 0) sMaxRel = 0;
+	pdl_wait();
 	EffectState &S = tab.state[g];
 	const uint32_t slots = S.slotCount[S.parity];
 	if (slots > kSmallSortMax) __trap(); // the host routes an effect here only when its slot bound fits
@@ -454,8 +456,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, 
 	const uint32_t items = (slots + kSmallThreads - 1) / kSmallThreads;
 	const uint32_t warpBegin = warp * 32 * items;
 
-	if (tid == 0) sMaxRel = 0;
-	__syncthreads();
+	__syncthreads(); // sMaxRel = 0, written ahead of the wait
 
 	uint32_t key[kSmallItems], rank2[kSmallItems / 2], val2[kSmallItems / 2];
 	uint32_t okBits = 0, maxRel = 0;
