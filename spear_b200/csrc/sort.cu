@@ -46,75 +46,50 @@ static const size_t kPassSmemBytes = (2 * kSortTileKeys + kSortWarps * 256) * si
 static_assert(kSortThreads >= 256 && kSortThreads <= 1024 && kHistItems <= 32, "sort tile: 4096 to 16384 keys");
 static_assert(kSortWarps * 512 <= 2 * kSortTileKeys, "the per-warp peer-mask tables alias the key / value staging buffers");
 
-static const uint32_t kHistTilesPerCta = 4; // consecutive tiles per histogram CTA: one flush of global atomics per effect it meets
-
-__global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t numTiles, uint32_t *hist)
+__global__ void __launch_bounds__(256) k_sort_hist(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles, uint32_t *hist)
 {
-	pdl_launch_dependents();
+	pdl_enter();
 	__shared__ uint32_t sHist[4 * 256];
-	for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) sHist[i] = 0;
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	const uint32_t firstTile = blockIdx.x * kHistTilesPerCta;
-	SortTile st = tiles[firstTile];          // the work lists came with the frame's host-to-device copy, ahead of every kernel
+	SortTile st = tiles[blockIdx.x];
 	uint32_t g = segEffects[st.effect];
-	pdl_wait();
-	uint32_t segBase = tab.params[g].slotBase;
+	const EffectState &S = tab.state[g];
+	uint32_t slots = S.slotCount[S.parity];
+	uint32_t begin = st.tile * kSortTileKeys;
+	if (begin >= slots) return;
+	uint32_t count = min(kSortTileKeys, slots - begin);
+	for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) sHist[i] = 0;
 	__syncthreads();
-	bool any = false;
-	for (uint32_t t = 0; t < kHistTilesPerCta && firstTile + t < numTiles; t++) {
-		if (t) {
-			const SortTile nx = tiles[firstTile + t];
-			if (nx.effect != st.effect) {
-				// the next tile belongs to another effect: this one's counts go out, the table starts over
-				__syncthreads();
-				if (any) {
-					uint32_t *dst = hist + (size_t)st.effect * 1024;
-					for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) { const uint32_t v = sHist[i]; if (v) atomicAdd(&dst[i], v); sHist[i] = 0; }
-				}
-				__syncthreads();
-				any = false;
-				g = segEffects[nx.effect];
-				segBase = tab.params[g].slotBase;
-			}
-			st = nx;
-		}
-		const EffectState &S = tab.state[g];
-		const uint32_t slots = S.slotCount[S.parity];
-		const uint32_t begin = st.tile * kSortTileKeys;
-		if (begin >= slots) continue; // CTA-uniform
-		any = true;
-		const uint32_t count = min(kSortTileKeys, slots - begin);
-		const uint32_t *keys = pool.keys + segBase + begin;
-		const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5);
-		const uint32_t keyMin = effect_key_min(S); // digits are taken from key - keyMin: same order, fewer significant bits
-		// All loads of the tile first and with no branch between them -- one memory round trip per tile instead of one per
-		// key (alive word -> branch -> key was two dependent loads, sixteen times over: the kernel took the same 42 us for
-		// 1M and for 10M keys). Key i = tid + 256 * it sits in alive word warp + 8 * it, bit lane: lane l < 16 fetches the
-		// word of iteration l (lane l < kHistItems), a dead slot's key is stale but mapped.
-		uint32_t myWord = 0;
-		if (lane < kHistItems && (warp + 8 * lane) * 32 < count) myWord = mask[warp + 8 * lane];
-		uint32_t key[kHistItems];
+	const uint32_t segBase = tab.params[g].slotBase;
+	const uint32_t *keys = pool.keys + segBase + begin;
+	const uint32_t *mask = pool.aliveMask + ((segBase + begin) >> 5);
+	const uint32_t keyMin = effect_key_min(S); // digits are taken from key - keyMin: same order, fewer significant bits
+	// All loads of the tile first and with no branch between them -- one memory round trip per CTA instead of one per
+	// key (alive word -> branch -> key was two dependent loads, sixteen times over: the kernel took the same 42 us for
+	// 1M and for 10M keys). Key i = tid + 256 * it sits in alive word warp + 8 * it, bit lane: lane l < 16 fetches the
+	// word of iteration l (lane l < kHistItems), a dead slot's key is stale but mapped.
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t myWord = 0;
+	if (lane < kHistItems && (warp + 8 * lane) * 32 < count) myWord = mask[warp + 8 * lane];
+	uint32_t key[kHistItems];
 #pragma unroll
-		for (uint32_t it = 0; it < kHistItems; it++) {
-			const uint32_t i = threadIdx.x + it * 256u;
-			key[it] = i < count ? keys[i] : 0u;
-		}
+	for (uint32_t it = 0; it < kHistItems; it++) {
+		const uint32_t i = threadIdx.x + it * 256u;
+		key[it] = i < count ? keys[i] : 0u;
+	}
 #pragma unroll
-		for (uint32_t it = 0; it < kHistItems; it++) {
-			const uint32_t i = threadIdx.x + it * 256u;
-			const uint32_t word = __shfl_sync(FULL_MASK, myWord, it);
-			if (i >= count || !((word >> lane) & 1u)) continue;
-			const uint32_t k = key[it] - keyMin;
-			// (one count per warp for the top digits, which are the same for most keys of an effect, was measured twice:
-			// slower -- same-address shared-memory atomics are not what this kernel waits for)
-			atomicAdd(&sHist[0 * 256 + (k & 255u)], 1u);
-			atomicAdd(&sHist[1 * 256 + ((k >> 8) & 255u)], 1u);
-			atomicAdd(&sHist[2 * 256 + ((k >> 16) & 255u)], 1u);
-			atomicAdd(&sHist[3 * 256 + (k >> 24)], 1u);
-		}
+	for (uint32_t it = 0; it < kHistItems; it++) {
+		const uint32_t i = threadIdx.x + it * 256u;
+		const uint32_t word = __shfl_sync(FULL_MASK, myWord, it);
+		if (i >= count || !((word >> lane) & 1u)) continue;
+		const uint32_t k = key[it] - keyMin;
+		// (one count per warp for the top digits, which are the same for most keys of an effect, was measured twice:
+		// slower -- same-address shared-memory atomics are not what this kernel waits for)
+		atomicAdd(&sHist[0 * 256 + (k & 255u)], 1u);
+		atomicAdd(&sHist[1 * 256 + ((k >> 8) & 255u)], 1u);
+		atomicAdd(&sHist[2 * 256 + ((k >> 16) & 255u)], 1u);
+		atomicAdd(&sHist[3 * 256 + (k >> 24)], 1u);
 	}
 	__syncthreads();
-	if (!any) return;
 	uint32_t *dst = hist + (size_t)st.effect * 1024;
 	for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) {
 		uint32_t v = sHist[i];
@@ -178,7 +153,7 @@ __global__ void __launch_bounds__(kSortThreads, SPR_SORT_MIN_CTAS) k_sort_pass(P
 	uint32_t *keys0, uint32_t *vals0, uint32_t *keys1, uint32_t *vals1,
 	const uint32_t *hist, const uint32_t *passMask, uint32_t *lookback, uint32_t *ticket, uint32_t pass)
 {
-	pdl_launch_dependents();
+	pdl_enter();
 	extern __shared__ __align__(16) uint32_t sPassDyn[];
 	uint32_t *sKeys = sPassDyn;                         // [kSortTileKeys]
 	uint32_t *sVals = sPassDyn + kSortTileKeys;         // [kSortTileKeys]
@@ -200,12 +175,8 @@ __global__ void __launch_bounds__(kSortThreads, SPR_SORT_MIN_CTAS) k_sort_pass(P
 	const uint32_t tileSlot = blockIdx.x;
 	(void)ticket; (void)sTicket;
 #endif
-	// ahead of the wait: the work lists (uploaded before the frame's first kernel) and the table clears
 	const SortTile st = tiles[tileSlot];
 	const uint32_t g = segEffects[st.effect];
-	// per-warp digit counts and the two per-warp peer-mask tables (aliased onto sKeys / sVals, idle until staging)
-	for (uint32_t i = tid; i < kSortWarps * 256; i += kSortThreads) { sCnt[i] = 0; sPassDyn[i] = 0; sPassDyn[i + kSortWarps * 256] = 0; }
-	pdl_wait();
 	const uint32_t runMask = passMask[st.effect] | 1u; // pass 0 always runs: its scatter is the compaction
 	if (!FIRST && !((runMask >> pass) & 1u)) return; // constant digit: nothing would move
 	const bool isLast = (runMask >> (pass + 1u)) == 0u;
@@ -226,7 +197,9 @@ __global__ void __launch_bounds__(kSortThreads, SPR_SORT_MIN_CTAS) k_sort_pass(P
 #ifdef SPR_SORT_PROFILE
 	long long profT = clock64();
 #endif
-	__syncthreads(); // the tables cleared ahead of the wait
+	// per-warp digit counts and the two per-warp peer-mask tables (aliased onto sKeys / sVals, idle until staging)
+	for (uint32_t i = tid; i < kSortWarps * 256; i += kSortThreads) { sCnt[i] = 0; sPassDyn[i] = 0; sPassDyn[i + kSortWarps * 256] = 0; }
+	__syncthreads();
 	PROF_T(0);
 
 	// ---- load keys (warp-striped: warp w owns keys [w*512, w*512+512) of the tile) and rank them.
@@ -605,11 +578,10 @@ template <bool EXPAND>
 __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	const uint32_t *valsAlt, const uint32_t *passMask)
 {
-	pdl_launch_dependents();
+	pdl_enter();
 	// kExpandPerTile CTAs per sort tile: 1024 particles per CTA, 4 per thread, all gathers in flight at once
-	SortTile st = tiles[blockIdx.x / kExpandPerTile]; // work lists: uploaded before the frame's first kernel, read ahead of the wait
+	SortTile st = tiles[blockIdx.x / kExpandPerTile];
 	uint32_t g = segEffects[st.effect];
-	pdl_wait();
 	uint32_t alive = tab.state[g].aliveCount;
 	uint32_t begin = st.tile * kSortTileKeys + (blockIdx.x % kExpandPerTile) * 1024u;
 	if (begin >= alive) return;
@@ -691,7 +663,7 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 	uint32_t launches = 0;
 	if (numBigSegments && numBigTiles) {
 		T_BEGIN(0);
-		launch_chain(k_sort_hist, (numBigTiles + kHistTilesPerCta - 1) / kHistTilesPerCta, 256, 0, st, pool, tab, segEffects, tiles, numBigTiles, sc.hist);
+		launch_chain(k_sort_hist, numBigTiles, 256, 0, st, pool, tab, segEffects, tiles, sc.hist);
 		T_END(0);
 		uint32_t rows = numBigSegments * 4;
 		T_BEGIN(1);

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, call AX: three-way A/B on one box -- current (hoisted prologues, 1-tile histogram CTAs), the same with the wait first (nohoist1), and the build before both (prehoist)
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+B="--no-cpu-baseline --no-stream-mode --no-billboards --no-vertex-stage --no-c4-slice --no-kernel-timing --steps 20 --warmup 5"
+for R in 1 2; do
+  for W in c3 c4; do
+    for V in "" nohoist1 prehoist; do
+      SPR_LIB_VARIANT=$V timeout 300 python bench.py --workload $W $B > $O/r2ax_${W}_${V:-now}_$R.json 2> $O/r2ax_${W}_${V:-now}_$R.err
+      python -c "import json;d=json.load(open('$O/r2ax_${W}_${V:-now}_$R.json'));print('$W ${V:-now} run $R: %.4f ms'%d['ms_per_step'], ['%.4f'%x for x in d['repeats']['ms_per_step']])"
+    done
+  done
+done
