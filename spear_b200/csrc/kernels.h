@@ -67,6 +67,7 @@ struct SortScratch {
 	uint32_t *hist;                  // [numSegments][4][256] digit histograms -> digit bases, then [numSegments] pass masks, then [4] pass tickets
 	uint32_t *lookback;              // [4][numSortTiles][256] chained-scan status words
 	bool deferExpansion;             // sprContextSetDeferredExpansion: sort, but leave the 4x expansion to the assembly
+	uint32_t numSms, smallMaxSlots;  // k_sort_small: SMs of the device, slot bound of the largest one-CTA effect of the frame (for the key-range split)
 };
 // Optional timing callbacks around each sort kernel class (0 hist, 1 scan, 2 pass, 3 expand_sorted, 4 sort_small).
 struct SortTimingHooks {

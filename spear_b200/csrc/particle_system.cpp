@@ -551,7 +551,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	std::vector<uint32_t> &segEffects = nested ? nestedSeg : scratchSegEffects;
 	std::vector<SortTile> &sortTiles = nested ? nestedTiles : scratchSortTiles;
 	segEffects.clear(); sortTiles.clear();
-	uint32_t numBigSegments = 0, numBigTiles = 0;
+	uint32_t numBigSegments = 0, numBigTiles = 0, smallMaxSlots = 0;
 	if (sortMode && numTinyEffects != numLiveEffects) { // (one-granule effects are sorted inside k_integrate_pass: a context of nothing else has no lists to build)
 		// tile-path effects first, then the ones one CTA sorts whole (k_sort_small): ownedSlots is the effect's slot
 		// bound rounded up to a tile, never below its real slot count
@@ -561,7 +561,7 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 		for (const ActiveEntry &ae : entries) {
 			if (!ae.numSubsteps) continue;
 			if (slotCapacityOf[ae.effect] == kGranuleSlots) continue; // sorted and expanded inside k_integrate_sort
-			if (smallSort && ownedSlots[ae.effect] <= kSmallSortMax) small.push_back(ae.effect);
+			if (smallSort && ownedSlots[ae.effect] <= kSmallSortMax) { small.push_back(ae.effect); if (ownedSlots[ae.effect] > smallMaxSlots) smallMaxSlots = ownedSlots[ae.effect]; }
 			else segEffects.push_back(ae.effect);
 		}
 		numBigSegments = (uint32_t)segEffects.size();
@@ -664,12 +664,13 @@ void Context::update(const UpdateRequest *reqs, uint32_t numReqs)
 	TablePtrs tab = tablePtrs();
 	const ActiveEntry *dEntries = DPTR(ActiveEntry, oEntries);
 	const uint32_t nEntries = (uint32_t)entries.size();
-	SortScratch sortScratch = { nullptr, nullptr, nullptr, nullptr, deferExpansion };
+	SortScratch sortScratch = { nullptr, nullptr, nullptr, nullptr, deferExpansion, numSms, 0 };
 	if (sortMode && !segEffects.empty()) {
 		sortScratch.keysAlt = dKeys[1]; sortScratch.valsAlt = dVals[1];
 		dSortHist.reserve(segEffects.size() * (4 * 256 + 1) + 4, 0, stream); // histograms, pass masks, four pass tickets
 		dSortLookback.reserve(sortTiles.size() * 4 * 256 + 1, 0, stream);
 		sortScratch.hist = dSortHist.ptr; sortScratch.lookback = dSortLookback.ptr;
+		sortScratch.smallMaxSlots = smallMaxSlots;
 		clear_sort_scratch(stream, sortScratch, (uint32_t)segEffects.size(), (uint32_t)sortTiles.size());
 	}
 	TIMED(kKPlan, launch_plan(stream, tab, DPTR(SystemWork, oWork), (uint32_t)work.size(), dEntries, frameStamp));

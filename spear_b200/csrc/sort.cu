@@ -404,7 +404,12 @@ static_assert(kSmallItems * kSmallThreads == kSmallSortMax, "kSmallSortMax must 
 static_assert(kSmallWarps * 512 * 4 <= kSmallSortMax * 4, "the peer-mask tables alias the key buffer");
 static_assert(kSmallSortMax <= 65536, "local slot indices are 16-bit");
 
-__global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects)
+// splitLog > 0 (a frame with few one-CTA effects, which would leave most SMs idle): 2 or 4 CTAs share an effect BY KEY RANGE.
+// Every CTA of the group loads all keys of the effect, builds the same 256-bin histogram of their top 8 significant bits and
+// cuts it into parts of about equal population; it keeps the keys of its own part -- the histogram's prefix tells where its
+// piece of the sorted list starts --, compacts them in slot order and sorts them as below: fewer keys per thread, fewer
+// bits (a pass less when the part's range drops below a byte boundary), no communication between the CTAs.
+__global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, uint32_t splitLog)
 {
 	pdl_launch_dependents();
 	extern __shared__ __align__(16) uint8_t sRaw[];
@@ -414,9 +419,11 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, 
 	__shared__ uint32_t sBase[256];     // exclusive scan of the digit totals
 	__shared__ uint32_t sWarpSum[8];
 	__shared__ uint32_t sMaxRel, sTotal;
+	__shared__ uint32_t sPartWarp[kSmallWarps], sPivot[8];
 
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t g = segEffects[blockIdx.x]; // host-uploaded list: read ahead of the wait
+	const uint32_t g = segEffects[blockIdx.x >> splitLog]; // host-uploaded list: read ahead of the wait
+	const uint32_t part = blockIdx.x & ((1u << splitLog) - 1u);
 	if (tid == 0) sMaxRel = 0;
 	pdl_wait();
 	EffectState &S = tab.state[g];
@@ -426,8 +433,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, 
 	const uint32_t keyMin = effect_key_min(S);
 	// the CTA's keys are warp-striped: warp w owns [w * 32 * items, (w + 1) * 32 * items), item i of lane l is
 	// w * 32 * items + i * 32 + l -- ascending in (warp, item, lane), which is the order ranks are given in
-	const uint32_t items = (slots + kSmallThreads - 1) / kSmallThreads;
-	const uint32_t warpBegin = warp * 32 * items;
+	uint32_t items = (slots + kSmallThreads - 1) / kSmallThreads;
+	uint32_t warpBegin = warp * 32 * items;
 
 	__syncthreads(); // sMaxRel = 0, written ahead of the wait
 
@@ -462,7 +469,101 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, 
 	if (lane == 0 && maxRel) atomicMax(&sMaxRel, maxRel);
 	__syncthreads();
 	maxRel = sMaxRel;
-	const uint32_t numPasses = maxRel ? (32u - (uint32_t)__clz(maxRel) + 7u) / 8u : 1u; // pass 0 always runs: it compacts
+	uint32_t bits = maxRel ? 32u - (uint32_t)__clz(maxRel) : 0u;
+	uint32_t outOffset = 0, totalAlive = 0;
+	if (splitLog) {
+		// ---- the parts: key ranges of about equal POPULATION, cut at boundaries of the 256 bins of the top 8 significant
+		// bits (every CTA of the group computes the same histogram, hence the same cuts, from the same keys)
+		const uint32_t numParts = 1u << splitLog;
+		const uint32_t hshift = bits > 8u ? bits - 8u : 0u;
+		const uint32_t ltMaskS = (1u << lane) - 1u;
+		if (tid < 256) sBase[tid] = 0;
+		if (tid < 8) sPivot[tid] = 256;
+		__syncthreads();
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			if ((okBits >> i) & 1u) atomicAdd(&sBase[key[i] >> hshift], 1u);
+		}
+		__syncthreads();
+		uint32_t cntD = 0, inclD = 0;
+		if (tid < 256) { // inclusive scan of the bin counts
+			cntD = sBase[tid];
+			inclD = cntD;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL_MASK, inclD, d); if (lane >= d) inclD += o; }
+			if (lane == 31) sWarpSum[warp] = inclD;
+		}
+		__syncthreads();
+		if (tid < 256) {
+#pragma unroll
+			for (uint32_t w = 0; w < 8; w++) if (w < warp) inclD += sWarpSum[w];
+			sBase[tid] = inclD;
+		}
+		__syncthreads();
+		totalAlive = sBase[255];
+		if (tid < 256 && cntD) {
+			// cut q sits behind the bin in which the running count reaches q / numParts of the keys
+			for (uint32_t q = 1; q < numParts; q++) {
+				const uint32_t target = (uint32_t)(((uint64_t)totalAlive * q + numParts - 1) / numParts);
+				if (inclD >= target && inclD - cntD < target) sPivot[q] = tid + 1;
+			}
+		}
+		__syncthreads();
+		const uint32_t binLo = part ? sPivot[part] : 0u, binHi = part + 1 < numParts ? sPivot[part + 1] : 256u;
+		if (binHi <= binLo) { if (part == 0 && tid == 0) S.aliveCount = totalAlive; return; } // an empty part (CTA-uniform)
+		outOffset = binLo ? sBase[binLo - 1] : 0u;
+		const uint32_t nMine = sBase[binHi - 1] - outOffset;
+		if (nMine == 0) { if (part == 0 && tid == 0) S.aliveCount = totalAlive; return; }
+		const uint32_t partBase = binLo << hshift;
+		uint32_t mine = 0, mineBits = 0;
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			if ((okBits >> i) & 1u) {
+				const uint32_t b = key[i] >> hshift;
+				if (b >= binLo && b < binHi) { mine++; mineBits |= 1u << i; }
+			}
+		}
+		mine = __reduce_add_sync(FULL_MASK, mine);
+		if (lane == 0) sPartWarp[warp] = mine;
+		__syncthreads();
+		uint32_t warpBase = 0;
+#pragma unroll 8
+		for (uint32_t w = 0; w < kSmallWarps; w++) if (w < warp) warpBase += sPartWarp[w];
+		// ---- compact the part in ascending slot order = (warp, item, lane) order; its keys become relative to the part's base
+		uint32_t run = warpBase;
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			const bool in = (mineBits >> i) & 1u;
+			const uint32_t bal = __ballot_sync(FULL_MASK, in);
+			if (in) {
+				const uint32_t pos = run + __popc(bal & ltMaskS);
+				sKey[pos] = key[i] - partBase;
+				sVal[pos] = (uint16_t)((i & 1u) ? (val2[i >> 1] >> 16) : (val2[i >> 1] & 0xffffu));
+			}
+			run += __popc(bal);
+		}
+		__syncthreads();
+		items = (nMine + kSmallThreads - 1) / kSmallThreads;
+		warpBegin = warp * 32 * items;
+		okBits = 0;
+#pragma unroll
+		for (uint32_t i = 0; i < kSmallItems; i++) {
+			if (i >= items) break;
+			const uint32_t idx = warpBegin + i * 32 + lane;
+			const bool ok = idx < nMine;
+			key[i] = ok ? sKey[idx] : 0u;
+			const uint32_t v = ok ? sVal[idx] : 0u;
+			if (i & 1u) val2[i >> 1] |= v << 16; else val2[i >> 1] = v;
+			if (ok) okBits |= 1u << i;
+		}
+		__syncthreads(); // all reads done before the first pass clears the tables aliased onto sKey
+		const uint32_t span = ((binHi - binLo) << hshift) - 1u; // keys of the part, relative to its base, are <= span
+		bits = span ? 32u - (uint32_t)__clz(span) : 0u;
+	}
+	const uint32_t numPasses = bits ? (bits + 7u) / 8u : 1u; // pass 0 always runs: it compacts
 
 	uint32_t n = 0; // live keys; known after pass 0
 	for (uint32_t pass = 0; pass < numPasses; pass++) {
@@ -541,9 +642,9 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_sort_small(PoolPtrs pool, 
 		__syncthreads(); // all reads done before the next pass clears the aliased tables
 	}
 	// ---- the sorted slot list (PoolPtrs::vals: what k_expand_sorted and sprReadStreamSlots read)
-	uint32_t *vout = pool.vals + segBase;
+	uint32_t *vout = pool.vals + segBase + outOffset;
 	for (uint32_t j = tid; j < n; j += kSmallThreads) vout[j] = sVal[j];
-	if (tid == 0) S.aliveCount = n; // gpuParticles.size / 4 (:670); the tile path writes it in k_sort_scan
+	if (tid == 0 && part == 0) S.aliveCount = splitLog ? totalAlive : n; // gpuParticles.size / 4 (:670); the tile path writes it in k_sort_scan
 }
 
 // One lane per particle: a coalesced read of 32 slot indices, one 256-bit gather of the 32-byte
@@ -683,7 +784,12 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 	if (numSegments > numBigSegments) {
 		// their pass masks stay 0 (cleared with the histograms): k_expand_sorted then reads PoolPtrs::vals
 		T_BEGIN(4);
-		launch_chain(k_sort_small, numSegments - numBigSegments, kSmallThreads, kSmallSmemBytes, st, pool, tab, segEffects + numBigSegments);
+		// few one-CTA effects, at least one of them big enough to be worth it: 2 or 4 CTAs share each effect by key range
+		static const bool splitAllowed = [] { const char *e = getenv("SPR_SMALL_SPLIT"); return !(e && e[0] == '0'); }(); // A/B: SPR_SMALL_SPLIT=0
+		const uint32_t numSmall = numSegments - numBigSegments;
+		uint32_t splitLog = 0;
+		if (splitAllowed && sc.smallMaxSlots > 4096u) splitLog = numSmall * 4 <= sc.numSms ? 2u : numSmall * 2 <= sc.numSms ? 1u : 0u;
+		launch_chain(k_sort_small, numSmall << splitLog, kSmallThreads, kSmallSmemBytes, st, pool, tab, segEffects + numBigSegments, splitLog);
 		T_END(4);
 		launches++;
 	}
