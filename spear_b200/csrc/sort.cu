@@ -675,12 +675,23 @@ __device__ inline void st_record_cs(float4 *p, const float4 &a, const float4 &b)
 
 // EXPAND = false (deferred expansion, sprContextSetDeferredExpansion): only the sorted slots are brought home to
 // PoolPtrs::vals; the records are gathered later by the pack kernels, straight into a run buffer.
+// One record per thread, 1024 threads per CTA, two CTAs per SM (32 registers, every warp slot of the SM in use) measured
+// 1 % faster on the kernel than four records per thread in 256-thread CTAs (64 registers, half the warp slots) at C3, C4 and C2;
+// two per thread at three CTAs of 512 (40 registers, spills) 4 % slower at C3: profiles/r02_sort_experiments.md M.
+#ifndef SPR_EXPAND_PER_THREAD
+#define SPR_EXPAND_PER_THREAD 1
+#endif
+#ifndef SPR_EXPAND_MIN_CTAS
+#define SPR_EXPAND_MIN_CTAS 2
+#endif
+static const uint32_t kExpPer = SPR_EXPAND_PER_THREAD;       // records per thread of k_expand_sorted (all gathers in flight at once)
+static const uint32_t kExpThreads = 1024 / kExpPer;          // a CTA expands 1024 consecutive ranks
 template <bool EXPAND>
-__global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
+__global__ void __launch_bounds__(kExpThreads, SPR_EXPAND_MIN_CTAS) k_expand_sorted(PoolPtrs pool, TablePtrs tab, const uint32_t *segEffects, const SortTile *tiles,
 	const uint32_t *valsAlt, const uint32_t *passMask)
 {
 	pdl_enter();
-	// kExpandPerTile CTAs per sort tile: 1024 particles per CTA, 4 per thread, all gathers in flight at once
+	// kExpandPerTile CTAs per sort tile: 1024 particles per CTA, kExpPer per thread, all gathers in flight at once
 	SortTile st = tiles[blockIdx.x / kExpandPerTile];
 	uint32_t g = segEffects[st.effect];
 	uint32_t alive = tab.state[g].aliveCount;
@@ -695,22 +706,22 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	const uint32_t *vals = (fromAlt ? valsAlt : pool.vals) + segBase + begin;
 	const float4 *state = pool.state + 2ull * segBase;
 	float4 *dst = pool.vertices + 8ull * (segBase + begin);
-	uint32_t slot[4];
-	float4 a[4], b[4];
+	uint32_t slot[kExpPer];
+	float4 a[kExpPer], b[kExpPer];
 #pragma unroll
-	for (int u = 0; u < 4; u++) {
+	for (int u = 0; u < (int)kExpPer; u++) {
 		a[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); b[u] = a[u];
-		uint32_t i = u * 256 + threadIdx.x;
+		uint32_t i = u * kExpThreads + threadIdx.x;
 		slot[u] = i < count ? vals[i] : 0xffffffffu;
 		if (fromAlt && i < count) pool.vals[segBase + begin + i] = slot[u];
 	}
 	if (!EXPAND) return;
 	if (tab.state[g].slotCount[tab.state[g].parity] > kLargeGatherSlots) {
 #pragma unroll
-		for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_64b(state + 2ull * slot[u], a[u], b[u]);
+		for (int u = 0; u < (int)kExpPer; u++) if (slot[u] != 0xffffffffu) ld_record_64b(state + 2ull * slot[u], a[u], b[u]);
 	} else {
 #pragma unroll
-		for (int u = 0; u < 4; u++) if (slot[u] != 0xffffffffu) ld_record_cg(state + 2ull * slot[u], a[u], b[u]);
+		for (int u = 0; u < (int)kExpPer; u++) if (slot[u] != 0xffffffffu) ld_record_cg(state + 2ull * slot[u], a[u], b[u]);
 	}
 	// The warp's 32 records go out transposed: store j of lane l is copy (l & 3) of the group's particle j * 8 + l / 4,
 	// fetched from that particle's lane with shuffles, so that each store instruction of the warp covers 1 KB of
@@ -718,8 +729,8 @@ __global__ void __launch_bounds__(256) k_expand_sorted(PoolPtrs pool, TablePtrs 
 	// LSU wavefronts: tools/expand_store_bench.cu, 10M random 0.392 -> 0.382 ms, 1M (L2 resident) 0.042 -> 0.034 ms.
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
-	for (int u = 0; u < 4; u++) {
-		const uint32_t wbase = u * 256 + warp * 32;   // the warp's group of 32 consecutive ranks
+	for (int u = 0; u < (int)kExpPer; u++) {
+		const uint32_t wbase = u * kExpThreads + warp * 32;   // the warp's group of 32 consecutive ranks
 		if (wbase >= count) continue;                   // warp-uniform
 		const uint32_t cnt = min(32u, count - wbase);
 		float4 *d = dst + 8ull * wbase;
@@ -794,8 +805,8 @@ uint32_t launch_sort_and_expand(cudaStream_t st, const PoolPtrs &pool, const Tab
 		launches++;
 	}
 	T_BEGIN(3);
-	if (sc.deferExpansion) launch_chain(k_expand_sorted<false>, numTiles * kExpandPerTile, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
-	else launch_chain(k_expand_sorted<true>, numTiles * kExpandPerTile, 256, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
+	if (sc.deferExpansion) launch_chain(k_expand_sorted<false>, numTiles * kExpandPerTile, kExpThreads, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
+	else launch_chain(k_expand_sorted<true>, numTiles * kExpandPerTile, kExpThreads, 0, st, pool, tab, segEffects, tiles, sc.valsAlt, passMask);
 	T_END(3);
 	return launches + 1;
 }
