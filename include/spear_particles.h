@@ -636,6 +636,9 @@ SPR_API int sprExpandFromPeers(SprContext *ctx, void *const *bufferPtrs, uint32_
  * whether 2 or 8 CTAs per SM pull, profiles/r02_peer_allgather_microbench_8gpu.txt), so a caller that runs it on a second
  * context / stream under the next frame's simulation gives it a small share and leaves the rest of every SM to the
  * simulation kernels (bench.py: gather.fused_overlapped). */
+/* At a share of 1 or 2 the assembly runs as a bulk-asynchronous pipeline (cp.async.bulk loads out of the peers into shared
+ * memory, bulk tensor stores of the 4x expansion: no register holds data in flight, a third of the registers of the
+ * load/store kernel), which leaves the simulation beside it more of the SM; same stream, bit for bit. */
 SPR_API int sprContextSetAssemblyShare(SprContext *ctx, uint32_t ctasPerSm);
 /* Deferred expansion (SPR_CTX_SORT_PARTICLES contexts only, else SPR_ERR_UNSUPPORTED), for pipelines whose consumer is the
  * ASSEMBLED draw stream (sprPackRuns / sprRunBufferPack -> sprExpandRuns / sprExpandFromPeers), which contains this

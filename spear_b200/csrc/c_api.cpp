@@ -548,7 +548,7 @@ SPR_API int sprExpandFromPeers(SprContext *c, void *const *bufferPtrs, uint32_t 
 	REQUIRE(c && bufferPtrs && deviceVerticesOut && numRanks >= 1 && numRanks <= 16 && myRank < numRanks);
 	return guarded([&] {
 		SPR_CUDA(cudaSetDevice(c->ctx.device));
-		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, myRank, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms * c->ctx.assemblyCtasPerSm);
+		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, myRank, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms * c->ctx.assemblyCtasPerSm, c->ctx.assemblyCtasPerSm <= 2);
 		c->ctx.launchCount++;
 		SPR_CUDA(cudaGetLastError());
 	});

@@ -1481,6 +1481,110 @@ __global__ void __launch_bounds__(256) k_expand_from_peers(PeerRuns runs, float4
 	}
 }
 
+// The same assembly with NO register held per byte in flight, for the overlapped pipeline where the kernel is confined to
+// a small share of every SM (sprContextSetAssemblyShare): lane 0 of every warp drives a pipeline of kPeerStages bulk
+// asynchronous loads (cp.async.bulk global -> shared, 4 KB = 128 records each, completion on an mbarrier) out of the
+// peers' runs and hands every landed chunk to four bulk tensor stores (one per copy of the quad, the vertex stream as
+// [record][copy][8 floats]) -- neither the pull nor the 4x expansion issues an LSU instruction on the data. Runs are cut
+// into full 128-record chunks; the tail of every run (< 128 records) goes through the warp's lanes at the end.
+static const int kPeerWarps = 4, kPeerStages = 3;       // 48 KB of shared memory per CTA: fits beside four k_sort_pass CTAs
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(kPeerWarps * 32) k_expand_from_peers_tma(PeerRuns runs, float4 *out, uint64_t capacityRecords, unsigned long long *totalOut,
+	const __grid_constant__ CUtensorMap map)
+{
+	pdl_enter();
+	extern __shared__ __align__(128) uint8_t sPeerStage[];
+	__shared__ __align__(8) unsigned long long sBar[kPeerWarps][kPeerStages];
+	__shared__ unsigned long long sOffset[17];
+	__shared__ unsigned long long sMaxFull;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) {
+		unsigned long long run = 0, mx = 0;
+		for (uint32_t r = 0; r < runs.numRanks; r++) {
+			sOffset[r] = run;
+			unsigned long long c;
+			asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(c) : "l"(runs.buf[r]) : "memory");
+			if (run + c > capacityRecords) c = capacityRecords > run ? capacityRecords - run : 0;
+			run += c;
+			if (c / 128 > mx) mx = c / 128;
+		}
+		sOffset[runs.numRanks] = run;
+		sMaxFull = mx;
+		if (blockIdx.x == 0 && totalOut) *totalOut = run;
+	}
+	if (lane == 0) {
+		for (int s = 0; s < kPeerStages; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&sBar[warp][s])) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	const uint64_t gw = (uint64_t)blockIdx.x * kPeerWarps + warp, stride = (uint64_t)gridDim.x * kPeerWarps;
+	if (lane == 0) {
+		// work item j -> full chunk (j / numRanks) of rank (j + myRank) % numRanks, as in k_expand_from_peers: every GPU reads all
+		// peers at any moment and starts on a different one
+		const uint64_t items = sMaxFull * runs.numRanks;
+		uint8_t *stage = sPeerStage + (size_t)warp * kPeerStages * 4096;
+		auto valid = [&](uint64_t j, uint32_t &r, uint64_t &c) {
+			r = (uint32_t)((j + runs.myRank) % runs.numRanks); c = j / runs.numRanks;
+			return c < (sOffset[r + 1] - sOffset[r]) / 128;
+		};
+		auto issue_load = [&](int s, uint32_t r, uint64_t c) {
+			const uint32_t bar = smem_addr(&sBar[warp][s]);
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(4096) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				:: "r"(smem_addr(stage + s * 4096)), "l"(runs.buf[r] + 2 + 256ull * c), "r"(4096), "r"(bar) : "memory");
+		};
+		uint64_t issueJ = gw;
+		uint32_t r; uint64_t c;
+		uint32_t qr[kPeerStages]; uint64_t qc[kPeerStages]; // what sits in each stage
+		int filled = 0;
+		for (; filled < kPeerStages && issueJ < items; issueJ += stride) {
+			if (!valid(issueJ, r, c)) continue;
+			qr[filled] = r; qc[filled] = c;
+			issue_load(filled, r, c);
+			filled++;
+		}
+		uint32_t phase = 0;
+		int s = 0;
+		while (filled > 0) {
+			const uint32_t bar = smem_addr(&sBar[warp][s]);
+			uint32_t done = 0;
+			while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+			const int first = (int)(sOffset[qr[s]] + qc[s] * 128);
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+					:: "l"((uint64_t)&map), "r"(smem_addr(stage + s * 4096)), "r"(0), "r"(k), "r"(first) : "memory");
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			// refill this stage with the warp's next chunk once its stores have read it
+			bool refilled = false;
+			for (; issueJ < items && !refilled; issueJ += stride) {
+				if (!valid(issueJ, r, c)) continue;
+				asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+				qr[s] = r; qc[s] = c;
+				issue_load(s, r, c);
+				refilled = true;
+			}
+			if (!refilled) filled--;
+			if (++s == kPeerStages) { s = 0; phase ^= 1u; }
+		}
+		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+	}
+	__syncwarp();
+	// the tails: run r's last (count % 128) records, one run per warp at a time, through the lanes
+	for (uint64_t r = gw; r < runs.numRanks; r += stride) {
+		const unsigned long long count = sOffset[r + 1] - sOffset[r];
+		const unsigned long long base = count / 128 * 128;
+		const float4 *src = runs.buf[r] + 2;
+		for (unsigned long long i = base + lane; i < count; i += 32) {
+			float4 a, b;
+			asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+				: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 2ull * i));
+			float4 *d = out + 8ull * (sOffset[r] + i);
+			st_record(d, a, b); st_record(d + 2, a, b); st_record(d + 4, a, b); st_record(d + 6, a, b);
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------
 // Launch wrappers
 // ---------------------------------------------------------------------------
@@ -1657,12 +1761,29 @@ void launch_pack_runs_buf(cudaStream_t st, const PoolPtrs &pool, const TablePtrs
 	else k_pack_runs_buf<false><<<numSms * 8, 256, 0, st>>>(pool, tab, effects, n, offsets, (float4*)buf, capacityRecords);
 }
 
-void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numCtas)
+void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numCtas, bool smallShare)
 {
 	PeerRuns runs;
 	runs.numRanks = numRanks;
 	runs.myRank = myRank;
 	for (uint32_t r = 0; r < 16; r++) runs.buf[r] = r < numRanks ? (const float4*)bufs[r] : nullptr;
+	// Bulk-async variant for a kernel that shares the SMs with the next frame's simulation (smallShare: at most two CTAs per SM,
+	// sprContextSetAssemblyShare): 128-thread CTAs, one pipeline per warp, 6 K registers per CTA instead of 18 K and none of them
+	// holding data in flight -- 8 GPUs, deferred expansion: 3.19 -> 3.05 ms per step at one CTA per SM. With the GPU to itself the
+	// LSU kernel's 256 threads x 4 records pull faster (2.97 against 3.12 ms): it stays the kernel of the larger shares.
+	// SPR_PEER_TMA=0 / 1 forces one or the other (A/B).
+	static const int forced = [] { const char *e = getenv("SPR_PEER_TMA"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+	const bool tma = forced >= 0 ? forced == 1 : smallShare;
+	VertexTensorMap vm;
+	if (tma && capacityRecords >= 128 && encode_vertex_map(&vm, out, capacityRecords)) {
+		CUtensorMap map;
+		memcpy(&map, &vm, sizeof(map));
+		static bool configured = false;
+		const size_t smem = (size_t)kPeerWarps * kPeerStages * 4096;
+		if (!configured) { cudaFuncSetAttribute(k_expand_from_peers_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+		k_expand_from_peers_tma<<<numCtas, kPeerWarps * 32, smem, st>>>(runs, out, capacityRecords, (unsigned long long*)totalOut, map);
+		return;
+	}
 	k_expand_from_peers<<<numCtas, 256, 0, st>>>(runs, out, capacityRecords, (unsigned long long*)totalOut); // persistent: grid-stride over 1024-record chunks
 }
 

@@ -44,7 +44,7 @@ void launch_pack_runs(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &ta
 	const uint64_t *offsets, float4 *out, uint64_t capacityRecords, uint32_t numSms, bool fromState);
 void launch_pack_runs_buf(cudaStream_t st, const PoolPtrs &pool, const TablePtrs &tab, const uint32_t *effects, uint32_t n,
 	const uint64_t *offsets, void *buf, uint64_t capacityRecords, uint32_t numSms, bool fromState);
-void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numCtas);
+void launch_expand_from_peers(cudaStream_t st, void *const *bufs, uint32_t numRanks, uint32_t myRank, float4 *out, uint64_t capacityRecords, uint64_t *totalOut, uint32_t numCtas, bool smallShare);
 void launch_expand_runs(cudaStream_t st, const float4 *records, uint64_t numRecords, float4 *out, uint32_t numSms);
 
 // vertex_stage.cu: Particle.glsl `vs` over draw records

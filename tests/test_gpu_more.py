@@ -543,12 +543,16 @@ def test_type_lut_and_ubo(oracle_port):
         assert bytes(ubo) == bytes(o.type_ubo(t))
 
 
-def test_pack_and_fused_expand_from_run_buffers(oracle_port):
+@pytest.mark.parametrize("share", [0, 1], ids=["whole_gpu_lsu_kernel", "one_cta_per_sm_bulk_async_kernel"])
+def test_pack_and_fused_expand_from_run_buffers(oracle_port, share):
     """sprRunBufferPack + sprExpandFromPeers with two run buffers of the same GPU standing in for two
-    ranks: the assembled stream is run 0 then run 1, each equal to the effects' own vertex streams."""
+    ranks: the assembled stream is run 0 then run 1, each equal to the effects' own vertex streams. At an assembly
+    share of one CTA per SM the expansion is the bulk-asynchronous pipeline (cp.async.bulk loads, tensor stores, the
+    runs' tails through the lanes), at the default share the load/store kernel."""
     import torch
     P = _particles()
     ctx = P.ParticleContext(sort_particles=True, initial_slot_capacity=1 << 16)
+    ctx.set_assembly_share(share)
     try:
         s = ctx.create_system((1, 11, 3, 4))
         comps = [S.comp_c2(k, burst=700 + 100 * k, churn=True) for k in range(4)]
@@ -599,6 +603,7 @@ def test_deferred_expansion_assembles_the_same_stream(oracle_port):
         assert idss[0] == idss[1]
         ids = idss[0]
         ctxs[1].set_deferred_expansion(True)
+        ctxs[1].set_assembly_share(1)   # ... and assembles through the bulk-asynchronous kernel, the other context through the load/store one
         cap = 1 << 17
         out = [torch.zeros((cap * 4, 8), dtype=torch.float32, device="cuda") for _ in range(2)]
         tot = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(2)]
