@@ -530,15 +530,24 @@ def run_ours(args, rank, world):
             # from the slot state equals the pack from the local stream is tests/test_gpu_more.py::test_deferred_expansion_*.
             ctx.set_deferred_expansion(True)
             d_by_share = {}
-            for share in [int(x) for x in args.assembly_shares.split(",")]:   # the lighter simulation may want a different share
-                d_by_share[share] = timed_overlapped(share)
-            d_best_share = min(d_by_share, key=lambda k: d_by_share[k][0][0])
-            (dms, dps, dlaunches), d_regions = d_by_share[d_best_share]
+            # both assembly kernels (sprContextSetAssemblyKernel: 1 = load/store, 2 = bulk-asynchronous pipeline) at every share: which
+            # one wins depends on what bounds the assembly at this GPU count (NVLink ingress at 8, HBM stores at 2-4)
+            for kern in (1, 2):
+                ctx_b.set_assembly_kernel(kern)
+                for share in [int(x) for x in args.assembly_shares.split(",")]:   # the lighter simulation may want a different share
+                    d_by_share[(share, kern)] = timed_overlapped(share)
+            d_best = min(d_by_share, key=lambda k: d_by_share[k][0][0])
+            d_best_share = d_best[0]
+            (dms, dps, dlaunches), d_regions = d_by_share[d_best]
+            ctx_b.set_assembly_kernel(d_best[1])
             ctx_b.synchronize()
             ctx.pack_runs(sys_list, eff_list, mine.data_ptr(), cap, None, want_total=False)
             dist.all_gather_into_tensor(allrec, mine)
             ctx.expand_runs(allrec.data_ptr(), world * cap, verts.data_ptr())
+            ctx.set_assembly_kernel(d_best[1])   # the check runs the kernel that was timed
+            verts_f.zero_()
             fstep(do_step=False)
+            ctx.set_assembly_kernel(0)
             barrier()
             ok_d, off = True, 0
             for r, c in enumerate(counts):
@@ -552,7 +561,8 @@ def run_ours(args, rank, world):
             ctx.synchronize()
         gather = {"deferred_ms_per_step": dms / args.steps, "deferred_particle_steps_this_rank": dps, "deferred_launches_this_rank": dlaunches,
                   "deferred_regions_ms_per_step": d_regions, "deferred_matches_nccl": ok_d,
-                  "deferred_share": d_best_share, "deferred_by_share": {str(k): v[0][0] / args.steps for k, v in d_by_share.items()},
+                  "deferred_share": d_best_share, "deferred_kernel": "bulk_async" if d_best[1] == 2 else "load_store",
+                  "deferred_by_share": {"%d_%s" % (k[0], "bulk_async" if k[1] == 2 else "load_store"): v[0][0] / args.steps for k, v in d_by_share.items()},
                   "ms_per_step": gms / args.steps, "particle_steps_this_rank": gps, "fused_ms_per_step": fms / args.steps,
                   "fused_particle_steps_this_rank": fps, "fused_matches_nccl": ok,
                   "overlapped_ms_per_step": oms / args.steps, "overlapped_particle_steps_this_rank": ops,
@@ -677,7 +687,8 @@ def run_ours(args, rank, world):
                                      "note": "the fused assembly of frame k runs on a second stream while frame k+1 is simulated (double-buffered run buffers); "
                                              "the assembly kernel keeps a fixed share of every SM (sprContextSetAssemblyShare), the best share of --assembly-shares is reported"},
                 "fused_deferred": {"value_with_gather": d_total_ps / (dms * 1e-3), "ms_per_step": dms / args.steps,
-                                   "assembly_ctas_per_sm": gather["deferred_share"], "ms_per_step_by_assembly_share": gather["deferred_by_share"],
+                                   "assembly_ctas_per_sm": gather["deferred_share"], "assembly_kernel": gather["deferred_kernel"],
+                                   "ms_per_step_by_assembly_share": gather["deferred_by_share"],
                                    "matches_nccl_path_bit_for_bit": d_ok == world,
                                    "nvlink_gbs_in_per_gpu": nv / (dms / args.steps * 1e-3) / 1e9,
                                    "nvlink_roofline_frac": nv / (dms / args.steps * 1e-3) / 1e9 / 770.0,

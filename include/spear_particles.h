@@ -640,6 +640,10 @@ SPR_API int sprExpandFromPeers(SprContext *ctx, void *const *bufferPtrs, uint32_
  * memory, bulk tensor stores of the 4x expansion: no register holds data in flight, a third of the registers of the
  * load/store kernel), which leaves the simulation beside it more of the SM; same stream, bit for bit. */
 SPR_API int sprContextSetAssemblyShare(SprContext *ctx, uint32_t ctasPerSm);
+/* Which kernel sprExpandFromPeers runs: 0 = chosen by the share (bulk-asynchronous at 1 or 2 CTAs per SM, load/store above),
+ * 1 = the load/store kernel, 2 = the bulk-asynchronous pipeline. Same stream either way; which one is faster under a given
+ * simulation depends on what bounds the assembly (NVLink ingress at 8 GPUs, HBM stores at 2-4): bench.py tries both. */
+SPR_API int sprContextSetAssemblyKernel(SprContext *ctx, uint32_t kernel);
 /* Deferred expansion (SPR_CTX_SORT_PARTICLES contexts only, else SPR_ERR_UNSUPPORTED), for pipelines whose consumer is the
  * ASSEMBLED draw stream (sprPackRuns / sprRunBufferPack -> sprExpandRuns / sprExpandFromPeers), which contains this
  * GPU's shard too: while on, sprUpdateParticles[Batch] emits, integrates, compacts and sorts as always but does not write

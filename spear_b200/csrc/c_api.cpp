@@ -548,7 +548,8 @@ SPR_API int sprExpandFromPeers(SprContext *c, void *const *bufferPtrs, uint32_t 
 	REQUIRE(c && bufferPtrs && deviceVerticesOut && numRanks >= 1 && numRanks <= 16 && myRank < numRanks);
 	return guarded([&] {
 		SPR_CUDA(cudaSetDevice(c->ctx.device));
-		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, myRank, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms * c->ctx.assemblyCtasPerSm, c->ctx.assemblyCtasPerSm <= 2);
+		launch_expand_from_peers(c->ctx.stream, bufferPtrs, numRanks, myRank, (float4*)deviceVerticesOut, capacityRecords, deviceTotalRecords, c->ctx.numSms * c->ctx.assemblyCtasPerSm,
+			c->ctx.assemblyKernel ? c->ctx.assemblyKernel == 2 : c->ctx.assemblyCtasPerSm <= 2);
 		c->ctx.launchCount++;
 		SPR_CUDA(cudaGetLastError());
 	});
@@ -559,6 +560,13 @@ SPR_API int sprContextSetDeferredExpansion(SprContext *c, int on)
 	REQUIRE(c);
 	if (on && !(c->ctx.flags & SPR_CTX_SORT_PARTICLES)) { g_lastError = "deferred expansion needs SPR_CTX_SORT_PARTICLES"; return SPR_ERR_UNSUPPORTED; }
 	c->ctx.deferExpansion = on != 0;
+	return SPR_OK;
+}
+
+SPR_API int sprContextSetAssemblyKernel(SprContext *c, uint32_t kernel)
+{
+	REQUIRE(c && kernel <= 2);
+	c->ctx.assemblyKernel = kernel;
 	return SPR_OK;
 }
 

@@ -181,6 +181,7 @@ struct Context {
 	bool ownStream = false;
 	uint32_t numSms = 148;
 	bool deferExpansion = false;               // sprContextSetDeferredExpansion (sort mode): updates sort but do not write the local vertex stream
+	uint32_t assemblyKernel = 0;               // sprContextSetAssemblyKernel: 0 = by share, 1 = load/store kernel, 2 = bulk-asynchronous pipeline
 	uint32_t assemblyCtasPerSm = 8;            // sprContextSetAssemblyShare: resident CTAs per SM of sprExpandFromPeers
 	uint64_t launchCount = 0;
 	uint64_t totalSimSteps = 0;            // simulateParticlesImp calls issued so far (all effects)

@@ -29,7 +29,7 @@ EXPORTS = [
     "sprGetEffectTypeUbo", "sprGetEffectDeviceView", "sprPackRuns", "sprExpandRuns",
     "sprContextEnableKernelTiming", "sprContextGetKernelTimes", "sprBakeEffectType", "sprRenderMainBatch", "sprContextGetTotals",
     "sprRunBufferCreate", "sprRunBufferDestroy", "sprRunBufferGetIpcHandle", "sprRunBufferOpenPeer", "sprRunBufferClosePeer",
-    "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers", "sprContextSetAssemblyShare", "sprContextSetDeferredExpansion", "sprShadeVertices",
+    "sprRunBufferDevicePtr", "sprRunBufferPack", "sprExpandFromPeers", "sprContextSetAssemblyShare", "sprContextSetAssemblyKernel", "sprContextSetDeferredExpansion", "sprShadeVertices",
     "sprBillboardSystemCreate", "sprBillboardSystemDestroy", "sprBillboardAdd", "sprBillboardRenderMain",
     "sprBillboardReadVertices", "sprBillboardPack", "sprBillboardAddPacked",
     "sprDescriptorsFromJson", "sprDescriptorCount", "sprDescriptorGet", "sprDescriptorTextureName", "sprDescriptorsFree",
@@ -88,6 +88,7 @@ def _load():
     lib.sprRunBufferPack.argtypes = [vp, P(vp), P(u32), u32, vp]
     lib.sprExpandFromPeers.argtypes = [vp, P(vp), u32, u32, vp, u64, vp]
     lib.sprContextSetAssemblyShare.argtypes = [vp, u32]
+    lib.sprContextSetAssemblyKernel.argtypes = [vp, u32]
     lib.sprContextSetDeferredExpansion.argtypes = [vp, C.c_int]
     lib.sprShadeVertices.argtypes = [vp, P(abi.DrawRecord), u32, P(abi.FogImage), vp, u64, P(u64)]
     lib.sprBillboardSystemCreate.argtypes = [vp, u32, P(vp)]
@@ -278,6 +279,10 @@ class ParticleContext:
     def set_assembly_share(self, ctas_per_sm):
         """Resident CTAs per SM of expand_from_peers (0 = the whole GPU)."""
         _check(lib.sprContextSetAssemblyShare(self.h, ctas_per_sm))
+
+    def set_assembly_kernel(self, kernel):
+        """0 = by share, 1 = load/store kernel, 2 = bulk-asynchronous pipeline (expand_from_peers)."""
+        _check(lib.sprContextSetAssemblyKernel(self.h, kernel))
 
     def set_deferred_expansion(self, on):
         """Sort mode: updates stop writing the local vertex stream, the pack calls gather the sorted records from the slot state."""

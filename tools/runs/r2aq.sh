@@ -11,6 +11,6 @@ d=json.load(open('$O/r2aq_n$N.json'))
 print('value', d['value']/1e9, 'ms', d['ms_per_step'], 'compute_only', d['compute_only']['ms_per_step'])
 g=d['gather']
 for k in ("nccl","fused","fused_overlapped","fused_deferred"):
-    print(k, g.get(k, {}).get("ms_per_step_by_assembly_share"), g.get(k, {}).get("ms_per_step"), (g.get(k, {}).get("value_with_gather") or 0)/1e9, g.get(k, {}).get("matches_nccl_path_bit_for_bit"))
+    print(k, g.get(k, {}).get("assembly_kernel"), g.get(k, {}).get("ms_per_step_by_assembly_share"), g.get(k, {}).get("ms_per_step"), (g.get(k, {}).get("value_with_gather") or 0)/1e9, g.get(k, {}).get("matches_nccl_path_bit_for_bit"))
 print(d['config'].get('assembly'))
 P
