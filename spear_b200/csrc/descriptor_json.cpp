@@ -30,6 +30,7 @@ struct JValue {
 	int64_t i = 0;
 	double d = 0.0;
 	std::string s;
+	bool multiline = false;                                 // String whose first character is a raw line break (jsi_flag_multiline)
 	std::vector<JValue> items;                              // Array
 	std::vector<std::pair<std::string, JValue>> props;      // Object, in file order
 	const JValue *get(const char *key) const {
@@ -68,7 +69,9 @@ struct Parser {
 		else { s += (char)(0xf0 | (c >> 18)); s += (char)(0x80 | ((c >> 12) & 0x3f)); s += (char)(0x80 | ((c >> 6) & 0x3f)); s += (char)(0x80 | (c & 0x3f)); }
 	}
 
-	bool parseString(std::string &out) { // p is after the opening quote
+	// multiline (may be null): set when a RAW line break is the first thing in the string, alone or behind one raw carriage
+	// return -- the reader's jsi_flag_multiline (src/ext/json_input.cpp.h:689-693); an escaped \n does not count
+	bool parseString(std::string &out, bool *multiline = nullptr) { // p is after the opening quote
 		while (p < end) {
 			char c = *p++;
 			if (c == '"') return true;
@@ -92,6 +95,7 @@ struct Parser {
 				default: return fail("bad escape");
 				}
 			} else {
+				if (c == '\n' && multiline && (out.empty() || out == "\r")) *multiline = true;
 				out += c; // control characters are allowed inside strings (allow_control_in_string)
 			}
 		}
@@ -138,7 +142,7 @@ struct Parser {
 		} else if (c == '"') {
 			p++;
 			v.kind = JValue::String;
-			ok = parseString(v.s);
+			ok = parseString(v.s, &v.multiline);
 		} else if (c == '-' || (c >= '0' && c <= '9')) {
 			const char *q = p;
 			if (*q == '-') q++;
@@ -228,12 +232,46 @@ static uint64_t fnv1a64(const std::string &s)
 	return h;
 }
 
+// What sp::readJson stores for a string value flagged multiline (src/sp/Json.cpp:134-166): the line break that opens the
+// string is dropped, the indentation of the first line (its count of spaces and its count of tabs) is the indentation that
+// is taken off every following line -- as long as either count is unmet, blanks of both kinds are eaten --, lines are
+// joined with '\n', and a last line that holds nothing but indentation (the one in front of the closing quote) is dropped.
+static std::string dedentMultiline(const std::string &s)
+{
+	const char *p = s.c_str(); // NUL-terminated: an embedded NUL ends the value, as it does in the reference's C string
+	if (*p == '\r') p++;
+	if (*p == '\n') p++;
+	uint32_t wantSpaces = 0, wantTabs = 0;
+	for (;; p++) {
+		if (*p == ' ') wantSpaces++;
+		else if (*p == '\t') wantTabs++;
+		else break;
+	}
+	std::string out;
+	auto copyLine = [&] { while (*p != '\r' && *p != '\n' && *p != '\0') out += *p++; };
+	copyLine();
+	while (*p != '\0') {
+		if (*p == '\r') p++;
+		if (*p == '\n') p++;
+		uint32_t spaces = 0, tabs = 0;
+		for (; spaces < wantSpaces || tabs < wantTabs; p++) {
+			if (*p == ' ') spaces++;
+			else if (*p == '\t') tabs++;
+			else break;
+		}
+		if (*p == '\0') break;
+		out += '\n';
+		copyLine();
+	}
+	return out;
+}
+
 static bool readComponent(Reader &R, const JValue &o, DescriptorSet::Item &it)
 {
 	SprParticleSystemComponent &c = it.comp;
 	sprComponentDefaults(&c); // the C++ defaults of ServerState.h:187-239: absent fields keep them
 	if (const JValue *t = o.get("texture")) {
-		if (t->kind == JValue::String) it.texture = t->s;
+		if (t->kind == JValue::String) it.texture = t->multiline ? dedentMultiline(t->s) : t->s;
 		else if (t->kind != JValue::Null) return R.fail("field 'texture' expects a string");
 	}
 	c.texture = it.texture.empty() ? 0 : fnv1a64(it.texture);

@@ -39,6 +39,12 @@ HAND_WRITTEN = {
   ],
 }
 """,
+    # a string value that opens with a raw line break is a multi-line string: sp::readJson takes the first line's indentation
+    # off every line (Json.cpp:134-166); an escaped \\n or a line break further in does not make one
+    "multiline_texture": '{ "type": "ParticleSystem", "texture": "\n      Assets/fx/\n        smoke sheet.png\n\n      tail\n    ", "size": 3 }',
+    "multiline_texture_crlf_tabs": '{ "texture": "\r\n\t\t  first\r\n\t\t  second\r\n\t third\r\n\t\t\t\t  fourth\r\n", "lifeTime": 2 }',
+    "not_multiline_texture": '{ "texture": "Assets/fx/a\n   b.png", "burstAmount": 3 }',
+    "escaped_newline_texture": '{ "texture": "\\n   Assets/fx/c.png" }',
     "tagged_component": '{ "type": "ParticleSystem", "size": 2.5, "sizeVariance": 1, "alphaSpline": { "points": [] } }',
     "no_particle_components": '{ "name": "x", "components": [ { "type": "Door" } ] }',
     "fail_wrong_type_number": '{ "timeStep": "fast" }',
