@@ -685,7 +685,8 @@ def run_ours(args, rank, world):
                                      "nvlink_roofline_frac": nv / (oms / args.steps * 1e-3) / 1e9 / 770.0,
                                      "assembly_ctas_per_sm": gather["overlapped_share"], "ms_per_step_by_assembly_share": gather["overlapped_by_share"],
                                      "note": "the fused assembly of frame k runs on a second stream while frame k+1 is simulated (double-buffered run buffers); "
-                                             "the assembly kernel keeps a fixed share of every SM (sprContextSetAssemblyShare), the best share of --assembly-shares is reported"},
+                                             "the assembly kernel keeps a fixed share of every SM (sprContextSetAssemblyShare), the best share of --assembly-shares is reported; "
+                                             "at shares of 1 and 2 CTAs per SM it is the bulk-asynchronous pipeline (cp.async.bulk loads + tensor stores), above that the load/store kernel"},
                 "fused_deferred": {"value_with_gather": d_total_ps / (dms * 1e-3), "ms_per_step": dms / args.steps,
                                    "assembly_ctas_per_sm": gather["deferred_share"], "assembly_kernel": gather["deferred_kernel"],
                                    "ms_per_step_by_assembly_share": gather["deferred_by_share"],
