@@ -195,3 +195,71 @@ def test_restatement_matches_executed_shader_on_random_input(type_id):
     fog = rng.integers(0, 256, size=(24, 32, 2), dtype=np.uint8)
     for fg in (None, fog):
         _assert_matches_shader(VS.shade(p, inst, typ, lut, fog=fg), G.shade(p, inst, typ, atlas, fg), "type %d fog %s" % (type_id, fg is not None))
+
+
+def _reference_available():
+    from oracle import orc
+    return orc.have("reference") and G.have()
+
+
+@pytest.mark.skipif(not _reference_available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_a_reference_frame_through_the_reference_shader():
+    """Everything from the reference at once, on the CPU: its ParticleSystem.cpp simulates and renders a few frames (headless
+    harness), the atlas is the one ITS sg_make_image / sg_bqq_copy_subimages calls filled, the uniform blocks are the ones it
+    handed to sg_apply_uniforms, the vertex stream is its own -- and its shipped GLSL runs over that. The restatement, fed
+    the type's two LUT rows instead of the atlas, must give the same vertices; the atlas must hold every type's rows in the
+    cell oracle/glsl_vs.atlas_from_luts assumes (ParticleSystem.cpp:323-324, :403-404)."""
+    import scenarios as S
+    from oracle import orc
+    from spear_b200 import abi
+    from tests_render_args import make_render_args
+    camera = (16.0, 20.0, -30.0)
+    comps = [
+        abi.make_component(
+            timeStep=1 / 60, burstAmount=600, spawnTime=0.002, spawnTimeVariance=0.001, lifeTime=0.8, lifeTimeVariance=0.5,
+            drag=0.3, gravity=(0, -9.81, 0), size=0.6, sizeVariance=0.4, rotation=30.0, rotationVariance=180.0, spin=90.0, spinVariance=45.0,
+            frameRate=12.0, randomStartFrame=1, emitPosition=dict(boxExtent=(1, 0.5, 1)), emitVelocity=dict(sphere=dict(minRadius=1, maxRadius=3)),
+            scaleSpline=[(0, 0), (0.3, 1), (1, 0.2)], alphaSpline=[(0, 1), (1, 0)], additiveSpline=[(0, 0.3), (1, 0.9)],
+            erosionSpline=[(0, 1), (0.5, 0.4), (1, 0.1)], gradient=dict(points=[(0, (1, 0.5, 0.1)), (0.5, (0.9, 0.1, 0.4)), (1, (0.1, 0.1, 0.1))])),
+        abi.make_component(
+            timeStep=1 / 50, burstAmount=300, spawnTime=0.01, lifeTime=1.5, lifeTimeVariance=1.0, localSpace=1, size=1.5, relativeFrameRate=1,
+            frameRate=8.0, spin=-200.0, emitVelocity=dict(boxExtent=(2, 4, 2)), gradient=dict(defaultColor=(0.2, 0.7, 1.0))),
+        S.comp_fountain(),
+    ]
+    comps[0].frameCount[0], comps[0].frameCount[1] = 4, 2
+    comps[1].frameCount[0], comps[1].frameCount[1] = 3, 3
+    trs = [abi.make_transform((2, 1, 3), (0, 0.38268343, 0, 0.92387953), 1.5), abi.make_transform((14, 0, 12)), abi.make_transform((20, 2, 18), (0, 0, 0, 1), 0.5)]
+    o = orc.OracleSystem("reference", (1, 7, 3, 4))
+    try:
+        ids = [o.add_effect(c, t) for c, t in zip(comps, trs)]
+        ra = make_render_args(camera)
+        for k in range(4):      # everything is in view
+            for pl in range(4):
+                ra.frustum.side[k][pl] = 1.0 if k == 3 else 0.0
+                ra.frustum.caps[k][pl] = 1.0 if k == 3 else 0.0
+        checked = dead_quads = 0
+        for f in range(72):
+            o.update(ids, abi.make_frame_args(0.011 + 0.002 * (f % 5), f * 0.017, f, camera=camera))
+            if f < 28 or f % 4:
+                continue
+            recs, _ = o.render(ids, ra, capacity=8)
+            assert len(recs) == 3
+            atlas = o.read_atlas()
+            assert atlas is not None
+            luts = {r.typeId: o.type_lut(r.typeId) for r in recs}
+            mine = G.atlas_from_luts(luts)
+            for a in (atlas, mine):
+                a[1::2, :, 3] = 0      # gradient rows: the alpha byte is uninitialised stack in the reference (:326, :366-400), the shader reads .xyz
+            assert np.array_equal(atlas, mine), "the reference's atlas does not hold the types' rows where atlas_from_luts puts them"
+            for r in recs:
+                stream = o.read_stream(r.effectId)
+                assert len(stream) == 4 * r.numParticles and r.numParticles > 0
+                inst = np.frombuffer(bytes(r.instanceUbo), dtype=F)[:40]
+                typ = np.frombuffer(bytes(o.type_ubo(r.typeId)), dtype=F)[:24]
+                ref = G.shade(stream[::4], inst, typ, atlas, None)
+                _assert_matches_shader(VS.shade(stream[::4], inst, typ, luts[r.typeId], fog=None), ref, "frame %d effect %d" % (f, r.effectId))
+                dead_quads += int(np.all(ref[:, 0:4] == 0.0, axis=1).sum()) // 4
+                checked += 1
+        assert checked == 33 and dead_quads > 0, (checked, dead_quads)   # particles in their last step collapse (Particle.glsl:113-115)
+    finally:
+        o.close()
